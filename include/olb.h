@@ -1,0 +1,275 @@
+/*
+ * olb.h -- C ABI of libolb: the B200-native batched real-ray trace hot path.
+ *
+ * This is the drop-in boundary for ONE path of Optiland (reference under
+ * /root/reference, v0.6.0): the per-surface loop
+ *     SurfaceGroup.trace            optiland/surfaces/surface_group.py:245-257
+ *       Surface.trace               optiland/surfaces/standard_surface.py:200-215
+ *         Surface._trace_real       optiland/surfaces/standard_surface.py:232-248
+ *         Surface._record_real      optiland/surfaces/standard_surface.py:260-274
+ * The reference is pure Python and has no FFI below `optiland.backend`
+ * (optiland/backend/__init__.py:100-190), so there is no existing C interface
+ * to mirror; each entry point below names the reference function(s) whose work
+ * it replaces.  The reference-side binding (ctypes) is shown in INTEGRATION.md.
+ *
+ * Rules of the ABI
+ *   - plain pointers and sizes only; no torch / C++ types;
+ *   - the CALLER owns every buffer (ray state, records, tables, workspace);
+ *     the library allocates nothing that outlives a call except handles
+ *     explicitly created/destroyed by the caller (olb_host_ctx_*);
+ *   - every function returns OLB_OK (0) or a negative error code, and never
+ *     throws; olb_last_error() returns a thread-local message;
+ *   - numerical failure is IN-BAND, as in the reference: a missed surface or
+ *     total internal reflection yields NaN coordinates that propagate
+ *     (optiland/geometries/standard.py:132-135, optiland/rays/real_rays.py:179-180),
+ *     vignetting sets intensity to 0 and the ray keeps propagating
+ *     (optiland/rays/real_rays.py:154-161);
+ *   - device pointers must be 16-byte aligned; `stream` is a cudaStream_t
+ *     passed as void* (NULL = legacy default stream);
+ *   - re-entrant per (stream, buffers); no global mutable state.
+ */
+#ifndef OLB_H_
+#define OLB_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OLB_VERSION_MAJOR 0
+#define OLB_VERSION_MINOR 1
+
+/* ---- error codes ------------------------------------------------------- */
+#define OLB_OK                 0
+#define OLB_ERR_INVALID_ARG   -1   /* NULL pointer, bad range, bad enum        */
+#define OLB_ERR_UNSUPPORTED   -2   /* surface kind / feature not built         */
+#define OLB_ERR_CUDA          -3   /* a CUDA runtime call failed               */
+#define OLB_ERR_ALIGNMENT     -4   /* device pointer not 16-byte aligned       */
+#define OLB_ERR_TABLE         -5   /* malformed surface table / pool offsets   */
+
+/* ---- surface geometry kinds (OlbSurface.kind) --------------------------- */
+#define OLB_GEOM_NOOP          0   /* ObjectSurface: no physics, still records
+                                      (optiland/surfaces/object_surface.py:56-93) */
+#define OLB_GEOM_PLANE         1   /* optiland/geometries/plane.py:72-109        */
+#define OLB_GEOM_STANDARD      2   /* sphere/conic closed form
+                                      optiland/geometries/standard.py:97-175     */
+#define OLB_GEOM_EVEN_ASPHERE  3   /* Newton iteration on conic + sum C_i r^(2i+2)
+                                      optiland/geometries/newton_raphson.py:119-168,
+                                      optiland/geometries/even_asphere.py:93-140 */
+#define OLB_GEOM_ZERNIKE       4   /* Newton iteration on conic + Zernike sum
+                                      optiland/geometries/zernike.py:153-252     */
+#define OLB_GEOM_ODD_ASPHERE   5   /* conic + sum C_i r^(i+1)
+                                      optiland/geometries/odd_asphere.py         */
+#define OLB_GEOM_POLYNOMIAL    6   /* conic + sum C_ij x^i y^j
+                                      optiland/geometries/polynomial.py:105-155  */
+
+/* ---- OlbSurface.flags --------------------------------------------------- */
+#define OLB_SF_REFLECT     (1u << 0)  /* is_reflective: rays.reflect instead of refract
+                                         optiland/interactions/refractive_reflective_model.py:45-50 */
+#define OLB_SF_ROTATED     (1u << 1)  /* R != identity (cs has tilts or tilted parents)      */
+#define OLB_SF_APERTURE    (1u << 2)  /* surface.aperture is set (aper_off/aper_len valid)   */
+#define OLB_SF_ABSORBING   (1u << 3)  /* some k1(lambda) > 0: Beer-Lambert attenuation
+                                         optiland/propagation/homogeneous.py:45-53            */
+#define OLB_SF_NORECORD    (1u << 4)  /* do not write this surface's record row              */
+
+/* ---- coatings (OlbSurface.coating) -------------------------------------- */
+#define OLB_COAT_NONE      0   /* rays.update() : identity for RealRays, basis change
+                                  for PolarizedRays (optiland/interactions/base.py:111-128) */
+#define OLB_COAT_SIMPLE    1   /* SimpleCoating: i *= T or R (optiland/coatings.py:164-237) */
+#define OLB_COAT_FRESNEL   2   /* FresnelCoating (optiland/coatings.py:362-386,
+                                  optiland/jones.py:71-117); needs polarized rays       */
+
+/* ---- aperture programs --------------------------------------------------
+ * surface.aperture (optiland/physical_apertures/*.py) is flattened by the host
+ * into a postfix program over the pool: each instruction is one opcode double
+ * followed by its operands.  The evaluator keeps a small boolean stack; the
+ * final value is `inside`; rays with inside == false get i := 0
+ * (optiland/physical_apertures/base.py:71-82).  NaN coordinates compare false,
+ * so NaN rays are clipped, as in the reference.
+ */
+#define OLB_AP_RADIAL      1   /* r_max, r_min : r_min^2 <= x^2+y^2 <= r_max^2
+                                  (radial.py:56-70)                                   */
+#define OLB_AP_OFFSET_RADIAL 2 /* r_max, r_min, dx, dy   (offset_radial.py)           */
+#define OLB_AP_RECT        3   /* x_min, x_max, y_min, y_max (rectangular.py)         */
+#define OLB_AP_ELLIPSE     4   /* a, b, dx, dy           (elliptical.py)              */
+#define OLB_AP_UNION       16  /* pops 2, pushes a | b   (base.py:259-340)            */
+#define OLB_AP_INTERSECT   17  /* pops 2, pushes a & b                                */
+#define OLB_AP_DIFFERENCE  18  /* pops 2, pushes a & ~b                               */
+
+/* ---- trace flags (argument `flags` of olb_trace_*) ------------------------ */
+#define OLB_TF_POLARIZED   (1u << 0)  /* rays carry a 3x3 complex P matrix (OlbRays.p)  */
+
+#define OLB_MAX_SURFACES   64
+#define OLB_MAX_WAVELENGTHS 16
+
+/*
+ * One optical surface, as the hot path sees it (data contract: SURVEY.md
+ * Appendix B).  All real numbers are fp64 on the host side; the fp32 kernel
+ * derives its own fp32 working copy on the device.  `pool` offsets are in
+ * units of doubles into the table's pool array.
+ *
+ * Pose: (t, R) is the flattened effective transform of geometry.cs including
+ * every parent reference_cs (optiland/coordinate_system.py:145-165):
+ *     local  = R^T (global - t)      [CoordinateSystem.localize, :73-89]
+ *     global = R local + t           [CoordinateSystem.globalize, :91-107]
+ *
+ * Media: for wavelength index j (0 <= j < n_wl of the table)
+ *     pool[media_off + 0*n_wl + j] = n1  material_pre.n(lambda_j)
+ *     pool[media_off + 1*n_wl + j] = n2  material_post.n(lambda_j)
+ *     pool[media_off + 2*n_wl + j] = k1  material_pre.k(lambda_j)
+ *     pool[media_off + 3*n_wl + j] = coating n1 (FresnelCoating.material_pre)
+ *     pool[media_off + 4*n_wl + j] = coating n2 (FresnelCoating.material_post)
+ * evaluated on the host by the reference's own material classes
+ * (optiland/materials/base.py:98-149).
+ */
+typedef struct OlbSurface {
+  int32_t kind;        /* OLB_GEOM_*                                          */
+  uint32_t flags;      /* OLB_SF_*                                            */
+  int32_t n_coef;      /* number of geometry coefficients / Zernike terms     */
+  int32_t coef_off;    /* pool offset of the coefficient block (see below)    */
+  int32_t aper_off;    /* pool offset of the aperture program                 */
+  int32_t aper_len;    /* its length in doubles                               */
+  int32_t max_iter;    /* Newton max_iter (newton_raphson.py:58-61)           */
+  int32_t coating;     /* OLB_COAT_*                                          */
+  int32_t media_off;   /* pool offset of the 5 x n_wl media block             */
+  int32_t aux0;        /* polynomial: number of columns (y powers)            */
+  int32_t reserved[2];
+  double t[3];         /* effective translation                               */
+  double R[9];         /* effective rotation, row-major                       */
+  double radius;       /* geometry.radius (inf => plane branch of Standard)   */
+  double conic;        /* geometry.k                                          */
+  double tol;          /* Newton tol                                          */
+  double coat_t;       /* SimpleCoating.transmittance                         */
+  double coat_r;       /* SimpleCoating.reflectance                           */
+  double norm_radius;  /* Zernike norm_radius / polynomial norm               */
+} OlbSurface;          /* 192 bytes, multiple of 16                           */
+
+/*
+ * Coefficient blocks in the pool
+ *   EVEN_ASPHERE : n_coef doubles C_0.. ; term i is C_i * r^(2(i+1))
+ *   ODD_ASPHERE  : n_coef doubles C_0.. ; term i is C_i * r^(i+1)
+ *   POLYNOMIAL   : n_coef = rows*cols doubles, C[i*cols+j] * x^i y^j
+ *   ZERNIKE      : n_coef terms, each 4 doubles {n, m, c*N_nm (sag), c (derivative)}
+ *                  -- the reference's derivative path omits the normalisation
+ *                  constant N_nm (optiland/zernike/base.py:104-136 vs :42-68);
+ *                  this quirk is reproduced, not fixed.
+ */
+
+/* The whole table: surfaces + pool + wavelength list. Host or device memory
+ * (host for olb_trace_*: the library stages it; it is < 64 KiB). */
+typedef struct OlbTable {
+  const OlbSurface* surfaces;  /* n_surfaces entries                           */
+  int32_t n_surfaces;
+  int32_t n_wl;                /* number of distinct wavelengths, >= 1         */
+  const double* wavelengths;   /* n_wl values (micrometres), exact ray.w values */
+  const double* pool;          /* pool_len doubles                             */
+  int32_t pool_len;
+  int32_t reserved;
+} OlbTable;
+
+/*
+ * Ray state, structure of arrays (RealRays: optiland/rays/real_rays.py:23-89).
+ * All pointers are DEVICE pointers to n_rays elements of the kernel's element
+ * type (float for *_f32, double for *_f64).  The trace updates x..opd in place
+ * (the reference assigns new arrays to the same attributes).
+ *   w       wavelength per ray; may be NULL when the table has n_wl == 1
+ *   L0..N0  optional outputs: direction before the last interaction, in the
+ *           last surface's local frame (real_rays.py:170-172); NULL to skip
+ *   p       optional 3x3 complex polarization matrix per ray
+ *           (optiland/rays/polarized_rays.py:50), layout [18][n_rays]:
+ *           plane 2*(3*r+c) = Re P[r][c], plane 2*(3*r+c)+1 = Im P[r][c]
+ */
+typedef struct OlbRays {
+  void* x; void* y; void* z;
+  void* L; void* M; void* N;
+  void* i; void* w; void* opd;
+  void* L0; void* M0; void* N0;
+  void* p;
+} OlbRays;
+
+/*
+ * Per-surface records (Surface._record_real, standard_surface.py:260-274; the
+ * stacked views SurfaceGroup.x .. .intensity, surface_group.py:108-153).
+ * Each pointer is a DEVICE pointer to a row-major (n_rows, row_stride) array;
+ * row r receives the state after surface (first + r), in GLOBAL coordinates.
+ * Any pointer may be NULL (that quantity is not recorded); rec itself may be
+ * NULL (endpoint-only trace).
+ */
+typedef struct OlbRecords {
+  void* x; void* y; void* z;
+  void* L; void* M; void* N;
+  void* intensity; void* opd;
+  int64_t row_stride;   /* elements between consecutive rows (>= n_rays)      */
+} OlbRecords;
+
+/* Status word written by the kernels (device int32, caller-owned, optional). */
+#define OLB_ST_ZERNIKE_RANGE (1 << 0)  /* some |x/norm_radius| or |y/norm_radius| > 1:
+                                          the reference raises ValueError
+                                          (optiland/geometries/zernike.py:254-266) */
+
+int olb_version(void);
+/* Copies the calling thread's last error message into buf (NUL terminated). */
+int olb_last_error(char* buf, int buf_len);
+
+/*
+ * Bytes of device workspace olb_trace_* needs for `table` (the staged,
+ * type-converted surface table).  The caller allocates it once and may reuse
+ * it for every call with a table of the same or smaller size.
+ */
+int64_t olb_table_workspace_bytes(const OlbTable* table);
+
+/*
+ * Stage `table` (HOST memory) into `workspace` (DEVICE memory,
+ * >= olb_table_workspace_bytes) on `stream`.  Replaces the per-call Python walk
+ * over live surface objects; call again whenever a surface parameter changes.
+ */
+int olb_table_upload(const OlbTable* table, void* workspace, int64_t workspace_bytes,
+                     void* stream);
+
+/*
+ * Trace n_rays rays through surfaces [first, last) of the staged table.
+ * Replaces SurfaceGroup.trace(rays, skip=first) (surface_group.py:245-257) --
+ * and, with last = first + 1, a single Surface.trace as issued by the ray
+ * aimers (optiland/rays/ray_aiming/iterative.py:366).
+ *   workspace : device table written by olb_table_upload
+ *   rays      : device SoA (updated in place)
+ *   rec       : optional record rows, row r <-> surface first + r
+ *   status    : optional device int32, OR-ed with OLB_ST_* bits
+ * Asynchronous on `stream`.
+ */
+int olb_trace_f32(const void* workspace, int32_t first, int32_t last,
+                  const OlbRays* rays, const OlbRecords* rec, int64_t n_rays,
+                  uint32_t flags, int32_t* status, void* stream);
+int olb_trace_f64(const void* workspace, int32_t first, int32_t last,
+                  const OlbRays* rays, const OlbRecords* rec, int64_t n_rays,
+                  uint32_t flags, int32_t* status, void* stream);
+
+/*
+ * Host-buffer end-to-end trace: HOST SoA in, HOST final ray state out, the
+ * per-surface records stay on the device (rec, optional).  Rays are cut into
+ * chunks; H2D copy, kernel and D2H copy of consecutive chunks overlap on three
+ * streams.  `h_in` supplies x,y,z,L,M,N,i,w (opd ignored, starts at 0);
+ * `h_out` receives x,y,z,L,M,N,i,opd.  Host buffers should be pinned.
+ *   dev_scratch : device memory, >= olb_host_scratch_bytes(elem_size, chunk)
+ */
+int64_t olb_host_scratch_bytes(int32_t elem_size, int64_t chunk_rays);
+int olb_trace_host_f32(const void* workspace, int32_t first, int32_t last,
+                       const OlbRays* h_in, const OlbRays* h_out,
+                       const OlbRecords* rec, int64_t n_rays, int64_t chunk_rays,
+                       void* dev_scratch, int64_t dev_scratch_bytes, uint32_t flags,
+                       int32_t* status);
+int olb_trace_host_f64(const void* workspace, int32_t first, int32_t last,
+                       const OlbRays* h_in, const OlbRays* h_out,
+                       const OlbRecords* rec, int64_t n_rays, int64_t chunk_rays,
+                       void* dev_scratch, int64_t dev_scratch_bytes, uint32_t flags,
+                       int32_t* status);
+
+/* Number of kernel launches issued by this process through the library
+ * (for bench.py's gpu_launches claim). */
+int64_t olb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OLB_H_ */

@@ -1,0 +1,202 @@
+"""Flatten a live Optiland ``SurfaceGroup`` into a ``SurfaceTable``.
+
+This is the only module that looks at Optiland objects; it imports nothing from
+Optiland itself (it dispatches on class *names*), so it is importable on a box
+without the reference.  What it reads per surface is exactly what the reference's
+hot path reads:
+
+* pose           ``geometry.cs.get_effective_transform()``  optiland/coordinate_system.py:145-165
+* geometry       ``type(geometry)``, ``radius``, ``k``, ``coefficients``, ``tol``, ``max_iter``
+                 optiland/geometries/{plane,standard,newton_raphson,even_asphere,odd_asphere,
+                 polynomial,zernike}.py
+* media          ``material_pre.n/k(lambda)``, ``material_post.n(lambda)``  optiland/materials/base.py:98-149
+* interaction    ``interaction_model.is_reflective``, ``coating``, ``bsdf``  optiland/interactions/base.py:26-128
+* aperture       ``surface.aperture`` tree  optiland/physical_apertures/*.py
+
+Anything outside the supported set raises ``UnsupportedSurface`` so the caller
+(``optiland_b200.plugin``) can fall back to the reference's Python loop.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from . import table as T
+
+
+class UnsupportedSurface(Exception):
+    """The surface (or one of its parts) is outside the CUDA path's scope."""
+
+
+def _f(v) -> float:
+    """Scalar backend value (numpy scalar / 0-d tensor / float) -> python float."""
+    if hasattr(v, "detach"):
+        v = v.detach().cpu().numpy()
+    return float(np.asarray(v, dtype=np.float64).reshape(-1)[0]) if np.ndim(v) else float(v)
+
+
+def _arr(v) -> np.ndarray:
+    if hasattr(v, "detach"):
+        v = v.detach().cpu().numpy()
+    return np.asarray(v, dtype=np.float64)
+
+
+def _cls(obj) -> str:
+    return type(obj).__name__
+
+
+def pack_aperture(ap) -> np.ndarray:
+    """Postfix program for an aperture tree (see include/olb.h)."""
+    name = _cls(ap)
+    if name == "RadialAperture":
+        return T.aperture_radial(_f(ap.r_max), _f(ap.r_min))
+    if name == "OffsetRadialAperture":
+        return T.aperture_offset_radial(_f(ap.r_max), _f(ap.r_min), _f(ap.offset_x), _f(ap.offset_y))
+    if name == "RectangularAperture":
+        return T.aperture_rect(_f(ap.x_min), _f(ap.x_max), _f(ap.y_min), _f(ap.y_max))
+    if name == "EllipticalAperture":
+        return T.aperture_ellipse(_f(ap.a), _f(ap.b), _f(ap.offset_x), _f(ap.offset_y))
+    ops = {"UnionAperture": T.AP_UNION, "IntersectionAperture": T.AP_INTERSECT,
+           "DifferenceAperture": T.AP_DIFFERENCE}
+    if name in ops:
+        return T.aperture_combine(ops[name], pack_aperture(ap.a), pack_aperture(ap.b))
+    raise UnsupportedSurface(f"aperture type {name}")
+
+
+def _index_table(material, wavelengths, what: str) -> np.ndarray:
+    fn = getattr(material, what)
+    out = np.empty(len(wavelengths), dtype=np.float64)
+    for j, wl in enumerate(wavelengths):
+        v = fn(float(wl))
+        v = _arr(v)
+        if np.iscomplexobj(v):
+            raise UnsupportedSurface("complex refractive index")
+        out[j] = float(v.reshape(-1)[0])
+    return out
+
+
+_GEOM_KINDS = {
+    "Plane": T.GEOM_PLANE,
+    "StandardGeometry": T.GEOM_STANDARD,
+    "EvenAsphere": T.GEOM_EVEN_ASPHERE,
+    "OddAsphere": T.GEOM_ODD_ASPHERE,
+    "PolynomialGeometry": T.GEOM_POLYNOMIAL,
+    "ZernikePolynomialGeometry": T.GEOM_ZERNIKE,
+}
+
+
+def pack_surface(surface, wavelengths) -> T.SurfaceSpec:
+    """One Optiland ``Surface`` / ``ObjectSurface`` / ``ImageSurface`` -> ``SurfaceSpec``."""
+    sname = _cls(surface)
+    n_wl = len(wavelengths)
+    if sname == "ObjectSurface":
+        # no physics, still records (optiland/surfaces/object_surface.py:56-93)
+        return T.SurfaceSpec(kind=T.GEOM_NOOP, n1=np.ones(n_wl), n2=np.ones(n_wl), k1=np.zeros(n_wl))
+    if sname not in ("Surface", "ImageSurface"):
+        raise UnsupportedSurface(f"surface class {sname}")
+
+    g = surface.geometry
+    gname = _cls(g)
+    if gname not in _GEOM_KINDS:
+        raise UnsupportedSurface(f"geometry {gname}")
+    kind = _GEOM_KINDS[gname]
+
+    im = surface.interaction_model
+    if _cls(im) != "RefractiveReflectiveModel":
+        raise UnsupportedSurface(f"interaction model {_cls(im)}")
+    if getattr(im, "bsdf", None) is not None:
+        raise UnsupportedSurface("bsdf scatter")
+
+    t_eff, R_eff = g.cs.get_effective_transform()
+    t_eff, R_eff = _arr(t_eff), _arr(R_eff)
+    if not (np.all(np.isfinite(t_eff)) and np.all(np.isfinite(R_eff))):
+        raise UnsupportedSurface("non-finite pose")
+    # exact identity for untilted systems: cos(0)=1, sin(0)=0 already; snap -0.0
+    R_eff = R_eff + 0.0
+
+    spec = T.SurfaceSpec(kind=kind, t=t_eff, R=R_eff, reflective=bool(im.is_reflective))
+    if kind != T.GEOM_PLANE:
+        spec.radius = _f(g.radius)
+        spec.conic = _f(g.k)
+    if kind in T.NEWTON_KINDS:
+        spec.tol = float(g.tol)
+        spec.max_iter = int(g.max_iter)
+    if kind in (T.GEOM_EVEN_ASPHERE, T.GEOM_ODD_ASPHERE):
+        spec.coefficients = np.array([_f(c) for c in g.coefficients], dtype=np.float64)
+    elif kind == T.GEOM_POLYNOMIAL:
+        C = g.coefficients
+        spec.coefficients = np.atleast_2d(np.array([[_f(c) for c in row] for row in C], dtype=np.float64))
+    elif kind == T.GEOM_ZERNIKE:
+        z = g.zernike
+        coeffs = [_f(c) for c in z.coeffs]
+        terms = []
+        for (n, m), c in zip(z.indices, coeffs):
+            norm = _f(z._norm_constant(int(n), int(m)))
+            # the reference forms coeff * N_nm first (optiland/zernike/base.py:63-68)
+            terms.append((float(n), float(m), c * norm, c))
+        spec.coefficients = np.array(terms, dtype=np.float64).reshape(-1, 4)
+        spec.norm_radius = _f(g.norm_radius)
+
+    if surface.aperture is not None:
+        spec.aperture = pack_aperture(surface.aperture)
+
+    mpre, mpost = surface.material_pre, surface.material_post
+    spec.n1 = _index_table(mpre, wavelengths, "n")
+    spec.k1 = _index_table(mpre, wavelengths, "k")
+    spec.n2 = _index_table(mpost, wavelengths, "n")
+
+    coating = getattr(im, "coating", None)
+    if coating is not None:
+        cname = _cls(coating)
+        if cname == "SimpleCoating":
+            spec.coating = T.COAT_SIMPLE
+            spec.coat_t = _f(coating.transmittance)
+            spec.coat_r = _f(coating.reflectance)
+        elif cname == "FresnelCoating":
+            spec.coating = T.COAT_FRESNEL
+            spec.coat_n1 = _index_table(coating.material_pre, wavelengths, "n")
+            spec.coat_n2 = _index_table(coating.material_post, wavelengths, "n")
+        else:
+            raise UnsupportedSurface(f"coating {cname}")
+    spec.__post_init__()
+    return spec
+
+
+def pack_surface_group(surface_group, wavelengths) -> T.SurfaceTable:
+    """Whole ``SurfaceGroup`` -> ``SurfaceTable`` tabulated at ``wavelengths`` (micrometres)."""
+    wavelengths = np.atleast_1d(np.asarray(wavelengths, dtype=np.float64))
+    if len(wavelengths) > T.MAX_WAVELENGTHS:
+        raise UnsupportedSurface(f"more than {T.MAX_WAVELENGTHS} distinct wavelengths")
+    surfaces = list(surface_group.surfaces)
+    if len(surfaces) > T.MAX_SURFACES:
+        raise UnsupportedSurface(f"more than {T.MAX_SURFACES} surfaces")
+    return T.SurfaceTable([pack_surface(s, wavelengths) for s in surfaces], wavelengths)
+
+
+def launch_scalars(optic, Hx: float, Hy: float) -> dict:
+    """Scalars from which the launch state of an infinite-object angle field is a closed
+    form of (Px, Py): optiland/fields/field_types/angle.py:17-58 and
+    optiland/rays/ray_aiming/paraxial.py:33-106.  Used to regenerate identical launch rays
+    on a box without the reference (bench / tests)."""
+    import optiland.backend as be  # only called where the reference is importable
+
+    fd = optic.fields.field_definition
+    if _cls(fd) != "AngleField" or not bool(optic.object_surface.is_infinite):
+        raise UnsupportedSurface("launch_scalars: only infinite-object angle fields")
+    vxf, vyf = optic.fields.get_vig_factor(Hx, Hy)
+    return {
+        "EPL": _f(optic.paraxial.EPL()),
+        "EPD": _f(optic.paraxial.EPD()),
+        "offset": _f(fd._get_starting_z_offset(optic)),
+        "max_field": _f(optic.fields.max_field),
+        "z1": _f(be.to_numpy(optic.surfaces.positions)[1]),
+        "vx": 1.0 - _f(vxf),
+        "vy": 1.0 - _f(vyf),
+        "Hx": float(Hx),
+        "Hy": float(Hy),
+    }
+
+
+def _isinf(v) -> bool:
+    return math.isinf(_f(v))
