@@ -15,8 +15,7 @@
  * Rules of the ABI
  *   - plain pointers and sizes only; no torch / C++ types;
  *   - the CALLER owns every buffer (ray state, records, tables, workspace);
- *     the library allocates nothing that outlives a call except handles
- *     explicitly created/destroyed by the caller (olb_host_ctx_*);
+ *     the library allocates nothing that outlives a call;
  *   - every function returns OLB_OK (0) or a negative error code, and never
  *     throws; olb_last_error() returns a thread-local message;
  *   - numerical failure is IN-BAND, as in the reference: a missed surface or
@@ -26,7 +25,8 @@
  *     (optiland/rays/real_rays.py:154-161);
  *   - device pointers must be 16-byte aligned; `stream` is a cudaStream_t
  *     passed as void* (NULL = legacy default stream);
- *   - re-entrant per (stream, buffers); no global mutable state.
+ *   - re-entrant per (stream, buffers); no global mutable state except the
+ *     launch counter and the thread-local error string.
  */
 #ifndef OLB_H_
 #define OLB_H_
@@ -99,6 +99,9 @@ extern "C" {
 
 /* ---- trace flags (argument `flags` of olb_trace_*) ------------------------ */
 #define OLB_TF_POLARIZED   (1u << 0)  /* rays carry a 3x3 complex P matrix (OlbRays.p)  */
+#define OLB_TF_NO_FINAL    (1u << 1)  /* do not write the final state back into rays.x..opd:
+                                         the caller takes it from the last record row (saves
+                                         32-64 B/ray of HBM writes; needs rec)              */
 
 #define OLB_MAX_SURFACES   64
 #define OLB_MAX_WAVELENGTHS 16
@@ -213,35 +216,48 @@ int olb_version(void);
 int olb_last_error(char* buf, int buf_len);
 
 /*
- * Bytes of device workspace olb_trace_* needs for `table` (the staged,
- * type-converted surface table).  The caller allocates it once and may reuse
- * it for every call with a table of the same or smaller size.
+ * Device-resident ("prepared") table handle.  Filled by olb_table_upload; a plain
+ * caller-owned struct (the library keeps no registry): pass it to olb_trace_*.
+ * `workspace` is caller-allocated DEVICE memory of >= olb_table_workspace_bytes().
  */
+typedef struct OlbDeviceTable {
+  void* workspace;
+  int64_t workspace_bytes;
+  uint32_t magic;
+  uint32_t features;       /* code paths the table needs (selects the kernel variant) */
+  int32_t n_surfaces;
+  int32_t n_wl;
+  int32_t off_f64, bytes_f64;   /* fp64 blob inside workspace */
+  int32_t off_f32, bytes_f32;   /* fp32 blob inside workspace */
+} OlbDeviceTable;
+
+/* Bytes of device workspace needed for `table` (< 256 KiB). Negative = error code. */
 int64_t olb_table_workspace_bytes(const OlbTable* table);
 
 /*
- * Stage `table` (HOST memory) into `workspace` (DEVICE memory,
- * >= olb_table_workspace_bytes) on `stream`.  Replaces the per-call Python walk
- * over live surface objects; call again whenever a surface parameter changes.
+ * Validate `table` (HOST memory), precompute everything that is uniform over rays
+ * (flattened poses, surface-to-surface transforms, n1/n2 per wavelength, monomial form
+ * of Zernike sums) and copy the result into `workspace` (DEVICE) on `stream`;
+ * synchronises `stream`.  Replaces the per-call Python walk over live surface objects;
+ * call again whenever a surface parameter changes.
  */
 int olb_table_upload(const OlbTable* table, void* workspace, int64_t workspace_bytes,
-                     void* stream);
+                     void* stream, OlbDeviceTable* out);
 
 /*
- * Trace n_rays rays through surfaces [first, last) of the staged table.
+ * Trace n_rays rays through surfaces [first, last) of the prepared table.
  * Replaces SurfaceGroup.trace(rays, skip=first) (surface_group.py:245-257) --
  * and, with last = first + 1, a single Surface.trace as issued by the ray
  * aimers (optiland/rays/ray_aiming/iterative.py:366).
- *   workspace : device table written by olb_table_upload
- *   rays      : device SoA (updated in place)
+ *   rays      : device SoA (updated in place unless OLB_TF_NO_FINAL)
  *   rec       : optional record rows, row r <-> surface first + r
  *   status    : optional device int32, OR-ed with OLB_ST_* bits
  * Asynchronous on `stream`.
  */
-int olb_trace_f32(const void* workspace, int32_t first, int32_t last,
+int olb_trace_f32(const OlbDeviceTable* table, int32_t first, int32_t last,
                   const OlbRays* rays, const OlbRecords* rec, int64_t n_rays,
                   uint32_t flags, int32_t* status, void* stream);
-int olb_trace_f64(const void* workspace, int32_t first, int32_t last,
+int olb_trace_f64(const OlbDeviceTable* table, int32_t first, int32_t last,
                   const OlbRays* rays, const OlbRecords* rec, int64_t n_rays,
                   uint32_t flags, int32_t* status, void* stream);
 
@@ -254,12 +270,12 @@ int olb_trace_f64(const void* workspace, int32_t first, int32_t last,
  *   dev_scratch : device memory, >= olb_host_scratch_bytes(elem_size, chunk)
  */
 int64_t olb_host_scratch_bytes(int32_t elem_size, int64_t chunk_rays);
-int olb_trace_host_f32(const void* workspace, int32_t first, int32_t last,
+int olb_trace_host_f32(const OlbDeviceTable* table, int32_t first, int32_t last,
                        const OlbRays* h_in, const OlbRays* h_out,
                        const OlbRecords* rec, int64_t n_rays, int64_t chunk_rays,
                        void* dev_scratch, int64_t dev_scratch_bytes, uint32_t flags,
                        int32_t* status);
-int olb_trace_host_f64(const void* workspace, int32_t first, int32_t last,
+int olb_trace_host_f64(const OlbDeviceTable* table, int32_t first, int32_t last,
                        const OlbRays* h_in, const OlbRays* h_out,
                        const OlbRecords* rec, int64_t n_rays, int64_t chunk_rays,
                        void* dev_scratch, int64_t dev_scratch_bytes, uint32_t flags,

@@ -1,0 +1,117 @@
+"""ctypes binding of the C ABI in ``include/olb.h`` (libolb.so, built in-tree).
+
+There is no CPU fallback: ``load()`` raises if the shared library is missing or does
+not export every symbol the header declares.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from functools import lru_cache
+
+import numpy as np
+
+from . import table as T
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libolb.so")
+
+OK = 0
+ERRORS = {-1: "OLB_ERR_INVALID_ARG", -2: "OLB_ERR_UNSUPPORTED", -3: "OLB_ERR_CUDA",
+          -4: "OLB_ERR_ALIGNMENT", -5: "OLB_ERR_TABLE"}
+
+TF_POLARIZED = 1 << 0
+TF_NO_FINAL = 1 << 1
+
+
+class OlbTable(C.Structure):
+    _fields_ = [
+        ("surfaces", C.c_void_p), ("n_surfaces", C.c_int32), ("n_wl", C.c_int32),
+        ("wavelengths", C.c_void_p), ("pool", C.c_void_p), ("pool_len", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
+class OlbRays(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in
+                ("x", "y", "z", "L", "M", "N", "i", "w", "opd", "L0", "M0", "N0", "p")]
+
+
+class OlbRecords(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("x", "y", "z", "L", "M", "N", "intensity", "opd")] + [
+        ("row_stride", C.c_int64)]
+
+
+class OlbDeviceTable(C.Structure):
+    _fields_ = [
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("magic", C.c_uint32),
+        ("features", C.c_uint32), ("n_surfaces", C.c_int32), ("n_wl", C.c_int32),
+        ("off_f64", C.c_int32), ("bytes_f64", C.c_int32), ("off_f32", C.c_int32),
+        ("bytes_f32", C.c_int32),
+    ]
+
+
+# every symbol include/olb.h declares: name -> (restype, argtypes)
+_P = C.POINTER
+SYMBOLS = {
+    "olb_version": (C.c_int, []),
+    "olb_last_error": (C.c_int, [C.c_char_p, C.c_int]),
+    "olb_launch_count": (C.c_int64, []),
+    "olb_table_workspace_bytes": (C.c_int64, [_P(OlbTable)]),
+    "olb_table_upload": (C.c_int, [_P(OlbTable), C.c_void_p, C.c_int64, C.c_void_p, _P(OlbDeviceTable)]),
+    "olb_trace_f32": (C.c_int, [_P(OlbDeviceTable), C.c_int32, C.c_int32, _P(OlbRays), _P(OlbRecords),
+                                C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "olb_trace_f64": (C.c_int, [_P(OlbDeviceTable), C.c_int32, C.c_int32, _P(OlbRays), _P(OlbRecords),
+                                C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "olb_host_scratch_bytes": (C.c_int64, [C.c_int32, C.c_int64]),
+    "olb_trace_host_f32": (C.c_int, [_P(OlbDeviceTable), C.c_int32, C.c_int32, _P(OlbRays), _P(OlbRays),
+                                     _P(OlbRecords), C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
+                                     C.c_uint32, C.c_void_p]),
+    "olb_trace_host_f64": (C.c_int, [_P(OlbDeviceTable), C.c_int32, C.c_int32, _P(OlbRays), _P(OlbRays),
+                                     _P(OlbRecords), C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
+                                     C.c_uint32, C.c_void_p]),
+}
+
+
+class OlbError(RuntimeError):
+    pass
+
+
+@lru_cache(maxsize=1)
+def load() -> C.CDLL:
+    """Load libolb.so and bind every declared symbol.  Fails loudly; no fallback."""
+    if not os.path.exists(LIB_PATH):
+        raise OlbError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  optiland_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the export is missing
+        fn.restype = restype
+        fn.argtypes = argtypes
+    return lib
+
+
+def last_error() -> str:
+    buf = C.create_string_buffer(512)
+    load().olb_last_error(buf, len(buf))
+    return buf.value.decode("utf-8", "replace")
+
+
+def check(rc: int, what: str) -> None:
+    if rc != OK:
+        raise OlbError(f"{what} failed: {ERRORS.get(rc, rc)}: {last_error()}")
+
+
+class HostTable:
+    """Owns the packed numpy arrays an ``OlbTable`` points into."""
+
+    def __init__(self, tab: T.SurfaceTable):
+        self.surf, self.pool = tab.pack()
+        self.surf = np.ascontiguousarray(self.surf)
+        self.pool = np.ascontiguousarray(self.pool)
+        self.wl = np.ascontiguousarray(tab.wavelengths, dtype=np.float64)
+        self.c = OlbTable(
+            surfaces=self.surf.ctypes.data, n_surfaces=len(self.surf), n_wl=len(self.wl),
+            wavelengths=self.wl.ctypes.data, pool=self.pool.ctypes.data, pool_len=len(self.pool),
+            reserved=0)

@@ -1,0 +1,422 @@
+// olb_math.cuh -- per-ray arithmetic of the real-ray trace hot path.
+//
+// One templated function, `surface_step`, does for ONE ray at ONE surface what the
+// reference does with ~190 element-wise array ops:
+//   localize -> distance -> propagate + OPD (+ absorption) -> clip -> normal ->
+//   refract / reflect -> coating
+// and leaves the ray in the surface's LOCAL frame (the caller globalizes for the
+// record).  Reference: optiland/surfaces/standard_surface.py:232-248 and the
+// functions cited at each block below.
+//
+// The functions are __host__ __device__ so that the very same arithmetic can be
+// instantiated on the CPU by tests/hostcheck (test infrastructure; never shipped in
+// libolb.so) and checked against the oracle in the GPU-less build container.
+#ifndef OLB_MATH_CUH_
+#define OLB_MATH_CUH_
+
+#include <math.h>
+#include <stdint.h>
+
+#include "olb_prep.h"
+
+#if defined(__CUDACC__)
+#define OLB_HD __host__ __device__ __forceinline__
+#else
+#define OLB_HD inline
+#endif
+
+namespace olb {
+
+// ---- scalar helpers: IEEE for double, approx-unit (<= 2 ulp) for float on device ----
+OLB_HD double o_sqrt(double v) { return sqrt(v); }
+OLB_HD double o_div(double a, double b) { return a / b; }
+OLB_HD double o_rcp(double a) { return 1.0 / a; }
+OLB_HD double o_rsqrt(double a) { return 1.0 / sqrt(a); }
+OLB_HD double o_abs(double a) { return fabs(a); }
+OLB_HD double o_exp(double a) { return exp(a); }
+OLB_HD double o_fma(double a, double b, double c) { return fma(a, b, c); }
+OLB_HD float o_abs(float a) { return fabsf(a); }
+OLB_HD float o_fma(float a, float b, float c) { return fmaf(a, b, c); }
+#if defined(__CUDA_ARCH__)
+OLB_HD float o_sqrt(float v) { float r; asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+OLB_HD float o_rcp(float v) { float r; asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+OLB_HD float o_rsqrt(float v) { float r; asm("rsqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+OLB_HD float o_div(float a, float b) { return a * o_rcp(b); }
+OLB_HD float o_exp(float a) { return __expf(a); }
+#else
+OLB_HD float o_sqrt(float v) { return sqrtf(v); }
+OLB_HD float o_rcp(float v) { return 1.0f / v; }
+OLB_HD float o_rsqrt(float v) { return 1.0f / sqrtf(v); }
+OLB_HD float o_div(float a, float b) { return a / b; }
+OLB_HD float o_exp(float a) { return expf(a); }
+#endif
+
+template <typename T> struct Eps;
+template <> struct Eps<float> { static constexpr float v = 1.1920929e-7f; };
+template <> struct Eps<double> { static constexpr double v = 2.220446049250313e-16; };
+
+// Ray state held in registers. Position/direction are in the CURRENT frame (global at
+// entry, then the local frame of the last traced surface).
+template <typename T>
+struct Ray {
+  T x, y, z, L, M, N, i, opd;
+  T opd_lo;    // fp32 only: low word of a two-float OPD accumulator (see accumulate_opd)
+  T L0, M0, N0;  // direction before the last interaction (real_rays.py:170-172)
+  int widx;    // wavelength index into the media tables
+};
+
+// OPD accumulation: opd += |t * n1|  (standard_surface.py:244).  In fp32 the sum is
+// carried as an unevaluated (hi, lo) pair (Knuth TwoSum) so that the ~190 mm optical
+// path of a camera lens does not lose 0.3 lambda to 13 roundings as the reference's own
+// fp32 path does (SURVEY.md section 8d "precision reality check").
+OLB_HD void accumulate_opd(Ray<double>& r, double v) { r.opd += v; }
+OLB_HD void accumulate_opd(Ray<float>& r, float v) {
+  float s = r.opd + v;
+  float bb = s - r.opd;
+  float err = (r.opd - (s - bb)) + (v - bb);
+  r.opd = s;
+  r.opd_lo += err;
+}
+OLB_HD double opd_value(const Ray<double>& r) { return r.opd; }
+OLB_HD float opd_value(const Ray<float>& r) { return r.opd + r.opd_lo; }
+
+template <typename T>
+OLB_HD void apply_affine(const T* A, const T* b, bool rotated, T& x, T& y, T& z, T& L, T& M, T& N) {
+  if (rotated) {
+    T px = x, py = y, pz = z, dl = L, dm = M, dn = N;
+    x = o_fma(A[0], px, o_fma(A[1], py, o_fma(A[2], pz, b[0])));
+    y = o_fma(A[3], px, o_fma(A[4], py, o_fma(A[5], pz, b[1])));
+    z = o_fma(A[6], px, o_fma(A[7], py, o_fma(A[8], pz, b[2])));
+    L = o_fma(A[0], dl, o_fma(A[1], dm, A[2] * dn));
+    M = o_fma(A[3], dl, o_fma(A[4], dm, A[5] * dn));
+    N = o_fma(A[6], dl, o_fma(A[7], dm, A[8] * dn));
+  } else {
+    x += b[0]; y += b[1]; z += b[2];
+  }
+}
+
+// ---- closed-form conic intersection -----------------------------------------------
+// optiland/geometries/standard.py:97-148.  Same roots t1 = (-b+sqrt(d))/2a,
+// t2 = (-b-sqrt(d))/2a and the same selection rule (|z1| <= |z2| -> t1, a == 0 -> -c/b),
+// but evaluated with the cancellation-free pairing q = -(b/2 + sign(b) sqrt(d/4)),
+// {q/a, c/q}: the reference's form loses ~3e-9 mm on a 10^4-mm telescope in fp64 and is
+// unusable in fp32 there.
+template <typename T>
+OLB_HD T conic_distance(T x, T y, T z, T L, T M, T N, const PrepSurface<T>& S) {
+  if (S.flags & PSF_RADIUS_INF) {
+    T Ns = o_abs(N) > (T)1e-14 ? N : (T)1e-14;
+    return -o_div(z, Ns);
+  }
+  const T k = S.conic, R = S.radius;
+  T a = o_fma(k * N, N, o_fma(L, L, o_fma(M, M, N * N)));
+  T zz = o_fma(S.kp1, z, -R);                          // (1+k) z - R
+  T hb = o_fma(L, x, o_fma(M, y, N * zz));             // b / 2
+  T c = o_fma(x, x, o_fma(y, y, z * (zz - R)));        // x^2 + y^2 + z((1+k) z - 2R)
+  T disc = o_fma(hb, hb, -a * c);                      // d / 4
+  T sq = o_sqrt(disc);
+  T q = hb >= 0 ? -(hb + sq) : (sq - hb);
+  T ta = o_div(q, a);
+  T tb = (q == 0) ? ta : o_div(c, q);
+  T t1 = hb >= 0 ? tb : ta;                            // (-b + sqrt d) / 2a
+  T t2 = hb >= 0 ? ta : tb;                            // (-b - sqrt d) / 2a
+  T z1 = o_fma(t1, N, z), z2 = o_fma(t2, N, z);
+  T t = (o_abs(z1) <= o_abs(z2)) ? t1 : t2;
+  if (a == 0) t = -o_div(c, 2 * hb);
+  return t;
+}
+
+// Conic part of the sag and of the slope denominators.
+//   sag   = r2 / (R (1 + sqrt(1 - (1+k) r2 / R^2)))        standard.py:80-95
+//   slope = (x, y) / (R sqrt(1 - (1+k) r2 / R^2))           standard.py:163-167
+template <typename T>
+OLB_HD void conic_sag_slope(T r2, const PrepSurface<T>& S, T& sag, T& inv_denom) {
+  T s2 = o_fma(-S.kp1 * r2, S.curv * S.curv, (T)1);
+  T s = o_sqrt(s2);
+  sag = o_div(r2 * S.curv, (T)1 + s);
+  inv_denom = o_div(S.curv, s);
+}
+
+// Bivariate polynomial P(x, y) = sum_ij C[i*cols+j] x^i y^j with both partials (nested
+// Horner).  `tri`: table is triangular (i + j <= rows - 1), skip the structural zeros.
+template <typename T>
+OLB_HD void poly2_eval(const T* C, int rows, int cols, bool tri, T x, T y, T& P, T& Px, T& Py) {
+  P = 0; Px = 0; Py = 0;
+  for (int i = rows - 1; i >= 0; --i) {
+    const T* row = C + i * cols;
+    const int jmax = tri ? (rows - 1 - i) : (cols - 1);
+    T q = 0, qy = 0;
+    for (int j = jmax; j >= 0; --j) {
+      qy = o_fma(qy, y, q);
+      q = o_fma(q, y, row[j]);
+    }
+    Px = o_fma(Px, x, P);
+    P = o_fma(P, x, q);
+    Py = o_fma(Py, x, qy);
+  }
+}
+template <typename T>
+OLB_HD T poly2_value(const T* C, int rows, int cols, bool tri, T x, T y) {
+  T P = 0;
+  for (int i = rows - 1; i >= 0; --i) {
+    const T* row = C + i * cols;
+    const int jmax = tri ? (rows - 1 - i) : (cols - 1);
+    T q = 0;
+    for (int j = jmax; j >= 0; --j) q = o_fma(q, y, row[j]);
+    P = o_fma(P, x, q);
+  }
+  return P;
+}
+
+// Sag of a Newton-family surface at (x, y).  `status` collects OLB_ST_* bits.
+//   even asphere  even_asphere.py:93-109   conic + sum C_i r2^(i+1)
+//   odd asphere   odd_asphere.py:86-101    conic + sum C_i r^(i+1)
+//   polynomial    polynomial.py:105-121    conic + sum C_ij x^i y^j
+//   Zernike       zernike.py:153-180       conic + sum c_i N_i Z_i(rho, phi), monomial form
+template <typename T>
+OLB_HD T newton_sag(T x, T y, const PrepSurface<T>& S, const T* pool, int& status) {
+  T r2 = o_fma(x, x, y * y);
+  T sag, inv_denom;
+  conic_sag_slope(r2, S, sag, inv_denom);
+  if (S.kind == OLB_GEOM_EVEN_ASPHERE) {
+    const T* c = pool + S.coef_off;
+    T h = 0;
+    for (int i = S.n_coef - 1; i >= 0; --i) h = o_fma(h, r2, c[i]);
+    sag = o_fma(h, r2, sag);
+  } else if (S.kind == OLB_GEOM_ODD_ASPHERE) {
+    const T* c = pool + S.coef_off;
+    T r = o_sqrt(r2), h = 0;
+    for (int i = S.n_coef - 1; i >= 0; --i) h = o_fma(h, r, c[i]);
+    sag = o_fma(h, r, sag);
+  } else {
+    T xn = x * S.inv_norm, yn = y * S.inv_norm;
+    if (S.kind == OLB_GEOM_ZERNIKE && (o_abs(xn) > (T)1 || o_abs(yn) > (T)1)) status |= OLB_ST_ZERNIKE_RANGE;
+    sag += poly2_value(pool + S.coef_off, S.poly_rows, S.poly_cols, (S.flags & PSF_POLY_TRI) != 0, xn, yn);
+  }
+  return sag;
+}
+
+// Slopes (dz/dx, dz/dy) of a Newton-family surface: the un-normalised (dfdx, dfdy) of
+// even_asphere.py:111-140, odd_asphere.py:103-142, polynomial.py:123-155,
+// zernike.py:182-252 (Zernike: derivative WITHOUT N_nm and exactly zero at rho == 0,
+// reproducing the reference's eps-regularised chain rule).
+template <typename T>
+OLB_HD void newton_slopes(T x, T y, const PrepSurface<T>& S, const T* pool, T& fx, T& fy) {
+  T r2 = o_fma(x, x, y * y);
+  T sag, g;
+  conic_sag_slope(r2, S, sag, g);
+  if (S.kind == OLB_GEOM_EVEN_ASPHERE) {
+    const T* c = pool + S.coef_off;
+    T h = 0;
+    for (int i = S.n_coef - 1; i >= 0; --i) h = o_fma(h, r2, (T)(2 * (i + 1)) * c[i]);
+    g += h;
+    fx = x * g; fy = y * g;
+  } else if (S.kind == OLB_GEOM_ODD_ASPHERE) {
+    const T* c = pool + S.coef_off;
+    T r = o_sqrt(r2), h = 0;
+    for (int i = S.n_coef - 1; i >= 0; --i) h = o_fma(h, r, (T)(i + 1) * c[i]);
+    // terms (i+1) x C_i r^(i-1); non-finite terms are zeroed by the reference (r == 0)
+    T hr = r > 0 ? o_div(h, r) : (T)0;
+    g += hr;
+    fx = x * g; fy = y * g;
+  } else {
+    T xn = x * S.inv_norm, yn = y * S.inv_norm;
+    T P, Px, Py;
+    poly2_eval(pool + S.poly_d_off, S.poly_rows, S.poly_cols, (S.flags & PSF_POLY_TRI) != 0, xn, yn, P, Px, Py);
+    if (S.kind == OLB_GEOM_ZERNIKE) {
+      // The reference forms dZ/dx = A drho/dx + B dphi/dx with REGULARISED chain-rule factors
+      //   drho/dx = xn / (R (rho + eps)),  dphi/dx = -yn / (R (rho^2 + eps)),  eps = 1e-14
+      // (zernike.py:206-231).  With A = (xn Dx + yn Dy)/rho and B = xn Dy - yn Dx recovered from
+      // the exact partials (Dx, Dy) this damps the slope by a = rho/(rho+eps), b = rho^2/(rho^2+eps)
+      // -- 0.25 % at rho = 2e-6, exactly zero on the axis.  Reproduced, not fixed.
+      const T eps = (T)1e-14;
+      T rho2 = o_fma(xn, xn, yn * yn);
+      if (rho2 == 0) { Px = 0; Py = 0; }
+      else {
+        T rho = o_sqrt(rho2);
+        T a_ = o_div(rho, rho + eps), b_ = o_div(rho2, rho2 + eps), inv = o_rcp(rho2);
+        T xx = xn * xn, yy = yn * yn, xy = xn * yn * (a_ - b_);
+        T Dx = Px, Dy = Py;
+        Px = o_fma(Dx, o_fma(a_, xx, b_ * yy), Dy * xy) * inv;
+        Py = o_fma(Dy, o_fma(a_, yy, b_ * xx), Dx * xy) * inv;
+      }
+    }
+    fx = o_fma(x, g, Px * S.inv_norm);
+    fy = o_fma(y, g, Py * S.inv_norm);
+  }
+}
+
+// Newton-Raphson refinement of t (newton_raphson.py:119-168).  The reference stops
+// when max over ALL rays |f| < tol; a kernel cannot see all rays, so each ray iterates
+// until its own |f| < tol and then takes ONE more step, which by quadratic convergence
+// leaves a residual ~tol^2: every ray ends at least as converged as in the reference,
+// and the two differ by at most the reference's own stopping residual (< tol).  In fp32
+// the tolerance is floored at the rounding noise of f so the loop cannot spin.
+template <typename T>
+OLB_HD T newton_distance(T x, T y, T z, T L, T M, T N, const PrepSurface<T>& S, const T* pool, int& status) {
+  T t = conic_distance(x, y, z, L, M, N, S);
+  for (int it = 0; it < S.max_iter; ++it) {
+    T xi = o_fma(t, L, x), yi = o_fma(t, M, y), zi = o_fma(t, N, z);
+    T sag = newton_sag(xi, yi, S, pool, status);
+    T f = sag - zi;
+    if (!(f == f)) break;  // NaN stays NaN (the reference would spin to max_iter on it)
+    T tol = S.tol;
+    T floor_ = (T)8 * Eps<T>::v * (o_abs(zi) + o_abs(sag));
+    if (floor_ > tol) tol = floor_;
+    const bool conv = o_abs(f) < tol;
+    T fx, fy;
+    newton_slopes(xi, yi, S, pool, fx, fy);
+    // f'(t) = fx L + fy M - N  with fx = -nx/nz = dz/dx  (newton_raphson.py:155-161)
+    T df = o_fma(fx, L, o_fma(fy, M, -N));
+    T dfs = o_abs(df) > (T)1e-14 ? df : (T)1e-14;
+    t -= o_div(f, dfs);
+    if (conv) break;  // that was the polishing step
+  }
+  return t;
+}
+
+// Aperture program (postfix) -> inside?   physical_apertures/*.py, see include/olb.h.
+template <typename T>
+OLB_HD bool aperture_inside(const T* prog, int len, T x, T y) {
+  uint32_t stack = 0;  // bit stack, top at bit 0
+  int i = 0;
+  while (i < len) {
+    int op = (int)prog[i];
+    bool v;
+    if (op == OLB_AP_RADIAL) {
+      T r2 = o_fma(x, x, y * y);
+      v = (r2 <= prog[i + 1] * prog[i + 1]) && (r2 >= prog[i + 2] * prog[i + 2]);
+      i += 3;
+    } else if (op == OLB_AP_OFFSET_RADIAL) {
+      T dx = x - prog[i + 3], dy = y - prog[i + 4];
+      T r2 = o_fma(dx, dx, dy * dy);
+      v = (r2 <= prog[i + 1] * prog[i + 1]) && (r2 >= prog[i + 2] * prog[i + 2]);
+      i += 5;
+    } else if (op == OLB_AP_RECT) {
+      v = (prog[i + 1] <= x) && (x <= prog[i + 2]) && (prog[i + 3] <= y) && (y <= prog[i + 4]);
+      i += 5;
+    } else if (op == OLB_AP_ELLIPSE) {
+      T dx = x - prog[i + 3], dy = y - prog[i + 4];
+      T a = prog[i + 1], b = prog[i + 2];
+      v = (o_div(dx * dx, a * a) + o_div(dy * dy, b * b)) <= (T)1;
+      i += 5;
+    } else {
+      bool b_ = stack & 1u, a_ = (stack >> 1) & 1u;
+      stack >>= 2;
+      v = op == OLB_AP_UNION ? (a_ || b_) : op == OLB_AP_INTERSECT ? (a_ && b_) : (a_ && !b_);
+      i += 1;
+    }
+    stack = (stack << 1) | (v ? 1u : 0u);
+  }
+  return stack & 1u;
+}
+
+// The surface step.  FEAT gates code that most systems never need (register pressure).
+template <typename T, uint32_t FEAT>
+OLB_HD void surface_step(Ray<T>& r, const PrepSurface<T>& S, const T* pool, bool from_global, int& status) {
+  // -- localize (coordinate_system.py:73-89), from global or from the previous local frame
+  if (FEAT & FEAT_ROT) {
+    if (from_global) apply_affine(S.Ag, S.bg, (S.flags & PSF_ROT_IN_G) != 0, r.x, r.y, r.z, r.L, r.M, r.N);
+    else apply_affine(S.Ar, S.br, (S.flags & PSF_ROT_IN_R) != 0, r.x, r.y, r.z, r.L, r.M, r.N);
+  } else {
+    const T* b = from_global ? S.bg : S.br;
+    r.x += b[0]; r.y += b[1]; r.z += b[2];
+  }
+  const T* med = pool + S.media_off + MED_STRIDE * (r.widx < 0 ? 0 : r.widx);
+  const T bad = r.widx < 0 ? (T)NAN : (T)0;  // unknown wavelength -> NaN in band
+
+  // -- distance
+  T t;
+  if (S.kind == OLB_GEOM_PLANE) {
+    t = -o_div(r.z, r.N);                               // plane.py:72-88
+  } else if (S.kind == OLB_GEOM_STANDARD || !(FEAT & FEAT_NEWTON)) {
+    t = conic_distance(r.x, r.y, r.z, r.L, r.M, r.N, S);
+  } else {
+    t = newton_distance(r.x, r.y, r.z, r.L, r.M, r.N, S, pool, status);
+  }
+  // -- propagate (homogeneous.py:30-57) and OPD (standard_surface.py:244)
+  r.x = o_fma(t, r.L, r.x);
+  r.y = o_fma(t, r.M, r.y);
+  r.z = o_fma(t, r.N, r.z);
+  if ((FEAT & FEAT_EXTRA) && (S.flags & OLB_SF_ABSORBING)) r.i *= o_exp(-med[MED_ALPHA] * t);
+  accumulate_opd(r, o_abs(t * (med[MED_N1] + bad)));
+
+  // -- aperture clip (standard_surface.py:245-246; real_rays.py:154-161): NaN -> clipped
+  if (S.flags & OLB_SF_APERTURE) {
+    bool inside;
+    if (S.flags & PSF_APER_RADIAL) {
+      T r2 = o_fma(r.x, r.x, r.y * r.y);
+      inside = (r2 <= pool[S.aper_off + 1]) && (r2 >= pool[S.aper_off + 2]);
+    } else if (FEAT & FEAT_EXTRA) {
+      inside = aperture_inside(pool + S.aper_off, S.aper_len, r.x, r.y);
+    } else {
+      inside = true;
+    }
+    if (!inside) r.i = 0;
+  }
+
+  // -- surface normal
+  T nx, ny, nz;
+  if (S.kind == OLB_GEOM_PLANE) {
+    nx = 0; ny = 0; nz = 1;                             // plane.py:90-109
+  } else if (S.kind == OLB_GEOM_STANDARD || !(FEAT & FEAT_NEWTON)) {
+    // standard.py:150-175: (x, y, -denom)/ (denom * mag) with denom = R sqrt(1-(1+k) r2/R^2);
+    // multiplied through by sqrt(.) >= 0 this is (x c, y c, -s) / sqrt(1 - k r2 c^2).
+    T c = S.curv;
+    T r2 = o_fma(r.x, r.x, r.y * r.y);
+    T s = o_sqrt(o_fma(-S.kp1 * r2, c * c, (T)1));
+    nx = r.x * c; ny = r.y * c; nz = -s;
+    if (S.conic != 0) {
+      T inv = o_rsqrt(o_fma(-S.conic * r2, c * c, (T)1));
+      nx *= inv; ny *= inv; nz *= inv;
+    }
+  } else {
+    T fx, fy;
+    newton_slopes(r.x, r.y, S, pool, fx, fy);
+    T inv = o_rsqrt(o_fma(fx, fx, o_fma(fy, fy, (T)1)));
+    nx = fx * inv; ny = fy * inv; nz = -inv;
+  }
+
+  // -- interaction (refractive_reflective_model.py:32-55)
+  if (FEAT & (FEAT_EXTRA | FEAT_POL)) { r.L0 = r.L; r.M0 = r.M; r.N0 = r.N; }
+  T dot = o_fma(r.L, nx, o_fma(r.M, ny, r.N * nz));
+  if (S.flags & OLB_SF_REFLECT) {
+    // real_rays.py:189-205 with the aligned normal: d - 2 |dot| sign(dot) n = d - 2 dot n
+    T m2 = -2 * dot;
+    r.L = o_fma(m2, nx, r.L);
+    r.M = o_fma(m2, ny, r.M);
+    r.N = o_fma(m2, nz, r.N);
+  } else {
+    // real_rays.py:163-187 + _align_surface_normal :535-571 (sign(0) = 0, sign(NaN) = NaN)
+    T u = med[MED_U] + bad;
+    T sgn = dot > 0 ? (T)1 : (dot < 0 ? (T)-1 : dot);
+    T ad = o_abs(dot);
+    T root = o_sqrt(o_fma(u * u, o_fma(ad, ad, (T)-1), (T)1));   // sqrt(1 - u^2 (1 - dot^2))
+    T g = sgn * o_fma(-u, ad, root);
+    r.L = o_fma(u, r.L, nx * g);
+    r.M = o_fma(u, r.M, ny * g);
+    r.N = o_fma(u, r.N, nz * g);
+  }
+  // -- coating (interactions/base.py:111-128; coatings.py:164-237)
+  if ((FEAT & FEAT_EXTRA) && S.coating == OLB_COAT_SIMPLE)
+    r.i *= (S.flags & OLB_SF_REFLECT) ? S.coat_r : S.coat_t;
+}
+
+// Local -> global for the record (coordinate_system.py:91-107).
+template <typename T, uint32_t FEAT>
+OLB_HD void to_global(const Ray<T>& r, const PrepSurface<T>& S, T& x, T& y, T& z, T& L, T& M, T& N) {
+  if ((FEAT & FEAT_ROT) && (S.flags & OLB_SF_ROTATED)) {
+    const T* R = S.R;
+    x = o_fma(R[0], r.x, o_fma(R[1], r.y, o_fma(R[2], r.z, S.t[0])));
+    y = o_fma(R[3], r.x, o_fma(R[4], r.y, o_fma(R[5], r.z, S.t[1])));
+    z = o_fma(R[6], r.x, o_fma(R[7], r.y, o_fma(R[8], r.z, S.t[2])));
+    L = o_fma(R[0], r.L, o_fma(R[1], r.M, R[2] * r.N));
+    M = o_fma(R[3], r.L, o_fma(R[4], r.M, R[5] * r.N));
+    N = o_fma(R[6], r.L, o_fma(R[7], r.M, R[8] * r.N));
+  } else {
+    x = r.x + S.t[0]; y = r.y + S.t[1]; z = r.z + S.t[2];
+    L = r.L; M = r.M; N = r.N;
+  }
+}
+
+}  // namespace olb
+#endif  // OLB_MATH_CUH_

@@ -1,0 +1,368 @@
+// olb_prep.h -- device-side ("prepared") surface table and its host-side construction.
+//
+// The host table of include/olb.h (fp64, reference vocabulary) is turned once per
+// upload into one contiguous blob per element type T (float / double):
+//
+//     [ PrepHeader ][ PrepSurface<T> x n_surf ][ T pool[...] ]
+//
+// which the trace kernel pulls into shared memory with a single TMA bulk copy.
+// Everything that is uniform over rays is precomputed here in fp64: flattened poses
+// and surface-to-surface relative transforms, curvature, index ratios n1/n2 per
+// wavelength, Beer-Lambert coefficients, and the monomial form of Zernike sums.
+//
+// Reference data contract: SURVEY.md Appendix B; citations inline.
+#ifndef OLB_PREP_H_
+#define OLB_PREP_H_
+
+#include <stdint.h>
+
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/olb.h"
+
+namespace olb {
+
+// Feature bits: which code paths a table needs (selects the kernel instantiation).
+enum : uint32_t {
+  FEAT_ROT = 1u << 0,      // some surface has a rotated pose
+  FEAT_NEWTON = 1u << 1,   // even/odd asphere, polynomial, Zernike (Newton iteration)
+  FEAT_EXTRA = 1u << 2,    // absorption, non-radial aperture programs, simple coatings
+  FEAT_POL = 1u << 3,      // polarized rays (P matrix) / Fresnel coatings
+};
+
+struct PrepHeader {
+  int32_t n_surf;
+  int32_t n_wl;
+  int32_t pool_len;     // in elements of T
+  uint32_t features;    // FEAT_* needed by this table
+  int32_t blob_bytes;   // total bytes of this blob (multiple of 16)
+  int32_t elem_size;    // sizeof(T)
+  int32_t pad[2];
+};  // 32 bytes
+
+// Media block per surface in the pool: n_wl records of MEDIA_STRIDE values each.
+enum { MED_N1 = 0, MED_U = 1, MED_ALPHA = 2, MED_CN = 3, MED_STRIDE = 4 };
+//   MED_N1    n1                           (OPD: standard_surface.py:244)
+//   MED_U     n1 / n2                      (refract: real_rays.py:174)
+//   MED_ALPHA 4*pi*k1/lambda * 1e3         (homogeneous.py:45-53)
+//   MED_CN    coating n2 / coating n1      (jones.py:95)
+
+template <typename T>
+struct PrepSurface {
+  int32_t kind;
+  uint32_t flags;      // OLB_SF_* plus the PSF_* bits below
+  int32_t n_coef;      // even/odd: number of coefficients
+  int32_t coef_off;    // pool offset (elements of T)
+  int32_t aper_off;
+  int32_t aper_len;
+  int32_t max_iter;
+  int32_t coating;
+  int32_t media_off;
+  int32_t poly_rows;   // bivariate tables: rows (x powers) and cols (y powers)
+  int32_t poly_cols;
+  int32_t poly_d_off;  // pool offset of the derivative-source table (Zernike quirk)
+  // incoming transform from GLOBAL coordinates: p_loc = Ag * p + bg
+  T Ag[9], bg[3];
+  // incoming transform from the PREVIOUS surface's local frame: p_loc = Ar * p + br
+  T Ar[9], br[3];
+  // outgoing transform to global: p_glob = R * p_loc + t
+  T R[9], t[3];
+  T radius, curv, conic, kp1;   // curv = 1/radius (0 for infinite radius), kp1 = 1 + k
+  T tol, coat_t, coat_r, inv_norm;  // inv_norm = 1 / norm_radius
+};
+
+enum : uint32_t {
+  PSF_ROT_IN_G = 1u << 8,    // Ag != I
+  PSF_ROT_IN_R = 1u << 9,    // Ar != I
+  PSF_RADIUS_INF = 1u << 10, // StandardGeometry with infinite radius (standard.py:108-111)
+  PSF_APER_RADIAL = 1u << 11,// aperture program is a single RADIAL op (fast path)
+  PSF_POLY_TRI = 1u << 12,   // bivariate table is triangular (i + j <= rows-1)
+};
+
+static inline void mat3_mul(const double* A, const double* B, double* C) {
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) {
+      double s = 0;
+      for (int k = 0; k < 3; ++k) s += A[3 * r + k] * B[3 * k + c];
+      C[3 * r + c] = s;
+    }
+}
+static inline void mat3_transpose(const double* A, double* At) {
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) At[3 * c + r] = A[3 * r + c];
+}
+static inline bool mat3_is_identity(const double* A) {
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c)
+      if (A[3 * r + c] != (r == c ? 1.0 : 0.0)) return false;
+  return true;
+}
+
+// ---- Zernike -> monomials in (xn, yn) -----------------------------------------
+// Z_n^m = R_n^|m|(rho) * {cos(m phi) | sin(|m| phi)},  optiland/zernike/base.py:42-68,
+// R_n^m(rho) = sum_k (-1)^k (n-k)! / (k! ((n+m)/2-k)! ((n-m)/2-k)!) rho^(n-2k)  (:217-243)
+// rho^j cos(m phi) etc. are polynomials in xn = rho cos(phi), yn = rho sin(phi):
+//   rho^(n-2k) {cos|sin}(m phi) = (xn^2+yn^2)^((n-m)/2-k) * {Re|Im} (xn + i yn)^m
+static inline double fact(int n) {
+  double f = 1;
+  for (int i = 2; i <= n; ++i) f *= i;
+  return f;
+}
+static inline double binom(int n, int k) { return fact(n) / (fact(k) * fact(n - k)); }
+
+// Adds coef * Z_n^m to the (deg+1)x(deg+1) row-major table tab[i*(deg+1)+j] ~ xn^i yn^j.
+static inline void zernike_add_monomials(int n, int m, double coef, int deg, double* tab) {
+  const int ma = m < 0 ? -m : m;
+  const int W = deg + 1;
+  for (int k = 0; k <= (n - ma) / 2; ++k) {
+    double rc = ((k & 1) ? -1.0 : 1.0) * fact(n - k) /
+                (fact(k) * fact((n + ma) / 2 - k) * fact((n - ma) / 2 - k));
+    const int q = (n - ma) / 2 - k;  // power of (xn^2 + yn^2)
+    for (int a = 0; a <= q; ++a) {   // (x^2+y^2)^q = sum_a C(q,a) x^(2a) y^(2(q-a))
+      double ca = binom(q, a);
+      for (int j = 0; j <= ma; ++j) {  // (x+iy)^m = sum_j C(m,j) x^(m-j) (iy)^j
+        // i^j: j%4==0 -> 1, 1 -> i, 2 -> -1, 3 -> -i
+        const bool imag = (j & 1) != 0;
+        if ((m >= 0) == imag) continue;  // cos wants real part, sin wants imaginary part
+        double sgn = ((j >> 1) & 1) ? -1.0 : 1.0;
+        int px = 2 * a + (ma - j);
+        int py = 2 * (q - a) + j;
+        tab[px * W + py] += coef * rc * ca * binom(ma, j) * sgn;
+      }
+    }
+  }
+}
+
+struct PrepResult {
+  std::vector<unsigned char> blob_f64, blob_f32;
+  uint32_t features = 0;
+  std::string error;
+};
+
+template <typename T>
+static void build_blob(const OlbTable& tab, const std::vector<std::vector<double>>& pools,
+                       const std::vector<PrepSurface<double>>& ps, uint32_t features,
+                       std::vector<unsigned char>& out) {
+  // flatten per-surface pools into one pool, fixing offsets
+  std::vector<PrepSurface<T>> surf(ps.size());
+  std::vector<T> pool;
+  for (size_t s = 0; s < ps.size(); ++s) {
+    const PrepSurface<double>& a = ps[s];
+    PrepSurface<T>& b = surf[s];
+    const int base = (int)pool.size();
+    b.kind = a.kind; b.flags = a.flags; b.n_coef = a.n_coef;
+    b.coef_off = a.coef_off + base; b.aper_off = a.aper_off + base; b.aper_len = a.aper_len;
+    b.max_iter = a.max_iter; b.coating = a.coating; b.media_off = a.media_off + base;
+    b.poly_rows = a.poly_rows; b.poly_cols = a.poly_cols; b.poly_d_off = a.poly_d_off + base;
+    for (int i = 0; i < 9; ++i) { b.Ag[i] = (T)a.Ag[i]; b.Ar[i] = (T)a.Ar[i]; b.R[i] = (T)a.R[i]; }
+    for (int i = 0; i < 3; ++i) { b.bg[i] = (T)a.bg[i]; b.br[i] = (T)a.br[i]; b.t[i] = (T)a.t[i]; }
+    b.radius = (T)a.radius; b.curv = (T)a.curv; b.conic = (T)a.conic; b.kp1 = (T)a.kp1;
+    b.tol = (T)a.tol; b.coat_t = (T)a.coat_t; b.coat_r = (T)a.coat_r; b.inv_norm = (T)a.inv_norm;
+    for (double v : pools[s]) pool.push_back((T)v);
+    while (pool.size() % 4) pool.push_back((T)0);
+  }
+  // wavelengths at the end of the pool
+  const int wl_off = (int)pool.size();
+  for (int j = 0; j < tab.n_wl; ++j) pool.push_back((T)tab.wavelengths[j]);
+  while (pool.size() % 4) pool.push_back((T)0);
+
+  PrepHeader h{};
+  h.n_surf = (int32_t)ps.size();
+  h.n_wl = tab.n_wl;
+  h.pool_len = (int32_t)pool.size();
+  h.features = features;
+  h.elem_size = (int32_t)sizeof(T);
+  h.pad[0] = wl_off;
+  size_t bytes = sizeof(PrepHeader) + surf.size() * sizeof(PrepSurface<T>) + pool.size() * sizeof(T);
+  bytes = (bytes + 15) & ~size_t(15);
+  h.blob_bytes = (int32_t)bytes;
+  out.assign(bytes, 0);
+  unsigned char* p = out.data();
+  std::memcpy(p, &h, sizeof(h)); p += sizeof(h);
+  std::memcpy(p, surf.data(), surf.size() * sizeof(PrepSurface<T>)); p += surf.size() * sizeof(PrepSurface<T>);
+  std::memcpy(p, pool.data(), pool.size() * sizeof(T));
+}
+
+static inline int aperture_operands(int op) {
+  switch (op) {
+    case OLB_AP_RADIAL: return 2;
+    case OLB_AP_OFFSET_RADIAL: case OLB_AP_RECT: case OLB_AP_ELLIPSE: return 4;
+    case OLB_AP_UNION: case OLB_AP_INTERSECT: case OLB_AP_DIFFERENCE: return 0;
+    default: return -1;
+  }
+}
+
+// Validate + prepare. Returns empty error string on success.
+static inline PrepResult prepare_table(const OlbTable& tab) {
+  PrepResult res;
+  if (!tab.surfaces || !tab.wavelengths || !tab.pool) { res.error = "NULL table member"; return res; }
+  if (tab.n_surfaces < 1 || tab.n_surfaces > OLB_MAX_SURFACES) { res.error = "n_surfaces out of range"; return res; }
+  if (tab.n_wl < 1 || tab.n_wl > OLB_MAX_WAVELENGTHS) { res.error = "n_wl out of range"; return res; }
+  const int n_wl = tab.n_wl;
+  std::vector<PrepSurface<double>> ps(tab.n_surfaces);
+  std::vector<std::vector<double>> pools(tab.n_surfaces);
+  uint32_t features = 0;
+  int prev = -1;  // previous surface with a frame (non-NOOP)
+  auto in_pool = [&](int off, int len) { return off >= 0 && len >= 0 && (int64_t)off + len <= tab.pool_len; };
+
+  for (int s = 0; s < tab.n_surfaces; ++s) {
+    const OlbSurface& in = tab.surfaces[s];
+    PrepSurface<double>& o = ps[s];
+    std::memset(&o, 0, sizeof(o));
+    std::vector<double>& pool = pools[s];
+    o.kind = in.kind;
+    o.flags = in.flags & 0xffu;
+    o.max_iter = in.max_iter;
+    o.coating = in.coating;
+    if (in.kind < OLB_GEOM_NOOP || in.kind > OLB_GEOM_POLYNOMIAL) { res.error = "unknown geometry kind"; return res; }
+
+    // ---- pose --------------------------------------------------------------
+    double Rt[9];
+    mat3_transpose(in.R, Rt);
+    for (int i = 0; i < 9; ++i) { o.R[i] = in.R[i]; o.Ag[i] = Rt[i]; }
+    for (int i = 0; i < 3; ++i) o.t[i] = in.t[i];
+    const bool rotated = !mat3_is_identity(in.R);
+    for (int r = 0; r < 3; ++r) {
+      if (rotated) o.bg[r] = -(Rt[3 * r] * in.t[0] + Rt[3 * r + 1] * in.t[1] + Rt[3 * r + 2] * in.t[2]);
+      else o.bg[r] = -in.t[r];
+    }
+    if (rotated) { o.flags |= OLB_SF_ROTATED | PSF_ROT_IN_G; features |= FEAT_ROT; }
+    else o.flags &= ~uint32_t(OLB_SF_ROTATED);
+    if (in.kind != OLB_GEOM_NOOP) {
+      if (prev >= 0) {
+        const OlbSurface& pv = tab.surfaces[prev];
+        const bool prev_rot = !mat3_is_identity(pv.R);
+        if (!rotated && !prev_rot) {
+          for (int i = 0; i < 9; ++i) o.Ar[i] = (i % 4 == 0) ? 1.0 : 0.0;
+          for (int r = 0; r < 3; ++r) o.br[r] = pv.t[r] - in.t[r];
+        } else {
+          mat3_mul(Rt, pv.R, o.Ar);  // R_cur^T R_prev
+          double d[3] = {pv.t[0] - in.t[0], pv.t[1] - in.t[1], pv.t[2] - in.t[2]};
+          for (int r = 0; r < 3; ++r) o.br[r] = Rt[3 * r] * d[0] + Rt[3 * r + 1] * d[1] + Rt[3 * r + 2] * d[2];
+          if (!mat3_is_identity(o.Ar)) { o.flags |= PSF_ROT_IN_R; features |= FEAT_ROT; }
+        }
+      } else {
+        for (int i = 0; i < 9; ++i) o.Ar[i] = o.Ag[i];
+        for (int r = 0; r < 3; ++r) o.br[r] = o.bg[r];
+        if (rotated) o.flags |= PSF_ROT_IN_R;
+      }
+      prev = s;
+    }
+
+    // ---- geometry ----------------------------------------------------------
+    o.radius = in.radius; o.conic = in.conic; o.kp1 = 1.0 + in.conic;
+    o.tol = in.tol;
+    o.coat_t = in.coat_t; o.coat_r = in.coat_r;
+    o.inv_norm = 1.0;
+    if (in.kind == OLB_GEOM_PLANE || in.kind == OLB_GEOM_NOOP) { o.radius = INFINITY; o.curv = 0; }
+    else if (std::isinf(in.radius)) { o.curv = 0; o.flags |= PSF_RADIUS_INF; }
+    else { o.curv = 1.0 / in.radius; }
+    const bool newton = in.kind >= OLB_GEOM_EVEN_ASPHERE;
+    if (newton) {
+      features |= FEAT_NEWTON;
+      if (in.max_iter < 0) { res.error = "negative max_iter"; return res; }
+    }
+    if (in.kind == OLB_GEOM_EVEN_ASPHERE || in.kind == OLB_GEOM_ODD_ASPHERE) {
+      if (!in_pool(in.coef_off, in.n_coef)) { res.error = "coefficient block outside pool"; return res; }
+      o.n_coef = in.n_coef;
+      o.coef_off = (int)pool.size();
+      for (int i = 0; i < in.n_coef; ++i) pool.push_back(tab.pool[in.coef_off + i]);
+      while (pool.size() % 4) pool.push_back(0);
+    } else if (in.kind == OLB_GEOM_POLYNOMIAL) {
+      const int cols = in.aux0 > 0 ? in.aux0 : 1;
+      if (in.n_coef % cols || !in_pool(in.coef_off, in.n_coef)) { res.error = "bad polynomial block"; return res; }
+      o.poly_rows = in.n_coef / cols; o.poly_cols = cols;
+      if (o.poly_rows > 24 || cols > 24) { res.error = "polynomial order too high (max 23)"; return res; }
+      o.coef_off = (int)pool.size();
+      for (int i = 0; i < in.n_coef; ++i) pool.push_back(tab.pool[in.coef_off + i]);
+      while (pool.size() % 4) pool.push_back(0);
+      o.poly_d_off = o.coef_off;  // derivative of the same polynomial (polynomial.py:123-155)
+      o.inv_norm = 1.0;
+    } else if (in.kind == OLB_GEOM_ZERNIKE) {
+      if (!in_pool(in.coef_off, 4 * in.n_coef)) { res.error = "Zernike block outside pool"; return res; }
+      if (!(in.norm_radius > 0)) { res.error = "Zernike norm_radius must be positive"; return res; }
+      int deg = 0;
+      for (int i = 0; i < in.n_coef; ++i) {
+        const double* tm = tab.pool + in.coef_off + 4 * i;
+        int n = (int)tm[0], m = (int)tm[1];
+        if (n < 0 || (m < 0 ? -m : m) > n || ((n - m) & 1) || n > 23) { res.error = "bad Zernike (n, m)"; return res; }
+        if (n > deg) deg = n;
+      }
+      const int W = deg + 1;
+      std::vector<double> S(W * W, 0.0), D(W * W, 0.0);
+      for (int i = 0; i < in.n_coef; ++i) {
+        const double* tm = tab.pool + in.coef_off + 4 * i;
+        zernike_add_monomials((int)tm[0], (int)tm[1], tm[2], deg, S.data());  // c * N_nm
+        zernike_add_monomials((int)tm[0], (int)tm[1], tm[3], deg, D.data());  // c (quirk: no N_nm)
+      }
+      o.poly_rows = W; o.poly_cols = W; o.flags |= PSF_POLY_TRI;
+      o.coef_off = (int)pool.size();
+      pool.insert(pool.end(), S.begin(), S.end());
+      while (pool.size() % 4) pool.push_back(0);
+      o.poly_d_off = (int)pool.size();
+      pool.insert(pool.end(), D.begin(), D.end());
+      while (pool.size() % 4) pool.push_back(0);
+      o.inv_norm = 1.0 / in.norm_radius;
+    }
+
+    // ---- aperture ------------------------------------------------------------
+    if (in.flags & OLB_SF_APERTURE) {
+      if (!in_pool(in.aper_off, in.aper_len) || in.aper_len < 1) { res.error = "aperture program outside pool"; return res; }
+      int i = 0, depth = 0;
+      while (i < in.aper_len) {
+        int op = (int)tab.pool[in.aper_off + i];
+        int nops = aperture_operands(op);
+        if (nops < 0) { res.error = "bad aperture opcode"; return res; }
+        if (op >= OLB_AP_UNION) { if (depth < 2) { res.error = "aperture stack underflow"; return res; } depth -= 1; }
+        else { depth += 1; if (depth > 8) { res.error = "aperture program too deep"; return res; } }
+        i += 1 + nops;
+      }
+      if (i != in.aper_len || depth != 1) { res.error = "malformed aperture program"; return res; }
+      o.aper_off = (int)pool.size();
+      o.aper_len = in.aper_len;
+      for (int k = 0; k < in.aper_len; ++k) pool.push_back(tab.pool[in.aper_off + k]);
+      while (pool.size() % 4) pool.push_back(0);
+      if ((int)tab.pool[in.aper_off] == OLB_AP_RADIAL && in.aper_len == 3) {
+        o.flags |= PSF_APER_RADIAL;
+        // store squared radii right after the program for the fast path
+        double rmax = tab.pool[in.aper_off + 1], rmin = tab.pool[in.aper_off + 2];
+        pool[o.aper_off + 1] = rmax * rmax;  // reference compares r2 <= r_max**2 (radial.py:68-69)
+        pool[o.aper_off + 2] = rmin * rmin;
+      } else {
+        features |= FEAT_EXTRA;
+      }
+    }
+
+    // ---- media -----------------------------------------------------------------
+    if (!in_pool(in.media_off, 5 * n_wl)) { res.error = "media block outside pool"; return res; }
+    o.media_off = (int)pool.size();
+    bool absorbing = false;
+    for (int j = 0; j < n_wl; ++j) {
+      const double n1 = tab.pool[in.media_off + 0 * n_wl + j];
+      const double n2 = tab.pool[in.media_off + 1 * n_wl + j];
+      const double k1 = tab.pool[in.media_off + 2 * n_wl + j];
+      const double c1 = tab.pool[in.media_off + 3 * n_wl + j];
+      const double c2 = tab.pool[in.media_off + 4 * n_wl + j];
+      if (k1 > 0) absorbing = true;
+      pool.push_back(n1);
+      pool.push_back(n1 / n2);
+      pool.push_back(4.0 * M_PI * k1 / tab.wavelengths[j] * 1e3);
+      pool.push_back(c2 / c1);
+    }
+    if (absorbing) { o.flags |= OLB_SF_ABSORBING; features |= FEAT_EXTRA; }
+    else o.flags &= ~uint32_t(OLB_SF_ABSORBING);
+    if (in.coating == OLB_COAT_SIMPLE) features |= FEAT_EXTRA;
+    else if (in.coating == OLB_COAT_FRESNEL) features |= FEAT_POL;
+    else if (in.coating != OLB_COAT_NONE) { res.error = "unknown coating"; return res; }
+  }
+  res.features = features;
+  build_blob<double>(tab, pools, ps, features, res.blob_f64);
+  build_blob<float>(tab, pools, ps, features, res.blob_f32);
+  return res;
+}
+
+}  // namespace olb
+#endif  // OLB_PREP_H_

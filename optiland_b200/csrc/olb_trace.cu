@@ -1,0 +1,532 @@
+// olb_trace.cu -- sm_100a trace kernel + the C ABI of include/olb.h.
+//
+// One persistent kernel walks the WHOLE surface list for a tile of rays: the ray state
+// lives in registers from launch state to image surface, the prepared surface table
+// lives in shared memory (one TMA bulk copy per CTA), and the only HBM traffic is the
+// algorithmic minimum -- 7-8 coalesced vector loads per ray and 8 streaming vector
+// stores per ray per recorded surface.  The reference does the
+// same work with ~190 eager element-wise launches per surface.
+//
+// No tensor cores: there is no contraction on this path.  The roofline is HBM.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/olb.h"
+#include "olb_math.cuh"
+#include "olb_prep.h"
+
+namespace olb {
+
+static constexpr int BLOCK = 256;
+
+static thread_local std::string g_last_error;
+static std::atomic<int64_t> g_launches{0};
+
+static int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+#define OLB_CUDA(call)                                                                    \
+  do {                                                                                    \
+    cudaError_t e__ = (call);                                                             \
+    if (e__ != cudaSuccess)                                                               \
+      return fail(OLB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));     \
+  } while (0)
+
+// Device workspace layout: [64-byte pad][blob f64][blob f32], each 16-byte aligned.
+static constexpr uint32_t WS_MAGIC = 0x4f4c4231u;  // "OLB1"
+
+struct TraceArgs {
+  const unsigned char* blob;  // prepared table for this element type (device)
+  int32_t blob_bytes;
+  int32_t first, last;
+  uint32_t tflags;
+  int64_t n_rays;
+  int64_t rec_stride;
+  void* x; void* y; void* z; void* L; void* M; void* N; void* i; void* w; void* opd;
+  void* L0; void* M0; void* N0; void* p;
+  void* rx; void* ry; void* rz; void* rL; void* rM; void* rN; void* ri; void* ropd;
+  int32_t* status;
+};
+
+// ---- vector access helpers -------------------------------------------------------------
+template <typename T, int RPT> struct Vec;
+template <> struct Vec<float, 4> { using type = float4; };
+template <> struct Vec<float, 2> { using type = float2; };
+template <> struct Vec<double, 2> { using type = double2; };
+
+template <typename T, int RPT>
+__device__ __forceinline__ void load_rays(const T* __restrict__ p, int64_t base, int valid, T (&v)[RPT]) {
+  if constexpr (RPT == 1) {
+    v[0] = __ldcs(p + base);
+  } else {
+    if (valid == RPT) {
+      using V = typename Vec<T, RPT>::type;
+      V q = __ldcs(reinterpret_cast<const V*>(p + base));
+      const T* e = reinterpret_cast<const T*>(&q);
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) v[k] = e[k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) v[k] = k < valid ? __ldcs(p + base + k) : (T)0;
+    }
+  }
+}
+template <typename T, int RPT>
+__device__ __forceinline__ void store_rays(T* __restrict__ p, int64_t base, int valid, const T (&v)[RPT]) {
+  if constexpr (RPT == 1) {
+    __stcs(p + base, v[0]);
+  } else {
+    if (valid == RPT) {
+      using V = typename Vec<T, RPT>::type;
+      V q;
+      T* e = reinterpret_cast<T*>(&q);
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) e[k] = v[k];
+      __stcs(reinterpret_cast<V*>(p + base), q);
+    } else {
+#pragma unroll
+      for (int k = 0; k < RPT; ++k)
+        if (k < valid) __stcs(p + base + k, v[k]);
+    }
+  }
+}
+
+// ---- TMA bulk copy of the prepared table into shared memory ------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void stage_table(unsigned char* smem, const unsigned char* gsrc, uint32_t bytes,
+                                            uint64_t* bar) {
+  const uint32_t bar_a = smem_u32(bar);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(smem)),
+        "l"(gsrc), "r"(bytes), "r"(bar_a)
+        : "memory");
+  }
+  // every thread waits for the bytes to land (phase 0)
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar_a)
+        : "memory");
+  }
+}
+
+// ---- the kernel -----------------------------------------------------------------------------
+template <typename T, int RPT, uint32_t FEAT>
+__global__ void __launch_bounds__(BLOCK) trace_kernel(const __grid_constant__ TraceArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+  unsigned char* tab = smem + 16;
+  stage_table(tab, a.blob, (uint32_t)a.blob_bytes, bar);
+
+  const PrepHeader* H = reinterpret_cast<const PrepHeader*>(tab);
+  const PrepSurface<T>* surf = reinterpret_cast<const PrepSurface<T>*>(tab + sizeof(PrepHeader));
+  const T* pool = reinterpret_cast<const T*>(surf + H->n_surf);
+  const int n_wl = H->n_wl;
+  const T* wl = pool + H->pad[0];
+
+  const int64_t n = a.n_rays;
+  const int64_t per_tile = (int64_t)BLOCK * RPT;
+  const int64_t n_tiles = (n + per_tile - 1) / per_tile;
+  const int first = a.first, last = a.last;
+  int status = 0;
+
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t base = (tile * BLOCK + threadIdx.x) * RPT;
+    if (base >= n) continue;
+    const int valid = (n - base) >= RPT ? RPT : (int)(n - base);
+
+    Ray<T> r[RPT];
+    {
+      T v[RPT];
+      load_rays<T, RPT>((const T*)a.x, base, valid, v);
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) r[k].x = v[k];
+      load_rays<T, RPT>((const T*)a.y, base, valid, v);
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) r[k].y = v[k];
+      load_rays<T, RPT>((const T*)a.z, base, valid, v);
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) r[k].z = v[k];
+      load_rays<T, RPT>((const T*)a.L, base, valid, v);
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) r[k].L = v[k];
+      load_rays<T, RPT>((const T*)a.M, base, valid, v);
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) r[k].M = v[k];
+      load_rays<T, RPT>((const T*)a.N, base, valid, v);
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) r[k].N = v[k];
+      load_rays<T, RPT>((const T*)a.i, base, valid, v);
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) r[k].i = v[k];
+      load_rays<T, RPT>((const T*)a.opd, base, valid, v);
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) { r[k].opd = v[k]; r[k].opd_lo = 0; r[k].widx = 0; r[k].L0 = r[k].M0 = r[k].N0 = 0; }
+      if (n_wl > 1) {
+        load_rays<T, RPT>((const T*)a.w, base, valid, v);
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+          int idx = -1;
+          for (int j = 0; j < n_wl; ++j)
+            if (v[k] == wl[j]) idx = j;
+          r[k].widx = idx;
+        }
+      }
+    }
+
+    bool have_frame = false;  // false: registers hold GLOBAL coordinates
+    T gx[RPT], gy[RPT], gz[RPT], gL[RPT], gM[RPT], gN[RPT];
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) { gx[k] = r[k].x; gy[k] = r[k].y; gz[k] = r[k].z; gL[k] = r[k].L; gM[k] = r[k].M; gN[k] = r[k].N; }
+
+    for (int s = first; s < last; ++s) {
+      const PrepSurface<T>& S = surf[s];
+      const bool noop = S.kind == OLB_GEOM_NOOP;
+      if (!noop) {
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) surface_step<T, FEAT>(r[k], S, pool, !have_frame, status);
+        have_frame = true;
+      }
+      const bool record = a.rx != nullptr && !(S.flags & OLB_SF_NORECORD);
+      if (record || s == last - 1) {
+        if (!noop) {
+#pragma unroll
+          for (int k = 0; k < RPT; ++k) to_global<T, FEAT>(r[k], S, gx[k], gy[k], gz[k], gL[k], gM[k], gN[k]);
+        }
+      }
+      if (record) {
+        const int64_t off = (int64_t)(s - first) * a.rec_stride + base;
+        T v[RPT];
+        store_rays<T, RPT>((T*)a.rx, off, valid, gx);
+        store_rays<T, RPT>((T*)a.ry, off, valid, gy);
+        store_rays<T, RPT>((T*)a.rz, off, valid, gz);
+        store_rays<T, RPT>((T*)a.rL, off, valid, gL);
+        store_rays<T, RPT>((T*)a.rM, off, valid, gM);
+        store_rays<T, RPT>((T*)a.rN, off, valid, gN);
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) v[k] = r[k].i;
+        store_rays<T, RPT>((T*)a.ri, off, valid, v);
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) v[k] = opd_value(r[k]);
+        store_rays<T, RPT>((T*)a.ropd, off, valid, v);
+      }
+    }
+
+    if (!(a.tflags & OLB_TF_NO_FINAL)) {
+      T v[RPT];
+      store_rays<T, RPT>((T*)a.x, base, valid, gx);
+      store_rays<T, RPT>((T*)a.y, base, valid, gy);
+      store_rays<T, RPT>((T*)a.z, base, valid, gz);
+      store_rays<T, RPT>((T*)a.L, base, valid, gL);
+      store_rays<T, RPT>((T*)a.M, base, valid, gM);
+      store_rays<T, RPT>((T*)a.N, base, valid, gN);
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) v[k] = r[k].i;
+      store_rays<T, RPT>((T*)a.i, base, valid, v);
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) v[k] = opd_value(r[k]);
+      store_rays<T, RPT>((T*)a.opd, base, valid, v);
+    }
+    if constexpr ((FEAT & FEAT_EXTRA) != 0) {
+      if (a.L0 != nullptr) {
+        T v[RPT];
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) v[k] = r[k].L0;
+        store_rays<T, RPT>((T*)a.L0, base, valid, v);
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) v[k] = r[k].M0;
+        store_rays<T, RPT>((T*)a.M0, base, valid, v);
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) v[k] = r[k].N0;
+        store_rays<T, RPT>((T*)a.N0, base, valid, v);
+      }
+    }
+  }
+  if (status != 0 && a.status != nullptr) atomicOr(a.status, status);
+}
+
+// ---- launcher -------------------------------------------------------------------------------
+template <typename T, int RPT, uint32_t FEAT>
+static int launch_instance(const TraceArgs& a, cudaStream_t stream) {
+  auto kern = trace_kernel<T, RPT, FEAT>;
+  const size_t smem = 16 + (size_t)a.blob_bytes;
+  static thread_local int cached_dev = -1;
+  static thread_local int num_sms = 0;
+  static thread_local int blocks_per_sm = 0;
+  static thread_local size_t cached_smem = 0;
+  int dev = 0;
+  OLB_CUDA(cudaGetDevice(&dev));
+  if (dev != cached_dev || smem != cached_smem) {
+    if (smem > 48 * 1024) {
+      OLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    OLB_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    OLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, BLOCK, smem));
+    if (blocks_per_sm < 1) return fail(OLB_ERR_CUDA, "kernel does not fit on an SM (table too large?)");
+    cached_dev = dev;
+    cached_smem = smem;
+  }
+  const int64_t per_tile = (int64_t)BLOCK * RPT;
+  const int64_t n_tiles = (a.n_rays + per_tile - 1) / per_tile;
+  int64_t grid = (int64_t)num_sms * blocks_per_sm;  // persistent: one wave of resident CTAs
+  if (grid > n_tiles) grid = n_tiles;
+  if (grid < 1) return OLB_OK;
+  kern<<<(unsigned)grid, BLOCK, smem, stream>>>(a);
+  OLB_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return OLB_OK;
+}
+
+template <typename T, int RPT>
+static int launch_feat(const TraceArgs& a, uint32_t features, cudaStream_t stream) {
+  if (features & FEAT_POL) return fail(OLB_ERR_UNSUPPORTED, "polarized trace not built in this version");
+  if ((features & (FEAT_ROT | FEAT_EXTRA)) != 0)
+    return launch_instance<T, RPT, FEAT_ROT | FEAT_NEWTON | FEAT_EXTRA>(a, stream);
+  if (features & FEAT_NEWTON) return launch_instance<T, RPT, FEAT_NEWTON>(a, stream);
+  return launch_instance<T, RPT, 0u>(a, stream);
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+template <typename T>
+static int trace_impl(const OlbDeviceTable* wh, int32_t first, int32_t last, const OlbRays* rays,
+                      const OlbRecords* rec, int64_t n_rays, uint32_t flags, int32_t* status,
+                      cudaStream_t stream) {
+  if (!wh || wh->magic != WS_MAGIC || !wh->workspace)
+    return fail(OLB_ERR_INVALID_ARG, "table handle was not initialised by olb_table_upload");
+  const unsigned char* workspace_dev = (const unsigned char*)wh->workspace;
+  if (!rays) return fail(OLB_ERR_INVALID_ARG, "rays is NULL");
+  if (n_rays < 0) return fail(OLB_ERR_INVALID_ARG, "n_rays < 0");
+  if (first < 0 || last > wh->n_surfaces || first > last) return fail(OLB_ERR_INVALID_ARG, "bad surface range");
+  if (n_rays == 0 || first == last) return OLB_OK;
+  void* req[] = {rays->x, rays->y, rays->z, rays->L, rays->M, rays->N, rays->i, rays->opd};
+  for (void* p : req) {
+    if (!p) return fail(OLB_ERR_INVALID_ARG, "a required ray array is NULL");
+    if (!aligned16(p)) return fail(OLB_ERR_ALIGNMENT, "ray array not 16-byte aligned");
+  }
+  if (wh->n_wl > 1) {
+    if (!rays->w) return fail(OLB_ERR_INVALID_ARG, "rays.w is NULL but the table has several wavelengths");
+    if (!aligned16(rays->w)) return fail(OLB_ERR_ALIGNMENT, "rays.w not 16-byte aligned");
+  }
+  TraceArgs a{};
+  a.blob = workspace_dev + (sizeof(T) == 8 ? wh->off_f64 : wh->off_f32);
+  a.blob_bytes = sizeof(T) == 8 ? wh->bytes_f64 : wh->bytes_f32;
+  a.first = first; a.last = last; a.tflags = flags; a.n_rays = n_rays;
+  a.x = rays->x; a.y = rays->y; a.z = rays->z; a.L = rays->L; a.M = rays->M; a.N = rays->N;
+  a.i = rays->i; a.w = rays->w; a.opd = rays->opd;
+  a.L0 = rays->L0; a.M0 = rays->M0; a.N0 = rays->N0; a.p = rays->p;
+  a.status = status;
+  uint32_t features = wh->features;
+  if (flags & OLB_TF_POLARIZED) features |= FEAT_POL;
+  if (rays->L0 || rays->M0 || rays->N0) {
+    if (!(rays->L0 && rays->M0 && rays->N0)) return fail(OLB_ERR_INVALID_ARG, "L0/M0/N0 must be all set or all NULL");
+    if (!aligned16(rays->L0) || !aligned16(rays->M0) || !aligned16(rays->N0))
+      return fail(OLB_ERR_ALIGNMENT, "L0/M0/N0 not 16-byte aligned");
+    features |= FEAT_EXTRA;
+  }
+  constexpr int V = sizeof(T) == 4 ? 4 : 2;
+  bool vec_ok = true;
+  if (rec) {
+    void* rr[] = {rec->x, rec->y, rec->z, rec->L, rec->M, rec->N, rec->intensity, rec->opd};
+    int n_set = 0;
+    for (void* p : rr) n_set += p != nullptr;
+    if (n_set != 0 && n_set != 8)
+      return fail(OLB_ERR_INVALID_ARG, "record arrays must be all set or all NULL");
+    if (n_set == 8) {
+      for (void* p : rr)
+        if (!aligned16(p)) return fail(OLB_ERR_ALIGNMENT, "record array not 16-byte aligned");
+      if (rec->row_stride < n_rays) return fail(OLB_ERR_INVALID_ARG, "record row_stride < n_rays");
+      a.rx = rec->x; a.ry = rec->y; a.rz = rec->z; a.rL = rec->L; a.rM = rec->M; a.rN = rec->N;
+      a.ri = rec->intensity; a.ropd = rec->opd; a.rec_stride = rec->row_stride;
+      if (rec->row_stride % V) vec_ok = false;
+    }
+  }
+  if ((flags & OLB_TF_NO_FINAL) && !a.rx)
+    return fail(OLB_ERR_INVALID_ARG, "OLB_TF_NO_FINAL needs record arrays (the result would be lost)");
+  if (vec_ok) return launch_feat<T, V>(a, features, stream);
+  return launch_feat<T, 1>(a, features, stream);
+}
+
+}  // namespace olb
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+using namespace olb;
+
+extern "C" {
+
+int olb_version(void) { return OLB_VERSION_MAJOR * 1000 + OLB_VERSION_MINOR; }
+
+int olb_last_error(char* buf, int buf_len) {
+  if (!buf || buf_len <= 0) return OLB_ERR_INVALID_ARG;
+  snprintf(buf, (size_t)buf_len, "%s", g_last_error.c_str());
+  return OLB_OK;
+}
+
+int64_t olb_launch_count(void) { return g_launches.load(); }
+
+int64_t olb_table_workspace_bytes(const OlbTable* table) {
+  if (!table) return fail(OLB_ERR_INVALID_ARG, "table is NULL");
+  PrepResult pr = prepare_table(*table);
+  if (!pr.error.empty()) return fail(OLB_ERR_TABLE, pr.error);
+  return (int64_t)(64 + pr.blob_f64.size() + pr.blob_f32.size());
+}
+
+int olb_table_upload(const OlbTable* table, void* workspace, int64_t workspace_bytes, void* stream,
+                     OlbDeviceTable* out) {
+  if (!table || !workspace || !out) return fail(OLB_ERR_INVALID_ARG, "table, workspace or out is NULL");
+  if (!aligned16(workspace)) return fail(OLB_ERR_ALIGNMENT, "workspace not 16-byte aligned");
+  PrepResult pr = prepare_table(*table);
+  if (!pr.error.empty()) return fail(OLB_ERR_TABLE, pr.error);
+  OlbDeviceTable h{};
+  h.workspace = workspace;
+  h.workspace_bytes = workspace_bytes;
+  h.magic = WS_MAGIC;
+  h.features = pr.features;
+  h.n_surfaces = table->n_surfaces;
+  h.n_wl = table->n_wl;
+  h.off_f64 = 64;
+  h.bytes_f64 = (int32_t)pr.blob_f64.size();
+  h.off_f32 = 64 + h.bytes_f64;
+  h.bytes_f32 = (int32_t)pr.blob_f32.size();
+  const int64_t need = 64 + (int64_t)h.bytes_f64 + h.bytes_f32;
+  if (workspace_bytes < need) return fail(OLB_ERR_INVALID_ARG, "workspace too small");
+  std::vector<unsigned char> staging((size_t)need, 0);
+  std::memcpy(staging.data() + h.off_f64, pr.blob_f64.data(), pr.blob_f64.size());
+  std::memcpy(staging.data() + h.off_f32, pr.blob_f32.data(), pr.blob_f32.size());
+  cudaStream_t st = (cudaStream_t)stream;
+  OLB_CUDA(cudaMemcpyAsync(workspace, staging.data(), (size_t)need, cudaMemcpyHostToDevice, st));
+  OLB_CUDA(cudaStreamSynchronize(st));
+  *out = h;
+  return OLB_OK;
+}
+
+int olb_trace_f32(const OlbDeviceTable* table, int32_t first, int32_t last, const OlbRays* rays,
+                  const OlbRecords* rec, int64_t n_rays, uint32_t flags, int32_t* status, void* stream) {
+  return trace_impl<float>(table, first, last, rays, rec, n_rays, flags, status, (cudaStream_t)stream);
+}
+
+int olb_trace_f64(const OlbDeviceTable* table, int32_t first, int32_t last, const OlbRays* rays,
+                  const OlbRecords* rec, int64_t n_rays, uint32_t flags, int32_t* status, void* stream) {
+  return trace_impl<double>(table, first, last, rays, rec, n_rays, flags, status, (cudaStream_t)stream);
+}
+
+// ---- host-buffer end-to-end path ---------------------------------------------------------------
+// scratch layout: 2 slots x 9 arrays (x,y,z,L,M,N,i,w,opd) x chunk elements
+int64_t olb_host_scratch_bytes(int32_t elem_size, int64_t chunk_rays) {
+  if ((elem_size != 4 && elem_size != 8) || chunk_rays < 1) return fail(OLB_ERR_INVALID_ARG, "bad scratch query");
+  const int64_t chunk_al = (chunk_rays + 63) & ~int64_t(63);
+  return 2 * 9 * chunk_al * elem_size;
+}
+
+}  // extern "C"
+
+template <typename T>
+static int trace_host_impl(const OlbDeviceTable* table, int32_t first, int32_t last, const OlbRays* h_in,
+                           const OlbRays* h_out, const OlbRecords* rec, int64_t n_rays, int64_t chunk,
+                           void* scratch, int64_t scratch_bytes, uint32_t flags, int32_t* status) {
+  if (!table || table->magic != WS_MAGIC) return fail(OLB_ERR_INVALID_ARG, "table handle was not initialised");
+  const OlbDeviceTable& wh = *table;
+  if (!h_in || !h_out || !scratch) return fail(OLB_ERR_INVALID_ARG, "NULL argument");
+  if (chunk < 1) return fail(OLB_ERR_INVALID_ARG, "chunk_rays < 1");
+  if (scratch_bytes < olb_host_scratch_bytes((int)sizeof(T), chunk)) return fail(OLB_ERR_INVALID_ARG, "scratch too small");
+  if (!aligned16(scratch)) return fail(OLB_ERR_ALIGNMENT, "scratch not 16-byte aligned");
+  const bool need_w = wh.n_wl > 1;
+  const void* in[9] = {h_in->x, h_in->y, h_in->z, h_in->L, h_in->M, h_in->N, h_in->i, h_in->w, nullptr};
+  void* out[9] = {h_out->x, h_out->y, h_out->z, h_out->L, h_out->M, h_out->N, h_out->i, nullptr, h_out->opd};
+  for (int k = 0; k < 7; ++k)
+    if (!in[k] || !out[k]) return fail(OLB_ERR_INVALID_ARG, "a required host ray array is NULL");
+  if (!out[8]) return fail(OLB_ERR_INVALID_ARG, "h_out.opd is NULL");
+  if (need_w && !in[7]) return fail(OLB_ERR_INVALID_ARG, "h_in.w is NULL but the table has several wavelengths");
+
+  const int64_t chunk_al = (chunk + 63) & ~int64_t(63);
+  T* slot[2][9];
+  for (int s = 0; s < 2; ++s)
+    for (int k = 0; k < 9; ++k) slot[s][k] = (T*)scratch + ((int64_t)s * 9 + k) * chunk_al;
+
+  cudaStream_t st[2];
+  for (int s = 0; s < 2; ++s) OLB_CUDA(cudaStreamCreateWithFlags(&st[s], cudaStreamNonBlocking));
+  int result = OLB_OK;
+  int64_t done = 0;
+  int ci = 0;
+  while (done < n_rays) {
+    const int64_t m = (n_rays - done) < chunk ? (n_rays - done) : chunk;
+    const int s = ci & 1;
+    cudaStream_t q = st[s];
+    // slot reuse is ordered by the stream itself (chunk ci and ci+2 share stream + slot)
+    for (int k = 0; k < 8; ++k) {
+      if (k == 7 && !need_w) continue;
+      cudaError_t e = cudaMemcpyAsync(slot[s][k], (const T*)in[k] + done, (size_t)m * sizeof(T), cudaMemcpyHostToDevice, q);
+      if (e != cudaSuccess) { result = fail(OLB_ERR_CUDA, cudaGetErrorString(e)); break; }
+    }
+    if (result) break;
+    cudaError_t e = cudaMemsetAsync(slot[s][8], 0, (size_t)m * sizeof(T), q);
+    if (e != cudaSuccess) { result = fail(OLB_ERR_CUDA, cudaGetErrorString(e)); break; }
+    OlbRays d{};
+    d.x = slot[s][0]; d.y = slot[s][1]; d.z = slot[s][2]; d.L = slot[s][3]; d.M = slot[s][4]; d.N = slot[s][5];
+    d.i = slot[s][6]; d.w = need_w ? slot[s][7] : nullptr; d.opd = slot[s][8];
+    OlbRecords rr{};
+    const OlbRecords* rp = nullptr;
+    if (rec && rec->x) {
+      rr = *rec;
+      rr.x = (T*)rec->x + done; rr.y = (T*)rec->y + done; rr.z = (T*)rec->z + done;
+      rr.L = (T*)rec->L + done; rr.M = (T*)rec->M + done; rr.N = (T*)rec->N + done;
+      rr.intensity = (T*)rec->intensity + done; rr.opd = (T*)rec->opd + done;
+      rp = &rr;
+    }
+    result = trace_impl<T>(&wh, first, last, &d, rp, m, flags & ~uint32_t(OLB_TF_NO_FINAL), status, q);
+    if (result) break;
+    for (int k = 0; k < 9; ++k) {
+      if (k == 7) continue;
+      e = cudaMemcpyAsync((T*)out[k] + done, slot[s][k], (size_t)m * sizeof(T), cudaMemcpyDeviceToHost, q);
+      if (e != cudaSuccess) { result = fail(OLB_ERR_CUDA, cudaGetErrorString(e)); break; }
+    }
+    if (result) break;
+    done += m;
+    ++ci;
+  }
+  for (int s = 0; s < 2; ++s) {
+    cudaError_t e = cudaStreamSynchronize(st[s]);
+    if (e != cudaSuccess && !result) result = fail(OLB_ERR_CUDA, cudaGetErrorString(e));
+    cudaStreamDestroy(st[s]);
+  }
+  return result;
+}
+
+extern "C" {
+
+int olb_trace_host_f32(const OlbDeviceTable* table, int32_t first, int32_t last, const OlbRays* h_in,
+                       const OlbRays* h_out, const OlbRecords* rec, int64_t n_rays, int64_t chunk_rays,
+                       void* dev_scratch, int64_t dev_scratch_bytes, uint32_t flags, int32_t* status) {
+  return trace_host_impl<float>(table, first, last, h_in, h_out, rec, n_rays, chunk_rays, dev_scratch,
+                                dev_scratch_bytes, flags, status);
+}
+int olb_trace_host_f64(const OlbDeviceTable* table, int32_t first, int32_t last, const OlbRays* h_in,
+                       const OlbRays* h_out, const OlbRecords* rec, int64_t n_rays, int64_t chunk_rays,
+                       void* dev_scratch, int64_t dev_scratch_bytes, uint32_t flags, int32_t* status) {
+  return trace_host_impl<double>(table, first, last, h_in, h_out, rec, n_rays, chunk_rays, dev_scratch,
+                                 dev_scratch_bytes, flags, status);
+}
+
+}  // extern "C"

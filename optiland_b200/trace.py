@@ -1,0 +1,220 @@
+"""Host-side mirror of the reference's interface for the hot path.
+
+Names, argument meaning and error behaviour follow the reference so that the parity tests
+read like the reference's own:
+
+* ``RealRays``      <- optiland/rays/real_rays.py:23-89   (SoA container, same attribute names)
+* ``SurfaceGroup``  <- optiland/surfaces/surface_group.py:27, ``trace(rays, skip=0)`` :245-257 and
+  the stacked record properties ``x, y, z, L, M, N, opd, intensity`` :108-153
+
+Everything numeric happens in libolb.so (sm_100a CUDA) through the C ABI; torch is used only
+to own device memory and streams.  There is no CPU path: constructing these objects on a
+box without CUDA or without the built library raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import table as T
+
+_REC_KEYS = ("x", "y", "z", "L", "M", "N", "intensity", "opd")
+_DTYPES = {torch.float32: "f32", torch.float64: "f64"}
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise _lib.OlbError("optiland_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+def _as_dev(v, n, dtype, device):
+    t = torch.as_tensor(v, dtype=dtype, device=device)
+    if t.ndim == 0:
+        t = t.expand(n)
+    t = t.reshape(-1).contiguous()
+    if t.data_ptr() % 16:
+        t = t.clone()
+    return t
+
+
+class RealRays:
+    """Device-resident ray batch (structure of arrays), reference attribute names."""
+
+    def __init__(self, x, y, z, L, M, N, intensity, wavelength, dtype=torch.float32, device=None):
+        _require_cuda()
+        if dtype not in _DTYPES:
+            raise ValueError("dtype must be torch.float32 or torch.float64")
+        device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        n = max(int(np.size(v)) if not torch.is_tensor(v) else v.numel()
+                for v in (x, y, z, L, M, N, intensity, wavelength))
+        self.x = _as_dev(x, n, dtype, device)
+        self.y = _as_dev(y, n, dtype, device)
+        self.z = _as_dev(z, n, dtype, device)
+        self.L = _as_dev(L, n, dtype, device)
+        self.M = _as_dev(M, n, dtype, device)
+        self.N = _as_dev(N, n, dtype, device)
+        self.i = _as_dev(intensity, n, dtype, device)
+        self.w = _as_dev(wavelength, n, dtype, device)
+        self.opd = torch.zeros_like(self.x)
+        self.L0 = self.M0 = self.N0 = None
+        self.is_normalized = True
+
+    def __len__(self):
+        return self.x.numel()
+
+    @property
+    def dtype(self):
+        return self.x.dtype
+
+    @property
+    def device(self):
+        return self.x.device
+
+
+class DeviceTable:
+    """A ``SurfaceTable`` prepared and resident on one GPU (olb_table_upload)."""
+
+    def __init__(self, table: T.SurfaceTable, device=None):
+        _require_cuda()
+        self.lib = _lib.load()
+        self.table = table
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.host = _lib.HostTable(table)
+        nbytes = self.lib.olb_table_workspace_bytes(C.byref(self.host.c))
+        if nbytes < 0:
+            _lib.check(int(nbytes), "olb_table_workspace_bytes")
+        self.workspace = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        self.c = _lib.OlbDeviceTable()
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            rc = self.lib.olb_table_upload(C.byref(self.host.c), self.workspace.data_ptr(), int(nbytes),
+                                           C.c_void_p(stream), C.byref(self.c))
+        _lib.check(rc, "olb_table_upload")
+        self.has_zernike = any(s.kind == T.GEOM_ZERNIKE for s in table.surfaces)
+
+    @property
+    def features(self) -> int:
+        return int(self.c.features)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def trace_device(dtab: DeviceTable, rays: RealRays, first: int, last: int, record: bool = True,
+                 want_l0: bool = False):
+    """One call of olb_trace_f32/f64.  Returns the dict of (rows, N) record tensors (or None).
+
+    With ``record`` the final state is NOT written a second time: ``rays.x`` .. ``rays.opd``
+    become views of the last record row (OLB_TF_NO_FINAL), saving 32-64 B/ray of HBM traffic.
+    The reference never mutates these arrays in place (it re-assigns attributes), so the
+    aliasing is not observable through its API.
+    """
+    lib = dtab.lib
+    n = len(rays)
+    sfx = _DTYPES[rays.dtype]
+    fn = getattr(lib, f"olb_trace_{sfx}")
+    if rays.device != dtab.device:
+        raise ValueError(f"rays on {rays.device}, table on {dtab.device}")
+    rows = last - first
+    recs = None
+    c_rec = None
+    flags = 0
+    if record and rows > 0:
+        vec = 4 if rays.dtype == torch.float32 else 2
+        stride = (n + 63) // 64 * 64 if n % vec else n
+        buf = torch.empty((8, rows, stride), dtype=rays.dtype, device=rays.device)
+        recs = {k: buf[j, :, :n] for j, k in enumerate(_REC_KEYS)}
+        c_rec = _lib.OlbRecords(*[buf[j].data_ptr() for j in range(8)], stride)
+        flags |= _lib.TF_NO_FINAL
+    if want_l0:
+        rays.L0 = torch.empty_like(rays.x)
+        rays.M0 = torch.empty_like(rays.x)
+        rays.N0 = torch.empty_like(rays.x)
+    c_rays = _lib.OlbRays(
+        x=rays.x.data_ptr(), y=rays.y.data_ptr(), z=rays.z.data_ptr(), L=rays.L.data_ptr(),
+        M=rays.M.data_ptr(), N=rays.N.data_ptr(), i=rays.i.data_ptr(),
+        w=rays.w.data_ptr() if dtab.table.n_wl > 1 else None, opd=rays.opd.data_ptr(),
+        L0=rays.L0.data_ptr() if want_l0 else None, M0=rays.M0.data_ptr() if want_l0 else None,
+        N0=rays.N0.data_ptr() if want_l0 else None, p=None)
+    status = torch.zeros(1, dtype=torch.int32, device=rays.device) if dtab.has_zernike else None
+    with torch.cuda.device(rays.device):
+        stream = torch.cuda.current_stream(rays.device).cuda_stream
+        rc = fn(C.byref(dtab.c), first, last, C.byref(c_rays), C.byref(c_rec) if c_rec is not None else None,
+                n, flags, _ptr(status), C.c_void_p(stream))
+    _lib.check(rc, f"olb_trace_{sfx}")
+    if status is not None and int(status.item()) & T.ST_ZERNIKE_RANGE:
+        # same exception, same message as optiland/geometries/zernike.py:254-266
+        raise ValueError(
+            "Zernike coordinates must be normalized to [-1, 1]. Consider updating the normalization "
+            "radius to 1.1x the surface aperture.")
+    if recs is not None:
+        rays.x, rays.y, rays.z = recs["x"][-1], recs["y"][-1], recs["z"][-1]
+        rays.L, rays.M, rays.N = recs["L"][-1], recs["M"][-1], recs["N"][-1]
+        rays.i, rays.opd = recs["intensity"][-1], recs["opd"][-1]
+    return recs
+
+
+class SurfaceGroup:
+    """The traced part of the reference's ``SurfaceGroup``: ``trace`` + stacked records."""
+
+    def __init__(self, table: T.SurfaceTable, device=None):
+        self.table = table
+        self.device_table = DeviceTable(table, device)
+        self._rec = None
+
+    @property
+    def num_surfaces(self) -> int:
+        return self.table.num_surfaces
+
+    def trace(self, rays: RealRays, skip: int = 0, stop: int | None = None, record: bool = True):
+        """``SurfaceGroup.trace(rays, skip)`` (surface_group.py:245-257); ``stop`` bounds the range
+        (exclusive) for the per-surface callers (ray_aiming/iterative.py:366)."""
+        last = self.num_surfaces if stop is None else stop
+        if not 0 <= skip <= last <= self.num_surfaces:
+            raise ValueError("bad surface range")
+        self._rec = trace_device(self.device_table, rays, skip, last, record=record)
+        return rays
+
+    def _get(self, key):
+        if self._rec is None:
+            raise RuntimeError("no records: call trace(..., record=True) first")
+        return self._rec[key]
+
+    x = property(lambda self: self._get("x"))
+    y = property(lambda self: self._get("y"))
+    z = property(lambda self: self._get("z"))
+    L = property(lambda self: self._get("L"))
+    M = property(lambda self: self._get("M"))
+    N = property(lambda self: self._get("N"))
+    opd = property(lambda self: self._get("opd"))
+    intensity = property(lambda self: self._get("intensity"))
+
+
+def trace_host(dtab: DeviceTable, h_in: dict, h_out: dict, n: int, dtype=torch.float32, chunk: int = 1 << 20,
+               scratch: torch.Tensor | None = None, rec=None, first: int = 0, last: int | None = None):
+    """olb_trace_host_*: HOST SoA in (pinned tensors x,y,z,L,M,N,i[,w]) -> HOST final state out
+    (x,y,z,L,M,N,i,opd); chunks are pipelined H2D / kernel / D2H on two streams."""
+    lib = dtab.lib
+    sfx = _DTYPES[dtype]
+    es = 4 if dtype == torch.float32 else 8
+    last = dtab.table.num_surfaces if last is None else last
+    need = int(lib.olb_host_scratch_bytes(es, chunk))
+    if scratch is None or scratch.numel() < need:
+        scratch = torch.empty(need, dtype=torch.uint8, device=dtab.device)
+    c_in = _lib.OlbRays(**{k: h_in[k].data_ptr() for k in ("x", "y", "z", "L", "M", "N", "i")},
+                        w=h_in["w"].data_ptr() if "w" in h_in and dtab.table.n_wl > 1 else None)
+    c_out = _lib.OlbRays(**{k: h_out[k].data_ptr() for k in ("x", "y", "z", "L", "M", "N", "i", "opd")})
+    c_rec = None
+    if rec is not None:
+        c_rec = _lib.OlbRecords(*[rec[j].data_ptr() for j in range(8)], rec.shape[-1])
+    with torch.cuda.device(dtab.device):
+        rc = getattr(lib, f"olb_trace_host_{sfx}")(
+            C.byref(dtab.c), first, last, C.byref(c_in), C.byref(c_out),
+            C.byref(c_rec) if c_rec is not None else None, n, chunk, C.c_void_p(scratch.data_ptr()),
+            scratch.numel(), 0, None)
+    _lib.check(rc, f"olb_trace_host_{sfx}")
+    return scratch

@@ -1,0 +1,334 @@
+"""TEST INFRASTRUCTURE ONLY -- generate tests/golden/*.npz from the UNMODIFIED reference.
+
+Run in the build container (where /root/reference exists):
+
+    python -m oracle.make_golden
+
+Each fixture holds, for one optical system and one seeded ray batch:
+  * the packed surface table (``optiland_b200.pack.pack_surface_group`` of the LIVE
+    reference objects -> ``SurfaceTable.to_arrays``),
+  * the launch rays the reference generated (x,y,z,L,M,N,i,w),
+  * what the reference's own ``SurfaceGroup.trace`` produced with the NumPy backend
+    (fp64): the stacked per-surface records and the final ray state,
+  * (polarized case) the P matrices and the final intensity.
+Nothing here is a restatement: the outputs come from the reference's code path
+(optiland/surfaces/surface_group.py:245-257).  The GPU box has no reference; it reads
+these files.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle.ref_import import import_reference  # noqa: E402
+
+import_reference()
+
+import optiland.backend as be  # noqa: E402
+from optiland import optic as _optic  # noqa: E402
+from optiland import physical_apertures as pa  # noqa: E402
+from optiland.coatings import SimpleCoating  # noqa: E402
+from optiland.materials import IdealMaterial  # noqa: E402
+from optiland.rays import PolarizationState, RealRays  # noqa: E402
+from optiland.samples.objectives import CookeTriplet, DoubleGauss, ReverseTelephoto  # noqa: E402
+from optiland.samples.simple import AsphericSinglet  # noqa: E402
+from optiland.samples.telescopes import HubbleTelescope  # noqa: E402
+
+from optiland_b200.pack import launch_scalars, pack_surface_group  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+REC = ("x", "y", "z", "L", "M", "N", "intensity", "opd")
+
+
+def disk(n, seed=0, rmax=1.0):
+    rng = np.random.default_rng(seed)
+    r = rmax * np.sqrt(rng.random(n))
+    th = 2 * np.pi * rng.random(n)
+    return r * np.cos(th), r * np.sin(th)
+
+
+def run_case(name, lens, rays, wavelengths, extra=None, polarized=False, expect_error=None):
+    """Trace `rays` through lens.surfaces with the reference and save everything."""
+    inp = {k: np.array(getattr(rays, k), dtype=np.float64) for k in "xyzLMNiw"}
+    tab = pack_surface_group(lens.surfaces, wavelengths)
+    out = dict(tab.to_arrays())
+    for k, v in inp.items():
+        out["in_" + k] = v
+    err = ""
+    try:
+        lens.surfaces.trace(rays)
+    except ValueError as e:  # Zernike range check raises in the reference
+        err = str(e)
+        if expect_error is None:
+            raise
+    out["ref_error"] = np.array(err)
+    if not err:
+        S = lens.surfaces
+        for k in REC:
+            out["rec_" + k] = np.array(getattr(S, k), dtype=np.float64)
+        for k in "xyzLMN":
+            out["out_" + k] = np.array(getattr(rays, k), dtype=np.float64)
+        out["out_i"] = np.array(rays.i, dtype=np.float64)
+        out["out_opd"] = np.array(rays.opd, dtype=np.float64)
+        for k in ("L0", "M0", "N0"):
+            out["out_" + k] = np.array(getattr(rays, k), dtype=np.float64)
+        if polarized:
+            out["out_p"] = np.array(rays.p)
+    for k, v in (extra or {}).items():
+        out["x_" + k] = np.asarray(v)
+    os.makedirs(OUT, exist_ok=True)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **out)
+    nan_frac = float(np.mean(np.isnan(out["out_x"]))) if not err else -1
+    print(f"{name:28s} S={tab.num_surfaces:2d} N={inp['x'].size:5d} n_wl={tab.n_wl} "
+          f"nan={nan_frac:.3f} err={err[:30]!r} {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+def gen(lens, Hx, Hy, Px, Py, wl):
+    return lens.ray_tracer.ray_generator.generate_rays(Hx, Hy, Px, Py, wl)
+
+
+# ---------------------------------------------------------------------------
+
+def case_cooke():
+    """Config 1: Cooke triplet, 3 fields x hexapolar(6 rings)=127 pts, 0.55 um; also the
+    reference's golden spot radii (tests/test_analysis.py:88-102)."""
+    from optiland.analysis import SpotDiagram
+    from optiland.distribution import create_distribution
+
+    lens = CookeTriplet()
+    d = create_distribution("hexapolar")
+    d.generate_points(6)
+    Px, Py = np.array(d.x), np.array(d.y)
+    fields = [0.0, 0.7, 1.0]
+    Hy = np.repeat(fields, Px.size)
+    rays = gen(lens, np.zeros_like(Hy), Hy, np.tile(Px, 3), np.tile(Py, 3), 0.55)
+    spot = SpotDiagram(CookeTriplet())
+    rms = np.array(spot.rms_spot_radius())  # (fields, wavelengths)
+    geo = np.array(spot.geometric_spot_radius())
+    run_case("cooke_c1", lens, rays, [0.55],
+             extra={"spot_rms": rms, "spot_geo": geo, "n_pupil": Px.size, "Px": Px, "Py": Py})
+
+
+def case_dgauss():
+    """Config 2 (small N): Double-Gauss, on-axis, 0.5876 um, uniform-in-disk pupil."""
+    lens = DoubleGauss()
+    Px, Py = disk(512, seed=0)
+    rays = gen(lens, 0.0, 0.0, Px, Py, 0.5876)
+    sc = launch_scalars(lens, 0.0, 0.0)
+    run_case("dgauss_c2", lens, rays, [0.5876],
+             extra={"Px": Px, "Py": Py, **{"launch_" + k: v for k, v in sc.items()}})
+    # off-axis, three wavelengths interleaved per ray (trace_generic-style batches)
+    lens = DoubleGauss()
+    Px, Py = disk(600, seed=1)
+    wl = np.tile([0.4861, 0.5876, 0.6563], 200)
+    rays = gen(lens, 0.0, 0.7, Px, Py, wl)
+    run_case("dgauss_multiwl", lens, rays, [0.4861, 0.5876, 0.6563])
+    # NaN in band: rays far outside the pupil miss surfaces / suffer TIR
+    lens = DoubleGauss()
+    Px, Py = disk(300, seed=2, rmax=4.0)
+    rays = gen(lens, 0.0, 1.0, Px, Py, 0.5876)
+    run_case("dgauss_nan", lens, rays, [0.5876])
+
+
+def reverse_telephoto_asphere(tol):
+    lens = _optic.Optic()
+    ref = ReverseTelephoto()
+    lens.surfaces.add(index=0, radius=be.inf, thickness=be.inf)
+    spec = [
+        (1.69111096, 0.08259680, "N-SK10"), (0.94414496, 0.8, None), (4.32100401, 0.080256, "SK15"),
+        (1.78117621, 0.5, None), (2.64050282, 0.27638160, "BASF2"), (-3.86177348, 0.1, None),
+        (1.05627661, 0.2, "FK3"), (-4.06933311, 0.2001384, None), (np.inf, 0.06688, None),
+        (-2.61246583, 0.064372, ("SF15", "hikari")), (0.99117409, 0.3, None),
+        (9.03045960, 0.18743120, "N-LAK12"), (-1.35680743, 2.35130547, None),
+    ]
+    for j, (R, th, mat) in enumerate(spec, start=1):
+        kw = dict(index=j, radius=R, thickness=th)
+        if mat is not None:
+            kw["material"] = mat
+        if j == 9:
+            kw["is_stop"] = True
+        if j == 1:
+            kw.update(surface_type="even_asphere", conic=0.0, coefficients=[1e-3, -2e-3, 5e-4], tol=tol)
+        if j == 13:
+            kw.update(surface_type="even_asphere", conic=-0.3, coefficients=[-2e-3, 1e-3, -4e-4], tol=tol)
+        lens.surfaces.add(**kw)
+    lens.surfaces.add(index=14)
+    lens.set_aperture(aperture_type="EPD", value=0.3)
+    lens.fields.set_type(field_type="angle")
+    for f in (0, 21, 30):
+        lens.fields.add(y=f)
+    lens.wavelengths.add(value=0.5876, is_primary=True)
+    del ref
+    return lens
+
+
+def case_telephoto():
+    """Config 3: reverse telephoto with two even aspheres (Newton path)."""
+    for tag, tol in (("tol1e-10", 1e-10), ("tol1e-6", 1e-6)):
+        lens = reverse_telephoto_asphere(tol)
+        Px, Py = disk(400, seed=3)
+        rays = gen(lens, 0.0, 0.7, Px, Py, 0.5876)
+        run_case(f"telephoto_c3_{tag}", lens, rays, [0.5876])
+    lens = AsphericSinglet()
+    Px, Py = disk(300, seed=4)
+    rays = gen(lens, 0.0, 0.0, Px, Py, 0.587)
+    run_case("aspheric_singlet", lens, rays, [0.587])
+
+
+def case_hubble():
+    """Config 4: Hubble (conic mirrors, radial obscuration on the primary)."""
+    lens = HubbleTelescope()
+    Px, Py = disk(600, seed=5)
+    rays = gen(lens, 0.0, 1.0, Px, Py, 0.55)
+    sc = launch_scalars(lens, 0.0, 1.0)
+    run_case("hubble_c4", lens, rays, [0.55],
+             extra={"Px": Px, "Py": Py, **{"launch_" + k: v for k, v in sc.items()}})
+
+
+def zernike_singlet(zernike_type="fringe", coefficients=None, norm_radius=12.0, fresnel=False):
+    lens = _optic.Optic()
+    if coefficients is None:
+        coefficients = [0.0, 2e-3, -1e-3, 4e-3, 1e-3, -2e-3, 5e-4, -7e-4, 3e-3, 2e-4, -3e-4, 1e-4,
+                        6e-4, -2e-4, 1e-4, 4e-4]
+    lens.surfaces.add(index=0, radius=be.inf, thickness=be.inf)
+    lens.surfaces.add(index=1, radius=40.0, thickness=6.0, material="N-BK7", is_stop=True,
+                      surface_type="zernike", zernike_type=zernike_type, conic=-0.5,
+                      coefficients=coefficients, norm_radius=norm_radius, tol=1e-10)
+    lens.surfaces.add(index=2, radius=-60.0, thickness=45.0)
+    lens.surfaces.add(index=3)
+    lens.set_aperture(aperture_type="EPD", value=16.0)
+    lens.fields.set_type(field_type="angle")
+    lens.fields.add(y=0)
+    lens.fields.add(y=5)
+    lens.wavelengths.add(value=0.55, is_primary=True)
+    if fresnel:
+        lens.surfaces.set_fresnel_coatings()
+        lens.set_polarization(PolarizationState(is_polarized=False))
+    return lens
+
+
+def case_zernike():
+    """Config 5 geometry: Zernike freeform (fringe / standard / noll), Newton path."""
+    for ztype in ("fringe", "standard", "noll"):
+        lens = zernike_singlet(ztype)
+        Px, Py = disk(400, seed=6)
+        Px[0] = 0.0
+        Py[0] = 0.0  # exact axial ray: exercises the rho == 0 branch of the normal
+        rays = gen(lens, 0.0, 0.0 if ztype == "fringe" else 0.7, Px, Py, 0.55)
+        run_case(f"zernike_{ztype}", lens, rays, [0.55])
+    # out-of-range coordinates: the reference raises ValueError (zernike.py:254-266)
+    lens = zernike_singlet("fringe", norm_radius=6.0)
+    Px, Py = disk(50, seed=7)
+    rays = gen(lens, 0.0, 0.0, Px, Py, 0.55)
+    run_case("zernike_range_error", lens, rays, [0.55], expect_error=True)
+
+
+def case_polarized():
+    """Config 5 polarization: Zernike surface + Fresnel coatings + unpolarized PolarizedRays,
+    three wavelengths."""
+    lens = zernike_singlet("fringe", fresnel=True)
+    Px, Py = disk(300, seed=8)
+    wl = np.tile([0.48, 0.55, 0.65], 100)
+    rays = gen(lens, 0.0, 1.0, Px, Py, wl)
+    assert type(rays).__name__ == "PolarizedRays"
+    i0 = np.array(rays._i0)
+    k0 = np.stack([np.array(rays._L0), np.array(rays._M0), np.array(rays._N0)])
+    # what RealRayTracer.trace does after the loop (real_ray_tracer.py:112-113)
+    import copy
+    probe = copy.deepcopy(rays)
+    lens2 = zernike_singlet("fringe", fresnel=True)
+    lens2.surfaces.trace(probe)
+    probe.update_intensity(lens2.polarization_state)
+    run_case("zernike_polarized_c5", lens, rays, [0.48, 0.55, 0.65], polarized=True,
+             extra={"i0": i0, "k0": k0, "final_intensity_unpolarized": np.array(probe.i)})
+    # plain (uncoated) polarized trace on the Cooke triplet, polarized input state
+    lens = CookeTriplet()
+    lens.set_polarization(PolarizationState(is_polarized=True, Ex=1.0, Ey=0.5, phase_x=0.0, phase_y=0.3))
+    Px, Py = disk(200, seed=9)
+    rays = gen(lens, 0.0, 0.7, Px, Py, 0.55)
+    i0 = np.array(rays._i0)
+    k0 = np.stack([np.array(rays._L0), np.array(rays._M0), np.array(rays._N0)])
+    probe = copy.deepcopy(rays)
+    lens2 = CookeTriplet()
+    lens2.set_polarization(PolarizationState(is_polarized=True, Ex=1.0, Ey=0.5, phase_x=0.0, phase_y=0.3))
+    lens2.surfaces.trace(probe)
+    probe.update_intensity(lens2.polarization_state)
+    run_case("cooke_polarized", lens, rays, [0.55], polarized=True,
+             extra={"i0": i0, "k0": k0, "final_intensity": np.array(probe.i),
+                    # PolarizationState normalises (Ex, Ey) (optiland/rays/polarization_state.py:53-56)
+                    "state": np.array([1.0 / np.sqrt(1.25), 0.5 / np.sqrt(1.25), 0.0, 0.3])})
+
+
+def case_tilted():
+    """Decentered / tilted surfaces incl. a fold mirror (rotated poses, reflect)."""
+    lens = _optic.Optic()
+    lens.surfaces.add(index=0, radius=be.inf, thickness=be.inf)
+    lens.surfaces.add(index=1, radius=50.0, thickness=5.0, material="N-BK7", is_stop=True,
+                      dx=0.3, dy=-0.2, rx=0.02, ry=-0.015)
+    lens.surfaces.add(index=2, radius=-80.0, thickness=30.0, rz=0.4, rx=-0.01, conic=-0.8)
+    lens.surfaces.add(index=3, radius=be.inf, thickness=-25.0, material="mirror", rx=np.pi / 4)
+    lens.surfaces.add(index=4, radius=be.inf, thickness=0.0, rx=np.pi / 2, dy=0.5,
+                      aperture=pa.RectangularAperture(-3.0, 3.5, -2.0, 4.0))
+    lens.set_aperture(aperture_type="EPD", value=10.0)
+    lens.fields.set_type(field_type="angle")
+    lens.fields.add(y=0)
+    lens.fields.add(y=3)
+    lens.wavelengths.add(value=0.6, is_primary=True)
+    Px, Py = disk(400, seed=10)
+    rays = gen(lens, 0.0, 1.0, Px, Py, 0.6)
+    run_case("tilted_fold", lens, rays, [0.6])
+
+
+def case_misc():
+    """Odd asphere, polynomial, aperture trees, simple coating, absorbing medium."""
+    lens = _optic.Optic()
+    glass = IdealMaterial(n=1.6, k=2e-6)  # absorbing: exercises Beer-Lambert attenuation
+    lens.surfaces.add(index=0, radius=be.inf, thickness=be.inf)
+    lens.surfaces.add(index=1, radius=45.0, thickness=6.0, material=glass, is_stop=True,
+                      surface_type="odd_asphere", conic=0.1, coefficients=[1e-3, -2e-4, 3e-5, 1e-6], tol=1e-10,
+                      aperture=pa.UnionAperture(pa.RadialAperture(r_max=5.0, r_min=1.0),
+                                                pa.OffsetRadialAperture(r_max=3.0, r_min=0.0,
+                                                                        offset_x=5.0, offset_y=1.0)))
+    lens.surfaces.add(index=2, radius=-70.0, thickness=4.0, coating=SimpleCoating(0.9, 0.05),
+                      surface_type="polynomial", conic=0.0, tol=1e-10,
+                      coefficients=[[0.0, 1e-3, 2e-4, -1e-5], [-2e-3, 5e-4, 1e-5, 0.0], [3e-4, -1e-5, 0.0, 2e-6]])
+    lens.surfaces.add(index=3, radius=30.0, thickness=5.0, material="N-SF11",
+                      aperture=pa.DifferenceAperture(pa.EllipticalAperture(6.0, 4.5, 0.2, -0.1),
+                                                     pa.RectangularAperture(-1.0, 1.0, -0.5, 0.7)))
+    lens.surfaces.add(index=4, radius=be.inf, thickness=20.0,
+                      aperture=pa.IntersectionAperture(pa.RadialAperture(r_max=6.0),
+                                                       pa.RectangularAperture(-5.0, 5.0, -4.0, 6.0)))
+    lens.surfaces.add(index=5)
+    lens.set_aperture(aperture_type="EPD", value=14.0)
+    lens.fields.set_type(field_type="angle")
+    lens.fields.add(y=0)
+    lens.fields.add(y=4)
+    lens.wavelengths.add(value=0.55, is_primary=True)
+    Px, Py = disk(500, seed=11)
+    # (no exact chief ray here: the r^1 odd term makes the vertex a cone tip, where the slope
+    #  is discontinuous and any rounding difference flips it)
+    rays = gen(lens, 0.0, 0.5, Px, Py, 0.55)
+    run_case("misc_apertures_coatings", lens, rays, [0.55])
+
+
+def main():
+    be.set_backend("numpy")
+    case_cooke()
+    case_dgauss()
+    case_telephoto()
+    case_hubble()
+    case_zernike()
+    case_polarized()
+    case_tilted()
+    case_misc()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,88 @@
+// TEST INFRASTRUCTURE ONLY -- CPU instantiation of the device arithmetic.
+//
+// olb_math.cuh (surface_step / to_global) and olb_prep.h (table preparation) are the
+// exact sources libolb.so compiles for sm_100a; here they are compiled by g++ so the
+// GPU-less build container can check the kernel arithmetic against the oracle
+// (tests/test_hostcheck.py).  This object is never linked into libolb.so and the
+// product package never loads it: it is not a CPU fallback.
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../optiland_b200/csrc/olb_math.cuh"
+
+using namespace olb;
+
+template <typename T, uint32_t FEAT>
+static void walk(const unsigned char* blob, int first, int last, int64_t n, T** ray /*x y z L M N i w opd*/,
+                 T** rec /*8 arrays rows*n or null*/, T** l0 /*3 or null*/, int* status_out) {
+  const PrepHeader* H = reinterpret_cast<const PrepHeader*>(blob);
+  const PrepSurface<T>* surf = reinterpret_cast<const PrepSurface<T>*>(blob + sizeof(PrepHeader));
+  const T* pool = reinterpret_cast<const T*>(surf + H->n_surf);
+  const T* wl = pool + H->pad[0];
+  int status = 0;
+  for (int64_t k = 0; k < n; ++k) {
+    Ray<T> r{};
+    r.x = ray[0][k]; r.y = ray[1][k]; r.z = ray[2][k]; r.L = ray[3][k]; r.M = ray[4][k]; r.N = ray[5][k];
+    r.i = ray[6][k]; r.opd = ray[8][k]; r.opd_lo = 0; r.widx = 0;
+    if (H->n_wl > 1) {
+      int idx = -1;
+      for (int j = 0; j < H->n_wl; ++j)
+        if (ray[7][k] == wl[j]) idx = j;
+      r.widx = idx;
+    }
+    bool have_frame = false;
+    T g[6] = {r.x, r.y, r.z, r.L, r.M, r.N};
+    for (int s = first; s < last; ++s) {
+      const PrepSurface<T>& S = surf[s];
+      const bool noop = S.kind == OLB_GEOM_NOOP;
+      if (!noop) { surface_step<T, FEAT>(r, S, pool, !have_frame, status); have_frame = true; }
+      const bool record = rec != nullptr && !(S.flags & OLB_SF_NORECORD);
+      if ((record || s == last - 1) && !noop) to_global<T, FEAT>(r, S, g[0], g[1], g[2], g[3], g[4], g[5]);
+      if (record) {
+        const int64_t off = (int64_t)(s - first) * n + k;
+        for (int q = 0; q < 6; ++q) rec[q][off] = g[q];
+        rec[6][off] = r.i;
+        rec[7][off] = opd_value(r);
+      }
+    }
+    for (int q = 0; q < 6; ++q) ray[q][k] = g[q];
+    ray[6][k] = r.i;
+    ray[8][k] = opd_value(r);
+    if (l0) { l0[0][k] = r.L0; l0[1][k] = r.M0; l0[2][k] = r.N0; }
+  }
+  *status_out |= status;
+}
+
+template <typename T>
+static int run(const OlbTable* tab, int first, int last, int64_t n, T** ray, T** rec, T** l0, int* status,
+               char* err, int err_len) {
+  PrepResult pr = prepare_table(*tab);
+  if (!pr.error.empty()) { snprintf(err, err_len, "%s", pr.error.c_str()); return OLB_ERR_TABLE; }
+  const unsigned char* blob = sizeof(T) == 8 ? pr.blob_f64.data() : pr.blob_f32.data();
+  if (pr.features & FEAT_POL) { snprintf(err, err_len, "polarized not supported in hostcheck"); return OLB_ERR_UNSUPPORTED; }
+  // exercise the same three instantiations the launcher picks from
+  if (pr.features & (FEAT_ROT | FEAT_EXTRA) || l0)
+    walk<T, FEAT_ROT | FEAT_NEWTON | FEAT_EXTRA>(blob, first, last, n, ray, rec, l0, status);
+  else if (pr.features & FEAT_NEWTON)
+    walk<T, FEAT_NEWTON>(blob, first, last, n, ray, rec, l0, status);
+  else
+    walk<T, 0u>(blob, first, last, n, ray, rec, l0, status);
+  return OLB_OK;
+}
+
+extern "C" {
+int olbhc_trace_f64(const OlbTable* tab, int first, int last, int64_t n, double** ray, double** rec, double** l0,
+                    int* status, char* err, int err_len) {
+  return run<double>(tab, first, last, n, ray, rec, l0, status, err, err_len);
+}
+int olbhc_trace_f32(const OlbTable* tab, int first, int last, int64_t n, float** ray, float** rec, float** l0,
+                    int* status, char* err, int err_len) {
+  return run<float>(tab, first, last, n, ray, rec, l0, status, err, err_len);
+}
+int olbhc_features(const OlbTable* tab) {
+  PrepResult pr = prepare_table(*tab);
+  return pr.error.empty() ? (int)pr.features : -1;
+}
+}

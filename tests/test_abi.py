@@ -1,0 +1,72 @@
+"""The C-ABI shared library loads and exports every symbol include/olb.h declares (no compute)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from optiland_b200 import _lib
+from optiland_b200 import table as T
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "olb.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(olb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_and_binding_agree():
+    assert _declared_symbols() == sorted(_lib.SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    for name in _declared_symbols():
+        assert hasattr(lib, name), name
+    assert lib.olb_version() >= 1
+
+
+def test_struct_sizes_match_header():
+    assert T.OLB_SURFACE_DTYPE.itemsize == 192
+    assert C.sizeof(_lib.OlbRays) == 13 * 8
+    assert C.sizeof(_lib.OlbRecords) == 9 * 8
+    assert C.sizeof(_lib.OlbTable) == 40
+    assert C.sizeof(_lib.OlbDeviceTable) == 48
+
+
+def test_table_validation_errors_no_gpu_needed():
+    """olb_table_workspace_bytes validates on the host: malformed tables are rejected with a
+    message, well-formed ones report a size (no device call is made)."""
+    lib = _lib.load()
+    good = T.SurfaceTable([T.SurfaceSpec(kind=T.GEOM_NOOP), T.SurfaceSpec(kind=T.GEOM_STANDARD, radius=50.0,
+                                                                             n2=[1.5])], [0.55])
+    ht = _lib.HostTable(good)
+    assert lib.olb_table_workspace_bytes(C.byref(ht.c)) > 0
+    ht.surf["kind"][1] = 99
+    assert lib.olb_table_workspace_bytes(C.byref(ht.c)) == -5
+    assert "kind" in _lib.last_error()
+    ht = _lib.HostTable(good)
+    ht.surf["media_off"][1] = 10_000
+    assert lib.olb_table_workspace_bytes(C.byref(ht.c)) == -5
+    assert "media" in _lib.last_error()
+
+
+def test_pack_roundtrip():
+    s = T.SurfaceSpec(kind=T.GEOM_ZERNIKE, radius=30.0, conic=-1.0, norm_radius=5.0,
+                      coefficients=np.array([[2, 0, 1e-3, 5e-4], [3, -1, 2e-3, 1e-3]]),
+                      aperture=T.aperture_combine(T.AP_UNION, T.aperture_radial(3.0, 1.0), T.aperture_rect(-1, 1, -2, 2)),
+                      n1=[1.0, 1.0], n2=[1.5, 1.6], k1=[0.0, 1e-6], reflective=False,
+                      coating=T.COAT_FRESNEL, coat_n1=[1.0, 1.0], coat_n2=[1.5, 1.6])
+    tab = T.SurfaceTable([T.SurfaceSpec(kind=T.GEOM_NOOP, n1=[1, 1], n2=[1, 1], k1=[0, 0]), s], [0.5, 0.6])
+    back = T.SurfaceTable.from_arrays(tab.to_arrays())
+    b = back.surfaces[1]
+    assert b.kind == s.kind and b.radius == s.radius and b.norm_radius == s.norm_radius
+    np.testing.assert_array_equal(b.coefficients, s.coefficients)
+    np.testing.assert_array_equal(b.aperture, s.aperture)
+    np.testing.assert_array_equal(b.n2, s.n2)
+    np.testing.assert_array_equal(b.coat_n2, s.coat_n2)
+    with pytest.raises(ValueError):
+        T.validate_aperture_program(np.array([T.AP_UNION], dtype=float))

@@ -1,0 +1,193 @@
+"""Parity tests proper: the sm_100a kernel, called through the C ABI, against (a) the golden
+records produced by the unmodified reference, (b) the NumPy oracle on the same seeded inputs,
+and (c) size-independent properties at BASELINE.json's full sizes."""
+import numpy as np
+import pytest
+import torch
+
+from optiland_b200 import table as T
+from tests._util import ERROR_CASES, REAL_CASES, REC, Case, max_abs_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _rays(c, dtype, idx=None):
+    from optiland_b200.trace import RealRays
+
+    r = c.rays if idx is None else {k: v[idx] for k, v in c.rays.items()}
+    return RealRays(r["x"], r["y"], r["z"], r["L"], r["M"], r["N"], r["i"], r["w"], dtype=dtype)
+
+
+def newton_tol(c):
+    tols = [s.tol for s in c.table.surfaces if s.kind in T.NEWTON_KINDS]
+    return max(tols) if tols else 0.0
+
+
+def _np(t):
+    return t.double().cpu().numpy()
+
+
+@pytest.mark.parametrize("name", REAL_CASES)
+def test_f64_kernel_vs_reference_golden(name):
+    """fp64 kernel == reference NumPy backend within 1e-11 x system scale (+ the reference's own
+    Newton stopping residual on Newton surfaces)."""
+    from optiland_b200.trace import SurfaceGroup
+
+    c = Case(name)
+    sg = SurfaceGroup(c.table)
+    rays = _rays(c, torch.float64)
+    sg.trace(rays)
+    tol = 1e-11 * c.scale + 2.0 * newton_tol(c)
+    for k in REC:
+        assert max_abs_err(_np(getattr(sg, k)), c.rec[k]) <= tol, k
+    for k in ("x", "y", "z", "L", "M", "N", "i", "opd"):
+        assert max_abs_err(_np(getattr(rays, k)), c.out[k]) <= tol, k
+
+
+def _fp32_err(a, b):
+    m = np.isfinite(a) & np.isfinite(b)
+    assert np.mean(np.isfinite(a) != np.isfinite(b)) <= 0.02
+    d = np.sort(np.abs(a[m] - b[m]))
+    return (float(d[int(0.98 * (d.size - 1))]), float(d[-1])) if d.size else (0.0, 0.0)
+
+
+@pytest.mark.parametrize("name", REAL_CASES)
+def test_f32_kernel_vs_reference_golden(name):
+    """fp32 kernel vs fp64 reference: 2e-6 x system scale for intercepts and OPD, 5e-6 for
+    direction cosines (98 % of entries; ill-conditioned grazing rays get 100x)."""
+    from optiland_b200.trace import SurfaceGroup
+
+    c = Case(name)
+    sg = SurfaceGroup(c.table)
+    rays = _rays(c, torch.float32)
+    sg.trace(rays)
+    ptol = 2e-6 * c.scale + 2.0 * newton_tol(c)
+    for k in ("x", "y", "z", "opd"):
+        p98, worst = _fp32_err(_np(getattr(sg, k)), c.rec[k])
+        assert p98 <= ptol and worst <= 100 * ptol, (k, p98, worst, ptol)
+    for k in ("L", "M", "N"):
+        p98, worst = _fp32_err(_np(getattr(sg, k)), c.rec[k])
+        assert p98 <= 5e-6 and worst <= 5e-4, (k, p98, worst)
+
+
+@pytest.mark.parametrize("name", ERROR_CASES)
+def test_zernike_range_raises_like_reference(name):
+    from optiland_b200.trace import SurfaceGroup
+
+    c = Case(name)
+    sg = SurfaceGroup(c.table)
+    with pytest.raises(ValueError, match="Zernike coordinates must be normalized"):
+        sg.trace(_rays(c, torch.float64))
+
+
+@pytest.mark.parametrize("n", [0, 1, 3, 255, 257, 1000, 4099])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_ragged_sizes_against_oracle(n, dtype):
+    """Empty, single-ray and non-multiple-of-vector-width batches (tail handling)."""
+    from oracle import trace_oracle as O
+    from optiland_b200.trace import SurfaceGroup
+
+    c = Case("dgauss_multiwl")
+    rng = np.random.default_rng(n)
+    idx = rng.integers(0, c.n, size=n)
+    sub = {k: v[idx] for k, v in c.rays.items()}
+    sg = SurfaceGroup(c.table)
+    rays = _rays(c, dtype, idx)
+    sg.trace(rays)
+    if n == 0:
+        assert sg.x.shape == (c.table.num_surfaces, 0)
+        return
+    _, orec, _ = O.trace(c.table, sub)
+    tol = 1e-11 * c.scale if dtype == torch.float64 else 2e-5 * c.scale
+    for k in REC:
+        assert max_abs_err(_np(getattr(sg, k)), orec[k]) <= tol, k
+
+
+def test_partial_range_skip_and_stop():
+    """SurfaceGroup.trace(rays, skip) semantics + early stop, without records (in-place update)."""
+    from oracle import trace_oracle as O
+    from optiland_b200.trace import SurfaceGroup
+
+    c = Case("dgauss_c2")
+    sg = SurfaceGroup(c.table)
+    rays = _rays(c, torch.float64)
+    sg.trace(rays, skip=0, stop=3, record=False)
+    sg.trace(rays, skip=3, stop=9)
+    assert sg.x.shape == (6, c.n)
+    mid, _, _ = O.trace(c.table, c.rays, 0, 3)
+    ref_out, ref_rec, _ = O.trace(c.table, {k: mid[k] for k in ("x", "y", "z", "L", "M", "N", "i", "w", "opd")}, 3, 9)
+    for k in REC:
+        assert max_abs_err(_np(getattr(sg, k)), ref_rec[k]) <= 1e-11 * c.scale, k
+
+
+def test_full_size_properties_double_gauss():
+    """Config 2 at full size (10 M rays, fp32, full records): size-independent properties.
+    (1) determinism: two traces of the same batch are bit-identical; (2) a strided sample of
+    4096 rays matches the oracle; (3) permutation equivariance: tracing a reversed batch gives
+    the reversed result bit-for-bit; (4) OPD is non-decreasing across surfaces and direction
+    cosines stay normalised."""
+    from oracle import trace_oracle as O
+    from optiland_b200.launch import launch_infinite_angle
+    from optiland_b200.trace import RealRays, SurfaceGroup
+
+    c = Case("dgauss_c2")
+    sc = {k[9:]: float(c.z[k]) for k in c.z.files if k.startswith("x_launch_")}
+    n = 10_000_000
+    g = torch.Generator(device="cuda").manual_seed(0)
+    r = torch.rand(n, generator=g, device="cuda", dtype=torch.float64).sqrt()
+    th = 2 * np.pi * torch.rand(n, generator=g, device="cuda", dtype=torch.float64)
+    Px, Py = r * torch.cos(th), r * torch.sin(th)
+    x0, y0, z0, L, M, N = launch_infinite_angle(Px, Py, sc)
+    one = torch.ones_like(x0)
+    sg = SurfaceGroup(c.table)
+
+    def run(order=None):
+        args = [x0, y0, z0, L, M, N, one, one * 0.5876]
+        if order is not None:
+            args = [a[order] for a in args]
+        rays = RealRays(*args, dtype=torch.float32)
+        sg.trace(rays)
+        return {k: getattr(sg, k) for k in REC}
+
+    a = run()
+    img_x, img_y = a["x"][-1].clone(), a["y"][-1].clone()
+    opd = a["opd"]
+    assert bool((opd[1:] >= opd[:-1]).all())
+    nrm = a["L"][-1] ** 2 + a["M"][-1] ** 2 + a["N"][-1] ** 2
+    assert float((nrm - 1).abs().max()) < 1e-5
+    sample = torch.arange(0, n, n // 4096, device="cuda")[:4096]
+    sub = {k: v[sample].cpu().numpy() for k, v in zip("xyzLMN", (x0, y0, z0, L, M, N))}
+    sub["i"] = np.ones(4096)
+    sub["w"] = np.full(4096, 0.5876)
+    sub = {k: v.astype(np.float32).astype(np.float64) for k, v in sub.items()}
+    sub["w"] = np.full(4096, 0.5876)
+    _, orec, _ = O.trace(c.table, sub)
+    for k in ("x", "y", "z", "opd"):
+        assert max_abs_err(_np(a[k][:, sample]), orec[k]) <= 2e-6 * c.scale, k
+    del a
+    b = run()
+    assert torch.equal(b["x"][-1], img_x) and torch.equal(b["y"][-1], img_y)
+    del b
+    rev = torch.arange(n - 1, -1, -1, device="cuda")
+    d = run(rev)
+    assert torch.equal(d["x"][-1].flip(0), img_x) and torch.equal(d["y"][-1].flip(0), img_y)
+
+
+def test_host_buffer_path_matches_device_path():
+    """olb_trace_host_f32 (pinned host in/out, chunked + pipelined) == device path, bit for bit."""
+    from optiland_b200.trace import DeviceTable, SurfaceGroup, trace_host
+
+    c = Case("hubble_c4")
+    n = 300_000
+    rng = np.random.default_rng(1)
+    idx = rng.integers(0, c.n, size=n)
+    h_in = {k: torch.from_numpy(c.rays[k][idx].astype(np.float32)).pin_memory() for k in c.rays}
+    h_out = {k: torch.empty(n, dtype=torch.float32).pin_memory() for k in ("x", "y", "z", "L", "M", "N", "i", "opd")}
+    dt = DeviceTable(c.table)
+    trace_host(dt, h_in, h_out, n, torch.float32, chunk=70_001)
+    sg = SurfaceGroup(c.table)
+    rays = _rays(c, torch.float32, idx)
+    sg.trace(rays)
+    for k in ("x", "y", "z", "L", "M", "N", "i", "opd"):
+        a, b = h_out[k].numpy(), getattr(rays, k).cpu().numpy()
+        assert np.array_equal(a, b, equal_nan=True), k

@@ -1,0 +1,128 @@
+"""CPU instantiation of the DEVICE arithmetic (olb_math.cuh + olb_prep.h compiled by g++,
+tests/hostcheck/hostcheck.cpp) against the reference-generated golden fixtures.
+
+This lets the GPU-less build container verify the kernel's math; the same comparisons
+run on the B200 through the C ABI in tests/test_gpu_parity.py.  The host-check library
+is test infrastructure only -- the product has no CPU path.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from optiland_b200 import _lib
+from optiland_b200 import table as T
+from tests._util import ERROR_CASES, REAL_CASES, REC, Case, max_abs_err
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "hostcheck", "hostcheck.cpp")
+SO = os.path.join(HERE, "hostcheck", "_hostcheck.so")
+CSRC = os.path.join(os.path.dirname(HERE), "optiland_b200", "csrc")
+
+
+@pytest.fixture(scope="module")
+def hc():
+    deps = [SRC, os.path.join(CSRC, "olb_math.cuh"), os.path.join(CSRC, "olb_prep.h")]
+    if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(d) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", SO, SRC])
+    return C.CDLL(SO)
+
+
+def run_hostcheck(hc, table, rays, dtype, first=0, last=None, want_l0=False):
+    last = table.num_surfaces if last is None else last
+    ht = _lib.HostTable(table)
+    n = rays["x"].size
+    keys = ("x", "y", "z", "L", "M", "N", "i", "w", "opd")
+    arrs = [np.ascontiguousarray(rays.get(k, np.zeros(n)), dtype=dtype).copy() for k in keys]
+    rows = last - first
+    rec = [np.full((rows, n), np.nan, dtype=dtype) for _ in range(8)]
+    l0 = [np.zeros(n, dtype=dtype) for _ in range(3)]
+    PP = C.c_void_p * 9
+    ray_ptrs = PP(*[a.ctypes.data for a in arrs])
+    rec_ptrs = (C.c_void_p * 8)(*[a.ctypes.data for a in rec])
+    l0_ptrs = (C.c_void_p * 3)(*[a.ctypes.data for a in l0])
+    status = C.c_int(0)
+    err = C.create_string_buffer(256)
+    fn = hc.olbhc_trace_f64 if dtype == np.float64 else hc.olbhc_trace_f32
+    fn.restype = C.c_int
+    rc = fn(C.byref(ht.c), C.c_int(first), C.c_int(last), C.c_int64(n), ray_ptrs, rec_ptrs,
+            l0_ptrs if want_l0 else None, C.byref(status), err, 256)
+    assert rc == 0, err.value
+    out = dict(zip(keys, arrs))
+    out.update(L0=l0[0], M0=l0[1], N0=l0[2])
+    return out, dict(zip(REC, rec)), status.value
+
+
+def newton_tol(c):
+    tols = [s.tol for s in c.table.surfaces if s.kind in T.NEWTON_KINDS]
+    return max(tols) if tols else 0.0
+
+
+@pytest.mark.parametrize("name", REAL_CASES)
+def test_device_math_f64_vs_reference(hc, name):
+    c = Case(name)
+    out, rec, status = run_hostcheck(hc, c.table, c.rays, np.float64, want_l0=True)
+    assert status == 0
+    # fp64 tolerance: 1e-11 x system scale (FMA contraction, flattened poses, stable conic
+    # roots) + the reference's own Newton stopping residual where a Newton surface exists.
+    tol = 1e-11 * c.scale + 2.0 * newton_tol(c)
+    for k in REC:
+        assert max_abs_err(rec[k], c.rec[k]) <= tol, (k, max_abs_err(rec[k], c.rec[k]), tol)
+    for k in ("x", "y", "z", "L", "M", "N", "i", "opd", "L0", "M0", "N0"):
+        assert max_abs_err(out[k], c.out[k]) <= tol, k
+
+
+@pytest.mark.parametrize("name", REAL_CASES)
+def test_device_math_f32_vs_reference(hc, name):
+    c = Case(name)
+    _, rec, status = run_hostcheck(hc, c.table, c.rays, np.float32)
+    assert status == 0
+    # fp32: 2e-6 of the system scale for positions / OPD, 5e-6 for direction cosines -- for
+    # 98 % of the entries; grazing / near-TIR rays are ill-conditioned (their fp64 value moves
+    # by more than that under a 1-ulp input change), so the worst 2 % get 100x the budget.
+    ptol = 2e-6 * c.scale + 2.0 * newton_tol(c)
+    for k in ("x", "y", "z", "opd"):
+        p98, worst = _fp32_err(rec[k], c.rec[k])
+        assert p98 <= ptol and worst <= 100 * ptol, (k, p98, worst, ptol)
+    for k in ("L", "M", "N"):
+        p98, worst = _fp32_err(rec[k], c.rec[k])
+        assert p98 <= 5e-6 and worst <= 5e-4, (k, p98, worst)
+    p98, _ = _fp32_err(rec["intensity"], c.rec["intensity"])
+    assert p98 <= 1e-5
+
+
+def _fp32_err(a, b):
+    """(98th percentile, max) of |a-b| over entries finite in both; fp32 may turn a grazing
+    ray into NaN where fp64 does not (and vice versa): at most 2 % such disagreements."""
+    a = np.asarray(a, dtype=np.float64)
+    m = np.isfinite(a) & np.isfinite(b)
+    mismatch = np.mean(np.isfinite(a) != np.isfinite(b))
+    assert mismatch <= 0.02, mismatch
+    d = np.sort(np.abs(a[m] - b[m]))
+    if not d.size:
+        return 0.0, 0.0
+    return float(d[int(0.98 * (d.size - 1))]), float(d[-1])
+
+
+@pytest.mark.parametrize("name", ERROR_CASES)
+def test_device_math_flags_zernike_range(hc, name):
+    c = Case(name)
+    _, _, status = run_hostcheck(hc, c.table, c.rays, np.float64)
+    assert status & T.ST_ZERNIKE_RANGE
+
+
+def test_partial_range_and_noop(hc):
+    """Trace surfaces [3, 9) only (SurfaceGroup.trace(rays, skip=3) semantics + early stop)."""
+    from oracle import trace_oracle as O
+
+    c = Case("dgauss_c2")
+    mid, _, _ = O.trace(c.table, c.rays, 0, 3)
+    mid_in = {k: mid[k] for k in ("x", "y", "z", "L", "M", "N", "i", "w", "opd")}
+    ref_out, ref_rec, _ = O.trace(c.table, mid_in, 3, 9)
+    out, rec, _ = run_hostcheck(hc, c.table, mid_in, np.float64, first=3, last=9)
+    for k in REC:
+        assert rec[k].shape == (6, c.n)
+        assert max_abs_err(rec[k], ref_rec[k]) <= 1e-11 * c.scale, k
+    assert max_abs_err(out["opd"], ref_out["opd"]) <= 1e-11 * c.scale
