@@ -14,7 +14,7 @@ import numpy as np
 from . import table as T
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libolb.so")
+LIB_PATH = os.environ.get("OLB_LIB", os.path.join(_HERE, "libolb.so"))  # OLB_LIB: tuning builds only
 
 OK = 0
 ERRORS = {-1: "OLB_ERR_INVALID_ARG", -2: "OLB_ERR_UNSUPPORTED", -3: "OLB_ERR_CUDA",

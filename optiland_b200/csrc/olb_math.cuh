@@ -27,7 +27,8 @@
 
 namespace olb {
 
-// ---- scalar helpers: IEEE for double, approx-unit (<= 2 ulp) for float on device ----
+// ---- scalar helpers: IEEE for double; for float on the device the single-instruction MUFU
+// forms (<= 2 ulp, flush-to-zero: no denormal fix-up code around every rcp / sqrt) ----
 OLB_HD double o_sqrt(double v) { return sqrt(v); }
 OLB_HD double o_div(double a, double b) { return a / b; }
 OLB_HD double o_rcp(double a) { return 1.0 / a; }
@@ -38,11 +39,12 @@ OLB_HD double o_fma(double a, double b, double c) { return fma(a, b, c); }
 OLB_HD float o_abs(float a) { return fabsf(a); }
 OLB_HD float o_fma(float a, float b, float c) { return fmaf(a, b, c); }
 #if defined(__CUDA_ARCH__)
-OLB_HD float o_sqrt(float v) { float r; asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
-OLB_HD float o_rcp(float v) { float r; asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
-OLB_HD float o_rsqrt(float v) { float r; asm("rsqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+OLB_HD float o_sqrt(float v) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+OLB_HD float o_rcp(float v) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+OLB_HD float o_rsqrt(float v) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
 OLB_HD float o_div(float a, float b) { return a * o_rcp(b); }
-OLB_HD float o_exp(float a) { return __expf(a); }
+// exp(a) = 2^(a log2 e): one FMUL + MUFU.EX2 (flush-to-zero; attenuation factors are O(1))
+OLB_HD float o_exp(float a) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a * 1.4426950408889634f)); return r; }
 #else
 OLB_HD float o_sqrt(float v) { return sqrtf(v); }
 OLB_HD float o_rcp(float v) { return 1.0f / v; }
@@ -116,13 +118,15 @@ OLB_HD T conic_distance(T x, T y, T z, T L, T M, T N, const PrepSurface<T>& S) {
   T sq = o_sqrt(disc);
   T q = hb >= 0 ? -(hb + sq) : (sq - hb);
   T ta = o_div(q, a);
-  T tb = (q == 0) ? ta : o_div(c, q);
+  T tb = o_div(c, q);
   T t1 = hb >= 0 ? tb : ta;                            // (-b + sqrt d) / 2a
   T t2 = hb >= 0 ? ta : tb;                            // (-b - sqrt d) / 2a
   T z1 = o_fma(t1, N, z), z2 = o_fma(t2, N, z);
-  T t = (o_abs(z1) <= o_abs(z2)) ? t1 : t2;
-  if (a == 0) t = -o_div(c, 2 * hb);
-  return t;
+  // Degenerate inputs need no extra branches: a == 0 (paraboloid hit by an axial ray) makes
+  // ta = +-inf, so the comparison keeps tb = c/q = -c/b, the reference's a == 0 value
+  // (standard.py:144-146); q == 0 (b = d = 0) makes tb = NaN, and since hb >= 0 then holds the
+  // comparison is false and t2 = ta = 0, the reference's double root.
+  return (o_abs(z1) <= o_abs(z2)) ? t1 : t2;
 }
 
 // Conic part of the sag and of the slope denominators.
@@ -310,9 +314,12 @@ OLB_HD bool aperture_inside(const T* prog, int len, T x, T y) {
   return stack & 1u;
 }
 
-// The surface step.  FEAT gates code that most systems never need (register pressure).
-template <typename T, uint32_t FEAT>
-OLB_HD void surface_step(Ray<T>& r, const PrepSurface<T>& S, const T* pool, bool from_global, int& status) {
+// The surface step.  FEAT gates code that most systems never need (register pressure, code
+// size); KIND (0 plane, 1 sphere/conic closed form, 2 Newton family) is resolved by the caller
+// ONCE per surface, outside the per-ray loop, so the hot loop carries no geometry branches.
+enum { KIND_PLANE = 0, KIND_CONIC = 1, KIND_NEWTON = 2 };
+template <typename T, uint32_t FEAT, int KIND>
+OLB_HD void surface_step_k(Ray<T>& r, const PrepSurface<T>& S, const T* pool, bool from_global, int& status) {
   // -- localize (coordinate_system.py:73-89), from global or from the previous local frame
   if (FEAT & FEAT_ROT) {
     if (from_global) apply_affine(S.Ag, S.bg, (S.flags & PSF_ROT_IN_G) != 0, r.x, r.y, r.z, r.L, r.M, r.N);
@@ -326,9 +333,9 @@ OLB_HD void surface_step(Ray<T>& r, const PrepSurface<T>& S, const T* pool, bool
 
   // -- distance
   T t;
-  if (S.kind == OLB_GEOM_PLANE) {
+  if (KIND == KIND_PLANE) {
     t = -o_div(r.z, r.N);                               // plane.py:72-88
-  } else if (S.kind == OLB_GEOM_STANDARD || !(FEAT & FEAT_NEWTON)) {
+  } else if (KIND == KIND_CONIC) {
     t = conic_distance(r.x, r.y, r.z, r.L, r.M, r.N, S);
   } else {
     t = newton_distance(r.x, r.y, r.z, r.L, r.M, r.N, S, pool, status);
@@ -337,7 +344,7 @@ OLB_HD void surface_step(Ray<T>& r, const PrepSurface<T>& S, const T* pool, bool
   r.x = o_fma(t, r.L, r.x);
   r.y = o_fma(t, r.M, r.y);
   r.z = o_fma(t, r.N, r.z);
-  if ((FEAT & FEAT_EXTRA) && (S.flags & OLB_SF_ABSORBING)) r.i *= o_exp(-med[MED_ALPHA] * t);
+  if (S.flags & OLB_SF_ABSORBING) r.i *= o_exp(-med[MED_ALPHA] * t);
   accumulate_opd(r, o_abs(t * (med[MED_N1] + bad)));
 
   // -- aperture clip (standard_surface.py:245-246; real_rays.py:154-161): NaN -> clipped
@@ -356,9 +363,9 @@ OLB_HD void surface_step(Ray<T>& r, const PrepSurface<T>& S, const T* pool, bool
 
   // -- surface normal
   T nx, ny, nz;
-  if (S.kind == OLB_GEOM_PLANE) {
+  if (KIND == KIND_PLANE) {
     nx = 0; ny = 0; nz = 1;                             // plane.py:90-109
-  } else if (S.kind == OLB_GEOM_STANDARD || !(FEAT & FEAT_NEWTON)) {
+  } else if (KIND == KIND_CONIC) {
     // standard.py:150-175: (x, y, -denom)/ (denom * mag) with denom = R sqrt(1-(1+k) r2/R^2);
     // multiplied through by sqrt(.) >= 0 this is (x c, y c, -s) / sqrt(1 - k r2 c^2).
     T c = S.curv;
@@ -399,6 +406,15 @@ OLB_HD void surface_step(Ray<T>& r, const PrepSurface<T>& S, const T* pool, bool
   // -- coating (interactions/base.py:111-128; coatings.py:164-237)
   if ((FEAT & FEAT_EXTRA) && S.coating == OLB_COAT_SIMPLE)
     r.i *= (S.flags & OLB_SF_REFLECT) ? S.coat_r : S.coat_t;
+}
+
+// Runtime dispatch on the geometry kind (one ray).  The CUDA kernel does this dispatch once
+// per surface around its per-ray loop instead; the host-check uses this form.
+template <typename T, uint32_t FEAT>
+OLB_HD void surface_step(Ray<T>& r, const PrepSurface<T>& S, const T* pool, bool from_global, int& status) {
+  if (S.kind == OLB_GEOM_PLANE) surface_step_k<T, FEAT, KIND_PLANE>(r, S, pool, from_global, status);
+  else if (S.kind == OLB_GEOM_STANDARD) surface_step_k<T, FEAT, KIND_CONIC>(r, S, pool, from_global, status);
+  else if (FEAT & FEAT_NEWTON) surface_step_k<T, FEAT, KIND_NEWTON>(r, S, pool, from_global, status);
 }
 
 // Local -> global for the record (coordinate_system.py:91-107).

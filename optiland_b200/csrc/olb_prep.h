@@ -29,7 +29,7 @@ namespace olb {
 enum : uint32_t {
   FEAT_ROT = 1u << 0,      // some surface has a rotated pose
   FEAT_NEWTON = 1u << 1,   // even/odd asphere, polynomial, Zernike (Newton iteration)
-  FEAT_EXTRA = 1u << 2,    // absorption, non-radial aperture programs, simple coatings
+  FEAT_EXTRA = 1u << 2,    // non-radial aperture programs, simple coatings, L0/M0/N0 output
   FEAT_POL = 1u << 3,      // polarized rays (P matrix) / Fresnel coatings
 };
 
@@ -352,7 +352,7 @@ static inline PrepResult prepare_table(const OlbTable& tab) {
       pool.push_back(4.0 * M_PI * k1 / tab.wavelengths[j] * 1e3);
       pool.push_back(c2 / c1);
     }
-    if (absorbing) { o.flags |= OLB_SF_ABSORBING; features |= FEAT_EXTRA; }
+    if (absorbing) o.flags |= OLB_SF_ABSORBING;
     else o.flags &= ~uint32_t(OLB_SF_ABSORBING);
     if (in.coating == OLB_COAT_SIMPLE) features |= FEAT_EXTRA;
     else if (in.coating == OLB_COAT_FRESNEL) features |= FEAT_POL;

@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <cstring>
@@ -23,7 +24,13 @@
 
 namespace olb {
 
-static constexpr int BLOCK = 256;
+#ifndef OLB_BLOCK
+#define OLB_BLOCK 256
+#endif
+#ifndef OLB_MIN_BLOCKS
+#define OLB_MIN_BLOCKS 1
+#endif
+static constexpr int BLOCK = OLB_BLOCK;
 
 static thread_local std::string g_last_error;
 static std::atomic<int64_t> g_launches{0};
@@ -132,7 +139,7 @@ __device__ __forceinline__ void stage_table(unsigned char* smem, const unsigned 
 
 // ---- the kernel -----------------------------------------------------------------------------
 template <typename T, int RPT, uint32_t FEAT>
-__global__ void __launch_bounds__(BLOCK) trace_kernel(const __grid_constant__ TraceArgs a) {
+__global__ void __launch_bounds__(BLOCK, OLB_MIN_BLOCKS) trace_kernel(const __grid_constant__ TraceArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
   unsigned char* tab = smem + 16;
@@ -203,8 +210,18 @@ __global__ void __launch_bounds__(BLOCK) trace_kernel(const __grid_constant__ Tr
       const PrepSurface<T>& S = surf[s];
       const bool noop = S.kind == OLB_GEOM_NOOP;
       if (!noop) {
+        // geometry dispatch ONCE per surface (warp-uniform), outside the per-ray loop
+        const bool fg = !have_frame;
+        if (S.kind == OLB_GEOM_PLANE) {
 #pragma unroll
-        for (int k = 0; k < RPT; ++k) surface_step<T, FEAT>(r[k], S, pool, !have_frame, status);
+          for (int k = 0; k < RPT; ++k) surface_step_k<T, FEAT, KIND_PLANE>(r[k], S, pool, fg, status);
+        } else if (S.kind == OLB_GEOM_STANDARD) {
+#pragma unroll
+          for (int k = 0; k < RPT; ++k) surface_step_k<T, FEAT, KIND_CONIC>(r[k], S, pool, fg, status);
+        } else if constexpr ((FEAT & FEAT_NEWTON) != 0) {
+#pragma unroll 1  // one copy of the Newton / polynomial code: keep the kernel inside the I-cache
+          for (int k = 0; k < RPT; ++k) surface_step_k<T, FEAT, KIND_NEWTON>(r[k], S, pool, fg, status);
+        }
         have_frame = true;
       }
       const bool record = a.rx != nullptr && !(S.flags & OLB_SF_NORECORD);
@@ -289,6 +306,8 @@ static int launch_instance(const TraceArgs& a, cudaStream_t stream) {
   const int64_t per_tile = (int64_t)BLOCK * RPT;
   const int64_t n_tiles = (a.n_rays + per_tile - 1) / per_tile;
   int64_t grid = (int64_t)num_sms * blocks_per_sm;  // persistent: one wave of resident CTAs
+  static const int grid_mult = [] { const char* e = getenv("OLB_GRID_MULT"); return e ? atoi(e) : 1; }();
+  if (grid_mult > 1) grid *= grid_mult;
   if (grid > n_tiles) grid = n_tiles;
   if (grid < 1) return OLB_OK;
   kern<<<(unsigned)grid, BLOCK, smem, stream>>>(a);
@@ -300,10 +319,10 @@ static int launch_instance(const TraceArgs& a, cudaStream_t stream) {
 template <typename T, int RPT>
 static int launch_feat(const TraceArgs& a, uint32_t features, cudaStream_t stream) {
   if (features & FEAT_POL) return fail(OLB_ERR_UNSUPPORTED, "polarized trace not built in this version");
-  if ((features & (FEAT_ROT | FEAT_EXTRA)) != 0)
-    return launch_instance<T, RPT, FEAT_ROT | FEAT_NEWTON | FEAT_EXTRA>(a, stream);
-  if (features & FEAT_NEWTON) return launch_instance<T, RPT, FEAT_NEWTON>(a, stream);
-  return launch_instance<T, RPT, 0u>(a, stream);
+  if (features == 0) return launch_instance<T, RPT, 0u>(a, stream);
+  if (features == FEAT_ROT) return launch_instance<T, RPT, FEAT_ROT>(a, stream);
+  if (features == FEAT_NEWTON) return launch_instance<T, RPT, FEAT_NEWTON>(a, stream);
+  return launch_instance<T, RPT, FEAT_ROT | FEAT_NEWTON | FEAT_EXTRA>(a, stream);
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -363,7 +382,9 @@ static int trace_impl(const OlbDeviceTable* wh, int32_t first, int32_t last, con
   }
   if ((flags & OLB_TF_NO_FINAL) && !a.rx)
     return fail(OLB_ERR_INVALID_ARG, "OLB_TF_NO_FINAL needs record arrays (the result would be lost)");
-  if (vec_ok) return launch_feat<T, V>(a, features, stream);
+  // tuning knob (benchmarks only): OLB_FORCE_RPT=1 selects the scalar-access instantiation
+  static const int force_rpt = [] { const char* e = getenv("OLB_FORCE_RPT"); return e ? atoi(e) : 0; }();
+  if (vec_ok && force_rpt != 1) return launch_feat<T, V>(a, features, stream);
   return launch_feat<T, 1>(a, features, stream);
 }
 

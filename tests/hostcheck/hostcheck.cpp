@@ -63,12 +63,11 @@ static int run(const OlbTable* tab, int first, int last, int64_t n, T** ray, T**
   const unsigned char* blob = sizeof(T) == 8 ? pr.blob_f64.data() : pr.blob_f32.data();
   if (pr.features & FEAT_POL) { snprintf(err, err_len, "polarized not supported in hostcheck"); return OLB_ERR_UNSUPPORTED; }
   // exercise the same three instantiations the launcher picks from
-  if (pr.features & (FEAT_ROT | FEAT_EXTRA) || l0)
-    walk<T, FEAT_ROT | FEAT_NEWTON | FEAT_EXTRA>(blob, first, last, n, ray, rec, l0, status);
-  else if (pr.features & FEAT_NEWTON)
-    walk<T, FEAT_NEWTON>(blob, first, last, n, ray, rec, l0, status);
-  else
-    walk<T, 0u>(blob, first, last, n, ray, rec, l0, status);
+  uint32_t f = pr.features | (l0 ? FEAT_EXTRA : 0u);
+  if (f == 0) walk<T, 0u>(blob, first, last, n, ray, rec, l0, status);
+  else if (f == FEAT_ROT) walk<T, FEAT_ROT>(blob, first, last, n, ray, rec, l0, status);
+  else if (f == FEAT_NEWTON) walk<T, FEAT_NEWTON>(blob, first, last, n, ray, rec, l0, status);
+  else walk<T, FEAT_ROT | FEAT_NEWTON | FEAT_EXTRA>(blob, first, last, n, ray, rec, l0, status);
   return OLB_OK;
 }
 

@@ -126,3 +126,30 @@ def test_partial_range_and_noop(hc):
         assert rec[k].shape == (6, c.n)
         assert max_abs_err(rec[k], ref_rec[k]) <= 1e-11 * c.scale, k
     assert max_abs_err(out["opd"], ref_out["opd"]) <= 1e-11 * c.scale
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_degenerate_conic_roots(hc, dtype):
+    """a == 0 (axial rays onto a paraboloid: the reference's `-c/b` branch, standard.py:144-146),
+    a plane-like infinite radius StandardGeometry (N_safe guard :108-111) and rays that miss
+    (NaN in band) all follow the oracle without special-case branches in the kernel."""
+    from oracle import trace_oracle as O
+
+    n = 64
+    rng = np.random.default_rng(5)
+    x = rng.uniform(-3, 3, n)
+    y = rng.uniform(-3, 3, n)
+    x[-4:] = 60.0  # misses the R = 40 sphere below -> NaN
+    surfaces = [
+        T.SurfaceSpec(kind=T.GEOM_STANDARD, radius=-50.0, conic=-1.0, reflective=True, t=[0, 0, 10.0]),
+        T.SurfaceSpec(kind=T.GEOM_STANDARD, radius=float("inf"), t=[0, 0, 2.0], n1=[1.0], n2=[1.5]),
+        T.SurfaceSpec(kind=T.GEOM_STANDARD, radius=40.0, conic=0.0, t=[0, 0, -5.0], n1=[1.5], n2=[1.0]),
+    ]
+    tab = T.SurfaceTable(surfaces, [0.55])
+    rays = dict(x=x, y=y, z=np.zeros(n), L=np.zeros(n), M=np.zeros(n), N=np.ones(n), i=np.ones(n), w=np.full(n, 0.55))
+    _, orec, _ = O.trace(tab, rays)
+    _, rec, _ = run_hostcheck(hc, tab, rays, dtype)
+    assert np.isnan(orec["x"][-1][-4:]).all() and np.isfinite(orec["x"][-1][:-4]).all()
+    tol = 1e-12 * 60 if dtype == np.float64 else 5e-6 * 60  # steep rays at x = 60 mm amplify fp32 rounding
+    for k in REC:
+        assert max_abs_err(rec[k], orec[k]) <= tol, (k, max_abs_err(rec[k], orec[k]))
