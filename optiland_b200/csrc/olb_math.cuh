@@ -253,25 +253,36 @@ OLB_HD void newton_slopes(T x, T y, const PrepSurface<T>& S, const T* pool, T& f
 // when max over ALL rays |f| < tol; a kernel cannot see all rays, so each ray iterates
 // until its own |f| < tol and then takes ONE more step, which by quadratic convergence
 // leaves a residual ~tol^2: every ray ends at least as converged as in the reference,
-// and the two differ by at most the reference's own stopping residual (< tol).  In fp32
-// the tolerance is floored at the rounding noise of f so the loop cannot spin.
+// and the two differ by at most the reference's own stopping residual (< tol).
+// Rounding noise: the tolerance is floored at 8 eps (|z| + |sag|), and the loop also
+// stops as soon as a step fails to halve |f| (quadratic convergence has ended: the
+// iterate sits on the noise floor of f, which for fp32 polynomial sags lies above the
+// floor estimate) keeping the better of the last two iterates -- so fp32 cannot spin
+// to max_iter.
 template <typename T>
 OLB_HD T newton_distance(T x, T y, T z, T L, T M, T N, const PrepSurface<T>& S, const T* pool, int& status) {
   T t = conic_distance(x, y, z, L, M, N, S);
+  T t_prev = t, f_prev = (T)INFINITY;
   for (int it = 0; it < S.max_iter; ++it) {
     T xi = o_fma(t, L, x), yi = o_fma(t, M, y), zi = o_fma(t, N, z);
     T sag = newton_sag(xi, yi, S, pool, status);
     T f = sag - zi;
-    if (!(f == f)) break;  // NaN stays NaN (the reference would spin to max_iter on it)
+    T af = o_abs(f);
+    if (!(af == af)) break;  // NaN stays NaN (the reference would spin to max_iter on it)
     T tol = S.tol;
     T floor_ = (T)8 * Eps<T>::v * (o_abs(zi) + o_abs(sag));
     if (floor_ > tol) tol = floor_;
-    const bool conv = o_abs(f) < tol;
+    const bool conv = af < tol;
+    if (!conv && !(af < (T)0.5 * f_prev)) {  // stalled on the noise floor (or diverging)
+      if (!(af < f_prev)) t = t_prev;
+      break;
+    }
     T fx, fy;
     newton_slopes(xi, yi, S, pool, fx, fy);
     // f'(t) = fx L + fy M - N  with fx = -nx/nz = dz/dx  (newton_raphson.py:155-161)
     T df = o_fma(fx, L, o_fma(fy, M, -N));
     T dfs = o_abs(df) > (T)1e-14 ? df : (T)1e-14;
+    t_prev = t; f_prev = af;
     t -= o_div(f, dfs);
     if (conv) break;  // that was the polishing step
   }

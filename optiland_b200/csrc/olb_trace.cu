@@ -27,8 +27,12 @@ namespace olb {
 #ifndef OLB_BLOCK
 #define OLB_BLOCK 256
 #endif
-#ifndef OLB_MIN_BLOCKS
-#define OLB_MIN_BLOCKS 1
+// Minimum resident CTAs per SM asked of ptxas: 16 bytes of ray state per access (float4 /
+// double2) -> 2 CTAs (<= 128 registers), narrower variants -> 3 CTAs (<= 85 registers).
+#ifdef OLB_MIN_BLOCKS
+template <typename T, int RPT> struct MinBlocks { static constexpr int v = OLB_MIN_BLOCKS; };
+#else
+template <typename T, int RPT> struct MinBlocks { static constexpr int v = (sizeof(T) * RPT <= 8) ? 3 : 2; };
 #endif
 static constexpr int BLOCK = OLB_BLOCK;
 
@@ -105,6 +109,8 @@ __device__ __forceinline__ void store_rays(T* __restrict__ p, int64_t base, int 
   }
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // ---- TMA bulk copy of the prepared table into shared memory ------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -139,7 +145,7 @@ __device__ __forceinline__ void stage_table(unsigned char* smem, const unsigned 
 
 // ---- the kernel -----------------------------------------------------------------------------
 template <typename T, int RPT, uint32_t FEAT>
-__global__ void __launch_bounds__(BLOCK, OLB_MIN_BLOCKS) trace_kernel(const __grid_constant__ TraceArgs a) {
+__global__ void __launch_bounds__(BLOCK, (MinBlocks<T, RPT>::v)) trace_kernel(const __grid_constant__ TraceArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
   unsigned char* tab = smem + 16;
@@ -201,6 +207,18 @@ __global__ void __launch_bounds__(BLOCK, OLB_MIN_BLOCKS) trace_kernel(const __gr
       }
     }
 
+    // Pull the NEXT tile's launch state into L2 while this tile computes (no registers held):
+    // the first loads of the next iteration then see L2 latency instead of HBM latency.
+    {
+      const int64_t nb = base + (int64_t)gridDim.x * per_tile;
+      if (nb + RPT <= n && (threadIdx.x * RPT * (int)sizeof(T)) % 32 == 0) {
+        prefetch_l2((const T*)a.x + nb); prefetch_l2((const T*)a.y + nb); prefetch_l2((const T*)a.z + nb);
+        prefetch_l2((const T*)a.L + nb); prefetch_l2((const T*)a.M + nb); prefetch_l2((const T*)a.N + nb);
+        prefetch_l2((const T*)a.i + nb); prefetch_l2((const T*)a.opd + nb);
+        if (n_wl > 1) prefetch_l2((const T*)a.w + nb);
+      }
+    }
+
     bool have_frame = false;  // false: registers hold GLOBAL coordinates
     T gx[RPT], gy[RPT], gz[RPT], gL[RPT], gM[RPT], gN[RPT];
 #pragma unroll
@@ -219,7 +237,7 @@ __global__ void __launch_bounds__(BLOCK, OLB_MIN_BLOCKS) trace_kernel(const __gr
 #pragma unroll
           for (int k = 0; k < RPT; ++k) surface_step_k<T, FEAT, KIND_CONIC>(r[k], S, pool, fg, status);
         } else if constexpr ((FEAT & FEAT_NEWTON) != 0) {
-#pragma unroll 1  // one copy of the Newton / polynomial code: keep the kernel inside the I-cache
+#pragma unroll  // (the launcher gives Newton tables RPT <= 2, so this stays inside the I-cache)
           for (int k = 0; k < RPT; ++k) surface_step_k<T, FEAT, KIND_NEWTON>(r[k], S, pool, fg, status);
         }
         have_frame = true;
@@ -325,6 +343,14 @@ static int launch_feat(const TraceArgs& a, uint32_t features, cudaStream_t strea
   return launch_instance<T, RPT, FEAT_ROT | FEAT_NEWTON | FEAT_EXTRA>(a, stream);
 }
 
+// fp32 x 4 rays/thread exists only for the closed-form feature sets (code size, registers).
+template <typename T, int RPT>
+static int launch_feat_cf(const TraceArgs& a, uint32_t features, cudaStream_t stream) {
+  if (features & FEAT_POL) return fail(OLB_ERR_UNSUPPORTED, "polarized trace not built in this version");
+  if (features == 0) return launch_instance<T, RPT, 0u>(a, stream);
+  return launch_instance<T, RPT, FEAT_ROT>(a, stream);
+}
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 template <typename T>
@@ -364,7 +390,7 @@ static int trace_impl(const OlbDeviceTable* wh, int32_t first, int32_t last, con
     features |= FEAT_EXTRA;
   }
   constexpr int V = sizeof(T) == 4 ? 4 : 2;
-  bool vec_ok = true;
+  bool vec_ok = true, rec_stride_ok2 = true;
   if (rec) {
     void* rr[] = {rec->x, rec->y, rec->z, rec->L, rec->M, rec->N, rec->intensity, rec->opd};
     int n_set = 0;
@@ -378,13 +404,26 @@ static int trace_impl(const OlbDeviceTable* wh, int32_t first, int32_t last, con
       a.rx = rec->x; a.ry = rec->y; a.rz = rec->z; a.rL = rec->L; a.rM = rec->M; a.rN = rec->N;
       a.ri = rec->intensity; a.ropd = rec->opd; a.rec_stride = rec->row_stride;
       if (rec->row_stride % V) vec_ok = false;
+      if (rec->row_stride % 2) rec_stride_ok2 = false;
     }
   }
   if ((flags & OLB_TF_NO_FINAL) && !a.rx)
     return fail(OLB_ERR_INVALID_ARG, "OLB_TF_NO_FINAL needs record arrays (the result would be lost)");
-  // tuning knob (benchmarks only): OLB_FORCE_RPT=1 selects the scalar-access instantiation
+  // Rays per thread.  Closed-form tables (planes / conics, optionally rotated): fp32 -> 4
+  // (float4 accesses, 120 regs, 16 warps/SM), fp64 -> 1 (74 regs, 24 warps/SM).  Tables with
+  // Newton surfaces / aperture programs / coatings: fp32 -> 2, fp64 -> 1 (their per-ray code
+  // is large; more rays per thread only spills).  Measured: profiles/tune_r1.md.
+  // OLB_FORCE_RPT is a tuning knob for benchmarks only.
   static const int force_rpt = [] { const char* e = getenv("OLB_FORCE_RPT"); return e ? atoi(e) : 0; }();
-  if (vec_ok && force_rpt != 1) return launch_feat<T, V>(a, features, stream);
+  const bool closed_form = (features & ~FEAT_ROT) == 0;
+  int rpt = force_rpt > 0 ? force_rpt : (sizeof(T) == 4 ? (closed_form ? 4 : 2) : 1);
+  if (!closed_form && rpt > 2) rpt = 2;
+  if constexpr (sizeof(T) == 4) {
+    if (rpt >= 4 && vec_ok) return launch_feat_cf<T, 4>(a, features, stream);
+    if (rpt >= 2 && rec_stride_ok2) return launch_feat<T, 2>(a, features, stream);
+  } else {
+    if (rpt >= 2 && vec_ok) return launch_feat<T, 2>(a, features, stream);
+  }
   return launch_feat<T, 1>(a, features, stream);
 }
 
