@@ -1,0 +1,240 @@
+"""Drop-in for Optiland: the CUDA trace loop behind ``optiland.backend``'s registry.
+
+``install()``:
+
+1. registers ``B200TorchBackend`` -- a subclass of the reference's ``TorchBackend``
+   (/root/reference/optiland/backend/torch_backend.py:113) that keeps all of its ~140 array
+   ops (so autograd interop and every ``be.*`` call are unchanged), still reports the name
+   ``"torch"`` (28 call sites branch on ``be.get_backend() == "torch"``) and adds ONE
+   capability, ``trace_surfaces(surface_group, rays, start, stop) -> bool``; it is installed
+   the way the reference's own test registers a foreign backend
+   (/root/reference/tests/test_backend.py:79-85): by assignment into ``_backends``;
+2. wraps ``SurfaceGroup.trace`` (optiland/surfaces/surface_group.py:245-257) and ``Surface.trace``
+   (optiland/surfaces/standard_surface.py:200-215, the per-surface entry the ray aimers use) so that
+   they try the capability first and run the reference's own Python body when it declines
+   (unsupported surface kind, CPU tensors, gradients requested, ...).
+
+``Optic.trace``, ``SpotDiagram``, ``Wavefront``, PSF and the optimisers are untouched and call
+the path unchanged.  Declining is NOT a CPU fallback of this package: it hands the call back to
+the reference's own code, which is what runs today.
+"""
+from __future__ import annotations
+
+import threading
+from collections import OrderedDict
+
+import numpy as np
+
+from . import table as T
+from .pack import UnsupportedSurface, pack_surface, pack_surface_group
+
+_REC_ATTR = (("x", "x"), ("y", "y"), ("z", "z"), ("L", "L"), ("M", "M"), ("N", "N"),
+             ("intensity", "intensity"), ("opd", "opd"))
+_tls = threading.local()
+_state: dict = {"installed": False}
+
+
+class CudaEngine:
+    """Runs a packed table on the GPU through libolb (``optiland_b200.trace``)."""
+
+    def __init__(self, cache_size: int = 8):
+        self._cache: OrderedDict[bytes, object] = OrderedDict()
+        self._cache_size = cache_size
+
+    def accepts(self, rays) -> bool:
+        import torch
+
+        keys = ("x", "y", "z", "L", "M", "N", "i", "w", "opd")
+        ts = [getattr(rays, k, None) for k in keys]
+        if any(not torch.is_tensor(t) for t in ts):
+            return False
+        t0 = ts[0]
+        if not t0.is_cuda or t0.dtype not in (torch.float32, torch.float64) or t0.ndim != 1:
+            return False
+        return all(t.is_cuda and t.dtype == t0.dtype and t.shape == t0.shape and t.device == t0.device for t in ts)
+
+    def device_table(self, table: T.SurfaceTable, device):
+        from .trace import DeviceTable
+
+        surf, pool = table.pack()
+        key = surf.tobytes() + pool.tobytes() + table.wavelengths.tobytes() + str(device).encode()
+        dt = self._cache.get(key)
+        if dt is None:
+            dt = DeviceTable(table, device)
+            self._cache[key] = dt
+            while len(self._cache) > self._cache_size:
+                self._cache.popitem(last=False)
+        else:
+            self._cache.move_to_end(key)
+        return dt
+
+    def trace(self, table: T.SurfaceTable, rays, first: int, last: int):
+        """Trace Optiland's ``rays`` object in place; return {key: (rows, N) tensor}."""
+        from .trace import RealRays, trace_device
+
+        shell = RealRays.__new__(RealRays)
+        for k in ("x", "y", "z", "L", "M", "N", "i", "w", "opd"):
+            t = getattr(rays, k).detach().contiguous()
+            if t.data_ptr() % 16:
+                t = t.clone()
+            setattr(shell, k, t)
+        shell.L0 = shell.M0 = shell.N0 = None
+        shell.is_normalized = True
+        dt = self.device_table(table, shell.x.device)
+        rec = trace_device(dt, shell, first, last, record=True)
+        for k in ("x", "y", "z", "L", "M", "N", "i", "opd"):
+            setattr(rays, k, getattr(shell, k))
+        return rec
+
+
+def _unique_wavelengths(w):
+    """Distinct wavelengths of the batch (exact values), or None if there are too many."""
+    import torch
+
+    if w.numel() == 0:
+        return None
+    lo, hi = torch.aminmax(w)
+    if bool(lo == hi):
+        return np.array([float(lo)], dtype=np.float64)
+    u = torch.unique(w)
+    if u.numel() > T.MAX_WAVELENGTHS:
+        return None
+    return u.double().cpu().numpy()
+
+
+def _set_pre_interaction_direction(rays, table, rec, first, last, launch_dir):
+    """rays.L0/M0/N0: direction before the last interaction, in the last surface's local frame
+    (optiland/rays/real_rays.py:170-172).  It equals the direction recorded after the previous
+    surface (or the launch direction), rotated into that frame -- no kernel output needed."""
+    if last - first >= 2:
+        Lg, Mg, Ng = rec["L"][-2], rec["M"][-2], rec["N"][-2]
+    else:
+        Lg, Mg, Ng = launch_dir
+    s = table.surfaces[last - 1]
+    if s.kind == T.GEOM_NOOP:
+        return
+    if s.rotated:
+        R = s.R
+        L0 = R[0, 0] * Lg + R[1, 0] * Mg + R[2, 0] * Ng
+        M0 = R[0, 1] * Lg + R[1, 1] * Mg + R[2, 1] * Ng
+        N0 = R[0, 2] * Lg + R[1, 2] * Mg + R[2, 2] * Ng
+    else:
+        L0, M0, N0 = Lg, Mg, Ng
+    rays.L0, rays.M0, rays.N0 = L0, M0, N0
+
+
+def _try_trace(backend, surfaces, rays, table_builder) -> bool:
+    """Common body of the two wrappers.  ``surfaces``: the Surface objects to be traced (in
+    order); ``table_builder(wavelengths)`` packs them.  Returns False to decline."""
+    if type(rays).__name__ != "RealRays":
+        return False  # PolarizedRays / ParaxialRays: reference path
+    engine = _state["engine"]
+    if not engine.accepts(rays):
+        return False
+    if backend.grad_mode.requires_grad:
+        return False  # autograd through the kernel is not built yet: reference's eager graph
+    wl = _unique_wavelengths(rays.w)
+    if wl is None:
+        return False
+    try:
+        table = table_builder(wl)
+    except UnsupportedSurface:
+        return False
+    if any(s.coating == T.COAT_FRESNEL for s in table.surfaces):
+        return False
+    launch_dir = (rays.L, rays.M, rays.N)
+    rec = engine.trace(table, rays, 0, table.num_surfaces)
+    for row, surf in enumerate(surfaces):
+        for attr, key in _REC_ATTR:
+            setattr(surf, attr, rec[key][row])
+    _set_pre_interaction_direction(rays, table, rec, 0, table.num_surfaces, launch_dir)
+    return True
+
+
+def install(engine=None, alias: str | None = None) -> None:
+    """Register the backend and wrap the two trace entry points (idempotent)."""
+    import optiland.backend as be
+    from optiland.backend.torch_backend import TorchBackend
+    from optiland.surfaces.standard_surface import Surface
+    from optiland.surfaces.surface_group import SurfaceGroup
+
+    if _state["installed"]:
+        if engine is not None:
+            _state["engine"] = engine
+        return
+    _state["engine"] = engine if engine is not None else CudaEngine()
+
+    class B200TorchBackend(TorchBackend):
+        """TorchBackend + one capability: the fused CUDA trace loop."""
+
+        def trace_surfaces(self, surface_group, rays, start: int, stop: int) -> bool:
+            surfaces = list(surface_group.surfaces)[start:stop]
+            if not surfaces:
+                return False
+
+            def build(wl):
+                full = pack_surface_group(surface_group, wl)
+                return T.SurfaceTable(full.surfaces[start:stop], full.wavelengths)
+
+            return _try_trace(self, surfaces, rays, build)
+
+        def trace_surface(self, surface, rays) -> bool:
+            if type(surface).__name__ not in ("Surface", "ImageSurface"):
+                return False
+            return _try_trace(self, [surface], rays,
+                              lambda wl: T.SurfaceTable([pack_surface(surface, wl)], wl))
+
+    registry = be.__getattr__.__globals__["_backends"]  # same hook as tests/test_backend.py:79-85
+    old = registry.get("torch")
+    new = B200TorchBackend()
+    if old is not None and hasattr(old, "_config"):
+        new._config = old._config  # keep device / precision / grad-mode settings
+    registry["torch"] = new
+    if alias:
+        registry[alias] = new
+
+    orig_group_trace = SurfaceGroup.trace
+    orig_surface_trace = Surface.trace
+
+    def group_trace(self, rays, skip=0):
+        backend = registry.get(be.get_backend())
+        if hasattr(backend, "trace_surfaces") and not getattr(_tls, "in_reference", False):
+            self.reset()
+            if backend.trace_surfaces(self, rays, skip, len(self.surfaces)):
+                return rays
+        _tls.in_reference = True
+        try:
+            return orig_group_trace(self, rays, skip)
+        finally:
+            _tls.in_reference = False
+
+    def surface_trace(self, rays):
+        backend = registry.get(be.get_backend())
+        if hasattr(backend, "trace_surface") and not getattr(_tls, "in_reference", False):
+            self.reset()
+            if backend.trace_surface(self, rays):
+                return rays
+        return orig_surface_trace(self, rays)
+
+    SurfaceGroup.trace = group_trace
+    Surface.trace = surface_trace
+    _state.update(installed=True, orig_group_trace=orig_group_trace, orig_surface_trace=orig_surface_trace,
+                  old_backend=old, alias=alias)
+
+
+def uninstall() -> None:
+    if not _state.get("installed"):
+        return
+    import optiland.backend as be
+    from optiland.surfaces.standard_surface import Surface
+    from optiland.surfaces.surface_group import SurfaceGroup
+
+    registry = be.__getattr__.__globals__["_backends"]
+    SurfaceGroup.trace = _state["orig_group_trace"]
+    Surface.trace = _state["orig_surface_trace"]
+    if _state.get("old_backend") is not None:
+        registry["torch"] = _state["old_backend"]
+    if _state.get("alias"):
+        registry.pop(_state["alias"], None)
+    _state.clear()
+    _state["installed"] = False

@@ -1,0 +1,194 @@
+"""Host logic of the Optiland plugin (backend registration, SurfaceGroup.trace / Surface.trace
+wrappers, packing of LIVE reference objects, record hand-back, declining) exercised against the
+unmodified reference.  Runs only where /root/reference exists (the build container).
+
+There is no GPU here, so the device call is replaced by a TEST-ONLY engine that evaluates the
+packed table with the NumPy oracle; everything else is the product code path.  The same packed
+tables run on the real kernel in tests/test_gpu_parity.py.
+"""
+import numpy as np
+import pytest
+
+from oracle.ref_import import reference_available
+
+pytestmark = pytest.mark.skipif(not reference_available(), reason="reference not present on this box")
+
+
+class OracleEngine:
+    """TEST-ONLY stand-in for optiland_b200.plugin.CudaEngine."""
+
+    def __init__(self):
+        self.calls = []
+
+    def accepts(self, rays):
+        import torch
+
+        return all(torch.is_tensor(getattr(rays, k)) for k in ("x", "y", "z", "L", "M", "N", "i", "w", "opd"))
+
+    def trace(self, table, rays, first, last):
+        import torch
+
+        from oracle import trace_oracle as O
+
+        self.calls.append((table.num_surfaces, int(rays.x.numel())))
+        inp = {k: getattr(rays, k).detach().double().numpy() for k in ("x", "y", "z", "L", "M", "N", "i", "w", "opd")}
+        out, rec, status = O.trace(table, inp, first, last)
+        if status:
+            raise ValueError("Zernike coordinates must be normalized to [-1, 1].")
+        dt = rays.x.dtype
+        for k in ("x", "y", "z", "L", "M", "N", "i", "opd"):
+            setattr(rays, k, torch.from_numpy(out[k]).to(dt))
+        return {k: torch.from_numpy(v).to(dt) for k, v in rec.items()}
+
+
+@pytest.fixture()
+def plugin():
+    from oracle.ref_import import import_reference
+
+    import_reference()
+    import optiland.backend as be
+
+    from optiland_b200 import plugin as P
+
+    be.set_backend("torch")
+    be.set_precision("float64")
+    be.grad_mode.disable()
+    eng = OracleEngine()
+    P.install(engine=eng)
+    yield P, eng, be
+    P.uninstall()
+    be.set_backend("numpy")
+
+
+def _numpy_reference(make_lens, trace):
+    import optiland.backend as be
+
+    be.set_backend("numpy")
+    lens = make_lens()
+    rays = trace(lens)
+    out = {k: np.array(getattr(lens.surfaces, k)) for k in ("x", "y", "z", "L", "M", "N", "opd", "intensity")}
+    fin = {k: np.array(getattr(rays, k)) for k in ("x", "y", "z", "L", "M", "N", "i", "opd")}
+    be.set_backend("torch")
+    return out, fin
+
+
+def test_backend_registration_keeps_name_torch(plugin):
+    P, eng, be = plugin
+    assert be.get_backend() == "torch"
+    backend = be.__getattr__.__globals__["_backends"]["torch"]
+    assert type(backend).__name__ == "B200TorchBackend" and backend.name == "torch"
+    assert hasattr(backend, "trace_surfaces")
+    assert float(be.sin(be.array(0.5))) == pytest.approx(np.sin(0.5))  # every TorchBackend op still there
+
+
+def test_optic_trace_goes_through_capability_and_matches_numpy(plugin):
+    P, eng, be = plugin
+    from optiland.samples.objectives import DoubleGauss
+
+    def trace(lens):
+        return lens.trace(Hx=0.0, Hy=0.7, wavelength=0.5876, num_rays=8, distribution="hexapolar")
+
+    ref_rec, ref_fin = _numpy_reference(DoubleGauss, trace)
+    lens = DoubleGauss()
+    rays = trace(lens)
+    assert eng.calls and eng.calls[-1][0] == 13  # whole surface group in ONE engine call
+    for k, v in ref_rec.items():
+        got = be.to_numpy(getattr(lens.surfaces, k))
+        assert got.shape == v.shape
+        np.testing.assert_allclose(got, v, rtol=0, atol=1e-11)
+    for k, v in ref_fin.items():
+        np.testing.assert_allclose(be.to_numpy(getattr(rays, k)), v, rtol=0, atol=1e-11)
+    # L0/M0/N0 = direction before the last interaction
+    np.testing.assert_allclose(be.to_numpy(rays.L0), ref_rec["L"][-2], atol=1e-12)
+
+
+def test_spot_diagram_runs_unchanged_on_top(plugin):
+    """Config 1: analysis layer untouched; golden RMS radii of /root/reference/tests/test_analysis.py:88-102."""
+    P, eng, be = plugin
+    from optiland.analysis import SpotDiagram
+    from optiland.samples.objectives import CookeTriplet
+
+    spot = SpotDiagram(CookeTriplet())
+    rms = spot.rms_spot_radius()
+    assert len(eng.calls) >= 9
+    golden = [[0.003791335461448, 0.004293689564257, 0.006195618755672],
+              [0.01582480029344623, 0.016918412809703662, 0.019221165873836682],
+              [0.013236232767092956, 0.012116688566406967, 0.013648684944411313]]
+    for f in range(3):
+        for w in range(3):
+            assert float(rms[f][w]) == pytest.approx(golden[f][w], rel=1e-9)
+
+
+def test_declines_and_falls_back_to_reference_python(plugin):
+    P, eng, be = plugin
+    from optiland.samples.objectives import CookeTriplet
+
+    # gradients requested -> decline (autograd through the kernel not built yet)
+    be.grad_mode.enable()
+    n0 = len(eng.calls)
+    lens = CookeTriplet()
+    rays = lens.trace(0.0, 1.0, 0.55, 4, "hexapolar")
+    assert len(eng.calls) == n0 and rays.x.requires_grad
+    be.grad_mode.disable()
+
+    # unsupported geometry (toroidal) -> decline, results still those of the reference
+    def make():
+        from optiland import optic
+
+        lens = optic.Optic()
+        lens.surfaces.add(index=0, radius=be.inf, thickness=be.inf)
+        lens.surfaces.add(index=1, surface_type="toroidal", radius_x=50.0, radius_y=60.0, thickness=5.0,
+                          material="N-BK7", is_stop=True)
+        lens.surfaces.add(index=2, radius=-80.0, thickness=50.0)
+        lens.surfaces.add(index=3)
+        lens.set_aperture(aperture_type="EPD", value=10.0)
+        lens.fields.set_type(field_type="angle")
+        lens.fields.add(y=0)
+        lens.wavelengths.add(value=0.55, is_primary=True)
+        return lens
+
+    def trace(lens):
+        return lens.trace(0.0, 0.0, 0.55, 4, "hexapolar")
+
+    ref_rec, _ = _numpy_reference(make, trace)
+    n0 = len(eng.calls)
+    lens = make()
+    trace(lens)
+    assert all(c[0] != 4 for c in eng.calls[n0:])  # the 4-surface group was never handed to the engine
+    np.testing.assert_allclose(be.to_numpy(lens.surfaces.y), ref_rec["y"], atol=1e-10)
+
+
+def test_per_surface_entry_used_by_ray_aimers(plugin):
+    """Surface.trace (one surface) is what iterative ray aiming calls (ray_aiming/iterative.py:366)."""
+    P, eng, be = plugin
+    from optiland.samples.objectives import CookeTriplet
+
+    def trace(lens):
+        lens.set_ray_aiming("iterative", max_iter=10, tol=1e-9)
+        return lens.trace(0.0, 0.7, 0.55, 4, "hexapolar")
+
+    ref_rec, ref_fin = _numpy_reference(CookeTriplet, trace)
+    n0 = len(eng.calls)
+    lens = CookeTriplet()
+    rays = trace(lens)
+    assert any(c[0] == 1 for c in eng.calls[n0:])  # single-surface tables were traced
+    np.testing.assert_allclose(be.to_numpy(rays.y), ref_fin["y"], atol=1e-9)
+    np.testing.assert_allclose(be.to_numpy(lens.surfaces.x), ref_rec["x"], atol=1e-9)
+
+
+def test_multi_wavelength_and_zernike_error(plugin):
+    P, eng, be = plugin
+    from optiland.samples.objectives import DoubleGauss
+
+    lens = DoubleGauss()
+    n = 30
+    Px = np.linspace(-0.5, 0.5, n)
+    wl = np.tile([0.4861, 0.5876, 0.6563], n // 3)
+    rays = lens.ray_tracer.ray_generator.generate_rays(be.zeros(n), be.zeros(n), be.array(Px), be.zeros(n), be.array(wl))
+    lens.surfaces.trace(rays)
+    be.set_backend("numpy")
+    ref = DoubleGauss()
+    r2 = ref.ray_tracer.ray_generator.generate_rays(np.zeros(n), np.zeros(n), Px, np.zeros(n), wl)
+    ref.surfaces.trace(r2)
+    be.set_backend("torch")
+    np.testing.assert_allclose(be.to_numpy(rays.opd), np.array(r2.opd), atol=1e-11)
