@@ -199,15 +199,9 @@ def run_ours(args):
     # ---- surface table: rank 0 packs, NCCL-broadcasts the (tiny) packed table ----------
     c, sc = load_case()
     if world > 1:
-        surf, pool = c.table.pack()
-        raw = np.concatenate([surf.view(np.uint8).ravel(), pool.view(np.uint8).ravel(),
-                              c.table.wavelengths.view(np.uint8).ravel()])
-        tbytes = torch.from_numpy(raw.copy()).to(dev) if rank == 0 else torch.empty(raw.size, dtype=torch.uint8, device=dev)
-        dist.broadcast(tbytes, src=0)
-        raw = tbytes.cpu().numpy()
-        ns, npool = surf.size * T.OLB_SURFACE_DTYPE.itemsize, pool.size * 8
-        table = T.SurfaceTable.unpack(raw[:ns].view(T.OLB_SURFACE_DTYPE), raw[ns:ns + npool].view(np.float64),
-                                      raw[ns + npool:].view(np.float64))
+        from optiland_b200.distributed import broadcast_table
+
+        table = broadcast_table(c.table if rank == 0 else None, src=0)
     else:
         table = c.table
     dtab = DeviceTable(table, dev)
@@ -337,7 +331,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_kind,
                          "algorithmic_bytes_per_ray": bytes_per_ray, "kernel_ms": kern_ms,
-                         "kernel": "olb::trace_kernel<%s,%d,0>" % ("float" if es == 4 else "double", vec)},
+                         "kernel": "olb::trace_kernel<%s,%d,0>" % (("float", 4) if es == 4 else ("double", 1))},
             "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cpu_threads, "kind": "port",
                              "sample": f"{cpu_n} rays x {n_traced} surfaces in {cpu_dt:.1f} s, NumPy fp64 oracle port, "
                                        f"{cpu_threads} threads over 100k-ray chunks (os.cpu_count={os.cpu_count()})"},

@@ -1,0 +1,79 @@
+"""Multi-GPU plumbing for the trace path: one process per GPU (``torch.distributed``).
+
+Rays are independent: each rank traces a contiguous range of the batch,
+so there is NO data-path collective.  The only exchanges are
+  * a broadcast of the packed surface table (a few KiB) from the rank that owns the live
+    Optiland objects, and
+  * optional all-reduces of analysis moments (spot centroid / RMS radius) -- a handful of
+    scalars, latency-bound on NVLink/NVSwitch.
+Works with the ``nccl`` backend (CUDA tensors) and with ``gloo`` (CPU tensors; used by the
+world_size-2 tests that run without GPUs).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import table as T
+
+
+def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous slice [lo, hi) of n rays owned by ``rank``; keeps field/pupil ordering so the
+    per-rank record rows concatenate into the reference's (S, N) layout."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def _comm_device(group=None) -> torch.device:
+    backend = dist.get_backend(group)
+    return torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+
+
+def broadcast_table(table: T.SurfaceTable | None, src: int = 0, group=None) -> T.SurfaceTable:
+    """Broadcast a packed ``SurfaceTable`` from ``src`` to every rank (others pass ``None``)."""
+    dev = _comm_device(group)
+    rank = dist.get_rank(group)
+    if rank == src:
+        surf, pool = table.pack()
+        wl = np.ascontiguousarray(table.wavelengths, dtype=np.float64)
+        raw = np.concatenate([surf.view(np.uint8).ravel(), pool.view(np.uint8).ravel(), wl.view(np.uint8).ravel()])
+        sizes = torch.tensor([surf.size, pool.size, wl.size], dtype=torch.int64, device=dev)
+    else:
+        sizes = torch.zeros(3, dtype=torch.int64, device=dev)
+    dist.broadcast(sizes, src=src, group=group)
+    ns, npool, nwl = (int(v) for v in sizes.cpu())
+    total = ns * T.OLB_SURFACE_DTYPE.itemsize + 8 * npool + 8 * nwl
+    buf = torch.from_numpy(raw.copy()).to(dev) if rank == src else torch.empty(total, dtype=torch.uint8, device=dev)
+    dist.broadcast(buf, src=src, group=group)
+    raw = buf.cpu().numpy()
+    a = ns * T.OLB_SURFACE_DTYPE.itemsize
+    b = a + 8 * npool
+    return T.SurfaceTable.unpack(raw[:a].view(T.OLB_SURFACE_DTYPE).copy(), raw[a:b].view(np.float64).copy(),
+                                 raw[b:].view(np.float64).copy())
+
+
+def _allreduce_sum(v: torch.Tensor, group=None) -> torch.Tensor:
+    if dist.is_available() and dist.is_initialized():
+        v = v.to(_comm_device(group))
+        dist.all_reduce(v, op=dist.ReduceOp.SUM, group=group)
+    return v.cpu()
+
+
+def global_rms_spot_radius(x: torch.Tensor, y: torch.Tensor, intensity: torch.Tensor, group=None) -> float:
+    """RMS spot radius about the centroid over ALL ranks' rays (the rms_spot_size operand,
+    optiland/optimization/operand/ray.py:299-342, sharded).  Rays with i <= 0 or non-finite
+    intercepts are masked as in optiland/analysis/spot_diagram/core.py:471-472.  Two 3-/1-scalar
+    all-reduces (centroid first, then the centred second moment: the one-pass form loses 8
+    digits on an off-axis field); both are latency-bound."""
+    m = (intensity > 0) & torch.isfinite(x) & torch.isfinite(y)
+    zero = torch.zeros((), dtype=torch.float64, device=x.device)
+    xd = torch.where(m, x.double(), zero)
+    yd = torch.where(m, y.double(), zero)
+    cnt, sx, sy = (float(v) for v in _allreduce_sum(torch.stack([m.sum().double(), xd.sum(), yd.sum()]), group))
+    if cnt == 0:
+        return float("nan")
+    cx, cy = sx / cnt, sy / cnt
+    d2 = torch.where(m, (x.double() - cx) ** 2 + (y.double() - cy) ** 2, zero).sum().reshape(1)
+    return float(np.sqrt(float(_allreduce_sum(d2, group)[0]) / cnt))
