@@ -99,6 +99,7 @@ extern "C" {
 
 /* ---- trace flags (argument `flags` of olb_trace_*) ------------------------ */
 #define OLB_TF_POLARIZED   (1u << 0)  /* rays carry a 3x3 complex P matrix (OlbRays.p)  */
+#define OLB_TF_POL_IDENTITY (1u << 2) /* with POLARIZED: P starts as identity, rays.p is output only */
 #define OLB_TF_NO_FINAL    (1u << 1)  /* do not write the final state back into rays.x..opd:
                                          the caller takes it from the last record row (saves
                                          32-64 B/ray of HBM writes; needs rec)              */
@@ -179,9 +180,12 @@ typedef struct OlbTable {
  *   w       wavelength per ray; may be NULL when the table has n_wl == 1
  *   L0..N0  optional outputs: direction before the last interaction, in the
  *           last surface's local frame (real_rays.py:170-172); NULL to skip
- *   p       optional 3x3 complex polarization matrix per ray
- *           (optiland/rays/polarized_rays.py:50), layout [18][n_rays]:
- *           plane 2*(3*r+c) = Re P[r][c], plane 2*(3*r+c)+1 = Im P[r][c]
+ *   p       3x3 complex polarization matrix per ray (optiland/rays/polarized_rays.py:50);
+ *           required with OLB_TF_POLARIZED.  Layout: a contiguous complex (N,3,3) array,
+ *           i.e. [n_rays][3][3][2] elements with (Re, Im) interleaved -- exactly the memory
+ *           of the reference's `rays.p` tensor (torch.view_as_real).  Updated in place; with
+ *           OLB_TF_POL_IDENTITY the input is not read (P starts as the identity, as
+ *           PolarizedRays.__init__ sets it).
  */
 typedef struct OlbRays {
   void* x; void* y; void* z;

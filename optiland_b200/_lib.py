@@ -22,6 +22,7 @@ ERRORS = {-1: "OLB_ERR_INVALID_ARG", -2: "OLB_ERR_UNSUPPORTED", -3: "OLB_ERR_CUD
 
 TF_POLARIZED = 1 << 0
 TF_NO_FINAL = 1 << 1
+TF_POL_IDENTITY = 1 << 2
 
 
 class OlbTable(C.Structure):

@@ -65,6 +65,8 @@ struct Ray {
   T opd_lo;    // fp32 only: low word of a two-float OPD accumulator (see accumulate_opd)
   T L0, M0, N0;  // direction before the last interaction (real_rays.py:170-172)
   int widx;    // wavelength index into the media tables
+  T P[18];     // FEAT_POL only: 3x3 complex polarization matrix, P[2*(3r+c)] = Re, +1 = Im
+               // (optiland/rays/polarized_rays.py:50); untouched (and optimised away) otherwise
 };
 
 // OPD accumulation: opd += |t * n1|  (standard_surface.py:244).  In fp32 the sum is
@@ -325,6 +327,80 @@ OLB_HD bool aperture_inside(const T* prog, int len, T x, T y) {
   return stack & 1u;
 }
 
+
+// ---- polarization (PolarizedRays.update, polarized_rays.py:136-202; JonesFresnel, jones.py:71-117) ----
+template <typename T> struct Cx { T re, im; };
+template <typename T> OLB_HD Cx<T> c_mul(Cx<T> a, Cx<T> b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+template <typename T> OLB_HD Cx<T> c_div(Cx<T> a, Cx<T> b) {
+  T d = o_rcp(o_fma(b.re, b.re, b.im * b.im));
+  return {(a.re * b.re + a.im * b.im) * d, (a.im * b.re - a.re * b.im) * d};
+}
+
+// P := O_out * J * O_in * P for one ray.  k0 = (L0,M0,N0), k1 = (L,M,N) in the surface's local
+// frame (the reference mixes local frames across tilted surfaces; reproduced).  `cosi` = |n.k0|.
+template <typename T>
+OLB_HD void polar_update(Ray<T>& r, const PrepSurface<T>& S, T ncoat, T cosi) {
+  const T k0[3] = {r.L0, r.M0, r.N0}, k1[3] = {r.L, r.M, r.N};
+  // s = k0 x k1, with the reference's fallback when k0 || k1 (polarized_rays.py:151-163)
+  T s[3] = {k0[1] * k1[2] - k0[2] * k1[1], k0[2] * k1[0] - k0[0] * k1[2], k0[0] * k1[1] - k0[1] * k1[0]};
+  T mag = o_sqrt(o_fma(s[0], s[0], o_fma(s[1], s[1], s[2] * s[2])));
+  if (mag == 0) {
+    T pf[3] = {(T)0, k0[2], -k0[1]};                       // k0 x (1,0,0)
+    if (o_fma(pf[1], pf[1], pf[2] * pf[2]) == 0) { pf[0] = -k0[2]; pf[1] = 0; pf[2] = k0[0]; }  // k0 x (0,1,0)
+    s[0] = pf[1] * k0[2] - pf[2] * k0[1];                  // p_fallback x k0
+    s[1] = pf[2] * k0[0] - pf[0] * k0[2];
+    s[2] = pf[0] * k0[1] - pf[1] * k0[0];
+    mag = o_sqrt(o_fma(s[0], s[0], o_fma(s[1], s[1], s[2] * s[2])));
+  }
+  T inv = o_rcp(mag);
+  s[0] *= inv; s[1] *= inv; s[2] *= inv;
+  const T p0[3] = {k0[1] * s[2] - k0[2] * s[1], k0[2] * s[0] - k0[0] * s[2], k0[0] * s[1] - k0[1] * s[0]};
+  const T p1[3] = {k1[1] * s[2] - k1[2] * s[1], k1[2] * s[0] - k1[0] * s[2], k1[0] * s[1] - k1[1] * s[0]};
+  // Jones diagonal (js, jp, jk)
+  Cx<T> js = {(T)1, (T)0}, jp = {(T)1, (T)0};
+  T jk = 1;
+  if (S.coating == OLB_COAT_FRESNEL) {
+    // aoi = arccos(clip(|n.k0|)) (coatings.py:72-93): cos(aoi) = c, sin^2(aoi) = 1 - c^2
+    T c = cosi > (T)1 ? (T)1 : cosi;
+    T n = ncoat, n2 = n * n;
+    T rad = n2 - o_fma(-c, c, (T)1);
+    Cx<T> root = rad >= 0 ? Cx<T>{o_sqrt(rad), (T)0} : Cx<T>{(T)0, o_sqrt(-rad)};   // principal sqrt
+    if (!(rad == rad)) root = Cx<T>{rad, (T)0};
+    Cx<T> cc = {c, (T)0}, n2c = {n2 * c, (T)0};
+    if (S.flags & OLB_SF_REFLECT) {
+      js = c_div(Cx<T>{cc.re - root.re, -root.im}, Cx<T>{cc.re + root.re, root.im});
+      Cx<T> pp = c_div(Cx<T>{n2c.re - root.re, -root.im}, Cx<T>{n2c.re + root.re, root.im});
+      jp = {-pp.re, -pp.im};
+      jk = -1;
+    } else {
+      js = c_div(Cx<T>{2 * c, (T)0}, Cx<T>{cc.re + root.re, root.im});
+      jp = c_div(Cx<T>{2 * n * c, (T)0}, Cx<T>{n2c.re + root.re, root.im});
+    }
+  }
+  // M[r][c] = s_r js s_c + p1_r jp p0_c + k1_r jk k0_c      (o_out @ J @ o_in)
+  Cx<T> Mx[9];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      T ss = s[a] * s[b], pp = p1[a] * p0[b], kk = k1[a] * k0[b] * jk;
+      Mx[3 * a + b] = {o_fma(ss, js.re, o_fma(pp, jp.re, kk)), o_fma(ss, js.im, pp * jp.im)};
+    }
+  // P := M P, column by column
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    Cx<T> col[3] = {{r.P[2 * c], r.P[2 * c + 1]}, {r.P[2 * (3 + c)], r.P[2 * (3 + c) + 1]}, {r.P[2 * (6 + c)], r.P[2 * (6 + c) + 1]}};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      Cx<T> v = c_mul(Mx[3 * a], col[0]);
+      Cx<T> w1 = c_mul(Mx[3 * a + 1], col[1]);
+      Cx<T> w2 = c_mul(Mx[3 * a + 2], col[2]);
+      r.P[2 * (3 * a + c)] = v.re + w1.re + w2.re;
+      r.P[2 * (3 * a + c) + 1] = v.im + w1.im + w2.im;
+    }
+  }
+}
+
 // The surface step.  FEAT gates code that most systems never need (register pressure, code
 // size); KIND (0 plane, 1 sphere/conic closed form, 2 Newton family) is resolved by the caller
 // ONCE per surface, outside the per-ray loop, so the hot loop carries no geometry branches.
@@ -417,6 +493,8 @@ OLB_HD void surface_step_k(Ray<T>& r, const PrepSurface<T>& S, const T* pool, bo
   // -- coating (interactions/base.py:111-128; coatings.py:164-237)
   if ((FEAT & FEAT_EXTRA) && S.coating == OLB_COAT_SIMPLE)
     r.i *= (S.flags & OLB_SF_REFLECT) ? S.coat_r : S.coat_t;
+  // -- polarization: rays.update() / coating.interact -> rays.update(jones)  (base.py:119-128)
+  if (FEAT & FEAT_POL) polar_update(r, S, med[MED_CN] + bad, o_abs(o_fma(r.L0, nx, o_fma(r.M0, ny, r.N0 * nz))));
 }
 
 // Runtime dispatch on the geometry kind (one ray).  The CUDA kernel does this dispatch once

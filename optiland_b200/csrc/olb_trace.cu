@@ -30,9 +30,12 @@ namespace olb {
 // Minimum resident CTAs per SM asked of ptxas: 16 bytes of ray state per access (float4 /
 // double2) -> 2 CTAs (<= 128 registers), narrower variants -> 3 CTAs (<= 85 registers).
 #ifdef OLB_MIN_BLOCKS
-template <typename T, int RPT> struct MinBlocks { static constexpr int v = OLB_MIN_BLOCKS; };
+template <typename T, int RPT, uint32_t FEAT> struct MinBlocks { static constexpr int v = OLB_MIN_BLOCKS; };
 #else
-template <typename T, int RPT> struct MinBlocks { static constexpr int v = (sizeof(T) * RPT <= 8) ? 3 : 2; };
+template <typename T, int RPT, uint32_t FEAT> struct MinBlocks {
+  // polarized: 18 more live values per ray (the P matrix) -> give ptxas 128 (fp32) / 255 (fp64) registers
+  static constexpr int v = (FEAT & 8u) ? (sizeof(T) == 4 ? 2 : 1) : ((sizeof(T) * RPT <= 8) ? 3 : 2);
+};
 #endif
 static constexpr int BLOCK = OLB_BLOCK;
 
@@ -71,6 +74,8 @@ template <typename T, int RPT> struct Vec;
 template <> struct Vec<float, 4> { using type = float4; };
 template <> struct Vec<float, 2> { using type = float2; };
 template <> struct Vec<double, 2> { using type = double2; };
+template <> struct Vec<float, 1> { using type = float; };
+template <> struct Vec<double, 1> { using type = double; };
 
 template <typename T, int RPT>
 __device__ __forceinline__ void load_rays(const T* __restrict__ p, int64_t base, int valid, T (&v)[RPT]) {
@@ -145,7 +150,7 @@ __device__ __forceinline__ void stage_table(unsigned char* smem, const unsigned 
 
 // ---- the kernel -----------------------------------------------------------------------------
 template <typename T, int RPT, uint32_t FEAT>
-__global__ void __launch_bounds__(BLOCK, (MinBlocks<T, RPT>::v)) trace_kernel(const __grid_constant__ TraceArgs a) {
+__global__ void __launch_bounds__(BLOCK, (MinBlocks<T, RPT, FEAT>::v)) trace_kernel(const __grid_constant__ TraceArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
   unsigned char* tab = smem + 16;
@@ -203,6 +208,22 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<T, RPT>::v)) trace_kernel(co
           for (int j = 0; j < n_wl; ++j)
             if (v[k] == wl[j]) idx = j;
           r[k].widx = idx;
+        }
+      }
+    }
+
+    if constexpr ((FEAT & FEAT_POL) != 0) {
+      static_assert(RPT == 1, "polarized kernels process one ray per thread");
+      if (a.tflags & OLB_TF_POL_IDENTITY) {
+#pragma unroll
+        for (int q = 0; q < 18; ++q) r[0].P[q] = (q == 0 || q == 8 || q == 16) ? (T)1 : (T)0;
+      } else {
+        using V2 = typename Vec<T, 2>::type;
+        const V2* src = reinterpret_cast<const V2*>((const T*)a.p + base * 18);
+#pragma unroll
+        for (int q = 0; q < 9; ++q) {
+          V2 v = __ldcs(src + q);
+          r[0].P[2 * q] = v.x; r[0].P[2 * q + 1] = v.y;
         }
       }
     }
@@ -282,6 +303,15 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<T, RPT>::v)) trace_kernel(co
       for (int k = 0; k < RPT; ++k) v[k] = opd_value(r[k]);
       store_rays<T, RPT>((T*)a.opd, base, valid, v);
     }
+    if constexpr ((FEAT & FEAT_POL) != 0) {
+      using V2 = typename Vec<T, 2>::type;
+      V2* dst = reinterpret_cast<V2*>((T*)a.p + base * 18);
+#pragma unroll
+      for (int q = 0; q < 9; ++q) {
+        V2 v; v.x = r[0].P[2 * q]; v.y = r[0].P[2 * q + 1];
+        __stcs(dst + q, v);
+      }
+    }
     if constexpr ((FEAT & FEAT_EXTRA) != 0) {
       if (a.L0 != nullptr) {
         T v[RPT];
@@ -336,7 +366,10 @@ static int launch_instance(const TraceArgs& a, cudaStream_t stream) {
 
 template <typename T, int RPT>
 static int launch_feat(const TraceArgs& a, uint32_t features, cudaStream_t stream) {
-  if (features & FEAT_POL) return fail(OLB_ERR_UNSUPPORTED, "polarized trace not built in this version");
+  if (features & FEAT_POL) {
+    if constexpr (RPT == 1) return launch_instance<T, 1, FEAT_ROT | FEAT_NEWTON | FEAT_EXTRA | FEAT_POL>(a, stream);
+    else return fail(OLB_ERR_UNSUPPORTED, "polarized trace uses one ray per thread");
+  }
   if (features == 0) return launch_instance<T, RPT, 0u>(a, stream);
   if (features == FEAT_ROT) return launch_instance<T, RPT, FEAT_ROT>(a, stream);
   if (features == FEAT_NEWTON) return launch_instance<T, RPT, FEAT_NEWTON>(a, stream);
@@ -415,6 +448,14 @@ static int trace_impl(const OlbDeviceTable* wh, int32_t first, int32_t last, con
   // is large; more rays per thread only spills).  Measured: profiles/tune_r1.md.
   // OLB_FORCE_RPT is a tuning knob for benchmarks only.
   static const int force_rpt = [] { const char* e = getenv("OLB_FORCE_RPT"); return e ? atoi(e) : 0; }();
+  if (features & FEAT_POL) {
+    if (!(flags & OLB_TF_POLARIZED))
+      return fail(OLB_ERR_INVALID_ARG, "table has Fresnel coatings: needs OLB_TF_POLARIZED and rays.p "
+                                       "(the reference raises for polarization == 'ignore', ray_generator.py:90-94)");
+    if (!rays->p) return fail(OLB_ERR_INVALID_ARG, "OLB_TF_POLARIZED needs rays.p");
+    if (!aligned16(rays->p)) return fail(OLB_ERR_ALIGNMENT, "rays.p not 16-byte aligned");
+    return launch_feat<T, 1>(a, features, stream);
+  }
   const bool closed_form = (features & ~FEAT_ROT) == 0;
   int rpt = force_rpt > 0 ? force_rpt : (sizeof(T) == 4 ? (closed_form ? 4 : 2) : 1);
   if (!closed_form && rpt > 2) rpt = 2;

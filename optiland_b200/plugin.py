@@ -70,9 +70,17 @@ class CudaEngine:
 
     def trace(self, table: T.SurfaceTable, rays, first: int, last: int):
         """Trace Optiland's ``rays`` object in place; return {key: (rows, N) tensor}."""
-        from .trace import RealRays, trace_device
+        import torch
 
-        shell = RealRays.__new__(RealRays)
+        from .trace import PolarizedRays, RealRays, trace_device
+
+        polarized = type(rays).__name__ == "PolarizedRays"
+        shell = (PolarizedRays if polarized else RealRays).__new__(PolarizedRays if polarized else RealRays)
+        if polarized:
+            # the reference starts from a REAL identity stack (polarized_rays.py:50); the kernel
+            # always carries the complex form
+            cdt = torch.complex64 if rays.x.dtype == torch.float32 else torch.complex128
+            shell.p = rays.p.detach().to(cdt).contiguous()
         for k in ("x", "y", "z", "L", "M", "N", "i", "w", "opd"):
             t = getattr(rays, k).detach().contiguous()
             if t.data_ptr() % 16:
@@ -84,6 +92,8 @@ class CudaEngine:
         rec = trace_device(dt, shell, first, last, record=True)
         for k in ("x", "y", "z", "L", "M", "N", "i", "opd"):
             setattr(rays, k, getattr(shell, k))
+        if polarized:
+            rays.p = shell.p
         return rec
 
 
@@ -126,8 +136,9 @@ def _set_pre_interaction_direction(rays, table, rec, first, last, launch_dir):
 def _try_trace(backend, surfaces, rays, table_builder) -> bool:
     """Common body of the two wrappers.  ``surfaces``: the Surface objects to be traced (in
     order); ``table_builder(wavelengths)`` packs them.  Returns False to decline."""
-    if type(rays).__name__ != "RealRays":
-        return False  # PolarizedRays / ParaxialRays: reference path
+    polarized = type(rays).__name__ == "PolarizedRays"
+    if type(rays).__name__ != "RealRays" and not polarized:
+        return False  # ParaxialRays etc.: reference path
     engine = _state["engine"]
     if not engine.accepts(rays):
         return False
@@ -140,8 +151,8 @@ def _try_trace(backend, surfaces, rays, table_builder) -> bool:
         table = table_builder(wl)
     except UnsupportedSurface:
         return False
-    if any(s.coating == T.COAT_FRESNEL for s in table.surfaces):
-        return False
+    if not polarized and any(s.coating == T.COAT_FRESNEL for s in table.surfaces):
+        return False  # the reference raises for this combination (ray_generator.py:90-94)
     launch_dir = (rays.L, rays.M, rays.N)
     rec = engine.trace(table, rays, 0, table.num_surfaces)
     for row, surf in enumerate(surfaces):

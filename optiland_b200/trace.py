@@ -74,6 +74,40 @@ class RealRays:
         return self.x.device
 
 
+class PolarizedRays(RealRays):
+    """``RealRays`` + the 3x3 complex polarization matrix ``p`` per ray, initialised to the identity
+    (optiland/rays/polarized_rays.py:17-56).  ``p`` is a complex (N, 3, 3) tensor: the same memory
+    layout as the reference's, which is what the C ABI takes."""
+
+    def __init__(self, x, y, z, L, M, N, intensity, wavelength, dtype=torch.float32, device=None):
+        super().__init__(x, y, z, L, M, N, intensity, wavelength, dtype=dtype, device=device)
+        self.p = None  # identity until the first trace (OLB_TF_POL_IDENTITY: not read from HBM)
+        self._i0 = self.i.clone()
+        self._L0, self._M0, self._N0 = self.L.clone(), self.M.clone(), self.N.clone()
+
+    def update_intensity(self, state=None):
+        """Host-side epilogue of RealRayTracer.trace (polarized_rays.py:57-133, :204-233):
+        i = sum |P E0|^2 * i0 / n_fields; ``state`` = (Ex, Ey, phase_x, phase_y) or None (unpolarized)."""
+        k = torch.stack([self._L0, self._M0, self._N0], dim=1)
+        xh = torch.tensor([1.0, 0.0, 0.0], dtype=k.dtype, device=k.device).expand_as(k)
+        pv = torch.linalg.cross(k, xh)
+        norms = torch.linalg.norm(pv, dim=1)
+        if bool((norms == 0).any()):
+            raise ValueError("k-vector parallel to x-axis is not currently supported.")
+        pv = pv / norms[:, None]
+        sv = torch.linalg.cross(pv, k)
+        states = [state] if state is not None else [(1.0, 0.0, 0.0, 0.0), (0.0, 1.0, 0.0, 0.0)]
+        inten = torch.zeros_like(self._i0)
+        P = self.p
+        for Ex, Ey, phx, phy in states:
+            ax = complex(np.cos(phx), np.sin(phx)) * Ex
+            ay = complex(np.cos(phy), np.sin(phy)) * Ey
+            E0 = sv.to(P.dtype) * ax + pv.to(P.dtype) * ay
+            E1 = torch.matmul(P, E0[:, :, None])[:, :, 0]
+            inten = inten + (E1.abs() ** 2).sum(dim=1)
+        self.i = inten * self._i0 / len(states)
+
+
 class DeviceTable:
     """A ``SurfaceTable`` prepared and resident on one GPU (olb_table_upload)."""
 
@@ -134,12 +168,22 @@ def trace_device(dtab: DeviceTable, rays: RealRays, first: int, last: int, recor
         rays.L0 = torch.empty_like(rays.x)
         rays.M0 = torch.empty_like(rays.x)
         rays.N0 = torch.empty_like(rays.x)
+    p_ptr = None
+    if isinstance(rays, PolarizedRays):
+        flags |= _lib.TF_POLARIZED
+        cdt = torch.complex64 if rays.dtype == torch.float32 else torch.complex128
+        if rays.p is None:
+            rays.p = torch.empty((n, 3, 3), dtype=cdt, device=rays.device)
+            flags |= _lib.TF_POL_IDENTITY
+        else:
+            rays.p = rays.p.to(cdt).contiguous()
+        p_ptr = torch.view_as_real(rays.p).data_ptr()
     c_rays = _lib.OlbRays(
         x=rays.x.data_ptr(), y=rays.y.data_ptr(), z=rays.z.data_ptr(), L=rays.L.data_ptr(),
         M=rays.M.data_ptr(), N=rays.N.data_ptr(), i=rays.i.data_ptr(),
         w=rays.w.data_ptr() if dtab.table.n_wl > 1 else None, opd=rays.opd.data_ptr(),
         L0=rays.L0.data_ptr() if want_l0 else None, M0=rays.M0.data_ptr() if want_l0 else None,
-        N0=rays.N0.data_ptr() if want_l0 else None, p=None)
+        N0=rays.N0.data_ptr() if want_l0 else None, p=p_ptr)
     status = torch.zeros(1, dtype=torch.int32, device=rays.device) if dtab.has_zernike else None
     with torch.cuda.device(rays.device):
         stream = torch.cuda.current_stream(rays.device).cuda_stream

@@ -41,7 +41,7 @@ def main():
             rr.__dict__.update(base.__dict__)
             return trace_device(dtab, rr, 0, S, record=record)
 
-        for record in (True,):
+        for record in (True, False):
             for _ in range(5):
                 step(record)
             torch.cuda.synchronize()
@@ -55,7 +55,10 @@ def main():
             ms = a.elapsed_time(b) / K
             n_loads = 8 if c.table.n_wl == 1 else 9
             gb = es * (n_loads + 8 * S) * n / 1e9
-            out[tag] = {"ms": round(ms, 4), "GBps": round(gb / ms * 1e3, 1), "Grs_per_s": round(n * (S - 1) / ms / 1e6, 2)}
+            if record:
+                out[tag] = {"ms": round(ms, 4), "GBps": round(gb / ms * 1e3, 1), "Grs_per_s": round(n * (S - 1) / ms / 1e6, 2)}
+            else:
+                out[tag]["ms_norecord"] = round(ms, 4)
         del base
         torch.cuda.empty_cache()
     print(json.dumps(out))

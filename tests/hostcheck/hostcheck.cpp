@@ -16,7 +16,8 @@ using namespace olb;
 
 template <typename T, uint32_t FEAT>
 static void walk(const unsigned char* blob, int first, int last, int64_t n, T** ray /*x y z L M N i w opd*/,
-                 T** rec /*8 arrays rows*n or null*/, T** l0 /*3 or null*/, int* status_out) {
+                 T** rec /*8 arrays rows*n or null*/, T** l0 /*3 or null*/, T* pmat /*[n][18] or null*/,
+                 int* status_out) {
   const PrepHeader* H = reinterpret_cast<const PrepHeader*>(blob);
   const PrepSurface<T>* surf = reinterpret_cast<const PrepSurface<T>*>(blob + sizeof(PrepHeader));
   const T* pool = reinterpret_cast<const T*>(surf + H->n_surf);
@@ -32,6 +33,8 @@ static void walk(const unsigned char* blob, int first, int last, int64_t n, T** 
         if (ray[7][k] == wl[j]) idx = j;
       r.widx = idx;
     }
+    if ((FEAT & FEAT_POL) && pmat)
+      for (int q = 0; q < 18; ++q) r.P[q] = pmat[k * 18 + q];
     bool have_frame = false;
     T g[6] = {r.x, r.y, r.z, r.L, r.M, r.N};
     for (int s = first; s < last; ++s) {
@@ -51,34 +54,40 @@ static void walk(const unsigned char* blob, int first, int last, int64_t n, T** 
     ray[6][k] = r.i;
     ray[8][k] = opd_value(r);
     if (l0) { l0[0][k] = r.L0; l0[1][k] = r.M0; l0[2][k] = r.N0; }
+    if ((FEAT & FEAT_POL) && pmat)
+      for (int q = 0; q < 18; ++q) pmat[k * 18 + q] = r.P[q];
   }
   *status_out |= status;
 }
 
 template <typename T>
-static int run(const OlbTable* tab, int first, int last, int64_t n, T** ray, T** rec, T** l0, int* status,
-               char* err, int err_len) {
+static int run(const OlbTable* tab, int first, int last, int64_t n, T** ray, T** rec, T** l0, T* pmat,
+               int* status, char* err, int err_len) {
   PrepResult pr = prepare_table(*tab);
   if (!pr.error.empty()) { snprintf(err, err_len, "%s", pr.error.c_str()); return OLB_ERR_TABLE; }
   const unsigned char* blob = sizeof(T) == 8 ? pr.blob_f64.data() : pr.blob_f32.data();
-  if (pr.features & FEAT_POL) { snprintf(err, err_len, "polarized not supported in hostcheck"); return OLB_ERR_UNSUPPORTED; }
+  if ((pr.features & FEAT_POL) && !pmat) { snprintf(err, err_len, "table needs polarized rays (p)"); return OLB_ERR_INVALID_ARG; }
+  if (pmat) {
+    walk<T, FEAT_ROT | FEAT_NEWTON | FEAT_EXTRA | FEAT_POL>(blob, first, last, n, ray, rec, l0, pmat, status);
+    return OLB_OK;
+  }
   // exercise the same three instantiations the launcher picks from
   uint32_t f = pr.features | (l0 ? FEAT_EXTRA : 0u);
-  if (f == 0) walk<T, 0u>(blob, first, last, n, ray, rec, l0, status);
-  else if (f == FEAT_ROT) walk<T, FEAT_ROT>(blob, first, last, n, ray, rec, l0, status);
-  else if (f == FEAT_NEWTON) walk<T, FEAT_NEWTON>(blob, first, last, n, ray, rec, l0, status);
-  else walk<T, FEAT_ROT | FEAT_NEWTON | FEAT_EXTRA>(blob, first, last, n, ray, rec, l0, status);
+  if (f == 0) walk<T, 0u>(blob, first, last, n, ray, rec, l0, nullptr, status);
+  else if (f == FEAT_ROT) walk<T, FEAT_ROT>(blob, first, last, n, ray, rec, l0, nullptr, status);
+  else if (f == FEAT_NEWTON) walk<T, FEAT_NEWTON>(blob, first, last, n, ray, rec, l0, nullptr, status);
+  else walk<T, FEAT_ROT | FEAT_NEWTON | FEAT_EXTRA>(blob, first, last, n, ray, rec, l0, nullptr, status);
   return OLB_OK;
 }
 
 extern "C" {
 int olbhc_trace_f64(const OlbTable* tab, int first, int last, int64_t n, double** ray, double** rec, double** l0,
-                    int* status, char* err, int err_len) {
-  return run<double>(tab, first, last, n, ray, rec, l0, status, err, err_len);
+                    double* pmat, int* status, char* err, int err_len) {
+  return run<double>(tab, first, last, n, ray, rec, l0, pmat, status, err, err_len);
 }
 int olbhc_trace_f32(const OlbTable* tab, int first, int last, int64_t n, float** ray, float** rec, float** l0,
-                    int* status, char* err, int err_len) {
-  return run<float>(tab, first, last, n, ray, rec, l0, status, err, err_len);
+                    float* pmat, int* status, char* err, int err_len) {
+  return run<float>(tab, first, last, n, ray, rec, l0, pmat, status, err, err_len);
 }
 int olbhc_features(const OlbTable* tab) {
   PrepResult pr = prepare_table(*tab);

@@ -191,3 +191,45 @@ def test_host_buffer_path_matches_device_path():
     for k in ("x", "y", "z", "L", "M", "N", "i", "opd"):
         a, b = h_out[k].numpy(), getattr(rays, k).cpu().numpy()
         assert np.array_equal(a, b, equal_nan=True), k
+
+
+@pytest.mark.parametrize("name", ["zernike_polarized_c5", "cooke_polarized"])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_polarized_trace_vs_reference_golden(name, dtype):
+    """Config 5: P-matrix propagation + Fresnel coatings (+ Zernike surface, 3 wavelengths) and the
+    intensity epilogue, against the reference's PolarizedRays."""
+    from optiland_b200.trace import PolarizedRays, SurfaceGroup
+
+    c = Case(name)
+    r = c.rays
+    rays = PolarizedRays(r["x"], r["y"], r["z"], r["L"], r["M"], r["N"], r["i"], r["w"], dtype=dtype)
+    sg = SurfaceGroup(c.table)
+    sg.trace(rays)
+    f64 = dtype == torch.float64
+    tol = 1e-11 * c.scale + 2 * newton_tol(c) if f64 else 2e-6 * c.scale
+    for k in ("x", "y", "opd"):
+        assert max_abs_err(_np(getattr(sg, k)), c.rec[k]) <= tol, k
+    p = rays.p.to(torch.complex128).cpu().numpy()
+    assert np.max(np.abs(p - c.out["p"])) <= (1e-11 if f64 else 2e-5)
+    if "x_state" in c.z:
+        rays.update_intensity(tuple(c.extra("state")))
+        ref_i = c.extra("final_intensity")
+    else:
+        rays.update_intensity(None)
+        ref_i = c.extra("final_intensity_unpolarized")
+    assert np.max(np.abs(_np(rays.i) - ref_i)) <= (1e-11 if f64 else 5e-5)
+    # a second trace segment continues from the stored P (input P is read back)
+    rays2 = PolarizedRays(r["x"], r["y"], r["z"], r["L"], r["M"], r["N"], r["i"], r["w"], dtype=dtype)
+    sg.trace(rays2, skip=0, stop=2, record=False)
+    sg.trace(rays2, skip=2)
+    assert np.max(np.abs(rays2.p.to(torch.complex128).cpu().numpy() - c.out["p"])) <= (1e-11 if f64 else 2e-5)
+
+
+def test_fresnel_table_without_polarized_rays_is_an_error():
+    from optiland_b200 import _lib
+    from optiland_b200.trace import SurfaceGroup
+
+    c = Case("zernike_polarized_c5")
+    sg = SurfaceGroup(c.table)
+    with pytest.raises(_lib.OlbError, match="POLARIZED"):
+        sg.trace(_rays(c, torch.float64))

@@ -30,7 +30,7 @@ def hc():
     return C.CDLL(SO)
 
 
-def run_hostcheck(hc, table, rays, dtype, first=0, last=None, want_l0=False):
+def run_hostcheck(hc, table, rays, dtype, first=0, last=None, want_l0=False, pmat=None):
     last = table.num_surfaces if last is None else last
     ht = _lib.HostTable(table)
     n = rays["x"].size
@@ -47,10 +47,17 @@ def run_hostcheck(hc, table, rays, dtype, first=0, last=None, want_l0=False):
     err = C.create_string_buffer(256)
     fn = hc.olbhc_trace_f64 if dtype == np.float64 else hc.olbhc_trace_f32
     fn.restype = C.c_int
+    parr = None
+    if pmat is not None:
+        cdt = np.complex128 if dtype == np.float64 else np.complex64
+        parr = np.ascontiguousarray(pmat, dtype=cdt).copy()
     rc = fn(C.byref(ht.c), C.c_int(first), C.c_int(last), C.c_int64(n), ray_ptrs, rec_ptrs,
-            l0_ptrs if want_l0 else None, C.byref(status), err, 256)
+            l0_ptrs if want_l0 else None, C.c_void_p(parr.ctypes.data) if parr is not None else None,
+            C.byref(status), err, 256)
     assert rc == 0, err.value
     out = dict(zip(keys, arrs))
+    if parr is not None:
+        out["p"] = parr
     out.update(L0=l0[0], M0=l0[1], N0=l0[2])
     return out, dict(zip(REC, rec)), status.value
 
@@ -153,3 +160,22 @@ def test_degenerate_conic_roots(hc, dtype):
     tol = 1e-12 * 60 if dtype == np.float64 else 5e-6 * 60  # steep rays at x = 60 mm amplify fp32 rounding
     for k in REC:
         assert max_abs_err(rec[k], orec[k]) <= tol, (k, max_abs_err(rec[k], orec[k]))
+
+
+@pytest.mark.parametrize("name", ["zernike_polarized_c5", "cooke_polarized"])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_device_math_polarized_vs_reference(hc, name, dtype):
+    """P-matrix update (PolarizedRays.update) + Fresnel Jones matrices vs. the reference."""
+    from tests._util import Case as _Case
+
+    c = _Case(name)
+    p0 = np.tile(np.eye(3, dtype=np.complex128), (c.n, 1, 1))
+    out, rec, status = run_hostcheck(hc, c.table, c.rays, dtype, pmat=p0)
+    assert status == 0
+    if dtype == np.float64:
+        tol, ptol = 1e-11 * c.scale + 2 * newton_tol(c), 1e-11
+    else:
+        tol, ptol = 2e-6 * c.scale, 2e-5
+    for k in ("x", "y", "opd"):
+        assert max_abs_err(rec[k], c.rec[k]) <= tol, k
+    assert np.max(np.abs(out["p"] - c.out["p"])) <= ptol

@@ -32,7 +32,12 @@ class OracleEngine:
 
         self.calls.append((table.num_surfaces, int(rays.x.numel())))
         inp = {k: getattr(rays, k).detach().double().numpy() for k in ("x", "y", "z", "L", "M", "N", "i", "w", "opd")}
-        out, rec, status = O.trace(table, inp, first, last)
+        polarized = type(rays).__name__ == "PolarizedRays"
+        if polarized:
+            inp["p"] = rays.p.detach().numpy().astype(np.complex128)
+        out, rec, status = O.trace(table, inp, first, last, polarized=polarized)
+        if polarized:
+            rays.p = torch.from_numpy(out["p"])
         if status:
             raise ValueError("Zernike coordinates must be normalized to [-1, 1].")
         dt = rays.x.dtype
@@ -192,3 +197,33 @@ def test_multi_wavelength_and_zernike_error(plugin):
     ref.surfaces.trace(r2)
     be.set_backend("torch")
     np.testing.assert_allclose(be.to_numpy(rays.opd), np.array(r2.opd), atol=1e-11)
+
+
+def test_polarized_trace_with_fresnel_coatings(plugin):
+    """Config 5 flavour: Fresnel coatings + unpolarized PolarizedRays through Optic.trace; the
+    reference's own update_intensity runs on the P matrices the capability returned."""
+    P, eng, be = plugin
+    from optiland.rays import PolarizationState
+    from optiland.samples.objectives import CookeTriplet
+
+    def make():
+        lens = CookeTriplet()
+        lens.surfaces.set_fresnel_coatings()
+        lens.updater.set_polarization(PolarizationState(is_polarized=False))
+        return lens
+
+    def trace(lens):
+        return lens.trace(0.0, 0.7, 0.55, 5, "hexapolar")
+
+    be.set_backend("numpy")
+    ref = make()
+    r_ref = trace(ref)
+    ref_i, ref_p = np.array(r_ref.i), np.array(r_ref.p)
+    be.set_backend("torch")
+    n0 = len(eng.calls)
+    lens = make()
+    rays = trace(lens)
+    assert len(eng.calls) == n0 + 1 and type(rays).__name__ == "PolarizedRays"
+    np.testing.assert_allclose(be.to_numpy(rays.i), ref_i, atol=1e-12)
+    np.testing.assert_allclose(rays.p.detach().numpy(), ref_p, atol=1e-12)
+    assert float(ref_i.max()) < 0.8  # Fresnel losses really applied
