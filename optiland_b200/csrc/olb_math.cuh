@@ -53,6 +53,22 @@ OLB_HD float o_div(float a, float b) { return a / b; }
 OLB_HD float o_exp(float a) { return expf(a); }
 #endif
 
+// Product that the compiler must NOT fuse into an FMA: cross products of (nearly) parallel
+// vectors rely on a*b - b*a cancelling exactly, which fma(a, b, -round(b*a)) does not.
+#if defined(__CUDA_ARCH__)
+OLB_HD float o_mul_nc(float a, float b) { return __fmul_rn(a, b); }
+OLB_HD double o_mul_nc(double a, double b) { return __dmul_rn(a, b); }
+#else
+OLB_HD float o_mul_nc(float a, float b) { volatile float p = a * b; return p; }
+OLB_HD double o_mul_nc(double a, double b) { volatile double p = a * b; return p; }
+#endif
+template <typename T>
+OLB_HD void o_cross(const T* a, const T* b, T* c) {
+  c[0] = o_mul_nc(a[1], b[2]) - o_mul_nc(a[2], b[1]);
+  c[1] = o_mul_nc(a[2], b[0]) - o_mul_nc(a[0], b[2]);
+  c[2] = o_mul_nc(a[0], b[1]) - o_mul_nc(a[1], b[0]);
+}
+
 template <typename T> struct Eps;
 template <> struct Eps<float> { static constexpr float v = 1.1920929e-7f; };
 template <> struct Eps<double> { static constexpr double v = 2.220446049250313e-16; };
@@ -341,21 +357,22 @@ template <typename T> OLB_HD Cx<T> c_div(Cx<T> a, Cx<T> b) {
 template <typename T>
 OLB_HD void polar_update(Ray<T>& r, const PrepSurface<T>& S, T ncoat, T cosi) {
   const T k0[3] = {r.L0, r.M0, r.N0}, k1[3] = {r.L, r.M, r.N};
-  // s = k0 x k1, with the reference's fallback when k0 || k1 (polarized_rays.py:151-163)
-  T s[3] = {k0[1] * k1[2] - k0[2] * k1[1], k0[2] * k1[0] - k0[0] * k1[2], k0[0] * k1[1] - k0[1] * k1[0]};
+  // s = k0 x k1, with the reference's fallback when k0 || k1 (polarized_rays.py:151-163).  At an
+  // index-matched surface (the image surface: n1 == n2) k1 == k0 and s must come out exactly 0.
+  T s[3];
+  o_cross(k0, k1, s);
   T mag = o_sqrt(o_fma(s[0], s[0], o_fma(s[1], s[1], s[2] * s[2])));
   if (mag == 0) {
     T pf[3] = {(T)0, k0[2], -k0[1]};                       // k0 x (1,0,0)
     if (o_fma(pf[1], pf[1], pf[2] * pf[2]) == 0) { pf[0] = -k0[2]; pf[1] = 0; pf[2] = k0[0]; }  // k0 x (0,1,0)
-    s[0] = pf[1] * k0[2] - pf[2] * k0[1];                  // p_fallback x k0
-    s[1] = pf[2] * k0[0] - pf[0] * k0[2];
-    s[2] = pf[0] * k0[1] - pf[1] * k0[0];
+    o_cross(pf, k0, s);                                    // p_fallback x k0
     mag = o_sqrt(o_fma(s[0], s[0], o_fma(s[1], s[1], s[2] * s[2])));
   }
   T inv = o_rcp(mag);
   s[0] *= inv; s[1] *= inv; s[2] *= inv;
-  const T p0[3] = {k0[1] * s[2] - k0[2] * s[1], k0[2] * s[0] - k0[0] * s[2], k0[0] * s[1] - k0[1] * s[0]};
-  const T p1[3] = {k1[1] * s[2] - k1[2] * s[1], k1[2] * s[0] - k1[0] * s[2], k1[0] * s[1] - k1[1] * s[0]};
+  T p0[3], p1[3];
+  o_cross(k0, s, p0);
+  o_cross(k1, s, p1);
   // Jones diagonal (js, jp, jk)
   Cx<T> js = {(T)1, (T)0}, jp = {(T)1, (T)0};
   T jk = 1;

@@ -42,17 +42,35 @@ def main():
             return trace_device(dtab, rr, 0, S, record=record)
 
         for record in (True, False):
+            def one():
+                if record:
+                    return step(True)
+                # the record-less trace updates the ray arrays in place: give it a private copy
+                rr = RealRays.__new__(RealRays)
+                rr.__dict__.update(base.__dict__)
+                for k in ("x", "y", "z", "L", "M", "N", "i", "opd"):
+                    setattr(rr, k, getattr(base, k).clone())
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                trace_device(dtab, rr, 0, S, record=False)
+                e1.record()
+                return e0, e1
             for _ in range(5):
-                step(record)
+                one()
             torch.cuda.synchronize()
             K = 30
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for _ in range(K):
-                step(record)
-            b.record()
-            torch.cuda.synchronize()
-            ms = a.elapsed_time(b) / K
+            if record:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(K):
+                    one()
+                b.record()
+                torch.cuda.synchronize()
+                ms = a.elapsed_time(b) / K
+            else:
+                evs = [one() for _ in range(K)]
+                torch.cuda.synchronize()
+                ms = sum(a.elapsed_time(b) for a, b in evs) / K
             n_loads = 8 if c.table.n_wl == 1 else 9
             gb = es * (n_loads + 8 * S) * n / 1e9
             if record:
