@@ -233,6 +233,8 @@ typedef struct OlbDeviceTable {
   int32_t n_wl;
   int32_t off_f64, bytes_f64;   /* fp64 blob inside workspace */
   int32_t off_f32, bytes_f32;   /* fp32 blob inside workspace */
+  int32_t bwd_supported;        /* 1 if olb_trace_bwd_* covers every surface of the table */
+  int32_t reserved;
 } OlbDeviceTable;
 
 /* Bytes of device workspace needed for `table` (< 256 KiB). Negative = error code. */
@@ -284,6 +286,39 @@ int olb_trace_host_f64(const OlbDeviceTable* table, int32_t first, int32_t last,
                        const OlbRecords* rec, int64_t n_rays, int64_t chunk_rays,
                        void* dev_scratch, int64_t dev_scratch_bytes, uint32_t flags,
                        int32_t* status);
+
+/*
+ * Reverse mode (the backward pass of the autograd configuration; reference:
+ * loss.backward() through the eager graph, optiland/optimization/optimizer/torch/base.py:96-156).
+ * Given dLoss/d(record rows) it returns dLoss/d(launch state) and ACCUMULATES
+ * dLoss/d(surface parameters) into grad_params: n_surfaces blocks of OLB_GP_COUNT doubles,
+ *   [OLB_GP_TX..TZ] pose translation t, [OLB_GP_CURV] curvature 1/radius (d/dradius =
+ *   -curv^2 * this), [OLB_GP_CONIC] k, [OLB_GP_N1] n1, [OLB_GP_N2] n2,
+ *   [OLB_GP_COEF + j] even-asphere coefficient C_j (j < OLB_GP_MAX_COEF).
+ * Everything is recomputed from the forward call's inputs and records (nothing else is
+ * saved): `rays_in` is the launch state the forward call consumed (x,y,z,L,M,N,i), `rec` its
+ * full records for the same [first, last).  grad_rec pointers may be NULL individually
+ * (that quantity has zero gradient); grad_rays_in (x,y,z,L,M,N,i,opd) may be NULL.
+ * Supported tables (OlbDeviceTable.bwd_supported): unrotated poses, plane / standard /
+ * even-asphere geometry, no or radial aperture, no or simple coating, one wavelength;
+ * otherwise OLB_ERR_UNSUPPORTED.  Rays that are NaN at a surface carry no gradient.
+ */
+#define OLB_GP_TX 0
+#define OLB_GP_TY 1
+#define OLB_GP_TZ 2
+#define OLB_GP_CURV 3
+#define OLB_GP_CONIC 4
+#define OLB_GP_N1 5
+#define OLB_GP_N2 6
+#define OLB_GP_COEF 7
+#define OLB_GP_MAX_COEF 12
+#define OLB_GP_COUNT (OLB_GP_COEF + OLB_GP_MAX_COEF)
+int olb_trace_bwd_f32(const OlbDeviceTable* table, int32_t first, int32_t last,
+                      const OlbRays* rays_in, const OlbRecords* rec, const OlbRecords* grad_rec,
+                      const OlbRays* grad_rays_in, double* grad_params, int64_t n_rays, void* stream);
+int olb_trace_bwd_f64(const OlbDeviceTable* table, int32_t first, int32_t last,
+                      const OlbRays* rays_in, const OlbRecords* rec, const OlbRecords* grad_rec,
+                      const OlbRays* grad_rays_in, double* grad_params, int64_t n_rays, void* stream);
 
 /* Number of kernel launches issued by this process through the library
  * (for bench.py's gpu_launches claim). */

@@ -23,6 +23,8 @@ ERRORS = {-1: "OLB_ERR_INVALID_ARG", -2: "OLB_ERR_UNSUPPORTED", -3: "OLB_ERR_CUD
 TF_POLARIZED = 1 << 0
 TF_NO_FINAL = 1 << 1
 TF_POL_IDENTITY = 1 << 2
+GP_TX, GP_TY, GP_TZ, GP_CURV, GP_CONIC, GP_N1, GP_N2, GP_COEF, GP_MAX_COEF = 0, 1, 2, 3, 4, 5, 6, 7, 12
+GP_COUNT = GP_COEF + GP_MAX_COEF
 
 
 class OlbTable(C.Structure):
@@ -48,7 +50,7 @@ class OlbDeviceTable(C.Structure):
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("magic", C.c_uint32),
         ("features", C.c_uint32), ("n_surfaces", C.c_int32), ("n_wl", C.c_int32),
         ("off_f64", C.c_int32), ("bytes_f64", C.c_int32), ("off_f32", C.c_int32),
-        ("bytes_f32", C.c_int32),
+        ("bytes_f32", C.c_int32), ("bwd_supported", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -64,6 +66,10 @@ SYMBOLS = {
                                 C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p]),
     "olb_trace_f64": (C.c_int, [_P(OlbDeviceTable), C.c_int32, C.c_int32, _P(OlbRays), _P(OlbRecords),
                                 C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "olb_trace_bwd_f32": (C.c_int, [_P(OlbDeviceTable), C.c_int32, C.c_int32, _P(OlbRays), _P(OlbRecords),
+                                    _P(OlbRecords), _P(OlbRays), C.c_void_p, C.c_int64, C.c_void_p]),
+    "olb_trace_bwd_f64": (C.c_int, [_P(OlbDeviceTable), C.c_int32, C.c_int32, _P(OlbRays), _P(OlbRecords),
+                                    _P(OlbRecords), _P(OlbRays), C.c_void_p, C.c_int64, C.c_void_p]),
     "olb_host_scratch_bytes": (C.c_int64, [C.c_int32, C.c_int64]),
     "olb_trace_host_f32": (C.c_int, [_P(OlbDeviceTable), C.c_int32, C.c_int32, _P(OlbRays), _P(OlbRays),
                                      _P(OlbRecords), C.c_int64, C.c_int64, C.c_void_p, C.c_int64,

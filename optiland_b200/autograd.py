@@ -1,0 +1,133 @@
+"""Differentiable trace: ``torch.autograd.Function`` over olb_trace_* / olb_trace_bwd_*.
+
+The reference obtains gradients by ``loss.backward()`` through the eager graph of every
+element-wise op of the trace (/root/reference/optiland/optimization/optimizer/torch/base.py:96-156),
+reading record rows as in the ``rms_spot_size`` operand (optimization/operand/ray.py:299-342).  Here
+the forward is ONE kernel launch and the backward ONE launch of the hand-derived adjoint
+(``olb_math.cuh::surface_backward``); nothing but the launch state and the records is saved.
+
+Parameters enter as one tensor ``params`` of shape (S, GP_COUNT) (fp64) laid out like the C ABI's
+gradient block: columns ``GP_TX, GP_TY, GP_TZ`` pose translation, ``GP_CURV`` curvature 1/radius,
+``GP_CONIC``, ``GP_N1``, ``GP_N2``, ``GP_COEF + j`` even-asphere coefficients.  Callers build it from
+their own leaf tensors with ordinary torch ops (e.g. ``params[s, GP_CURV] = 1 / radius``), so the
+chain rule to radii, thicknesses, ... is autograd's job.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import table as T
+from .trace import _DTYPES, _REC_KEYS, DeviceTable
+
+GP_TX, GP_TY, GP_TZ, GP_CURV, GP_CONIC, GP_N1, GP_N2, GP_COEF = 0, 1, 2, 3, 4, 5, 6, 7
+GP_MAX_COEF = _lib.GP_MAX_COEF
+GP_COUNT = _lib.GP_COUNT
+
+
+def table_to_params(table: T.SurfaceTable) -> torch.Tensor:
+    """(S, GP_COUNT) fp64 tensor of the differentiable parameters of ``table`` (one wavelength)."""
+    if table.n_wl != 1:
+        raise ValueError("differentiable trace supports one wavelength per call")
+    p = np.zeros((table.num_surfaces, GP_COUNT))
+    for s, spec in enumerate(table.surfaces):
+        p[s, GP_TX:GP_TZ + 1] = spec.t
+        p[s, GP_CURV] = 0.0 if not np.isfinite(spec.radius) else 1.0 / spec.radius
+        p[s, GP_CONIC] = spec.conic
+        p[s, GP_N1], p[s, GP_N2] = spec.n1[0], spec.n2[0]
+        if spec.kind == T.GEOM_EVEN_ASPHERE:
+            k = len(spec.coefficients)
+            if k > GP_MAX_COEF:
+                raise ValueError(f"more than {GP_MAX_COEF} even-asphere coefficients")
+            p[s, GP_COEF:GP_COEF + k] = spec.coefficients
+    return torch.from_numpy(p)
+
+
+def params_to_table(table: T.SurfaceTable, params: torch.Tensor) -> T.SurfaceTable:
+    """``table`` with its differentiable parameters replaced by the VALUES in ``params``."""
+    p = params.detach().double().cpu().numpy()
+    specs = []
+    for s, spec in enumerate(table.surfaces):
+        ch = dict(t=p[s, GP_TX:GP_TZ + 1].copy(), n1=np.array([p[s, GP_N1]]), n2=np.array([p[s, GP_N2]]))
+        if spec.kind in (T.GEOM_STANDARD, T.GEOM_EVEN_ASPHERE):
+            ch["radius"] = float("inf") if p[s, GP_CURV] == 0 else 1.0 / p[s, GP_CURV]
+            ch["conic"] = float(p[s, GP_CONIC])
+        if spec.kind == T.GEOM_EVEN_ASPHERE:
+            ch["coefficients"] = p[s, GP_COEF:GP_COEF + len(spec.coefficients)].copy()
+        specs.append(dataclasses.replace(spec, **ch))
+    return T.SurfaceTable(specs, table.wavelengths)
+
+
+class _TraceFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, template, device_tables, params, x, y, z, L, M, N, i, opd):
+        ctx.set_materialize_grads(False)
+        lib = _lib.load()
+        dtype = x.dtype
+        sfx = _DTYPES[dtype]
+        table = params_to_table(template, params)
+        dtab = DeviceTable(table, x.device)
+        device_tables.append(dtab)
+        if not dtab.c.bwd_supported:
+            raise _lib.OlbError("differentiable trace: table not supported by olb_trace_bwd_* (rotated pose, "
+                                "non plane/standard/even-asphere geometry, non-radial aperture, Fresnel coating)")
+        n = x.numel()
+        S = table.num_surfaces
+        ins = [t.detach().contiguous() for t in (x, y, z, L, M, N, i, opd)]
+        vec = 4 if dtype == torch.float32 else 2
+        stride = n if n % vec == 0 else (n + 63) // 64 * 64
+        buf = torch.empty((8, S, stride), dtype=dtype, device=x.device)
+        c_rec = _lib.OlbRecords(*[buf[j].data_ptr() for j in range(8)], stride)
+        c_rays = _lib.OlbRays(**{k: t.data_ptr() for k, t in zip(("x", "y", "z", "L", "M", "N", "i", "opd"), ins)})
+        with torch.cuda.device(x.device):
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+            rc = getattr(lib, f"olb_trace_{sfx}")(C.byref(dtab.c), 0, S, C.byref(c_rays), C.byref(c_rec), n,
+                                                  _lib.TF_NO_FINAL, None, C.c_void_p(stream))
+        _lib.check(rc, f"olb_trace_{sfx}")
+        ctx.dtab, ctx.ins, ctx.buf, ctx.stride, ctx.sfx = dtab, ins, buf, stride, sfx
+        ctx.needs_ray_grad = any(t.requires_grad for t in (x, y, z, L, M, N, i, opd))
+        return tuple(buf[j, :, :n] for j in range(8))
+
+    @staticmethod
+    def backward(ctx, *grads):
+        lib = _lib.load()
+        dtab, ins, buf, stride = ctx.dtab, ctx.ins, ctx.buf, ctx.stride
+        n = ins[0].numel()
+        S = buf.shape[1]
+        dtype = buf.dtype
+        gbufs = [None if g is None else g.to(dtype).contiguous() for g in grads]
+        gstride = n
+        c_grec = _lib.OlbRecords(*[(g.data_ptr() if g is not None else None) for g in gbufs], gstride)
+        c_rec = _lib.OlbRecords(*[buf[j].data_ptr() for j in range(8)], stride)
+        c_in = _lib.OlbRays(**{k: t.data_ptr() for k, t in zip(("x", "y", "z", "L", "M", "N", "i", "opd"), ins)})
+        gin = [torch.empty_like(ins[0]) for _ in range(8)] if ctx.needs_ray_grad else None
+        c_gin = _lib.OlbRays(**{k: t.data_ptr() for k, t in zip(("x", "y", "z", "L", "M", "N", "i", "opd"), gin)}) if gin else None
+        gpar = torch.zeros((S, GP_COUNT), dtype=torch.float64, device=buf.device)
+        with torch.cuda.device(buf.device):
+            stream = torch.cuda.current_stream(buf.device).cuda_stream
+            rc = getattr(lib, f"olb_trace_bwd_{ctx.sfx}")(
+                C.byref(dtab.c), 0, S, C.byref(c_in), C.byref(c_rec), C.byref(c_grec),
+                C.byref(c_gin) if c_gin is not None else None, C.c_void_p(gpar.data_ptr()), n, C.c_void_p(stream))
+        _lib.check(rc, f"olb_trace_bwd_{ctx.sfx}")
+        gi = gin if gin is not None else [None] * 8
+        return (None, None, gpar.cpu() if not ctx.params_on_device else gpar, *gi)
+
+
+def trace_differentiable(template: T.SurfaceTable, params: torch.Tensor, rays):
+    """Trace ``rays`` (an ``optiland_b200.trace.RealRays``) through ``template`` with parameter VALUES
+    taken from ``params``; returns a dict of (S, N) record tensors that are autograd outputs of
+    ``params`` (and of the ray tensors when they require grad)."""
+    holder: list = []
+    outs = _TraceFnWrapper.apply(template, holder, params, rays.x, rays.y, rays.z, rays.L, rays.M, rays.N, rays.i, rays.opd)
+    return dict(zip(_REC_KEYS, outs))
+
+
+class _TraceFnWrapper(_TraceFn):
+    @staticmethod
+    def forward(ctx, template, holder, params, *ray_tensors):
+        ctx.params_on_device = params.is_cuda
+        return _TraceFn.forward(ctx, template, holder, params, *ray_tensors)

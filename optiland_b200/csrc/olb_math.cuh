@@ -503,6 +503,10 @@ OLB_HD void surface_step_k(Ray<T>& r, const PrepSurface<T>& S, const T* pool, bo
     T ad = o_abs(dot);
     T root = o_sqrt(o_fma(u * u, o_fma(ad, ad, (T)-1), (T)1));   // sqrt(1 - u^2 (1 - dot^2))
     T g = sgn * o_fma(-u, ad, root);
+    // Index-matched surface (u == 1; every image surface): no deflection, exactly.  The
+    // reference gets this from sqrt(x*x) == |x| in IEEE arithmetic; PolarizedRays.update needs
+    // k1 == k0 bit-for-bit here (its s = k0 x k1 basis must fall back, polarized_rays.py:151-163).
+    if (u == (T)1) g = (T)0 * dot;   // 0, or NaN when dot is NaN (NaN stays in band)
     r.L = o_fma(u, r.L, nx * g);
     r.M = o_fma(u, r.M, ny * g);
     r.N = o_fma(u, r.N, nz * g);
@@ -538,6 +542,162 @@ OLB_HD void to_global(const Ray<T>& r, const PrepSurface<T>& S, T& x, T& y, T& z
     x = r.x + S.t[0]; y = r.y + S.t[1]; z = r.z + S.t[2];
     L = r.L; M = r.M; N = r.N;
   }
+}
+
+}  // namespace olb
+
+
+// =============================================================================================
+// Reverse mode: adjoint of ONE surface step for ONE ray (the backward pass of config 3).
+//
+// The reference differentiates the eager graph of every element-wise op of section 3.1
+// (optiland/optimization/optimizer/torch/base.py:96-156).  Here the adjoint is derived by hand:
+//   * through the intersection by the implicit-function theorem on F(p0 + t d0; theta) = 0,
+//     F = sag(x, y) - z  ->  dt = -(gradF.(dp0 + t dd0) + F_theta dtheta) / (gradF.d0)
+//     (valid for the closed-form conic AND the Newton family: no unrolled iterations),
+//   * through the normal via the Hessian of the rotationally symmetric sag,
+//   * through Snell refraction / reflection, OPD, absorption and the pose translation.
+// Supported: unrotated poses, plane / sphere-conic / even asphere, radial (or no) aperture,
+// simple coatings, one wavelength.  Everything is recomputed from the recorded rows (state
+// after surface s-1 and position after surface s): the forward pass stores nothing extra.
+// =============================================================================================
+namespace olb {
+
+enum { GP_TX = 0, GP_TY = 1, GP_TZ = 2, GP_CURV = 3, GP_CONIC = 4, GP_N1 = 5, GP_N2 = 6, GP_COEF = 7,
+       GP_MAX_COEF = 12, GP_COUNT = GP_COEF + GP_MAX_COEF };
+
+template <typename T>
+struct Adjoint { T x, y, z, L, M, N, i, opd; };
+
+// pre: state BEFORE the surface in GLOBAL coordinates (record row s-1 or the launch state);
+// (x1g, y1g, z1g): position AFTER the surface (record row s), global.
+// a: in = dLoss/d(state after the surface, global); out = dLoss/d(state before it, global).
+// pg[GP_COUNT]: += dLoss/d(surface parameters).  Returns false (and leaves `a` zeroed) when
+// the ray is not finite at this surface (NaN in band: it carries no gradient).
+template <typename T>
+OLB_HD bool surface_backward(const PrepSurface<T>& S, const T* pool, T xg0, T yg0, T zg0, T L, T M, T N, T i0,
+                             T x1g, T y1g, T z1g, Adjoint<T>& a, T* pg) {
+  const T* med = pool + S.media_off;  // one wavelength
+  const T n1 = med[MED_N1], u = med[MED_U];
+  const T n2 = o_div(n1, u);
+  // local frame (unrotated): p = pg - t
+  const T x0 = xg0 - S.t[0], y0 = yg0 - S.t[1], z0 = zg0 - S.t[2];
+  const T x1 = x1g - S.t[0], y1 = y1g - S.t[1], z1 = z1g - S.t[2];
+  const T dd = o_fma(L, L, o_fma(M, M, N * N));
+  const T t = o_div(o_fma(x1 - x0, L, o_fma(y1 - y0, M, (z1 - z0) * N)), dd);
+  const T chk = x1 + y1 + z1 + L + M + N + t;
+  if (!(chk == chk) || chk - chk != 0) {  // NaN / inf anywhere
+    a.x = a.y = a.z = a.L = a.M = a.N = a.i = a.opd = 0;
+    return false;
+  }
+  // ---- recompute slopes, curvature terms -------------------------------------------------
+  const bool plane = S.kind == OLB_GEOM_PLANE;
+  const T r2 = o_fma(x1, x1, y1 * y1);
+  T g = 0, gp = 0, sconic = 1, c = 0, kp1 = S.kp1;
+  T asph_p = 0, asph_pp = 0;
+  if (!plane) {
+    c = S.curv;
+    sconic = o_sqrt(o_fma(-kp1 * r2, c * c, (T)1));
+    const T is = o_rcp(sconic);
+    const T is3 = is * is * is;
+    g = c * is;                                   // conic part of 2 S'(r2)
+    gp = (T)0.5 * kp1 * c * c * c * is3;          // d/dr2
+    if (S.kind == OLB_GEOM_EVEN_ASPHERE) {
+      const T* cf = pool + S.coef_off;
+      for (int j = S.n_coef - 1; j >= 0; --j) {   // Horner: sum 2(j+1) C_j r2^j and its r2-derivative
+        asph_pp = o_fma(asph_pp, r2, asph_p);
+        asph_p = o_fma(asph_p, r2, (T)(2 * (j + 1)) * cf[j]);
+      }
+      g += asph_p;
+      gp += asph_pp;
+    }
+  }
+  const T fx = x1 * g, fy = y1 * g;
+  const T invG = plane ? (T)1 : o_rsqrt(o_fma(fx, fx, o_fma(fy, fy, (T)1)));
+  // unit normal: plane (0,0,+1) (plane.py:90-109), otherwise (fx, fy, -1)/|.|
+  const T nx = plane ? (T)0 : fx * invG, ny = plane ? (T)0 : fy * invG, nz = plane ? (T)1 : -invG;
+  const T dot = o_fma(L, nx, o_fma(M, ny, N * nz));
+
+  // ---- adjoint of globalize ---------------------------------------------------------------
+  T apx = a.x, apy = a.y, apz = a.z;            // d/d p1
+  pg[GP_TX] += apx; pg[GP_TY] += apy; pg[GP_TZ] += apz;
+  T ai = a.i;
+  if (S.coating == OLB_COAT_SIMPLE) ai *= (S.flags & OLB_SF_REFLECT) ? S.coat_r : S.coat_t;
+  // ---- adjoint of the interaction ------------------------------------------------------------
+  T adL, adM, adN, anx, any_, anz;
+  if (S.flags & OLB_SF_REFLECT) {
+    const T dn = o_fma(a.L, nx, o_fma(a.M, ny, a.N * nz));
+    adL = o_fma((T)-2 * dn, nx, a.L); adM = o_fma((T)-2 * dn, ny, a.M); adN = o_fma((T)-2 * dn, nz, a.N);
+    anx = (T)-2 * o_fma(dot, a.L, dn * L); any_ = (T)-2 * o_fma(dot, a.M, dn * M); anz = (T)-2 * o_fma(dot, a.N, dn * N);
+  } else {
+    const T sgn = dot > 0 ? (T)1 : (dot < 0 ? (T)-1 : (T)0);
+    const T aa = o_abs(dot);
+    const T mx = sgn * nx, my = sgn * ny, mz = sgn * nz;
+    const T root = o_sqrt(o_fma(u * u, o_fma(aa, aa, (T)-1), (T)1));
+    const T h = o_fma(-u, aa, root);
+    const T ah = o_fma(a.L, mx, o_fma(a.M, my, a.N * mz));
+    const T ir = o_rcp(root);
+    T au = o_fma(a.L, L, o_fma(a.M, M, a.N * N)) - aa * ah + ah * u * o_fma(aa, aa, (T)-1) * ir;
+    T adot = -u * ah + ah * u * u * aa * ir;
+    if (u == (T)1) { au = o_fma(a.L, L, o_fma(a.M, M, a.N * N)) - aa * ah + ah * o_fma(aa, aa, (T)-1) * o_rcp(aa); adot = 0; }
+    adL = o_fma(u, a.L, adot * mx); adM = o_fma(u, a.M, adot * my); adN = o_fma(u, a.N, adot * mz);
+    const T amx = o_fma(h, a.L, adot * L), amy = o_fma(h, a.M, adot * M), amz = o_fma(h, a.N, adot * N);
+    anx = sgn * amx; any_ = sgn * amy; anz = sgn * amz;
+    pg[GP_N1] += o_div(au, n2);
+    pg[GP_N2] -= o_div(au * u, n2);
+  }
+  // ---- adjoint of the normal (Hessian of the sag) -------------------------------------------
+  T ax1 = 0, ay1 = 0, ag = 0;
+  if (!plane) {
+    const T an_n = o_fma(anx, nx, o_fma(any_, ny, anz * nz));
+    const T afx = (anx - an_n * nx) * invG, afy = (any_ - an_n * ny) * invG;
+    ag = o_fma(afx, x1, afy * y1);
+    const T ar2 = ag * gp;
+    ax1 = o_fma(afx, g, (T)2 * x1 * ar2);
+    ay1 = o_fma(afy, g, (T)2 * y1 * ar2);
+  }
+  // ---- clip / absorption / OPD ------------------------------------------------------------------
+  T at = 0;
+  {
+    bool inside = true;
+    if (S.flags & OLB_SF_APERTURE) inside = (r2 <= pool[S.aper_off + 1]) && (r2 >= pool[S.aper_off + 2]);
+    T E = 1;
+    if (S.flags & OLB_SF_ABSORBING) { E = o_exp(-med[MED_ALPHA] * t); at -= ai * i0 * med[MED_ALPHA] * E * (inside ? (T)1 : (T)0); }
+    ai = inside ? ai * E : (T)0;
+    const T tn = t * n1;
+    const T sg = tn > 0 ? (T)1 : (tn < 0 ? (T)-1 : (T)0);
+    at = o_fma(a.opd * sg, n1, at);
+    pg[GP_N1] += a.opd * sg * t;
+  }
+  // ---- propagate p1 = p0 + t d0 ---------------------------------------------------------------------
+  apx += ax1; apy += ay1;
+  adL = o_fma(t, apx, adL); adM = o_fma(t, apy, adM); adN = o_fma(t, apz, adN);
+  at += o_fma(apx, L, o_fma(apy, M, apz * N));
+  // ---- intersection (implicit function theorem) -------------------------------------------------------
+  const T D = o_fma(fx, L, o_fma(fy, M, -N));
+  const T q = -o_div(at, D);
+  apx = o_fma(q, fx, apx); apy = o_fma(q, fy, apy); apz -= q;
+  const T qt = q * t;
+  adL = o_fma(qt, fx, adL); adM = o_fma(qt, fy, adM); adN -= qt;
+  if (!plane) {
+    const T is = o_rcp(sconic), is3 = is * is * is, ops = (T)1 + sconic;
+    // d sag / d c = r2 / (s (1+s)) ; d sag / d k = c^3 r2^2 / (2 s (1+s)^2)
+    // d g / d c = 1 / s^3          ; d g / d k   = c^3 r2 / (2 s^3)
+    const T c3 = c * c * c;
+    pg[GP_CURV] += q * r2 * is * o_rcp(ops) + ag * is3;
+    pg[GP_CONIC] += q * (T)0.5 * c3 * r2 * r2 * is * o_rcp(ops * ops) + ag * (T)0.5 * c3 * r2 * is3;
+    if (S.kind == OLB_GEOM_EVEN_ASPHERE) {
+      T pw = 1;                                  // r2^j
+      for (int j = 0; j < S.n_coef && j < GP_MAX_COEF; ++j) {
+        pg[GP_COEF + j] += q * pw * r2 + ag * (T)(2 * (j + 1)) * pw;   // d sag/dC_j = r2^(j+1); d g/dC_j = 2(j+1) r2^j
+        pw *= r2;
+      }
+    }
+  }
+  // ---- localize p0 = pg0 - t -------------------------------------------------------------------------
+  pg[GP_TX] -= apx; pg[GP_TY] -= apy; pg[GP_TZ] -= apz;
+  a.x = apx; a.y = apy; a.z = apz; a.L = adL; a.M = adM; a.N = adN; a.i = ai;  // a.opd passes through
+  return true;
 }
 
 }  // namespace olb

@@ -139,6 +139,7 @@ static inline void zernike_add_monomials(int n, int m, double coef, int deg, dou
 struct PrepResult {
   std::vector<unsigned char> blob_f64, blob_f32;
   uint32_t features = 0;
+  bool bwd_supported = true;   // every surface is covered by surface_backward (olb_math.cuh)
   std::string error;
 };
 
@@ -359,6 +360,15 @@ static inline PrepResult prepare_table(const OlbTable& tab) {
     else if (in.coating != OLB_COAT_NONE) { res.error = "unknown coating"; return res; }
   }
   res.features = features;
+  for (int s = 0; s < tab.n_surfaces; ++s) {
+    const PrepSurface<double>& o = ps[s];
+    const bool kind_ok = o.kind == OLB_GEOM_NOOP || o.kind == OLB_GEOM_PLANE || o.kind == OLB_GEOM_STANDARD ||
+                         (o.kind == OLB_GEOM_EVEN_ASPHERE && o.n_coef <= 12);
+    const bool aper_ok = !(o.flags & OLB_SF_APERTURE) || (o.flags & PSF_APER_RADIAL);
+    if (!kind_ok || !aper_ok || (o.flags & (OLB_SF_ROTATED | PSF_ROT_IN_G | PSF_ROT_IN_R)) ||
+        o.coating == OLB_COAT_FRESNEL || tab.n_wl != 1)
+      res.bwd_supported = false;
+  }
   build_blob<double>(tab, pools, ps, features, res.blob_f64);
   build_blob<float>(tab, pools, ps, features, res.blob_f32);
   return res;

@@ -330,6 +330,143 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<T, RPT, FEAT>::v)) trace_ker
   if (status != 0 && a.status != nullptr) atomicOr(a.status, status);
 }
 
+
+// ---- backward kernel -------------------------------------------------------------------------
+struct BwdArgs {
+  const unsigned char* blob;
+  int32_t blob_bytes;
+  int32_t first, last, n_surf;
+  int64_t n_rays, rec_stride, grec_stride;
+  const void* in[7];     // launch state x y z L M N i
+  const void* rec[8];    // forward records
+  const void* grec[8];   // dLoss/d records (entries may be null)
+  void* gin[8];          // dLoss/d launch state (may be null as a whole: gin[0] == null)
+  double* gparams;       // n_surf * GP_COUNT, accumulated
+};
+
+template <typename T>
+__global__ void __launch_bounds__(BLOCK, 2) trace_bwd_kernel(const __grid_constant__ BwdArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+  unsigned char* tab = smem + 16;
+  stage_table(tab, a.blob, (uint32_t)a.blob_bytes, bar);
+  const PrepHeader* H = reinterpret_cast<const PrepHeader*>(tab);
+  const PrepSurface<T>* surf = reinterpret_cast<const PrepSurface<T>*>(tab + sizeof(PrepHeader));
+  const T* pool = reinterpret_cast<const T*>(surf + H->n_surf);
+  double* acc = reinterpret_cast<double*>(tab + ((a.blob_bytes + 15) & ~15));
+  const int n_acc = a.n_surf * GP_COUNT;
+  for (int q = threadIdx.x; q < n_acc; q += BLOCK) acc[q] = 0.0;
+  __syncthreads();
+
+  const int64_t n = a.n_rays;
+  const int64_t n_tiles = (n + BLOCK - 1) / BLOCK;
+  const int lane = threadIdx.x & 31;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t k = tile * BLOCK + threadIdx.x;
+    const bool valid = k < n;
+    const int64_t kk = valid ? k : 0;
+    Adjoint<T> ad{0, 0, 0, 0, 0, 0, 0, 0};
+    for (int s = a.last - 1; s >= a.first; --s) {
+      const int64_t off = (int64_t)(s - a.first) * a.rec_stride + kk;
+      const int64_t goff = (int64_t)(s - a.first) * a.grec_stride + kk;
+      if (valid) {
+        if (a.grec[0]) ad.x += __ldcs((const T*)a.grec[0] + goff);
+        if (a.grec[1]) ad.y += __ldcs((const T*)a.grec[1] + goff);
+        if (a.grec[2]) ad.z += __ldcs((const T*)a.grec[2] + goff);
+        if (a.grec[3]) ad.L += __ldcs((const T*)a.grec[3] + goff);
+        if (a.grec[4]) ad.M += __ldcs((const T*)a.grec[4] + goff);
+        if (a.grec[5]) ad.N += __ldcs((const T*)a.grec[5] + goff);
+        if (a.grec[6]) ad.i += __ldcs((const T*)a.grec[6] + goff);
+        if (a.grec[7]) ad.opd += __ldcs((const T*)a.grec[7] + goff);
+      }
+      const PrepSurface<T>& S = surf[s];
+      if (S.kind == OLB_GEOM_NOOP) continue;   // records its input unchanged: adjoint passes through
+      T pg[GP_COUNT];
+#pragma unroll
+      for (int q = 0; q < GP_COUNT; ++q) pg[q] = 0;
+      if (valid) {
+        T pre[7];
+        if (s == a.first) {
+#pragma unroll
+          for (int q = 0; q < 7; ++q) pre[q] = __ldcs((const T*)a.in[q] + kk);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 7; ++q) pre[q] = __ldcs((const T*)a.rec[q] + off - a.rec_stride);
+        }
+        const T x1 = __ldcs((const T*)a.rec[0] + off), y1 = __ldcs((const T*)a.rec[1] + off),
+                z1 = __ldcs((const T*)a.rec[2] + off);
+        surface_backward<T>(S, pool, pre[0], pre[1], pre[2], pre[3], pre[4], pre[5], pre[6], x1, y1, z1, ad, pg);
+      }
+      // warp tree-reduction of the parameter gradients, one shared-memory atomic per warp
+      const int n_slots = GP_COEF + (S.kind == OLB_GEOM_EVEN_ASPHERE ? S.n_coef : 0);
+      for (int q = 0; q < n_slots; ++q) {
+        T v = pg[q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0 && v != 0) atomicAdd(&acc[s * GP_COUNT + q], (double)v);
+      }
+    }
+    if (valid && a.gin[0]) {
+      __stcs((T*)a.gin[0] + k, ad.x); __stcs((T*)a.gin[1] + k, ad.y); __stcs((T*)a.gin[2] + k, ad.z);
+      __stcs((T*)a.gin[3] + k, ad.L); __stcs((T*)a.gin[4] + k, ad.M); __stcs((T*)a.gin[5] + k, ad.N);
+      __stcs((T*)a.gin[6] + k, ad.i); __stcs((T*)a.gin[7] + k, ad.opd);
+    }
+  }
+  __syncthreads();
+  for (int q = threadIdx.x; q < n_acc; q += BLOCK)
+    if (acc[q] != 0.0) atomicAdd(&a.gparams[q], acc[q]);
+}
+
+template <typename T>
+static int trace_bwd_impl(const OlbDeviceTable* wh, int32_t first, int32_t last, const OlbRays* rays_in,
+                          const OlbRecords* rec, const OlbRecords* grec, const OlbRays* gin, double* gparams,
+                          int64_t n_rays, cudaStream_t stream) {
+  if (!wh || wh->magic != WS_MAGIC || !wh->workspace)
+    return fail(OLB_ERR_INVALID_ARG, "table handle was not initialised by olb_table_upload");
+  if (!wh->bwd_supported)
+    return fail(OLB_ERR_UNSUPPORTED, "backward: table has a rotated pose, a non plane/standard/even-asphere "
+                                     "geometry, a non-radial aperture, a Fresnel coating or several wavelengths");
+  if (!rays_in || !rec || !gparams) return fail(OLB_ERR_INVALID_ARG, "rays_in, rec and grad_params are required");
+  if (first < 0 || last > wh->n_surfaces || first > last) return fail(OLB_ERR_INVALID_ARG, "bad surface range");
+  if (n_rays <= 0 || first == last) return OLB_OK;
+  BwdArgs a{};
+  a.blob = (const unsigned char*)wh->workspace + (sizeof(T) == 8 ? wh->off_f64 : wh->off_f32);
+  a.blob_bytes = sizeof(T) == 8 ? wh->bytes_f64 : wh->bytes_f32;
+  a.first = first; a.last = last; a.n_surf = wh->n_surfaces; a.n_rays = n_rays;
+  const void* in[7] = {rays_in->x, rays_in->y, rays_in->z, rays_in->L, rays_in->M, rays_in->N, rays_in->i};
+  const void* rr[8] = {rec->x, rec->y, rec->z, rec->L, rec->M, rec->N, rec->intensity, rec->opd};
+  for (int q = 0; q < 7; ++q) { if (!in[q]) return fail(OLB_ERR_INVALID_ARG, "a launch-state array is NULL"); a.in[q] = in[q]; }
+  for (int q = 0; q < 8; ++q) { if (!rr[q]) return fail(OLB_ERR_INVALID_ARG, "backward needs all 8 record arrays"); a.rec[q] = rr[q]; }
+  a.rec_stride = rec->row_stride;
+  if (a.rec_stride < n_rays) return fail(OLB_ERR_INVALID_ARG, "record row_stride < n_rays");
+  if (grec) {
+    const void* gg[8] = {grec->x, grec->y, grec->z, grec->L, grec->M, grec->N, grec->intensity, grec->opd};
+    for (int q = 0; q < 8; ++q) a.grec[q] = gg[q];
+    a.grec_stride = grec->row_stride;
+    if (a.grec_stride < n_rays) return fail(OLB_ERR_INVALID_ARG, "grad record row_stride < n_rays");
+  }
+  if (gin) {
+    void* go[8] = {gin->x, gin->y, gin->z, gin->L, gin->M, gin->N, gin->i, gin->opd};
+    for (int q = 0; q < 8; ++q) { if (!go[q]) return fail(OLB_ERR_INVALID_ARG, "grad_rays_in needs all 8 arrays"); a.gin[q] = go[q]; }
+  }
+  a.gparams = gparams;
+  auto kern = trace_bwd_kernel<T>;
+  const size_t smem = 16 + ((size_t)a.blob_bytes + 15 & ~size_t(15)) + (size_t)wh->n_surfaces * GP_COUNT * sizeof(double);
+  if (smem > 48 * 1024) OLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int dev = 0, num_sms = 0, per_sm = 0;
+  OLB_CUDA(cudaGetDevice(&dev));
+  OLB_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  OLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, smem));
+  if (per_sm < 1) return fail(OLB_ERR_CUDA, "backward kernel does not fit on an SM");
+  int64_t grid = (int64_t)num_sms * per_sm;
+  const int64_t n_tiles = (n_rays + BLOCK - 1) / BLOCK;
+  if (grid > n_tiles) grid = n_tiles;
+  kern<<<(unsigned)grid, BLOCK, smem, stream>>>(a);
+  OLB_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return OLB_OK;
+}
+
 // ---- launcher -------------------------------------------------------------------------------
 template <typename T, int RPT, uint32_t FEAT>
 static int launch_instance(const TraceArgs& a, cudaStream_t stream) {
@@ -511,6 +648,7 @@ int olb_table_upload(const OlbTable* table, void* workspace, int64_t workspace_b
   h.bytes_f64 = (int32_t)pr.blob_f64.size();
   h.off_f32 = 64 + h.bytes_f64;
   h.bytes_f32 = (int32_t)pr.blob_f32.size();
+  h.bwd_supported = pr.bwd_supported ? 1 : 0;
   const int64_t need = 64 + (int64_t)h.bytes_f64 + h.bytes_f32;
   if (workspace_bytes < need) return fail(OLB_ERR_INVALID_ARG, "workspace too small");
   std::vector<unsigned char> staging((size_t)need, 0);
@@ -531,6 +669,19 @@ int olb_trace_f32(const OlbDeviceTable* table, int32_t first, int32_t last, cons
 int olb_trace_f64(const OlbDeviceTable* table, int32_t first, int32_t last, const OlbRays* rays,
                   const OlbRecords* rec, int64_t n_rays, uint32_t flags, int32_t* status, void* stream) {
   return trace_impl<double>(table, first, last, rays, rec, n_rays, flags, status, (cudaStream_t)stream);
+}
+
+int olb_trace_bwd_f32(const OlbDeviceTable* table, int32_t first, int32_t last, const OlbRays* rays_in,
+                      const OlbRecords* rec, const OlbRecords* grad_rec, const OlbRays* grad_rays_in,
+                      double* grad_params, int64_t n_rays, void* stream) {
+  return trace_bwd_impl<float>(table, first, last, rays_in, rec, grad_rec, grad_rays_in, grad_params, n_rays,
+                               (cudaStream_t)stream);
+}
+int olb_trace_bwd_f64(const OlbDeviceTable* table, int32_t first, int32_t last, const OlbRays* rays_in,
+                      const OlbRecords* rec, const OlbRecords* grad_rec, const OlbRays* grad_rays_in,
+                      double* grad_params, int64_t n_rays, void* stream) {
+  return trace_bwd_impl<double>(table, first, last, rays_in, rec, grad_rec, grad_rays_in, grad_params, n_rays,
+                                (cudaStream_t)stream);
 }
 
 // ---- host-buffer end-to-end path ---------------------------------------------------------------

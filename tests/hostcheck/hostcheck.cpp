@@ -80,7 +80,55 @@ static int run(const OlbTable* tab, int first, int last, int64_t n, T** ray, T**
   return OLB_OK;
 }
 
+// Reverse sweep over surfaces for every ray: the loop the backward kernel runs per thread.
+template <typename T>
+static int run_backward(const OlbTable* tab, int first, int last, int64_t n, T** ray_in /*x y z L M N i w opd*/,
+                        T** rec /*8 x rows*n*/, T** grec /*8, entries may be null*/, T** gin /*8 out*/,
+                        double* gparams /*n_surf*GP_COUNT, accumulated*/, char* err, int err_len) {
+  PrepResult pr = prepare_table(*tab);
+  if (!pr.error.empty()) { snprintf(err, err_len, "%s", pr.error.c_str()); return OLB_ERR_TABLE; }
+  const unsigned char* blob = sizeof(T) == 8 ? pr.blob_f64.data() : pr.blob_f32.data();
+  const PrepHeader* H = reinterpret_cast<const PrepHeader*>(blob);
+  const PrepSurface<T>* surf = reinterpret_cast<const PrepSurface<T>*>(blob + sizeof(PrepHeader));
+  const T* pool = reinterpret_cast<const T*>(surf + H->n_surf);
+  for (int64_t k = 0; k < n; ++k) {
+    Adjoint<T> a{0, 0, 0, 0, 0, 0, 0, 0};
+    for (int s = last - 1; s >= first; --s) {
+      const int64_t off = (int64_t)(s - first) * n + k;
+      if (grec[0]) a.x += grec[0][off];
+      if (grec[1]) a.y += grec[1][off];
+      if (grec[2]) a.z += grec[2][off];
+      if (grec[3]) a.L += grec[3][off];
+      if (grec[4]) a.M += grec[4][off];
+      if (grec[5]) a.N += grec[5][off];
+      if (grec[6]) a.i += grec[6][off];
+      if (grec[7]) a.opd += grec[7][off];
+      const PrepSurface<T>& S = surf[s];
+      if (S.kind == OLB_GEOM_NOOP) continue;
+      T pre[7];
+      if (s == first) { for (int q = 0; q < 7; ++q) pre[q] = ray_in[q][k]; }
+      else { for (int q = 0; q < 7; ++q) pre[q] = rec[q][off - n]; }
+      T pg[GP_COUNT] = {0};
+      surface_backward<T>(S, pool, pre[0], pre[1], pre[2], pre[3], pre[4], pre[5], pre[6], rec[0][off], rec[1][off],
+                          rec[2][off], a, pg);
+      for (int q = 0; q < GP_COUNT; ++q) gparams[(int64_t)s * GP_COUNT + q] += (double)pg[q];
+    }
+    gin[0][k] = a.x; gin[1][k] = a.y; gin[2][k] = a.z; gin[3][k] = a.L; gin[4][k] = a.M; gin[5][k] = a.N;
+    gin[6][k] = a.i; gin[7][k] = a.opd;
+  }
+  return OLB_OK;
+}
+
 extern "C" {
+int olbhc_backward_f64(const OlbTable* tab, int first, int last, int64_t n, double** ray_in, double** rec,
+                       double** grec, double** gin, double* gparams, char* err, int err_len) {
+  return run_backward<double>(tab, first, last, n, ray_in, rec, grec, gin, gparams, err, err_len);
+}
+int olbhc_backward_f32(const OlbTable* tab, int first, int last, int64_t n, float** ray_in, float** rec,
+                       float** grec, float** gin, double* gparams, char* err, int err_len) {
+  return run_backward<float>(tab, first, last, n, ray_in, rec, grec, gin, gparams, err, err_len);
+}
+int olbhc_gp_count() { return GP_COUNT; }
 int olbhc_trace_f64(const OlbTable* tab, int first, int last, int64_t n, double** ray, double** rec, double** l0,
                     double* pmat, int* status, char* err, int err_len) {
   return run<double>(tab, first, last, n, ray, rec, l0, pmat, status, err, err_len);
