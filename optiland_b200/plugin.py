@@ -12,7 +12,9 @@
 2. wraps ``SurfaceGroup.trace`` (optiland/surfaces/surface_group.py:245-257) and ``Surface.trace``
    (optiland/surfaces/standard_surface.py:200-215, the per-surface entry the ray aimers use) so that
    they try the capability first and run the reference's own Python body when it declines
-   (unsupported surface kind, CPU tensors, gradients requested, ...).
+   (unsupported surface kind, CPU tensors, ...).  With ``be.grad_mode`` on, the capability runs
+   the forward and the hand-derived adjoint kernel as ONE ``torch.autograd.Function`` whose inputs
+   are the live parameter tensors, so ``TorchBaseOptimizer`` differentiates through it.
 
 ``Optic.trace``, ``SpotDiagram``, ``Wavefront``, PSF and the optimisers are untouched and call
 the path unchanged.  Declining is NOT a CPU fallback of this package: it hands the call back to
@@ -97,12 +99,29 @@ class CudaEngine:
         return rec
 
 
+    def trace_grad(self, table: T.SurfaceTable, params, rays):
+        """Differentiable trace of Optiland's ``rays``: records are autograd outputs of ``params`` and of
+        the ray tensors.  None if the table is outside olb_trace_bwd_*'s scope."""
+        from . import autograd as AG
+
+        dt = self.device_table(table, rays.x.device)
+        if not dt.c.bwd_supported:
+            return None
+        ins = [getattr(rays, k) for k in ("x", "y", "z", "L", "M", "N", "i", "opd")]
+        outs = AG._TraceFnWrapper.apply(table, [], params, *ins)
+        rec = dict(zip(("x", "y", "z", "L", "M", "N", "intensity", "opd"), outs))
+        for k, key in (("x", "x"), ("y", "y"), ("z", "z"), ("L", "L"), ("M", "M"), ("N", "N"), ("i", "intensity"), ("opd", "opd")):
+            setattr(rays, k, rec[key][-1])
+        return rec
+
+
 def _unique_wavelengths(w):
     """Distinct wavelengths of the batch (exact values), or None if there are too many."""
     import torch
 
     if w.numel() == 0:
         return None
+    w = w.detach()
     lo, hi = torch.aminmax(w)
     if bool(lo == hi):
         return np.array([float(lo)], dtype=np.float64)
@@ -133,6 +152,51 @@ def _set_pre_interaction_direction(rays, table, rec, first, last, launch_dir):
     rays.L0, rays.M0, rays.N0 = L0, M0, N0
 
 
+def _live_params(surfaces, table, wavelength):
+    """(S, GP_COUNT) fp64 tensor of the differentiable parameters, built with torch ops FROM THE LIVE
+    tensors of the Optiland objects (geometry.cs.x/y/z, geometry.radius, geometry.k,
+    geometry.coefficients, material_pre/post.n(lambda)) so that gradients flow back to whatever leaves
+    the optimiser owns (optic/optic_updater.py:38-157).  None if a surface is outside the adjoint's scope."""
+    import torch
+
+    from .autograd import GP_COEF, GP_CONIC, GP_COUNT, GP_CURV, GP_MAX_COEF, GP_N1, GP_N2, GP_TX
+
+    def scalar(v, like):
+        t = v if torch.is_tensor(v) else torch.as_tensor(float(v))
+        return t.to(dtype=torch.float64, device=like.device).reshape(())
+
+    like = None
+    for surf in surfaces:
+        r = getattr(surf.geometry, "radius", None)
+        if torch.is_tensor(r):
+            like = r
+            break
+    if like is None:
+        like = torch.zeros(())
+    rows = []
+    zero = torch.zeros((), dtype=torch.float64, device=like.device)
+    for surf, spec in zip(surfaces, table.surfaces):
+        vals = [zero] * GP_COUNT
+        if spec.kind != T.GEOM_NOOP:
+            g = surf.geometry
+            cs = g.cs
+            if cs.reference_cs is not None or spec.rotated or spec.kind not in (T.GEOM_PLANE, T.GEOM_STANDARD, T.GEOM_EVEN_ASPHERE):
+                return None
+            vals[GP_TX], vals[GP_TX + 1], vals[GP_TX + 2] = scalar(cs.x, like), scalar(cs.y, like), scalar(cs.z, like)
+            if spec.kind != T.GEOM_PLANE:
+                vals[GP_CURV] = zero if not np.isfinite(spec.radius) else 1.0 / scalar(g.radius, like)
+                vals[GP_CONIC] = scalar(g.k, like)
+            vals[GP_N1] = scalar(surf.material_pre.n(wavelength), like)
+            vals[GP_N2] = scalar(surf.material_post.n(wavelength), like)
+            if spec.kind == T.GEOM_EVEN_ASPHERE:
+                if len(g.coefficients) > GP_MAX_COEF:
+                    return None
+                for j, cj in enumerate(g.coefficients):
+                    vals[GP_COEF + j] = scalar(cj, like)
+        rows.append(torch.stack(vals))
+    return torch.stack(rows)
+
+
 def _try_trace(backend, surfaces, rays, table_builder) -> bool:
     """Common body of the two wrappers.  ``surfaces``: the Surface objects to be traced (in
     order); ``table_builder(wavelengths)`` packs them.  Returns False to decline."""
@@ -142,8 +206,6 @@ def _try_trace(backend, surfaces, rays, table_builder) -> bool:
     engine = _state["engine"]
     if not engine.accepts(rays):
         return False
-    if backend.grad_mode.requires_grad:
-        return False  # autograd through the kernel is not built yet: reference's eager graph
     wl = _unique_wavelengths(rays.w)
     if wl is None:
         return False
@@ -154,7 +216,21 @@ def _try_trace(backend, surfaces, rays, table_builder) -> bool:
     if not polarized and any(s.coating == T.COAT_FRESNEL for s in table.surfaces):
         return False  # the reference raises for this combination (ray_generator.py:90-94)
     launch_dir = (rays.L, rays.M, rays.N)
-    rec = engine.trace(table, rays, 0, table.num_surfaces)
+    if backend.grad_mode.requires_grad:
+        # be.grad_mode on: the records must be autograd outputs of the live parameter tensors
+        # (optimization/operand/ray.py:299-342 differentiates through a recorded row).  One custom
+        # Function (forward kernel + adjoint kernel) replaces the eager graph; tables outside the
+        # adjoint's scope go back to the reference's eager path.
+        if polarized or table.n_wl != 1:
+            return False
+        params = _live_params(surfaces, table, float(wl[0]))
+        if params is None:
+            return False
+        rec = engine.trace_grad(table, params, rays)
+        if rec is None:
+            return False
+    else:
+        rec = engine.trace(table, rays, 0, table.num_surfaces)
     for row, surf in enumerate(surfaces):
         for attr, key in _REC_ATTR:
             setattr(surf, attr, rec[key][row])

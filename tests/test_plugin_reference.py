@@ -46,6 +46,47 @@ class OracleEngine:
         return {k: torch.from_numpy(v).to(dt) for k, v in rec.items()}
 
 
+    def trace_grad(self, table, params, rays):
+        """TEST-ONLY differentiable engine: oracle forward + the CPU instantiation of the device adjoint
+        (tests/hostcheck) -- the arithmetic of olb_trace_bwd_* without a GPU."""
+        import ctypes as C
+
+        import torch
+
+        from oracle import trace_oracle as O
+        from optiland_b200 import autograd as AG
+        from tests.test_hostcheck import SO
+        from tests.test_hostcheck_backward import run_backward
+
+        hc = C.CDLL(SO)
+        self.calls.append(("grad", table.num_surfaces, int(rays.x.numel())))
+        keys = ("x", "y", "z", "L", "M", "N", "i", "opd")
+
+        class Fn(torch.autograd.Function):
+            @staticmethod
+            def forward(ctx, params, *ins):
+                ctx.set_materialize_grads(False)
+                tab = AG.params_to_table(table, params)
+                inp = {k: t.detach().double().numpy() for k, t in zip(keys, ins)}
+                inp["w"] = rays.w.detach().double().numpy()
+                _, rec, _ = O.trace(tab, inp)
+                ctx.tab, ctx.inp, ctx.rec = tab, inp, rec
+                return tuple(torch.from_numpy(rec[k]) for k in ("x", "y", "z", "L", "M", "N", "intensity", "opd"))
+
+            @staticmethod
+            def backward(ctx, *grads):
+                grec = {k: (None if g is None else g.double().numpy()) for k, g in
+                        zip(("x", "y", "z", "L", "M", "N", "intensity", "opd"), grads)}
+                gin, gpar = run_backward(hc, ctx.tab, ctx.inp, ctx.rec, grec)
+                return (torch.from_numpy(gpar), *[torch.from_numpy(gin[k]) for k in keys])
+
+        outs = Fn.apply(params, *[getattr(rays, k) for k in keys])
+        rec = dict(zip(("x", "y", "z", "L", "M", "N", "intensity", "opd"), outs))
+        for k, key in zip(keys, ("x", "y", "z", "L", "M", "N", "intensity", "opd")):
+            setattr(rays, k, rec[key][-1])
+        return rec
+
+
 @pytest.fixture()
 def plugin():
     from oracle.ref_import import import_reference
@@ -127,14 +168,6 @@ def test_spot_diagram_runs_unchanged_on_top(plugin):
 def test_declines_and_falls_back_to_reference_python(plugin):
     P, eng, be = plugin
     from optiland.samples.objectives import CookeTriplet
-
-    # gradients requested -> decline (autograd through the kernel not built yet)
-    be.grad_mode.enable()
-    n0 = len(eng.calls)
-    lens = CookeTriplet()
-    rays = lens.trace(0.0, 1.0, 0.55, 4, "hexapolar")
-    assert len(eng.calls) == n0 and rays.x.requires_grad
-    be.grad_mode.disable()
 
     # unsupported geometry (toroidal) -> decline, results still those of the reference
     def make():
@@ -227,3 +260,40 @@ def test_polarized_trace_with_fresnel_coatings(plugin):
     np.testing.assert_allclose(be.to_numpy(rays.i), ref_i, atol=1e-12)
     np.testing.assert_allclose(rays.p.detach().numpy(), ref_p, atol=1e-12)
     assert float(ref_i.max()) < 0.8  # Fresnel losses really applied
+
+
+def test_autograd_through_the_capability_matches_reference_eager_graph(plugin):
+    """Config 3 through the drop-in: with be.grad_mode on, d(RMS spot)/d(radius, conic, thickness-z) obtained
+    via Optic.trace -> capability (one custom autograd Function) equals the reference's own eager autograd,
+    INCLUDING the dependence of the launch rays on the radii through paraxial ray aiming."""
+    import torch
+
+    P, eng, be = plugin
+    from oracle.make_golden import reverse_telephoto_asphere
+
+    def run(lens):
+        rays = lens.trace(0.0, 0.7, 0.5876, 6, "hexapolar")
+        x = lens.surfaces.x[-1, :]
+        y = lens.surfaces.y[-1, :]
+        loss = torch.sqrt(torch.mean((x - torch.mean(x)) ** 2 + (y - torch.mean(y)) ** 2))
+        loss.backward()
+        out = {"loss": float(loss.detach())}
+        for s in (1, 2, 13):
+            g = lens.surfaces.surfaces[s].geometry
+            out[f"r{s}"] = float(g.radius.grad)
+        out["k13"] = float(lens.surfaces.surfaces[13].geometry.k.grad)
+        out["z1"] = float(lens.surfaces.surfaces[1].geometry.cs.z.grad)
+        return out
+
+    be.grad_mode.enable()
+    try:
+        n0 = len(eng.calls)
+        got = run(reverse_telephoto_asphere(1e-12))
+        assert any(c[0] == "grad" for c in eng.calls[n0:])
+        P.uninstall()                       # the reference's own eager graph
+        ref = run(reverse_telephoto_asphere(1e-12))
+    finally:
+        be.grad_mode.disable()
+    assert got["loss"] == pytest.approx(ref["loss"], rel=1e-9)
+    for k in ref:
+        assert got[k] == pytest.approx(ref[k], rel=2e-6), k
