@@ -688,8 +688,9 @@ OLB_HD bool surface_backward(const PrepSurface<T>& S, const T* pool, T xg0, T yg
     pg[GP_CONIC] += q * (T)0.5 * c3 * r2 * r2 * is * o_rcp(ops * ops) + ag * (T)0.5 * c3 * r2 * is3;
     if (S.kind == OLB_GEOM_EVEN_ASPHERE) {
       T pw = 1;                                  // r2^j
-      for (int j = 0; j < S.n_coef && j < GP_MAX_COEF; ++j) {
-        pg[GP_COEF + j] += q * pw * r2 + ag * (T)(2 * (j + 1)) * pw;   // d sag/dC_j = r2^(j+1); d g/dC_j = 2(j+1) r2^j
+#pragma unroll
+      for (int j = 0; j < GP_MAX_COEF; ++j) {    // compile-time bound: pg[] stays in registers
+        if (j < S.n_coef) pg[GP_COEF + j] += q * pw * r2 + ag * (T)(2 * (j + 1)) * pw;  // d sag/dC_j = r2^(j+1); d g/dC_j = 2(j+1) r2^j
         pw *= r2;
       }
     }

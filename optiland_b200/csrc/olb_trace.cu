@@ -344,8 +344,11 @@ struct BwdArgs {
   double* gparams;       // n_surf * GP_COUNT, accumulated
 };
 
-template <typename T>
-__global__ void __launch_bounds__(BLOCK, 2) trace_bwd_kernel(const __grid_constant__ BwdArgs a) {
+// RPB rays per thread (ray j of a tile = tile*BLOCK*RPB + j*BLOCK + thread: coalesced scalar accesses).
+// Their parameter-gradient contributions for one surface are summed in registers first, so the
+// warp tree-reduction + shared-memory atomic is paid once per RPB rays.
+template <typename T, int RPB>
+__global__ void __launch_bounds__(BLOCK, (sizeof(T) == 8 ? 1 : 2)) trace_bwd_kernel(const __grid_constant__ BwdArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
   unsigned char* tab = smem + 16;
@@ -359,57 +362,79 @@ __global__ void __launch_bounds__(BLOCK, 2) trace_bwd_kernel(const __grid_consta
   __syncthreads();
 
   const int64_t n = a.n_rays;
-  const int64_t n_tiles = (n + BLOCK - 1) / BLOCK;
+  const int64_t per_tile = (int64_t)BLOCK * RPB;
+  const int64_t n_tiles = (n + per_tile - 1) / per_tile;
   const int lane = threadIdx.x & 31;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t k = tile * BLOCK + threadIdx.x;
-    const bool valid = k < n;
-    const int64_t kk = valid ? k : 0;
-    Adjoint<T> ad{0, 0, 0, 0, 0, 0, 0, 0};
+    int64_t kk[RPB];
+    bool valid[RPB];
+    Adjoint<T> ad[RPB];
+#pragma unroll
+    for (int j = 0; j < RPB; ++j) {
+      const int64_t k = tile * per_tile + (int64_t)j * BLOCK + threadIdx.x;
+      valid[j] = k < n;
+      kk[j] = valid[j] ? k : 0;
+      ad[j] = Adjoint<T>{0, 0, 0, 0, 0, 0, 0, 0};
+    }
     for (int s = a.last - 1; s >= a.first; --s) {
-      const int64_t off = (int64_t)(s - a.first) * a.rec_stride + kk;
-      const int64_t goff = (int64_t)(s - a.first) * a.grec_stride + kk;
-      if (valid) {
-        if (a.grec[0]) ad.x += __ldcs((const T*)a.grec[0] + goff);
-        if (a.grec[1]) ad.y += __ldcs((const T*)a.grec[1] + goff);
-        if (a.grec[2]) ad.z += __ldcs((const T*)a.grec[2] + goff);
-        if (a.grec[3]) ad.L += __ldcs((const T*)a.grec[3] + goff);
-        if (a.grec[4]) ad.M += __ldcs((const T*)a.grec[4] + goff);
-        if (a.grec[5]) ad.N += __ldcs((const T*)a.grec[5] + goff);
-        if (a.grec[6]) ad.i += __ldcs((const T*)a.grec[6] + goff);
-        if (a.grec[7]) ad.opd += __ldcs((const T*)a.grec[7] + goff);
+      const int64_t roff = (int64_t)(s - a.first) * a.rec_stride;
+      const int64_t groff = (int64_t)(s - a.first) * a.grec_stride;
+#pragma unroll
+      for (int j = 0; j < RPB; ++j) {
+        if (!valid[j]) continue;
+        const int64_t goff = groff + kk[j];
+        if (a.grec[0]) ad[j].x += __ldcs((const T*)a.grec[0] + goff);
+        if (a.grec[1]) ad[j].y += __ldcs((const T*)a.grec[1] + goff);
+        if (a.grec[2]) ad[j].z += __ldcs((const T*)a.grec[2] + goff);
+        if (a.grec[3]) ad[j].L += __ldcs((const T*)a.grec[3] + goff);
+        if (a.grec[4]) ad[j].M += __ldcs((const T*)a.grec[4] + goff);
+        if (a.grec[5]) ad[j].N += __ldcs((const T*)a.grec[5] + goff);
+        if (a.grec[6]) ad[j].i += __ldcs((const T*)a.grec[6] + goff);
+        if (a.grec[7]) ad[j].opd += __ldcs((const T*)a.grec[7] + goff);
       }
       const PrepSurface<T>& S = surf[s];
       if (S.kind == OLB_GEOM_NOOP) continue;   // records its input unchanged: adjoint passes through
       T pg[GP_COUNT];
 #pragma unroll
       for (int q = 0; q < GP_COUNT; ++q) pg[q] = 0;
-      if (valid) {
+#pragma unroll
+      for (int j = 0; j < RPB; ++j) {
+        if (!valid[j]) continue;
+        const int64_t off = roff + kk[j];
         T pre[7];
         if (s == a.first) {
 #pragma unroll
-          for (int q = 0; q < 7; ++q) pre[q] = __ldcs((const T*)a.in[q] + kk);
+          for (int q = 0; q < 7; ++q) pre[q] = __ldcs((const T*)a.in[q] + kk[j]);
         } else {
 #pragma unroll
           for (int q = 0; q < 7; ++q) pre[q] = __ldcs((const T*)a.rec[q] + off - a.rec_stride);
         }
         const T x1 = __ldcs((const T*)a.rec[0] + off), y1 = __ldcs((const T*)a.rec[1] + off),
                 z1 = __ldcs((const T*)a.rec[2] + off);
-        surface_backward<T>(S, pool, pre[0], pre[1], pre[2], pre[3], pre[4], pre[5], pre[6], x1, y1, z1, ad, pg);
+        surface_backward<T>(S, pool, pre[0], pre[1], pre[2], pre[3], pre[4], pre[5], pre[6], x1, y1, z1, ad[j], pg);
       }
-      // warp tree-reduction of the parameter gradients, one shared-memory atomic per warp
-      const int n_slots = GP_COEF + (S.kind == OLB_GEOM_EVEN_ASPHERE ? S.n_coef : 0);
-      for (int q = 0; q < n_slots; ++q) {
+      // warp tree-reduction of the parameter gradients, one shared-memory atomic per warp and slot
+      const int n_coef = S.kind == OLB_GEOM_EVEN_ASPHERE ? S.n_coef : 0;
+      const bool curved = S.kind != OLB_GEOM_PLANE;
+#pragma unroll
+      for (int q = 0; q < GP_COUNT; ++q) {
+        if (q >= GP_COEF + n_coef) break;
+        if (!curved && (q == GP_CURV || q == GP_CONIC)) continue;
         T v = pg[q];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         if (lane == 0 && v != 0) atomicAdd(&acc[s * GP_COUNT + q], (double)v);
       }
     }
-    if (valid && a.gin[0]) {
-      __stcs((T*)a.gin[0] + k, ad.x); __stcs((T*)a.gin[1] + k, ad.y); __stcs((T*)a.gin[2] + k, ad.z);
-      __stcs((T*)a.gin[3] + k, ad.L); __stcs((T*)a.gin[4] + k, ad.M); __stcs((T*)a.gin[5] + k, ad.N);
-      __stcs((T*)a.gin[6] + k, ad.i); __stcs((T*)a.gin[7] + k, ad.opd);
+    if (a.gin[0]) {
+#pragma unroll
+      for (int j = 0; j < RPB; ++j) {
+        if (!valid[j]) continue;
+        const int64_t k = kk[j];
+        __stcs((T*)a.gin[0] + k, ad[j].x); __stcs((T*)a.gin[1] + k, ad[j].y); __stcs((T*)a.gin[2] + k, ad[j].z);
+        __stcs((T*)a.gin[3] + k, ad[j].L); __stcs((T*)a.gin[4] + k, ad[j].M); __stcs((T*)a.gin[5] + k, ad[j].N);
+        __stcs((T*)a.gin[6] + k, ad[j].i); __stcs((T*)a.gin[7] + k, ad[j].opd);
+      }
     }
   }
   __syncthreads();
@@ -450,7 +475,8 @@ static int trace_bwd_impl(const OlbDeviceTable* wh, int32_t first, int32_t last,
     for (int q = 0; q < 8; ++q) { if (!go[q]) return fail(OLB_ERR_INVALID_ARG, "grad_rays_in needs all 8 arrays"); a.gin[q] = go[q]; }
   }
   a.gparams = gparams;
-  auto kern = trace_bwd_kernel<T>;
+  constexpr int RPB = sizeof(T) == 4 ? 4 : 2;
+  auto kern = trace_bwd_kernel<T, RPB>;
   const size_t smem = 16 + ((size_t)a.blob_bytes + 15 & ~size_t(15)) + (size_t)wh->n_surfaces * GP_COUNT * sizeof(double);
   if (smem > 48 * 1024) OLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, num_sms = 0, per_sm = 0;
@@ -459,7 +485,7 @@ static int trace_bwd_impl(const OlbDeviceTable* wh, int32_t first, int32_t last,
   OLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, smem));
   if (per_sm < 1) return fail(OLB_ERR_CUDA, "backward kernel does not fit on an SM");
   int64_t grid = (int64_t)num_sms * per_sm;
-  const int64_t n_tiles = (n_rays + BLOCK - 1) / BLOCK;
+  const int64_t n_tiles = (n_rays + (int64_t)BLOCK * RPB - 1) / ((int64_t)BLOCK * RPB);
   if (grid > n_tiles) grid = n_tiles;
   kern<<<(unsigned)grid, BLOCK, smem, stream>>>(a);
   OLB_CUDA(cudaGetLastError());
