@@ -234,7 +234,7 @@ typedef struct OlbDeviceTable {
   int32_t off_f64, bytes_f64;   /* fp64 blob inside workspace */
   int32_t off_f32, bytes_f32;   /* fp32 blob inside workspace */
   int32_t bwd_supported;        /* 1 if olb_trace_bwd_* covers every surface of the table */
-  int32_t reserved;
+  int32_t bwd_slots;            /* gradient accumulator slots per thread (backward kernel)   */
 } OlbDeviceTable;
 
 /* Bytes of device workspace needed for `table` (< 256 KiB). Negative = error code. */
@@ -302,6 +302,8 @@ int olb_trace_host_f64(const OlbDeviceTable* table, int32_t first, int32_t last,
  * Supported tables (OlbDeviceTable.bwd_supported): unrotated poses, plane / standard /
  * even-asphere geometry, no or radial aperture, no or simple coating, one wavelength;
  * otherwise OLB_ERR_UNSUPPORTED.  Rays that are NaN at a surface carry no gradient.
+ * grad_row_mask: bit r set = record row r of grad_rec may be non-zero (rows with a clear bit
+ * are not read); pass ~0 when unknown.
  */
 #define OLB_GP_TX 0
 #define OLB_GP_TY 1
@@ -315,10 +317,12 @@ int olb_trace_host_f64(const OlbDeviceTable* table, int32_t first, int32_t last,
 #define OLB_GP_COUNT (OLB_GP_COEF + OLB_GP_MAX_COEF)
 int olb_trace_bwd_f32(const OlbDeviceTable* table, int32_t first, int32_t last,
                       const OlbRays* rays_in, const OlbRecords* rec, const OlbRecords* grad_rec,
-                      const OlbRays* grad_rays_in, double* grad_params, int64_t n_rays, void* stream);
+                      const OlbRays* grad_rays_in, double* grad_params, int64_t n_rays,
+                      uint64_t grad_row_mask, void* stream);
 int olb_trace_bwd_f64(const OlbDeviceTable* table, int32_t first, int32_t last,
                       const OlbRays* rays_in, const OlbRecords* rec, const OlbRecords* grad_rec,
-                      const OlbRays* grad_rays_in, double* grad_params, int64_t n_rays, void* stream);
+                      const OlbRays* grad_rays_in, double* grad_params, int64_t n_rays,
+                      uint64_t grad_row_mask, void* stream);
 
 /* Number of kernel launches issued by this process through the library
  * (for bench.py's gpu_launches claim). */

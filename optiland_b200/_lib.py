@@ -50,7 +50,7 @@ class OlbDeviceTable(C.Structure):
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("magic", C.c_uint32),
         ("features", C.c_uint32), ("n_surfaces", C.c_int32), ("n_wl", C.c_int32),
         ("off_f64", C.c_int32), ("bytes_f64", C.c_int32), ("off_f32", C.c_int32),
-        ("bytes_f32", C.c_int32), ("bwd_supported", C.c_int32), ("reserved", C.c_int32),
+        ("bytes_f32", C.c_int32), ("bwd_supported", C.c_int32), ("bwd_slots", C.c_int32),
     ]
 
 
@@ -67,9 +67,9 @@ SYMBOLS = {
     "olb_trace_f64": (C.c_int, [_P(OlbDeviceTable), C.c_int32, C.c_int32, _P(OlbRays), _P(OlbRecords),
                                 C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p]),
     "olb_trace_bwd_f32": (C.c_int, [_P(OlbDeviceTable), C.c_int32, C.c_int32, _P(OlbRays), _P(OlbRecords),
-                                    _P(OlbRecords), _P(OlbRays), C.c_void_p, C.c_int64, C.c_void_p]),
+                                    _P(OlbRecords), _P(OlbRays), C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p]),
     "olb_trace_bwd_f64": (C.c_int, [_P(OlbDeviceTable), C.c_int32, C.c_int32, _P(OlbRays), _P(OlbRecords),
-                                    _P(OlbRecords), _P(OlbRays), C.c_void_p, C.c_int64, C.c_void_p]),
+                                    _P(OlbRecords), _P(OlbRays), C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p]),
     "olb_host_scratch_bytes": (C.c_int64, [C.c_int32, C.c_int64]),
     "olb_trace_host_f32": (C.c_int, [_P(OlbDeviceTable), C.c_int32, C.c_int32, _P(OlbRays), _P(OlbRays),
                                      _P(OlbRecords), C.c_int64, C.c_int64, C.c_void_p, C.c_int64,

@@ -63,8 +63,12 @@ def params_to_table(table: T.SurfaceTable, params: torch.Tensor) -> T.SurfaceTab
 
 
 class _TraceFn(torch.autograd.Function):
+    """forward(template, holder, rows, params, x, y, z, L, M, N, i, opd).  ``rows`` = None: the 8 outputs
+    are the full (S, N) record arrays; ``rows`` = tuple of row indices: 8 * len(rows) outputs, one (N,)
+    tensor per (quantity, row) -- the backward pass then reads gradients only for those rows."""
+
     @staticmethod
-    def forward(ctx, template, device_tables, params, x, y, z, L, M, N, i, opd):
+    def forward(ctx, template, device_tables, rows, params, x, y, z, L, M, N, i, opd):
         ctx.set_materialize_grads(False)
         lib = _lib.load()
         dtype = x.dtype
@@ -89,8 +93,12 @@ class _TraceFn(torch.autograd.Function):
                                                   _lib.TF_NO_FINAL, None, C.c_void_p(stream))
         _lib.check(rc, f"olb_trace_{sfx}")
         ctx.dtab, ctx.ins, ctx.buf, ctx.stride, ctx.sfx = dtab, ins, buf, stride, sfx
+        ctx.rows = None if rows is None else tuple(r % S for r in rows)
+        ctx.params_on_device = params.is_cuda
         ctx.needs_ray_grad = any(t.requires_grad for t in (x, y, z, L, M, N, i, opd))
-        return tuple(buf[j, :, :n] for j in range(8))
+        if ctx.rows is None:
+            return tuple(buf[j, :, :n] for j in range(8))
+        return tuple(buf[j, r, :n] for j in range(8) for r in ctx.rows)
 
     @staticmethod
     def backward(ctx, *grads):
@@ -99,9 +107,28 @@ class _TraceFn(torch.autograd.Function):
         n = ins[0].numel()
         S = buf.shape[1]
         dtype = buf.dtype
-        gbufs = [None if g is None else g.to(dtype).contiguous() for g in grads]
-        gstride = n
-        c_grec = _lib.OlbRecords(*[(g.data_ptr() if g is not None else None) for g in gbufs], gstride)
+        if ctx.rows is None:
+            gbufs = [None if g is None else g.to(dtype).contiguous() for g in grads]
+            mask = (1 << 64) - 1
+        else:
+            # dense (S, n) gradient arrays are allocated WITHOUT a fill; only the rows named in the mask
+            # are written here and read by the kernel
+            nr = len(ctx.rows)
+            gbufs, mask = [], 0
+            for j in range(8):
+                gs = grads[j * nr:(j + 1) * nr]
+                if all(g is None for g in gs):
+                    gbufs.append(None)
+                    continue
+                gb = torch.empty((S, n), dtype=dtype, device=buf.device)
+                for r, g in zip(ctx.rows, gs):
+                    if g is None:
+                        gb[r].zero_()
+                    else:
+                        gb[r].copy_(g)
+                    mask |= 1 << r
+                gbufs.append(gb)
+        c_grec = _lib.OlbRecords(*[(g.data_ptr() if g is not None else None) for g in gbufs], n)
         c_rec = _lib.OlbRecords(*[buf[j].data_ptr() for j in range(8)], stride)
         c_in = _lib.OlbRays(**{k: t.data_ptr() for k, t in zip(("x", "y", "z", "L", "M", "N", "i", "opd"), ins)})
         gin = [torch.empty_like(ins[0]) for _ in range(8)] if ctx.needs_ray_grad else None
@@ -111,23 +138,25 @@ class _TraceFn(torch.autograd.Function):
             stream = torch.cuda.current_stream(buf.device).cuda_stream
             rc = getattr(lib, f"olb_trace_bwd_{ctx.sfx}")(
                 C.byref(dtab.c), 0, S, C.byref(c_in), C.byref(c_rec), C.byref(c_grec),
-                C.byref(c_gin) if c_gin is not None else None, C.c_void_p(gpar.data_ptr()), n, C.c_void_p(stream))
+                C.byref(c_gin) if c_gin is not None else None, C.c_void_p(gpar.data_ptr()), n,
+                C.c_uint64(mask & ((1 << 64) - 1)), C.c_void_p(stream))
         _lib.check(rc, f"olb_trace_bwd_{ctx.sfx}")
         gi = gin if gin is not None else [None] * 8
-        return (None, None, gpar.cpu() if not ctx.params_on_device else gpar, *gi)
+        return (None, None, None, gpar if ctx.params_on_device else gpar.cpu(), *gi)
 
 
-def trace_differentiable(template: T.SurfaceTable, params: torch.Tensor, rays):
+def trace_differentiable(template: T.SurfaceTable, params: torch.Tensor, rays, rows=None):
     """Trace ``rays`` (an ``optiland_b200.trace.RealRays``) through ``template`` with parameter VALUES
-    taken from ``params``; returns a dict of (S, N) record tensors that are autograd outputs of
-    ``params`` (and of the ray tensors when they require grad)."""
+    taken from ``params``.  Returns a dict of record tensors that are autograd outputs of ``params``
+    (and of the ray tensors when they require grad): (S, N) arrays when ``rows`` is None, otherwise
+    only the requested rows -- (N,) tensors for a single row, lists of (N,) tensors for several --
+    which keeps the backward pass from touching gradients of rows the loss never reads."""
     holder: list = []
-    outs = _TraceFnWrapper.apply(template, holder, params, rays.x, rays.y, rays.z, rays.L, rays.M, rays.N, rays.i, rays.opd)
-    return dict(zip(_REC_KEYS, outs))
-
-
-class _TraceFnWrapper(_TraceFn):
-    @staticmethod
-    def forward(ctx, template, holder, params, *ray_tensors):
-        ctx.params_on_device = params.is_cuda
-        return _TraceFn.forward(ctx, template, holder, params, *ray_tensors)
+    rows_t = None if rows is None else tuple(int(r) for r in rows)
+    outs = _TraceFn.apply(template, holder, rows_t, params, rays.x, rays.y, rays.z, rays.L, rays.M, rays.N, rays.i, rays.opd)
+    if rows_t is None:
+        return dict(zip(_REC_KEYS, outs))
+    nr = len(rows_t)
+    if nr == 1:
+        return {k: outs[j] for j, k in enumerate(_REC_KEYS)}
+    return {k: list(outs[j * nr:(j + 1) * nr]) for j, k in enumerate(_REC_KEYS)}

@@ -64,6 +64,8 @@ struct PrepSurface {
   int32_t poly_rows;   // bivariate tables: rows (x powers) and cols (y powers)
   int32_t poly_cols;
   int32_t poly_d_off;  // pool offset of the derivative-source table (Zernike quirk)
+  int32_t gslot;       // backward: first per-thread gradient accumulator slot of this surface
+  int32_t gslots;      //           number of slots (GP_COEF + n_coef; 0 for NOOP)
   // incoming transform from GLOBAL coordinates: p_loc = Ag * p + bg
   T Ag[9], bg[3];
   // incoming transform from the PREVIOUS surface's local frame: p_loc = Ar * p + br
@@ -140,6 +142,7 @@ struct PrepResult {
   std::vector<unsigned char> blob_f64, blob_f32;
   uint32_t features = 0;
   bool bwd_supported = true;   // every surface is covered by surface_backward (olb_math.cuh)
+  int total_gslots = 0;        // per-thread gradient accumulator slots the backward kernel needs
   std::string error;
 };
 
@@ -158,6 +161,7 @@ static void build_blob(const OlbTable& tab, const std::vector<std::vector<double
     b.coef_off = a.coef_off + base; b.aper_off = a.aper_off + base; b.aper_len = a.aper_len;
     b.max_iter = a.max_iter; b.coating = a.coating; b.media_off = a.media_off + base;
     b.poly_rows = a.poly_rows; b.poly_cols = a.poly_cols; b.poly_d_off = a.poly_d_off + base;
+    b.gslot = a.gslot; b.gslots = a.gslots;
     for (int i = 0; i < 9; ++i) { b.Ag[i] = (T)a.Ag[i]; b.Ar[i] = (T)a.Ar[i]; b.R[i] = (T)a.R[i]; }
     for (int i = 0; i < 3; ++i) { b.bg[i] = (T)a.bg[i]; b.br[i] = (T)a.br[i]; b.t[i] = (T)a.t[i]; }
     b.radius = (T)a.radius; b.curv = (T)a.curv; b.conic = (T)a.conic; b.kp1 = (T)a.kp1;
@@ -360,6 +364,13 @@ static inline PrepResult prepare_table(const OlbTable& tab) {
     else if (in.coating != OLB_COAT_NONE) { res.error = "unknown coating"; return res; }
   }
   res.features = features;
+  int gslot = 0;
+  for (int s = 0; s < tab.n_surfaces; ++s) {
+    ps[s].gslot = gslot;
+    ps[s].gslots = ps[s].kind == OLB_GEOM_NOOP ? 0 : 7 + (ps[s].kind == OLB_GEOM_EVEN_ASPHERE ? ps[s].n_coef : 0);
+    gslot += ps[s].gslots;
+  }
+  res.total_gslots = gslot;
   for (int s = 0; s < tab.n_surfaces; ++s) {
     const PrepSurface<double>& o = ps[s];
     const bool kind_ok = o.kind == OLB_GEOM_NOOP || o.kind == OLB_GEOM_PLANE || o.kind == OLB_GEOM_STANDARD ||

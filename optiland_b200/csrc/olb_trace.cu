@@ -337,6 +337,8 @@ struct BwdArgs {
   int32_t blob_bytes;
   int32_t first, last, n_surf;
   int64_t n_rays, rec_stride, grec_stride;
+  uint64_t grow_mask;    // bit r set: record row r may have a non-zero gradient (others are skipped)
+  int32_t n_slots;       // per-thread gradient accumulator slots (OlbDeviceTable.bwd_slots)
   const void* in[7];     // launch state x y z L M N i
   const void* rec[8];    // forward records
   const void* grec[8];   // dLoss/d records (entries may be null)
@@ -344,10 +346,12 @@ struct BwdArgs {
   double* gparams;       // n_surf * GP_COUNT, accumulated
 };
 
-// RPB rays per thread (ray j of a tile = tile*BLOCK*RPB + j*BLOCK + thread: coalesced scalar accesses).
-// Their parameter-gradient contributions for one surface are summed in registers first, so the
-// warp tree-reduction + shared-memory atomic is paid once per RPB rays.
-template <typename T, int RPB>
+// One ray per thread per tile.  Parameter gradients: PRIVATE fp32/fp64 accumulators per thread in
+// shared memory, laid out [slot][thread] (bank-conflict free), summed over all the rays the thread
+// processes in its persistent loop; reduced across the CTA once at the end (warp tree + one fp64
+// global atomic per slot and CTA).  When a table needs more slots than shared memory holds
+// (SMEM_ACC == false) each surface's contributions are warp-reduced immediately instead.
+template <typename T, bool SMEM_ACC>
 __global__ void __launch_bounds__(BLOCK, (sizeof(T) == 8 ? 1 : 2)) trace_bwd_kernel(const __grid_constant__ BwdArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
@@ -356,96 +360,103 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(T) == 8 ? 1 : 2)) trace_bwd_ker
   const PrepHeader* H = reinterpret_cast<const PrepHeader*>(tab);
   const PrepSurface<T>* surf = reinterpret_cast<const PrepSurface<T>*>(tab + sizeof(PrepHeader));
   const T* pool = reinterpret_cast<const T*>(surf + H->n_surf);
-  double* acc = reinterpret_cast<double*>(tab + ((a.blob_bytes + 15) & ~15));
-  const int n_acc = a.n_surf * GP_COUNT;
-  for (int q = threadIdx.x; q < n_acc; q += BLOCK) acc[q] = 0.0;
+  unsigned char* after = tab + ((a.blob_bytes + 15) & ~15);
+  T* tacc = reinterpret_cast<T*>(after);                 // SMEM_ACC: [n_slots][BLOCK]
+  double* wacc = reinterpret_cast<double*>(after);       // !SMEM_ACC: [n_surf * GP_COUNT]
+  const int n_slots = a.n_slots;
+  if (SMEM_ACC) {
+    for (int q = threadIdx.x; q < n_slots * BLOCK; q += BLOCK) tacc[q] = 0;
+  } else {
+    for (int q = threadIdx.x; q < a.n_surf * GP_COUNT; q += BLOCK) wacc[q] = 0.0;
+  }
   __syncthreads();
 
   const int64_t n = a.n_rays;
-  const int64_t per_tile = (int64_t)BLOCK * RPB;
-  const int64_t n_tiles = (n + per_tile - 1) / per_tile;
+  const int64_t n_tiles = (n + BLOCK - 1) / BLOCK;
   const int lane = threadIdx.x & 31;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    int64_t kk[RPB];
-    bool valid[RPB];
-    Adjoint<T> ad[RPB];
-#pragma unroll
-    for (int j = 0; j < RPB; ++j) {
-      const int64_t k = tile * per_tile + (int64_t)j * BLOCK + threadIdx.x;
-      valid[j] = k < n;
-      kk[j] = valid[j] ? k : 0;
-      ad[j] = Adjoint<T>{0, 0, 0, 0, 0, 0, 0, 0};
-    }
+    const int64_t k = tile * BLOCK + threadIdx.x;
+    const bool valid = k < n;
+    if (SMEM_ACC && !valid) continue;    // (the warp-reduce path needs the whole warp)
+    const int64_t kk = valid ? k : 0;
+    Adjoint<T> ad{0, 0, 0, 0, 0, 0, 0, 0};
     for (int s = a.last - 1; s >= a.first; --s) {
-      const int64_t roff = (int64_t)(s - a.first) * a.rec_stride;
-      const int64_t groff = (int64_t)(s - a.first) * a.grec_stride;
-#pragma unroll
-      for (int j = 0; j < RPB; ++j) {
-        if (!valid[j]) continue;
-        const int64_t goff = groff + kk[j];
-        if (a.grec[0]) ad[j].x += __ldcs((const T*)a.grec[0] + goff);
-        if (a.grec[1]) ad[j].y += __ldcs((const T*)a.grec[1] + goff);
-        if (a.grec[2]) ad[j].z += __ldcs((const T*)a.grec[2] + goff);
-        if (a.grec[3]) ad[j].L += __ldcs((const T*)a.grec[3] + goff);
-        if (a.grec[4]) ad[j].M += __ldcs((const T*)a.grec[4] + goff);
-        if (a.grec[5]) ad[j].N += __ldcs((const T*)a.grec[5] + goff);
-        if (a.grec[6]) ad[j].i += __ldcs((const T*)a.grec[6] + goff);
-        if (a.grec[7]) ad[j].opd += __ldcs((const T*)a.grec[7] + goff);
-      }
+      const int64_t off = (int64_t)(s - a.first) * a.rec_stride + kk;
+      const int64_t goff = (int64_t)(s - a.first) * a.grec_stride + kk;
       const PrepSurface<T>& S = surf[s];
-      if (S.kind == OLB_GEOM_NOOP) continue;   // records its input unchanged: adjoint passes through
+      const bool noop = S.kind == OLB_GEOM_NOOP;
+      // issue every load of this surface first: they are independent of the arithmetic
+      T g8[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pre[7] = {0, 0, 0, 0, 0, 0, 0}, x1 = 0, y1 = 0, z1 = 0;
+      if (valid) {
+        if ((a.grow_mask >> (s - a.first)) & 1ull) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (a.grec[q]) g8[q] = __ldcs((const T*)a.grec[q] + goff);
+        }
+        if (!noop) {
+          if (s == a.first) {
+#pragma unroll
+            for (int q = 0; q < 7; ++q) pre[q] = __ldcs((const T*)a.in[q] + kk);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 7; ++q) pre[q] = __ldcs((const T*)a.rec[q] + off - a.rec_stride);
+          }
+          x1 = __ldcs((const T*)a.rec[0] + off); y1 = __ldcs((const T*)a.rec[1] + off); z1 = __ldcs((const T*)a.rec[2] + off);
+        }
+      }
+      ad.x += g8[0]; ad.y += g8[1]; ad.z += g8[2]; ad.L += g8[3]; ad.M += g8[4]; ad.N += g8[5]; ad.i += g8[6]; ad.opd += g8[7];
+      if (noop) continue;   // records its input unchanged: the adjoint passes through
       T pg[GP_COUNT];
 #pragma unroll
       for (int q = 0; q < GP_COUNT; ++q) pg[q] = 0;
+      if (valid) surface_backward<T>(S, pool, pre[0], pre[1], pre[2], pre[3], pre[4], pre[5], pre[6], x1, y1, z1, ad, pg);
+      if (SMEM_ACC) {
+        T* mine = tacc + (int64_t)S.gslot * BLOCK + threadIdx.x;
 #pragma unroll
-      for (int j = 0; j < RPB; ++j) {
-        if (!valid[j]) continue;
-        const int64_t off = roff + kk[j];
-        T pre[7];
-        if (s == a.first) {
+        for (int q = 0; q < GP_COUNT; ++q)
+          if (q < S.gslots) mine[q * BLOCK] += pg[q];
+      } else {
 #pragma unroll
-          for (int q = 0; q < 7; ++q) pre[q] = __ldcs((const T*)a.in[q] + kk[j]);
-        } else {
+        for (int q = 0; q < GP_COUNT; ++q) {
+          if (q >= S.gslots) break;
+          T v = pg[q];
 #pragma unroll
-          for (int q = 0; q < 7; ++q) pre[q] = __ldcs((const T*)a.rec[q] + off - a.rec_stride);
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          if (lane == 0 && v != 0) atomicAdd(&wacc[s * GP_COUNT + q], (double)v);
         }
-        const T x1 = __ldcs((const T*)a.rec[0] + off), y1 = __ldcs((const T*)a.rec[1] + off),
-                z1 = __ldcs((const T*)a.rec[2] + off);
-        surface_backward<T>(S, pool, pre[0], pre[1], pre[2], pre[3], pre[4], pre[5], pre[6], x1, y1, z1, ad[j], pg);
-      }
-      // warp tree-reduction of the parameter gradients, one shared-memory atomic per warp and slot
-      const int n_coef = S.kind == OLB_GEOM_EVEN_ASPHERE ? S.n_coef : 0;
-      const bool curved = S.kind != OLB_GEOM_PLANE;
-#pragma unroll
-      for (int q = 0; q < GP_COUNT; ++q) {
-        if (q >= GP_COEF + n_coef) break;
-        if (!curved && (q == GP_CURV || q == GP_CONIC)) continue;
-        T v = pg[q];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0 && v != 0) atomicAdd(&acc[s * GP_COUNT + q], (double)v);
       }
     }
-    if (a.gin[0]) {
-#pragma unroll
-      for (int j = 0; j < RPB; ++j) {
-        if (!valid[j]) continue;
-        const int64_t k = kk[j];
-        __stcs((T*)a.gin[0] + k, ad[j].x); __stcs((T*)a.gin[1] + k, ad[j].y); __stcs((T*)a.gin[2] + k, ad[j].z);
-        __stcs((T*)a.gin[3] + k, ad[j].L); __stcs((T*)a.gin[4] + k, ad[j].M); __stcs((T*)a.gin[5] + k, ad[j].N);
-        __stcs((T*)a.gin[6] + k, ad[j].i); __stcs((T*)a.gin[7] + k, ad[j].opd);
-      }
+    if (valid && a.gin[0]) {
+      __stcs((T*)a.gin[0] + k, ad.x); __stcs((T*)a.gin[1] + k, ad.y); __stcs((T*)a.gin[2] + k, ad.z);
+      __stcs((T*)a.gin[3] + k, ad.L); __stcs((T*)a.gin[4] + k, ad.M); __stcs((T*)a.gin[5] + k, ad.N);
+      __stcs((T*)a.gin[6] + k, ad.i); __stcs((T*)a.gin[7] + k, ad.opd);
     }
   }
   __syncthreads();
-  for (int q = threadIdx.x; q < n_acc; q += BLOCK)
-    if (acc[q] != 0.0) atomicAdd(&a.gparams[q], acc[q]);
+  if (SMEM_ACC) {
+    // CTA reduction: warp w sums slots w, w+8, ...: 8 values per lane, tree, one fp64 atomic
+    const int warp = threadIdx.x >> 5;
+    for (int s = 0; s < a.n_surf; ++s) {
+      const PrepSurface<T>& S = surf[s];
+      for (int q = warp; q < S.gslots; q += BLOCK / 32) {
+        const T* col = tacc + (int64_t)(S.gslot + q) * BLOCK;
+        double v = 0;
+        for (int j = lane; j < BLOCK; j += 32) v += (double)col[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0 && v != 0) atomicAdd(&a.gparams[s * GP_COUNT + q], v);
+      }
+    }
+  } else {
+    for (int q = threadIdx.x; q < a.n_surf * GP_COUNT; q += BLOCK)
+      if (wacc[q] != 0.0) atomicAdd(&a.gparams[q], wacc[q]);
+  }
 }
 
 template <typename T>
 static int trace_bwd_impl(const OlbDeviceTable* wh, int32_t first, int32_t last, const OlbRays* rays_in,
                           const OlbRecords* rec, const OlbRecords* grec, const OlbRays* gin, double* gparams,
-                          int64_t n_rays, cudaStream_t stream) {
+                          int64_t n_rays, uint64_t grow_mask, cudaStream_t stream) {
   if (!wh || wh->magic != WS_MAGIC || !wh->workspace)
     return fail(OLB_ERR_INVALID_ARG, "table handle was not initialised by olb_table_upload");
   if (!wh->bwd_supported)
@@ -475,9 +486,14 @@ static int trace_bwd_impl(const OlbDeviceTable* wh, int32_t first, int32_t last,
     for (int q = 0; q < 8; ++q) { if (!go[q]) return fail(OLB_ERR_INVALID_ARG, "grad_rays_in needs all 8 arrays"); a.gin[q] = go[q]; }
   }
   a.gparams = gparams;
-  constexpr int RPB = sizeof(T) == 4 ? 4 : 2;
-  auto kern = trace_bwd_kernel<T, RPB>;
-  const size_t smem = 16 + ((size_t)a.blob_bytes + 15 & ~size_t(15)) + (size_t)wh->n_surfaces * GP_COUNT * sizeof(double);
+  a.grow_mask = grow_mask;
+  a.n_slots = wh->bwd_slots;
+  const size_t base_smem = 16 + (((size_t)a.blob_bytes + 15) & ~size_t(15));
+  const size_t smem_acc = base_smem + (size_t)wh->bwd_slots * BLOCK * sizeof(T);
+  const size_t smem_warp = base_smem + (size_t)wh->n_surfaces * GP_COUNT * sizeof(double);
+  const bool use_smem_acc = smem_acc <= 110 * 1024;   // 2 CTAs per SM still fit
+  auto kern = use_smem_acc ? trace_bwd_kernel<T, true> : trace_bwd_kernel<T, false>;
+  const size_t smem = use_smem_acc ? smem_acc : smem_warp;
   if (smem > 48 * 1024) OLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, num_sms = 0, per_sm = 0;
   OLB_CUDA(cudaGetDevice(&dev));
@@ -485,7 +501,7 @@ static int trace_bwd_impl(const OlbDeviceTable* wh, int32_t first, int32_t last,
   OLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, smem));
   if (per_sm < 1) return fail(OLB_ERR_CUDA, "backward kernel does not fit on an SM");
   int64_t grid = (int64_t)num_sms * per_sm;
-  const int64_t n_tiles = (n_rays + (int64_t)BLOCK * RPB - 1) / ((int64_t)BLOCK * RPB);
+  const int64_t n_tiles = (n_rays + BLOCK - 1) / BLOCK;
   if (grid > n_tiles) grid = n_tiles;
   kern<<<(unsigned)grid, BLOCK, smem, stream>>>(a);
   OLB_CUDA(cudaGetLastError());
@@ -675,6 +691,7 @@ int olb_table_upload(const OlbTable* table, void* workspace, int64_t workspace_b
   h.off_f32 = 64 + h.bytes_f64;
   h.bytes_f32 = (int32_t)pr.blob_f32.size();
   h.bwd_supported = pr.bwd_supported ? 1 : 0;
+  h.bwd_slots = pr.total_gslots;
   const int64_t need = 64 + (int64_t)h.bytes_f64 + h.bytes_f32;
   if (workspace_bytes < need) return fail(OLB_ERR_INVALID_ARG, "workspace too small");
   std::vector<unsigned char> staging((size_t)need, 0);
@@ -699,15 +716,15 @@ int olb_trace_f64(const OlbDeviceTable* table, int32_t first, int32_t last, cons
 
 int olb_trace_bwd_f32(const OlbDeviceTable* table, int32_t first, int32_t last, const OlbRays* rays_in,
                       const OlbRecords* rec, const OlbRecords* grad_rec, const OlbRays* grad_rays_in,
-                      double* grad_params, int64_t n_rays, void* stream) {
+                      double* grad_params, int64_t n_rays, uint64_t grad_row_mask, void* stream) {
   return trace_bwd_impl<float>(table, first, last, rays_in, rec, grad_rec, grad_rays_in, grad_params, n_rays,
-                               (cudaStream_t)stream);
+                               grad_row_mask, (cudaStream_t)stream);
 }
 int olb_trace_bwd_f64(const OlbDeviceTable* table, int32_t first, int32_t last, const OlbRays* rays_in,
                       const OlbRecords* rec, const OlbRecords* grad_rec, const OlbRays* grad_rays_in,
-                      double* grad_params, int64_t n_rays, void* stream) {
+                      double* grad_params, int64_t n_rays, uint64_t grad_row_mask, void* stream) {
   return trace_bwd_impl<double>(table, first, last, rays_in, rec, grad_rec, grad_rays_in, grad_params, n_rays,
-                                (cudaStream_t)stream);
+                                grad_row_mask, (cudaStream_t)stream);
 }
 
 // ---- host-buffer end-to-end path ---------------------------------------------------------------

@@ -108,7 +108,7 @@ class CudaEngine:
         if not dt.c.bwd_supported:
             return None
         ins = [getattr(rays, k) for k in ("x", "y", "z", "L", "M", "N", "i", "opd")]
-        outs = AG._TraceFnWrapper.apply(table, [], params, *ins)
+        outs = AG._TraceFn.apply(table, [], None, params, *ins)
         rec = dict(zip(("x", "y", "z", "L", "M", "N", "intensity", "opd"), outs))
         for k, key in (("x", "x"), ("y", "y"), ("z", "z"), ("L", "L"), ("M", "M"), ("N", "N"), ("i", "intensity"), ("opd", "opd")):
             setattr(rays, k, rec[key][-1])

@@ -24,9 +24,9 @@ for it in range(6):
     e[0].record()
     rr = RealRays.__new__(RealRays)
     rr.__dict__.update(base.__dict__)
-    rec = AG.trace_differentiable(c.table, params, rr)
+    rec = AG.trace_differentiable(c.table, params, rr, rows=(-1,))
     e[1].record()
-    x, y = rec["x"][-1], rec["y"][-1]
+    x, y = rec["x"], rec["y"]
     loss = torch.sqrt(torch.mean((x - x.mean()) ** 2 + (y - y.mean()) ** 2))
     e[2].record()
     params.grad = None

@@ -70,8 +70,8 @@ def autograd_case(n):
         def step():
             rr = RealRays.__new__(RealRays)
             rr.__dict__.update(base.__dict__)
-            rec = AG.trace_differentiable(c.table, params, rr)
-            x, y = rec["x"][-1], rec["y"][-1]
+            rec = AG.trace_differentiable(c.table, params, rr, rows=(-1,))
+            x, y = rec["x"], rec["y"]
             loss = torch.sqrt(torch.mean((x - x.mean()) ** 2 + (y - y.mean()) ** 2))
             params.grad = None
             loss.backward()

@@ -308,3 +308,35 @@ def test_autograd_ray_input_gradients_and_unsupported_tables():
     rr = RealRays(*[t.rays[k] for k in ("x", "y", "z", "L", "M", "N", "i", "w")], dtype=torch.float64)
     with pytest.raises(_lib.OlbError, match="not supported"):
         AG.trace_differentiable(t.table, torch.zeros((t.table.num_surfaces, AG.GP_COUNT)), rr)
+
+
+def test_autograd_selected_rows_equals_dense():
+    """rows=(-1,) (gradient read only for the image-surface row) gives the same gradients as the dense form."""
+    from optiland_b200 import autograd as AG
+    from optiland_b200.trace import RealRays
+
+    c = Case("telephoto_c3_tol1e-10")
+    r = c.rays
+    out = []
+    for rows in (None, (-1,), (3, -1)):
+        rays = RealRays(r["x"], r["y"], r["z"], r["L"], r["M"], r["N"], r["i"], r["w"], dtype=torch.float64)
+        params = AG.table_to_params(c.table).requires_grad_(True)
+        rec = AG.trace_differentiable(c.table, params, rays, rows=rows)
+        if rows is None:
+            x, y, o = rec["x"][-1], rec["y"][-1], rec["opd"][3]
+        elif len(rows) == 1:
+            x, y, o = rec["x"], rec["y"], None
+        else:
+            x, y, o = rec["x"][1], rec["y"][1], rec["opd"][0]
+        loss = (x * x + y * y).mean().sqrt()
+        if o is not None:
+            loss = loss + 1e-3 * o.mean()
+        loss.backward()
+        out.append(params.grad.clone())
+    ref_img = out[1]
+    rays = RealRays(r["x"], r["y"], r["z"], r["L"], r["M"], r["N"], r["i"], r["w"], dtype=torch.float64)
+    params = AG.table_to_params(c.table).requires_grad_(True)
+    rec = AG.trace_differentiable(c.table, params, rays)
+    (rec["x"][-1] ** 2 + rec["y"][-1] ** 2).mean().sqrt().backward()
+    assert torch.allclose(params.grad, ref_img, rtol=1e-12, atol=1e-15)
+    assert torch.allclose(out[0], out[2], rtol=1e-12, atol=1e-15)
