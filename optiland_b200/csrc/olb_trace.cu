@@ -500,7 +500,8 @@ static int trace_bwd_impl(const OlbDeviceTable* wh, int32_t first, int32_t last,
   OLB_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   OLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, smem));
   if (per_sm < 1) return fail(OLB_ERR_CUDA, "backward kernel does not fit on an SM");
-  int64_t grid = (int64_t)num_sms * per_sm;
+  static const int bwd_mult = [] { const char* e = getenv("OLB_BWD_GRID_MULT"); return e ? atoi(e) : 8; }();
+  int64_t grid = (int64_t)num_sms * per_sm * (bwd_mult > 0 ? bwd_mult : 1);
   const int64_t n_tiles = (n_rays + BLOCK - 1) / BLOCK;
   if (grid > n_tiles) grid = n_tiles;
   kern<<<(unsigned)grid, BLOCK, smem, stream>>>(a);
@@ -532,9 +533,13 @@ static int launch_instance(const TraceArgs& a, cudaStream_t stream) {
   }
   const int64_t per_tile = (int64_t)BLOCK * RPT;
   const int64_t n_tiles = (a.n_rays + per_tile - 1) / per_tile;
-  int64_t grid = (int64_t)num_sms * blocks_per_sm;  // persistent: one wave of resident CTAs
-  static const int grid_mult = [] { const char* e = getenv("OLB_GRID_MULT"); return e ? atoi(e) : 1; }();
-  if (grid_mult > 1) grid *= grid_mult;
+  // Grid: OVER-SUBSCRIBED grid-stride loop, 64 x the resident CTA count (capped at one tile per CTA).
+  // A one-wave persistent grid keeps all CTAs in lock-step (everybody loads, then everybody stores row
+  // r ...) and the 104 concurrent write streams then reach only 5.3 TB/s -- the bare access pattern
+  // without any arithmetic behaves the same (scripts/storebench.cu: 5.35 TB/s at 296 CTAs, 6.05 TB/s
+  // at one tile per CTA).  Staggered CTA start times give 6.2-6.5 TB/s (profiles/tune_r1.md).
+  static const int grid_mult = [] { const char* e = getenv("OLB_GRID_MULT"); return e ? atoi(e) : 64; }();
+  int64_t grid = (int64_t)num_sms * blocks_per_sm * (grid_mult > 0 ? grid_mult : 1);
   if (grid > n_tiles) grid = n_tiles;
   if (grid < 1) return OLB_OK;
   kern<<<(unsigned)grid, BLOCK, smem, stream>>>(a);
