@@ -268,6 +268,39 @@ int olb_trace_f64(const OlbDeviceTable* table, int32_t first, int32_t last,
                   uint32_t flags, int32_t* status, void* stream);
 
 /*
+ * Launch state from pupil coordinates (the step immediately before the path):
+ * ParaxialRayAimer.aim_rays (optiland/rays/ray_aiming/paraxial.py:33-106) on top of
+ * AngleField / ObjectHeight.get_ray_origins (optiland/fields/field_types/angle.py:17-58) makes every
+ * launch ray of ONE field an affine function of its normalised pupil point (Px, Py):
+ *     origin p0 = (origin0.x + origin_scale.x * Px, origin0.y + origin_scale.y * Py, origin0.z)
+ *     target p1 = (target0.x + target_scale.x * Px, target0.y + target_scale.y * Py, target0.z)
+ *     direction = (p1 - p0) / |p1 - p0|      ((0,0,1) when |p1 - p0| < 1e-9, paraxial.py:95-103)
+ * with intensity `intensity` (no apodization: 1) and OPD 0.  The kernel evaluates this instead
+ * of reading x,y,z,L,M,N,i,opd: 8 B/ray of input instead of 32 B/ray.
+ */
+typedef struct OlbPupilLaunch {
+  const void* Px;            /* n_rays elements of the kernel's type (device; host for *_host_*) */
+  const void* Py;
+  double origin0[3];
+  double origin_scale[2];
+  double target0[3];
+  double target_scale[2];
+  double intensity;
+} OlbPupilLaunch;
+
+/*
+ * As olb_trace_*, but the launch state comes from `launch`.  `out` receives the final state
+ * (x,y,z,L,M,N,i,opd; not needed with OLB_TF_NO_FINAL) and supplies `w` when the table has several
+ * wavelengths.  Record row 0 of an object surface holds the generated launch state.
+ */
+int olb_trace_pupil_f32(const OlbDeviceTable* table, int32_t first, int32_t last,
+                        const OlbPupilLaunch* launch, const OlbRays* out, const OlbRecords* rec,
+                        int64_t n_rays, uint32_t flags, int32_t* status, void* stream);
+int olb_trace_pupil_f64(const OlbDeviceTable* table, int32_t first, int32_t last,
+                        const OlbPupilLaunch* launch, const OlbRays* out, const OlbRecords* rec,
+                        int64_t n_rays, uint32_t flags, int32_t* status, void* stream);
+
+/*
  * Host-buffer end-to-end trace: HOST SoA in, HOST final ray state out, the
  * per-surface records stay on the device (rec, optional).  Rays are cut into
  * chunks; H2D copy, kernel and D2H copy of consecutive chunks overlap on three
@@ -286,6 +319,18 @@ int olb_trace_host_f64(const OlbDeviceTable* table, int32_t first, int32_t last,
                        const OlbRecords* rec, int64_t n_rays, int64_t chunk_rays,
                        void* dev_scratch, int64_t dev_scratch_bytes, uint32_t flags,
                        int32_t* status);
+/* Same pipeline with the launch state generated on the device from HOST pupil arrays
+ * (launch->Px, launch->Py are host pointers): 8 B/ray cross PCIe instead of 28-32 B/ray. */
+int olb_trace_host_pupil_f32(const OlbDeviceTable* table, int32_t first, int32_t last,
+                             const OlbPupilLaunch* launch, const OlbRays* h_out,
+                             const OlbRecords* rec, int64_t n_rays, int64_t chunk_rays,
+                             void* dev_scratch, int64_t dev_scratch_bytes, uint32_t flags,
+                             int32_t* status);
+int olb_trace_host_pupil_f64(const OlbDeviceTable* table, int32_t first, int32_t last,
+                             const OlbPupilLaunch* launch, const OlbRays* h_out,
+                             const OlbRecords* rec, int64_t n_rays, int64_t chunk_rays,
+                             void* dev_scratch, int64_t dev_scratch_bytes, uint32_t flags,
+                             int32_t* status);
 
 /*
  * Reverse mode (the backward pass of the autograd configuration; reference:

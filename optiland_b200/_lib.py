@@ -45,6 +45,11 @@ class OlbRecords(C.Structure):
         ("row_stride", C.c_int64)]
 
 
+class OlbPupilLaunch(C.Structure):
+    _fields_ = [("Px", C.c_void_p), ("Py", C.c_void_p), ("origin0", C.c_double * 3), ("origin_scale", C.c_double * 2),
+                ("target0", C.c_double * 3), ("target_scale", C.c_double * 2), ("intensity", C.c_double)]
+
+
 class OlbDeviceTable(C.Structure):
     _fields_ = [
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("magic", C.c_uint32),
@@ -70,6 +75,16 @@ SYMBOLS = {
                                     _P(OlbRecords), _P(OlbRays), C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p]),
     "olb_trace_bwd_f64": (C.c_int, [_P(OlbDeviceTable), C.c_int32, C.c_int32, _P(OlbRays), _P(OlbRecords),
                                     _P(OlbRecords), _P(OlbRays), C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p]),
+    "olb_trace_pupil_f32": (C.c_int, [_P(OlbDeviceTable), C.c_int32, C.c_int32, _P(OlbPupilLaunch), _P(OlbRays),
+                                      _P(OlbRecords), C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "olb_trace_pupil_f64": (C.c_int, [_P(OlbDeviceTable), C.c_int32, C.c_int32, _P(OlbPupilLaunch), _P(OlbRays),
+                                      _P(OlbRecords), C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "olb_trace_host_pupil_f32": (C.c_int, [_P(OlbDeviceTable), C.c_int32, C.c_int32, _P(OlbPupilLaunch), _P(OlbRays),
+                                           _P(OlbRecords), C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
+                                           C.c_uint32, C.c_void_p]),
+    "olb_trace_host_pupil_f64": (C.c_int, [_P(OlbDeviceTable), C.c_int32, C.c_int32, _P(OlbPupilLaunch), _P(OlbRays),
+                                           _P(OlbRecords), C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
+                                           C.c_uint32, C.c_void_p]),
     "olb_host_scratch_bytes": (C.c_int64, [C.c_int32, C.c_int64]),
     "olb_trace_host_f32": (C.c_int, [_P(OlbDeviceTable), C.c_int32, C.c_int32, _P(OlbRays), _P(OlbRays),
                                      _P(OlbRecords), C.c_int64, C.c_int64, C.c_void_p, C.c_int64,

@@ -100,6 +100,24 @@ OLB_HD void accumulate_opd(Ray<float>& r, float v) {
 OLB_HD double opd_value(const Ray<double>& r) { return r.opd; }
 OLB_HD float opd_value(const Ray<float>& r) { return r.opd + r.opd_lo; }
 
+// Launch state of one ray from its pupil point (include/olb.h: OlbPupilLaunch; reference:
+// rays/ray_aiming/paraxial.py:85-105 on top of fields/field_types/angle.py:40-57).
+template <typename T>
+OLB_HD void pupil_launch(Ray<T>& r, T Px, T Py, const T* o0, const T* os, const T* t0, const T* ts, T inten) {
+  r.x = o_fma(os[0], Px, o0[0]);
+  r.y = o_fma(os[1], Py, o0[1]);
+  r.z = o0[2];
+  T dx = o_fma(ts[0], Px, t0[0]) - r.x, dy = o_fma(ts[1], Py, t0[1]) - r.y, dz = t0[2] - r.z;
+  T mag = o_sqrt(o_fma(dx, dx, o_fma(dy, dy, dz * dz)));
+  const bool zero = mag < (T)1e-9;
+  T inv = o_rcp(zero ? (T)1 : mag);
+  r.L = zero ? (T)0 : dx * inv;
+  r.M = zero ? (T)0 : dy * inv;
+  r.N = zero ? (T)1 : dz * inv;
+  r.i = inten;
+  r.opd = 0;
+}
+
 template <typename T>
 OLB_HD void apply_affine(const T* A, const T* b, bool rotated, T& x, T& y, T& z, T& L, T& M, T& N) {
   if (rotated) {

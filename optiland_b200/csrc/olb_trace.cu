@@ -38,6 +38,9 @@ template <typename T, int RPT, uint32_t FEAT> struct MinBlocks {
 };
 #endif
 static constexpr int BLOCK = OLB_BLOCK;
+#ifndef OLB_HOST_SLOTS
+#define OLB_HOST_SLOTS 3
+#endif
 
 static thread_local std::string g_last_error;
 static std::atomic<int64_t> g_launches{0};
@@ -67,6 +70,9 @@ struct TraceArgs {
   void* L0; void* M0; void* N0; void* p;
   void* rx; void* ry; void* rz; void* rL; void* rM; void* rN; void* ri; void* ropd;
   int32_t* status;
+  // launch state from pupil coordinates (OlbPupilLaunch) when px != nullptr
+  const void* px; const void* py;
+  double lo0[3], los[2], lt0[3], lts[2], linten;
 };
 
 // ---- vector access helpers -------------------------------------------------------------
@@ -176,6 +182,16 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<T, RPT, FEAT>::v)) trace_ker
     Ray<T> r[RPT];
     {
       T v[RPT];
+      if (a.px != nullptr) {
+        // launch state generated from the pupil point: 2 loads instead of 8
+        T pv[RPT];
+        load_rays<T, RPT>((const T*)a.px, base, valid, pv);
+        load_rays<T, RPT>((const T*)a.py, base, valid, v);
+        const T o0[3] = {(T)a.lo0[0], (T)a.lo0[1], (T)a.lo0[2]}, os[2] = {(T)a.los[0], (T)a.los[1]};
+        const T t0[3] = {(T)a.lt0[0], (T)a.lt0[1], (T)a.lt0[2]}, ts[2] = {(T)a.lts[0], (T)a.lts[1]};
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) pupil_launch<T>(r[k], pv[k], v[k], o0, os, t0, ts, (T)a.linten);
+      } else {
       load_rays<T, RPT>((const T*)a.x, base, valid, v);
 #pragma unroll
       for (int k = 0; k < RPT; ++k) r[k].x = v[k];
@@ -199,7 +215,10 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<T, RPT, FEAT>::v)) trace_ker
       for (int k = 0; k < RPT; ++k) r[k].i = v[k];
       load_rays<T, RPT>((const T*)a.opd, base, valid, v);
 #pragma unroll
-      for (int k = 0; k < RPT; ++k) { r[k].opd = v[k]; r[k].opd_lo = 0; r[k].widx = 0; r[k].L0 = r[k].M0 = r[k].N0 = 0; }
+      for (int k = 0; k < RPT; ++k) r[k].opd = v[k];
+      }
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) { r[k].opd_lo = 0; r[k].widx = 0; r[k].L0 = r[k].M0 = r[k].N0 = 0; }
       if (n_wl > 1) {
         load_rays<T, RPT>((const T*)a.w, base, valid, v);
 #pragma unroll
@@ -232,7 +251,11 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<T, RPT, FEAT>::v)) trace_ker
     // the first loads of the next iteration then see L2 latency instead of HBM latency.
     {
       const int64_t nb = base + (int64_t)gridDim.x * per_tile;
-      if (nb + RPT <= n && (threadIdx.x * RPT * (int)sizeof(T)) % 32 == 0) {
+      if (a.px != nullptr) {
+        if (nb + RPT <= n && (threadIdx.x * RPT * (int)sizeof(T)) % 32 == 0) {
+          prefetch_l2((const T*)a.px + nb); prefetch_l2((const T*)a.py + nb);
+        }
+      } else if (nb + RPT <= n && (threadIdx.x * RPT * (int)sizeof(T)) % 32 == 0) {
         prefetch_l2((const T*)a.x + nb); prefetch_l2((const T*)a.y + nb); prefetch_l2((const T*)a.z + nb);
         prefetch_l2((const T*)a.L + nb); prefetch_l2((const T*)a.M + nb); prefetch_l2((const T*)a.N + nb);
         prefetch_l2((const T*)a.i + nb); prefetch_l2((const T*)a.opd + nb);
@@ -574,7 +597,7 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 template <typename T>
 static int trace_impl(const OlbDeviceTable* wh, int32_t first, int32_t last, const OlbRays* rays,
                       const OlbRecords* rec, int64_t n_rays, uint32_t flags, int32_t* status,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, const OlbPupilLaunch* launch = nullptr) {
   if (!wh || wh->magic != WS_MAGIC || !wh->workspace)
     return fail(OLB_ERR_INVALID_ARG, "table handle was not initialised by olb_table_upload");
   const unsigned char* workspace_dev = (const unsigned char*)wh->workspace;
@@ -583,9 +606,15 @@ static int trace_impl(const OlbDeviceTable* wh, int32_t first, int32_t last, con
   if (first < 0 || last > wh->n_surfaces || first > last) return fail(OLB_ERR_INVALID_ARG, "bad surface range");
   if (n_rays == 0 || first == last) return OLB_OK;
   void* req[] = {rays->x, rays->y, rays->z, rays->L, rays->M, rays->N, rays->i, rays->opd};
+  const bool need_state = launch == nullptr || !(flags & OLB_TF_NO_FINAL);
   for (void* p : req) {
-    if (!p) return fail(OLB_ERR_INVALID_ARG, "a required ray array is NULL");
-    if (!aligned16(p)) return fail(OLB_ERR_ALIGNMENT, "ray array not 16-byte aligned");
+    if (!p && need_state) return fail(OLB_ERR_INVALID_ARG, "a required ray array is NULL");
+    if (p && !aligned16(p)) return fail(OLB_ERR_ALIGNMENT, "ray array not 16-byte aligned");
+  }
+  if (launch) {
+    if (!launch->Px || !launch->Py) return fail(OLB_ERR_INVALID_ARG, "launch.Px / launch.Py is NULL");
+    if (!aligned16(launch->Px) || !aligned16(launch->Py)) return fail(OLB_ERR_ALIGNMENT, "launch.Px / Py not 16-byte aligned");
+    if (flags & OLB_TF_POLARIZED) return fail(OLB_ERR_UNSUPPORTED, "pupil launch with polarized rays is not built");
   }
   if (wh->n_wl > 1) {
     if (!rays->w) return fail(OLB_ERR_INVALID_ARG, "rays.w is NULL but the table has several wavelengths");
@@ -599,6 +628,12 @@ static int trace_impl(const OlbDeviceTable* wh, int32_t first, int32_t last, con
   a.i = rays->i; a.w = rays->w; a.opd = rays->opd;
   a.L0 = rays->L0; a.M0 = rays->M0; a.N0 = rays->N0; a.p = rays->p;
   a.status = status;
+  if (launch) {
+    a.px = launch->Px; a.py = launch->Py;
+    for (int q = 0; q < 3; ++q) { a.lo0[q] = launch->origin0[q]; a.lt0[q] = launch->target0[q]; }
+    for (int q = 0; q < 2; ++q) { a.los[q] = launch->origin_scale[q]; a.lts[q] = launch->target_scale[q]; }
+    a.linten = launch->intensity;
+  }
   uint32_t features = wh->features;
   if (flags & OLB_TF_POLARIZED) features |= FEAT_POL;
   if (rays->L0 || rays->M0 || rays->N0) {
@@ -733,12 +768,27 @@ int olb_trace_bwd_f64(const OlbDeviceTable* table, int32_t first, int32_t last, 
                                 grad_row_mask, (cudaStream_t)stream);
 }
 
+int olb_trace_pupil_f32(const OlbDeviceTable* table, int32_t first, int32_t last, const OlbPupilLaunch* launch,
+                        const OlbRays* out, const OlbRecords* rec, int64_t n_rays, uint32_t flags, int32_t* status,
+                        void* stream) {
+  if (!launch) return fail(OLB_ERR_INVALID_ARG, "launch is NULL");
+  OlbRays none{};
+  return trace_impl<float>(table, first, last, out ? out : &none, rec, n_rays, flags, status, (cudaStream_t)stream, launch);
+}
+int olb_trace_pupil_f64(const OlbDeviceTable* table, int32_t first, int32_t last, const OlbPupilLaunch* launch,
+                        const OlbRays* out, const OlbRecords* rec, int64_t n_rays, uint32_t flags, int32_t* status,
+                        void* stream) {
+  if (!launch) return fail(OLB_ERR_INVALID_ARG, "launch is NULL");
+  OlbRays none{};
+  return trace_impl<double>(table, first, last, out ? out : &none, rec, n_rays, flags, status, (cudaStream_t)stream, launch);
+}
+
 // ---- host-buffer end-to-end path ---------------------------------------------------------------
-// scratch layout: 2 slots x 9 arrays (x,y,z,L,M,N,i,w,opd) x chunk elements
+// scratch layout: OLB_HOST_SLOTS slots x 9 arrays (x,y,z,L,M,N,i,w,opd) x chunk elements
 int64_t olb_host_scratch_bytes(int32_t elem_size, int64_t chunk_rays) {
   if ((elem_size != 4 && elem_size != 8) || chunk_rays < 1) return fail(OLB_ERR_INVALID_ARG, "bad scratch query");
   const int64_t chunk_al = (chunk_rays + 63) & ~int64_t(63);
-  return 2 * 9 * chunk_al * elem_size;
+  return (int64_t)OLB_HOST_SLOTS * 9 * chunk_al * elem_size;
 }
 
 }  // extern "C"
@@ -746,9 +796,17 @@ int64_t olb_host_scratch_bytes(int32_t elem_size, int64_t chunk_rays) {
 template <typename T>
 static int trace_host_impl(const OlbDeviceTable* table, int32_t first, int32_t last, const OlbRays* h_in,
                            const OlbRays* h_out, const OlbRecords* rec, int64_t n_rays, int64_t chunk,
-                           void* scratch, int64_t scratch_bytes, uint32_t flags, int32_t* status) {
+                           void* scratch, int64_t scratch_bytes, uint32_t flags, int32_t* status,
+                           const OlbPupilLaunch* launch = nullptr) {
   if (!table || table->magic != WS_MAGIC) return fail(OLB_ERR_INVALID_ARG, "table handle was not initialised");
   const OlbDeviceTable& wh = *table;
+  OlbRays pupil_in{};
+  if (launch) {   // slots 0/1 carry Px/Py instead of x/y; the rest of the launch state is generated on the device
+    if (!launch->Px || !launch->Py) return fail(OLB_ERR_INVALID_ARG, "launch.Px / launch.Py is NULL");
+    pupil_in.x = const_cast<void*>(launch->Px); pupil_in.y = const_cast<void*>(launch->Py);
+    pupil_in.w = h_out ? h_out->w : nullptr;
+    h_in = &pupil_in;
+  }
   if (!h_in || !h_out || !scratch) return fail(OLB_ERR_INVALID_ARG, "NULL argument");
   if (chunk < 1) return fail(OLB_ERR_INVALID_ARG, "chunk_rays < 1");
   if (scratch_bytes < olb_host_scratch_bytes((int)sizeof(T), chunk)) return fail(OLB_ERR_INVALID_ARG, "scratch too small");
@@ -757,27 +815,29 @@ static int trace_host_impl(const OlbDeviceTable* table, int32_t first, int32_t l
   const void* in[9] = {h_in->x, h_in->y, h_in->z, h_in->L, h_in->M, h_in->N, h_in->i, h_in->w, nullptr};
   void* out[9] = {h_out->x, h_out->y, h_out->z, h_out->L, h_out->M, h_out->N, h_out->i, nullptr, h_out->opd};
   for (int k = 0; k < 7; ++k)
-    if (!in[k] || !out[k]) return fail(OLB_ERR_INVALID_ARG, "a required host ray array is NULL");
+    if ((!in[k] && !(launch && k >= 2)) || !out[k]) return fail(OLB_ERR_INVALID_ARG, "a required host ray array is NULL");
   if (!out[8]) return fail(OLB_ERR_INVALID_ARG, "h_out.opd is NULL");
   if (need_w && !in[7]) return fail(OLB_ERR_INVALID_ARG, "h_in.w is NULL but the table has several wavelengths");
 
   const int64_t chunk_al = (chunk + 63) & ~int64_t(63);
-  T* slot[2][9];
-  for (int s = 0; s < 2; ++s)
+  constexpr int NS = OLB_HOST_SLOTS;   // chunks in flight: H2D of one overlaps kernel / D2H of the others
+  T* slot[NS][9];
+  for (int s = 0; s < NS; ++s)
     for (int k = 0; k < 9; ++k) slot[s][k] = (T*)scratch + ((int64_t)s * 9 + k) * chunk_al;
 
-  cudaStream_t st[2];
-  for (int s = 0; s < 2; ++s) OLB_CUDA(cudaStreamCreateWithFlags(&st[s], cudaStreamNonBlocking));
+  cudaStream_t st[NS];
+  for (int s = 0; s < NS; ++s) OLB_CUDA(cudaStreamCreateWithFlags(&st[s], cudaStreamNonBlocking));
   int result = OLB_OK;
   int64_t done = 0;
   int ci = 0;
   while (done < n_rays) {
     const int64_t m = (n_rays - done) < chunk ? (n_rays - done) : chunk;
-    const int s = ci & 1;
+    const int s = ci % NS;
     cudaStream_t q = st[s];
     // slot reuse is ordered by the stream itself (chunk ci and ci+2 share stream + slot)
     for (int k = 0; k < 8; ++k) {
       if (k == 7 && !need_w) continue;
+      if (launch && k >= 2 && k != 7) continue;
       cudaError_t e = cudaMemcpyAsync(slot[s][k], (const T*)in[k] + done, (size_t)m * sizeof(T), cudaMemcpyHostToDevice, q);
       if (e != cudaSuccess) { result = fail(OLB_ERR_CUDA, cudaGetErrorString(e)); break; }
     }
@@ -796,7 +856,15 @@ static int trace_host_impl(const OlbDeviceTable* table, int32_t first, int32_t l
       rr.intensity = (T*)rec->intensity + done; rr.opd = (T*)rec->opd + done;
       rp = &rr;
     }
-    result = trace_impl<T>(&wh, first, last, &d, rp, m, flags & ~uint32_t(OLB_TF_NO_FINAL), status, q);
+    OlbPupilLaunch dl{};
+    if (launch) {
+      // the pupil slots double as the x / y outputs: read before written by the same thread
+      dl = *launch;
+      dl.Px = slot[s][0];
+      dl.Py = slot[s][1];
+    }
+    result = trace_impl<T>(&wh, first, last, &d, rp, m, flags & ~uint32_t(OLB_TF_NO_FINAL), status, q,
+                           launch ? &dl : nullptr);
     if (result) break;
     for (int k = 0; k < 9; ++k) {
       if (k == 7) continue;
@@ -807,7 +875,7 @@ static int trace_host_impl(const OlbDeviceTable* table, int32_t first, int32_t l
     done += m;
     ++ci;
   }
-  for (int s = 0; s < 2; ++s) {
+  for (int s = 0; s < NS; ++s) {
     cudaError_t e = cudaStreamSynchronize(st[s]);
     if (e != cudaSuccess && !result) result = fail(OLB_ERR_CUDA, cudaGetErrorString(e));
     cudaStreamDestroy(st[s]);
@@ -828,6 +896,20 @@ int olb_trace_host_f64(const OlbDeviceTable* table, int32_t first, int32_t last,
                        void* dev_scratch, int64_t dev_scratch_bytes, uint32_t flags, int32_t* status) {
   return trace_host_impl<double>(table, first, last, h_in, h_out, rec, n_rays, chunk_rays, dev_scratch,
                                  dev_scratch_bytes, flags, status);
+}
+int olb_trace_host_pupil_f32(const OlbDeviceTable* table, int32_t first, int32_t last, const OlbPupilLaunch* launch,
+                             const OlbRays* h_out, const OlbRecords* rec, int64_t n_rays, int64_t chunk_rays,
+                             void* dev_scratch, int64_t dev_scratch_bytes, uint32_t flags, int32_t* status) {
+  if (!launch) return fail(OLB_ERR_INVALID_ARG, "launch is NULL");
+  return trace_host_impl<float>(table, first, last, nullptr, h_out, rec, n_rays, chunk_rays, dev_scratch,
+                                dev_scratch_bytes, flags, status, launch);
+}
+int olb_trace_host_pupil_f64(const OlbDeviceTable* table, int32_t first, int32_t last, const OlbPupilLaunch* launch,
+                             const OlbRays* h_out, const OlbRecords* rec, int64_t n_rays, int64_t chunk_rays,
+                             void* dev_scratch, int64_t dev_scratch_bytes, uint32_t flags, int32_t* status) {
+  if (!launch) return fail(OLB_ERR_INVALID_ARG, "launch is NULL");
+  return trace_host_impl<double>(table, first, last, nullptr, h_out, rec, n_rays, chunk_rays, dev_scratch,
+                                 dev_scratch_bytes, flags, status, launch);
 }
 
 }  // extern "C"

@@ -35,3 +35,16 @@ def launch_infinite_angle(Px, Py, sc: dict):
     M = (y1 - y0) / mag
     N = (z1 - z0) / mag
     return x0, y0, z0, L, M, N
+
+
+def pupil_affine_infinite_angle(sc: dict) -> dict:
+    """The same launch state as ``launch_infinite_angle`` in the affine form the kernel evaluates
+    (include/olb.h ``OlbPupilLaunch``): origin = origin0 + origin_scale * (Px, Py), target likewise,
+    direction = normalised (target - origin)."""
+    EPL, EPD, offset = sc["EPL"], sc["EPD"], sc["offset"]
+    xo = -math.tan(math.radians(sc["max_field"] * sc["Hx"])) * (offset + EPL)
+    yo = -math.tan(math.radians(sc["max_field"] * sc["Hy"])) * (offset + EPL)
+    zo = sc["z1"] - offset
+    sx, sy = EPD / 2 * sc["vx"], EPD / 2 * sc["vy"]
+    return {"origin0": (xo, yo, zo), "origin_scale": (sx, sy), "target0": (0.0, 0.0, EPL),
+            "target_scale": (EPD * sc["vx"] / 2, EPD * sc["vy"] / 2), "intensity": 1.0}

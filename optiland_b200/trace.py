@@ -202,6 +202,48 @@ def trace_device(dtab: DeviceTable, rays: RealRays, first: int, last: int, recor
     return recs
 
 
+def _c_launch(affine: dict, Px, Py):
+    la = _lib.OlbPupilLaunch()
+    la.Px, la.Py = Px.data_ptr(), Py.data_ptr()
+    la.origin0 = (C.c_double * 3)(*affine["origin0"])
+    la.origin_scale = (C.c_double * 2)(*affine["origin_scale"])
+    la.target0 = (C.c_double * 3)(*affine["target0"])
+    la.target_scale = (C.c_double * 2)(*affine["target_scale"])
+    la.intensity = float(affine.get("intensity", 1.0))
+    return la
+
+
+def trace_pupil_device(dtab: DeviceTable, Px: torch.Tensor, Py: torch.Tensor, affine: dict, first: int, last: int,
+                       wavelength: torch.Tensor | None = None):
+    """olb_trace_pupil_*: launch state generated in-kernel from pupil coordinates (one field), full
+    records.  Returns (rays, records): ``rays`` is a ``RealRays`` view of the last record row."""
+    lib = dtab.lib
+    n = Px.numel()
+    dtype = Px.dtype
+    sfx = _DTYPES[dtype]
+    rows = last - first
+    vec = 4 if dtype == torch.float32 else 2
+    stride = (n + 63) // 64 * 64 if n % vec else n
+    buf = torch.empty((8, rows, stride), dtype=dtype, device=Px.device)
+    recs = {k: buf[j, :, :n] for j, k in enumerate(_REC_KEYS)}
+    c_rec = _lib.OlbRecords(*[buf[j].data_ptr() for j in range(8)], stride)
+    la = _c_launch(affine, Px.contiguous(), Py.contiguous())
+    out = _lib.OlbRays(w=wavelength.data_ptr() if (wavelength is not None and dtab.table.n_wl > 1) else None)
+    with torch.cuda.device(Px.device):
+        stream = torch.cuda.current_stream(Px.device).cuda_stream
+        rc = getattr(lib, f"olb_trace_pupil_{sfx}")(C.byref(dtab.c), first, last, C.byref(la), C.byref(out),
+                                                    C.byref(c_rec), n, _lib.TF_NO_FINAL, None, C.c_void_p(stream))
+    _lib.check(rc, f"olb_trace_pupil_{sfx}")
+    rays = RealRays.__new__(RealRays)
+    rays.x, rays.y, rays.z = recs["x"][-1], recs["y"][-1], recs["z"][-1]
+    rays.L, rays.M, rays.N = recs["L"][-1], recs["M"][-1], recs["N"][-1]
+    rays.i, rays.opd = recs["intensity"][-1], recs["opd"][-1]
+    rays.w = wavelength
+    rays.L0 = rays.M0 = rays.N0 = None
+    rays.is_normalized = True
+    return rays, recs
+
+
 class SurfaceGroup:
     """The traced part of the reference's ``SurfaceGroup``: ``trace`` + stacked records."""
 
@@ -223,6 +265,13 @@ class SurfaceGroup:
         self._rec = trace_device(self.device_table, rays, skip, last, record=record)
         return rays
 
+    def trace_pupil(self, Px, Py, affine: dict, wavelength=None):
+        """``Optic.trace`` for one field without materialising the launch arrays: pupil coordinates in,
+        the launch state (paraxial aiming, optiland/rays/ray_aiming/paraxial.py:33-106) is evaluated
+        in-kernel.  ``affine``: see ``optiland_b200.launch.pupil_affine_infinite_angle``."""
+        rays, self._rec = trace_pupil_device(self.device_table, Px, Py, affine, 0, self.num_surfaces, wavelength)
+        return rays
+
     def _get(self, key):
         if self._rec is None:
             raise RuntimeError("no records: call trace(..., record=True) first")
@@ -239,7 +288,8 @@ class SurfaceGroup:
 
 
 def trace_host(dtab: DeviceTable, h_in: dict, h_out: dict, n: int, dtype=torch.float32, chunk: int = 1 << 20,
-               scratch: torch.Tensor | None = None, rec=None, first: int = 0, last: int | None = None):
+               scratch: torch.Tensor | None = None, rec=None, first: int = 0, last: int | None = None,
+               affine: dict | None = None):
     """olb_trace_host_*: HOST SoA in (pinned tensors x,y,z,L,M,N,i[,w]) -> HOST final state out
     (x,y,z,L,M,N,i,opd); chunks are pipelined H2D / kernel / D2H on two streams."""
     lib = dtab.lib
@@ -249,9 +299,22 @@ def trace_host(dtab: DeviceTable, h_in: dict, h_out: dict, n: int, dtype=torch.f
     need = int(lib.olb_host_scratch_bytes(es, chunk))
     if scratch is None or scratch.numel() < need:
         scratch = torch.empty(need, dtype=torch.uint8, device=dtab.device)
+    c_out = _lib.OlbRays(**{k: h_out[k].data_ptr() for k in ("x", "y", "z", "L", "M", "N", "i", "opd")})
+    if affine is not None:
+        # HOST pupil arrays in (8 B/ray over PCIe), launch state generated on the device
+        la = _c_launch(affine, h_in["Px"], h_in["Py"])
+        c_rec = None
+        if rec is not None:
+            c_rec = _lib.OlbRecords(*[rec[j].data_ptr() for j in range(8)], rec.shape[-1])
+        with torch.cuda.device(dtab.device):
+            rc = getattr(lib, f"olb_trace_host_pupil_{sfx}")(
+                C.byref(dtab.c), first, last, C.byref(la), C.byref(c_out),
+                C.byref(c_rec) if c_rec is not None else None, n, chunk, C.c_void_p(scratch.data_ptr()),
+                scratch.numel(), 0, None)
+        _lib.check(rc, f"olb_trace_host_pupil_{sfx}")
+        return scratch
     c_in = _lib.OlbRays(**{k: h_in[k].data_ptr() for k in ("x", "y", "z", "L", "M", "N", "i")},
                         w=h_in["w"].data_ptr() if "w" in h_in and dtab.table.n_wl > 1 else None)
-    c_out = _lib.OlbRays(**{k: h_out[k].data_ptr() for k in ("x", "y", "z", "L", "M", "N", "i", "opd")})
     c_rec = None
     if rec is not None:
         c_rec = _lib.OlbRecords(*[rec[j].data_ptr() for j in range(8)], rec.shape[-1])

@@ -70,3 +70,25 @@ def test_pack_roundtrip():
     np.testing.assert_array_equal(b.coat_n2, s.coat_n2)
     with pytest.raises(ValueError):
         T.validate_aperture_program(np.array([T.AP_UNION], dtype=float))
+
+
+def test_pupil_affine_launch_equals_reference_launch_arrays():
+    """The affine (Px, Py) -> launch state form handed to the kernel reproduces the launch arrays the
+    reference's RayGenerator produced (golden inputs)."""
+    from optiland_b200.launch import launch_infinite_angle, pupil_affine_infinite_angle
+    from tests._util import Case
+
+    for name in ("dgauss_c2", "hubble_c4"):
+        c = Case(name)
+        sc = {k[9:]: float(c.z[k]) for k in c.z.files if k.startswith("x_launch_")}
+        Px, Py = c.extra("Px"), c.extra("Py")
+        a = pupil_affine_infinite_angle(sc)
+        x0 = a["origin0"][0] + a["origin_scale"][0] * Px
+        y0 = a["origin0"][1] + a["origin_scale"][1] * Py
+        d = np.stack([a["target0"][0] + a["target_scale"][0] * Px - x0, a["target0"][1] + a["target_scale"][1] * Py - y0,
+                      np.full_like(Px, a["target0"][2] - a["origin0"][2])])
+        d /= np.linalg.norm(d, axis=0)
+        ref = launch_infinite_angle(Px, Py, sc)
+        for got, want, key in zip((x0, y0, d[0], d[1], d[2]), (ref[0], ref[1], ref[3], ref[4], ref[5]), "xyLMN"):
+            np.testing.assert_allclose(got, want, rtol=0, atol=1e-12 * c.scale)
+            np.testing.assert_allclose(got, c.rays[key], rtol=0, atol=1e-12 * c.scale)

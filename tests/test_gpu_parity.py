@@ -389,3 +389,32 @@ def test_full_size_polarized_zernike_4M_rays():
     ref_opd = torch.from_numpy(c.rec["opd"][-1]).cuda()[torch.from_numpy(idx).cuda()]
     # "OPD within 1e-5 lambda": lambda = 0.48..0.65 um -> 1e-5 lambda ~ 5e-9 mm
     assert float((sg.opd[-1] - ref_opd).abs().max()) <= 5e-9
+
+
+@pytest.mark.parametrize("name", ["dgauss_c2", "hubble_c4"])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_pupil_launch_mode_matches_reference(name, dtype):
+    """f-1: launch state generated in-kernel from pupil coordinates (paraxial aiming, angle field,
+    infinite object) == the reference's RayGenerator + SurfaceGroup.trace records, incl. row 0."""
+    from optiland_b200.launch import pupil_affine_infinite_angle
+    from optiland_b200.trace import DeviceTable, SurfaceGroup, trace_host
+
+    c = Case(name)
+    sc = {k[9:]: float(c.z[k]) for k in c.z.files if k.startswith("x_launch_")}
+    aff = pupil_affine_infinite_angle(sc)
+    Px = torch.from_numpy(c.extra("Px")).to("cuda", dtype)
+    Py = torch.from_numpy(c.extra("Py")).to("cuda", dtype)
+    sg = SurfaceGroup(c.table)
+    rays = sg.trace_pupil(Px, Py, aff)
+    f64 = dtype == torch.float64
+    tol = 1e-11 * c.scale if f64 else 2e-6 * c.scale
+    for k in REC:
+        assert max_abs_err(_np(getattr(sg, k)), c.rec[k]) <= (tol if k not in ("L", "M", "N") or f64 else 5e-6), k
+    assert max_abs_err(_np(rays.opd), c.out["opd"]) <= tol
+    # host-buffer variant: pinned pupil arrays in, final state out
+    n = c.n
+    h_in = {"Px": Px.cpu().pin_memory(), "Py": Py.cpu().pin_memory()}
+    h_out = {k: torch.empty(n, dtype=dtype).pin_memory() for k in ("x", "y", "z", "L", "M", "N", "i", "opd")}
+    trace_host(DeviceTable(c.table), h_in, h_out, n, dtype, chunk=257, affine=aff)
+    for k in ("x", "y", "z", "L", "M", "N", "i", "opd"):
+        assert np.array_equal(h_out[k].numpy(), getattr(rays, k).cpu().numpy(), equal_nan=True), k
