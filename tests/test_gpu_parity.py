@@ -418,3 +418,39 @@ def test_pupil_launch_mode_matches_reference(name, dtype):
     trace_host(DeviceTable(c.table), h_in, h_out, n, dtype, chunk=257, affine=aff)
     for k in ("x", "y", "z", "L", "M", "N", "i", "opd"):
         assert np.array_equal(h_out[k].numpy(), getattr(rays, k).cpu().numpy(), equal_nan=True), k
+
+
+def test_c_abi_error_codes_on_device_calls():
+    """Bad arguments are reported through return codes + olb_last_error, never by crashing."""
+    import ctypes as C
+
+    from optiland_b200 import _lib
+    from optiland_b200.trace import DeviceTable
+
+    c = Case("dgauss_c2")
+    dt = DeviceTable(c.table)
+    lib = dt.lib
+    n = 1024
+    buf = torch.zeros((9, n + 4), dtype=torch.float32, device="cuda")
+    ptrs = [buf[j].data_ptr() for j in range(9)]
+    good = dict(zip(("x", "y", "z", "L", "M", "N", "i", "opd"), ptrs))
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def call(rays, first=0, last=13, rec=None, flags=0, nn=n):
+        return lib.olb_trace_f32(C.byref(dt.c), first, last, C.byref(rays), C.byref(rec) if rec else None, nn, flags,
+                                 None, stream)
+
+    assert call(_lib.OlbRays(**good)) == 0
+    bad = dict(good); bad["z"] = None
+    assert call(_lib.OlbRays(**bad)) == -1 and "NULL" in _lib.last_error()
+    mis = dict(good); mis["y"] = ptrs[1] + 4
+    assert call(_lib.OlbRays(**mis)) == -4 and "aligned" in _lib.last_error()
+    assert call(_lib.OlbRays(**good), first=5, last=3) == -1
+    assert call(_lib.OlbRays(**good), last=99) == -1
+    assert call(_lib.OlbRays(**good), flags=_lib.TF_NO_FINAL) == -1 and "NO_FINAL" in _lib.last_error()
+    rec = _lib.OlbRecords(*([ptrs[0]] * 8), n - 1)
+    assert call(_lib.OlbRays(**good), rec=rec) == -1 and "row_stride" in _lib.last_error()
+    assert call(_lib.OlbRays(**good), nn=0) == 0          # empty batch: nothing to do
+    fake = _lib.OlbDeviceTable()
+    assert lib.olb_trace_f32(C.byref(fake), 0, 1, C.byref(_lib.OlbRays(**good)), None, n, 0, None, stream) == -1
+    torch.cuda.synchronize()
