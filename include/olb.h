@@ -63,6 +63,12 @@ extern "C" {
                                       optiland/geometries/odd_asphere.py         */
 #define OLB_GEOM_POLYNOMIAL    6   /* conic + sum C_ij x^i y^j
                                       optiland/geometries/polynomial.py:105-155  */
+#define OLB_GEOM_CHEBYSHEV     7   /* conic + sum C_ij T_i(x/norm_x) T_j(y/norm_y)
+                                      optiland/geometries/chebyshev.py:126-191   */
+#define OLB_GEOM_BICONIC       8   /* zx(x; Rx, kx) + zy(y; Ry, ky)
+                                      optiland/geometries/biconic.py:72-160      */
+#define OLB_GEOM_TOROIDAL      9   /* Y-Z conic + even polynomial curve rotated about an
+                                      axis at distance R_rot: optiland/geometries/toroidal.py:87-232 */
 
 /* ---- OlbSurface.flags --------------------------------------------------- */
 #define OLB_SF_REFLECT     (1u << 0)  /* is_reflective: rays.reflect instead of refract
@@ -154,6 +160,11 @@ typedef struct OlbSurface {
  *   EVEN_ASPHERE : n_coef doubles C_0.. ; term i is C_i * r^(2(i+1))
  *   ODD_ASPHERE  : n_coef doubles C_0.. ; term i is C_i * r^(i+1)
  *   POLYNOMIAL   : n_coef = rows*cols doubles, C[i*cols+j] * x^i y^j
+ *   CHEBYSHEV    : {norm_x, norm_y} then n_coef = rows*cols doubles C[i*cols+j] (aux0 = cols)
+ *   BICONIC      : {radius_y, conic_y}; OlbSurface.radius / conic hold radius_x / conic_x
+ *   TOROIDAL     : {radius_rot, conic_yz} then n_coef doubles alpha_i (term alpha_i y^(2(i+1)));
+ *                  OlbSurface.radius holds the Y-Z base radius, OlbSurface.conic must be 0 (the
+ *                  reference starts Newton from that SPHERE, toroidal.py:71-73)
  *   ZERNIKE      : n_coef terms, each 4 doubles {n, m, c*N_nm (sag), c (derivative)}
  *                  -- the reference's derivative path omits the normalisation
  *                  constant N_nm (optiland/zernike/base.py:104-136 vs :42-68);
@@ -211,6 +222,7 @@ typedef struct OlbRecords {
 } OlbRecords;
 
 /* Status word written by the kernels (device int32, caller-owned, optional). */
+#define OLB_ST_CHEBYSHEV_RANGE (1 << 1) /* same for Chebyshev surfaces (chebyshev.py:230-244)            */
 #define OLB_ST_ZERNIKE_RANGE (1 << 0)  /* some |x/norm_radius| or |y/norm_radius| > 1:
                                           the reference raises ValueError
                                           (optiland/geometries/zernike.py:254-266) */

@@ -212,8 +212,55 @@ OLB_HD T poly2_value(const T* C, int rows, int cols, bool tri, T x, T y) {
 //   odd asphere   odd_asphere.py:86-101    conic + sum C_i r^(i+1)
 //   polynomial    polynomial.py:105-121    conic + sum C_ij x^i y^j
 //   Zernike       zernike.py:153-180       conic + sum c_i N_i Z_i(rho, phi), monomial form
+// Biconic profile helpers (biconic.py:72-160): z_u = c u^2 / (1 + sqrt(clamp(1 - (1+k) c^2 u^2))), the
+// reference clamps the radicand to 0 (sag) / 1e-14 (slope) below 1e-14.
+template <typename T>
+OLB_HD T biconic_profile(T u, T c, T kp1) {
+  if (c == 0) return 0;
+  T v = o_fma(-kp1 * c * c, u * u, (T)1);
+  T rt = v < (T)1e-14 ? (T)0 : v;
+  return o_div(c * u * u, (T)1 + o_sqrt(rt));
+}
+template <typename T>
+OLB_HD T biconic_slope(T u, T c, T kp1) {
+  if (c == 0) return 0;
+  T v = o_fma(-kp1 * c * c, u * u, (T)1);
+  T rt = v < (T)1e-14 ? (T)1e-14 : v;
+  return o_div(c * u, o_sqrt(rt));
+}
+// Toroidal Y-Z curve (toroidal.py:87-160): conic (radicand clamped at 0 / eps) + sum alpha_i y^(2(i+1)).
+template <typename T>
+OLB_HD void toroidal_yz(T y, const PrepSurface<T>& S, const T* pool, T& zy, T& dzy) {
+  const T c = S.curv_y, y2 = y * y;
+  zy = 0; dzy = 0;
+  if (c != 0) {
+    T v = o_fma(-S.kp1_y * c * c, y2, (T)1);
+    zy = o_div(c * y2, (T)1 + o_sqrt(v < 0 ? (T)0 : v));
+    dzy = o_div(c * y, o_sqrt(v < (T)1e-14 ? (T)1e-14 : v));
+  }
+  const T* a = pool + S.coef_off;
+  T h = 0, hd = 0;
+  for (int i = S.n_coef - 1; i >= 0; --i) {
+    h = o_fma(h, y2, a[i]);
+    hd = o_fma(hd, y2, (T)(2 * (i + 1)) * a[i]);
+  }
+  zy = o_fma(h, y2, zy);
+  dzy = o_fma(hd, y, dzy);
+}
+
 template <typename T>
 OLB_HD T newton_sag(T x, T y, const PrepSurface<T>& S, const T* pool, int& status) {
+  if (S.kind == OLB_GEOM_BICONIC) return biconic_profile(x, S.curv, S.kp1) + biconic_profile(y, S.curv_y, S.kp1_y);
+  if (S.kind == OLB_GEOM_TOROIDAL) {
+    T zy, dzy;
+    toroidal_yz(y, S, pool, zy, dzy);
+    if (!(S.r_rot - S.r_rot == 0)) return zy;           // infinite radius of rotation: a cylinder
+    T d = S.r_rot - zy;
+    T term = o_fma(d, d, -x * x);
+    if (term < 0) return (T)NAN;
+    T sg = d > 0 ? (T)1 : (d < 0 ? (T)-1 : (T)0);
+    return zy + (d - sg * o_sqrt(term));               // toroidal.py:176-186
+  }
   T r2 = o_fma(x, x, y * y);
   T sag, inv_denom;
   conic_sag_slope(r2, S, sag, inv_denom);
@@ -228,8 +275,11 @@ OLB_HD T newton_sag(T x, T y, const PrepSurface<T>& S, const T* pool, int& statu
     for (int i = S.n_coef - 1; i >= 0; --i) h = o_fma(h, r, c[i]);
     sag = o_fma(h, r, sag);
   } else {
-    T xn = x * S.inv_norm, yn = y * S.inv_norm;
-    if (S.kind == OLB_GEOM_ZERNIKE && (o_abs(xn) > (T)1 || o_abs(yn) > (T)1)) status |= OLB_ST_ZERNIKE_RANGE;
+    T xn = x * S.inv_norm, yn = y * S.inv_norm_y;
+    if (o_abs(xn) > (T)1 || o_abs(yn) > (T)1) {
+      if (S.kind == OLB_GEOM_ZERNIKE) status |= OLB_ST_ZERNIKE_RANGE;
+      if (S.kind == OLB_GEOM_CHEBYSHEV) status |= OLB_ST_CHEBYSHEV_RANGE;
+    }
     sag += poly2_value(pool + S.coef_off, S.poly_rows, S.poly_cols, (S.flags & PSF_POLY_TRI) != 0, xn, yn);
   }
   return sag;
@@ -241,6 +291,25 @@ OLB_HD T newton_sag(T x, T y, const PrepSurface<T>& S, const T* pool, int& statu
 // reproducing the reference's eps-regularised chain rule).
 template <typename T>
 OLB_HD void newton_slopes(T x, T y, const PrepSurface<T>& S, const T* pool, T& fx, T& fy) {
+  if (S.kind == OLB_GEOM_BICONIC) {                     // biconic.py:107-160
+    fx = biconic_slope(x, S.curv, S.kp1);
+    fy = biconic_slope(y, S.curv_y, S.kp1_y);
+    return;
+  }
+  if (S.kind == OLB_GEOM_TOROIDAL) {                    // toroidal.py:188-232
+    T zy, dzy;
+    toroidal_yz(y, S, pool, zy, dzy);
+    if (!(S.r_rot - S.r_rot == 0)) { fx = 0; fy = dzy; return; }
+    T d = S.r_rot - zy;
+    T term = o_fma(d, d, -x * x);
+    if (!(term >= 0)) { fx = 0; fy = 0; return; }       // outside the torus: normal (0, 0, -1)
+    T sq = o_sqrt(term);
+    if (o_abs(sq) < (T)1e-14) sq = (T)1e-14;
+    T sr = S.r_rot > 0 ? (T)1 : (T)-1;
+    fx = o_div(sr * x, sq);
+    fy = o_div(sr * d * dzy, sq);
+    return;
+  }
   T r2 = o_fma(x, x, y * y);
   T sag, g;
   conic_sag_slope(r2, S, sag, g);
@@ -259,7 +328,7 @@ OLB_HD void newton_slopes(T x, T y, const PrepSurface<T>& S, const T* pool, T& f
     g += hr;
     fx = x * g; fy = y * g;
   } else {
-    T xn = x * S.inv_norm, yn = y * S.inv_norm;
+    T xn = x * S.inv_norm, yn = y * S.inv_norm_y;
     T P, Px, Py;
     poly2_eval(pool + S.poly_d_off, S.poly_rows, S.poly_cols, (S.flags & PSF_POLY_TRI) != 0, xn, yn, P, Px, Py);
     if (S.kind == OLB_GEOM_ZERNIKE) {
@@ -280,8 +349,11 @@ OLB_HD void newton_slopes(T x, T y, const PrepSurface<T>& S, const T* pool, T& f
         Py = o_fma(Dy, o_fma(a_, yy, b_ * xx), Dx * xy) * inv;
       }
     }
-    fx = o_fma(x, g, Px * S.inv_norm);
-    fy = o_fma(y, g, Py * S.inv_norm);
+    // Chebyshev quirk (reproduced, not fixed): the reference adds T_i'(x/norm_x) T_j(y/norm_y) to dz/dx
+    // WITHOUT the chain-rule factor 1/norm_x (chebyshev.py:171-181, :206-228)
+    const bool cheb = S.kind == OLB_GEOM_CHEBYSHEV;
+    fx = o_fma(x, g, cheb ? Px : Px * S.inv_norm);
+    fy = o_fma(y, g, cheb ? Py : Py * S.inv_norm_y);
   }
 }
 

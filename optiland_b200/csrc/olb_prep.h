@@ -73,7 +73,8 @@ struct PrepSurface {
   // outgoing transform to global: p_glob = R * p_loc + t
   T R[9], t[3];
   T radius, curv, conic, kp1;   // curv = 1/radius (0 for infinite radius), kp1 = 1 + k
-  T tol, coat_t, coat_r, inv_norm;  // inv_norm = 1 / norm_radius
+  T tol, coat_t, coat_r, inv_norm;  // inv_norm = 1 / norm_radius (Chebyshev: 1 / norm_x)
+  T inv_norm_y, curv_y, kp1_y, r_rot;  // Chebyshev 1/norm_y; biconic cy, 1+ky; toroidal: c_yz, 1+k_yz, R_rot
 };
 
 enum : uint32_t {
@@ -166,6 +167,7 @@ static void build_blob(const OlbTable& tab, const std::vector<std::vector<double
     for (int i = 0; i < 3; ++i) { b.bg[i] = (T)a.bg[i]; b.br[i] = (T)a.br[i]; b.t[i] = (T)a.t[i]; }
     b.radius = (T)a.radius; b.curv = (T)a.curv; b.conic = (T)a.conic; b.kp1 = (T)a.kp1;
     b.tol = (T)a.tol; b.coat_t = (T)a.coat_t; b.coat_r = (T)a.coat_r; b.inv_norm = (T)a.inv_norm;
+    b.inv_norm_y = (T)a.inv_norm_y; b.curv_y = (T)a.curv_y; b.kp1_y = (T)a.kp1_y; b.r_rot = (T)a.r_rot;
     for (double v : pools[s]) pool.push_back((T)v);
     while (pool.size() % 4) pool.push_back((T)0);
   }
@@ -222,7 +224,7 @@ static inline PrepResult prepare_table(const OlbTable& tab) {
     o.flags = in.flags & 0xffu;
     o.max_iter = in.max_iter;
     o.coating = in.coating;
-    if (in.kind < OLB_GEOM_NOOP || in.kind > OLB_GEOM_POLYNOMIAL) { res.error = "unknown geometry kind"; return res; }
+    if (in.kind < OLB_GEOM_NOOP || in.kind > OLB_GEOM_TOROIDAL) { res.error = "unknown geometry kind"; return res; }
 
     // ---- pose --------------------------------------------------------------
     double Rt[9];
@@ -261,7 +263,7 @@ static inline PrepResult prepare_table(const OlbTable& tab) {
     o.radius = in.radius; o.conic = in.conic; o.kp1 = 1.0 + in.conic;
     o.tol = in.tol;
     o.coat_t = in.coat_t; o.coat_r = in.coat_r;
-    o.inv_norm = 1.0;
+    o.inv_norm = 1.0; o.inv_norm_y = 1.0; o.curv_y = 0; o.kp1_y = 1.0; o.r_rot = INFINITY;
     if (in.kind == OLB_GEOM_PLANE || in.kind == OLB_GEOM_NOOP) { o.radius = INFINITY; o.curv = 0; }
     else if (std::isinf(in.radius)) { o.curv = 0; o.flags |= PSF_RADIUS_INF; }
     else { o.curv = 1.0 / in.radius; }
@@ -286,6 +288,52 @@ static inline PrepResult prepare_table(const OlbTable& tab) {
       while (pool.size() % 4) pool.push_back(0);
       o.poly_d_off = o.coef_off;  // derivative of the same polynomial (polynomial.py:123-155)
       o.inv_norm = 1.0;
+    } else if (in.kind == OLB_GEOM_CHEBYSHEV) {
+      // conic + sum C_ij T_i(x/nx) T_j(y/ny)  (chebyshev.py:126-150): expanded into monomials of
+      // (xn, yn) with the integer coefficients of T_n (T_0 = 1, T_1 = x, T_{n+1} = 2x T_n - T_{n-1}).
+      const int cols = in.aux0 > 0 ? in.aux0 : 1;
+      if (in.n_coef % cols || !in_pool(in.coef_off, in.n_coef + 2)) { res.error = "bad Chebyshev block"; return res; }
+      const int rows = in.n_coef / cols;
+      if (rows > 24 || cols > 24) { res.error = "Chebyshev order too high (max 23)"; return res; }
+      const double nx = tab.pool[in.coef_off], ny = tab.pool[in.coef_off + 1];
+      if (!(nx > 0) || !(ny > 0)) { res.error = "Chebyshev norms must be positive"; return res; }
+      const int M = rows > cols ? rows : cols;
+      std::vector<std::vector<double>> Tc(M, std::vector<double>(M, 0.0));  // Tc[n][p]: coefficient of x^p in T_n
+      Tc[0][0] = 1.0;
+      if (M > 1) Tc[1][1] = 1.0;
+      for (int n = 2; n < M; ++n)
+        for (int p = 0; p < M; ++p) Tc[n][p] = (p > 0 ? 2.0 * Tc[n - 1][p - 1] : 0.0) - Tc[n - 2][p];
+      std::vector<double> Pm(rows * cols, 0.0);
+      for (int i = 0; i < rows; ++i)
+        for (int j = 0; j < cols; ++j) {
+          const double c = tab.pool[in.coef_off + 2 + i * cols + j];
+          if (c == 0) continue;
+          for (int p = 0; p <= i; ++p)
+            for (int q = 0; q <= j; ++q) Pm[p * cols + q] += c * Tc[i][p] * Tc[j][q];
+        }
+      o.poly_rows = rows; o.poly_cols = cols;
+      o.coef_off = (int)pool.size();
+      pool.insert(pool.end(), Pm.begin(), Pm.end());
+      while (pool.size() % 4) pool.push_back(0);
+      o.poly_d_off = o.coef_off;
+      o.inv_norm = 1.0 / nx; o.inv_norm_y = 1.0 / ny;
+    } else if (in.kind == OLB_GEOM_BICONIC) {
+      if (!in_pool(in.coef_off, 2)) { res.error = "biconic block outside pool"; return res; }
+      const double Ry = tab.pool[in.coef_off], ky = tab.pool[in.coef_off + 1];
+      // cx / cy = 0 for an infinite or zero radius (biconic.py:63-64)
+      if (std::isinf(in.radius) || in.radius == 0) o.curv = 0;
+      o.curv_y = (std::isinf(Ry) || Ry == 0) ? 0.0 : 1.0 / Ry;
+      o.kp1_y = 1.0 + ky;
+    } else if (in.kind == OLB_GEOM_TOROIDAL) {
+      if (!in_pool(in.coef_off, 2 + in.n_coef) || in.n_coef < 0) { res.error = "toroidal block outside pool"; return res; }
+      if (in.conic != 0) { res.error = "toroidal: OlbSurface.conic must be 0 (the Newton start sphere)"; return res; }
+      o.r_rot = tab.pool[in.coef_off];
+      o.kp1_y = 1.0 + tab.pool[in.coef_off + 1];
+      o.curv_y = (std::isfinite(in.radius) && in.radius != 0) ? 1.0 / in.radius : 0.0;  // c_yz (toroidal.py:82-84)
+      o.n_coef = in.n_coef;
+      o.coef_off = (int)pool.size();
+      for (int i = 0; i < in.n_coef; ++i) pool.push_back(tab.pool[in.coef_off + 2 + i]);
+      while (pool.size() % 4) pool.push_back(0);
     } else if (in.kind == OLB_GEOM_ZERNIKE) {
       if (!in_pool(in.coef_off, 4 * in.n_coef)) { res.error = "Zernike block outside pool"; return res; }
       if (!(in.norm_radius > 0)) { res.error = "Zernike norm_radius must be positive"; return res; }
@@ -310,7 +358,7 @@ static inline PrepResult prepare_table(const OlbTable& tab) {
       o.poly_d_off = (int)pool.size();
       pool.insert(pool.end(), D.begin(), D.end());
       while (pool.size() % 4) pool.push_back(0);
-      o.inv_norm = 1.0 / in.norm_radius;
+      o.inv_norm = 1.0 / in.norm_radius; o.inv_norm_y = o.inv_norm;
     }
 
     // ---- aperture ------------------------------------------------------------

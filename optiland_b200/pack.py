@@ -83,6 +83,9 @@ _GEOM_KINDS = {
     "OddAsphere": T.GEOM_ODD_ASPHERE,
     "PolynomialGeometry": T.GEOM_POLYNOMIAL,
     "ZernikePolynomialGeometry": T.GEOM_ZERNIKE,
+    "ChebyshevPolynomialGeometry": T.GEOM_CHEBYSHEV,
+    "BiconicGeometry": T.GEOM_BICONIC,
+    "ToroidalGeometry": T.GEOM_TOROIDAL,
 }
 
 
@@ -127,6 +130,19 @@ def pack_surface(surface, wavelengths) -> T.SurfaceSpec:
     elif kind == T.GEOM_POLYNOMIAL:
         C = g.coefficients
         spec.coefficients = np.atleast_2d(np.array([[_f(c) for c in row] for row in C], dtype=np.float64))
+    elif kind == T.GEOM_CHEBYSHEV:
+        spec.coefficients = np.atleast_2d(_arr(g.coefficients))
+        spec.norm_radius = _f(g.norm_x)
+        spec.norm_y = _f(g.norm_y)
+    elif kind == T.GEOM_BICONIC:
+        # radius / k of the base class hold Rx / kx (biconic.py:56-57)
+        spec.radius_y = _f(g.Ry)
+        spec.conic_y = _f(g.ky)
+    elif kind == T.GEOM_TOROIDAL:
+        # base class: radius = R_yz, k = 0 (the Newton start sphere, toroidal.py:71-73)
+        spec.radius_y = _f(g.R_rot)
+        spec.conic_y = _f(g.k_yz)
+        spec.coefficients = np.array([_f(c) for c in g.coeffs_poly_y], dtype=np.float64)
     elif kind == T.GEOM_ZERNIKE:
         z = g.zernike
         coeffs = [_f(c) for c in z.coeffs]

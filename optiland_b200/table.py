@@ -26,6 +26,9 @@ GEOM_EVEN_ASPHERE = 3
 GEOM_ZERNIKE = 4
 GEOM_ODD_ASPHERE = 5
 GEOM_POLYNOMIAL = 6
+GEOM_CHEBYSHEV = 7
+GEOM_BICONIC = 8
+GEOM_TOROIDAL = 9
 
 SF_REFLECT = 1 << 0
 SF_ROTATED = 1 << 1
@@ -49,11 +52,13 @@ _AP_OPERANDS = {AP_RADIAL: 2, AP_OFFSET_RADIAL: 4, AP_RECT: 4, AP_ELLIPSE: 4,
 
 TF_POLARIZED = 1 << 0
 ST_ZERNIKE_RANGE = 1 << 0
+ST_CHEBYSHEV_RANGE = 1 << 1
 
 MAX_SURFACES = 64
 MAX_WAVELENGTHS = 16
 
-NEWTON_KINDS = (GEOM_EVEN_ASPHERE, GEOM_ZERNIKE, GEOM_ODD_ASPHERE, GEOM_POLYNOMIAL)
+NEWTON_KINDS = (GEOM_EVEN_ASPHERE, GEOM_ZERNIKE, GEOM_ODD_ASPHERE, GEOM_POLYNOMIAL, GEOM_CHEBYSHEV, GEOM_BICONIC,
+                GEOM_TOROIDAL)
 
 # numpy mirror of `struct OlbSurface` (192 bytes)
 OLB_SURFACE_DTYPE = np.dtype(
@@ -83,7 +88,10 @@ class SurfaceSpec:
     max_iter: int = 100
     # EVEN/ODD: (n,) ; POLYNOMIAL: (rows, cols) ; ZERNIKE: (n_terms, 4) {n, m, c*N_nm, c}
     coefficients: np.ndarray = field(default_factory=lambda: np.zeros(0))
-    norm_radius: float = 1.0
+    norm_radius: float = 1.0   # Zernike norm_radius; Chebyshev norm_x
+    norm_y: float = 1.0        # Chebyshev norm_y
+    radius_y: float = float("inf")  # biconic Ry; toroidal: radius of rotation R_rot
+    conic_y: float = 0.0            # biconic ky; toroidal: conic of the Y-Z curve
     reflective: bool = False
     aperture: np.ndarray | None = None  # postfix program, see include/olb.h
     n1: np.ndarray = field(default_factory=lambda: np.ones(1))
@@ -217,16 +225,25 @@ class SurfaceTable:
             r["coat_r"] = s.coat_r
             r["norm_radius"] = s.norm_radius
             coef = s.coefficients
-            if s.kind == GEOM_POLYNOMIAL:
+            extra_head = None
+            if s.kind in (GEOM_POLYNOMIAL, GEOM_CHEBYSHEV):
                 coef = np.atleast_2d(coef)
                 r["n_coef"] = coef.size
                 r["aux0"] = coef.shape[1]
+                if s.kind == GEOM_CHEBYSHEV:
+                    extra_head = [s.norm_radius, s.norm_y]
+            elif s.kind in (GEOM_BICONIC, GEOM_TOROIDAL):
+                r["n_coef"] = coef.size
+                extra_head = [s.radius_y, s.conic_y]
             elif s.kind == GEOM_ZERNIKE:
                 coef = coef.reshape(-1, 4)
                 r["n_coef"] = coef.shape[0]
             else:
                 r["n_coef"] = coef.size
-            r["coef_off"] = push(coef) if coef.size else 0
+            if extra_head is not None:
+                r["coef_off"] = push(np.concatenate([np.asarray(extra_head, float), coef.ravel()]))
+            else:
+                r["coef_off"] = push(coef) if coef.size else 0
             if s.aperture is not None:
                 r["aper_off"] = push(s.aperture)
                 r["aper_len"] = len(s.aperture)
@@ -264,11 +281,19 @@ class SurfaceTable:
             kind = int(r["kind"])
             n_coef = int(r["n_coef"])
             off = int(r["coef_off"])
+            head = None
             if kind == GEOM_ZERNIKE:
                 coef = pool[off: off + 4 * n_coef].reshape(-1, 4).copy()
             elif kind == GEOM_POLYNOMIAL:
                 cols = max(int(r["aux0"]), 1)
                 coef = pool[off: off + n_coef].reshape(-1, cols).copy()
+            elif kind == GEOM_CHEBYSHEV:
+                cols = max(int(r["aux0"]), 1)
+                head = pool[off: off + 2].copy()
+                coef = pool[off + 2: off + 2 + n_coef].reshape(-1, cols).copy()
+            elif kind in (GEOM_BICONIC, GEOM_TOROIDAL):
+                head = pool[off: off + 2].copy()
+                coef = pool[off + 2: off + 2 + n_coef].copy()
             else:
                 coef = pool[off: off + n_coef].copy()
             flags = int(r["flags"])
@@ -284,7 +309,10 @@ class SurfaceTable:
                     kind=kind, t=r["t"].copy(), R=r["R"].reshape(3, 3).copy(),
                     radius=float(r["radius"]), conic=float(r["conic"]), tol=float(r["tol"]),
                     max_iter=int(r["max_iter"]), coefficients=coef,
-                    norm_radius=float(r["norm_radius"]),
+                    norm_radius=float(head[0]) if kind == GEOM_CHEBYSHEV else float(r["norm_radius"]),
+                    norm_y=float(head[1]) if kind == GEOM_CHEBYSHEV else 1.0,
+                    radius_y=float(head[0]) if kind in (GEOM_BICONIC, GEOM_TOROIDAL) else float("inf"),
+                    conic_y=float(head[1]) if kind in (GEOM_BICONIC, GEOM_TOROIDAL) else 0.0,
                     reflective=bool(flags & SF_REFLECT), aperture=aper,
                     n1=media[0].copy(), n2=media[1].copy(), k1=media[2].copy(),
                     coating=coating, coat_t=float(r["coat_t"]), coat_r=float(r["coat_r"]),

@@ -127,7 +127,7 @@ class DeviceTable:
             rc = self.lib.olb_table_upload(C.byref(self.host.c), self.workspace.data_ptr(), int(nbytes),
                                            C.c_void_p(stream), C.byref(self.c))
         _lib.check(rc, "olb_table_upload")
-        self.has_zernike = any(s.kind == T.GEOM_ZERNIKE for s in table.surfaces)
+        self.has_zernike = any(s.kind in (T.GEOM_ZERNIKE, T.GEOM_CHEBYSHEV) for s in table.surfaces)
 
     @property
     def features(self) -> int:
@@ -190,11 +190,18 @@ def trace_device(dtab: DeviceTable, rays: RealRays, first: int, last: int, recor
         rc = fn(C.byref(dtab.c), first, last, C.byref(c_rays), C.byref(c_rec) if c_rec is not None else None,
                 n, flags, _ptr(status), C.c_void_p(stream))
     _lib.check(rc, f"olb_trace_{sfx}")
-    if status is not None and int(status.item()) & T.ST_ZERNIKE_RANGE:
-        # same exception, same message as optiland/geometries/zernike.py:254-266
-        raise ValueError(
-            "Zernike coordinates must be normalized to [-1, 1]. Consider updating the normalization "
-            "radius to 1.1x the surface aperture.")
+    if status is not None:
+        st = int(status.item())
+        if st & T.ST_ZERNIKE_RANGE:
+            # same exception, same message as optiland/geometries/zernike.py:254-266
+            raise ValueError(
+                "Zernike coordinates must be normalized to [-1, 1]. Consider updating the normalization "
+                "radius to 1.1x the surface aperture.")
+        if st & T.ST_CHEBYSHEV_RANGE:
+            # optiland/geometries/chebyshev.py:230-244
+            raise ValueError(
+                "Chebyshev input coordinates must be normalized to [-1, 1]. Consider updating the "
+                "normalization factors.")
     if recs is not None:
         rays.x, rays.y, rays.z = recs["x"][-1], recs["y"][-1], recs["z"][-1]
         rays.L, rays.M, rays.N = recs["L"][-1], recs["M"][-1], recs["N"][-1]

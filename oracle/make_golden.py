@@ -318,6 +318,43 @@ def case_misc():
     run_case("misc_apertures_coatings", lens, rays, [0.55])
 
 
+def case_more_geometries():
+    """Chebyshev, biconic and toroidal surfaces (the remaining Newton-family geometries)."""
+    lens = _optic.Optic()
+    lens.surfaces.add(index=0, radius=be.inf, thickness=be.inf)
+    lens.surfaces.add(index=1, radius=60.0, thickness=5.0, material="N-BK7", is_stop=True, conic=-0.3,
+                      surface_type="chebyshev", tol=1e-10, norm_x=9.0, norm_y=11.0,
+                      coefficients=[[0.0, 2e-3, -1e-3, 4e-4], [1e-3, -5e-4, 2e-4, 0.0], [-3e-3, 1e-4, 0.0, 6e-5],
+                                    [2e-4, 0.0, -8e-5, 0.0]])
+    lens.surfaces.add(index=2, thickness=4.0, material="N-SF11", surface_type="biconic", radius_x=-45.0,
+                      radius_y=-70.0, conic_x=0.4, conic_y=-1.2, tol=1e-10)
+    lens.surfaces.add(index=3, thickness=30.0, surface_type="toroidal", radius_x=-120.0, radius_y=-55.0,
+                      conic=-0.6, toroidal_coeffs_poly_y=[1e-5, -2e-7], tol=1e-10)
+    lens.surfaces.add(index=4)
+    lens.set_aperture(aperture_type="EPD", value=12.0)
+    lens.fields.set_type(field_type="angle")
+    lens.fields.add(y=0)
+    lens.fields.add(y=3)
+    lens.wavelengths.add(value=0.55, is_primary=True)
+    Px, Py = disk(400, seed=12)
+    rays = gen(lens, 0.0, 0.6, Px, Py, 0.55)
+    run_case("cheb_biconic_toroidal", lens, rays, [0.55])
+    # Chebyshev range error: the reference raises ValueError (chebyshev.py:230-244)
+    lens = _optic.Optic()
+    lens.surfaces.add(index=0, radius=be.inf, thickness=be.inf)
+    lens.surfaces.add(index=1, radius=60.0, thickness=5.0, material="N-BK7", is_stop=True, surface_type="chebyshev",
+                      norm_x=4.0, norm_y=4.0, coefficients=[[0.0, 1e-3], [1e-3, 0.0]])
+    lens.surfaces.add(index=2, thickness=30.0)
+    lens.surfaces.add(index=3)
+    lens.set_aperture(aperture_type="EPD", value=12.0)
+    lens.fields.set_type(field_type="angle")
+    lens.fields.add(y=0)
+    lens.wavelengths.add(value=0.55, is_primary=True)
+    Px, Py = disk(50, seed=13)
+    rays = gen(lens, 0.0, 0.0, Px, Py, 0.55)
+    run_case("chebyshev_range_error", lens, rays, [0.55], expect_error=True)
+
+
 def main():
     be.set_backend("numpy")
     case_cooke()
@@ -328,6 +365,7 @@ def main():
     case_polarized()
     case_tilted()
     case_misc()
+    case_more_geometries()
     case_autograd()
 
 
@@ -370,7 +408,10 @@ def case_autograd():
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "autograd":
+    if len(sys.argv) > 1 and sys.argv[1] == "more":
+        be.set_backend("numpy")
+        case_more_geometries()
+    elif len(sys.argv) > 1 and sys.argv[1] == "autograd":
         case_autograd()
     else:
         main()

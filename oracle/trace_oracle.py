@@ -160,6 +160,163 @@ def poly_normal(x, y, radius, k, C):
         return dzdx / norm, dzdy / norm, -1 / norm
 
 
+# ---- Chebyshev / biconic / toroidal ------------------------------------------
+
+def _cheb(n, x):
+    """optiland/geometries/chebyshev.py:193-204."""
+    return np.cos(n * np.arccos(x))
+
+
+def _cheb_d(n, x):
+    """optiland/geometries/chebyshev.py:206-228."""
+    return n * np.sin(n * np.arccos(x)) / np.sqrt(1 - x**2)
+
+
+def cheb_sag(x, y, radius, k, C, norm_x, norm_y, status):
+    """optiland/geometries/chebyshev.py:126-150."""
+    x_norm, y_norm = x / norm_x, y / norm_y
+    with np.errstate(all="ignore"):
+        if np.any(np.abs(x_norm) > 1) or np.any(np.abs(y_norm) > 1):
+            status[0] |= T.ST_CHEBYSHEV_RANGE  # reference raises ValueError (chebyshev.py:230-244)
+        r2 = x**2 + y**2
+        z = r2 / (radius * (1 + np.sqrt(1 - (1 + k) * r2 / radius**2)))
+        for i, j in np.argwhere(C != 0):
+            z = z + C[i, j] * _cheb(i, x_norm) * _cheb(j, y_norm)
+    return z
+
+
+def cheb_normal(x, y, radius, k, C, norm_x, norm_y, status):
+    """optiland/geometries/chebyshev.py:152-191.  (The chain-rule factor 1/norm is NOT applied by the
+    reference: d/dx of T_i(x/norm_x) is taken as T_i'(x/norm_x); reproduced.)"""
+    x_norm, y_norm = x / norm_x, y / norm_y
+    with np.errstate(all="ignore"):
+        if np.any(np.abs(x_norm) > 1) or np.any(np.abs(y_norm) > 1):
+            status[0] |= T.ST_CHEBYSHEV_RANGE
+        r2 = x**2 + y**2
+        denom = radius * np.sqrt(1 - (1 + k) * r2 / radius**2)
+        dzdx = x / denom
+        dzdy = y / denom
+        for i, j in np.argwhere(C != 0):
+            dzdx = dzdx + (_cheb_d(i, x_norm) * C[i, j] * _cheb(j, y_norm))
+            dzdy = dzdy + (_cheb_d(j, y_norm) * C[i, j] * _cheb(i, x_norm))
+        norm = np.sqrt(dzdx**2 + dzdy**2 + 1)
+        return dzdx / norm, dzdy / norm, -1 / norm
+
+
+def _curv(R):
+    return 0.0 if (math.isinf(R) or R == 0) else 1.0 / R
+
+
+def biconic_sag(x, y, Rx, kx, Ry, ky):
+    """optiland/geometries/biconic.py:72-105."""
+    cx, cy = _curv(Rx), _curv(Ry)
+    zx, zy = np.zeros_like(x), np.zeros_like(y)
+    with np.errstate(all="ignore"):
+        if cx != 0:
+            v = 1.0 - (1.0 + kx) * cx**2 * x**2
+            rt = np.where(v < 1e-14, 0.0, v)
+            den = 1.0 + np.sqrt(rt)
+            zx = (cx * x**2) / np.where(np.abs(den) < 1e-14, 1e-14, den)
+        if cy != 0:
+            v = 1.0 - (1.0 + ky) * cy**2 * y**2
+            rt = np.where(v < 1e-14, 0.0, v)
+            den = 1.0 + np.sqrt(rt)
+            zy = (cy * y**2) / np.where(np.abs(den) < 1e-14, 1e-14, den)
+    return zx + zy
+
+
+def biconic_normal(x, y, Rx, kx, Ry, ky):
+    """optiland/geometries/biconic.py:107-160."""
+    cx, cy = _curv(Rx), _curv(Ry)
+    with np.errstate(all="ignore"):
+        if cx == 0:
+            dfdx = np.zeros_like(x)
+        else:
+            v = 1.0 - (1.0 + kx) * cx**2 * x**2
+            sq = np.sqrt(np.where(v < 1e-14, 1e-14, v))
+            dfdx = (cx * x) / np.where(np.abs(sq) < 1e-14, 1e-14, sq)
+        if cy == 0:
+            dfdy = np.zeros_like(y)
+        else:
+            v = 1.0 - (1.0 + ky) * cy**2 * y**2
+            sq = np.sqrt(np.where(v < 1e-14, 1e-14, v))
+            dfdy = (cy * y) / np.where(np.abs(sq) < 1e-14, 1e-14, sq)
+        mag = np.sqrt(dfdx**2 + dfdy**2 + 1.0)
+        mag = np.where(mag < 1e-14, 1.0, mag)
+        return dfdx / mag, dfdy / mag, -1.0 / mag
+
+
+def _tor_zy(y, R_yz, k_yz, coefs):
+    """optiland/geometries/toroidal.py:87-121."""
+    y2 = y**2
+    z_y = np.zeros_like(y)
+    with np.errstate(all="ignore"):
+        if math.isfinite(R_yz) and R_yz != 0:
+            c = 1.0 / R_yz
+            v = 1.0 - (1.0 + k_yz) * c**2 * y2
+            den = 1.0 + np.sqrt(np.where(v < 0, 0.0, v))
+            z_y = (c * y2) / np.where(np.abs(den) < 1e-14, 1e-14, den)
+        if len(coefs) > 0:
+            poly, p = np.zeros_like(y), y2
+            for coeff in coefs:
+                poly = poly + coeff * p
+                p = p * y2
+            z_y = z_y + poly
+    return z_y
+
+
+def _tor_dzy(y, R_yz, k_yz, coefs):
+    """optiland/geometries/toroidal.py:123-160."""
+    y2 = y**2
+    dz = np.zeros_like(y)
+    with np.errstate(all="ignore"):
+        if math.isfinite(R_yz) and R_yz != 0:
+            c = 1.0 / R_yz
+            v = 1.0 - (1.0 + k_yz) * c**2 * y2
+            sq = np.sqrt(np.where(v < 1e-14, 1e-14, v))
+            dz = (c * y) / np.where(np.abs(sq) < 1e-14, 1e-14, sq)
+        if len(coefs) > 0:
+            poly, p = np.zeros_like(y), y
+            for i, coeff in enumerate(coefs):
+                poly = poly + coeff * (2.0 * (i + 1.0)) * p
+                p = p * y2
+            dz = dz + poly
+    return dz
+
+
+def toroidal_sag(x, y, R_rot, R_yz, k_yz, coefs):
+    """optiland/geometries/toroidal.py:162-186."""
+    z_y = _tor_zy(y, R_yz, k_yz, coefs)
+    if math.isinf(R_rot):
+        return z_y
+    with np.errstate(all="ignore"):
+        term = (R_rot - z_y) ** 2 - x**2
+        return np.where(term < 0, np.nan, z_y + ((R_rot - z_y) - np.sign(R_rot - z_y) * np.sqrt(term)))
+
+
+def toroidal_normal(x, y, R_rot, R_yz, k_yz, coefs):
+    """optiland/geometries/toroidal.py:188-232."""
+    z_y = _tor_zy(y, R_yz, k_yz, coefs)
+    dz_dy = _tor_dzy(y, R_yz, k_yz, coefs)
+    eps = 1e-14
+    with np.errstate(all="ignore"):
+        if math.isinf(R_rot):
+            fx, fy = np.zeros_like(x), dz_dy
+            term = np.full_like(x, np.inf)
+        else:
+            term = (R_rot - z_y) ** 2 - x**2
+            valid = term >= 0
+            sq = np.sqrt(np.where(valid, term, eps))
+            sq = np.where(np.abs(sq) < eps, eps, sq)
+            fx = np.where(valid, np.sign(R_rot) * x / sq, 0.0)
+            fy = np.where(valid, np.sign(R_rot) * (R_rot - z_y) * dz_dy / sq, 0.0)
+        mag = np.sqrt(fx**2 + fy**2 + 1.0)
+        mag = np.where(mag < eps, 1.0, mag)
+        nx, ny, nz = fx / mag, fy / mag, -1.0 / mag
+        ok = term >= 0
+        return np.where(ok, nx, 0.0), np.where(ok, ny, 0.0), np.where(ok, nz, -1.0)
+
+
 # ---- Zernike ---------------------------------------------------------------
 
 def _fact(n: int) -> float:
@@ -272,6 +429,16 @@ def _sag_and_normal_fns(s: T.SurfaceSpec, status):
     if s.kind == T.GEOM_POLYNOMIAL:
         C = np.atleast_2d(s.coefficients)
         return (lambda x, y: poly_sag(x, y, R, k, C)), (lambda x, y: poly_normal(x, y, R, k, C))
+    if s.kind == T.GEOM_CHEBYSHEV:
+        C = np.atleast_2d(s.coefficients)
+        nx_, ny_ = s.norm_radius, s.norm_y
+        return (lambda x, y: cheb_sag(x, y, R, k, C, nx_, ny_, status)), (lambda x, y: cheb_normal(x, y, R, k, C, nx_, ny_, status))
+    if s.kind == T.GEOM_BICONIC:
+        Ry, ky = s.radius_y, s.conic_y
+        return (lambda x, y: biconic_sag(x, y, R, k, Ry, ky)), (lambda x, y: biconic_normal(x, y, R, k, Ry, ky))
+    if s.kind == T.GEOM_TOROIDAL:
+        Rr, kyz, cf = s.radius_y, s.conic_y, list(s.coefficients)
+        return (lambda x, y: toroidal_sag(x, y, Rr, R, kyz, cf)), (lambda x, y: toroidal_normal(x, y, Rr, R, kyz, cf))
     if s.kind == T.GEOM_ZERNIKE:
         terms = s.coefficients.reshape(-1, 4)
         nr = s.norm_radius
