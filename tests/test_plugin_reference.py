@@ -169,15 +169,14 @@ def test_declines_and_falls_back_to_reference_python(plugin):
     P, eng, be = plugin
     from optiland.samples.objectives import CookeTriplet
 
-    # unsupported geometry (toroidal) -> decline, results still those of the reference
+    # unsupported interaction model (paraxial thin lens) -> decline, results still those of the reference
     def make():
         from optiland import optic
 
         lens = optic.Optic()
         lens.surfaces.add(index=0, radius=be.inf, thickness=be.inf)
-        lens.surfaces.add(index=1, surface_type="toroidal", radius_x=50.0, radius_y=60.0, thickness=5.0,
-                          material="N-BK7", is_stop=True)
-        lens.surfaces.add(index=2, radius=-80.0, thickness=50.0)
+        lens.surfaces.add(index=1, surface_type="paraxial", f=50.0, thickness=5.0, is_stop=True)
+        lens.surfaces.add(index=2, radius=-80.0, thickness=50.0, material="N-BK7")
         lens.surfaces.add(index=3)
         lens.set_aperture(aperture_type="EPD", value=10.0)
         lens.fields.set_type(field_type="angle")
