@@ -1,0 +1,76 @@
+"""TEST INFRASTRUCTURE ONLY -- stand-in for optiland_b200.plugin.CudaEngine on boxes without a GPU:
+evaluates the packed table with the NumPy oracle (forward) and the CPU instantiation of the device
+adjoint (backward).  Used by tests/test_plugin_reference.py and by the reference-test sweep."""
+import numpy as np
+
+
+class OracleEngine:
+    """TEST-ONLY stand-in for optiland_b200.plugin.CudaEngine."""
+
+    def __init__(self):
+        self.calls = []
+
+    def accepts(self, rays):
+        import torch
+
+        return all(torch.is_tensor(getattr(rays, k)) for k in ("x", "y", "z", "L", "M", "N", "i", "w", "opd"))
+
+    def trace(self, table, rays, first, last):
+        import torch
+
+        from oracle import trace_oracle as O
+
+        self.calls.append((table.num_surfaces, int(rays.x.numel())))
+        inp = {k: getattr(rays, k).detach().double().numpy() for k in ("x", "y", "z", "L", "M", "N", "i", "w", "opd")}
+        polarized = type(rays).__name__ == "PolarizedRays"
+        if polarized:
+            inp["p"] = rays.p.detach().numpy().astype(np.complex128)
+        out, rec, status = O.trace(table, inp, first, last, polarized=polarized)
+        if polarized:
+            rays.p = torch.from_numpy(out["p"])
+        if status:
+            raise ValueError("Zernike coordinates must be normalized to [-1, 1].")
+        dt = rays.x.dtype
+        for k in ("x", "y", "z", "L", "M", "N", "i", "opd"):
+            setattr(rays, k, torch.from_numpy(out[k]).to(dt))
+        return {k: torch.from_numpy(v).to(dt) for k, v in rec.items()}
+
+
+    def trace_grad(self, table, params, rays):
+        """TEST-ONLY differentiable engine: oracle forward + the CPU instantiation of the device adjoint
+        (tests/hostcheck) -- the arithmetic of olb_trace_bwd_* without a GPU."""
+        import torch
+
+        from oracle import trace_oracle as O
+        from optiland_b200 import autograd as AG
+        from oracle.hostcheck_api import load, run_backward
+
+        hc = load()
+        self.calls.append(("grad", table.num_surfaces, int(rays.x.numel())))
+        keys = ("x", "y", "z", "L", "M", "N", "i", "opd")
+
+        class Fn(torch.autograd.Function):
+            @staticmethod
+            def forward(ctx, params, *ins):
+                ctx.set_materialize_grads(False)
+                tab = AG.params_to_table(table, params)
+                inp = {k: t.detach().double().numpy() for k, t in zip(keys, ins)}
+                inp["w"] = rays.w.detach().double().numpy()
+                _, rec, _ = O.trace(tab, inp)
+                ctx.tab, ctx.inp, ctx.rec = tab, inp, rec
+                return tuple(torch.from_numpy(rec[k]) for k in ("x", "y", "z", "L", "M", "N", "intensity", "opd"))
+
+            @staticmethod
+            def backward(ctx, *grads):
+                grec = {k: (None if g is None else g.double().numpy()) for k, g in
+                        zip(("x", "y", "z", "L", "M", "N", "intensity", "opd"), grads)}
+                gin, gpar = run_backward(hc, ctx.tab, ctx.inp, ctx.rec, grec)
+                return (torch.from_numpy(gpar), *[torch.from_numpy(gin[k]) for k in keys])
+
+        outs = Fn.apply(params, *[getattr(rays, k) for k in keys])
+        rec = dict(zip(("x", "y", "z", "L", "M", "N", "intensity", "opd"), outs))
+        for k, key in zip(keys, ("x", "y", "z", "L", "M", "N", "intensity", "opd")):
+            setattr(rays, k, rec[key][-1])
+        return rec
+
+

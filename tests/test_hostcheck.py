@@ -16,50 +16,12 @@ from optiland_b200 import _lib
 from optiland_b200 import table as T
 from tests._util import ERROR_CASES, REAL_CASES, REC, Case, max_abs_err
 
-HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = os.path.join(HERE, "hostcheck", "hostcheck.cpp")
-SO = os.path.join(HERE, "hostcheck", "_hostcheck.so")
-CSRC = os.path.join(os.path.dirname(HERE), "optiland_b200", "csrc")
+from oracle.hostcheck_api import SO, load, run_hostcheck  # noqa: E402,F401
 
 
 @pytest.fixture(scope="module")
 def hc():
-    deps = [SRC, os.path.join(CSRC, "olb_math.cuh"), os.path.join(CSRC, "olb_prep.h")]
-    if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(d) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-mfma", "-ffp-contract=fast", "-shared", "-fPIC", "-o", SO, SRC])
-    return C.CDLL(SO)
-
-
-def run_hostcheck(hc, table, rays, dtype, first=0, last=None, want_l0=False, pmat=None):
-    last = table.num_surfaces if last is None else last
-    ht = _lib.HostTable(table)
-    n = rays["x"].size
-    keys = ("x", "y", "z", "L", "M", "N", "i", "w", "opd")
-    arrs = [np.ascontiguousarray(rays.get(k, np.zeros(n)), dtype=dtype).copy() for k in keys]
-    rows = last - first
-    rec = [np.full((rows, n), np.nan, dtype=dtype) for _ in range(8)]
-    l0 = [np.zeros(n, dtype=dtype) for _ in range(3)]
-    PP = C.c_void_p * 9
-    ray_ptrs = PP(*[a.ctypes.data for a in arrs])
-    rec_ptrs = (C.c_void_p * 8)(*[a.ctypes.data for a in rec])
-    l0_ptrs = (C.c_void_p * 3)(*[a.ctypes.data for a in l0])
-    status = C.c_int(0)
-    err = C.create_string_buffer(256)
-    fn = hc.olbhc_trace_f64 if dtype == np.float64 else hc.olbhc_trace_f32
-    fn.restype = C.c_int
-    parr = None
-    if pmat is not None:
-        cdt = np.complex128 if dtype == np.float64 else np.complex64
-        parr = np.ascontiguousarray(pmat, dtype=cdt).copy()
-    rc = fn(C.byref(ht.c), C.c_int(first), C.c_int(last), C.c_int64(n), ray_ptrs, rec_ptrs,
-            l0_ptrs if want_l0 else None, C.c_void_p(parr.ctypes.data) if parr is not None else None,
-            C.byref(status), err, 256)
-    assert rc == 0, err.value
-    out = dict(zip(keys, arrs))
-    if parr is not None:
-        out["p"] = parr
-    out.update(L0=l0[0], M0=l0[1], N0=l0[2])
-    return out, dict(zip(REC, rec)), status.value
+    return load()
 
 
 def newton_tol(c):

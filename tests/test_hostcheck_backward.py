@@ -12,29 +12,10 @@ from oracle import trace_oracle as O
 from optiland_b200 import _lib
 from optiland_b200 import table as T
 from tests._util import REC, Case
-from tests.test_hostcheck import hc, run_hostcheck  # noqa: F401  (fixture)
+from oracle.hostcheck_api import run_backward  # noqa: F401
+from tests.test_hostcheck import hc  # noqa: F401  (fixture)
 
 GP = dict(TX=0, TY=1, TZ=2, CURV=3, CONIC=4, N1=5, N2=6, COEF=7)
-
-
-def run_backward(hc, table, rays, rec, grec, dtype=np.float64):
-    ht = _lib.HostTable(table)
-    n = rays["x"].size
-    S = table.num_surfaces
-    keys = ("x", "y", "z", "L", "M", "N", "i", "w", "opd")
-    rin = [np.ascontiguousarray(rays.get(k, np.zeros(n)), dtype=dtype) for k in keys]
-    recs = [np.ascontiguousarray(rec[k], dtype=dtype) for k in REC]
-    grecs = [None if grec.get(k) is None else np.ascontiguousarray(grec[k], dtype=dtype) for k in REC]
-    gin = [np.zeros(n, dtype=dtype) for _ in range(8)]
-    gpc = hc.olbhc_gp_count()
-    gpar = np.zeros((S, gpc), dtype=np.float64)
-    P9 = (C.c_void_p * 9)(*[a.ctypes.data for a in rin])
-    P8 = lambda arrs: (C.c_void_p * 8)(*[(a.ctypes.data if a is not None else None) for a in arrs])  # noqa: E731
-    err = C.create_string_buffer(256)
-    fn = hc.olbhc_backward_f64 if dtype == np.float64 else hc.olbhc_backward_f32
-    rc = fn(C.byref(ht.c), 0, S, C.c_int64(n), P9, P8(recs), P8(grecs), P8(gin), C.c_void_p(gpar.ctypes.data), err, 256)
-    assert rc == 0, err.value
-    return dict(zip(("x", "y", "z", "L", "M", "N", "i", "opd"), gin)), gpar
 
 
 def loss_fn(table, rays, weights):

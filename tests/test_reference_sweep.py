@@ -1,0 +1,42 @@
+"""Drop-in check at the scale of the reference's OWN test-suite: selected reference test files
+(/root/reference/tests/*.py, torch backend, fp64, grad mode on -- the reference's conftest) are run
+twice in a subprocess, stock and with the optiland_b200 plugin installed over the test-only oracle
+engine, and must give identical outcomes while the capability is really exercised.  These files hold
+the reference's golden numbers for the consumers of the path (wavefront OPD RMS, Hubble operands,
+spot references, ray/record semantics).  scripts/ref_sweep.sh runs the long ones (test_analysis.py:
+1280 capability calls, identical results)."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+from oracle.ref_import import reference_available
+
+pytestmark = pytest.mark.skipif(not reference_available(), reason="reference not present on this box")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FILES = ["test_surface_group.py", "test_rays.py", "test_wavefront.py", "test_operand.py", "analysis/test_spot_reference.py"]
+
+
+def _run(fname, install):
+    env = dict(os.environ, OLB_SWEEP_INSTALL="1" if install else "0", PYTHONPATH=ROOT)
+    os.makedirs("/tmp/olb_sweep_root", exist_ok=True)
+    out = subprocess.run(
+        [sys.executable, "-m", "pytest", "-p", "oracle.sweep_plugin", "-p", "no:cacheprovider", "-q", "--no-header",
+         "--rootdir=/tmp/olb_sweep_root", "-c", "/dev/null", f"/root/reference/tests/{fname}",
+         "-k", "torch and not view and not draw and not plot"],
+        cwd="/tmp/olb_sweep_root", env=env, capture_output=True, text=True, timeout=600).stdout
+    counts = {k: int(v) for v, k in re.findall(r"(\d+) (passed|failed|error)", out)}
+    calls = re.search(r"capability calls: (\d+)", out)
+    return counts, int(calls.group(1)) if calls else 0
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("fname", FILES)
+def test_reference_tests_unchanged_with_plugin(fname):
+    stock, _ = _run(fname, install=False)
+    ours, calls = _run(fname, install=True)
+    assert stock.get("passed", 0) > 0
+    assert ours == stock, (fname, stock, ours)
+    assert calls > 0, "the capability was never exercised"
