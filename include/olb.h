@@ -106,6 +106,8 @@ extern "C" {
 /* ---- trace flags (argument `flags` of olb_trace_*) ------------------------ */
 #define OLB_TF_POLARIZED   (1u << 0)  /* rays carry a 3x3 complex P matrix (OlbRays.p)  */
 #define OLB_TF_POL_IDENTITY (1u << 2) /* with POLARIZED: P starts as identity, rays.p is output only */
+#define OLB_TF_MOMENTS     (1u << 3)  /* accumulate OlbMoments over the traced batch (fused analysis
+                                         epilogue); see olb_trace_moments_*          */
 #define OLB_TF_NO_FINAL    (1u << 1)  /* do not write the final state back into rays.x..opd:
                                          the caller takes it from the last record row (saves
                                          32-64 B/ray of HBM writes; needs rec)              */
@@ -311,6 +313,27 @@ int olb_trace_pupil_f32(const OlbDeviceTable* table, int32_t first, int32_t last
 int olb_trace_pupil_f64(const OlbDeviceTable* table, int32_t first, int32_t last,
                         const OlbPupilLaunch* launch, const OlbRays* out, const OlbRecords* rec,
                         int64_t n_rays, uint32_t flags, int32_t* status, void* stream);
+
+/*
+ * Fused analysis epilogue (the step immediately after the path): moments of the ray intercepts on the
+ * LAST traced surface, in that surface's local frame (what SpotDiagram transforms to,
+ * optiland/analysis/spot_diagram/core.py:462-481), over rays with intensity > 0 and finite intercepts
+ * (the mask of core.py:471-472), relative to `center`:
+ *   m[0] = count, m[1] = sum (x - cx), m[2] = sum (y - cy), m[3] = sum ((x-cx)^2 + (y-cy)^2),
+ *   m[4] = sum intensity, m[5] = sum opd, m[6] = sum opd^2, m[7] = reserved
+ * accumulated in fp64 INTO `moments` (device, 8 doubles; the caller zeroes it).  From these follow the
+ * centroid, the RMS spot radius about the centroid or about `center` (rms_spot_radius, core.py:357-370)
+ * and the OPD mean / variance without writing or re-reading any per-ray array: rec may be NULL and
+ * with OLB_TF_NO_FINAL the trace writes nothing per ray.  `launch` (optional) as in olb_trace_pupil_*.
+ */
+int olb_trace_moments_f32(const OlbDeviceTable* table, int32_t first, int32_t last,
+                          const OlbPupilLaunch* launch, const OlbRays* rays, const OlbRecords* rec,
+                          int64_t n_rays, uint32_t flags, const double center[2], double* moments,
+                          int32_t* status, void* stream);
+int olb_trace_moments_f64(const OlbDeviceTable* table, int32_t first, int32_t last,
+                          const OlbPupilLaunch* launch, const OlbRays* rays, const OlbRecords* rec,
+                          int64_t n_rays, uint32_t flags, const double center[2], double* moments,
+                          int32_t* status, void* stream);
 
 /*
  * Host-buffer end-to-end trace: HOST SoA in, HOST final ray state out, the

@@ -79,6 +79,12 @@ SYMBOLS = {
                                       _P(OlbRecords), C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p]),
     "olb_trace_pupil_f64": (C.c_int, [_P(OlbDeviceTable), C.c_int32, C.c_int32, _P(OlbPupilLaunch), _P(OlbRays),
                                       _P(OlbRecords), C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "olb_trace_moments_f32": (C.c_int, [_P(OlbDeviceTable), C.c_int32, C.c_int32, _P(OlbPupilLaunch), _P(OlbRays),
+                                        _P(OlbRecords), C.c_int64, C.c_uint32, _P(C.c_double), C.c_void_p,
+                                        C.c_void_p, C.c_void_p]),
+    "olb_trace_moments_f64": (C.c_int, [_P(OlbDeviceTable), C.c_int32, C.c_int32, _P(OlbPupilLaunch), _P(OlbRays),
+                                        _P(OlbRecords), C.c_int64, C.c_uint32, _P(C.c_double), C.c_void_p,
+                                        C.c_void_p, C.c_void_p]),
     "olb_trace_host_pupil_f32": (C.c_int, [_P(OlbDeviceTable), C.c_int32, C.c_int32, _P(OlbPupilLaunch), _P(OlbRays),
                                            _P(OlbRecords), C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
                                            C.c_uint32, C.c_void_p]),

@@ -73,6 +73,9 @@ struct TraceArgs {
   // launch state from pupil coordinates (OlbPupilLaunch) when px != nullptr
   const void* px; const void* py;
   double lo0[3], los[2], lt0[3], lts[2], linten;
+  // fused moments epilogue (OLB_TF_MOMENTS)
+  double* moments;
+  double mcx, mcy;
 };
 
 // ---- vector access helpers -------------------------------------------------------------
@@ -173,6 +176,7 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<T, RPT, FEAT>::v)) trace_ker
   const int64_t n_tiles = (n + per_tile - 1) / per_tile;
   const int first = a.first, last = a.last;
   int status = 0;
+  double mom[7] = {0, 0, 0, 0, 0, 0, 0};   // OLB_TF_MOMENTS: per-thread partial sums
 
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t base = (tile * BLOCK + threadIdx.x) * RPT;
@@ -311,6 +315,19 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<T, RPT, FEAT>::v)) trace_ker
       }
     }
 
+    if (a.tflags & OLB_TF_MOMENTS) {
+      // intercepts in the LAST surface's local frame (r.x, r.y), mask i > 0 and finite
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) {
+        if (k >= valid) continue;
+        const double dx = (double)r[k].x - a.mcx, dy = (double)r[k].y - a.mcy;
+        const double ii = (double)r[k].i, oo = (double)opd_value(r[k]);
+        if (ii > 0 && dx - dx == 0 && dy - dy == 0) {
+          mom[0] += 1.0; mom[1] += dx; mom[2] += dy; mom[3] += dx * dx + dy * dy; mom[4] += ii;
+          mom[5] += oo; mom[6] += oo * oo;
+        }
+      }
+    }
     if (!(a.tflags & OLB_TF_NO_FINAL)) {
       T v[RPT];
       store_rays<T, RPT>((T*)a.x, base, valid, gx);
@@ -597,7 +614,8 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 template <typename T>
 static int trace_impl(const OlbDeviceTable* wh, int32_t first, int32_t last, const OlbRays* rays,
                       const OlbRecords* rec, int64_t n_rays, uint32_t flags, int32_t* status,
-                      cudaStream_t stream, const OlbPupilLaunch* launch = nullptr) {
+                      cudaStream_t stream, const OlbPupilLaunch* launch = nullptr, const double* center = nullptr,
+                      double* moments = nullptr) {
   if (!wh || wh->magic != WS_MAGIC || !wh->workspace)
     return fail(OLB_ERR_INVALID_ARG, "table handle was not initialised by olb_table_upload");
   const unsigned char* workspace_dev = (const unsigned char*)wh->workspace;
@@ -606,6 +624,7 @@ static int trace_impl(const OlbDeviceTable* wh, int32_t first, int32_t last, con
   if (first < 0 || last > wh->n_surfaces || first > last) return fail(OLB_ERR_INVALID_ARG, "bad surface range");
   if (n_rays == 0 || first == last) return OLB_OK;
   void* req[] = {rays->x, rays->y, rays->z, rays->L, rays->M, rays->N, rays->i, rays->opd};
+  if (moments) flags |= OLB_TF_MOMENTS; else flags &= ~uint32_t(OLB_TF_MOMENTS);
   const bool need_state = launch == nullptr || !(flags & OLB_TF_NO_FINAL);
   for (void* p : req) {
     if (!p && need_state) return fail(OLB_ERR_INVALID_ARG, "a required ray array is NULL");
@@ -628,6 +647,8 @@ static int trace_impl(const OlbDeviceTable* wh, int32_t first, int32_t last, con
   a.i = rays->i; a.w = rays->w; a.opd = rays->opd;
   a.L0 = rays->L0; a.M0 = rays->M0; a.N0 = rays->N0; a.p = rays->p;
   a.status = status;
+  a.tflags = flags;
+  if (moments) { a.moments = moments; a.mcx = center ? center[0] : 0.0; a.mcy = center ? center[1] : 0.0; }
   if (launch) {
     a.px = launch->Px; a.py = launch->Py;
     for (int q = 0; q < 3; ++q) { a.lo0[q] = launch->origin0[q]; a.lt0[q] = launch->target0[q]; }
@@ -660,8 +681,8 @@ static int trace_impl(const OlbDeviceTable* wh, int32_t first, int32_t last, con
       if (rec->row_stride % 2) rec_stride_ok2 = false;
     }
   }
-  if ((flags & OLB_TF_NO_FINAL) && !a.rx)
-    return fail(OLB_ERR_INVALID_ARG, "OLB_TF_NO_FINAL needs record arrays (the result would be lost)");
+  if ((flags & OLB_TF_NO_FINAL) && !a.rx && !moments)
+    return fail(OLB_ERR_INVALID_ARG, "OLB_TF_NO_FINAL needs record arrays or moments (the result would be lost)");
   // Rays per thread.  Closed-form tables (planes / conics, optionally rotated): fp32 -> 4
   // (float4 accesses, 120 regs, 16 warps/SM), fp64 -> 1 (74 regs, 24 warps/SM).  Tables with
   // Newton surfaces / aperture programs / coatings: fp32 -> 2, fp64 -> 1 (their per-ray code
@@ -781,6 +802,23 @@ int olb_trace_pupil_f64(const OlbDeviceTable* table, int32_t first, int32_t last
   if (!launch) return fail(OLB_ERR_INVALID_ARG, "launch is NULL");
   OlbRays none{};
   return trace_impl<double>(table, first, last, out ? out : &none, rec, n_rays, flags, status, (cudaStream_t)stream, launch);
+}
+
+int olb_trace_moments_f32(const OlbDeviceTable* table, int32_t first, int32_t last, const OlbPupilLaunch* launch,
+                          const OlbRays* rays, const OlbRecords* rec, int64_t n_rays, uint32_t flags,
+                          const double center[2], double* moments, int32_t* status, void* stream) {
+  if (!moments) return fail(OLB_ERR_INVALID_ARG, "moments is NULL");
+  OlbRays none{};
+  return trace_impl<float>(table, first, last, rays ? rays : &none, rec, n_rays, flags, status, (cudaStream_t)stream,
+                           launch, center, moments);
+}
+int olb_trace_moments_f64(const OlbDeviceTable* table, int32_t first, int32_t last, const OlbPupilLaunch* launch,
+                          const OlbRays* rays, const OlbRecords* rec, int64_t n_rays, uint32_t flags,
+                          const double center[2], double* moments, int32_t* status, void* stream) {
+  if (!moments) return fail(OLB_ERR_INVALID_ARG, "moments is NULL");
+  OlbRays none{};
+  return trace_impl<double>(table, first, last, rays ? rays : &none, rec, n_rays, flags, status, (cudaStream_t)stream,
+                            launch, center, moments);
 }
 
 // ---- host-buffer end-to-end path ---------------------------------------------------------------

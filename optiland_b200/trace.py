@@ -251,6 +251,53 @@ def trace_pupil_device(dtab: DeviceTable, Px: torch.Tensor, Py: torch.Tensor, af
     return rays, recs
 
 
+def trace_moments_device(dtab: DeviceTable, n: int, dtype, rays: RealRays | None = None, pupil=None,
+                         center=(0.0, 0.0), moments: torch.Tensor | None = None, wavelength=None) -> torch.Tensor:
+    """olb_trace_moments_*: trace WITHOUT writing any per-ray output and accumulate the spot / OPD moments
+    of the image-surface intercepts in-kernel (8 fp64 values on the device; see include/olb.h).  Either
+    ``rays`` (launch-state arrays, left untouched) or ``pupil`` = (Px, Py, affine)."""
+    lib = dtab.lib
+    sfx = _DTYPES[dtype]
+    dev = dtab.device
+    if moments is None:
+        moments = torch.zeros(8, dtype=torch.float64, device=dev)
+    la = None
+    c_rays = _lib.OlbRays()
+    if pupil is not None:
+        Px, Py, affine = pupil
+        la = _c_launch(affine, Px, Py)
+        if wavelength is not None and dtab.table.n_wl > 1:
+            c_rays.w = wavelength.data_ptr()
+    else:
+        # the launch arrays are only read (OLB_TF_NO_FINAL): nothing is written back
+        for k in ("x", "y", "z", "L", "M", "N", "i", "opd"):
+            setattr(c_rays, k, getattr(rays, k).data_ptr())
+        if dtab.table.n_wl > 1:
+            c_rays.w = rays.w.data_ptr()
+    cen = (C.c_double * 2)(float(center[0]), float(center[1]))
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = getattr(lib, f"olb_trace_moments_{sfx}")(
+            C.byref(dtab.c), 0, dtab.table.num_surfaces, C.byref(la) if la is not None else None, C.byref(c_rays), None,
+            n, _lib.TF_NO_FINAL, cen, C.c_void_p(moments.data_ptr()), None, C.c_void_p(stream))
+    _lib.check(rc, f"olb_trace_moments_{sfx}")
+    return moments
+
+
+def moments_to_spot(m, center=(0.0, 0.0)) -> dict:
+    """count, centroid, RMS radius about the centroid and about ``center``, mean intensity, OPD mean / rms."""
+    m = [float(v) for v in (m.cpu() if torch.is_tensor(m) else m)]
+    cnt = m[0]
+    if cnt == 0:
+        return {"count": 0.0}
+    mx, my = m[1] / cnt, m[2] / cnt
+    var_c = max(m[3] / cnt - mx * mx - my * my, 0.0)
+    opd_mean = m[5] / cnt
+    return {"count": cnt, "centroid": (center[0] + mx, center[1] + my), "rms_centroid": var_c ** 0.5,
+            "rms_center": (m[3] / cnt) ** 0.5, "intensity_sum": m[4], "opd_mean": opd_mean,
+            "opd_rms": max(m[6] / cnt - opd_mean * opd_mean, 0.0) ** 0.5}
+
+
 class SurfaceGroup:
     """The traced part of the reference's ``SurfaceGroup``: ``trace`` + stacked records."""
 
@@ -278,6 +325,15 @@ class SurfaceGroup:
         in-kernel.  ``affine``: see ``optiland_b200.launch.pupil_affine_infinite_angle``."""
         rays, self._rec = trace_pupil_device(self.device_table, Px, Py, affine, 0, self.num_surfaces, wavelength)
         return rays
+
+    def spot_moments(self, rays=None, pupil=None, center=(0.0, 0.0), dtype=None):
+        """Fused trace + spot/OPD moments (no per-ray output at all); see ``trace_moments_device``."""
+        if pupil is not None:
+            n, dt = pupil[0].numel(), pupil[0].dtype
+        else:
+            n, dt = len(rays), rays.dtype
+        m = trace_moments_device(self.device_table, n, dtype or dt, rays=rays, pupil=pupil, center=center)
+        return moments_to_spot(m, center)
 
     def _get(self, key):
         if self._rec is None:

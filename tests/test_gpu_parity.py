@@ -511,3 +511,40 @@ def test_plugin_cuda_engine_on_optiland_shaped_rays():
     tr = types.SimpleNamespace(**{k: torch.from_numpy(t.rays[k]).cuda() for k in ("x", "y", "z", "L", "M", "N", "i", "w")})
     tr.opd = torch.zeros_like(tr.x)
     assert eng.trace_grad(t.table, torch.zeros((t.table.num_surfaces, AG.GP_COUNT), device="cuda"), tr) is None
+
+
+@pytest.mark.parametrize("name", ["hubble_c4", "dgauss_c2", "tilted_fold"])
+def test_fused_spot_moments_match_records(name):
+    """f-2: the in-kernel moments epilogue (no per-ray output) == the same statistics computed from the
+    reference's records: count of unvignetted rays, centroid, RMS radius about the centroid, OPD mean."""
+    from optiland_b200.launch import pupil_affine_infinite_angle
+    from optiland_b200.trace import SurfaceGroup
+
+    c = Case(name)
+    sg = SurfaceGroup(c.table)
+    rays = _rays(c, torch.float64)
+    x_in = rays.x.clone()
+    s = c.table.surfaces[-1]
+    # reference statistics in the image surface's local frame
+    p = np.stack([c.rec["x"][-1] - s.t[0], c.rec["y"][-1] - s.t[1], c.rec["z"][-1] - s.t[2]])
+    loc = s.R.T @ p
+    i = c.rec["intensity"][-1]
+    m = (i > 0) & np.isfinite(loc[0]) & np.isfinite(loc[1])
+    xs, ys = loc[0][m], loc[1][m]
+    ref_rms = np.sqrt(np.mean((xs - xs.mean()) ** 2 + (ys - ys.mean()) ** 2))
+    center = (float(xs[0]), float(ys[0]))
+    got = sg.spot_moments(rays=rays, center=center)
+    assert torch.equal(rays.x, x_in)  # launch arrays untouched, nothing written per ray
+    assert got["count"] == m.sum()
+    assert got["centroid"][0] == pytest.approx(xs.mean(), abs=1e-10 * c.scale)
+    assert got["centroid"][1] == pytest.approx(ys.mean(), abs=1e-10 * c.scale)
+    assert got["rms_centroid"] == pytest.approx(ref_rms, rel=1e-8)
+    assert got["opd_mean"] == pytest.approx(c.rec["opd"][-1][m].mean(), rel=1e-12)
+    assert got["intensity_sum"] == pytest.approx(i[m].sum(), rel=1e-12)
+    if "x_launch_EPL" in c.z.files:  # pupil mode gives the same numbers
+        sc = {k[9:]: float(c.z[k]) for k in c.z.files if k.startswith("x_launch_")}
+        Px = torch.from_numpy(c.extra("Px")).cuda()
+        Py = torch.from_numpy(c.extra("Py")).cuda()
+        got2 = sg.spot_moments(pupil=(Px, Py, pupil_affine_infinite_angle(sc)), center=center)
+        assert got2["count"] == got["count"]
+        assert got2["rms_centroid"] == pytest.approx(got["rms_centroid"], rel=1e-9)
