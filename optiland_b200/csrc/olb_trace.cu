@@ -368,8 +368,17 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<T, RPT, FEAT>::v)) trace_ker
     }
   }
   if (status != 0 && a.status != nullptr) atomicOr(a.status, status);
+  if (a.tflags & OLB_TF_MOMENTS) {
+    // CTA reduction: warp tree, then one fp64 atomic per moment and warp (uniform branch: launch argument)
+#pragma unroll
+    for (int q = 0; q < 7; ++q) {
+      double v = mom[q];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((threadIdx.x & 31) == 0 && v != 0) atomicAdd(&a.moments[q], v);
+    }
+  }
 }
-
 
 // ---- backward kernel -------------------------------------------------------------------------
 struct BwdArgs {
