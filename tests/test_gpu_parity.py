@@ -531,6 +531,9 @@ def test_fused_spot_moments_match_records(name):
     i = c.rec["intensity"][-1]
     m = (i > 0) & np.isfinite(loc[0]) & np.isfinite(loc[1])
     xs, ys = loc[0][m], loc[1][m]
+    if m.sum() == 0:  # every ray vignetted at the last aperture: all moments stay zero
+        assert sg.spot_moments(rays=rays)["count"] == 0
+        return
     ref_rms = np.sqrt(np.mean((xs - xs.mean()) ** 2 + (ys - ys.mean()) ** 2))
     center = (float(xs[0]), float(ys[0]))
     got = sg.spot_moments(rays=rays, center=center)
