@@ -1,11 +1,13 @@
 // olb_trace.cu -- sm_100a trace kernel + the C ABI of include/olb.h.
 //
-// One persistent kernel walks the WHOLE surface list for a tile of rays: the ray state
-// lives in registers from launch state to image surface, the prepared surface table
-// lives in shared memory (one TMA bulk copy per CTA), and the only HBM traffic is the
-// algorithmic minimum -- 7-8 coalesced vector loads per ray and 8 streaming vector
-// stores per ray per recorded surface.  The reference does the
-// same work with ~190 eager element-wise launches per surface.
+// Forward: ONE kernel walks the WHOLE surface list for a tile of rays: the ray state lives in
+// registers from launch state to image surface, the prepared surface table lives in shared
+// memory (one TMA bulk copy per CTA), and the only HBM traffic is the algorithmic minimum --
+// 8 coalesced vector loads per ray (2 in pupil-launch mode) and 8 streaming vector stores per
+// ray per recorded surface.  The reference does the same work with ~190
+// eager element-wise launches per surface.  Optional in-kernel stages:
+// launch-state generation from pupil coordinates (8f-1), polarization matrices, spot / OPD
+// moments (8f-2).  Backward: one adjoint kernel (trace_bwd_kernel).
 //
 // No tensor cores: there is no contraction on this path.  The roofline is HBM.
 #include <cuda_runtime.h>

@@ -9,7 +9,9 @@
    capability, ``trace_surfaces(surface_group, rays, start, stop) -> bool``; it is installed
    the way the reference's own test registers a foreign backend
    (/root/reference/tests/test_backend.py:79-85): by assignment into ``_backends``;
-2. wraps ``SurfaceGroup.trace`` (optiland/surfaces/surface_group.py:245-257) and ``Surface.trace``
+2. wraps ``RealRayTracer.trace`` (optiland/raytrace/real_ray_tracer.py:58-118) so that a single-field
+   ``Optic.trace`` on an infinite-object angle field generates its launch rays inside the kernel
+   (SURVEY.md 8f-1), and wraps ``SurfaceGroup.trace`` (optiland/surfaces/surface_group.py:245-257) and ``Surface.trace``
    (optiland/surfaces/standard_surface.py:200-215, the per-surface entry the ray aimers use) so that
    they try the capability first and run the reference's own Python body when it declines
    (unsupported surface kind, CPU tensors, ...).  With ``be.grad_mode`` on, the capability runs
@@ -98,6 +100,20 @@ class CudaEngine:
             rays.p = shell.p
         return rec
 
+
+    def accepts_tensor(self, t) -> bool:
+        import torch
+
+        return torch.is_tensor(t) and t.is_cuda and t.dtype in (torch.float32, torch.float64) and t.ndim == 1
+
+    def trace_pupil(self, table: T.SurfaceTable, Px, Py, affine: dict):
+        """Launch state generated in-kernel from the pupil samples (olb_trace_pupil_*).  Returns the record
+        dict; the final state is its last row."""
+        from .trace import trace_pupil_device
+
+        dt = self.device_table(table, Px.device)
+        _, rec = trace_pupil_device(dt, Px.detach().contiguous(), Py.detach().contiguous(), affine, 0, table.num_surfaces)
+        return rec
 
     def trace_grad(self, table: T.SurfaceTable, params, rays):
         """Differentiable trace of Optiland's ``rays``: records are autograd outputs of ``params`` and of
@@ -197,6 +213,32 @@ def _live_params(surfaces, table, wavelength):
     return torch.stack(rows)
 
 
+def _wants_grad(backend, surfaces, rays=None) -> bool:
+    """True when the call must stay differentiable: ``be.grad_mode`` is on, or some tensor involved --
+    a ray array or a live surface parameter -- requires grad even though the global switch is off (the
+    reference's eager ops would build a graph for it regardless)."""
+    if backend.grad_mode.requires_grad:
+        return True
+
+    def rg(v):
+        return bool(getattr(v, "requires_grad", False))
+
+    if rays is not None and any(rg(getattr(rays, k, None)) for k in ("x", "y", "z", "L", "M", "N", "i", "opd")):
+        return True
+    for surf in surfaces:
+        g = getattr(surf, "geometry", None)
+        if g is None:
+            continue
+        cs = g.cs
+        vals = [getattr(g, "radius", None), getattr(g, "k", None), cs.x, cs.y, cs.z, cs.rx, cs.ry, cs.rz]
+        coefs = getattr(g, "coefficients", None)
+        if coefs is not None:
+            vals += [coefs] if hasattr(coefs, "requires_grad") else list(np.ravel(np.asarray(coefs, dtype=object)))
+        if any(rg(v) for v in vals):
+            return True
+    return False
+
+
 def _try_trace(backend, surfaces, rays, table_builder) -> bool:
     """Common body of the two wrappers.  ``surfaces``: the Surface objects to be traced (in
     order); ``table_builder(wavelengths)`` packs them.  Returns False to decline."""
@@ -216,8 +258,8 @@ def _try_trace(backend, surfaces, rays, table_builder) -> bool:
     if not polarized and any(s.coating == T.COAT_FRESNEL for s in table.surfaces):
         return False  # the reference raises for this combination (ray_generator.py:90-94)
     launch_dir = (rays.L, rays.M, rays.N)
-    if backend.grad_mode.requires_grad:
-        # be.grad_mode on: the records must be autograd outputs of the live parameter tensors
+    if _wants_grad(backend, surfaces, rays):
+        # gradients wanted: the records must be autograd outputs of the live parameter tensors
         # (optimization/operand/ray.py:299-342 differentiates through a recorded row).  One custom
         # Function (forward kernel + adjoint kernel) replaces the eager graph; tables outside the
         # adjoint's scope go back to the reference's eager path.
@@ -265,6 +307,63 @@ def install(engine=None, alias: str | None = None) -> None:
 
             return _try_trace(self, surfaces, rays, build)
 
+        def trace_optic(self, tracer, Hx, Hy, wavelength, num_rays, distribution):
+            """``RealRayTracer.trace`` for ONE field with the launch state generated on the device
+            (SURVEY.md 8f-1): returns the traced ``RealRays`` or None to decline.  Covers what
+            ``RayGenerator.generate_rays`` + ``ParaxialRayAimer`` + ``AngleField.get_ray_origins`` do for an
+            infinite-object angle field without apodization / polarization / telecentricity."""
+            import numpy as _np
+            from optiland.distribution import create_distribution
+            from optiland.rays import RealRays
+
+            from .launch import pupil_affine_infinite_angle
+            from .pack import launch_scalars
+
+            optic = tracer.optic
+            if getattr(_tls, "in_reference", False) or _wants_grad(self, list(optic.surfaces.surfaces)):
+                return None
+            try:
+                hx, hy = float(_np.asarray(be.to_numpy(be.atleast_1d(Hx))).reshape(-1)[0]), \
+                    float(_np.asarray(be.to_numpy(be.atleast_1d(Hy))).reshape(-1)[0])
+                single = be.size(be.atleast_1d(Hx)) == 1 and be.size(be.atleast_1d(Hy)) == 1
+            except Exception:
+                return None
+            if not single or optic.polarization != "ignore" or optic.apodization or optic.obj_space_telecentric:
+                return None
+            # the aimer is (re)configured lazily inside generate_rays from this dict (ray_generator.py:67-71)
+            if getattr(tracer, "ray_aiming_config", {}).get("mode", "paraxial") != "paraxial":
+                return None
+            tracer._validate_normalized_coordinates(Hx, Hy, "field")
+            if isinstance(distribution, str):
+                distribution = create_distribution(distribution)
+                distribution.generate_points(num_rays)
+            Px, Py = distribution.x, distribution.y
+            engine = _state["engine"]
+            if not (engine.accepts_tensor(Px) and engine.accepts_tensor(Py)):
+                return None
+            try:
+                sc = launch_scalars(optic, hx, hy)
+                table = pack_surface_group(optic.surfaces, [float(wavelength)])
+            except (UnsupportedSurface, TypeError, ValueError):
+                return None
+            if any(s.coating == T.COAT_FRESNEL for s in table.surfaces):
+                return None
+            rec = engine.trace_pupil(table, Px, Py, pupil_affine_infinite_angle(sc))
+            optic.surfaces.reset()
+            for row, surf in enumerate(optic.surfaces.surfaces):
+                for attr, key in _REC_ATTR:
+                    setattr(surf, attr, rec[key][row])
+            rays = RealRays(rec["x"][-1], rec["y"][-1], rec["z"][-1], rec["L"][-1], rec["M"][-1], rec["N"][-1],
+                            rec["intensity"][-1], be.ones_like(rec["x"][-1]) * wavelength)
+            rays.opd = rec["opd"][-1]
+            _set_pre_interaction_direction(rays, table, rec, 0, table.num_surfaces,
+                                           (rec["L"][0], rec["M"][0], rec["N"][0]))
+            # tail of RealRayTracer.trace (raytrace/real_ray_tracer.py:105-118)
+            if optic.image_surface:
+                last_surface = optic.surfaces[-1]
+                last_surface.material_post.propagation_model.propagate(rays, last_surface.thickness)
+            return rays
+
         def trace_surface(self, surface, rays) -> bool:
             if type(surface).__name__ not in ("Surface", "ImageSurface"):
                 return False
@@ -303,10 +402,23 @@ def install(engine=None, alias: str | None = None) -> None:
                 return rays
         return orig_surface_trace(self, rays)
 
+    from optiland.raytrace.real_ray_tracer import RealRayTracer
+
+    orig_tracer_trace = RealRayTracer.trace
+
+    def tracer_trace(self, Hx, Hy, wavelength, num_rays=100, distribution="hexapolar"):
+        backend = registry.get(be.get_backend())
+        if hasattr(backend, "trace_optic") and _state.get("fuse_launch", True):
+            rays = backend.trace_optic(self, Hx, Hy, wavelength, num_rays, distribution)
+            if rays is not None:
+                return rays
+        return orig_tracer_trace(self, Hx, Hy, wavelength, num_rays, distribution)
+
     SurfaceGroup.trace = group_trace
     Surface.trace = surface_trace
+    RealRayTracer.trace = tracer_trace
     _state.update(installed=True, orig_group_trace=orig_group_trace, orig_surface_trace=orig_surface_trace,
-                  old_backend=old, alias=alias)
+                  orig_tracer_trace=orig_tracer_trace, old_backend=old, alias=alias, fuse_launch=True)
 
 
 def uninstall() -> None:
@@ -317,8 +429,11 @@ def uninstall() -> None:
     from optiland.surfaces.surface_group import SurfaceGroup
 
     registry = be.__getattr__.__globals__["_backends"]
+    from optiland.raytrace.real_ray_tracer import RealRayTracer
+
     SurfaceGroup.trace = _state["orig_group_trace"]
     Surface.trace = _state["orig_surface_trace"]
+    RealRayTracer.trace = _state["orig_tracer_trace"]
     if _state.get("old_backend") is not None:
         registry["torch"] = _state["old_backend"]
     if _state.get("alias"):

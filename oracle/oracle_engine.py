@@ -36,6 +36,29 @@ class OracleEngine:
         return {k: torch.from_numpy(v).to(dt) for k, v in rec.items()}
 
 
+    def accepts_tensor(self, t):
+        import torch
+
+        return torch.is_tensor(t) and t.ndim == 1
+
+    def trace_pupil(self, table, Px, Py, affine):
+        import torch
+
+        from oracle import trace_oracle as O
+
+        self.calls.append(("pupil", table.num_surfaces, int(Px.numel())))
+        px, py = Px.detach().double().numpy(), Py.detach().double().numpy()
+        x0 = affine["origin0"][0] + affine["origin_scale"][0] * px
+        y0 = affine["origin0"][1] + affine["origin_scale"][1] * py
+        d = np.stack([affine["target0"][0] + affine["target_scale"][0] * px - x0,
+                      affine["target0"][1] + affine["target_scale"][1] * py - y0,
+                      np.full_like(px, affine["target0"][2] - affine["origin0"][2])])
+        d = d / np.linalg.norm(d, axis=0)
+        inp = dict(x=x0, y=y0, z=np.full_like(px, affine["origin0"][2]), L=d[0], M=d[1], N=d[2],
+                   i=np.full_like(px, affine.get("intensity", 1.0)), w=np.full_like(px, table.wavelengths[0]))
+        _, rec, status = O.trace(table, inp)
+        return {k: torch.from_numpy(v).to(Px.dtype) for k, v in rec.items()}
+
     def trace_grad(self, table, params, rays):
         """TEST-ONLY differentiable engine: oracle forward + the CPU instantiation of the device adjoint
         (tests/hostcheck) -- the arithmetic of olb_trace_bwd_* without a GPU."""
@@ -46,6 +69,13 @@ class OracleEngine:
         from oracle.hostcheck_api import load, run_backward
 
         hc = load()
+        import ctypes as C
+
+        from optiland_b200 import _lib
+
+        ht = _lib.HostTable(table)  # keep the packed arrays alive across the call
+        if not hc.olbhc_bwd_supported(C.byref(ht.c)):
+            return None  # same scope rule as CudaEngine (OlbDeviceTable.bwd_supported): the plugin declines
         self.calls.append(("grad", table.num_surfaces, int(rays.x.numel())))
         keys = ("x", "y", "z", "L", "M", "N", "i", "opd")
 

@@ -18,6 +18,14 @@ from oracle.ref_import import import_reference  # noqa: E402
 
 import_reference()
 
+if os.environ.get("OLB_SWEEP_NOGRAD") == "1":
+    # the reference's conftest switches grad mode ON for the torch backend; with this switch it stays off
+    # (in both the stock and the plugin run) so the non-differentiable capability paths -- plain trace
+    # and in-kernel launch generation -- are the ones exercised
+    from optiland.backend.torch_backend import GradMode as _GradMode
+
+    _GradMode.enable = lambda self: None
+
 ENGINE = None
 if os.environ.get("OLB_SWEEP_INSTALL") == "1":
     from optiland_b200 import plugin as _P
@@ -30,4 +38,6 @@ if os.environ.get("OLB_SWEEP_INSTALL") == "1":
 def pytest_terminal_summary(terminalreporter):
     if ENGINE is not None:
         n_grad = sum(1 for c in ENGINE.calls if c and c[0] == "grad")
-        terminalreporter.write_line(f"[olb sweep] capability calls: {len(ENGINE.calls)} (differentiable: {n_grad})")
+        n_pupil = sum(1 for c in ENGINE.calls if c and c[0] == "pupil")
+        terminalreporter.write_line(f"[olb sweep] capability calls: {len(ENGINE.calls)} (differentiable: {n_grad}, "
+                                    f"fused launch: {n_pupil})")

@@ -87,6 +87,7 @@ static int run_backward(const OlbTable* tab, int first, int last, int64_t n, T**
                         double* gparams /*n_surf*GP_COUNT, accumulated*/, char* err, int err_len) {
   PrepResult pr = prepare_table(*tab);
   if (!pr.error.empty()) { snprintf(err, err_len, "%s", pr.error.c_str()); return OLB_ERR_TABLE; }
+  if (!pr.bwd_supported) { snprintf(err, err_len, "table outside the adjoint's scope"); return OLB_ERR_UNSUPPORTED; }
   const unsigned char* blob = sizeof(T) == 8 ? pr.blob_f64.data() : pr.blob_f32.data();
   const PrepHeader* H = reinterpret_cast<const PrepHeader*>(blob);
   const PrepSurface<T>* surf = reinterpret_cast<const PrepSurface<T>*>(blob + sizeof(PrepHeader));
@@ -129,6 +130,10 @@ int olbhc_backward_f32(const OlbTable* tab, int first, int last, int64_t n, floa
   return run_backward<float>(tab, first, last, n, ray_in, rec, grec, gin, gparams, err, err_len);
 }
 int olbhc_gp_count() { return GP_COUNT; }
+int olbhc_bwd_supported(const OlbTable* tab) {
+  PrepResult pr = prepare_table(*tab);
+  return pr.error.empty() && pr.bwd_supported ? 1 : 0;
+}
 int olbhc_trace_f64(const OlbTable* tab, int first, int last, int64_t n, double** ray, double** rec, double** l0,
                     double* pmat, int* status, char* err, int err_len) {
   return run<double>(tab, first, last, n, ray, rec, l0, pmat, status, err, err_len);

@@ -67,7 +67,7 @@ def test_optic_trace_goes_through_capability_and_matches_numpy(plugin):
     ref_rec, ref_fin = _numpy_reference(DoubleGauss, trace)
     lens = DoubleGauss()
     rays = trace(lens)
-    assert eng.calls and eng.calls[-1][0] == 13  # whole surface group in ONE engine call
+    assert eng.calls and eng.calls[-1][:2] == ("pupil", 13)  # Optic.trace: launch generated in the engine call
     for k, v in ref_rec.items():
         got = be.to_numpy(getattr(lens.surfaces, k))
         assert got.shape == v.shape
@@ -226,3 +226,24 @@ def test_autograd_through_the_capability_matches_reference_eager_graph(plugin):
     assert got["loss"] == pytest.approx(ref["loss"], rel=1e-9)
     for k in ref:
         assert got[k] == pytest.approx(ref[k], rel=2e-6), k
+
+
+def test_surface_group_trace_capability_when_launch_fusion_is_off(plugin):
+    """With the RealRayTracer.trace wrapper disabled the SurfaceGroup.trace wrapper carries the call
+    (launch rays from the reference's own RayGenerator)."""
+    P, eng, be = plugin
+    from optiland.samples.objectives import DoubleGauss
+
+    P._state["fuse_launch"] = False
+    try:
+        lens = DoubleGauss()
+        rays = lens.trace(Hx=0.0, Hy=0.7, wavelength=0.5876, num_rays=5, distribution="hexapolar")
+        assert eng.calls[-1][0] == 13
+    finally:
+        P._state["fuse_launch"] = True
+    n0 = len(eng.calls)
+    lens2 = DoubleGauss()
+    rays2 = lens2.trace(Hx=0.0, Hy=0.7, wavelength=0.5876, num_rays=5, distribution="hexapolar")
+    assert eng.calls[n0][0] == "pupil"
+    np.testing.assert_allclose(be.to_numpy(rays2.y), be.to_numpy(rays.y), atol=1e-11)
+    np.testing.assert_allclose(be.to_numpy(lens2.surfaces.opd), be.to_numpy(lens.surfaces.opd), atol=1e-11)

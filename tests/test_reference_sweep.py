@@ -19,8 +19,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 FILES = ["test_surface_group.py", "test_rays.py", "test_wavefront.py", "test_operand.py", "analysis/test_spot_reference.py"]
 
 
-def _run(fname, install):
-    env = dict(os.environ, OLB_SWEEP_INSTALL="1" if install else "0", PYTHONPATH=ROOT)
+def _run(fname, install, nograd=False):
+    env = dict(os.environ, OLB_SWEEP_INSTALL="1" if install else "0", PYTHONPATH=ROOT,
+               OLB_SWEEP_NOGRAD="1" if nograd else "0")
     os.makedirs("/tmp/olb_sweep_root", exist_ok=True)
     out = subprocess.run(
         [sys.executable, "-m", "pytest", "-p", "oracle.sweep_plugin", "-p", "no:cacheprovider", "-q", "--no-header",
@@ -28,8 +29,8 @@ def _run(fname, install):
          "-k", "torch and not view and not draw and not plot"],
         cwd="/tmp/olb_sweep_root", env=env, capture_output=True, text=True, timeout=600).stdout
     counts = {k: int(v) for v, k in re.findall(r"(\d+) (passed|failed|error)", out)}
-    calls = re.search(r"capability calls: (\d+)", out)
-    return counts, int(calls.group(1)) if calls else 0
+    calls = re.search(r"capability calls: (\d+) \(differentiable: (\d+), fused launch: (\d+)\)", out)
+    return counts, tuple(int(v) for v in calls.groups()) if calls else (0, 0, 0)
 
 
 @pytest.mark.timeout(900)
@@ -39,4 +40,15 @@ def test_reference_tests_unchanged_with_plugin(fname):
     ours, calls = _run(fname, install=True)
     assert stock.get("passed", 0) > 0
     assert ours == stock, (fname, stock, ours)
-    assert calls > 0, "the capability was never exercised"
+    assert calls[0] > 0 and calls[1] > 0, "the (differentiable) capability was never exercised"
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("fname", ["test_wavefront.py", "analysis/test_spot_reference.py"])
+def test_reference_tests_unchanged_with_plugin_grad_mode_off(fname):
+    """Same with be.grad_mode left off (the reference's conftest normally turns it on): now the plain trace
+    and the fused in-kernel launch generation (RealRayTracer.trace wrapper) carry the calls."""
+    stock, _ = _run(fname, install=False, nograd=True)
+    ours, calls = _run(fname, install=True, nograd=True)
+    assert stock.get("passed", 0) > 0 and ours == stock, (fname, stock, ours)
+    assert calls[1] == 0 and calls[2] > 0, calls
