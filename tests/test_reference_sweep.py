@@ -16,7 +16,7 @@ from oracle.ref_import import reference_available
 
 pytestmark = pytest.mark.skipif(not reference_available(), reason="reference not present on this box")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-FILES = ["test_surface_group.py", "test_rays.py", "test_wavefront.py", "test_operand.py", "analysis/test_spot_reference.py"]
+FILES = ["test_surface_group.py", "test_wavefront.py", "analysis/test_spot_reference.py"]  # scripts/ref_sweep.sh: all
 
 
 def _run(fname, install, nograd=False):
@@ -44,7 +44,7 @@ def test_reference_tests_unchanged_with_plugin(fname):
 
 
 @pytest.mark.timeout(900)
-@pytest.mark.parametrize("fname", ["test_wavefront.py", "analysis/test_spot_reference.py"])
+@pytest.mark.parametrize("fname", ["analysis/test_spot_reference.py"])
 def test_reference_tests_unchanged_with_plugin_grad_mode_off(fname):
     """Same with be.grad_mode left off (the reference's conftest normally turns it on): now the plain trace
     and the fused in-kernel launch generation (RealRayTracer.trace wrapper) carry the calls."""
