@@ -485,6 +485,16 @@ def test_plugin_cuda_engine_on_optiland_shaped_rays():
     cpu_rays = types.SimpleNamespace(**{k: torch.from_numpy(c.rays[k]) for k in ("x", "y", "z", "L", "M", "N", "i", "w")})
     cpu_rays.opd = torch.zeros(c.n, dtype=torch.float64)
     assert not eng.accepts(cpu_rays)  # CPU tensors: the plugin declines -> reference path
+    # --- fused launch (RealRayTracer.trace wrapper) ---
+    from optiland_b200.launch import pupil_affine_infinite_angle
+
+    c2 = Case("dgauss_c2")
+    sc = {k[9:]: float(c2.z[k]) for k in c2.z.files if k.startswith("x_launch_")}
+    Px, Py = torch.from_numpy(c2.extra("Px")).cuda(), torch.from_numpy(c2.extra("Py")).cuda()
+    assert eng.accepts_tensor(Px) and not eng.accepts_tensor(Px.cpu())
+    rec = eng.trace_pupil(c2.table, Px, Py, pupil_affine_infinite_angle(sc))
+    for k in REC:
+        assert max_abs_err(_np(rec[k]), c2.rec[k]) <= 1e-11 * c2.scale, k
     # --- polarized ---
     c = Case("zernike_polarized_c5")
     Pol = type("PolarizedRays", (), {})
