@@ -379,9 +379,9 @@ int olb_trace_host_pupil_f64(const OlbDeviceTable* table, int32_t first, int32_t
  * saved): `rays_in` is the launch state the forward call consumed (x,y,z,L,M,N,i), `rec` its
  * full records for the same [first, last).  grad_rec pointers may be NULL individually
  * (that quantity has zero gradient); grad_rays_in (x,y,z,L,M,N,i,opd) may be NULL.
- * Supported tables (OlbDeviceTable.bwd_supported): unrotated poses, plane / standard /
- * even-asphere geometry, no or radial aperture, no or simple coating, one wavelength;
- * otherwise OLB_ERR_UNSUPPORTED.  Rays that are NaN at a surface carry no gradient.
+ * Supported tables (OlbDeviceTable.bwd_supported): plane / standard / even-asphere geometry, any
+ * pose (tilt angles are constants: only the translation gets a gradient), any aperture tree, no or
+ * simple coating, one wavelength; otherwise OLB_ERR_UNSUPPORTED.  Rays that are NaN at a surface carry no gradient.
  * grad_row_mask: bit r set = record row r of grad_rec may be non-zero (rows with a clear bit
  * are not read); pass ~0 when unknown.
  */

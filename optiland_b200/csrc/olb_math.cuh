@@ -647,8 +647,8 @@ OLB_HD void to_global(const Ray<T>& r, const PrepSurface<T>& S, T& x, T& y, T& z
 //     (valid for the closed-form conic AND the Newton family: no unrolled iterations),
 //   * through the normal via the Hessian of the rotationally symmetric sag,
 //   * through Snell refraction / reflection, OPD, absorption and the pose translation.
-// Supported: unrotated poses, plane / sphere-conic / even asphere, radial (or no) aperture,
-// simple coatings, one wavelength.  Everything is recomputed from the recorded rows (state
+// Supported: plane / sphere-conic / even asphere, any pose (tilt angles are constants of the adjoint),
+// any aperture tree, simple coatings, one wavelength.  Everything is recomputed from the recorded rows (state
 // after surface s-1 and position after surface s): the forward pass stores nothing extra.
 // =============================================================================================
 namespace olb {
@@ -667,12 +667,22 @@ struct Adjoint { T x, y, z, L, M, N, i, opd; };
 template <typename T>
 OLB_HD bool surface_backward(const PrepSurface<T>& S, const T* pool, T xg0, T yg0, T zg0, T L, T M, T N, T i0,
                              T x1g, T y1g, T z1g, Adjoint<T>& a, T* pg) {
+  // (L, M, N are taken by value: they are rotated into the local frame below for tilted poses)
   const T* med = pool + S.media_off;  // one wavelength
   const T n1 = med[MED_N1], u = med[MED_U];
   const T n2 = o_div(n1, u);
-  // local frame (unrotated): p = pg - t
-  const T x0 = xg0 - S.t[0], y0 = yg0 - S.t[1], z0 = zg0 - S.t[2];
-  const T x1 = x1g - S.t[0], y1 = y1g - S.t[1], z1 = z1g - S.t[2];
+  // local frame: p = R^T (pg - t), d = R^T dg  (rotation only for tilted poses; it is a constant of the
+  // adjoint: gradients w.r.t. the tilt ANGLES are not produced, only those w.r.t. the translation t)
+  const bool rot = (S.flags & OLB_SF_ROTATED) != 0;
+  T x0 = xg0 - S.t[0], y0 = yg0 - S.t[1], z0 = zg0 - S.t[2];
+  T x1 = x1g - S.t[0], y1 = y1g - S.t[1], z1 = z1g - S.t[2];
+  if (rot) {
+    const T* R = S.R;
+    T a0 = x0, b0 = y0, c0 = z0, a1 = x1, b1 = y1, c1 = z1, dl = L, dm = M, dn = N;
+    x0 = R[0] * a0 + R[3] * b0 + R[6] * c0; y0 = R[1] * a0 + R[4] * b0 + R[7] * c0; z0 = R[2] * a0 + R[5] * b0 + R[8] * c0;
+    x1 = R[0] * a1 + R[3] * b1 + R[6] * c1; y1 = R[1] * a1 + R[4] * b1 + R[7] * c1; z1 = R[2] * a1 + R[5] * b1 + R[8] * c1;
+    L = R[0] * dl + R[3] * dm + R[6] * dn; M = R[1] * dl + R[4] * dm + R[7] * dn; N = R[2] * dl + R[5] * dm + R[8] * dn;
+  }
   const T dd = o_fma(L, L, o_fma(M, M, N * N));
   const T t = o_div(o_fma(x1 - x0, L, o_fma(y1 - y0, M, (z1 - z0) * N)), dd);
   const T chk = x1 + y1 + z1 + L + M + N + t;
@@ -709,8 +719,14 @@ OLB_HD bool surface_backward(const PrepSurface<T>& S, const T* pool, T xg0, T yg
   const T dot = o_fma(L, nx, o_fma(M, ny, N * nz));
 
   // ---- adjoint of globalize ---------------------------------------------------------------
-  T apx = a.x, apy = a.y, apz = a.z;            // d/d p1
-  pg[GP_TX] += apx; pg[GP_TY] += apy; pg[GP_TZ] += apz;
+  pg[GP_TX] += a.x; pg[GP_TY] += a.y; pg[GP_TZ] += a.z;    // pg1 = R p1 + t
+  T apx = a.x, apy = a.y, apz = a.z;            // d/d p1 (local)
+  if (rot) {
+    const T* R = S.R;
+    apx = R[0] * a.x + R[3] * a.y + R[6] * a.z; apy = R[1] * a.x + R[4] * a.y + R[7] * a.z; apz = R[2] * a.x + R[5] * a.y + R[8] * a.z;
+    T gl = a.L, gm = a.M, gn = a.N;
+    a.L = R[0] * gl + R[3] * gm + R[6] * gn; a.M = R[1] * gl + R[4] * gm + R[7] * gn; a.N = R[2] * gl + R[5] * gm + R[8] * gn;
+  }
   T ai = a.i;
   if (S.coating == OLB_COAT_SIMPLE) ai *= (S.flags & OLB_SF_REFLECT) ? S.coat_r : S.coat_t;
   // ---- adjoint of the interaction ------------------------------------------------------------
@@ -750,7 +766,9 @@ OLB_HD bool surface_backward(const PrepSurface<T>& S, const T* pool, T xg0, T yg
   T at = 0;
   {
     bool inside = true;
-    if (S.flags & OLB_SF_APERTURE) inside = (r2 <= pool[S.aper_off + 1]) && (r2 >= pool[S.aper_off + 2]);
+    if (S.flags & OLB_SF_APERTURE)
+      inside = (S.flags & PSF_APER_RADIAL) ? ((r2 <= pool[S.aper_off + 1]) && (r2 >= pool[S.aper_off + 2]))
+                                           : aperture_inside(pool + S.aper_off, S.aper_len, x1, y1);
     T E = 1;
     if (S.flags & OLB_SF_ABSORBING) { E = o_exp(-med[MED_ALPHA] * t); at -= ai * i0 * med[MED_ALPHA] * E * (inside ? (T)1 : (T)0); }
     ai = inside ? ai * E : (T)0;
@@ -786,6 +804,12 @@ OLB_HD bool surface_backward(const PrepSurface<T>& S, const T* pool, T xg0, T yg
     }
   }
   // ---- localize p0 = pg0 - t -------------------------------------------------------------------------
+  if (rot) {   // back to global: ag = R a_local
+    const T* R = S.R;
+    T u0 = apx, u1 = apy, u2 = apz, v0 = adL, v1 = adM, v2 = adN;
+    apx = R[0] * u0 + R[1] * u1 + R[2] * u2; apy = R[3] * u0 + R[4] * u1 + R[5] * u2; apz = R[6] * u0 + R[7] * u1 + R[8] * u2;
+    adL = R[0] * v0 + R[1] * v1 + R[2] * v2; adM = R[3] * v0 + R[4] * v1 + R[5] * v2; adN = R[6] * v0 + R[7] * v1 + R[8] * v2;
+  }
   pg[GP_TX] -= apx; pg[GP_TY] -= apy; pg[GP_TZ] -= apz;
   a.x = apx; a.y = apy; a.z = apz; a.L = adL; a.M = adM; a.N = adN; a.i = ai;  // a.opd passes through
   return true;

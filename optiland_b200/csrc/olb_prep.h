@@ -423,9 +423,7 @@ static inline PrepResult prepare_table(const OlbTable& tab) {
     const PrepSurface<double>& o = ps[s];
     const bool kind_ok = o.kind == OLB_GEOM_NOOP || o.kind == OLB_GEOM_PLANE || o.kind == OLB_GEOM_STANDARD ||
                          (o.kind == OLB_GEOM_EVEN_ASPHERE && o.n_coef <= 12);
-    const bool aper_ok = !(o.flags & OLB_SF_APERTURE) || (o.flags & PSF_APER_RADIAL);
-    if (!kind_ok || !aper_ok || (o.flags & (OLB_SF_ROTATED | PSF_ROT_IN_G | PSF_ROT_IN_R)) ||
-        o.coating == OLB_COAT_FRESNEL || tab.n_wl != 1)
+    if (!kind_ok || o.coating == OLB_COAT_FRESNEL || tab.n_wl != 1)
       res.bwd_supported = false;
   }
   build_blob<double>(tab, pools, ps, features, res.blob_f64);

@@ -511,8 +511,8 @@ static int trace_bwd_impl(const OlbDeviceTable* wh, int32_t first, int32_t last,
   if (!wh || wh->magic != WS_MAGIC || !wh->workspace)
     return fail(OLB_ERR_INVALID_ARG, "table handle was not initialised by olb_table_upload");
   if (!wh->bwd_supported)
-    return fail(OLB_ERR_UNSUPPORTED, "backward: table has a rotated pose, a non plane/standard/even-asphere "
-                                     "geometry, a non-radial aperture, a Fresnel coating or several wavelengths");
+    return fail(OLB_ERR_UNSUPPORTED, "backward: table not supported (a non plane/standard/even-asphere geometry, "
+                                     "a Fresnel coating or several wavelengths)");
   if (!rays_in || !rec || !gparams) return fail(OLB_ERR_INVALID_ARG, "rays_in, rec and grad_params are required");
   if (first < 0 || last > wh->n_surfaces || first > last) return fail(OLB_ERR_INVALID_ARG, "bad surface range");
   if (n_rays <= 0 || first == last) return OLB_OK;

@@ -196,7 +196,12 @@ def _live_params(surfaces, table, wavelength):
         if spec.kind != T.GEOM_NOOP:
             g = surf.geometry
             cs = g.cs
-            if cs.reference_cs is not None or spec.rotated or spec.kind not in (T.GEOM_PLANE, T.GEOM_STANDARD, T.GEOM_EVEN_ASPHERE):
+            if cs.reference_cs is not None or spec.kind not in (T.GEOM_PLANE, T.GEOM_STANDARD, T.GEOM_EVEN_ASPHERE):
+                return None
+            if spec.rotated and any(getattr(v, "requires_grad", False) for v in (cs.rx, cs.ry, cs.rz)):
+                # tilt angles are constants of the adjoint kernel: keep the reference's eager graph.  (For an
+                # untilted surface the reference skips the rotations altogether -- `if self.rz:`,
+                # coordinate_system.py:84-89 -- so zero angles get no gradient there either.)
                 return None
             vals[GP_TX], vals[GP_TX + 1], vals[GP_TX + 2] = scalar(cs.x, like), scalar(cs.y, like), scalar(cs.z, like)
             if spec.kind != T.GEOM_PLANE:

@@ -304,11 +304,29 @@ def test_autograd_ray_input_gradients_and_unsupported_tables():
     fd = (img_y(h) - img_y(-h)) / (2 * h)
     ok = torch.isfinite(fd) & m
     assert float((gy[ok] - fd[ok]).abs().max()) < 1e-6 * float(fd[ok].abs().max() + 1)
-    # a tilted system is outside the backward kernel's scope: loud error, no silent wrong gradient
-    t = Case("tilted_fold")
+    # a Zernike system is outside the backward kernel's scope: loud error, no silent wrong gradient
+    t = Case("zernike_fringe")
     rr = RealRays(*[t.rays[k] for k in ("x", "y", "z", "L", "M", "N", "i", "w")], dtype=torch.float64)
     with pytest.raises(_lib.OlbError, match="not supported"):
-        AG.trace_differentiable(t.table, torch.zeros((t.table.num_surfaces, AG.GP_COUNT)), rr)
+        AG.trace_differentiable(t.table, AG.table_to_params(t.table), rr)
+    # tilted / decentered poses and aperture trees ARE covered: translation gradient vs finite differences
+    t = Case("tilted_fold")
+
+    def img(params):
+        rr = RealRays(*[t.rays[k] for k in ("x", "y", "z", "L", "M", "N", "i", "w")], dtype=torch.float64)
+        rec = AG.trace_differentiable(t.table, params, rr, rows=(-2,))
+        return (rec["x"] * 0.3 + rec["y"] ** 2 + rec["opd"]).mean()
+
+    p0 = AG.table_to_params(t.table)
+    pr = p0.clone().requires_grad_(True)
+    img(pr).backward()
+    for (s_, q) in ((2, AG.GP_TZ), (1, AG.GP_TX), (2, AG.GP_CURV)):
+        h = 1e-6
+        pa, pb = p0.clone(), p0.clone()
+        pa[s_, q] += h
+        pb[s_, q] -= h
+        fd = (float(img(pa)) - float(img(pb))) / (2 * h)
+        assert pr.grad[s_, q].item() == pytest.approx(fd, rel=2e-5, abs=1e-8), (s_, q)
 
 
 def test_autograd_selected_rows_equals_dense():
@@ -520,7 +538,11 @@ def test_plugin_cuda_engine_on_optiland_shaped_rays():
     t = Case("tilted_fold")
     tr = types.SimpleNamespace(**{k: torch.from_numpy(t.rays[k]).cuda() for k in ("x", "y", "z", "L", "M", "N", "i", "w")})
     tr.opd = torch.zeros_like(tr.x)
-    assert eng.trace_grad(t.table, torch.zeros((t.table.num_surfaces, AG.GP_COUNT), device="cuda"), tr) is None
+    assert eng.trace_grad(t.table, AG.table_to_params(t.table).cuda(), tr) is not None  # tilted poses are in scope
+    z = Case("zernike_fringe")
+    zr = types.SimpleNamespace(**{k: torch.from_numpy(z.rays[k]).cuda() for k in ("x", "y", "z", "L", "M", "N", "i", "w")})
+    zr.opd = torch.zeros_like(zr.x)
+    assert eng.trace_grad(z.table, torch.zeros((z.table.num_surfaces, AG.GP_COUNT), device="cuda"), zr) is None
 
 
 @pytest.mark.parametrize("name", ["hubble_c4", "dgauss_c2", "tilted_fold"])

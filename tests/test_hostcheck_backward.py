@@ -49,7 +49,7 @@ def fd(table, rays, weights, s, what, h):
             - loss_fn(perturbed(table, s, **{what: -h}), rays, weights)) / (2 * h)
 
 
-@pytest.mark.parametrize("name", ["telephoto_c3_tol1e-10", "hubble_c4", "cooke_c1"])
+@pytest.mark.parametrize("name", ["telephoto_c3_tol1e-10", "hubble_c4", "cooke_c1", "tilted_fold"])
 def test_adjoint_matches_finite_differences(hc, name):
     c = Case(name)
     rng = np.random.default_rng(0)
