@@ -404,6 +404,20 @@ int olb_trace_bwd_f64(const OlbDeviceTable* table, int32_t first, int32_t last,
                       const OlbRays* grad_rays_in, double* grad_params, int64_t n_rays,
                       uint64_t grad_row_mask, void* stream);
 
+/*
+ * Huygens-Fresnel PSF summation (reference: NumbaSummation._huygens_fresnel_summation,
+ * optiland/psf/huygens_fresnel_strategies.py:97-160, and TorchSummation.compute :183-273):
+ *     field(P) = sum_Q amp_Q exp(-i k opd_Q) exp(i k R)/R * (1 + (P-Q).Q/(Rp R))/2,  psf = |field|^2
+ * for n_image image points P and n_pupil pupil points Q (all DEVICE fp64 arrays, global coordinates, mm;
+ * opd in mm; k = 2 pi / wavelength_mm).  pupil_amp_im may be NULL (real amplitudes); `field` (2*n_image
+ * doubles, re/im interleaved) may be NULL.  Asynchronous on `stream`.
+ */
+int olb_huygens_psf_f64(const double* image_x, const double* image_y, const double* image_z, int64_t n_image,
+                        const double* pupil_x, const double* pupil_y, const double* pupil_z,
+                        const double* pupil_amp_re, const double* pupil_amp_im, const double* pupil_opd,
+                        int32_t n_pupil, double wavelength_mm, double Rp, double* psf, double* field,
+                        void* stream);
+
 /* Number of kernel launches issued by this process through the library
  * (for bench.py's gpu_launches claim). */
 int64_t olb_launch_count(void);

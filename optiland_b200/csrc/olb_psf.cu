@@ -1,0 +1,100 @@
+// olb_psf.cu -- Huygens-Fresnel PSF summation, sm_100a.
+//
+// Reference: NumbaSummation._huygens_fresnel_summation (optiland/psf/huygens_fresnel_strategies.py:97-160,
+// a prange double loop) and TorchSummation.compute (:183-273, batched eager ops).  For every image point
+// P and every pupil point Q:
+//     field(P) += amp_Q * exp(-i k opd_Q) * exp(i k R) / R * 0.5 (1 + (P - Q).n_Q / R),   n_Q = Q / Rp
+// psf = |field|^2.  O(N_image x N_pupil) transcendental work, no HBM traffic to speak of: the bound is
+// the fp64 pipe.  k R is ~1e6 rad, so the phase must be formed in fp64; it is reduced EXACTLY to a
+// fraction of a turn before the sine / cosine ((R - opd)/lambda - rint(.)), which keeps sincospi on
+// its fast path (sincos(1e6) would take the Payne-Hanek slow path on every pair).
+//
+// One thread per image point; pupil points are staged through shared memory in tiles, each thread
+// streams the tile with all operands in registers.  No tensor cores: the phase is not separable into
+// a GEMM without the Fresnel approximation, which the reference does not make.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/olb.h"
+
+namespace olb {
+int fail_psf(int code, const char* msg);   // olb_trace.cu
+void count_launch();
+
+static constexpr int PSF_BLOCK = 128;
+static constexpr int PSF_TILE = 512;
+
+struct PsfArgs {
+  const double* ix; const double* iy; const double* iz;          // image points
+  const double* px; const double* py; const double* pz;          // pupil points
+  const double* pamp_re; const double* pamp_im; const double* popd;  // amplitude (complex allowed), opd [mm]
+  double* psf; double* field;                                    // |field|^2 and (optional) complex field (re, im interleaved)
+  int64_t n_img; int32_t n_pupil;
+  double inv_lambda, inv_Rp;
+};
+
+__global__ void __launch_bounds__(PSF_BLOCK) huygens_kernel(const __grid_constant__ PsfArgs a) {
+  __shared__ double s_x[PSF_TILE], s_y[PSF_TILE], s_z[PSF_TILE], s_ar[PSF_TILE], s_ai[PSF_TILE], s_opd[PSF_TILE];
+  const int64_t i = (int64_t)blockIdx.x * PSF_BLOCK + threadIdx.x;
+  const bool valid = i < a.n_img;
+  const double x = valid ? a.ix[i] : 0.0, y = valid ? a.iy[i] : 0.0, z = valid ? a.iz[i] : 0.0;
+  double re = 0.0, im = 0.0;
+  for (int base = 0; base < a.n_pupil; base += PSF_TILE) {
+    const int m = min(PSF_TILE, a.n_pupil - base);
+    __syncthreads();
+    for (int j = threadIdx.x; j < m; j += PSF_BLOCK) {
+      s_x[j] = a.px[base + j]; s_y[j] = a.py[base + j]; s_z[j] = a.pz[base + j];
+      s_ar[j] = a.pamp_re[base + j]; s_ai[j] = a.pamp_im ? a.pamp_im[base + j] : 0.0;
+      s_opd[j] = a.popd[base + j];
+    }
+    __syncthreads();
+    if (!valid) continue;
+#pragma unroll 4
+    for (int j = 0; j < m; ++j) {
+      const double u = s_x[j], v = s_y[j], w = s_z[j];
+      const double dx = x - u, dy = y - v, dz = z - w;
+      const double R2 = fma(dx, dx, fma(dy, dy, dz * dz));
+      const double rinv = rsqrt(R2);
+      const double R = R2 * rinv;
+      // phase / 2 pi = (R - opd) / lambda, reduced to [-1/2, 1/2] turns
+      const double turns = (R - s_opd[j]) * a.inv_lambda;
+      const double fr = turns - rint(turns);
+      double sn, cs;
+      sincospi(2.0 * fr, &sn, &cs);
+      const double dot = fma(dx, u, fma(dy, v, dz * w)) * a.inv_Rp;      // (P - Q) . n_Q
+      const double q = 0.5 * (1.0 + dot * rinv) * rinv;                   // obliquity / R
+      const double ar = s_ar[j] * q, ai = s_ai[j] * q;
+      re = fma(ar, cs, fma(-ai, sn, re));
+      im = fma(ar, sn, fma(ai, cs, im));
+    }
+  }
+  if (valid) {
+    a.psf[i] = re * re + im * im;
+    if (a.field) { a.field[2 * i] = re; a.field[2 * i + 1] = im; }
+  }
+}
+
+}  // namespace olb
+
+extern "C" int olb_huygens_psf_f64(const double* image_x, const double* image_y, const double* image_z, int64_t n_image,
+                                   const double* pupil_x, const double* pupil_y, const double* pupil_z,
+                                   const double* pupil_amp_re, const double* pupil_amp_im, const double* pupil_opd,
+                                   int32_t n_pupil, double wavelength_mm, double Rp, double* psf, double* field,
+                                   void* stream) {
+  using namespace olb;
+  if (!image_x || !image_y || !image_z || !pupil_x || !pupil_y || !pupil_z || !pupil_amp_re || !pupil_opd || !psf)
+    return fail_psf(OLB_ERR_INVALID_ARG, "olb_huygens_psf_f64: NULL argument");
+  if (n_image < 0 || n_pupil < 0 || !(wavelength_mm > 0) || Rp == 0)
+    return fail_psf(OLB_ERR_INVALID_ARG, "olb_huygens_psf_f64: bad size / wavelength / Rp");
+  if (n_image == 0) return OLB_OK;
+  PsfArgs a{image_x, image_y, image_z, pupil_x, pupil_y, pupil_z, pupil_amp_re, pupil_amp_im, pupil_opd, psf, field,
+            n_image, n_pupil, 1.0 / wavelength_mm, 1.0 / Rp};
+  const int64_t grid = (n_image + PSF_BLOCK - 1) / PSF_BLOCK;
+  huygens_kernel<<<(unsigned)grid, PSF_BLOCK, 0, (cudaStream_t)stream>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail_psf(OLB_ERR_CUDA, cudaGetErrorString(e));
+  count_launch();
+  return OLB_OK;
+}

@@ -51,6 +51,8 @@ static int fail(int code, const std::string& msg) {
   g_last_error = msg;
   return code;
 }
+int fail_psf(int code, const char* msg) { return fail(code, msg); }   // used by olb_psf.cu
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 #define OLB_CUDA(call)                                                                    \
   do {                                                                                    \
     cudaError_t e__ = (call);                                                             \

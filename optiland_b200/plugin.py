@@ -115,6 +115,17 @@ class CudaEngine:
         _, rec = trace_pupil_device(dt, Px.detach().contiguous(), Py.detach().contiguous(), affine, 0, table.num_surfaces)
         return rec
 
+    def huygens_psf(self, image_x, image_y, image_z, pupil_x, pupil_y, pupil_z, pupil_amp, pupil_opd, wavelength, Rp):
+        """Huygens-Fresnel summation on the GPU (olb_huygens_psf_f64); None to decline (CPU tensors)."""
+        import torch
+
+        from .psf import huygens_fresnel_psf
+
+        if not (torch.is_tensor(image_x) and image_x.is_cuda):
+            return None
+        return huygens_fresnel_psf(image_x, image_y, image_z, pupil_x, pupil_y, pupil_z, pupil_amp, pupil_opd,
+                                   wavelength, Rp).to(image_x.dtype)
+
     def trace_grad(self, table: T.SurfaceTable, params, rays):
         """Differentiable trace of Optiland's ``rays``: records are autograd outputs of ``params`` and of
         the ray tensors.  None if the table is outside olb_trace_bwd_*'s scope."""
@@ -419,11 +430,35 @@ def install(engine=None, alias: str | None = None) -> None:
                 return rays
         return orig_tracer_trace(self, Hx, Hy, wavelength, num_rays, distribution)
 
+    # f-3: the Huygens-Fresnel summation strategy of the torch backend (psf/huygens_fresnel_strategies.py:183-273)
+    from optiland.psf.huygens_fresnel_strategies import TorchSummation
+
+    orig_hf_compute = TorchSummation.compute
+
+    def hf_compute(self, image_x, image_y, image_z, pupil_x, pupil_y, pupil_z, pupil_amp, pupil_opd, wavelength, Rp):
+        engine = _state.get("engine")
+        if engine is not None and hasattr(engine, "huygens_psf") and not self.grad_wanted(
+                image_x, image_y, image_z, pupil_x, pupil_y, pupil_z, pupil_amp, pupil_opd):
+            ix, iy, iz = (be.to_tensor(t, device=self.device) for t in (image_x, image_y, image_z))
+            px, py, pz, po = (be.to_tensor(t, device=self.device) for t in (pupil_x, pupil_y, pupil_z, pupil_opd))
+            out = engine.huygens_psf(ix, iy, iz, px, py, pz, pupil_amp, po, float(wavelength), float(Rp))
+            if out is not None:
+                return out
+        return orig_hf_compute(self, image_x, image_y, image_z, pupil_x, pupil_y, pupil_z, pupil_amp, pupil_opd,
+                               wavelength, Rp)
+
+    def _grad_wanted(self, *tensors):
+        backend = registry.get(be.get_backend())
+        return bool(backend.grad_mode.requires_grad) or any(getattr(t, "requires_grad", False) for t in tensors)
+
+    TorchSummation.grad_wanted = _grad_wanted
+    TorchSummation.compute = hf_compute
     SurfaceGroup.trace = group_trace
     Surface.trace = surface_trace
     RealRayTracer.trace = tracer_trace
     _state.update(installed=True, orig_group_trace=orig_group_trace, orig_surface_trace=orig_surface_trace,
-                  orig_tracer_trace=orig_tracer_trace, old_backend=old, alias=alias, fuse_launch=True)
+                  orig_tracer_trace=orig_tracer_trace, orig_hf_compute=orig_hf_compute, old_backend=old, alias=alias,
+                  fuse_launch=True)
 
 
 def uninstall() -> None:
@@ -439,6 +474,9 @@ def uninstall() -> None:
     SurfaceGroup.trace = _state["orig_group_trace"]
     Surface.trace = _state["orig_surface_trace"]
     RealRayTracer.trace = _state["orig_tracer_trace"]
+    from optiland.psf.huygens_fresnel_strategies import TorchSummation
+
+    TorchSummation.compute = _state["orig_hf_compute"]
     if _state.get("old_backend") is not None:
         registry["torch"] = _state["old_backend"]
     if _state.get("alias"):

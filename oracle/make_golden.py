@@ -355,6 +355,41 @@ def case_more_geometries():
     run_case("chebyshev_range_error", lens, rays, [0.55], expect_error=True)
 
 
+def case_huygens():
+    """f-3: the reference's own Numba Huygens-Fresnel summation on a seeded pupil / image grid, and the
+    HuygensPSF of the Cooke triplet (pupil data + image grid + PSF) end to end."""
+    from optiland.psf import HuygensPSF
+    from optiland.psf.huygens_fresnel_strategies import NumbaSummation
+
+    rng = np.random.default_rng(21)
+    npup = 700
+    r = 9.0 * np.sqrt(rng.random(npup))
+    th = 2 * np.pi * rng.random(npup)
+    Rp = -80.0  # sign: n_Q = Q / Rp must point from the pupil towards the image (obliquity ~ 1)
+    pu, pv = r * np.cos(th), r * np.sin(th)
+    pw = -np.sqrt(Rp**2 - pu**2 - pv**2)  # exit-pupil reference sphere centred on the image point
+    amp = 0.5 + rng.random(npup)
+    opd = 2e-4 * rng.normal(size=npup)  # mm
+    gx, gy = np.meshgrid(np.linspace(-0.02, 0.02, 24), np.linspace(-0.02, 0.02, 24))
+    gz = np.zeros_like(gx)
+    psf = NumbaSummation().compute(gx, gy, gz, pu, pv, pw, amp, opd, 0.55e-3, Rp)
+    out = dict(image_x=gx, image_y=gy, image_z=gz, pupil_x=pu, pupil_y=pv, pupil_z=pw, pupil_amp=amp, pupil_opd=opd,
+               wavelength=0.55e-3, Rp=Rp, psf=np.array(psf))
+    # system level: Cooke triplet, field (0, 0.7), 32 x 32 pupil, 32 x 32 image
+    lens = CookeTriplet()
+    h = HuygensPSF(lens, field=(0, 0.7), wavelength=0.55, num_rays=32, image_size=32)
+    data = h.get_data((0, 0.7), 0.55)
+    ix, iy, iz = h._get_image_coordinates()
+    out.update(sys_image_x=np.array(ix), sys_image_y=np.array(iy), sys_image_z=np.array(iz),
+               sys_pupil_x=np.array(data.pupil_x), sys_pupil_y=np.array(data.pupil_y), sys_pupil_z=np.array(data.pupil_z),
+               sys_pupil_amp=np.sqrt(np.array(data.intensity)), sys_pupil_opd=np.array(data.opd) * 0.55e-3,
+               sys_Rp=float(data.radius), sys_norm=float(h.normalization), sys_psf=np.array(h.psf))
+    path = os.path.join(OUT, "huygens_psf_ref.npz")
+    np.savez_compressed(path, **out)
+    print("huygens_psf_ref", psf.shape, float(psf.max()), "system strehl-scaled peak", float(np.max(h.psf)),
+          f"{os.path.getsize(path) / 1024:.0f} KiB")
+
+
 def main():
     be.set_backend("numpy")
     case_cooke()
@@ -366,6 +401,7 @@ def main():
     case_tilted()
     case_misc()
     case_more_geometries()
+    case_huygens()
     case_autograd()
 
 
@@ -408,7 +444,10 @@ def case_autograd():
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "more":
+    if len(sys.argv) > 1 and sys.argv[1] == "huygens":
+        be.set_backend("numpy")
+        case_huygens()
+    elif len(sys.argv) > 1 and sys.argv[1] == "more":
         be.set_backend("numpy")
         case_more_geometries()
     elif len(sys.argv) > 1 and sys.argv[1] == "autograd":

@@ -59,6 +59,17 @@ class OracleEngine:
         _, rec, status = O.trace(table, inp)
         return {k: torch.from_numpy(v).to(Px.dtype) for k, v in rec.items()}
 
+    def huygens_psf(self, image_x, image_y, image_z, pupil_x, pupil_y, pupil_z, pupil_amp, pupil_opd, wavelength, Rp):
+        import torch
+
+        from oracle import trace_oracle as O
+
+        self.calls.append(("psf", int(image_x.numel()), int(pupil_x.numel())))
+        amp = pupil_amp.detach().numpy() if torch.is_tensor(pupil_amp) else np.asarray(pupil_amp)
+        psf, _ = O.huygens_fresnel_psf(*[t.detach().double().numpy() for t in (image_x, image_y, image_z, pupil_x, pupil_y, pupil_z)],
+                                       amp, pupil_opd.detach().double().numpy(), wavelength, Rp)
+        return torch.from_numpy(psf).to(image_x.dtype)
+
     def trace_grad(self, table, params, rays):
         """TEST-ONLY differentiable engine: oracle forward + the CPU instantiation of the device adjoint
         (tests/hostcheck) -- the arithmetic of olb_trace_bwd_* without a GPU."""

@@ -744,3 +744,27 @@ def trace(table: T.SurfaceTable, rays: dict, first: int = 0, last: int | None = 
         out["p"] = P
     records = {k: (np.stack(v) if v else np.zeros((0, x.size))) for k, v in rec.items()}
     return out, records, status[0]
+
+
+# --------------------------------------------------------------------------
+# Huygens-Fresnel PSF summation (consumer of the path)
+# --------------------------------------------------------------------------
+
+def huygens_fresnel_psf(image_x, image_y, image_z, pupil_x, pupil_y, pupil_z, pupil_amp, pupil_opd, wavelength, Rp):
+    """optiland/psf/huygens_fresnel_strategies.py:97-160 (NumbaSummation._huygens_fresnel_summation),
+    vectorised over the pupil for each image point; returns (psf, field)."""
+    k = 2.0 * np.pi / wavelength
+    shape = np.shape(image_x)
+    ix, iy, iz = (np.asarray(a, dtype=np.float64).ravel() for a in (image_x, image_y, image_z))
+    u, v, w = (np.asarray(a, dtype=np.float64).ravel() for a in (pupil_x, pupil_y, pupil_z))
+    amp = np.asarray(pupil_amp).ravel()
+    phase = np.exp(-1j * k * np.asarray(pupil_opd, dtype=np.float64).ravel())
+    field = np.zeros(ix.size, dtype=np.complex128)
+    for p in range(ix.size):
+        dx, dy, dz = ix[p] - u, iy[p] - v, iz[p] - w
+        R = np.sqrt(dx * dx + dy * dy + dz * dz)
+        wave = np.exp(1j * k * R) / R
+        dot = dx * (u / Rp) + dy * (v / Rp) + dz * (w / Rp)
+        field[p] = np.sum(amp * phase * wave * (0.5 * (1.0 + dot / R)))
+    field = field.reshape(shape)
+    return np.abs(field) ** 2, field

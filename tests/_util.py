@@ -13,7 +13,7 @@ REC = ("x", "y", "z", "L", "M", "N", "intensity", "opd")
 RAY_IN = ("x", "y", "z", "L", "M", "N", "i", "w")
 
 ALL_CASES = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
-                   if not p.endswith("_grad.npz"))
+                   if not p.endswith("_grad.npz") and not p.endswith("_ref.npz"))
 POLARIZED_CASES = [c for c in ALL_CASES if "polarized" in c]
 ERROR_CASES = [c for c in ALL_CASES if "error" in c]
 REAL_CASES = [c for c in ALL_CASES if c not in POLARIZED_CASES and c not in ERROR_CASES]

@@ -247,3 +247,19 @@ def test_surface_group_trace_capability_when_launch_fusion_is_off(plugin):
     assert eng.calls[n0][0] == "pupil"
     np.testing.assert_allclose(be.to_numpy(rays2.y), be.to_numpy(rays.y), atol=1e-11)
     np.testing.assert_allclose(be.to_numpy(lens2.surfaces.opd), be.to_numpy(lens.surfaces.opd), atol=1e-11)
+
+
+def test_huygens_psf_strategy_is_routed_through_the_engine(plugin):
+    """f-3: HuygensPSF on the torch backend calls the capability instead of TorchSummation's eager loop;
+    same Strehl-normalised PSF as the reference's NumPy/Numba path."""
+    P, eng, be = plugin
+    from optiland.psf import HuygensPSF
+    from optiland.samples.objectives import CookeTriplet
+
+    be.set_backend("numpy")
+    ref = np.array(HuygensPSF(CookeTriplet(), field=(0, 0.7), wavelength=0.55, num_rays=24, image_size=16).psf)
+    be.set_backend("torch")
+    n0 = len(eng.calls)
+    got = HuygensPSF(CookeTriplet(), field=(0, 0.7), wavelength=0.55, num_rays=24, image_size=16).psf
+    assert any(c[0] == "psf" for c in eng.calls[n0:])
+    np.testing.assert_allclose(be.to_numpy(got), ref, rtol=0, atol=1e-8 * ref.max())
