@@ -410,7 +410,8 @@ int olb_trace_bwd_f64(const OlbDeviceTable* table, int32_t first, int32_t last,
  *     field(P) = sum_Q amp_Q exp(-i k opd_Q) exp(i k R)/R * (1 + (P-Q).Q/(Rp R))/2,  psf = |field|^2
  * for n_image image points P and n_pupil pupil points Q (all DEVICE fp64 arrays, global coordinates, mm;
  * opd in mm; k = 2 pi / wavelength_mm).  pupil_amp_im may be NULL (real amplitudes); `field` (2*n_image
- * doubles, re/im interleaved) may be NULL.  Asynchronous on `stream`.
+ * doubles, re/im interleaved) may be NULL; when given it also serves as scratch so that small images can
+ * split the pupil sum over more CTAs.  Asynchronous on `stream`.
  */
 int olb_huygens_psf_f64(const double* image_x, const double* image_y, const double* image_z, int64_t n_image,
                         const double* pupil_x, const double* pupil_y, const double* pupil_z,

@@ -33,6 +33,7 @@ struct PsfArgs {
   double* psf; double* field;                                    // |field|^2 and (optional) complex field (re, im interleaved)
   int64_t n_img; int32_t n_pupil;
   double inv_lambda, inv_Rp;
+  int32_t pupil_per_split;   // gridDim.y > 1: each y-slice of the grid sums its own pupil range into `field`
 };
 
 __global__ void __launch_bounds__(PSF_BLOCK) huygens_kernel(const __grid_constant__ PsfArgs a) {
@@ -41,8 +42,10 @@ __global__ void __launch_bounds__(PSF_BLOCK) huygens_kernel(const __grid_constan
   const bool valid = i < a.n_img;
   const double x = valid ? a.ix[i] : 0.0, y = valid ? a.iy[i] : 0.0, z = valid ? a.iz[i] : 0.0;
   double re = 0.0, im = 0.0;
-  for (int base = 0; base < a.n_pupil; base += PSF_TILE) {
-    const int m = min(PSF_TILE, a.n_pupil - base);
+  const int p_lo = blockIdx.y * a.pupil_per_split;
+  const int p_hi = min(a.n_pupil, p_lo + a.pupil_per_split);
+  for (int base = p_lo; base < p_hi; base += PSF_TILE) {
+    const int m = min(PSF_TILE, p_hi - base);
     __syncthreads();
     for (int j = threadIdx.x; j < m; j += PSF_BLOCK) {
       s_x[j] = a.px[base + j]; s_y[j] = a.py[base + j]; s_z[j] = a.pz[base + j];
@@ -71,9 +74,19 @@ __global__ void __launch_bounds__(PSF_BLOCK) huygens_kernel(const __grid_constan
     }
   }
   if (valid) {
-    a.psf[i] = re * re + im * im;
-    if (a.field) { a.field[2 * i] = re; a.field[2 * i + 1] = im; }
+    if (gridDim.y > 1) {   // partial sums of this pupil slice; |.|^2 is taken by finish_kernel
+      atomicAdd(&a.field[2 * i], re);
+      atomicAdd(&a.field[2 * i + 1], im);
+    } else {
+      a.psf[i] = re * re + im * im;
+      if (a.field) { a.field[2 * i] = re; a.field[2 * i + 1] = im; }
+    }
   }
+}
+
+__global__ void finish_kernel(const double* __restrict__ field, double* __restrict__ psf, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) psf[i] = field[2 * i] * field[2 * i] + field[2 * i + 1] * field[2 * i + 1];
 }
 
 }  // namespace olb
@@ -90,9 +103,26 @@ extern "C" int olb_huygens_psf_f64(const double* image_x, const double* image_y,
     return fail_psf(OLB_ERR_INVALID_ARG, "olb_huygens_psf_f64: bad size / wavelength / Rp");
   if (n_image == 0) return OLB_OK;
   PsfArgs a{image_x, image_y, image_z, pupil_x, pupil_y, pupil_z, pupil_amp_re, pupil_amp_im, pupil_opd, psf, field,
-            n_image, n_pupil, 1.0 / wavelength_mm, 1.0 / Rp};
+            n_image, n_pupil, 1.0 / wavelength_mm, 1.0 / Rp, n_pupil};
   const int64_t grid = (n_image + PSF_BLOCK - 1) / PSF_BLOCK;
-  huygens_kernel<<<(unsigned)grid, PSF_BLOCK, 0, (cudaStream_t)stream>>>(a);
+  // Few image points (a 128 x 128 PSF is 128 CTAs on 148 SMs): split the pupil sum over gridDim.y so that
+  // ~8 CTAs per SM are in flight; needs the caller's `field` buffer for the partial sums.
+  int splits = 1;
+  if (field && grid < 8 * 148) {
+    splits = (int)((8 * 148 + grid - 1) / grid);
+    const int max_splits = (n_pupil + PSF_TILE - 1) / PSF_TILE;
+    if (splits > max_splits) splits = max_splits;
+    if (splits > 64) splits = 64;
+    if (splits < 1) splits = 1;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (splits > 1) {
+    a.pupil_per_split = ((n_pupil + splits - 1) / splits + PSF_TILE - 1) / PSF_TILE * PSF_TILE;
+    splits = (n_pupil + a.pupil_per_split - 1) / a.pupil_per_split;
+    cudaMemsetAsync(field, 0, (size_t)n_image * 2 * sizeof(double), st);
+  }
+  huygens_kernel<<<dim3((unsigned)grid, (unsigned)splits), PSF_BLOCK, 0, st>>>(a);
+  if (splits > 1) finish_kernel<<<(unsigned)((n_image + 255) / 256), 256, 0, st>>>(field, psf, n_image);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail_psf(OLB_ERR_CUDA, cudaGetErrorString(e));
   count_launch();

@@ -32,13 +32,13 @@ def huygens_fresnel_psf(image_x, image_y, image_z, pupil_x, pupil_y, pupil_z, pu
         ar, ai = amp.to(torch.float64).contiguous(), None
     n_img, n_pup = ix.numel(), px.numel()
     psf = torch.empty(n_img, dtype=torch.float64, device=device)
-    field = torch.empty(2 * n_img, dtype=torch.float64, device=device) if return_field else None
+    field = torch.empty(2 * n_img, dtype=torch.float64, device=device)  # also the scratch of the split-pupil mode
     with torch.cuda.device(device):
         stream = torch.cuda.current_stream(device).cuda_stream
         rc = lib.olb_huygens_psf_f64(ix.data_ptr(), iy.data_ptr(), iz.data_ptr(), n_img, px.data_ptr(), py.data_ptr(),
                                      pz.data_ptr(), ar.data_ptr(), ai.data_ptr() if ai is not None else None,
                                      popd.data_ptr(), n_pup, float(wavelength), float(Rp), psf.data_ptr(),
-                                     field.data_ptr() if field is not None else None, C.c_void_p(stream))
+                                     field.data_ptr(), C.c_void_p(stream))
     _lib.check(rc, "olb_huygens_psf_f64")
     shape = tuple(image_x.shape) if hasattr(image_x, "shape") else (n_img,)
     psf = psf.reshape(shape)
