@@ -583,3 +583,35 @@ def test_fused_spot_moments_match_records(name):
         got2 = sg.spot_moments(pupil=(Px, Py, pupil_affine_infinite_angle(sc)), center=center)
         assert got2["count"] == got["count"]
         assert got2["rms_centroid"] == pytest.approx(got["rms_centroid"], rel=1e-9)
+
+
+def test_record_offsets_beyond_2_31_elements():
+    """Maximum sizes: 170 M rays x 13 record rows = 2.2e9 elements per quantity (71 GB of records in fp32):
+    every offset computation must be 64-bit.  Rays are copies of the golden rays, so the LAST rows (largest
+    offsets) are checked entry-for-entry against a small trace of the same rays."""
+    from optiland_b200.trace import RealRays, SurfaceGroup
+
+    free, _ = torch.cuda.mem_get_info()
+    if free < 100 * 2**30:
+        pytest.skip("needs ~80 GB of free HBM")
+    c = Case("dgauss_c2")
+    n = 170_000_000
+    reps = n // c.n + 1
+    base = {k: torch.from_numpy(c.rays[k].astype(np.float32)).cuda() for k in c.rays}
+    big = {k: v.repeat(reps)[:n].contiguous() for k, v in base.items()}
+    sg = SurfaceGroup(c.table)
+    rays = RealRays(*[big[k] for k in ("x", "y", "z", "L", "M", "N", "i", "w")], dtype=torch.float32)
+    sg.trace(rays)
+    small = SurfaceGroup(c.table)
+    sr = RealRays(*[base[k] for k in ("x", "y", "z", "L", "M", "N", "i", "w")], dtype=torch.float32)
+    small.trace(sr)
+    assert sg.x.shape == (13, n)
+    tail = slice(n - 3 * c.n, n)
+    idx = torch.arange(n - 3 * c.n, n, device="cuda") % c.n
+    for k in REC:
+        got = getattr(sg, k)
+        assert torch.equal(got[-1, tail], getattr(small, k)[-1][idx]), k
+        assert torch.equal(got[0, :c.n], getattr(small, k)[0]), k
+        assert torch.equal(got[7, n // 2: n // 2 + 1000], getattr(small, k)[7][torch.arange(n // 2, n // 2 + 1000, device="cuda") % c.n]), k
+    del sg, rays, big
+    torch.cuda.empty_cache()
