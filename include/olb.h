@@ -106,6 +106,7 @@ extern "C" {
 /* ---- trace flags (argument `flags` of olb_trace_*) ------------------------ */
 #define OLB_TF_POLARIZED   (1u << 0)  /* rays carry a 3x3 complex P matrix (OlbRays.p)  */
 #define OLB_TF_POL_IDENTITY (1u << 2) /* with POLARIZED: P starts as identity, rays.p is output only */
+#define OLB_TF_SHARED_INPUT (1u << 4) /* batched trace: every system traces the SAME rays_per_system launch rays */
 #define OLB_TF_MOMENTS     (1u << 3)  /* accumulate OlbMoments over the traced batch (fused analysis
                                          epilogue); see olb_trace_moments_*          */
 #define OLB_TF_NO_FINAL    (1u << 1)  /* do not write the final state back into rays.x..opd:
@@ -249,6 +250,10 @@ typedef struct OlbDeviceTable {
   int32_t off_f32, bytes_f32;   /* fp32 blob inside workspace */
   int32_t bwd_supported;        /* 1 if olb_trace_bwd_* covers every surface of the table */
   int32_t bwd_slots;            /* gradient accumulator slots per thread (backward kernel)   */
+  int32_t n_systems;            /* 1, or the number of systems of a batched table            */
+  int32_t stride_f64;           /* bytes between consecutive systems' fp64 / fp32 blobs      */
+  int32_t stride_f32;
+  int32_t reserved;
 } OlbDeviceTable;
 
 /* Bytes of device workspace needed for `table` (< 256 KiB). Negative = error code. */
@@ -403,6 +408,41 @@ int olb_trace_bwd_f64(const OlbDeviceTable* table, int32_t first, int32_t last,
                       const OlbRays* rays_in, const OlbRecords* rec, const OlbRecords* grad_rec,
                       const OlbRays* grad_rays_in, double* grad_params, int64_t n_rays,
                       uint64_t grad_row_mask, void* stream);
+
+/*
+ * Batched many-systems trace: B perturbed copies of one template system -- the shape of
+ * tolerancing Monte-Carlo runs (optiland/tolerancing/monte_carlo.py) and of the BatchedRayEvaluator
+ * (optiland/optimization/batched_evaluator.py:277-705), which the reference evaluates as B separate small
+ * traces.  `params` (HOST): n_systems x n_surfaces blocks of OLB_BP_COUNT doubles with the ABSOLUTE values
+ *   [OLB_BP_TX..TZ] pose translation and [OLB_BP_R .. +8] row-major rotation (the effective transform,
+ *   coordinate_system.py:145-165, as in OlbSurface.t / .R), [OLB_BP_CURV] 1/radius, [OLB_BP_CONIC], [OLB_BP_N1], [OLB_BP_N2],
+ *   [OLB_BP_COEF + j] even-asphere coefficients;
+ * everything else (kinds, apertures, coatings, tolerances) comes from `template_table` (one wavelength).
+ * olb_trace_batch_* traces system b over the ray segment [b * rays_per_system, (b+1) * rays_per_system): ONE
+ * launch, grid.y = system, each CTA stages its own system's table.  With OLB_TF_SHARED_INPUT (+ NO_FINAL) all
+ * systems read the same rays_per_system launch rays.  rec rows have n_systems * rays_per_system columns;
+ * `moments` (optional) receives 8 doubles PER SYSTEM (see olb_trace_moments_*).
+ */
+#define OLB_BP_TX 0
+#define OLB_BP_TY 1
+#define OLB_BP_TZ 2
+#define OLB_BP_R 3
+#define OLB_BP_CURV 12
+#define OLB_BP_CONIC 13
+#define OLB_BP_N1 14
+#define OLB_BP_N2 15
+#define OLB_BP_COEF 16
+#define OLB_BP_MAX_COEF 12
+#define OLB_BP_COUNT (OLB_BP_COEF + OLB_BP_MAX_COEF)
+int64_t olb_table_batch_workspace_bytes(const OlbTable* template_table, int32_t n_systems);
+int olb_table_upload_batch(const OlbTable* template_table, const double* params, int32_t n_systems,
+                           void* workspace, int64_t workspace_bytes, void* stream, OlbDeviceTable* out);
+int olb_trace_batch_f32(const OlbDeviceTable* table, int32_t first, int32_t last, const OlbRays* rays,
+                        const OlbRecords* rec, int64_t rays_per_system, uint32_t flags,
+                        const double center[2], double* moments, int32_t* status, void* stream);
+int olb_trace_batch_f64(const OlbDeviceTable* table, int32_t first, int32_t last, const OlbRays* rays,
+                        const OlbRecords* rec, int64_t rays_per_system, uint32_t flags,
+                        const double center[2], double* moments, int32_t* status, void* stream);
 
 /*
  * Huygens-Fresnel PSF summation (reference: NumbaSummation._huygens_fresnel_summation,

@@ -23,6 +23,10 @@ ERRORS = {-1: "OLB_ERR_INVALID_ARG", -2: "OLB_ERR_UNSUPPORTED", -3: "OLB_ERR_CUD
 TF_POLARIZED = 1 << 0
 TF_NO_FINAL = 1 << 1
 TF_POL_IDENTITY = 1 << 2
+TF_MOMENTS = 1 << 3
+TF_SHARED_INPUT = 1 << 4
+BP_TX, BP_TY, BP_TZ, BP_R, BP_CURV, BP_CONIC, BP_N1, BP_N2, BP_COEF, BP_MAX_COEF = 0, 1, 2, 3, 12, 13, 14, 15, 16, 12
+BP_COUNT = BP_COEF + BP_MAX_COEF
 GP_TX, GP_TY, GP_TZ, GP_CURV, GP_CONIC, GP_N1, GP_N2, GP_COEF, GP_MAX_COEF = 0, 1, 2, 3, 4, 5, 6, 7, 12
 GP_COUNT = GP_COEF + GP_MAX_COEF
 
@@ -56,6 +60,7 @@ class OlbDeviceTable(C.Structure):
         ("features", C.c_uint32), ("n_surfaces", C.c_int32), ("n_wl", C.c_int32),
         ("off_f64", C.c_int32), ("bytes_f64", C.c_int32), ("off_f32", C.c_int32),
         ("bytes_f32", C.c_int32), ("bwd_supported", C.c_int32), ("bwd_slots", C.c_int32),
+        ("n_systems", C.c_int32), ("stride_f64", C.c_int32), ("stride_f32", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -91,6 +96,13 @@ SYMBOLS = {
     "olb_trace_host_pupil_f64": (C.c_int, [_P(OlbDeviceTable), C.c_int32, C.c_int32, _P(OlbPupilLaunch), _P(OlbRays),
                                            _P(OlbRecords), C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
                                            C.c_uint32, C.c_void_p]),
+    "olb_table_batch_workspace_bytes": (C.c_int64, [_P(OlbTable), C.c_int32]),
+    "olb_table_upload_batch": (C.c_int, [_P(OlbTable), C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p,
+                                         _P(OlbDeviceTable)]),
+    "olb_trace_batch_f32": (C.c_int, [_P(OlbDeviceTable), C.c_int32, C.c_int32, _P(OlbRays), _P(OlbRecords), C.c_int64,
+                                      C.c_uint32, _P(C.c_double), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "olb_trace_batch_f64": (C.c_int, [_P(OlbDeviceTable), C.c_int32, C.c_int32, _P(OlbRays), _P(OlbRecords), C.c_int64,
+                                      C.c_uint32, _P(C.c_double), C.c_void_p, C.c_void_p, C.c_void_p]),
     "olb_huygens_psf_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_double,
                                       C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -227,6 +227,11 @@ static inline PrepResult prepare_table(const OlbTable& tab) {
     if (in.kind < OLB_GEOM_NOOP || in.kind > OLB_GEOM_TOROIDAL) { res.error = "unknown geometry kind"; return res; }
 
     // ---- pose --------------------------------------------------------------
+    if (in.kind != OLB_GEOM_NOOP) {
+      bool finite = std::isfinite(in.t[0]) && std::isfinite(in.t[1]) && std::isfinite(in.t[2]);
+      for (int i = 0; i < 9; ++i) finite = finite && std::isfinite(in.R[i]);
+      if (!finite) { res.error = "non-finite surface pose"; return res; }
+    }
     double Rt[9];
     mat3_transpose(in.R, Rt);
     for (int i = 0; i < 9; ++i) { o.R[i] = in.R[i]; o.Ag[i] = Rt[i]; }

@@ -80,6 +80,11 @@ struct TraceArgs {
   // fused moments epilogue (OLB_TF_MOMENTS)
   double* moments;
   double mcx, mcy;
+  // batched systems (olb_trace_batch_*): blockIdx.y = system, its table at blob + y * blob_stride, its rays
+  // are the segment [y * sys_rays, (y+1) * sys_rays); shared_in: every system reads the SAME sys_rays inputs
+  int64_t sys_rays;
+  int32_t blob_stride;
+  int32_t shared_in;
 };
 
 // ---- vector access helpers -------------------------------------------------------------
@@ -167,7 +172,8 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<T, RPT, FEAT>::v)) trace_ker
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
   unsigned char* tab = smem + 16;
-  stage_table(tab, a.blob, (uint32_t)a.blob_bytes, bar);
+  const int sys = blockIdx.y;                                   // 0 unless batched
+  stage_table(tab, a.blob + (size_t)sys * (size_t)a.blob_stride, (uint32_t)a.blob_bytes, bar);
 
   const PrepHeader* H = reinterpret_cast<const PrepHeader*>(tab);
   const PrepSurface<T>* surf = reinterpret_cast<const PrepSurface<T>*>(tab + sizeof(PrepHeader));
@@ -175,7 +181,8 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<T, RPT, FEAT>::v)) trace_ker
   const int n_wl = H->n_wl;
   const T* wl = pool + H->pad[0];
 
-  const int64_t n = a.n_rays;
+  const int64_t n = a.sys_rays > 0 ? a.sys_rays : a.n_rays;     // rays of THIS system
+  const int64_t seg = (int64_t)sys * n;                         // where its outputs start
   const int64_t per_tile = (int64_t)BLOCK * RPT;
   const int64_t n_tiles = (n + per_tile - 1) / per_tile;
   const int first = a.first, last = a.last;
@@ -183,9 +190,11 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<T, RPT, FEAT>::v)) trace_ker
   double mom[7] = {0, 0, 0, 0, 0, 0, 0};   // OLB_TF_MOMENTS: per-thread partial sums
 
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t base = (tile * BLOCK + threadIdx.x) * RPT;
-    if (base >= n) continue;
-    const int valid = (n - base) >= RPT ? RPT : (int)(n - base);
+    const int64_t local = (tile * BLOCK + threadIdx.x) * RPT;
+    if (local >= n) continue;
+    const int valid = (n - local) >= RPT ? RPT : (int)(n - local);
+    const int64_t base = seg + local;                           // output index
+    const int64_t bin = a.shared_in ? local : base;             // input index
 
     Ray<T> r[RPT];
     {
@@ -193,42 +202,42 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<T, RPT, FEAT>::v)) trace_ker
       if (a.px != nullptr) {
         // launch state generated from the pupil point: 2 loads instead of 8
         T pv[RPT];
-        load_rays<T, RPT>((const T*)a.px, base, valid, pv);
-        load_rays<T, RPT>((const T*)a.py, base, valid, v);
+        load_rays<T, RPT>((const T*)a.px, bin, valid, pv);
+        load_rays<T, RPT>((const T*)a.py, bin, valid, v);
         const T o0[3] = {(T)a.lo0[0], (T)a.lo0[1], (T)a.lo0[2]}, os[2] = {(T)a.los[0], (T)a.los[1]};
         const T t0[3] = {(T)a.lt0[0], (T)a.lt0[1], (T)a.lt0[2]}, ts[2] = {(T)a.lts[0], (T)a.lts[1]};
 #pragma unroll
         for (int k = 0; k < RPT; ++k) pupil_launch<T>(r[k], pv[k], v[k], o0, os, t0, ts, (T)a.linten);
       } else {
-      load_rays<T, RPT>((const T*)a.x, base, valid, v);
+      load_rays<T, RPT>((const T*)a.x, bin, valid, v);
 #pragma unroll
       for (int k = 0; k < RPT; ++k) r[k].x = v[k];
-      load_rays<T, RPT>((const T*)a.y, base, valid, v);
+      load_rays<T, RPT>((const T*)a.y, bin, valid, v);
 #pragma unroll
       for (int k = 0; k < RPT; ++k) r[k].y = v[k];
-      load_rays<T, RPT>((const T*)a.z, base, valid, v);
+      load_rays<T, RPT>((const T*)a.z, bin, valid, v);
 #pragma unroll
       for (int k = 0; k < RPT; ++k) r[k].z = v[k];
-      load_rays<T, RPT>((const T*)a.L, base, valid, v);
+      load_rays<T, RPT>((const T*)a.L, bin, valid, v);
 #pragma unroll
       for (int k = 0; k < RPT; ++k) r[k].L = v[k];
-      load_rays<T, RPT>((const T*)a.M, base, valid, v);
+      load_rays<T, RPT>((const T*)a.M, bin, valid, v);
 #pragma unroll
       for (int k = 0; k < RPT; ++k) r[k].M = v[k];
-      load_rays<T, RPT>((const T*)a.N, base, valid, v);
+      load_rays<T, RPT>((const T*)a.N, bin, valid, v);
 #pragma unroll
       for (int k = 0; k < RPT; ++k) r[k].N = v[k];
-      load_rays<T, RPT>((const T*)a.i, base, valid, v);
+      load_rays<T, RPT>((const T*)a.i, bin, valid, v);
 #pragma unroll
       for (int k = 0; k < RPT; ++k) r[k].i = v[k];
-      load_rays<T, RPT>((const T*)a.opd, base, valid, v);
+      load_rays<T, RPT>((const T*)a.opd, bin, valid, v);
 #pragma unroll
       for (int k = 0; k < RPT; ++k) r[k].opd = v[k];
       }
 #pragma unroll
       for (int k = 0; k < RPT; ++k) { r[k].opd_lo = 0; r[k].widx = 0; r[k].L0 = r[k].M0 = r[k].N0 = 0; }
       if (n_wl > 1) {
-        load_rays<T, RPT>((const T*)a.w, base, valid, v);
+        load_rays<T, RPT>((const T*)a.w, bin, valid, v);
 #pragma unroll
         for (int k = 0; k < RPT; ++k) {
           int idx = -1;
@@ -258,8 +267,10 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<T, RPT, FEAT>::v)) trace_ker
     // Pull the NEXT tile's launch state into L2 while this tile computes (no registers held):
     // the first loads of the next iteration then see L2 latency instead of HBM latency.
     {
-      const int64_t nb = base + (int64_t)gridDim.x * per_tile;
-      if (a.px != nullptr) {
+      const int64_t nb = bin + (int64_t)gridDim.x * per_tile;
+      if (a.sys_rays > 0) {
+        // batched: one tile per CTA, nothing to prefetch
+      } else if (a.px != nullptr) {
         if (nb + RPT <= n && (threadIdx.x * RPT * (int)sizeof(T)) % 32 == 0) {
           prefetch_l2((const T*)a.px + nb); prefetch_l2((const T*)a.py + nb);
         }
@@ -379,7 +390,7 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<T, RPT, FEAT>::v)) trace_ker
       double v = mom[q];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if ((threadIdx.x & 31) == 0 && v != 0) atomicAdd(&a.moments[q], v);
+      if ((threadIdx.x & 31) == 0 && v != 0) atomicAdd(&a.moments[(size_t)sys * 8 + q], v);
     }
   }
 }
@@ -586,6 +597,17 @@ static int launch_instance(const TraceArgs& a, cudaStream_t stream) {
     cached_smem = smem;
   }
   const int64_t per_tile = (int64_t)BLOCK * RPT;
+  if (a.sys_rays > 0) {
+    // batched systems: grid.y = system, grid.x = tiles of one system (one tile per CTA, grid-stride beyond 65535)
+    const int64_t n_sys = a.n_rays / a.sys_rays;
+    int64_t gx = (a.sys_rays + per_tile - 1) / per_tile;
+    if (gx > 65535) gx = 65535;
+    if (n_sys > 65535) return fail(OLB_ERR_INVALID_ARG, "more than 65535 systems in one batch");
+    kern<<<dim3((unsigned)gx, (unsigned)n_sys), BLOCK, smem, stream>>>(a);
+    OLB_CUDA(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return OLB_OK;
+  }
   const int64_t n_tiles = (a.n_rays + per_tile - 1) / per_tile;
   // Grid: OVER-SUBSCRIBED grid-stride loop, 64 x the resident CTA count (capped at one tile per CTA).
   // A one-wave persistent grid keeps all CTAs in lock-step (everybody loads, then everybody stores row
@@ -628,7 +650,7 @@ template <typename T>
 static int trace_impl(const OlbDeviceTable* wh, int32_t first, int32_t last, const OlbRays* rays,
                       const OlbRecords* rec, int64_t n_rays, uint32_t flags, int32_t* status,
                       cudaStream_t stream, const OlbPupilLaunch* launch = nullptr, const double* center = nullptr,
-                      double* moments = nullptr) {
+                      double* moments = nullptr, int64_t rays_per_system = 0) {
   if (!wh || wh->magic != WS_MAGIC || !wh->workspace)
     return fail(OLB_ERR_INVALID_ARG, "table handle was not initialised by olb_table_upload");
   const unsigned char* workspace_dev = (const unsigned char*)wh->workspace;
@@ -661,6 +683,18 @@ static int trace_impl(const OlbDeviceTable* wh, int32_t first, int32_t last, con
   a.L0 = rays->L0; a.M0 = rays->M0; a.N0 = rays->N0; a.p = rays->p;
   a.status = status;
   a.tflags = flags;
+  if (rays_per_system > 0) {
+    if (wh->n_systems < 1 || n_rays != rays_per_system * (int64_t)wh->n_systems)
+      return fail(OLB_ERR_INVALID_ARG, "batched trace: n_rays must equal rays_per_system * n_systems of the table");
+    if (flags & OLB_TF_POLARIZED) return fail(OLB_ERR_UNSUPPORTED, "batched trace with polarized rays is not built");
+    a.sys_rays = rays_per_system;
+    a.blob_stride = sizeof(T) == 8 ? wh->stride_f64 : wh->stride_f32;
+    a.shared_in = (flags & OLB_TF_SHARED_INPUT) ? 1 : 0;
+    if (a.shared_in && !(flags & OLB_TF_NO_FINAL))
+      return fail(OLB_ERR_INVALID_ARG, "OLB_TF_SHARED_INPUT needs OLB_TF_NO_FINAL (results go to records / moments)");
+  } else if (wh->n_systems > 1) {
+    return fail(OLB_ERR_INVALID_ARG, "this table holds several systems: use olb_trace_batch_*");
+  }
   if (moments) { a.moments = moments; a.mcx = center ? center[0] : 0.0; a.mcy = center ? center[1] : 0.0; }
   if (launch) {
     a.px = launch->Px; a.py = launch->Py;
@@ -678,6 +712,10 @@ static int trace_impl(const OlbDeviceTable* wh, int32_t first, int32_t last, con
   }
   constexpr int V = sizeof(T) == 4 ? 4 : 2;
   bool vec_ok = true, rec_stride_ok2 = true;
+  if (rays_per_system > 0) {   // every system's segment must start on a vector boundary
+    if (rays_per_system % V) vec_ok = false;
+    if (rays_per_system % 2) rec_stride_ok2 = false;
+  }
   if (rec) {
     void* rr[] = {rec->x, rec->y, rec->z, rec->L, rec->M, rec->N, rec->intensity, rec->opd};
     int n_set = 0;
@@ -767,6 +805,9 @@ int olb_table_upload(const OlbTable* table, void* workspace, int64_t workspace_b
   h.bytes_f32 = (int32_t)pr.blob_f32.size();
   h.bwd_supported = pr.bwd_supported ? 1 : 0;
   h.bwd_slots = pr.total_gslots;
+  h.n_systems = 1;
+  h.stride_f64 = h.bytes_f64;
+  h.stride_f32 = h.bytes_f32;
   const int64_t need = 64 + (int64_t)h.bytes_f64 + h.bytes_f32;
   if (workspace_bytes < need) return fail(OLB_ERR_INVALID_ARG, "workspace too small");
   std::vector<unsigned char> staging((size_t)need, 0);
@@ -777,6 +818,104 @@ int olb_table_upload(const OlbTable* table, void* workspace, int64_t workspace_b
   OLB_CUDA(cudaStreamSynchronize(st));
   *out = h;
   return OLB_OK;
+}
+
+// ---- batched systems: B perturbed copies of one template ------------------------------------------------
+static int build_batch(const OlbTable* tmpl, const double* params, int32_t n_systems, std::vector<unsigned char>& all64,
+                       std::vector<unsigned char>& all32, OlbDeviceTable& h) {
+  if (!tmpl || !params) return fail(OLB_ERR_INVALID_ARG, "template table or params is NULL");
+  if (n_systems < 1 || n_systems > 65535) return fail(OLB_ERR_INVALID_ARG, "n_systems must be in [1, 65535]");
+  if (tmpl->n_wl != 1) return fail(OLB_ERR_UNSUPPORTED, "batched tables support one wavelength");
+  const int S = tmpl->n_surfaces;
+  std::vector<OlbSurface> surf(tmpl->surfaces, tmpl->surfaces + S);
+  std::vector<double> pool(tmpl->pool, tmpl->pool + tmpl->pool_len);
+  OlbTable t = *tmpl;
+  t.surfaces = surf.data();
+  t.pool = pool.data();
+  uint32_t features = 0;
+  for (int b = 0; b < n_systems; ++b) {
+    for (int s = 0; s < S; ++s) {
+      const double* p = params + ((size_t)b * S + s) * OLB_BP_COUNT;
+      OlbSurface& o = surf[s];
+      const OlbSurface& o0 = tmpl->surfaces[s];
+      if (o0.kind == OLB_GEOM_NOOP) continue;
+      o.t[0] = p[OLB_BP_TX]; o.t[1] = p[OLB_BP_TY]; o.t[2] = p[OLB_BP_TZ];
+      for (int q = 0; q < 9; ++q) o.R[q] = p[OLB_BP_R + q];
+      if (o0.kind != OLB_GEOM_PLANE) {
+        o.radius = p[OLB_BP_CURV] == 0 ? INFINITY : 1.0 / p[OLB_BP_CURV];
+        if (o0.kind != OLB_GEOM_TOROIDAL) o.conic = p[OLB_BP_CONIC];
+      }
+      pool[o0.media_off + 0] = p[OLB_BP_N1];
+      pool[o0.media_off + 1] = p[OLB_BP_N2];
+      if (o0.kind == OLB_GEOM_EVEN_ASPHERE)
+        for (int j = 0; j < o0.n_coef && j < OLB_BP_MAX_COEF; ++j) pool[o0.coef_off + j] = p[OLB_BP_COEF + j];
+    }
+    PrepResult pr = prepare_table(t);
+    if (!pr.error.empty()) return fail(OLB_ERR_TABLE, "system " + std::to_string(b) + ": " + pr.error);
+    if (b == 0) {
+      h.bytes_f64 = (int32_t)pr.blob_f64.size(); h.bytes_f32 = (int32_t)pr.blob_f32.size();
+      h.bwd_supported = 0; h.bwd_slots = 0;
+    } else if ((int32_t)pr.blob_f64.size() != h.bytes_f64 || (int32_t)pr.blob_f32.size() != h.bytes_f32) {
+      return fail(OLB_ERR_TABLE, "batched systems must share one table structure");
+    }
+    features |= pr.features;
+    all64.insert(all64.end(), pr.blob_f64.begin(), pr.blob_f64.end());
+    all32.insert(all32.end(), pr.blob_f32.begin(), pr.blob_f32.end());
+  }
+  // every blob must name the union of the features (the kernel variant is chosen once)
+  for (int b = 0; b < n_systems; ++b) {
+    reinterpret_cast<PrepHeader*>(all64.data() + (size_t)b * h.bytes_f64)->features = features;
+    reinterpret_cast<PrepHeader*>(all32.data() + (size_t)b * h.bytes_f32)->features = features;
+  }
+  h.magic = WS_MAGIC; h.features = features; h.n_surfaces = S; h.n_wl = 1; h.n_systems = n_systems;
+  h.stride_f64 = h.bytes_f64; h.stride_f32 = h.bytes_f32;
+  h.off_f64 = 64; h.off_f32 = 64 + (int32_t)all64.size();
+  return OLB_OK;
+}
+
+int64_t olb_table_batch_workspace_bytes(const OlbTable* template_table, int32_t n_systems) {
+  if (!template_table) return fail(OLB_ERR_INVALID_ARG, "table is NULL");
+  PrepResult pr = prepare_table(*template_table);
+  if (!pr.error.empty()) return fail(OLB_ERR_TABLE, pr.error);
+  // rotations may switch PSF bits but never the blob size
+  return 64 + (int64_t)n_systems * (int64_t)(pr.blob_f64.size() + pr.blob_f32.size());
+}
+
+int olb_table_upload_batch(const OlbTable* template_table, const double* params, int32_t n_systems, void* workspace,
+                           int64_t workspace_bytes, void* stream, OlbDeviceTable* out) {
+  if (!workspace || !out) return fail(OLB_ERR_INVALID_ARG, "workspace or out is NULL");
+  if (!aligned16(workspace)) return fail(OLB_ERR_ALIGNMENT, "workspace not 16-byte aligned");
+  std::vector<unsigned char> a64, a32;
+  OlbDeviceTable h{};
+  int rc = build_batch(template_table, params, n_systems, a64, a32, h);
+  if (rc) return rc;
+  const int64_t need = 64 + (int64_t)a64.size() + (int64_t)a32.size();
+  if (workspace_bytes < need) return fail(OLB_ERR_INVALID_ARG, "workspace too small");
+  if (need > INT32_MAX) return fail(OLB_ERR_INVALID_ARG, "batched table larger than 2 GiB");
+  h.workspace = workspace; h.workspace_bytes = workspace_bytes;
+  cudaStream_t st = (cudaStream_t)stream;
+  OLB_CUDA(cudaMemcpyAsync((unsigned char*)workspace + h.off_f64, a64.data(), a64.size(), cudaMemcpyHostToDevice, st));
+  OLB_CUDA(cudaMemcpyAsync((unsigned char*)workspace + h.off_f32, a32.data(), a32.size(), cudaMemcpyHostToDevice, st));
+  OLB_CUDA(cudaStreamSynchronize(st));
+  *out = h;
+  return OLB_OK;
+}
+
+int olb_trace_batch_f32(const OlbDeviceTable* table, int32_t first, int32_t last, const OlbRays* rays,
+                        const OlbRecords* rec, int64_t rays_per_system, uint32_t flags, const double center[2],
+                        double* moments, int32_t* status, void* stream) {
+  if (!table || rays_per_system < 1) return fail(OLB_ERR_INVALID_ARG, "bad batch arguments");
+  OlbRays none{};
+  return trace_impl<float>(table, first, last, rays ? rays : &none, rec, rays_per_system * table->n_systems, flags, status,
+                           (cudaStream_t)stream, nullptr, center, moments, rays_per_system);
+}
+int olb_trace_batch_f64(const OlbDeviceTable* table, int32_t first, int32_t last, const OlbRays* rays,
+                        const OlbRecords* rec, int64_t rays_per_system, uint32_t flags, const double center[2],
+                        double* moments, int32_t* status, void* stream) {
+  if (!table || rays_per_system < 1) return fail(OLB_ERR_INVALID_ARG, "bad batch arguments");
+  OlbRays none{};
+  return trace_impl<double>(table, first, last, rays ? rays : &none, rec, rays_per_system * table->n_systems, flags, status,
+                            (cudaStream_t)stream, nullptr, center, moments, rays_per_system);
 }
 
 int olb_trace_f32(const OlbDeviceTable* table, int32_t first, int32_t last, const OlbRays* rays,

@@ -34,7 +34,7 @@ def test_struct_sizes_match_header():
     assert C.sizeof(_lib.OlbRays) == 13 * 8
     assert C.sizeof(_lib.OlbRecords) == 9 * 8
     assert C.sizeof(_lib.OlbTable) == 40
-    assert C.sizeof(_lib.OlbDeviceTable) == 56
+    assert C.sizeof(_lib.OlbDeviceTable) == 72
 
 
 def test_table_validation_errors_no_gpu_needed():
