@@ -253,7 +253,7 @@ typedef struct OlbDeviceTable {
   int32_t n_systems;            /* 1, or the number of systems of a batched table            */
   int32_t stride_f64;           /* bytes between consecutive systems' fp64 / fp32 blobs      */
   int32_t stride_f32;
-  int32_t reserved;
+  int32_t hints;                /* launch-policy hints filled by the upload (never semantics) */
 } OlbDeviceTable;
 
 /* Bytes of device workspace needed for `table` (< 256 KiB). Negative = error code. */

@@ -60,7 +60,7 @@ class OlbDeviceTable(C.Structure):
         ("features", C.c_uint32), ("n_surfaces", C.c_int32), ("n_wl", C.c_int32),
         ("off_f64", C.c_int32), ("bytes_f64", C.c_int32), ("off_f32", C.c_int32),
         ("bytes_f32", C.c_int32), ("bwd_supported", C.c_int32), ("bwd_slots", C.c_int32),
-        ("n_systems", C.c_int32), ("stride_f64", C.c_int32), ("stride_f32", C.c_int32), ("reserved", C.c_int32),
+        ("n_systems", C.c_int32), ("stride_f64", C.c_int32), ("stride_f32", C.c_int32), ("hints", C.c_int32),
     ]
 
 

@@ -21,8 +21,14 @@
 
 #if defined(__CUDACC__)
 #define OLB_HD __host__ __device__ __forceinline__
+#ifdef OLB_NEWTON_CALL   // tuning knob: Newton solve as an out-of-line call (measured slower, profiles/tune_r1.md)
+#define OLB_HD_CALL __host__ __device__ __noinline__
+#else
+#define OLB_HD_CALL __host__ __device__ __forceinline__
+#endif
 #else
 #define OLB_HD inline
+#define OLB_HD_CALL inline
 #endif
 
 namespace olb {
@@ -397,6 +403,20 @@ OLB_HD T newton_distance(T x, T y, T z, T L, T M, T N, const PrepSurface<T>& S, 
   return t;
 }
 
+// The whole Newton-family intersection: distance + slopes at the hit point.  Inlined, the Newton-capable
+// kernels are 6-12 k SASS instructions; compiling this as ONE out-of-line function (-DOLB_NEWTON_CALL)
+// shrinks them by 30 % but the spills around the call cost more than the I-cache misses saved
+// (fp32 +4..27 %, fp64 +10..25 % slower; profiles/tune_r1.md, sweep 8), so it stays inlined.
+template <typename T> struct NewtonHit { T t, fx, fy; int status; };
+template <typename T>
+OLB_HD_CALL NewtonHit<T> newton_hit(T x, T y, T z, T L, T M, T N, const PrepSurface<T>* S, const T* pool) {
+  NewtonHit<T> h;
+  h.status = 0;
+  h.t = newton_distance(x, y, z, L, M, N, *S, pool, h.status);
+  newton_slopes(o_fma(h.t, L, x), o_fma(h.t, M, y), *S, pool, h.fx, h.fy);
+  return h;
+}
+
 // Aperture program (postfix) -> inside?   physical_apertures/*.py, see include/olb.h.
 template <typename T>
 OLB_HD bool aperture_inside(const T* prog, int len, T x, T y) {
@@ -527,12 +547,15 @@ OLB_HD void surface_step_k(Ray<T>& r, const PrepSurface<T>& S, const T* pool, bo
 
   // -- distance
   T t;
+  T nfx = 0, nfy = 0;                                   // Newton family: slopes at the hit point
   if (KIND == KIND_PLANE) {
     t = -o_div(r.z, r.N);                               // plane.py:72-88
   } else if (KIND == KIND_CONIC) {
     t = conic_distance(r.x, r.y, r.z, r.L, r.M, r.N, S);
   } else {
-    t = newton_distance(r.x, r.y, r.z, r.L, r.M, r.N, S, pool, status);
+    NewtonHit<T> h = newton_hit(r.x, r.y, r.z, r.L, r.M, r.N, &S, pool);
+    t = h.t; nfx = h.fx; nfy = h.fy;
+    status |= h.status;
   }
   // -- propagate (homogeneous.py:30-57) and OPD (standard_surface.py:244)
   r.x = o_fma(t, r.L, r.x);
@@ -571,10 +594,8 @@ OLB_HD void surface_step_k(Ray<T>& r, const PrepSurface<T>& S, const T* pool, bo
       nx *= inv; ny *= inv; nz *= inv;
     }
   } else {
-    T fx, fy;
-    newton_slopes(r.x, r.y, S, pool, fx, fy);
-    T inv = o_rsqrt(o_fma(fx, fx, o_fma(fy, fy, (T)1)));
-    nx = fx * inv; ny = fy * inv; nz = -inv;
+    T inv = o_rsqrt(o_fma(nfx, nfx, o_fma(nfy, nfy, (T)1)));
+    nx = nfx * inv; ny = nfy * inv; nz = -inv;
   }
 
   // -- interaction (refractive_reflective_model.py:32-55)

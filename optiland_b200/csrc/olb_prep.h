@@ -139,9 +139,11 @@ static inline void zernike_add_monomials(int n, int m, double coef, int deg, dou
   }
 }
 
+enum : uint32_t { HINT_POLY_NEWTON = 1u };   // a polynomial-family / biconic / toroidal Newton surface is present
 struct PrepResult {
   std::vector<unsigned char> blob_f64, blob_f32;
   uint32_t features = 0;
+  uint32_t hints = 0;          // HINT_* (launch policy only, never semantics)
   bool bwd_supported = true;   // every surface is covered by surface_backward (olb_math.cuh)
   int total_gslots = 0;        // per-thread gradient accumulator slots the backward kernel needs
   std::string error;
@@ -275,6 +277,7 @@ static inline PrepResult prepare_table(const OlbTable& tab) {
     const bool newton = in.kind >= OLB_GEOM_EVEN_ASPHERE;
     if (newton) {
       features |= FEAT_NEWTON;
+      if (in.kind > OLB_GEOM_ODD_ASPHERE) res.hints |= HINT_POLY_NEWTON;
       if (in.max_iter < 0) { res.error = "negative max_iter"; return res; }
     }
     if (in.kind == OLB_GEOM_EVEN_ASPHERE || in.kind == OLB_GEOM_ODD_ASPHERE) {

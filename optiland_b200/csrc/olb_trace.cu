@@ -641,6 +641,10 @@ template <typename T, int RPT>
 static int launch_feat_cf(const TraceArgs& a, uint32_t features, cudaStream_t stream) {
   if (features & FEAT_POL) return fail(OLB_ERR_UNSUPPORTED, "polarized trace not built in this version");
   if (features == 0) return launch_instance<T, RPT, 0u>(a, stream);
+#ifdef OLB_NEWTON_RPT4
+  if (features == FEAT_NEWTON) return launch_instance<T, RPT, FEAT_NEWTON>(a, stream);
+  if (features != FEAT_ROT) return launch_instance<T, RPT, FEAT_ROT | FEAT_NEWTON | FEAT_EXTRA>(a, stream);
+#endif
   return launch_instance<T, RPT, FEAT_ROT>(a, stream);
 }
 
@@ -749,8 +753,13 @@ static int trace_impl(const OlbDeviceTable* wh, int32_t first, int32_t last, con
     return launch_feat<T, 1>(a, features, stream);
   }
   const bool closed_form = (features & ~FEAT_ROT) == 0;
-  int rpt = force_rpt > 0 ? force_rpt : (sizeof(T) == 4 ? (closed_form ? 4 : 2) : 1);
+  // fp32: 4 rays/thread closed form, 2 with even/odd aspheres, 1 with the polynomial-family Newton surfaces
+  // (2 rays/thread is 5-45 % slower there: profiles/tune_r1.md, sweeps 7 and 8)
+  const bool poly_newton = (wh->hints & (int32_t)HINT_POLY_NEWTON) != 0;
+  int rpt = force_rpt > 0 ? force_rpt : (sizeof(T) == 4 ? (closed_form ? 4 : (poly_newton ? 1 : 2)) : 1);
+#ifndef OLB_NEWTON_RPT4
   if (!closed_form && rpt > 2) rpt = 2;
+#endif
   if constexpr (sizeof(T) == 4) {
     if (rpt >= 4 && vec_ok) return launch_feat_cf<T, 4>(a, features, stream);
     if (rpt >= 2 && rec_stride_ok2) return launch_feat<T, 2>(a, features, stream);
@@ -806,6 +815,7 @@ int olb_table_upload(const OlbTable* table, void* workspace, int64_t workspace_b
   h.bwd_supported = pr.bwd_supported ? 1 : 0;
   h.bwd_slots = pr.total_gslots;
   h.n_systems = 1;
+  h.hints = (int32_t)pr.hints;
   h.stride_f64 = h.bytes_f64;
   h.stride_f32 = h.bytes_f32;
   const int64_t need = 64 + (int64_t)h.bytes_f64 + h.bytes_f32;
@@ -859,6 +869,7 @@ static int build_batch(const OlbTable* tmpl, const double* params, int32_t n_sys
       return fail(OLB_ERR_TABLE, "batched systems must share one table structure");
     }
     features |= pr.features;
+    h.hints |= (int32_t)pr.hints;
     all64.insert(all64.end(), pr.blob_f64.begin(), pr.blob_f64.end());
     all32.insert(all32.end(), pr.blob_f32.begin(), pr.blob_f32.end());
   }
