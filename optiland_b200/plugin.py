@@ -35,7 +35,23 @@ from .pack import UnsupportedSurface, pack_surface, pack_surface_group
 _REC_ATTR = (("x", "x"), ("y", "y"), ("z", "z"), ("L", "L"), ("M", "M"), ("N", "N"),
              ("intensity", "intensity"), ("opd", "opd"))
 _tls = threading.local()
-_state: dict = {"installed": False}
+_state: dict = {"installed": False, "declines": {}}
+
+
+def _decline(reason: str):
+    """Count why a call went back to the reference's Python body (see ``stats()``)."""
+    d = _state.setdefault("declines", {})
+    d[reason] = d.get(reason, 0) + 1
+    return False
+
+
+def stats(reset: bool = False) -> dict:
+    """{reason: count} of the calls the capability declined since install / the last reset --
+    the answer to "why was my trace not accelerated?"."""
+    out = dict(_state.get("declines", {}))
+    if reset:
+        _state["declines"] = {}
+    return out
 
 
 class CudaEngine:
@@ -260,19 +276,20 @@ def _try_trace(backend, surfaces, rays, table_builder) -> bool:
     order); ``table_builder(wavelengths)`` packs them.  Returns False to decline."""
     polarized = type(rays).__name__ == "PolarizedRays"
     if type(rays).__name__ != "RealRays" and not polarized:
-        return False  # ParaxialRays etc.: reference path
+        return _decline(f"ray class {type(rays).__name__}")  # ParaxialRays etc.: reference path
     engine = _state["engine"]
     if not engine.accepts(rays):
-        return False
+        return _decline("rays not resident on a CUDA device (or not fp32/fp64)")
     wl = _unique_wavelengths(rays.w)
     if wl is None:
-        return False
+        return _decline(f"more than {T.MAX_WAVELENGTHS} distinct wavelengths")
     try:
         table = table_builder(wl)
-    except UnsupportedSurface:
-        return False
+    except UnsupportedSurface as e:
+        return _decline(f"unsupported: {e}")
     if not polarized and any(s.coating == T.COAT_FRESNEL for s in table.surfaces):
-        return False  # the reference raises for this combination (ray_generator.py:90-94)
+        # the reference raises for this combination (ray_generator.py:90-94)
+        return _decline("Fresnel coating with unpolarized rays")
     launch_dir = (rays.L, rays.M, rays.N)
     if _wants_grad(backend, surfaces, rays):
         # gradients wanted: the records must be autograd outputs of the live parameter tensors
@@ -280,13 +297,13 @@ def _try_trace(backend, surfaces, rays, table_builder) -> bool:
         # Function (forward kernel + adjoint kernel) replaces the eager graph; tables outside the
         # adjoint's scope go back to the reference's eager path.
         if polarized or table.n_wl != 1:
-            return False
+            return _decline("gradients wanted: polarized rays or several wavelengths in one call")
         params = _live_params(surfaces, table, float(wl[0]))
         if params is None:
-            return False
+            return _decline("gradients wanted: a surface outside the adjoint's scope")
         rec = engine.trace_grad(table, params, rays)
         if rec is None:
-            return False
+            return _decline("gradients wanted: table outside the adjoint's scope")
     else:
         rec = engine.trace(table, rays, 0, table.num_surfaces)
     for row, surf in enumerate(surfaces):
@@ -483,3 +500,4 @@ def uninstall() -> None:
         registry.pop(_state["alias"], None)
     _state.clear()
     _state["installed"] = False
+    _state["declines"] = {}

@@ -120,8 +120,11 @@ def test_declines_and_falls_back_to_reference_python(plugin):
     ref_rec, _ = _numpy_reference(make, trace)
     n0 = len(eng.calls)
     lens = make()
+    P.stats(reset=True)
     trace(lens)
     assert all(c[0] != 4 for c in eng.calls[n0:])  # the 4-surface group was never handed to the engine
+    why = P.stats()
+    assert any("unsupported" in k and "ThinLens" in k for k in why), why   # and the plugin says why
     np.testing.assert_allclose(be.to_numpy(lens.surfaces.y), ref_rec["y"], atol=1e-10)
 
 
