@@ -149,8 +149,8 @@ def check(rc: int, what: str) -> None:
 class HostTable:
     """Owns the packed numpy arrays an ``OlbTable`` points into."""
 
-    def __init__(self, tab: T.SurfaceTable):
-        self.surf, self.pool = tab.pack()
+    def __init__(self, tab: T.SurfaceTable, packed=None):
+        self.surf, self.pool = packed if packed is not None else tab.pack()
         self.surf = np.ascontiguousarray(self.surf)
         self.pool = np.ascontiguousarray(self.pool)
         self.wl = np.ascontiguousarray(tab.wavelengths, dtype=np.float64)

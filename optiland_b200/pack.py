@@ -19,6 +19,7 @@ Anything outside the supported set raises ``UnsupportedSurface`` so the caller
 from __future__ import annotations
 
 import math
+import threading
 
 import numpy as np
 
@@ -29,8 +30,16 @@ class UnsupportedSurface(Exception):
     """The surface (or one of its parts) is outside the CUDA path's scope."""
 
 
+_tls = threading.local()
+
+
 def _f(v) -> float:
     """Scalar backend value (numpy scalar / 0-d tensor / float) -> python float."""
+    pre = getattr(_tls, "resolved", None)
+    if pre is not None:
+        r = pre.get(id(v))
+        if r is not None:
+            return r
     if hasattr(v, "detach"):
         v = v.detach().cpu().numpy()
     return float(np.asarray(v, dtype=np.float64).reshape(-1)[0]) if np.ndim(v) else float(v)
@@ -44,6 +53,115 @@ def _arr(v) -> np.ndarray:
 
 def _cls(obj) -> str:
     return type(obj).__name__
+
+
+class _Prefetch:
+    """One device->host copy for ALL scalar parameters of a surface group.
+
+    With the torch backend on a CUDA device every radius / conic / pose component / refractive index is a
+    0-d device tensor, and converting them one by one costs a stream synchronisation each (~150 per
+    Double-Gauss, 2-3 ms).  This context walks the same attributes ``pack_surface`` reads, stacks the tensors
+    it finds (grouped by device and dtype) and resolves them together; ``_f`` then answers from the table by
+    object identity.  Anything not found falls back to the direct conversion, so this is purely a fast path.
+    """
+
+    force = False       # tests: take the stacked path for host tensors too
+    last_count = 0      # scalars resolved by the most recent prefetch
+
+    def __init__(self, surfaces, wavelengths):
+        self.surfaces = surfaces
+        self.wavelengths = wavelengths
+        self.keep = []          # keeps the tensors alive so that id() stays unique while the table is in use
+
+    def _add(self, v):
+        if hasattr(v, "detach") and hasattr(v, "numel") and v.numel() == 1 and v.dtype.is_floating_point:
+            self.keep.append(v)
+        elif isinstance(v, (list, tuple)):
+            for u in v:
+                self._add(u)
+
+    def _walk(self):
+        for surf in self.surfaces:
+            g = getattr(surf, "geometry", None)
+            if g is None:
+                continue
+            cs = getattr(g, "cs", None)
+            if cs is not None:
+                for k in ("x", "y", "z", "rx", "ry", "rz"):
+                    self._add(getattr(cs, k, None))
+            for k in ("radius", "k", "norm_x", "norm_y", "norm_radius", "Ry", "ky", "R_rot", "k_yz"):
+                self._add(getattr(g, k, None))
+            for k in ("coefficients", "coeffs_poly_y"):
+                c = getattr(g, k, None)
+                if isinstance(c, (list, tuple)):
+                    self._add([u for row in c for u in (row if isinstance(row, (list, tuple)) else [row])])
+            z = getattr(g, "zernike", None)
+            if z is not None:
+                self._add(list(getattr(z, "coeffs", [])))
+            ap = getattr(surf, "aperture", None)
+            stack = [ap] if ap is not None else []
+            while stack:
+                a = stack.pop()
+                for k in ("r_max", "r_min", "offset_x", "offset_y", "x_min", "x_max", "y_min", "y_max"):
+                    self._add(getattr(a, k, None))
+                for k in ("a", "b"):
+                    u = getattr(a, k, None)
+                    if u is not None and hasattr(u, "contains"):
+                        stack.append(u)
+                    else:
+                        self._add(u)
+            for mat in (getattr(surf, "material_pre", None), getattr(surf, "material_post", None)):
+                if mat is None:
+                    continue
+                for wl in self.wavelengths:
+                    for what in ("n", "k"):
+                        try:
+                            # the reference caches these per wavelength (materials/base.py:98-149), so the
+                            # later call in _index_table returns the same object
+                            self._add(getattr(mat, what)(float(wl)))
+                        except Exception:
+                            pass
+
+    def __enter__(self):
+        try:
+            self._walk()
+            if not _Prefetch.force and not any(t.is_cuda for t in self.keep):
+                _tls.resolved = None     # host tensors convert directly at no cost
+                return self
+            groups = {}
+            for t in self.keep:
+                groups.setdefault((t.device, t.dtype), []).append(t)
+            resolved = {}
+            for ts in groups.values():
+                import torch
+
+                vals = torch.stack([t.detach().reshape(()) for t in ts]).double().cpu().numpy()
+                for t, v in zip(ts, vals):
+                    resolved[id(t)] = float(v)
+            _tls.resolved = resolved
+            _Prefetch.last_count = len(resolved)
+        except Exception:
+            _tls.resolved = None
+        return self
+
+    def __exit__(self, *exc):
+        _tls.resolved = None
+        self.keep = []
+        return False
+
+
+def _pose(cs):
+    """(t, R) of ``cs.get_effective_transform()`` (coordinate_system.py:145-165).  An un-nested frame is
+    read directly -- six scalars and, only if tilted, one 3x3 product -- instead of through the ~20 small
+    backend ops of the reference method; nested frames use the reference method."""
+    if getattr(cs, "reference_cs", None) is not None:
+        t_eff, R_eff = cs.get_effective_transform()
+        return _arr(t_eff), _arr(R_eff) + 0.0
+    t = np.array([_f(cs.x), _f(cs.y), _f(cs.z)], dtype=np.float64)
+    rx, ry, rz = _f(cs.rx), _f(cs.ry), _f(cs.rz)
+    if rx == 0.0 and ry == 0.0 and rz == 0.0:
+        return t, np.eye(3)
+    return t, T.rotation_matrix(rx, ry, rz) + 0.0
 
 
 def pack_aperture(ap) -> np.ndarray:
@@ -67,8 +185,12 @@ def pack_aperture(ap) -> np.ndarray:
 def _index_table(material, wavelengths, what: str) -> np.ndarray:
     fn = getattr(material, what)
     out = np.empty(len(wavelengths), dtype=np.float64)
+    pre = getattr(_tls, "resolved", None)
     for j, wl in enumerate(wavelengths):
         v = fn(float(wl))
+        if pre is not None and id(v) in pre:
+            out[j] = pre[id(v)]
+            continue
         v = _arr(v)
         if np.iscomplexobj(v):
             raise UnsupportedSurface("complex refractive index")
@@ -111,12 +233,9 @@ def pack_surface(surface, wavelengths) -> T.SurfaceSpec:
     if getattr(im, "bsdf", None) is not None:
         raise UnsupportedSurface("bsdf scatter")
 
-    t_eff, R_eff = g.cs.get_effective_transform()
-    t_eff, R_eff = _arr(t_eff), _arr(R_eff)
+    t_eff, R_eff = _pose(g.cs)
     if not (np.all(np.isfinite(t_eff)) and np.all(np.isfinite(R_eff))):
         raise UnsupportedSurface("non-finite pose")
-    # exact identity for untilted systems: cos(0)=1, sin(0)=0 already; snap -0.0
-    R_eff = R_eff + 0.0
 
     spec = T.SurfaceSpec(kind=kind, t=t_eff, R=R_eff, reflective=bool(im.is_reflective))
     if kind != T.GEOM_PLANE:
@@ -187,7 +306,8 @@ def pack_surface_group(surface_group, wavelengths) -> T.SurfaceTable:
     surfaces = list(surface_group.surfaces)
     if len(surfaces) > T.MAX_SURFACES:
         raise UnsupportedSurface(f"more than {T.MAX_SURFACES} surfaces")
-    return T.SurfaceTable([pack_surface(s, wavelengths) for s in surfaces], wavelengths)
+    with _Prefetch(surfaces, wavelengths):
+        return T.SurfaceTable([pack_surface(s, wavelengths) for s in surfaces], wavelengths)
 
 
 def launch_scalars(optic, Hx: float, Hy: float) -> dict:

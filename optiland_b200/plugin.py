@@ -80,7 +80,7 @@ class CudaEngine:
         key = surf.tobytes() + pool.tobytes() + table.wavelengths.tobytes() + str(device).encode()
         dt = self._cache.get(key)
         if dt is None:
-            dt = DeviceTable(table, device)
+            dt = DeviceTable(table, device, packed=(surf, pool))
             self._cache[key] = dt
             while len(self._cache) > self._cache_size:
                 self._cache.popitem(last=False)

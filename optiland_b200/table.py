@@ -199,58 +199,62 @@ class SurfaceTable:
     def pack(self) -> tuple[np.ndarray, np.ndarray]:
         """Return (surfaces: OLB_SURFACE_DTYPE[n], pool: float64[m])."""
         n_wl = self.n_wl
-        surf = np.zeros(len(self.surfaces), dtype=OLB_SURFACE_DTYPE)
+        n = len(self.surfaces)
+        surf = np.zeros(n, dtype=OLB_SURFACE_DTYPE)
         pool: list[float] = []
 
         def push(values) -> int:
             off = len(pool)
-            pool.extend(float(v) for v in np.asarray(values, dtype=np.float64).ravel())
+            pool.extend(np.asarray(values, dtype=np.float64).ravel().tolist())
             # keep every block 16-byte aligned for vector loads
             if len(pool) % 2:
                 pool.append(0.0)
             return off
 
+        # integer / offset columns are filled per surface, then every struct field is assigned ONCE for all
+        # surfaces (a per-element structured assignment costs ~1 us; this runs on every plugin call)
+        ints = {k: [0] * n for k in ("n_coef", "aux0", "coef_off", "aper_off", "aper_len", "media_off")}
         for j, s in enumerate(self.surfaces):
-            r = surf[j]
-            r["kind"] = s.kind
-            r["flags"] = s.flags
-            r["t"] = s.t
-            r["R"] = s.R.ravel()
-            r["radius"] = s.radius
-            r["conic"] = s.conic
-            r["tol"] = s.tol
-            r["max_iter"] = s.max_iter
-            r["coating"] = s.coating
-            r["coat_t"] = s.coat_t
-            r["coat_r"] = s.coat_r
-            r["norm_radius"] = s.norm_radius
             coef = s.coefficients
             extra_head = None
             if s.kind in (GEOM_POLYNOMIAL, GEOM_CHEBYSHEV):
                 coef = np.atleast_2d(coef)
-                r["n_coef"] = coef.size
-                r["aux0"] = coef.shape[1]
+                ints["n_coef"][j] = coef.size
+                ints["aux0"][j] = coef.shape[1]
                 if s.kind == GEOM_CHEBYSHEV:
                     extra_head = [s.norm_radius, s.norm_y]
             elif s.kind in (GEOM_BICONIC, GEOM_TOROIDAL):
-                r["n_coef"] = coef.size
+                ints["n_coef"][j] = coef.size
                 extra_head = [s.radius_y, s.conic_y]
             elif s.kind == GEOM_ZERNIKE:
                 coef = coef.reshape(-1, 4)
-                r["n_coef"] = coef.shape[0]
+                ints["n_coef"][j] = coef.shape[0]
             else:
-                r["n_coef"] = coef.size
+                ints["n_coef"][j] = coef.size
             if extra_head is not None:
-                r["coef_off"] = push(np.concatenate([np.asarray(extra_head, float), coef.ravel()]))
+                ints["coef_off"][j] = push(np.concatenate([np.asarray(extra_head, float), coef.ravel()]))
             else:
-                r["coef_off"] = push(coef) if coef.size else 0
+                ints["coef_off"][j] = push(coef) if coef.size else 0
             if s.aperture is not None:
-                r["aper_off"] = push(s.aperture)
-                r["aper_len"] = len(s.aperture)
+                ints["aper_off"][j] = push(s.aperture)
+                ints["aper_len"][j] = len(s.aperture)
             cn1 = s.coat_n1 if s.coat_n1 is not None else s.n1
             cn2 = s.coat_n2 if s.coat_n2 is not None else s.n2
-            r["media_off"] = push(np.concatenate([s.n1, s.n2, s.k1, cn1, cn2]))
+            ints["media_off"][j] = push(np.concatenate([s.n1, s.n2, s.k1, cn1, cn2]))
             assert len(s.n1) == n_wl
+        for k, v in ints.items():
+            surf[k] = v
+        sl = self.surfaces
+        surf["kind"] = [s.kind for s in sl]
+        surf["flags"] = [s.flags for s in sl]
+        surf["max_iter"] = [s.max_iter for s in sl]
+        surf["coating"] = [s.coating for s in sl]
+        if n:
+            surf["t"] = np.stack([s.t for s in sl])
+            surf["R"] = np.stack([s.R.ravel() for s in sl])
+        for k, attr in (("radius", "radius"), ("conic", "conic"), ("tol", "tol"), ("coat_t", "coat_t"),
+                        ("coat_r", "coat_r"), ("norm_radius", "norm_radius")):
+            surf[k] = [getattr(s, attr) for s in sl]
         if not pool:
             pool.append(0.0)
             pool.append(0.0)

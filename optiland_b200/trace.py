@@ -111,12 +111,12 @@ class PolarizedRays(RealRays):
 class DeviceTable:
     """A ``SurfaceTable`` prepared and resident on one GPU (olb_table_upload)."""
 
-    def __init__(self, table: T.SurfaceTable, device=None):
+    def __init__(self, table: T.SurfaceTable, device=None, packed=None):
         _require_cuda()
         self.lib = _lib.load()
         self.table = table
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
-        self.host = _lib.HostTable(table)
+        self.host = _lib.HostTable(table, packed)   # ``packed``: a (surf, pool) pair the caller already made
         nbytes = self.lib.olb_table_workspace_bytes(C.byref(self.host.c))
         if nbytes < 0:
             _lib.check(int(nbytes), "olb_table_workspace_bytes")

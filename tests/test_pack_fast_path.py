@@ -1,0 +1,70 @@
+"""Host logic of the plugin's packing fast path (optiland_b200/pack.py): one stacked device->host copy for
+all scalar parameters and the direct pose read must give byte-identical tables to the scalar-by-scalar path."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from optiland_b200 import pack as PK
+from optiland_b200 import table as T
+from tests._fake_optiland import fake_surfaces
+from tests._util import Case
+
+CASES = ["cooke_c1", "dgauss_c2", "dgauss_multiwl", "telephoto_c3_tol1e-6", "hubble_c4"]
+
+
+def _group(table, device, angles=None):
+    return types.SimpleNamespace(surfaces=fake_surfaces(table, device, angles))
+
+
+def _same(a: T.SurfaceTable, b: T.SurfaceTable):
+    sa, pa = a.pack()
+    sb, pb = b.pack()
+    assert sa.tobytes() == sb.tobytes() and pa.tobytes() == pb.tobytes()
+    np.testing.assert_array_equal(a.wavelengths, b.wavelengths)
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("force", [False, True])
+def test_fake_optiland_objects_pack_to_the_golden_table(name, force, monkeypatch):
+    c = Case(name)
+    monkeypatch.setattr(PK._Prefetch, "force", force)
+    PK._Prefetch.last_count = 0
+    got = PK.pack_surface_group(_group(c.table, "cpu"), c.table.wavelengths)
+    _same(got, c.table)
+    if force:
+        assert PK._Prefetch.last_count >= 6 * (c.table.num_surfaces - 1)   # poses, radii, conics, indices
+    assert getattr(PK._tls, "resolved", None) is None                      # nothing leaks out of the context
+
+
+def test_tilted_pose_is_read_directly(monkeypatch):
+    c = Case("cooke_c1")
+    ang = {2: (0.01, -0.02, 0.3), 4: (0.0, 0.0, 1e-3)}
+    for force in (False, True):
+        monkeypatch.setattr(PK._Prefetch, "force", force)
+        got = PK.pack_surface_group(_group(c.table, "cpu", ang), c.table.wavelengths)
+        for s, spec in enumerate(got.surfaces):
+            if s in ang:
+                np.testing.assert_array_equal(spec.R, T.rotation_matrix(*ang[s]) + 0.0)
+            elif spec.kind != T.GEOM_NOOP:
+                np.testing.assert_array_equal(spec.R, np.eye(3))
+            np.testing.assert_array_equal(spec.t, c.table.surfaces[s].t)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+def test_cuda_resident_parameters_are_fetched_in_one_copy(name):
+    c = Case(name)
+    PK._Prefetch.last_count = 0
+    got = PK.pack_surface_group(_group(c.table, "cuda"), c.table.wavelengths)
+    _same(got, c.table)
+    assert PK._Prefetch.last_count >= 6 * (c.table.num_surfaces - 1)
+    # and the packed table traces like the golden one through the plugin's engine
+    from optiland_b200.plugin import CudaEngine
+
+    eng = CudaEngine()
+    rays = types.SimpleNamespace(**{k: torch.from_numpy(c.rays[k]).cuda() for k in ("x", "y", "z", "L", "M", "N", "i", "w")})
+    rays.opd = torch.zeros_like(rays.x)
+    rec = eng.trace(got, rays, 0, got.num_surfaces)
+    np.testing.assert_allclose(rec["x"].cpu().numpy(), c.rec["x"], rtol=0, atol=1e-11 * c.scale, equal_nan=True)
