@@ -73,9 +73,15 @@ class _TraceFn(torch.autograd.Function):
         lib = _lib.load()
         dtype = x.dtype
         sfx = _DTYPES[dtype]
-        table = params_to_table(template, params)
-        dtab = DeviceTable(table, x.device)
-        device_tables.append(dtab)
+        if device_tables and isinstance(device_tables[0], DeviceTable):
+            # the caller already prepared + uploaded the table that holds exactly the VALUES of ``params``
+            # (the plugin packs it from the live objects the parameters were read from)
+            dtab = device_tables[0]
+            table = dtab.table
+        else:
+            table = params_to_table(template, params)
+            dtab = DeviceTable(table, x.device)
+            device_tables.append(dtab)
         if not dtab.c.bwd_supported:
             raise _lib.OlbError("differentiable trace: table not supported by olb_trace_bwd_* (rotated pose, "
                                 "non plane/standard/even-asphere geometry, non-radial aperture, Fresnel coating)")
@@ -115,6 +121,9 @@ class _TraceFn(torch.autograd.Function):
             # are written here and read by the kernel
             nr = len(ctx.rows)
             gbufs, mask = [], 0
+            for q, r in enumerate(ctx.rows):       # rows some quantity has a gradient for
+                if any(grads[j * nr + q] is not None for j in range(8)):
+                    mask |= 1 << r
             for j in range(8):
                 gs = grads[j * nr:(j + 1) * nr]
                 if all(g is None for g in gs):
@@ -122,11 +131,12 @@ class _TraceFn(torch.autograd.Function):
                     continue
                 gb = torch.empty((S, n), dtype=dtype, device=buf.device)
                 for r, g in zip(ctx.rows, gs):
+                    if not (mask >> r) & 1:
+                        continue                   # the kernel never reads this row
                     if g is None:
                         gb[r].zero_()
                     else:
                         gb[r].copy_(g)
-                    mask |= 1 << r
                 gbufs.append(gb)
         c_grec = _lib.OlbRecords(*[(g.data_ptr() if g is not None else None) for g in gbufs], n)
         c_rec = _lib.OlbRecords(*[buf[j].data_ptr() for j in range(8)], stride)

@@ -151,8 +151,12 @@ class CudaEngine:
         if not dt.c.bwd_supported:
             return None
         ins = [getattr(rays, k) for k in ("x", "y", "z", "L", "M", "N", "i", "opd")]
-        outs = AG._TraceFn.apply(table, [], None, params, *ins)
-        rec = dict(zip(("x", "y", "z", "L", "M", "N", "intensity", "opd"), outs))
+        # one (N,) output per (quantity, row): the backward pass then touches only the rows the loss reads
+        # (a dense (S, N) output would make autograd zero-fill and the kernel re-read every row), and ``dt``
+        # -- packed from the same live values ``params`` was read from -- is reused instead of re-preparing
+        S = table.num_surfaces
+        outs = AG._TraceFn.apply(table, [dt], tuple(range(S)), params, *ins)
+        rec = {k: list(outs[j * S:(j + 1) * S]) for j, k in enumerate(("x", "y", "z", "L", "M", "N", "intensity", "opd"))}
         for k, key in (("x", "x"), ("y", "y"), ("z", "z"), ("L", "L"), ("M", "M"), ("N", "N"), ("i", "intensity"), ("opd", "opd")):
             setattr(rays, k, rec[key][-1])
         return rec
@@ -210,14 +214,17 @@ def _live_params(surfaces, table, wavelength):
 
     like = None
     for surf in surfaces:
-        r = getattr(surf.geometry, "radius", None)
+        r = getattr(getattr(surf, "geometry", None), "radius", None)
         if torch.is_tensor(r):
             like = r
             break
     if like is None:
         like = torch.zeros(())
-    rows = []
     zero = torch.zeros((), dtype=torch.float64, device=like.device)
+    one = torch.ones((), dtype=torch.float64, device=like.device)
+    # ONE stack for all S x GP_COUNT scalars (the curvature column first holds the RADIUS, or 1 where the
+    # curvature is zero), then one vectorised 1/radius: a handful of kernels instead of several per surface
+    flat, flat_r = [], []
     for surf, spec in zip(surfaces, table.surfaces):
         vals = [zero] * GP_COUNT
         if spec.kind != T.GEOM_NOOP:
@@ -231,9 +238,10 @@ def _live_params(surfaces, table, wavelength):
                 # coordinate_system.py:84-89 -- so zero angles get no gradient there either.)
                 return None
             vals[GP_TX], vals[GP_TX + 1], vals[GP_TX + 2] = scalar(cs.x, like), scalar(cs.y, like), scalar(cs.z, like)
+            curved = spec.kind != T.GEOM_PLANE and np.isfinite(spec.radius)
             if spec.kind != T.GEOM_PLANE:
-                vals[GP_CURV] = zero if not np.isfinite(spec.radius) else 1.0 / scalar(g.radius, like)
                 vals[GP_CONIC] = scalar(g.k, like)
+            flat_r.append(scalar(g.radius, like) if curved else one)
             vals[GP_N1] = scalar(surf.material_pre.n(wavelength), like)
             vals[GP_N2] = scalar(surf.material_post.n(wavelength), like)
             if spec.kind == T.GEOM_EVEN_ASPHERE:
@@ -241,8 +249,14 @@ def _live_params(surfaces, table, wavelength):
                     return None
                 for j, cj in enumerate(g.coefficients):
                     vals[GP_COEF + j] = scalar(cj, like)
-        rows.append(torch.stack(vals))
-    return torch.stack(rows)
+            vals[GP_CURV] = one if curved else zero      # selector: 1 -> 1/radius, 0 -> 0
+        else:
+            flat_r.append(one)
+        flat.extend(vals)
+    P = torch.stack(flat).reshape(len(table.surfaces), GP_COUNT)
+    radius = torch.stack(flat_r)
+    curv = P[:, GP_CURV] / radius
+    return torch.cat([P[:, :GP_CURV], curv[:, None], P[:, GP_CURV + 1:]], dim=1)
 
 
 def _wants_grad(backend, surfaces, rays=None) -> bool:

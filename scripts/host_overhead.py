@@ -56,6 +56,36 @@ def main():
         eng.trace(t, mk(), 0, t.num_surfaces)
 
     out["pack_upload_trace_ms_changed_table_1000_rays"] = timeit(changed)
+
+    # differentiable step as the plugin runs it for the reference's torch optimiser: pack live objects,
+    # parameters as autograd inputs, forward + adjoint kernels, d(loss)/d(radius of surface 3)
+    from optiland_b200 import plugin as P
+
+    leaf = torch.tensor(c.table.surfaces[3].radius, dtype=torch.float64, device="cuda", requires_grad=True)
+    stages = {"pack": 0.0, "live_params": 0.0, "forward": 0.0, "loss_backward": 0.0}
+
+    def grad_step(acc=True):
+        group.surfaces[3].geometry.radius = leaf * 1.0
+        t0 = time.perf_counter()
+        t = PK.pack_surface_group(group, wl)
+        t1 = time.perf_counter()
+        params = P._live_params(group.surfaces, t, float(wl[0]))
+        t2 = time.perf_counter()
+        rec = eng.trace_grad(t, params, mk())
+        t3 = time.perf_counter()
+        x, y = rec["x"][-1], rec["y"][-1]
+        loss = (x * x + y * y).mean()
+        leaf.grad = None
+        loss.backward()
+        torch.cuda.synchronize()
+        t4 = time.perf_counter()
+        if acc:
+            for k, v in zip(stages, (t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
+                stages[k] += v
+
+    out["grad_step_ms_1000_rays"] = timeit(grad_step, n=100)
+    out["grad_step_stages_ms"] = {k: round(v / 120 * 1e3, 4) for k, v in stages.items()}
+    assert leaf.grad is not None and float(leaf.grad.abs()) > 0
     print(json.dumps({k: (round(v, 4) if isinstance(v, float) else v) for k, v in out.items()}))
 
 
