@@ -1,4 +1,5 @@
-"""Launch state of an infinite-object angle field as a closed form of (Px, Py).
+"""Launch state of one field point as a closed form of (Px, Py): infinite-object angle fields, finite
+objects (angle / object-height fields) and object-space telecentric systems.
 
 Host-side mirror of the step immediately before the hot path, for boxes without
 the reference (bench, GPU tests): ``AngleField.get_ray_origins``
@@ -48,3 +49,34 @@ def pupil_affine_infinite_angle(sc: dict) -> dict:
     sx, sy = EPD / 2 * sc["vx"], EPD / 2 * sc["vy"]
     return {"origin0": (xo, yo, zo), "origin_scale": (sx, sy), "target0": (0.0, 0.0, EPL),
             "target_scale": (EPD * sc["vx"] / 2, EPD * sc["vy"] / 2), "intensity": 1.0}
+
+
+def pupil_affine(sc: dict) -> dict:
+    """Affine launch form for any mode of ``pack.launch_scalars`` (see there).  All three are
+    origin = origin0 + origin_scale * (Px, Py), target = target0 + target_scale * (Px, Py)."""
+    mode = int(sc.get("mode", 0))
+    if mode == 0:
+        return pupil_affine_infinite_angle(sc)
+    o0 = (sc["x0"], sc["y0"], sc["z0"])
+    if mode == 1:        # paraxial.py:90-96: aim at the paraxial entrance pupil
+        return {"origin0": o0, "origin_scale": (0.0, 0.0), "target0": (0.0, 0.0, sc["EPL"]),
+                "target_scale": (sc["EPD"] * sc["vx"] / 2, sc["EPD"] * sc["vy"] / 2), "intensity": 1.0}
+    if mode == 2:        # paraxial.py:82-88: telecentric object space
+        sin = sc["sin"]
+        z1 = math.sqrt(1 - sin ** 2) / sin + sc["z0"]
+        return {"origin0": o0, "origin_scale": (0.0, 0.0), "target0": (sc["x0"], sc["y0"], z1),
+                "target_scale": (sc["vx"], sc["vy"]), "intensity": 1.0}
+    raise ValueError(f"unknown launch mode {mode}")
+
+
+def launch_from_affine(Px, Py, aff: dict):
+    """x0, y0, z0, L, M, N from the affine form -- the arithmetic of the kernel's ``pupil_launch``
+    (olb_math.cuh), on numpy arrays or torch tensors."""
+    x0 = Px * aff["origin_scale"][0] + aff["origin0"][0]
+    y0 = Py * aff["origin_scale"][1] + aff["origin0"][1]
+    z0 = Px * 0 + aff["origin0"][2]
+    dx = Px * aff["target_scale"][0] + aff["target0"][0] - x0
+    dy = Py * aff["target_scale"][1] + aff["target0"][1] - y0
+    dz = aff["target0"][2] - z0
+    mag = _sqrt(dx ** 2 + dy ** 2 + dz ** 2)
+    return x0, y0, z0, dx / mag, dy / mag, dz / mag

@@ -311,27 +311,52 @@ def pack_surface_group(surface_group, wavelengths) -> T.SurfaceTable:
 
 
 def launch_scalars(optic, Hx: float, Hy: float) -> dict:
-    """Scalars from which the launch state of an infinite-object angle field is a closed
-    form of (Px, Py): optiland/fields/field_types/angle.py:17-58 and
-    optiland/rays/ray_aiming/paraxial.py:33-106.  Used to regenerate identical launch rays
-    on a box without the reference (bench / tests)."""
+    """Scalars from which the launch state of ONE field point is a closed form of (Px, Py) -- what
+    ``field_definition.get_ray_origins`` (optiland/fields/field_types/angle.py:17-58,
+    object_height.py:17-46) and ``ParaxialRayAimer.aim_rays`` (optiland/rays/ray_aiming/paraxial.py:33-106)
+    compute per ray.  ``optiland_b200.launch.pupil_affine`` turns them into the kernel's affine form.
+
+    mode 0 (no "mode" key in old fixtures): infinite object, angle field -- the ray origin slides with the
+        pupil point.
+    mode 1: finite object (angle or object-height field): every ray starts at the field's object point
+        (x0, y0, z0) and aims at the paraxial entrance pupil.
+    mode 2: finite object, object-space telecentric: target = origin + (Px vx, Py vy, cot(asin NA))."""
     import optiland.backend as be  # only called where the reference is importable
 
     fd = optic.fields.field_definition
-    if _cls(fd) != "AngleField" or not bool(optic.object_surface.is_infinite):
-        raise UnsupportedSurface("launch_scalars: only infinite-object angle fields")
+    name = _cls(fd)
+    infinite = bool(optic.object_surface.is_infinite)
     vxf, vyf = optic.fields.get_vig_factor(Hx, Hy)
-    return {
-        "EPL": _f(optic.paraxial.EPL()),
-        "EPD": _f(optic.paraxial.EPD()),
-        "offset": _f(fd._get_starting_z_offset(optic)),
-        "max_field": _f(optic.fields.max_field),
-        "z1": _f(be.to_numpy(optic.surfaces.positions)[1]),
-        "vx": 1.0 - _f(vxf),
-        "vy": 1.0 - _f(vyf),
-        "Hx": float(Hx),
-        "Hy": float(Hy),
-    }
+    vx, vy = 1.0 - _f(vxf), 1.0 - _f(vyf)
+    if name == "AngleField" and infinite:
+        if optic.obj_space_telecentric:
+            raise UnsupportedSurface("launch_scalars: telecentric object space with an angle field")
+        return {
+            "EPL": _f(optic.paraxial.EPL()),
+            "EPD": _f(optic.paraxial.EPD()),
+            "offset": _f(fd._get_starting_z_offset(optic)),
+            "max_field": _f(optic.fields.max_field),
+            "z1": _f(be.to_numpy(optic.surfaces.positions)[1]),
+            "vx": vx,
+            "vy": vy,
+            "Hx": float(Hx),
+            "Hy": float(Hy),
+        }
+    if infinite or name not in ("AngleField", "ObjectHeightField"):
+        raise UnsupportedSurface(f"launch_scalars: field type {name} with an {'in' if infinite else ''}finite object")
+    # finite object: the origin does not depend on the pupil point; ask the reference's own field definition
+    # for it (one probe at the pupil centre), like the refractive indices are asked of its materials
+    zero = be.array([0.0])
+    x0, y0, z0 = fd.get_ray_origins(optic, float(Hx), float(Hy), zero, zero, vx, vy)
+    sc = {"x0": _f(_arr(x0).reshape(-1)[0]), "y0": _f(_arr(y0).reshape(-1)[0]), "z0": _f(_arr(z0).reshape(-1)[0]),
+          "vx": vx, "vy": vy, "Hx": float(Hx), "Hy": float(Hy)}
+    if optic.obj_space_telecentric:
+        if name == "AngleField" or not optic.aperture.supports_telecentric:
+            raise UnsupportedSurface("launch_scalars: the reference raises for this telecentric configuration")
+        sc.update(mode=2.0, sin=_f(optic.aperture.value))
+    else:
+        sc.update(mode=1.0, EPL=_f(optic.paraxial.EPL()), EPD=_f(optic.paraxial.EPD()))
+    return sc
 
 
 def _isinf(v) -> bool:

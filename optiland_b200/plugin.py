@@ -357,13 +357,14 @@ def install(engine=None, alias: str | None = None) -> None:
         def trace_optic(self, tracer, Hx, Hy, wavelength, num_rays, distribution):
             """``RealRayTracer.trace`` for ONE field with the launch state generated on the device
             (SURVEY.md 8f-1): returns the traced ``RealRays`` or None to decline.  Covers what
-            ``RayGenerator.generate_rays`` + ``ParaxialRayAimer`` + ``AngleField.get_ray_origins`` do for an
-            infinite-object angle field without apodization / polarization / telecentricity."""
+            ``RayGenerator.generate_rays`` + ``ParaxialRayAimer`` + ``field_definition.get_ray_origins`` do for one
+            field point (infinite-object angle field, finite object with an object-height / angle field,
+            object-space telecentric system) without apodization / polarization."""
             import numpy as _np
             from optiland.distribution import create_distribution
             from optiland.rays import RealRays
 
-            from .launch import pupil_affine_infinite_angle
+            from .launch import pupil_affine
             from .pack import launch_scalars
 
             optic = tracer.optic
@@ -375,7 +376,7 @@ def install(engine=None, alias: str | None = None) -> None:
                 single = be.size(be.atleast_1d(Hx)) == 1 and be.size(be.atleast_1d(Hy)) == 1
             except Exception:
                 return None
-            if not single or optic.polarization != "ignore" or optic.apodization or optic.obj_space_telecentric:
+            if not single or optic.polarization != "ignore" or optic.apodization:
                 return None
             # the aimer is (re)configured lazily inside generate_rays from this dict (ray_generator.py:67-71)
             if getattr(tracer, "ray_aiming_config", {}).get("mode", "paraxial") != "paraxial":
@@ -395,7 +396,7 @@ def install(engine=None, alias: str | None = None) -> None:
                 return None
             if any(s.coating == T.COAT_FRESNEL for s in table.surfaces):
                 return None
-            rec = engine.trace_pupil(table, Px, Py, pupil_affine_infinite_angle(sc))
+            rec = engine.trace_pupil(table, Px, Py, pupil_affine(sc))
             optic.surfaces.reset()
             for row, surf in enumerate(optic.surfaces.surfaces):
                 for attr, key in _REC_ATTR:

@@ -390,6 +390,41 @@ def case_huygens():
           f"{os.path.getsize(path) / 1024:.0f} KiB")
 
 
+def finite_relay(field_type):
+    """Finite-conjugate 1:1-ish relay doublet: object 120 mm in front, `field_type` fields."""
+    lens = _optic.Optic()
+    lens.surfaces.add(index=0, radius=be.inf, thickness=120.0)
+    lens.surfaces.add(index=1, radius=61.0, thickness=7.0, material="N-BK7")
+    lens.surfaces.add(index=2, radius=-44.0, thickness=2.5, material="SF2", is_stop=True)
+    lens.surfaces.add(index=3, radius=-129.0, thickness=110.0)
+    lens.surfaces.add(index=4)
+    lens.set_aperture(aperture_type="EPD", value=18.0)
+    lens.fields.set_type(field_type=field_type)
+    lens.fields.add(y=0)
+    lens.fields.add(y=6.0)
+    lens.fields.add(y=9.0, x=2.0) if field_type == "object_height" else lens.fields.add(y=4.0, x=1.0)
+    lens.wavelengths.add(value=0.5876, is_primary=True)
+    return lens
+
+
+def case_finite_objects():
+    """f-1 beyond infinite-object angle fields: finite object with object-height and angle fields
+    (object_height.py:17-46, angle.py:49-58) and the object-space telecentric lithography sample
+    (paraxial.py:82-88; 44 surfaces)."""
+    from optiland.samples.lithography import UVProjectionLens
+
+    for name, lens, H in (("finite_object_height", finite_relay("object_height"), (2.0 / 9.0, 1.0)),
+                          ("finite_object_angle", finite_relay("angle"), (0.25, 1.0)),
+                          ("litho_telecentric", UVProjectionLens(), (0.0, 1.0))):
+        Px, Py = disk(400, seed=11)
+        wl = float(lens.primary_wavelength)
+        # per-ray field arrays, as RealRayTracer.trace passes them (real_ray_tracer.py:90-103): with scalar H
+        # the object-point origin would come back with size 1 and the object-surface record would be ragged
+        rays = gen(lens, np.full(Px.size, H[0]), np.full(Px.size, H[1]), Px, Py, wl)
+        sc = launch_scalars(lens, H[0], H[1])
+        run_case(name, lens, rays, [wl], extra={"Px": Px, "Py": Py, **{"launch_" + k: v for k, v in sc.items()}})
+
+
 def main():
     be.set_backend("numpy")
     case_cooke()
@@ -402,6 +437,7 @@ def main():
     case_misc()
     case_more_geometries()
     case_huygens()
+    case_finite_objects()
     case_autograd()
 
 
@@ -452,5 +488,8 @@ if __name__ == "__main__":
         case_more_geometries()
     elif len(sys.argv) > 1 and sys.argv[1] == "autograd":
         case_autograd()
+    elif len(sys.argv) > 1 and sys.argv[1] == "finite":
+        be.set_backend("numpy")
+        case_finite_objects()
     else:
         main()

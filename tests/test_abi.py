@@ -92,3 +92,24 @@ def test_pupil_affine_launch_equals_reference_launch_arrays():
         for got, want, key in zip((x0, y0, d[0], d[1], d[2]), (ref[0], ref[1], ref[3], ref[4], ref[5]), "xyLMN"):
             np.testing.assert_allclose(got, want, rtol=0, atol=1e-12 * c.scale)
             np.testing.assert_allclose(got, c.rays[key], rtol=0, atol=1e-12 * c.scale)
+
+
+LAUNCH_CASES = ["dgauss_c2", "hubble_c4", "finite_object_height", "finite_object_angle", "litho_telecentric"]
+
+
+@pytest.mark.parametrize("name", LAUNCH_CASES)
+def test_every_launch_mode_reproduces_the_reference_ray_generator(name):
+    """f-1 for all launch modes (infinite-object angle field; finite object with object-height / angle
+    fields; object-space telecentric): the affine form the kernel evaluates, restated by
+    launch.launch_from_affine, equals the launch rays RayGenerator + ParaxialRayAimer produced."""
+    from optiland_b200.launch import launch_from_affine, pupil_affine
+    from tests._util import Case
+
+    c = Case(name)
+    sc = {k[9:]: float(c.z[k]) for k in c.z.files if k.startswith("x_launch_")}
+    aff = pupil_affine(sc)
+    got = launch_from_affine(c.extra("Px"), c.extra("Py"), aff)
+    for g, key in zip(got, "xyzLMN"):
+        np.testing.assert_allclose(g, c.rays[key], rtol=0, atol=1e-12 * c.scale, err_msg=key)
+    if int(sc.get("mode", 0)) != 0:
+        assert aff["origin_scale"] == (0.0, 0.0)      # every ray starts at the object point

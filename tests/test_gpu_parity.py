@@ -410,17 +410,19 @@ def test_full_size_polarized_zernike_4M_rays():
     assert float((sg.opd[-1] - ref_opd).abs().max()) <= 5e-9
 
 
-@pytest.mark.parametrize("name", ["dgauss_c2", "hubble_c4"])
+@pytest.mark.parametrize("name", ["dgauss_c2", "hubble_c4", "finite_object_height", "finite_object_angle",
+                                  "litho_telecentric"])
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
 def test_pupil_launch_mode_matches_reference(name, dtype):
-    """f-1: launch state generated in-kernel from pupil coordinates (paraxial aiming, angle field,
-    infinite object) == the reference's RayGenerator + SurfaceGroup.trace records, incl. row 0."""
-    from optiland_b200.launch import pupil_affine_infinite_angle
+    """f-1: launch state generated in-kernel from pupil coordinates (paraxial aiming; infinite-object angle
+    fields, finite objects with object-height / angle fields, object-space telecentric) == the reference's
+    RayGenerator + SurfaceGroup.trace records, incl. row 0."""
+    from optiland_b200.launch import pupil_affine
     from optiland_b200.trace import DeviceTable, SurfaceGroup, trace_host
 
     c = Case(name)
     sc = {k[9:]: float(c.z[k]) for k in c.z.files if k.startswith("x_launch_")}
-    aff = pupil_affine_infinite_angle(sc)
+    aff = pupil_affine(sc)
     Px = torch.from_numpy(c.extra("Px")).to("cuda", dtype)
     Py = torch.from_numpy(c.extra("Py")).to("cuda", dtype)
     sg = SurfaceGroup(c.table)

@@ -78,6 +78,34 @@ def test_optic_trace_goes_through_capability_and_matches_numpy(plugin):
     np.testing.assert_allclose(be.to_numpy(rays.L0), ref_rec["L"][-2], atol=1e-12)
 
 
+def test_optic_trace_fused_launch_for_finite_and_telecentric_objects(plugin):
+    """f-1 beyond infinite-object angle fields: object-height field on a finite object, and the
+    object-space telecentric 44-surface lithography sample -- Optic.trace goes through the fused launch
+    and reproduces the NumPy reference, record by record."""
+    P, eng, be = plugin
+    from optiland.samples.lithography import UVProjectionLens
+
+    from oracle.make_golden import finite_relay
+
+    for make, H, wl, S in ((lambda: finite_relay("object_height"), (2.0 / 9.0, 1.0), 0.5876, 5),
+                           (lambda: finite_relay("angle"), (0.25, 1.0), 0.5876, 5),
+                           (UVProjectionLens, (0.0, 1.0), 0.248, 44)):
+        def trace(lens):
+            return lens.trace(Hx=H[0], Hy=H[1], wavelength=wl, num_rays=6, distribution="hexapolar")
+
+        ref_rec, ref_fin = _numpy_reference(make, trace)
+        lens = make()
+        rays = trace(lens)
+        assert eng.calls[-1][:2] == ("pupil", S), eng.calls[-1]
+        scale = max(1.0, float(np.nanmax(np.abs(ref_rec["z"]))))
+        for k, v in ref_rec.items():
+            got = be.to_numpy(getattr(lens.surfaces, k))
+            assert got.shape == v.shape
+            np.testing.assert_allclose(got, v, rtol=0, atol=1e-11 * scale, err_msg=k)
+        for k, v in ref_fin.items():
+            np.testing.assert_allclose(be.to_numpy(getattr(rays, k)), v, rtol=0, atol=1e-11 * scale, err_msg=k)
+
+
 def test_spot_diagram_runs_unchanged_on_top(plugin):
     """Config 1: analysis layer untouched; golden RMS radii of /root/reference/tests/test_analysis.py:88-102."""
     P, eng, be = plugin
