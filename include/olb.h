@@ -410,6 +410,44 @@ int olb_trace_bwd_f64(const OlbDeviceTable* table, int32_t first, int32_t last,
                       uint64_t grad_row_mask, void* stream);
 
 /*
+ * Fused wavefront epilogue (second half): instead of (or besides) records / the final state,
+ * the trace writes per ray the OPD in waves against a spherical reference and the point where the ray meets
+ * that sphere -- steps 4-5 of ChiefRayStrategy.compute_wavefront_data
+ * (optiland/wavefront/strategy.py:179-190) on top of SphericalReference.path_length
+ * (optiland/wavefront/reference_geometry.py:55-82):
+ *   t = distance back along the ray from its image-surface intercept to the sphere (centre, radius);
+ *   opd = ray.opd - n_image t + tilt . (Px, Py);  out.opd = (opd_ref - opd) / (wavelength_um * 1e-3);
+ *   out.pupil_{x,y,z} = intercept - t (L, M, N);  out.intensity = ray intensity on the last surface.
+ * `tilt` is the launch-plane term of _correct_tilt (strategy.py:93-139): (ux EPD/2, uy EPD/2) for an
+ * infinite-object angle field, else 0 (it needs `launch`, the pupil samples).  The caller computes centre,
+ * radius and opd_ref from the chief ray (one ordinary 1-ray trace).  Evaluated in fp64 for both element types.
+ * `last` must be the image surface.  With OLB_TF_NO_FINAL and rec == NULL nothing else is written per ray.
+ */
+typedef struct {
+  double center[3];
+  double radius;
+  double n_image;
+  double tilt[2];
+  double opd_ref;
+  double wavelength_um;
+} OlbWavefrontRef;
+typedef struct {
+  void* opd;        /* waves */
+  void* pupil_x;
+  void* pupil_y;
+  void* pupil_z;
+  void* intensity;
+} OlbWavefrontOut;
+int olb_trace_wavefront_f32(const OlbDeviceTable* table, int32_t first, int32_t last,
+                            const OlbPupilLaunch* launch, const OlbRays* rays, const OlbRecords* rec,
+                            int64_t n_rays, uint32_t flags, const OlbWavefrontRef* ref,
+                            const OlbWavefrontOut* out, int32_t* status, void* stream);
+int olb_trace_wavefront_f64(const OlbDeviceTable* table, int32_t first, int32_t last,
+                            const OlbPupilLaunch* launch, const OlbRays* rays, const OlbRecords* rec,
+                            int64_t n_rays, uint32_t flags, const OlbWavefrontRef* ref,
+                            const OlbWavefrontOut* out, int32_t* status, void* stream);
+
+/*
  * Batched many-systems trace: B perturbed copies of one template system -- the shape of
  * tolerancing Monte-Carlo runs (optiland/tolerancing/monte_carlo.py) and of the BatchedRayEvaluator
  * (optiland/optimization/batched_evaluator.py:277-705), which the reference evaluates as B separate small

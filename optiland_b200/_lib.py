@@ -54,6 +54,15 @@ class OlbPupilLaunch(C.Structure):
                 ("target0", C.c_double * 3), ("target_scale", C.c_double * 2), ("intensity", C.c_double)]
 
 
+class OlbWavefrontRef(C.Structure):
+    _fields_ = [("center", C.c_double * 3), ("radius", C.c_double), ("n_image", C.c_double), ("tilt", C.c_double * 2),
+                ("opd_ref", C.c_double), ("wavelength_um", C.c_double)]
+
+
+class OlbWavefrontOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("opd", "pupil_x", "pupil_y", "pupil_z", "intensity")]
+
+
 class OlbDeviceTable(C.Structure):
     _fields_ = [
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("magic", C.c_uint32),
@@ -96,6 +105,12 @@ SYMBOLS = {
     "olb_trace_host_pupil_f64": (C.c_int, [_P(OlbDeviceTable), C.c_int32, C.c_int32, _P(OlbPupilLaunch), _P(OlbRays),
                                            _P(OlbRecords), C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
                                            C.c_uint32, C.c_void_p]),
+    "olb_trace_wavefront_f32": (C.c_int, [_P(OlbDeviceTable), C.c_int32, C.c_int32, _P(OlbPupilLaunch), _P(OlbRays),
+                                          _P(OlbRecords), C.c_int64, C.c_uint32, _P(OlbWavefrontRef), _P(OlbWavefrontOut),
+                                          C.c_void_p, C.c_void_p]),
+    "olb_trace_wavefront_f64": (C.c_int, [_P(OlbDeviceTable), C.c_int32, C.c_int32, _P(OlbPupilLaunch), _P(OlbRays),
+                                          _P(OlbRecords), C.c_int64, C.c_uint32, _P(OlbWavefrontRef), _P(OlbWavefrontOut),
+                                          C.c_void_p, C.c_void_p]),
     "olb_table_batch_workspace_bytes": (C.c_int64, [_P(OlbTable), C.c_int32]),
     "olb_table_upload_batch": (C.c_int, [_P(OlbTable), C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p,
                                          _P(OlbDeviceTable)]),

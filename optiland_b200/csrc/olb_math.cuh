@@ -105,6 +105,8 @@ OLB_HD void accumulate_opd(Ray<float>& r, float v) {
 }
 OLB_HD double opd_value(const Ray<double>& r) { return r.opd; }
 OLB_HD float opd_value(const Ray<float>& r) { return r.opd + r.opd_lo; }
+OLB_HD double opd_value_f64(const Ray<double>& r) { return r.opd; }
+OLB_HD double opd_value_f64(const Ray<float>& r) { return (double)r.opd + (double)r.opd_lo; }  // both halves
 
 // Launch state of one ray from its pupil point (include/olb.h: OlbPupilLaunch; reference:
 // rays/ray_aiming/paraxial.py:85-105 on top of fields/field_types/angle.py:40-57).
@@ -122,6 +124,34 @@ OLB_HD void pupil_launch(Ray<T>& r, T Px, T Py, const T* o0, const T* os, const 
   r.N = zero ? (T)1 : dz * inv;
   r.i = inten;
   r.opd = 0;
+}
+
+// Wavefront epilogue: OPD of one traced ray against a spherical reference centred on the
+// chief ray's image point, and the point where the ray meets that sphere -- steps 4-5 of
+// ChiefRayStrategy.compute_wavefront_data (optiland/wavefront/strategy.py:179-190) with
+// SphericalReference.path_length (optiland/wavefront/reference_geometry.py:55-82) and the launch-plane tilt
+// term of _correct_tilt (strategy.py:93-139).  Always evaluated in fp64: c = |p - centre|^2 - R^2 cancels
+// ~R^2 against ~R^2, and the result is wanted to 1e-5 waves.
+struct WavefrontRef {
+  double c[3], R, n_image, tilt[2], opd_ref, inv_wl;   // inv_wl = 1 / (wavelength[um] * 1e-3) : waves per mm
+};
+OLB_HD void wavefront_point(double x, double y, double z, double L, double M, double N, double opd, double Px,
+                            double Py, const WavefrontRef& w, double& opd_wv, double& px, double& py, double& pz) {
+  const double Lr = -L, Mr = -M, Nr = -N;               // traced backwards from the image surface
+  const double a = Lr * Lr + Mr * Mr + Nr * Nr;
+  const double b = 2 * (Lr * (x - w.c[0]) + Mr * (y - w.c[1]) + Nr * (z - w.c[2]));
+  const double c = x * x + y * y + z * z - 2 * (x * w.c[0] + y * w.c[1] + z * w.c[2]) + w.c[0] * w.c[0] +
+                   w.c[1] * w.c[1] + w.c[2] * w.c[2] - w.R * w.R;
+  double d = b * b - 4 * a * c;
+  if (d < 0) d = 0;
+  const double sq = sqrt(d);
+  const double t1 = (-b - sq) / (2 * a), t2 = (-b + sq) / (2 * a);
+  const double t = t1 < 0 ? t2 : t1;
+  const double opd_img = w.n_image * t;
+  const double o = opd - opd_img + (w.tilt[0] * Px + w.tilt[1] * Py);
+  opd_wv = (w.opd_ref - o) * w.inv_wl;
+  const double tt = opd_img / w.n_image;
+  px = x - tt * L; py = y - tt * M; pz = z - tt * N;
 }
 
 template <typename T>

@@ -85,6 +85,9 @@ struct TraceArgs {
   int64_t sys_rays;
   int32_t blob_stride;
   int32_t shared_in;
+  // wavefront epilogue (olb_trace_wavefront_*) when wf_opd != nullptr
+  void* wf_opd; void* wf_px; void* wf_py; void* wf_pz; void* wf_i;
+  WavefrontRef wf;
 };
 
 // ---- vector access helpers -------------------------------------------------------------
@@ -342,6 +345,30 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<T, RPT, FEAT>::v)) trace_ker
           mom[5] += oo; mom[6] += oo * oo;
         }
       }
+    }
+    if (a.wf_opd != nullptr) {
+      // OPD map against the reference sphere + exit-pupil intercepts, from the GLOBAL final state; the
+      // pupil samples are re-read for the launch-plane tilt term (they were consumed by the launch)
+      T wpx[RPT], wpy[RPT];
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) { wpx[k] = 0; wpy[k] = 0; }
+      if (a.px != nullptr && (a.wf.tilt[0] != 0 || a.wf.tilt[1] != 0)) {
+        load_rays<T, RPT>((const T*)a.px, bin, valid, wpx);
+        load_rays<T, RPT>((const T*)a.py, bin, valid, wpy);
+      }
+      T o0[RPT], o1[RPT], o2[RPT], o3[RPT], o4[RPT];
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) {
+        double ow, qx, qy, qz;
+        wavefront_point((double)gx[k], (double)gy[k], (double)gz[k], (double)gL[k], (double)gM[k], (double)gN[k],
+                        opd_value_f64(r[k]), (double)wpx[k], (double)wpy[k], a.wf, ow, qx, qy, qz);
+        o0[k] = (T)ow; o1[k] = (T)qx; o2[k] = (T)qy; o3[k] = (T)qz; o4[k] = r[k].i;
+      }
+      store_rays<T, RPT>((T*)a.wf_opd, base, valid, o0);
+      store_rays<T, RPT>((T*)a.wf_px, base, valid, o1);
+      store_rays<T, RPT>((T*)a.wf_py, base, valid, o2);
+      store_rays<T, RPT>((T*)a.wf_pz, base, valid, o3);
+      store_rays<T, RPT>((T*)a.wf_i, base, valid, o4);
     }
     if (!(a.tflags & OLB_TF_NO_FINAL)) {
       T v[RPT];
@@ -697,7 +724,8 @@ template <typename T>
 static int trace_impl(const OlbDeviceTable* wh, int32_t first, int32_t last, const OlbRays* rays,
                       const OlbRecords* rec, int64_t n_rays, uint32_t flags, int32_t* status,
                       cudaStream_t stream, const OlbPupilLaunch* launch = nullptr, const double* center = nullptr,
-                      double* moments = nullptr, int64_t rays_per_system = 0) {
+                      double* moments = nullptr, int64_t rays_per_system = 0, const OlbWavefrontRef* wref = nullptr,
+                      const OlbWavefrontOut* wout = nullptr) {
   if (!wh || wh->magic != WS_MAGIC || !wh->workspace)
     return fail(OLB_ERR_INVALID_ARG, "table handle was not initialised by olb_table_upload");
   const unsigned char* workspace_dev = (const unsigned char*)wh->workspace;
@@ -743,6 +771,25 @@ static int trace_impl(const OlbDeviceTable* wh, int32_t first, int32_t last, con
     return fail(OLB_ERR_INVALID_ARG, "this table holds several systems: use olb_trace_batch_*");
   }
   if (moments) { a.moments = moments; a.mcx = center ? center[0] : 0.0; a.mcy = center ? center[1] : 0.0; }
+  if (wref || wout) {
+    if (!wref || !wout) return fail(OLB_ERR_INVALID_ARG, "wavefront: ref and out are both required");
+    void* wo[] = {wout->opd, wout->pupil_x, wout->pupil_y, wout->pupil_z, wout->intensity};
+    for (void* p : wo) {
+      if (!p) return fail(OLB_ERR_INVALID_ARG, "wavefront: an output array is NULL");
+      if (!aligned16(p)) return fail(OLB_ERR_ALIGNMENT, "wavefront output array not 16-byte aligned");
+    }
+    if (!(wref->radius > 0) || !(wref->n_image > 0) || !(wref->wavelength_um > 0))
+      return fail(OLB_ERR_INVALID_ARG, "wavefront: radius, n_image and wavelength must be positive");
+    if ((wref->tilt[0] != 0 || wref->tilt[1] != 0) && !launch)
+      return fail(OLB_ERR_INVALID_ARG, "wavefront: the launch-plane tilt term needs the pupil samples (launch)");
+    if (rays_per_system > 0 || (flags & OLB_TF_POLARIZED))
+      return fail(OLB_ERR_UNSUPPORTED, "wavefront epilogue with batched systems / polarized rays is not built");
+    if (last != wh->n_surfaces) return fail(OLB_ERR_INVALID_ARG, "wavefront: the trace must end on the image surface");
+    a.wf_opd = wout->opd; a.wf_px = wout->pupil_x; a.wf_py = wout->pupil_y; a.wf_pz = wout->pupil_z; a.wf_i = wout->intensity;
+    for (int q = 0; q < 3; ++q) a.wf.c[q] = wref->center[q];
+    a.wf.R = wref->radius; a.wf.n_image = wref->n_image; a.wf.tilt[0] = wref->tilt[0]; a.wf.tilt[1] = wref->tilt[1];
+    a.wf.opd_ref = wref->opd_ref; a.wf.inv_wl = 1.0 / (wref->wavelength_um * 1e-3);
+  }
   if (launch) {
     a.px = launch->Px; a.py = launch->Py;
     for (int q = 0; q < 3; ++q) { a.lo0[q] = launch->origin0[q]; a.lt0[q] = launch->target0[q]; }
@@ -779,8 +826,8 @@ static int trace_impl(const OlbDeviceTable* wh, int32_t first, int32_t last, con
       if (rec->row_stride % 2) rec_stride_ok2 = false;
     }
   }
-  if ((flags & OLB_TF_NO_FINAL) && !a.rx && !moments)
-    return fail(OLB_ERR_INVALID_ARG, "OLB_TF_NO_FINAL needs record arrays or moments (the result would be lost)");
+  if ((flags & OLB_TF_NO_FINAL) && !a.rx && !moments && !a.wf_opd)
+    return fail(OLB_ERR_INVALID_ARG, "OLB_TF_NO_FINAL needs record arrays, moments or wavefront outputs (the result would be lost)");
   // Rays per thread.  Closed-form tables (planes / conics, optionally rotated): fp32 -> 4
   // (float4 accesses, 120 regs, 16 warps/SM), fp64 -> 1 (74 regs, 24 warps/SM).  Tables with
   // Newton surfaces / aperture programs / coatings: fp32 -> 2, fp64 -> 1 (their per-ray code
@@ -1008,6 +1055,23 @@ int olb_trace_pupil_f64(const OlbDeviceTable* table, int32_t first, int32_t last
   if (!launch) return fail(OLB_ERR_INVALID_ARG, "launch is NULL");
   OlbRays none{};
   return trace_impl<double>(table, first, last, out ? out : &none, rec, n_rays, flags, status, (cudaStream_t)stream, launch);
+}
+
+int olb_trace_wavefront_f32(const OlbDeviceTable* table, int32_t first, int32_t last, const OlbPupilLaunch* launch,
+                            const OlbRays* rays, const OlbRecords* rec, int64_t n_rays, uint32_t flags,
+                            const OlbWavefrontRef* ref, const OlbWavefrontOut* out, int32_t* status, void* stream) {
+  if (!ref || !out) return fail(OLB_ERR_INVALID_ARG, "wavefront: ref / out is NULL");
+  OlbRays none{};
+  return trace_impl<float>(table, first, last, rays ? rays : &none, rec, n_rays, flags, status, (cudaStream_t)stream,
+                           launch, nullptr, nullptr, 0, ref, out);
+}
+int olb_trace_wavefront_f64(const OlbDeviceTable* table, int32_t first, int32_t last, const OlbPupilLaunch* launch,
+                            const OlbRays* rays, const OlbRecords* rec, int64_t n_rays, uint32_t flags,
+                            const OlbWavefrontRef* ref, const OlbWavefrontOut* out, int32_t* status, void* stream) {
+  if (!ref || !out) return fail(OLB_ERR_INVALID_ARG, "wavefront: ref / out is NULL");
+  OlbRays none{};
+  return trace_impl<double>(table, first, last, rays ? rays : &none, rec, n_rays, flags, status, (cudaStream_t)stream,
+                            launch, nullptr, nullptr, 0, ref, out);
 }
 
 int olb_trace_moments_f32(const OlbDeviceTable* table, int32_t first, int32_t last, const OlbPupilLaunch* launch,

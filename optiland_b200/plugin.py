@@ -131,6 +131,14 @@ class CudaEngine:
         _, rec = trace_pupil_device(dt, Px.detach().contiguous(), Py.detach().contiguous(), affine, 0, table.num_surfaces)
         return rec
 
+    def trace_wavefront(self, table: T.SurfaceTable, Px, Py, affine: dict, ref: dict) -> dict:
+        """One field's pupil grid -> OPD map + exit-pupil intercepts + intensity, nothing else written
+        (olb_trace_wavefront_*)."""
+        from .trace import trace_wavefront_device
+
+        dt = self.device_table(table, Px.device)
+        return trace_wavefront_device(dt, Px.detach().contiguous(), Py.detach().contiguous(), affine, ref)
+
     def huygens_psf(self, image_x, image_y, image_z, pupil_x, pupil_y, pupil_z, pupil_amp, pupil_opd, wavelength, Rp):
         """Huygens-Fresnel summation on the GPU (olb_huygens_psf_f64); None to decline (CPU tensors)."""
         import torch
@@ -412,6 +420,63 @@ def install(engine=None, alias: str | None = None) -> None:
                 last_surface.material_post.propagation_model.propagate(rays, last_surface.thickness)
             return rays
 
+        def wavefront_chief_ray(self, strategy, field, wavelength):
+            """``ChiefRayStrategy.compute_wavefront_data`` (wavefront/strategy.py:152-213) with steps 3-5 -- the
+            full-grid trace, the path length to the reference sphere, the OPD in waves and the exit-pupil
+            intercepts -- fused into one launch that writes 5 values per ray.  Steps 1-2 (chief
+            ray, reference sphere, reference OPD) run as in the reference.  Returns WavefrontData or None."""
+            import numpy as _np
+            from optiland.wavefront.wavefront_data import WavefrontData
+
+            from .launch import pupil_affine
+            from .pack import launch_scalars
+
+            optic = strategy.optic
+            engine = _state["engine"]
+            if not hasattr(engine, "trace_wavefront") or getattr(strategy, "reference_type", "sphere") != "sphere":
+                return None
+            if getattr(_tls, "in_reference", False) or _wants_grad(self, list(optic.surfaces.surfaces)):
+                return None
+            if optic.polarization != "ignore" or optic.apodization:
+                return None
+            if getattr(optic.ray_tracer, "ray_aiming_config", {}).get("mode", "paraxial") != "paraxial":
+                return None
+            dist = strategy.distribution
+            Px, Py = dist.x, dist.y
+            if not (engine.accepts_tensor(Px) and engine.accepts_tensor(Py)):
+                return None
+            try:
+                hx, hy = float(field[0]), float(field[1])
+                sc = launch_scalars(optic, hx, hy)
+                table = pack_surface_group(optic.surfaces, [float(wavelength)])
+            except (UnsupportedSurface, TypeError, ValueError):
+                return None
+            if any(s.coating == T.COAT_FRESNEL for s in table.surfaces):
+                return None
+            # steps 1-2, the reference's own code on ONE ray (strategy.py:160-170)
+            chief = optic.trace_generic(*field, Px=0.0, Py=0.0, wavelength=wavelength)
+            strategy._chief_ray = chief
+            geometry = strategy._create_reference_geometry(chief)
+            opd_ref = chief.opd - geometry.path_length(chief, strategy.n_image)
+            opd_ref = strategy._correct_tilt(field, opd_ref, x=0, y=0)
+            tilt = (0.0, 0.0)
+            if type(optic.fields.field_definition).__name__ == "AngleField" and bool(optic.object_surface.is_infinite):
+                # _correct_tilt (strategy.py:112-138): opd += ux X + uy Y with (X, Y) = (Px, Py) EPD / 2
+                mf = float(_np.asarray(be.to_numpy(optic.fields.max_field)).reshape(-1)[0])
+                tx, ty = _np.tan(_np.deg2rad(hx * mf)), _np.tan(_np.deg2rad(hy * mf))
+                uz = 1.0 / _np.sqrt(1.0 + tx**2 + ty**2)
+                epd = float(_np.asarray(be.to_numpy(optic.paraxial.EPD())).reshape(-1)[0])
+                tilt = (tx * uz * epd / 2, ty * uz * epd / 2)
+
+            def f(v):
+                return float(_np.asarray(be.to_numpy(v)).reshape(-1)[0])
+
+            ref = {"center": [f(c) for c in geometry.center], "radius": f(geometry.radius), "n_image": f(strategy.n_image),
+                   "tilt": tilt, "opd_ref": f(opd_ref), "wavelength_um": float(wavelength)}
+            out = engine.trace_wavefront(table, Px, Py, pupil_affine(sc), ref)
+            return WavefrontData(pupil_x=out["pupil_x"], pupil_y=out["pupil_y"], pupil_z=out["pupil_z"], opd=out["opd"],
+                                 intensity=out["intensity"], radius=geometry.radius)
+
         def trace_surface(self, surface, rays) -> bool:
             if type(surface).__name__ not in ("Surface", "ImageSurface"):
                 return False
@@ -465,6 +530,19 @@ def install(engine=None, alias: str | None = None) -> None:
     # f-3: the Huygens-Fresnel summation strategy of the torch backend (psf/huygens_fresnel_strategies.py:183-273)
     from optiland.psf.huygens_fresnel_strategies import TorchSummation
 
+    from optiland.wavefront.strategy import ChiefRayStrategy
+
+    orig_chief_compute = ChiefRayStrategy.compute_wavefront_data
+
+    def chief_compute(self, field, wavelength):
+        backend = registry.get(be.get_backend())
+        if hasattr(backend, "wavefront_chief_ray") and _state.get("fuse_wavefront", True):
+            data = backend.wavefront_chief_ray(self, field, wavelength)
+            if data is not None:
+                return data
+        return orig_chief_compute(self, field, wavelength)
+
+    ChiefRayStrategy.compute_wavefront_data = chief_compute
     orig_hf_compute = TorchSummation.compute
 
     def hf_compute(self, image_x, image_y, image_z, pupil_x, pupil_y, pupil_z, pupil_amp, pupil_opd, wavelength, Rp):
@@ -489,8 +567,8 @@ def install(engine=None, alias: str | None = None) -> None:
     Surface.trace = surface_trace
     RealRayTracer.trace = tracer_trace
     _state.update(installed=True, orig_group_trace=orig_group_trace, orig_surface_trace=orig_surface_trace,
-                  orig_tracer_trace=orig_tracer_trace, orig_hf_compute=orig_hf_compute, old_backend=old, alias=alias,
-                  fuse_launch=True)
+                  orig_tracer_trace=orig_tracer_trace, orig_hf_compute=orig_hf_compute, orig_chief_compute=orig_chief_compute,
+                  old_backend=old, alias=alias, fuse_launch=True, fuse_wavefront=True)
 
 
 def uninstall() -> None:
@@ -509,6 +587,9 @@ def uninstall() -> None:
     from optiland.psf.huygens_fresnel_strategies import TorchSummation
 
     TorchSummation.compute = _state["orig_hf_compute"]
+    from optiland.wavefront.strategy import ChiefRayStrategy
+
+    ChiefRayStrategy.compute_wavefront_data = _state["orig_chief_compute"]
     if _state.get("old_backend") is not None:
         registry["torch"] = _state["old_backend"]
     if _state.get("alias"):

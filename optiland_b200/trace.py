@@ -251,6 +251,39 @@ def trace_pupil_device(dtab: DeviceTable, Px: torch.Tensor, Py: torch.Tensor, af
     return rays, recs
 
 
+WAVEFRONT_KEYS = ("opd", "pupil_x", "pupil_y", "pupil_z", "intensity")
+
+
+def trace_wavefront_device(dtab: DeviceTable, Px: torch.Tensor, Py: torch.Tensor, affine: dict, ref: dict,
+                           wavelength: torch.Tensor | None = None) -> dict:
+    """olb_trace_wavefront_*: trace one field's pupil grid and write ONLY the wavefront data -- OPD in waves
+    against the spherical reference ``ref`` = {center (3), radius, n_image, tilt (2), opd_ref, wavelength_um},
+    the exit-pupil intercepts and the image-surface intensity -- no records, no final state
+    (optiland/wavefront/strategy.py:152-213).  Returns {key: (N,) tensor} for WAVEFRONT_KEYS."""
+    lib = dtab.lib
+    n = Px.numel()
+    dtype = Px.dtype
+    sfx = _DTYPES[dtype]
+    vec = 4 if dtype == torch.float32 else 2
+    stride = (n + 63) // 64 * 64 if n % vec else n          # keeps every output row 16-byte aligned
+    buf = torch.empty((5, stride), dtype=dtype, device=Px.device)
+    c_out = _lib.OlbWavefrontOut(*[buf[j].data_ptr() for j in range(5)])
+    c_ref = _lib.OlbWavefrontRef()
+    c_ref.center = (C.c_double * 3)(*[float(v) for v in ref["center"]])
+    c_ref.radius, c_ref.n_image = float(ref["radius"]), float(ref["n_image"])
+    c_ref.tilt = (C.c_double * 2)(*[float(v) for v in ref.get("tilt", (0.0, 0.0))])
+    c_ref.opd_ref, c_ref.wavelength_um = float(ref["opd_ref"]), float(ref["wavelength_um"])
+    la = _c_launch(affine, Px.contiguous(), Py.contiguous())
+    rays = _lib.OlbRays(w=wavelength.data_ptr() if (wavelength is not None and dtab.table.n_wl > 1) else None)
+    with torch.cuda.device(Px.device):
+        stream = torch.cuda.current_stream(Px.device).cuda_stream
+        rc = getattr(lib, f"olb_trace_wavefront_{sfx}")(
+            C.byref(dtab.c), 0, dtab.table.num_surfaces, C.byref(la), C.byref(rays), None, n, _lib.TF_NO_FINAL,
+            C.byref(c_ref), C.byref(c_out), None, C.c_void_p(stream))
+    _lib.check(rc, f"olb_trace_wavefront_{sfx}")
+    return {k: buf[j, :n] for j, k in enumerate(WAVEFRONT_KEYS)}
+
+
 def trace_moments_device(dtab: DeviceTable, n: int, dtype, rays: RealRays | None = None, pupil=None,
                          center=(0.0, 0.0), moments: torch.Tensor | None = None, wavelength=None) -> torch.Tensor:
     """olb_trace_moments_*: trace WITHOUT writing any per-ray output and accumulate the spot / OPD moments

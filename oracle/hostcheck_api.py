@@ -83,3 +83,19 @@ def run_backward(hc, table, rays, rec, grec, dtype=np.float64):
     return dict(zip(("x", "y", "z", "L", "M", "N", "i", "opd"), gin)), gpar
 
 
+
+
+def run_wavefront(hc, fin: dict, Px, Py, ref: dict) -> dict:
+    """olb_math.cuh::wavefront_point (the kernel's wavefront epilogue) on the CPU."""
+    n = np.size(fin["x"])
+    arrs = [np.ascontiguousarray(fin[k], dtype=np.float64) for k in ("x", "y", "z", "L", "M", "N", "opd")]
+    px, py = np.ascontiguousarray(Px, dtype=np.float64), np.ascontiguousarray(Py, dtype=np.float64)
+    tilt = ref.get("tilt", (0.0, 0.0))
+    r = np.array([*ref["center"], ref["radius"], ref["n_image"], tilt[0], tilt[1], ref["opd_ref"],
+                  1.0 / (float(ref["wavelength_um"]) * 1e-3)], dtype=np.float64)
+    out = [np.empty(n) for _ in range(4)]
+    hc.olbhc_wavefront.restype = C.c_int
+    rc = hc.olbhc_wavefront(C.c_int64(n), (C.c_void_p * 7)(*[a.ctypes.data for a in arrs]), C.c_void_p(px.ctypes.data),
+                            C.c_void_p(py.ctypes.data), C.c_void_p(r.ctypes.data), (C.c_void_p * 4)(*[a.ctypes.data for a in out]))
+    assert rc == 0
+    return dict(zip(("opd", "pupil_x", "pupil_y", "pupil_z"), out))

@@ -390,6 +390,54 @@ def case_huygens():
           f"{os.path.getsize(path) / 1024:.0f} KiB")
 
 
+def wavefront_ref_scalars(lens, strategy, field, wl):
+    """Reference-sphere scalars of ChiefRayStrategy.compute_wavefront_data (steps 1-2,
+    optiland/wavefront/strategy.py:160-170), computed with the reference's own methods."""
+    chief = lens.trace_generic(*field, Px=0.0, Py=0.0, wavelength=wl)
+    geometry = strategy._create_reference_geometry(chief)
+    opd_img_ref = geometry.path_length(chief, strategy.n_image)
+    opd_ref = strategy._correct_tilt(field, chief.opd - opd_img_ref, x=0, y=0)
+    tilt = (0.0, 0.0)
+    fd = lens.fields.field_definition
+    if type(fd).__name__ == "AngleField" and lens.object_surface.is_infinite:   # strategy.py:112-138
+        tx = np.tan(np.deg2rad(field[0] * float(lens.fields.max_field)))
+        ty = np.tan(np.deg2rad(field[1] * float(lens.fields.max_field)))
+        uz = 1.0 / np.sqrt(1.0 + tx**2 + ty**2)
+        epd = float(lens.paraxial.EPD())
+        tilt = (tx * uz * epd / 2, ty * uz * epd / 2)
+    return {"center": np.array([float(v) for v in geometry.center]), "radius": float(geometry.radius),
+            "n_image": float(np.ravel(strategy.n_image)[0]), "tilt": np.array(tilt),
+            "opd_ref": float(np.ravel(opd_ref)[0]), "wavelength_um": float(wl)}
+
+
+def case_wavefront():
+    """f-2 (second half): the reference's Wavefront analysis, chief-ray strategy, spherical reference."""
+    from optiland.wavefront import Wavefront
+
+    out = {}
+    for tag, lens, field, wl in (("dgauss", DoubleGauss(), (0.0, 0.7), 0.5876),
+                                 ("cooke", CookeTriplet(), (0.0, 1.0), 0.55),
+                                 ("finite", finite_relay("object_height"), (2.0 / 9.0, 1.0), 0.5876),
+                                 ("hubble", HubbleTelescope(), (0.0, 1.0), 0.55)):
+        w = Wavefront(lens, fields=[field], wavelengths=[wl], num_rays=12, distribution="hexapolar", strategy="chief_ray")
+        data = w.get_data(field, wl)
+        ref = wavefront_ref_scalars(lens, w.strategy, field, wl)
+        tab = pack_surface_group(lens.surfaces, [wl])
+        sc = launch_scalars(lens, field[0], field[1])
+        out.update({f"{tag}_{k}": v for k, v in tab.to_arrays().items()})
+        out.update({f"{tag}_launch_{k}": v for k, v in sc.items()})
+        out.update({f"{tag}_ref_{k}": v for k, v in ref.items()})
+        out.update({f"{tag}_Px": np.array(w.distribution.x), f"{tag}_Py": np.array(w.distribution.y),
+                    f"{tag}_opd": np.array(data.opd), f"{tag}_pupil_x": np.array(data.pupil_x),
+                    f"{tag}_pupil_y": np.array(data.pupil_y), f"{tag}_pupil_z": np.array(data.pupil_z),
+                    f"{tag}_intensity": np.array(data.intensity), f"{tag}_radius": float(data.radius)})
+        print(f"wavefront {tag:8s} N={np.size(data.opd)} opd rms {float(np.std(np.array(data.opd))):.4f} waves "
+              f"R={float(data.radius):.3f} tilt={ref['tilt']}")
+    path = os.path.join(OUT, "wavefront_chief_ray_ref.npz")
+    np.savez_compressed(path, **out)
+    print("wavefront_chief_ray_ref", f"{os.path.getsize(path) / 1024:.0f} KiB")
+
+
 def finite_relay(field_type):
     """Finite-conjugate 1:1-ish relay doublet: object 120 mm in front, `field_type` fields."""
     lens = _optic.Optic()
@@ -438,6 +486,7 @@ def main():
     case_more_geometries()
     case_huygens()
     case_finite_objects()
+    case_wavefront()
     case_autograd()
 
 
@@ -488,6 +537,9 @@ if __name__ == "__main__":
         case_more_geometries()
     elif len(sys.argv) > 1 and sys.argv[1] == "autograd":
         case_autograd()
+    elif len(sys.argv) > 1 and sys.argv[1] == "wavefront":
+        be.set_backend("numpy")
+        case_wavefront()
     elif len(sys.argv) > 1 and sys.argv[1] == "finite":
         be.set_backend("numpy")
         case_finite_objects()

@@ -59,6 +59,21 @@ class OracleEngine:
         _, rec, status = O.trace(table, inp)
         return {k: torch.from_numpy(v).to(Px.dtype) for k, v in rec.items()}
 
+    def trace_wavefront(self, table, Px, Py, affine, ref):
+        import torch
+
+        from oracle import trace_oracle as O
+        from optiland_b200.launch import launch_from_affine
+
+        self.calls.append(("wavefront", table.num_surfaces, int(Px.numel())))
+        px, py = Px.detach().double().numpy(), Py.detach().double().numpy()
+        x, y, z, L, M, N = launch_from_affine(px, py, affine)
+        inp = dict(x=x, y=y, z=z, L=L, M=M, N=N, i=np.full_like(px, affine.get("intensity", 1.0)),
+                   w=np.full_like(px, table.wavelengths[0]))
+        fin, _, _ = O.trace(table, inp)
+        out = O.wavefront_reference_sphere(fin, px, py, ref)
+        return {k: torch.from_numpy(np.asarray(v)).to(Px.dtype) for k, v in out.items()}
+
     def huygens_psf(self, image_x, image_y, image_z, pupil_x, pupil_y, pupil_z, pupil_amp, pupil_opd, wavelength, Rp):
         import torch
 

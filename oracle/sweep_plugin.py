@@ -38,6 +38,6 @@ if os.environ.get("OLB_SWEEP_INSTALL") == "1":
 def pytest_terminal_summary(terminalreporter):
     if ENGINE is not None:
         n_grad = sum(1 for c in ENGINE.calls if c and c[0] == "grad")
-        n_pupil = sum(1 for c in ENGINE.calls if c and c[0] == "pupil")
+        n_pupil = sum(1 for c in ENGINE.calls if c and c[0] in ("pupil", "wavefront"))
         terminalreporter.write_line(f"[olb sweep] capability calls: {len(ENGINE.calls)} (differentiable: {n_grad}, "
                                     f"fused launch: {n_pupil})")

@@ -768,3 +768,33 @@ def huygens_fresnel_psf(image_x, image_y, image_z, pupil_x, pupil_y, pupil_z, pu
         field[p] = np.sum(amp * phase * wave * (0.5 * (1.0 + dot / R)))
     field = field.reshape(shape)
     return np.abs(field) ** 2, field
+
+
+def wavefront_reference_sphere(fin: dict, Px, Py, ref: dict) -> dict:
+    """Steps 4-5 of ChiefRayStrategy.compute_wavefront_data (optiland/wavefront/strategy.py:179-190) for a
+    spherical reference: SphericalReference.path_length (optiland/wavefront/reference_geometry.py:55-82), the
+    launch-plane tilt term of _correct_tilt (strategy.py:93-139, pre-multiplied: tilt = (ux EPD/2, uy EPD/2)),
+    the OPD in waves and the exit-pupil intercepts.  ``fin``: final GLOBAL ray state (x y z L M N opd i)."""
+    f8 = np.float64
+    xr, yr, zr = (np.asarray(fin[k], dtype=f8) for k in "xyz")
+    Lf, Mf, Nf = (np.asarray(fin[k], dtype=f8) for k in "LMN")
+    xc, yc, zc = (float(v) for v in ref["center"])
+    R, n_img = float(ref["radius"]), float(ref["n_image"])
+    L, M, N = -Lf, -Mf, -Nf
+    with np.errstate(all="ignore"):
+        a = L**2 + M**2 + N**2
+        b = 2 * (L * (xr - xc) + M * (yr - yc) + N * (zr - zc))
+        c = xr**2 + yr**2 + zr**2 - 2 * (xr * xc + yr * yc + zr * zc) + xc**2 + yc**2 + zc**2 - R**2
+        d = b**2 - 4 * a * c
+        d = np.where(d < 0, 0, d)
+        t1 = (-b - np.sqrt(d)) / (2 * a)
+        t2 = (-b + np.sqrt(d)) / (2 * a)
+        t = np.where(t1 < 0, t2, t1)
+        opd_img = n_img * t
+        tilt = ref.get("tilt", (0.0, 0.0))
+        opd = np.asarray(fin["opd"], dtype=f8) - opd_img + (float(tilt[0]) * np.asarray(Px, dtype=f8)
+                                                            + float(tilt[1]) * np.asarray(Py, dtype=f8))
+        opd_wv = (float(ref["opd_ref"]) - opd) / (float(ref["wavelength_um"]) * 1e-3)
+        tt = opd_img / n_img
+        return {"opd": opd_wv, "pupil_x": xr - tt * Lf, "pupil_y": yr - tt * Mf, "pupil_z": zr - tt * Nf,
+                "intensity": np.asarray(fin["i"], dtype=f8)}

@@ -142,6 +142,17 @@ int olbhc_trace_f32(const OlbTable* tab, int first, int last, int64_t n, float**
                     float* pmat, int* status, char* err, int err_len) {
   return run<float>(tab, first, last, n, ray, rec, l0, pmat, status, err, err_len);
 }
+// wavefront epilogue (olb_math.cuh::wavefront_point) over n rays: fin = x y z L M N opd (fp64), ref = the 9
+// doubles of WavefrontRef, out = opd_wv, pupil_x, pupil_y, pupil_z
+int olbhc_wavefront(int64_t n, double** fin, const double* Px, const double* Py, const double* ref, double** out) {
+  WavefrontRef w;
+  w.c[0] = ref[0]; w.c[1] = ref[1]; w.c[2] = ref[2]; w.R = ref[3]; w.n_image = ref[4];
+  w.tilt[0] = ref[5]; w.tilt[1] = ref[6]; w.opd_ref = ref[7]; w.inv_wl = ref[8];
+  for (int64_t k = 0; k < n; ++k)
+    wavefront_point(fin[0][k], fin[1][k], fin[2][k], fin[3][k], fin[4][k], fin[5][k], fin[6][k], Px[k], Py[k], w,
+                    out[0][k], out[1][k], out[2][k], out[3][k]);
+  return 0;
+}
 int olbhc_features(const OlbTable* tab) {
   PrepResult pr = prepare_table(*tab);
   return pr.error.empty() ? (int)pr.features : -1;

@@ -106,6 +106,42 @@ def test_optic_trace_fused_launch_for_finite_and_telecentric_objects(plugin):
             np.testing.assert_allclose(be.to_numpy(getattr(rays, k)), v, rtol=0, atol=1e-11 * scale, err_msg=k)
 
 
+def test_wavefront_analysis_uses_the_fused_epilogue(plugin):
+    """f-2: Wavefront(strategy='chief_ray') under the plugin == the NumPy reference, and the full-grid trace
+    went through the wavefront capability (5 values per ray, no records)."""
+    P, eng, be = plugin
+    from optiland.samples.objectives import CookeTriplet
+    from optiland.wavefront import Wavefront
+
+    from oracle.make_golden import finite_relay
+
+    for make, field, wl in ((CookeTriplet, (0.0, 0.7), 0.55), (lambda: finite_relay("object_height"), (0.0, 1.0), 0.5876)):
+        def run(lens):
+            w = Wavefront(lens, fields=[field], wavelengths=[wl], num_rays=8, distribution="hexapolar", strategy="chief_ray")
+            d = w.get_data(field, wl)
+            return {k: np.array(be.to_numpy(getattr(d, k)), dtype=np.float64) for k in ("opd", "pupil_x", "pupil_y", "pupil_z", "intensity")}, \
+                float(np.asarray(be.to_numpy(d.radius)).reshape(-1)[0])
+
+        be.set_backend("numpy")
+        want, Rw = run(make())
+        be.set_backend("torch")
+        n0 = len(eng.calls)
+        got, Rg = run(make())
+        assert any(c[0] == "wavefront" for c in eng.calls[n0:]), eng.calls[n0:]
+        assert Rg == pytest.approx(Rw, rel=1e-12)
+        for k in want:
+            np.testing.assert_allclose(got[k], want[k], rtol=0, atol=1e-6 if k == "opd" else 1e-10, err_msg=k)
+    # the reference path is still there when the fusion is switched off
+    P._state["fuse_wavefront"] = False
+    try:
+        n0 = len(eng.calls)
+        lens = CookeTriplet()
+        Wavefront(lens, fields=[(0.0, 0.7)], wavelengths=[0.55], num_rays=6, distribution="hexapolar", strategy="chief_ray")
+        assert not any(c[0] == "wavefront" for c in eng.calls[n0:])
+    finally:
+        P._state["fuse_wavefront"] = True
+
+
 def test_spot_diagram_runs_unchanged_on_top(plugin):
     """Config 1: analysis layer untouched; golden RMS radii of /root/reference/tests/test_analysis.py:88-102."""
     P, eng, be = plugin

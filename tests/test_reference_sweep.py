@@ -44,10 +44,11 @@ def test_reference_tests_unchanged_with_plugin(fname):
 
 
 @pytest.mark.timeout(900)
-@pytest.mark.parametrize("fname", ["analysis/test_spot_reference.py"])
+@pytest.mark.parametrize("fname", ["analysis/test_spot_reference.py", "test_wavefront.py"])
 def test_reference_tests_unchanged_with_plugin_grad_mode_off(fname):
     """Same with be.grad_mode left off (the reference's conftest normally turns it on): now the plain trace
-    and the fused in-kernel launch generation (RealRayTracer.trace wrapper) carry the calls."""
+    and the fused in-kernel launch generation (RealRayTracer.trace wrapper) carry the calls; for
+    test_wavefront.py the reference's OPD goldens are then computed by the fused wavefront epilogue."""
     stock, _ = _run(fname, install=False, nograd=True)
     ours, calls = _run(fname, install=True, nograd=True)
     assert stock.get("passed", 0) > 0 and ours == stock, (fname, stock, ours)
