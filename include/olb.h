@@ -69,6 +69,8 @@ extern "C" {
                                       optiland/geometries/biconic.py:72-160      */
 #define OLB_GEOM_TOROIDAL      9   /* Y-Z conic + even polynomial curve rotated about an
                                       axis at distance R_rot: optiland/geometries/toroidal.py:87-232 */
+#define OLB_GEOM_FORBES_QBFS  10   /* conic + phi(r) u^2 (1 - u^2) sum a_m Q_m(u^2), u = r / norm_radius, Forbes'
+                                      slope-orthogonal Q polynomials: optiland/geometries/forbes/geometry.py:187-366 */
 
 /* ---- OlbSurface.flags --------------------------------------------------- */
 #define OLB_SF_REFLECT     (1u << 0)  /* is_reflective: rays.reflect instead of refract
@@ -168,6 +170,9 @@ typedef struct OlbSurface {
  *   TOROIDAL     : {radius_rot, conic_yz} then n_coef doubles alpha_i (term alpha_i y^(2(i+1)));
  *                  OlbSurface.radius holds the Y-Z base radius, OlbSurface.conic must be 0 (the
  *                  reference starts Newton from that SPHERE, toroidal.py:71-73)
+ *   FORBES_QBFS  : n_coef doubles a_0 .. a_M (missing radial orders = 0); OlbSurface.norm_radius = rho_max.
+ *                  The change of basis to the Clenshaw form (geometries/forbes/qpoly.py:56-115) happens in
+ *                  olb_table_upload.
  *   ZERNIKE      : n_coef terms, each 4 doubles {n, m, c*N_nm (sag), c (derivative)}
  *                  -- the reference's derivative path omits the normalisation
  *                  constant N_nm (optiland/zernike/base.py:104-136 vs :42-68);

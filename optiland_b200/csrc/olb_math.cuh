@@ -284,8 +284,79 @@ OLB_HD void toroidal_yz(T y, const PrepSurface<T>& S, const T* pool, T& zy, T& d
   dzy = o_fma(hd, y, dzy);
 }
 
+// Forbes Q (slope-orthogonal, "Q^bfs") radial surface, forbes/geometry.py:187-366.  S(x) = sum a_m Q_m(x) and
+// dS/dx by the Clenshaw recurrences of qpoly.py:131-143, 185-212 on the change-of-basis coefficients b
+// (prepared on the host): alpha_n = b_n + p alpha_{n+1} - alpha_{n+2}, p = 2 - 4x, S = 2 (alpha_0 + alpha_1);
+// alpha'_n = p alpha'_{n+1} - alpha'_{n+2} - 4 alpha_{n+1}, dS/dx = 2 (alpha'_0 + alpha'_1).
+template <typename T>
+OLB_HD void forbes_q_sum(const T* b, int nc, T x, T& S, T& dS) {
+  const T p = (T)2 - (T)4 * x;
+  T a1 = 0, a2 = 0, d1 = 0, d2 = 0;          // alpha_{n+1}, alpha_{n+2}, alpha'_{n+1}, alpha'_{n+2}
+  T a0 = 0, d0 = 0;
+  for (int n = nc - 1; n >= 0; --n) {
+    a0 = b[n] + p * a1 - a2;
+    d0 = p * d1 - d2 - (T)4 * a1;
+    if (n > 0) { a2 = a1; a1 = a0; d2 = d1; d1 = d0; }
+  }
+  if (nc > 1) { S = (T)2 * (a0 + a1); dS = (T)2 * (d0 + d1); }
+  else { S = (T)2 * a0; dS = (T)2 * d0; }
+}
+// conic correction factor phi and d phi / d rho (geometry.py:152-181)
+template <typename T>
+OLB_HD void forbes_phi(T r2, const PrepSurface<T>& S, T& phi, T& dphi) {
+  if (S.flags & PSF_RADIUS_INF) { phi = 1; dphi = 0; return; }
+  const T c2 = S.curv * S.curv;
+  T na = (T)1 - S.conic * c2 * r2, da = (T)1 - S.kp1 * c2 * r2;
+  na = na > 0 ? na : (T)1e-12;
+  da = da > 0 ? da : (T)1e-12;
+  const T Nn = o_sqrt(na), D = o_sqrt(da);
+  phi = o_div(Nn, D);
+  dphi = o_div(c2 * o_sqrt(r2), Nn * D * D * D);
+}
+template <typename T>
+OLB_HD T forbes_sag(T x, T y, const PrepSurface<T>& S, const T* pool) {
+  const T r2 = o_fma(x, x, y * y);
+  T zb = 0;                                              // _base_sag: radicand clamped at 0 (geometry.py:119-133)
+  if (!(S.flags & PSF_RADIUS_INF)) {
+    T arg = (T)1 - S.kp1 * r2 * S.curv * S.curv;
+    zb = o_div(r2 * S.curv, (T)1 + o_sqrt(arg < 0 ? (T)0 : arg));
+  }
+  const T usq = r2 * S.inv_norm * S.inv_norm;
+  if (S.n_coef == 0 || usq > (T)1) return zb;           // no terms / outside the normalisation radius: base conic
+  T Sx, dS, phi, dphi;
+  forbes_q_sum(pool + S.coef_off, S.n_coef, usq, Sx, dS);
+  forbes_phi(r2, S, phi, dphi);
+  return zb + usq * ((T)1 - usq) * phi * Sx;
+}
+template <typename T>
+OLB_HD void forbes_slopes(T x, T y, const PrepSurface<T>& S, const T* pool, T& fx, T& fy) {
+  const T eps = (T)1e-12;
+  const T r2 = o_fma(x, x, y * y);
+  const T rho = o_sqrt(r2 + eps * eps);                  // rho_safe (geometry.py:345)
+  T df = 0;                                              // _base_sag_derivative (geometry.py:135-149)
+  if (!(S.flags & PSF_RADIUS_INF) && S.curv != 0) {
+    T arg = (T)1 - S.kp1 * S.curv * S.curv * r2;
+    df = o_div(S.curv * rho, o_sqrt(arg > 0 ? arg : (T)1e-12));
+  }
+  if (S.n_coef > 0) {
+    const T u = rho * S.inv_norm, usq = u * u;
+    if (!(u >= (T)1)) {
+      T Sx, dS, phi, dphi;
+      forbes_q_sum(pool + S.coef_off, S.n_coef, usq, Sx, dS);
+      forbes_phi(r2, S, phi, dphi);
+      const T dpoly_drho = dS * (T)2 * u * S.inv_norm;
+      const T dpref = ((T)2 * u - (T)4 * u * usq) * S.inv_norm;
+      const T pre = usq - usq * usq;
+      df += dpref * phi * Sx + pre * dphi * Sx + pre * phi * dpoly_drho;
+    }
+  }
+  fx = df * o_div(x, rho);
+  fy = df * o_div(y, rho);
+}
+
 template <typename T>
 OLB_HD T newton_sag(T x, T y, const PrepSurface<T>& S, const T* pool, int& status) {
+  if (S.kind == OLB_GEOM_FORBES_QBFS) return forbes_sag(x, y, S, pool);
   if (S.kind == OLB_GEOM_BICONIC) return biconic_profile(x, S.curv, S.kp1) + biconic_profile(y, S.curv_y, S.kp1_y);
   if (S.kind == OLB_GEOM_TOROIDAL) {
     T zy, dzy;
@@ -327,6 +398,7 @@ OLB_HD T newton_sag(T x, T y, const PrepSurface<T>& S, const T* pool, int& statu
 // reproducing the reference's eps-regularised chain rule).
 template <typename T>
 OLB_HD void newton_slopes(T x, T y, const PrepSurface<T>& S, const T* pool, T& fx, T& fy) {
+  if (S.kind == OLB_GEOM_FORBES_QBFS) { forbes_slopes(x, y, S, pool, fx, fy); return; }
   if (S.kind == OLB_GEOM_BICONIC) {                     // biconic.py:107-160
     fx = biconic_slope(x, S.curv, S.kp1);
     fy = biconic_slope(y, S.curv_y, S.kp1_y);

@@ -226,7 +226,7 @@ static inline PrepResult prepare_table(const OlbTable& tab) {
     o.flags = in.flags & 0xffu;
     o.max_iter = in.max_iter;
     o.coating = in.coating;
-    if (in.kind < OLB_GEOM_NOOP || in.kind > OLB_GEOM_TOROIDAL) { res.error = "unknown geometry kind"; return res; }
+    if (in.kind < OLB_GEOM_NOOP || in.kind > OLB_GEOM_FORBES_QBFS) { res.error = "unknown geometry kind"; return res; }
 
     // ---- pose --------------------------------------------------------------
     if (in.kind != OLB_GEOM_NOOP) {
@@ -342,6 +342,36 @@ static inline PrepResult prepare_table(const OlbTable& tab) {
       o.coef_off = (int)pool.size();
       for (int i = 0; i < in.n_coef; ++i) pool.push_back(tab.pool[in.coef_off + 2 + i]);
       while (pool.size() % 4) pool.push_back(0);
+    } else if (in.kind == OLB_GEOM_FORBES_QBFS) {
+      if (in.n_coef < 0 || in.n_coef > 64 || !in_pool(in.coef_off, in.n_coef)) { res.error = "bad Forbes coefficient block"; return res; }
+      if (!(in.norm_radius > 0)) { res.error = "Forbes norm_radius must be positive"; return res; }
+      // Change of basis a_m -> b_m of the orthonormal polynomials the Clenshaw recurrence runs on
+      // (G. W. Forbes, Opt. Express 18, 19700 (2010), eqs. A.14-A.16; geometries/forbes/qpoly.py:56-115):
+      //   f_0 = 2, f_1 = sqrt(19)/2, g_0 = -1/2, h_{n-2} = -n(n-1) / (2 f_{n-2}),
+      //   g_{n-1} = -(1 + g_{n-2} h_{n-2}) / f_{n-1}, f_n = sqrt(n(n+1) + 3 - g_{n-1}^2 - h_{n-2}^2)
+      const int nc = in.n_coef;
+      std::vector<double> f(nc + 2), g(nc + 2), h(nc + 2), b(nc, 0.0);
+      for (int n = 0; n < nc; ++n) {
+        if (n == 0) f[0] = 2.0;
+        else if (n == 1) { g[0] = -0.5; f[1] = std::sqrt(19.0) / 2.0; }
+        else {
+          h[n - 2] = -(double)n * (n - 1) / (2.0 * f[n - 2]);
+          g[n - 1] = -(1.0 + g[n - 2] * h[n - 2]) / f[n - 1];
+          f[n] = std::sqrt((double)n * (n + 1) + 3.0 - g[n - 1] * g[n - 1] - h[n - 2] * h[n - 2]);
+        }
+      }
+      const double* a = tab.pool + in.coef_off;
+      const int m = nc - 1;
+      bool all_zero = true;
+      for (int i = 0; i < nc; ++i) all_zero = all_zero && a[i] == 0.0;
+      if (m >= 0) b[m] = a[m] / f[m];
+      if (m >= 1) b[m - 1] = (a[m - 1] - g[m - 1] * b[m]) / f[m - 1];
+      for (int i = m - 2; i >= 0; --i) b[i] = (a[i] - g[i] * b[i + 1] - h[i] * b[i + 2]) / f[i];
+      o.n_coef = all_zero ? 0 : nc;    // no / all-zero terms: the reference's slope takes the base-conic branch
+      o.coef_off = (int)pool.size();
+      for (int i = 0; i < nc; ++i) pool.push_back(b[i]);
+      while (pool.size() % 4) pool.push_back(0);
+      o.inv_norm = 1.0 / in.norm_radius;
     } else if (in.kind == OLB_GEOM_ZERNIKE) {
       if (!in_pool(in.coef_off, 4 * in.n_coef)) { res.error = "Zernike block outside pool"; return res; }
       if (!(in.norm_radius > 0)) { res.error = "Zernike norm_radius must be positive"; return res; }

@@ -95,6 +95,9 @@ class _Prefetch:
                 c = getattr(g, k, None)
                 if isinstance(c, (list, tuple)):
                     self._add([u for row in c for u in (row if isinstance(row, (list, tuple)) else [row])])
+            rt = getattr(g, "radial_terms", None)
+            if isinstance(rt, dict):
+                self._add(list(rt.values()))
             z = getattr(g, "zernike", None)
             if z is not None:
                 self._add(list(getattr(z, "coeffs", [])))
@@ -208,6 +211,8 @@ _GEOM_KINDS = {
     "ChebyshevPolynomialGeometry": T.GEOM_CHEBYSHEV,
     "BiconicGeometry": T.GEOM_BICONIC,
     "ToroidalGeometry": T.GEOM_TOROIDAL,
+    "ForbesQNormalSlopeGeometry": T.GEOM_FORBES_QBFS,
+    "ForbesQbfsGeometry": T.GEOM_FORBES_QBFS,       # deprecated alias class (forbes/geometry.py:733-759)
 }
 
 
@@ -262,6 +267,13 @@ def pack_surface(surface, wavelengths) -> T.SurfaceSpec:
         spec.radius_y = _f(g.R_rot)
         spec.conic_y = _f(g.k_yz)
         spec.coefficients = np.array([_f(c) for c in g.coeffs_poly_y], dtype=np.float64)
+    elif kind == T.GEOM_FORBES_QBFS:
+        # radial_terms {order: a_n}; missing orders are zero (forbes/geometry.py:258-274)
+        terms = {int(n): _f(v) for n, v in (g.radial_terms or {}).items()}
+        if any(n < 0 for n in terms):
+            raise UnsupportedSurface("Forbes radial term with a negative order")
+        spec.coefficients = np.array([terms.get(n, 0.0) for n in range(max(terms) + 1)] if terms else [], dtype=np.float64)
+        spec.norm_radius = _f(g.norm_radius)
     elif kind == T.GEOM_ZERNIKE:
         z = g.zernike
         coeffs = [_f(c) for c in z.coeffs]

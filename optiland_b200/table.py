@@ -29,6 +29,7 @@ GEOM_POLYNOMIAL = 6
 GEOM_CHEBYSHEV = 7
 GEOM_BICONIC = 8
 GEOM_TOROIDAL = 9
+GEOM_FORBES_QBFS = 10
 
 SF_REFLECT = 1 << 0
 SF_ROTATED = 1 << 1
@@ -58,7 +59,7 @@ MAX_SURFACES = 64
 MAX_WAVELENGTHS = 16
 
 NEWTON_KINDS = (GEOM_EVEN_ASPHERE, GEOM_ZERNIKE, GEOM_ODD_ASPHERE, GEOM_POLYNOMIAL, GEOM_CHEBYSHEV, GEOM_BICONIC,
-                GEOM_TOROIDAL)
+                GEOM_TOROIDAL, GEOM_FORBES_QBFS)
 
 # numpy mirror of `struct OlbSurface` (192 bytes)
 OLB_SURFACE_DTYPE = np.dtype(

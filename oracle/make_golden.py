@@ -390,6 +390,30 @@ def case_huygens():
           f"{os.path.getsize(path) / 1024:.0f} KiB")
 
 
+def case_forbes():
+    """Forbes Q (slope-orthogonal) radial aspheres (geometries/forbes/geometry.py:187-366): a singlet with two
+    forbes_qbfs surfaces (one with a conic base), rays reaching beyond the normalisation radius on the second
+    (departure switched off there) and a chief ray through the vertex."""
+    lens = _optic.Optic()
+    lens.surfaces.add(index=0, radius=be.inf, thickness=be.inf)
+    lens.surfaces.add(index=1, radius=22.0, thickness=6.0, material="N-BK7", is_stop=True, conic=-0.4,
+                      radial_terms={0: 0.12, 1: -0.041, 2: 0.013, 3: -0.006, 5: 0.002}, norm_radius=9.0,
+                      surface_type="forbes_qbfs", tol=1e-10)
+    lens.surfaces.add(index=2, radius=-31.0, thickness=28.0, conic=0.0,
+                      radial_terms={0: -0.27, 1: 0.087, 2: -0.048, 3: 0.026, 4: -0.012}, norm_radius=6.5,
+                      surface_type="forbes_qbfs", tol=1e-10)
+    lens.surfaces.add(index=3)
+    lens.set_aperture(aperture_type="EPD", value=15.0)
+    lens.fields.set_type(field_type="angle")
+    lens.fields.add(y=0)
+    lens.fields.add(y=4)
+    lens.wavelengths.add(value=0.55, is_primary=True)
+    Px, Py = disk(500, seed=31)
+    Px[0] = Py[0] = 0.0
+    rays = gen(lens, np.zeros(Px.size), np.concatenate([[0.0], np.full(Px.size - 1, 0.6)]), Px, Py, 0.55)
+    run_case("forbes_qbfs", lens, rays, [0.55])
+
+
 def wavefront_ref_scalars(lens, strategy, field, wl):
     """Reference-sphere scalars of ChiefRayStrategy.compute_wavefront_data (steps 1-2,
     optiland/wavefront/strategy.py:160-170), computed with the reference's own methods."""
@@ -486,6 +510,7 @@ def main():
     case_more_geometries()
     case_huygens()
     case_finite_objects()
+    case_forbes()
     case_wavefront()
     case_autograd()
 
@@ -537,6 +562,9 @@ if __name__ == "__main__":
         case_more_geometries()
     elif len(sys.argv) > 1 and sys.argv[1] == "autograd":
         case_autograd()
+    elif len(sys.argv) > 1 and sys.argv[1] == "forbes":
+        be.set_backend("numpy")
+        case_forbes()
     elif len(sys.argv) > 1 and sys.argv[1] == "wavefront":
         be.set_backend("numpy")
         case_wavefront()

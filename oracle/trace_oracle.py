@@ -439,6 +439,9 @@ def _sag_and_normal_fns(s: T.SurfaceSpec, status):
     if s.kind == T.GEOM_TOROIDAL:
         Rr, kyz, cf = s.radius_y, s.conic_y, list(s.coefficients)
         return (lambda x, y: toroidal_sag(x, y, Rr, R, kyz, cf)), (lambda x, y: toroidal_normal(x, y, Rr, R, kyz, cf))
+    if s.kind == T.GEOM_FORBES_QBFS:
+        a, nr = list(s.coefficients), s.norm_radius
+        return (lambda x, y: forbes_qbfs_sag(x, y, R, k, a, nr)), (lambda x, y: forbes_qbfs_normal(x, y, R, k, a, nr))
     if s.kind == T.GEOM_ZERNIKE:
         terms = s.coefficients.reshape(-1, 4)
         nr = s.norm_radius
@@ -447,6 +450,118 @@ def _sag_and_normal_fns(s: T.SurfaceSpec, status):
             lambda x, y: zernike_normal(x, y, R, k, terms, nr),
         )
     raise ValueError(f"not a Newton geometry: {s.kind}")
+
+
+# ---- Forbes Q (slope-orthogonal, "Q^bfs") radial surfaces -------------------------------------------------
+def _qbfs_fgh(nmax):
+    """Recurrence coefficients of the Q^bfs basis (optiland/geometries/forbes/qpoly.py:56-84; G. W. Forbes,
+    Opt. Express 18, 19700 (2010))."""
+    f, g, h = {0: 2.0, 1: np.sqrt(19.0) / 2}, {0: -0.5}, {}
+    for n in range(2, nmax + 1):
+        h[n - 2] = -n * (n - 1) / (2 * f[n - 2])
+        g[n - 1] = -(1 + g[n - 2] * h[n - 2]) / f[n - 1]
+        f[n] = np.sqrt(n * (n + 1) + 3 - g[n - 1] ** 2 - h[n - 2] ** 2)
+    return f, g, h
+
+
+def _qbfs_change_basis(cs):
+    """qpoly.py:87-115."""
+    m = len(cs) - 1
+    if m < 0:
+        return []
+    f, g, h = _qbfs_fgh(m)
+    bs = [0.0] * (m + 1)
+    bs[m] = cs[m] / f[m]
+    if m >= 1:
+        bs[m - 1] = (cs[m - 1] - g[m - 1] * bs[m]) / f[m - 1]
+    for i in range(m - 2, -1, -1):
+        bs[i] = (cs[i] - g[i] * bs[i + 1] - h[i] * bs[i + 2]) / f[i]
+    return bs
+
+
+def _qbfs_sum(cs, usq, want_derivative=False):
+    """clenshaw_qbfs / clenshaw_qbfs_der (qpoly.py:131-143, 146-162, 185-212): S and dS/d(usq)."""
+    bs = _qbfs_change_basis(cs)
+    m = len(bs) - 1
+    if m < 0:
+        z = np.zeros_like(usq)
+        return (z, z) if want_derivative else z
+    prefix = 2 - 4 * usq
+    al = [None] * (m + 1)
+    al[m] = bs[m] + np.zeros_like(usq)
+    if m > 0:
+        al[m - 1] = bs[m - 1] + prefix * al[m]
+    for i in range(m - 2, -1, -1):
+        al[i] = bs[i] + prefix * al[i + 1] - al[i + 2]
+    S = 2 * (al[0] + al[1]) if m > 0 else 2 * al[0]
+    if not want_derivative:
+        return S
+    d = [np.zeros_like(usq) for _ in range(m + 1)]
+    if m - 1 >= 0:
+        d[m - 1] = -4 * al[m]
+    if m - 2 >= 0:
+        d[m - 2] = prefix * d[m - 1] - 4 * al[m - 1]
+    for n in range(m - 3, -1, -1):
+        d[n] = prefix * d[n + 1] - d[n + 2] - 4 * al[n + 1]
+    dS = 2 * (d[0] + d[1]) if m > 0 else 2 * d[0]
+    return S, dS
+
+
+def _forbes_phi(r2, radius, k):
+    """_conic_correction_factor, forbes/geometry.py:152-181."""
+    if np.isinf(radius):
+        return 1.0, 0.0
+    c2 = (1.0 / radius) ** 2
+    rho = np.sqrt(r2)
+    num, den = 1 - k * c2 * r2, 1 - (k + 1) * c2 * r2
+    Nn = np.sqrt(np.where(num > 0, num, 1e-12))
+    D = np.sqrt(np.where(den > 0, den, 1e-12))
+    return Nn / D, (c2 * rho) / (Nn * D**3)
+
+
+def forbes_qbfs_sag(x, y, radius, k, a, norm_radius):
+    """ForbesQNormalSlopeGeometry.sag, forbes/geometry.py:276-298."""
+    with np.errstate(all="ignore"):
+        r2 = x**2 + y**2
+        if np.isinf(radius):
+            zb = np.zeros_like(r2)
+        else:
+            arg = 1 - (1 + k) * r2 / radius**2
+            zb = r2 / (radius * (1 + np.sqrt(np.where(arg < 0, 0, arg))))
+        usq = r2 / norm_radius**2
+        phi, _ = _forbes_phi(r2, radius, k)
+        dep = usq * (1 - usq) * phi * _qbfs_sum(a, usq)
+        return zb + np.where(usq > 1, 0.0, dep)
+
+
+def forbes_qbfs_normal(x, y, radius, k, a, norm_radius):
+    """_surface_normal / _surface_normal_analytical (NumPy branch), forbes/geometry.py:300-366."""
+    eps = 1e-12
+    with np.errstate(all="ignore"):
+        r2 = x**2 + y**2
+        rho = np.sqrt(r2 + eps**2)
+        if np.isinf(radius) or radius == 0:
+            dbase = np.zeros_like(rho)
+        else:
+            c = 1.0 / radius
+            arg = 1 - (k + 1) * c**2 * r2
+            dbase = c * rho / np.sqrt(np.where(arg > 0, arg, 1e-12))
+        if len(a) == 0 or all(v == 0 for v in a):
+            df = dbase
+        else:
+            u = rho / norm_radius
+            Sx, dS = _qbfs_sum(a, u**2, want_derivative=True)
+            dpoly_du = dS * 2 * u
+            dpref = (2 * u - 4 * u**3) / norm_radius
+            dpoly_drho = dpoly_du / norm_radius
+            phi, dphi = _forbes_phi(r2, radius, k)
+            usq = u**2
+            dep = dpref * phi * Sx + (usq - usq**2) * dphi * Sx + (usq - usq**2) * phi * dpoly_drho
+            df = dbase + np.where(u >= 1, 0.0, dep)
+        dfdx, dfdy = df * (x / rho), df * (y / rho)
+        mag = np.sqrt(dfdx**2 + dfdy**2 + 1)
+        mag = np.where(mag < eps, 1.0, mag)
+        return dfdx / mag, dfdy / mag, -1 / mag
 
 
 def newton_distance(x, y, z, L, M, N, s: T.SurfaceSpec, sag, normal):
