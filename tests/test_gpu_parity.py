@@ -474,6 +474,43 @@ def test_c_abi_error_codes_on_device_calls():
     assert call(_lib.OlbRays(**good), nn=0) == 0          # empty batch: nothing to do
     fake = _lib.OlbDeviceTable()
     assert lib.olb_trace_f32(C.byref(fake), 0, 1, C.byref(_lib.OlbRays(**good)), None, n, 0, None, stream) == -1
+    # wavefront epilogue: argument validation
+    from optiland_b200.launch import pupil_affine
+    from optiland_b200.trace import _c_launch
+
+    sc = {k[9:]: float(c.z[k]) for k in c.z.files if k.startswith("x_launch_")}
+    P = torch.zeros(n, dtype=torch.float32, device="cuda")
+    la = _c_launch(pupil_affine(sc), P, P)
+    out = _lib.OlbWavefrontOut(*ptrs[:5])
+    ref = _lib.OlbWavefrontRef()
+    ref.radius, ref.n_image, ref.wavelength_um = 100.0, 1.0, 0.55
+
+    def wf(ref_, out_, launch=la, last=13):
+        return lib.olb_trace_wavefront_f32(C.byref(dt.c), 0, last, C.byref(launch) if launch is not None else None,
+                                           C.byref(_lib.OlbRays(**good)), None, n, _lib.TF_NO_FINAL, C.byref(ref_),
+                                           C.byref(out_), None, stream)
+
+    assert wf(ref, out) == 0
+    assert wf(ref, out, last=12) == -1 and "image surface" in _lib.last_error()
+    bad_ref = _lib.OlbWavefrontRef()
+    assert wf(bad_ref, out) == -1 and "positive" in _lib.last_error()
+    assert wf(ref, _lib.OlbWavefrontOut(ptrs[0], None, ptrs[2], ptrs[3], ptrs[4])) == -1
+    tilted = _lib.OlbWavefrontRef()
+    tilted.radius, tilted.n_image, tilted.wavelength_um = 100.0, 1.0, 0.55
+    tilted.tilt = (C.c_double * 2)(0.0, 1.5)
+    assert wf(tilted, out, launch=None) == -1 and "pupil samples" in _lib.last_error()
+    # batched tables: wrong entry point / ray count
+    from optiland_b200.batch import BatchedTable, template_params
+
+    bt = BatchedTable(c.table, np.repeat(template_params(c.table)[None], 3, axis=0))
+    assert lib.olb_trace_f32(C.byref(bt.c), 0, 13, C.byref(_lib.OlbRays(**good)), None, n, 0, None, stream) == -1
+    assert "several systems" in _lib.last_error()
+    cen = (C.c_double * 2)(0.0, 0.0)
+    assert lib.olb_trace_batch_f32(C.byref(bt.c), 0, 13, C.byref(_lib.OlbRays(**good)), None, 100, 0, cen, None, None,
+                                   stream) == 0      # 3 x 100 rays of the 1024-ray buffers
+    assert lib.olb_trace_batch_f32(C.byref(bt.c), 0, 13, C.byref(_lib.OlbRays(**good)), None, 100, _lib.TF_SHARED_INPUT,
+                                   cen, None, None, stream) == -1 and "SHARED_INPUT" in _lib.last_error()
+    assert lib.olb_trace_bwd_f32(C.byref(bt.c), 0, 13, None, None, None, None, None, n, C.c_uint64(0), stream) != 0
     torch.cuda.synchronize()
 
 
