@@ -384,14 +384,16 @@ int olb_trace_host_pupil_f64(const OlbDeviceTable* table, int32_t first, int32_t
  * dLoss/d(surface parameters) into grad_params: n_surfaces blocks of OLB_GP_COUNT doubles,
  *   [OLB_GP_TX..TZ] pose translation t, [OLB_GP_CURV] curvature 1/radius (d/dradius =
  *   -curv^2 * this), [OLB_GP_CONIC] k, [OLB_GP_N1] n1, [OLB_GP_N2] n2,
- *   [OLB_GP_COEF + j] even-asphere coefficient C_j (j < OLB_GP_MAX_COEF).
+ *   [OLB_GP_COEF + j] even-asphere coefficient C_j (j < OLB_GP_MAX_COEF),
+ *   [OLB_GP_R + 3 i + j] pose rotation matrix entry R_ij (tilted poses only; the caller chains it to the
+ *   Euler angles, R = Rz Ry Rx, coordinate_system.py:121-143).
  * Everything is recomputed from the forward call's inputs and records (nothing else is
  * saved): `rays_in` is the launch state the forward call consumed (x,y,z,L,M,N,i), `rec` its
  * full records for the same [first, last).  grad_rec pointers may be NULL individually
  * (that quantity has zero gradient); grad_rays_in (x,y,z,L,M,N,i,opd) may be NULL.
  * Supported tables (OlbDeviceTable.bwd_supported): plane / standard / even-asphere geometry, any
- * pose (tilt angles are constants: only the translation gets a gradient), any aperture tree, no or
- * simple coating, one wavelength; otherwise OLB_ERR_UNSUPPORTED.  Rays that are NaN at a surface carry no gradient.
+ * pose (translation gradients, and for tilted poses dLoss/dR for the caller to chain to the tilt angles), any
+ * aperture tree, no or simple coating, one wavelength; otherwise OLB_ERR_UNSUPPORTED.  Rays that are NaN at a surface carry no gradient.
  * grad_row_mask: bit r set = record row r of grad_rec may be non-zero (rows with a clear bit
  * are not read); pass ~0 when unknown.
  */
@@ -404,7 +406,8 @@ int olb_trace_host_pupil_f64(const OlbDeviceTable* table, int32_t first, int32_t
 #define OLB_GP_N2 6
 #define OLB_GP_COEF 7
 #define OLB_GP_MAX_COEF 12
-#define OLB_GP_COUNT (OLB_GP_COEF + OLB_GP_MAX_COEF)
+#define OLB_GP_R (OLB_GP_COEF + OLB_GP_MAX_COEF)   /* 9 entries, row-major: dLoss/dR of a tilted pose */
+#define OLB_GP_COUNT (OLB_GP_R + 9)
 int olb_trace_bwd_f32(const OlbDeviceTable* table, int32_t first, int32_t last,
                       const OlbRays* rays_in, const OlbRecords* rec, const OlbRecords* grad_rec,
                       const OlbRays* grad_rays_in, double* grad_params, int64_t n_rays,

@@ -28,7 +28,8 @@ TF_SHARED_INPUT = 1 << 4
 BP_TX, BP_TY, BP_TZ, BP_R, BP_CURV, BP_CONIC, BP_N1, BP_N2, BP_COEF, BP_MAX_COEF = 0, 1, 2, 3, 12, 13, 14, 15, 16, 12
 BP_COUNT = BP_COEF + BP_MAX_COEF
 GP_TX, GP_TY, GP_TZ, GP_CURV, GP_CONIC, GP_N1, GP_N2, GP_COEF, GP_MAX_COEF = 0, 1, 2, 3, 4, 5, 6, 7, 12
-GP_COUNT = GP_COEF + GP_MAX_COEF
+GP_R = GP_COEF + GP_MAX_COEF      # 9 entries: dLoss/dR of a tilted pose (row-major)
+GP_COUNT = GP_R + 9
 
 
 class OlbTable(C.Structure):

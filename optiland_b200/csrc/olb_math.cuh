@@ -777,7 +777,8 @@ OLB_HD void to_global(const Ray<T>& r, const PrepSurface<T>& S, T& x, T& y, T& z
 namespace olb {
 
 enum { GP_TX = 0, GP_TY = 1, GP_TZ = 2, GP_CURV = 3, GP_CONIC = 4, GP_N1 = 5, GP_N2 = 6, GP_COEF = 7,
-       GP_MAX_COEF = 12, GP_COUNT = GP_COEF + GP_MAX_COEF };
+       GP_MAX_COEF = 12, GP_R = GP_COEF + GP_MAX_COEF, GP_COUNT = GP_R + 9,
+       GP_SCALARS = GP_R };   // pg[] of surface_backward holds the first GP_SCALARS; the 9 dLoss/dR go to gR
 
 template <typename T>
 struct Adjoint { T x, y, z, L, M, N, i, opd; };
@@ -785,11 +786,15 @@ struct Adjoint { T x, y, z, L, M, N, i, opd; };
 // pre: state BEFORE the surface in GLOBAL coordinates (record row s-1 or the launch state);
 // (x1g, y1g, z1g): position AFTER the surface (record row s), global.
 // a: in = dLoss/d(state after the surface, global); out = dLoss/d(state before it, global).
-// pg[GP_COUNT]: += dLoss/d(surface parameters).  Returns false (and leaves `a` zeroed) when
-// the ray is not finite at this surface (NaN in band: it carries no gradient).
+// pg[GP_SCALARS]: += dLoss/d(pose translation, curvature, conic, indices, asphere coefficients).
+// gR (nullable; element q at gR[q * gR_stride], row-major 3x3): += dLoss/dR of a ROTATED pose -- R enters four
+// times, p_loc = R^T (p - t), d_loc = R^T d, p' = R p_loc' + t, d' = R d_loc' -- from which the caller's
+// autograd graph gets the gradients of the tilt angles.  It is written straight to the caller's accumulators
+// (shared memory in the kernel) so that the 9 values never live in registers.
+// Returns false (and leaves `a` zeroed) when the ray is not finite at this surface (NaN in band: no gradient).
 template <typename T>
 OLB_HD bool surface_backward(const PrepSurface<T>& S, const T* pool, T xg0, T yg0, T zg0, T L, T M, T N, T i0,
-                             T x1g, T y1g, T z1g, Adjoint<T>& a, T* pg) {
+                             T x1g, T y1g, T z1g, Adjoint<T>& a, T* pg, T* gR = nullptr, int gR_stride = 1) {
   // (L, M, N are taken by value: they are rotated into the local frame below for tilted poses)
   const T* med = pool + S.media_off;  // one wavelength
   const T n1 = med[MED_N1], u = med[MED_U];
@@ -799,6 +804,7 @@ OLB_HD bool surface_backward(const PrepSurface<T>& S, const T* pool, T xg0, T yg
   const bool rot = (S.flags & OLB_SF_ROTATED) != 0;
   T x0 = xg0 - S.t[0], y0 = yg0 - S.t[1], z0 = zg0 - S.t[2];
   T x1 = x1g - S.t[0], y1 = y1g - S.t[1], z1 = z1g - S.t[2];
+  const T dgx = L, dgy = M, dgz = N;                      // d in GLOBAL axes (for dLoss/dR)
   if (rot) {
     const T* R = S.R;
     T a0 = x0, b0 = y0, c0 = z0, a1 = x1, b1 = y1, c1 = z1, dl = L, dm = M, dn = N;
@@ -844,6 +850,23 @@ OLB_HD bool surface_backward(const PrepSurface<T>& S, const T* pool, T xg0, T yg
   // ---- adjoint of globalize ---------------------------------------------------------------
   pg[GP_TX] += a.x; pg[GP_TY] += a.y; pg[GP_TZ] += a.z;    // pg1 = R p1 + t
   T apx = a.x, apy = a.y, apz = a.z;            // d/d p1 (local)
+  const bool wantR = rot && gR != nullptr;
+  if (wantR) {
+    // p' = R p1_loc + t and d' = R d_loc' :  dLoss/dR_ij += a(p')_i p1_loc_j + a(d')_i d_loc'_j, with the
+    // outgoing local direction d_loc' recomputed from the interaction (a.* are still in global axes here)
+    T ox, oy, oz;
+    if (S.flags & OLB_SF_REFLECT) {
+      ox = o_fma((T)-2 * dot, nx, L); oy = o_fma((T)-2 * dot, ny, M); oz = o_fma((T)-2 * dot, nz, N);
+    } else {
+      const T sgn = dot > 0 ? (T)1 : (dot < 0 ? (T)-1 : (T)0);
+      const T aa = o_abs(dot);
+      const T h = (u == (T)1) ? (T)0 : o_fma(-u, aa, o_sqrt(o_fma(u * u, o_fma(aa, aa, (T)-1), (T)1)));
+      ox = o_fma(u, L, h * sgn * nx); oy = o_fma(u, M, h * sgn * ny); oz = o_fma(u, N, h * sgn * nz);
+    }
+    gR[0 * gR_stride] += o_fma(a.x, x1, a.L * ox); gR[1 * gR_stride] += o_fma(a.x, y1, a.L * oy); gR[2 * gR_stride] += o_fma(a.x, z1, a.L * oz);
+    gR[3 * gR_stride] += o_fma(a.y, x1, a.M * ox); gR[4 * gR_stride] += o_fma(a.y, y1, a.M * oy); gR[5 * gR_stride] += o_fma(a.y, z1, a.M * oz);
+    gR[6 * gR_stride] += o_fma(a.z, x1, a.N * ox); gR[7 * gR_stride] += o_fma(a.z, y1, a.N * oy); gR[8 * gR_stride] += o_fma(a.z, z1, a.N * oz);
+  }
   if (rot) {
     const T* R = S.R;
     apx = R[0] * a.x + R[3] * a.y + R[6] * a.z; apy = R[1] * a.x + R[4] * a.y + R[7] * a.z; apz = R[2] * a.x + R[5] * a.y + R[8] * a.z;
@@ -927,6 +950,12 @@ OLB_HD bool surface_backward(const PrepSurface<T>& S, const T* pool, T xg0, T yg
     }
   }
   // ---- localize p0 = pg0 - t -------------------------------------------------------------------------
+  if (wantR) {   // p_loc = R^T (p - t), d_loc = R^T d :  dLoss/dR_ij += (p - t)_i a(p_loc)_j + d_i a(d_loc)_j
+    const T q0x = xg0 - S.t[0], q0y = yg0 - S.t[1], q0z = zg0 - S.t[2];
+    gR[0 * gR_stride] += o_fma(q0x, apx, dgx * adL); gR[1 * gR_stride] += o_fma(q0x, apy, dgx * adM); gR[2 * gR_stride] += o_fma(q0x, apz, dgx * adN);
+    gR[3 * gR_stride] += o_fma(q0y, apx, dgy * adL); gR[4 * gR_stride] += o_fma(q0y, apy, dgy * adM); gR[5 * gR_stride] += o_fma(q0y, apz, dgy * adN);
+    gR[6 * gR_stride] += o_fma(q0z, apx, dgz * adL); gR[7 * gR_stride] += o_fma(q0z, apy, dgz * adM); gR[8 * gR_stride] += o_fma(q0z, apz, dgz * adN);
+  }
   if (rot) {   // back to global: ag = R a_local
     const T* R = S.R;
     T u0 = apx, u1 = apy, u2 = apz, v0 = adL, v1 = adM, v2 = adN;

@@ -65,7 +65,7 @@ struct PrepSurface {
   int32_t poly_cols;
   int32_t poly_d_off;  // pool offset of the derivative-source table (Zernike quirk)
   int32_t gslot;       // backward: first per-thread gradient accumulator slot of this surface
-  int32_t gslots;      //           number of slots (GP_COEF + n_coef; 0 for NOOP)
+  int32_t gslots;      //           number of slots (7 + n_coef [+ 9 for a tilted pose]; 0 for NOOP)
   // incoming transform from GLOBAL coordinates: p_loc = Ag * p + bg
   T Ag[9], bg[3];
   // incoming transform from the PREVIOUS surface's local frame: p_loc = Ar * p + br
@@ -453,7 +453,9 @@ static inline PrepResult prepare_table(const OlbTable& tab) {
   int gslot = 0;
   for (int s = 0; s < tab.n_surfaces; ++s) {
     ps[s].gslot = gslot;
-    ps[s].gslots = ps[s].kind == OLB_GEOM_NOOP ? 0 : 7 + (ps[s].kind == OLB_GEOM_EVEN_ASPHERE ? ps[s].n_coef : 0);
+    // 7 scalars + even-asphere coefficients + (tilted pose) the 9 entries of dLoss/dR
+    ps[s].gslots = ps[s].kind == OLB_GEOM_NOOP ? 0 : 7 + (ps[s].kind == OLB_GEOM_EVEN_ASPHERE ? ps[s].n_coef : 0) +
+                                                         ((ps[s].flags & OLB_SF_ROTATED) ? 9 : 0);
     gslot += ps[s].gslots;
   }
   res.total_gslots = gslot;

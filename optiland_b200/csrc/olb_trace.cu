@@ -527,28 +527,46 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(T) == 8 ? OLB_BWD_MINB64 : 2)) 
       }
       ad.x += g8[0]; ad.y += g8[1]; ad.z += g8[2]; ad.L += g8[3]; ad.M += g8[4]; ad.N += g8[5]; ad.i += g8[6]; ad.opd += g8[7];
       if (!noop) {   // (a NOOP surface records its input unchanged: the adjoint passes through)
-        T pg[GP_COUNT];
+        T pg[GP_SCALARS];
 #pragma unroll
-        for (int q = 0; q < GP_COUNT; ++q) pg[q] = 0;
-        if (valid) surface_backward<T>(S, pool, pre[0], pre[1], pre[2], pre[3], pre[4], pre[5], pre[6], post[0], post[1], post[2], ad, pg);
+        for (int q = 0; q < GP_SCALARS; ++q) pg[q] = 0;
+        // slots of this surface: 7 scalars, its even-asphere coefficients, then dLoss/dR (9) if the pose is tilted
+        const int ncoef = S.kind == OLB_GEOM_EVEN_ASPHERE ? S.n_coef : 0;
+        const bool tilted = (S.flags & OLB_SF_ROTATED) != 0;
         if (SMEM_ACC) {
           T* mine = tacc + (int64_t)S.gslot * BLOCK + threadIdx.x;
+          if (valid)
+            surface_backward<T>(S, pool, pre[0], pre[1], pre[2], pre[3], pre[4], pre[5], pre[6], post[0], post[1], post[2],
+                                ad, pg, tilted ? mine + (GP_COEF + ncoef) * BLOCK : nullptr, BLOCK);
           // pose, curvature, conic, n1, n2: every surface has these 7; only even aspheres have more
 #pragma unroll
           for (int q = 0; q < GP_COEF; ++q) mine[q * BLOCK] += pg[q];
-          if (S.gslots > GP_COEF) {
+          if (ncoef > 0) {
 #pragma unroll
-            for (int q = GP_COEF; q < GP_COUNT; ++q)
-              if (q < S.gslots) mine[q * BLOCK] += pg[q];
+            for (int q = GP_COEF; q < GP_SCALARS; ++q)
+              if (q < GP_COEF + ncoef) mine[q * BLOCK] += pg[q];
           }
         } else {
+          T r9[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+          if (valid)
+            surface_backward<T>(S, pool, pre[0], pre[1], pre[2], pre[3], pre[4], pre[5], pre[6], post[0], post[1], post[2],
+                                ad, pg, tilted ? r9 : nullptr, 1);
 #pragma unroll
-          for (int q = 0; q < GP_COUNT; ++q) {
-            if (q >= S.gslots) break;
+          for (int q = 0; q < GP_SCALARS; ++q) {
+            if (q >= GP_COEF + ncoef) break;
             T v = pg[q];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
             if (lane == 0 && v != 0) atomicAdd(&wacc[s * GP_COUNT + q], (double)v);
+          }
+          if (tilted) {
+#pragma unroll
+            for (int q = 0; q < 9; ++q) {
+              T v = r9[q];
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+              if (lane == 0 && v != 0) atomicAdd(&wacc[s * GP_COUNT + GP_R + q], (double)v);
+            }
           }
         }
       }
@@ -578,7 +596,10 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(T) == 8 ? OLB_BWD_MINB64 : 2)) 
         for (int j = lane; j < BLOCK; j += 32) v += (double)col[j];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0 && v != 0) atomicAdd(&a.gparams[s * GP_COUNT + q], v);
+        // slot -> parameter: scalars and coefficients in place, the tilted pose's 9 slots -> GP_R ..
+        const int ncoef = S.kind == OLB_GEOM_EVEN_ASPHERE ? S.n_coef : 0;
+        const int qp = q < GP_COEF + ncoef ? q : GP_R + (q - GP_COEF - ncoef);
+        if (lane == 0 && v != 0) atomicAdd(&a.gparams[s * GP_COUNT + qp], v);
       }
     }
   } else {

@@ -214,7 +214,7 @@ def _live_params(surfaces, table, wavelength):
     the optimiser owns (optic/optic_updater.py:38-157).  None if a surface is outside the adjoint's scope."""
     import torch
 
-    from .autograd import GP_COEF, GP_CONIC, GP_COUNT, GP_CURV, GP_MAX_COEF, GP_N1, GP_N2, GP_TX
+    from .autograd import GP_COEF, GP_CONIC, GP_COUNT, GP_CURV, GP_MAX_COEF, GP_N1, GP_N2, GP_R, GP_TX
 
     def scalar(v, like):
         t = v if torch.is_tensor(v) else torch.as_tensor(float(v))
@@ -240,11 +240,21 @@ def _live_params(surfaces, table, wavelength):
             cs = g.cs
             if cs.reference_cs is not None or spec.kind not in (T.GEOM_PLANE, T.GEOM_STANDARD, T.GEOM_EVEN_ASPHERE):
                 return None
-            if spec.rotated and any(getattr(v, "requires_grad", False) for v in (cs.rx, cs.ry, cs.rz)):
-                # tilt angles are constants of the adjoint kernel: keep the reference's eager graph.  (For an
-                # untilted surface the reference skips the rotations altogether -- `if self.rz:`,
-                # coordinate_system.py:84-89 -- so zero angles get no gradient there either.)
-                return None
+            # pose rotation: constants (identity for an untilted surface -- the reference skips zero rotations
+            # altogether, `if self.rz:` coordinate_system.py:84-89, so zero angles get no gradient there either);
+            # for a tilted pose R = Rz Ry Rx is formed from the LIVE angle tensors (coordinate_system.py:121-143)
+            # so that the adjoint kernel's dLoss/dR reaches tilt variables
+            if spec.rotated:
+                # (an angle that is exactly 0 is skipped by the reference even on a tilted surface: constant)
+                rx, ry, rz = (scalar(v, like) if float(scalar(v, like).detach()) != 0.0 else zero for v in (cs.rx, cs.ry, cs.rz))
+                cx, sx, cy, sy, cz, sz = torch.cos(rx), torch.sin(rx), torch.cos(ry), torch.sin(ry), torch.cos(rz), torch.sin(rz)
+                Rm = (cz * cy, cz * sy * sx - sz * cx, cz * sy * cx + sz * sx,
+                      sz * cy, sz * sy * sx + cz * cx, sz * sy * cx - cz * sx,
+                      -sy, cy * sx, cy * cx)
+            else:
+                Rm = (one, zero, zero, zero, one, zero, zero, zero, one)
+            for q in range(9):
+                vals[GP_R + q] = Rm[q]
             vals[GP_TX], vals[GP_TX + 1], vals[GP_TX + 2] = scalar(cs.x, like), scalar(cs.y, like), scalar(cs.z, like)
             curved = spec.kind != T.GEOM_PLANE and np.isfinite(spec.radius)
             if spec.kind != T.GEOM_PLANE:

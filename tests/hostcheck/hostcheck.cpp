@@ -109,10 +109,11 @@ static int run_backward(const OlbTable* tab, int first, int last, int64_t n, T**
       T pre[7];
       if (s == first) { for (int q = 0; q < 7; ++q) pre[q] = ray_in[q][k]; }
       else { for (int q = 0; q < 7; ++q) pre[q] = rec[q][off - n]; }
-      T pg[GP_COUNT] = {0};
+      T pg[GP_SCALARS] = {0}, r9[9] = {0};
       surface_backward<T>(S, pool, pre[0], pre[1], pre[2], pre[3], pre[4], pre[5], pre[6], rec[0][off], rec[1][off],
-                          rec[2][off], a, pg);
-      for (int q = 0; q < GP_COUNT; ++q) gparams[(int64_t)s * GP_COUNT + q] += (double)pg[q];
+                          rec[2][off], a, pg, (S.flags & OLB_SF_ROTATED) ? r9 : nullptr, 1);
+      for (int q = 0; q < GP_SCALARS; ++q) gparams[(int64_t)s * GP_COUNT + q] += (double)pg[q];
+      for (int q = 0; q < 9; ++q) gparams[(int64_t)s * GP_COUNT + GP_R + q] += (double)r9[q];
     }
     gin[0][k] = a.x; gin[1][k] = a.y; gin[2][k] = a.z; gin[3][k] = a.L; gin[4][k] = a.M; gin[5][k] = a.N;
     gin[6][k] = a.i; gin[7][k] = a.opd;

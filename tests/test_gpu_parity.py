@@ -327,6 +327,30 @@ def test_autograd_ray_input_gradients_and_unsupported_tables():
         pb[s_, q] -= h
         fd = (float(img(pa)) - float(img(pb))) / (2 * h)
         assert pr.grad[s_, q].item() == pytest.approx(fd, rel=2e-5, abs=1e-8), (s_, q)
+    # tilt angles: dLoss/dR from the adjoint kernel, chained to (rx, ry, rz) by autograd through R = Rz Ry Rx
+    # (coordinate_system.py:121-143), against central differences of the forward kernel in the angles
+    s_rot = next(j for j, sp in enumerate(t.table.surfaces) if sp.rotated)
+    assert not torch.any(pr.grad[0, AG.GP_R:])                          # object surface: no pose
+    assert torch.any(pr.grad[s_rot, AG.GP_R:AG.GP_R + 9] != 0)
+
+    def rot(a):
+        cx, sx, cy, sy, cz, sz = torch.cos(a[0]), torch.sin(a[0]), torch.cos(a[1]), torch.sin(a[1]), torch.cos(a[2]), torch.sin(a[2])
+        return torch.stack([cz * cy, cz * sy * sx - sz * cx, cz * sy * cx + sz * sx,
+                            sz * cy, sz * sy * sx + cz * cx, sz * sy * cx - cz * sx,
+                            -sy, cy * sx, cy * cx])
+
+    def loss_of_angles(a):
+        p = torch.cat([p0[:s_rot], torch.cat([p0[s_rot, :AG.GP_R], rot(a)])[None], p0[s_rot + 1:]])
+        return img(p)
+
+    ang = torch.tensor([0.21, -0.13, 0.05], dtype=torch.float64, requires_grad=True)
+    loss_of_angles(ang).backward()
+    for q in range(3):
+        h = 1e-6
+        e = torch.zeros(3, dtype=torch.float64)
+        e[q] = h
+        fd = (float(loss_of_angles(ang.detach() + e)) - float(loss_of_angles(ang.detach() - e))) / (2 * h)
+        assert ang.grad[q].item() == pytest.approx(fd, rel=2e-5, abs=1e-8), q
 
 
 def test_autograd_selected_rows_equals_dense():

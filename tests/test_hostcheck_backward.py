@@ -15,7 +15,7 @@ from tests._util import REC, Case
 from oracle.hostcheck_api import run_backward  # noqa: F401
 from tests.test_hostcheck import hc  # noqa: F401  (fixture)
 
-GP = dict(TX=0, TY=1, TZ=2, CURV=3, CONIC=4, N1=5, N2=6, COEF=7)
+GP = dict(TX=0, TY=1, TZ=2, CURV=3, CONIC=4, N1=5, N2=6, COEF=7, R=19)
 
 
 def loss_fn(table, rays, weights):
@@ -41,6 +41,8 @@ def perturbed(table, s, **kw):
             ch["n1"] = spec.n1 + d
         elif k.startswith("coef"):
             c = spec.coefficients.copy(); c[int(k[4:])] += d; ch["coefficients"] = c
+        elif k.startswith("R"):      # one entry of the pose rotation matrix (treated as 9 independent numbers)
+            R = spec.R.copy(); R[int(k[1]), int(k[2])] += d; ch["R"] = R
     return table.replace_surface(s, **ch)
 
 
@@ -91,6 +93,10 @@ def test_adjoint_matches_finite_differences(hc, name):
             tests += [("curv", GP["CURV"], 1e-7 / max(abs(spec.radius), 1.0) ** 0), ("conic", GP["CONIC"], 1e-5)]
         if spec.kind == T.GEOM_EVEN_ASPHERE:
             tests += [(f"coef{j}", GP["COEF"] + j, 1e-6) for j in range(len(spec.coefficients))]
+        if spec.rotated:             # dLoss/dR, the input of the tilt-angle gradients
+            tests += [(f"R{i}{j}", GP["R"] + 3 * i + j, 1e-7) for i in range(3) for j in range(3)]
+        else:
+            assert not np.any(gpar[s, GP["R"]:GP["R"] + 9])
         for what, slot, hh in tests:
             if what == "curv":
                 hh = 1e-5 * abs(1.0 / spec.radius)
@@ -138,3 +144,31 @@ def test_config3_gradients_match_reference_autograd(hc):
     # cs.z of surface 1 is a leaf in the reference and every later surface sits at z_prev + thickness
     # (surfaces/factories/coordinate_system_factory.py:72-79): d/dz_1 shifts the whole system
     assert gpar[1:, GP["TZ"]].sum() == pytest.approx(float(g["d_z_1"]), rel=1e-7)
+
+
+def test_tilt_angle_gradient_through_dLoss_dR(hc):
+    """d loss / d(rx, ry, rz) of a tilted mirror: chain dLoss/dR (adjoint) with dR/d(angle) of R = Rz Ry Rx
+    (coordinate_system.py:121-143) and compare with central differences of the oracle in the ANGLES."""
+    c = Case("tilted_fold")
+    rng = np.random.default_rng(5)
+    sel = rng.choice(c.n, size=48, replace=False)
+    rays = {k: v[sel].copy() for k, v in c.rays.items()}
+    S, n = c.table.num_surfaces, sel.size
+    weights = {k: rng.normal(size=(S, n)) for k in REC}
+    s = next(j for j, sp in enumerate(c.table.surfaces) if sp.rotated)
+    ang0 = np.array([0.31, -0.12, 0.07])
+
+    def with_angles(a):
+        return c.table.replace_surface(s, R=T.rotation_matrix(*a) + 0.0)
+
+    table = with_angles(ang0)
+    _, rec, _ = O.trace(table, rays)
+    _, gpar = run_backward(hc, table, rays, rec, weights)
+    gR = gpar[s, GP["R"]:GP["R"] + 9].reshape(3, 3)
+    for q in range(3):
+        h = 1e-6
+        e = np.zeros(3); e[q] = h
+        dR = (T.rotation_matrix(*(ang0 + e)) - T.rotation_matrix(*(ang0 - e))) / (2 * h)
+        got = float(np.sum(gR * dR))
+        ref = (loss_fn(with_angles(ang0 + e), rays, weights) - loss_fn(with_angles(ang0 - e), rays, weights)) / (2 * h)
+        assert got == pytest.approx(ref, rel=1e-4, abs=1e-6 * np.abs(gpar).max()), (q, got, ref)

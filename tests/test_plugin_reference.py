@@ -295,6 +295,63 @@ def test_autograd_through_the_capability_matches_reference_eager_graph(plugin):
         assert got[k] == pytest.approx(ref[k], rel=2e-6), k
 
 
+def test_autograd_tilt_and_decenter_variables_match_reference_eager_graph(plugin):
+    """Tilted / decentered surfaces with be.grad_mode on: d(RMS spot)/d(rx, ry, rz, dx, dy, radius) through the
+    capability (adjoint kernel's dLoss/dR chained to the live angle tensors) equals the reference's own eager
+    autograd -- including its quirk that an angle that is exactly 0 gets no gradient."""
+    import torch
+
+    P, eng, be = plugin
+    from optiland import optic as _optic
+
+    def make():
+        lens = _optic.Optic()
+        lens.surfaces.add(index=0, radius=be.inf, thickness=be.inf)
+        lens.surfaces.add(index=1, radius=50.0, thickness=5.0, material="N-BK7", is_stop=True,
+                          dx=0.3, dy=-0.2, rx=0.02, ry=-0.015)
+        lens.surfaces.add(index=2, radius=-80.0, thickness=30.0, rz=0.4, rx=-0.01, conic=-0.8)
+        lens.surfaces.add(index=3, radius=be.inf, thickness=-25.0, material="mirror", rx=np.pi / 4)
+        lens.surfaces.add(index=4, radius=be.inf, thickness=0.0, rx=np.pi / 2, dy=0.5)
+        lens.set_aperture(aperture_type="EPD", value=10.0)
+        lens.fields.set_type(field_type="angle")
+        lens.fields.add(y=0)
+        lens.fields.add(y=3)
+        lens.wavelengths.add(value=0.6, is_primary=True)
+        return lens
+
+    def run(lens):
+        lens.trace(0.0, 1.0, 0.6, 5, "hexapolar")
+        x = lens.surfaces.x[-1, :]
+        y = lens.surfaces.y[-1, :]
+        z = lens.surfaces.z[-1, :]
+        loss = torch.sqrt(torch.mean((x - torch.mean(x)) ** 2 + (y - torch.mean(y)) ** 2 + (z - torch.mean(z)) ** 2))
+        loss.backward()
+        out = {"loss": float(loss.detach())}
+        for s in (1, 2, 3):
+            cs = lens.surfaces.surfaces[s].geometry.cs
+            for k in ("rx", "ry", "rz", "x", "y"):
+                g = getattr(cs, k).grad
+                out[f"{k}{s}"] = 0.0 if g is None else float(g)
+        out["r1"] = float(lens.surfaces.surfaces[1].geometry.radius.grad)
+        return out
+
+    be.grad_mode.enable()
+    try:
+        n0 = len(eng.calls)
+        got = run(make())
+        assert any(c[0] == "grad" for c in eng.calls[n0:]), P.stats()
+        P.uninstall()
+        ref = run(make())
+    finally:
+        be.grad_mode.disable()
+    assert got["loss"] == pytest.approx(ref["loss"], rel=1e-9)
+    scale = max(abs(v) for k, v in ref.items() if k != "loss")
+    for k in ref:
+        assert got[k] == pytest.approx(ref[k], rel=2e-6, abs=1e-9 * scale), (k, got[k], ref[k])
+    assert ref["rx1"] != 0 and ref["rz2"] != 0 and ref["rx3"] != 0      # the tilt gradients are really there
+    assert ref["rz1"] == 0 and got["rz1"] == 0                           # zero angle: skipped by the reference
+
+
 def test_surface_group_trace_capability_when_launch_fusion_is_off(plugin):
     """With the RealRayTracer.trace wrapper disabled the SurfaceGroup.trace wrapper carries the call
     (launch rays from the reference's own RayGenerator)."""
