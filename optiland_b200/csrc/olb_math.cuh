@@ -354,9 +354,14 @@ OLB_HD void forbes_slopes(T x, T y, const PrepSurface<T>& S, const T* pool, T& f
   fy = df * o_div(y, rho);
 }
 
-template <typename T>
+// FEAT: the Forbes code is compiled only into the general kernel (FEAT_EXTRA) -- inlined into the lean
+// Newton kernel it cost the even-asphere systems 7 % (fp32) to 26 % (fp64), profiles/tune_r1.md; a table with
+// a Forbes surface is routed to the general kernel by prepare_table.
+template <typename T, uint32_t FEAT = 0xffffffffu>
 OLB_HD T newton_sag(T x, T y, const PrepSurface<T>& S, const T* pool, int& status) {
-  if (S.kind == OLB_GEOM_FORBES_QBFS) return forbes_sag(x, y, S, pool);
+  if constexpr ((FEAT & FEAT_EXTRA) != 0) {
+    if (S.kind == OLB_GEOM_FORBES_QBFS) return forbes_sag(x, y, S, pool);
+  }
   if (S.kind == OLB_GEOM_BICONIC) return biconic_profile(x, S.curv, S.kp1) + biconic_profile(y, S.curv_y, S.kp1_y);
   if (S.kind == OLB_GEOM_TOROIDAL) {
     T zy, dzy;
@@ -396,9 +401,11 @@ OLB_HD T newton_sag(T x, T y, const PrepSurface<T>& S, const T* pool, int& statu
 // even_asphere.py:111-140, odd_asphere.py:103-142, polynomial.py:123-155,
 // zernike.py:182-252 (Zernike: derivative WITHOUT N_nm and exactly zero at rho == 0,
 // reproducing the reference's eps-regularised chain rule).
-template <typename T>
+template <typename T, uint32_t FEAT = 0xffffffffu>
 OLB_HD void newton_slopes(T x, T y, const PrepSurface<T>& S, const T* pool, T& fx, T& fy) {
-  if (S.kind == OLB_GEOM_FORBES_QBFS) { forbes_slopes(x, y, S, pool, fx, fy); return; }
+  if constexpr ((FEAT & FEAT_EXTRA) != 0) {
+    if (S.kind == OLB_GEOM_FORBES_QBFS) { forbes_slopes(x, y, S, pool, fx, fy); return; }
+  }
   if (S.kind == OLB_GEOM_BICONIC) {                     // biconic.py:107-160
     fx = biconic_slope(x, S.curv, S.kp1);
     fy = biconic_slope(y, S.curv_y, S.kp1_y);
@@ -475,13 +482,13 @@ OLB_HD void newton_slopes(T x, T y, const PrepSurface<T>& S, const T* pool, T& f
 // iterate sits on the noise floor of f, which for fp32 polynomial sags lies above the
 // floor estimate) keeping the better of the last two iterates -- so fp32 cannot spin
 // to max_iter.
-template <typename T>
+template <typename T, uint32_t FEAT = 0xffffffffu>
 OLB_HD T newton_distance(T x, T y, T z, T L, T M, T N, const PrepSurface<T>& S, const T* pool, int& status) {
   T t = conic_distance(x, y, z, L, M, N, S);
   T t_prev = t, f_prev = (T)INFINITY;
   for (int it = 0; it < S.max_iter; ++it) {
     T xi = o_fma(t, L, x), yi = o_fma(t, M, y), zi = o_fma(t, N, z);
-    T sag = newton_sag(xi, yi, S, pool, status);
+    T sag = newton_sag<T, FEAT>(xi, yi, S, pool, status);
     T f = sag - zi;
     T af = o_abs(f);
     if (!(af == af)) break;  // NaN stays NaN (the reference would spin to max_iter on it)
@@ -494,7 +501,7 @@ OLB_HD T newton_distance(T x, T y, T z, T L, T M, T N, const PrepSurface<T>& S, 
       break;
     }
     T fx, fy;
-    newton_slopes(xi, yi, S, pool, fx, fy);
+    newton_slopes<T, FEAT>(xi, yi, S, pool, fx, fy);
     // f'(t) = fx L + fy M - N  with fx = -nx/nz = dz/dx  (newton_raphson.py:155-161)
     T df = o_fma(fx, L, o_fma(fy, M, -N));
     T dfs = o_abs(df) > (T)1e-14 ? df : (T)1e-14;
@@ -510,12 +517,12 @@ OLB_HD T newton_distance(T x, T y, T z, T L, T M, T N, const PrepSurface<T>& S, 
 // shrinks them by 30 % but the spills around the call cost more than the I-cache misses saved
 // (fp32 +4..27 %, fp64 +10..25 % slower; profiles/tune_r1.md, sweep 8), so it stays inlined.
 template <typename T> struct NewtonHit { T t, fx, fy; int status; };
-template <typename T>
+template <typename T, uint32_t FEAT = 0xffffffffu>
 OLB_HD_CALL NewtonHit<T> newton_hit(T x, T y, T z, T L, T M, T N, const PrepSurface<T>* S, const T* pool) {
   NewtonHit<T> h;
   h.status = 0;
-  h.t = newton_distance(x, y, z, L, M, N, *S, pool, h.status);
-  newton_slopes(o_fma(h.t, L, x), o_fma(h.t, M, y), *S, pool, h.fx, h.fy);
+  h.t = newton_distance<T, FEAT>(x, y, z, L, M, N, *S, pool, h.status);
+  newton_slopes<T, FEAT>(o_fma(h.t, L, x), o_fma(h.t, M, y), *S, pool, h.fx, h.fy);
   return h;
 }
 
@@ -655,7 +662,7 @@ OLB_HD void surface_step_k(Ray<T>& r, const PrepSurface<T>& S, const T* pool, bo
   } else if (KIND == KIND_CONIC) {
     t = conic_distance(r.x, r.y, r.z, r.L, r.M, r.N, S);
   } else {
-    NewtonHit<T> h = newton_hit(r.x, r.y, r.z, r.L, r.M, r.N, &S, pool);
+    NewtonHit<T> h = newton_hit<T, FEAT>(r.x, r.y, r.z, r.L, r.M, r.N, &S, pool);
     t = h.t; nfx = h.fx; nfy = h.fy;
     status |= h.status;
   }

@@ -372,6 +372,7 @@ static inline PrepResult prepare_table(const OlbTable& tab) {
       for (int i = 0; i < nc; ++i) pool.push_back(b[i]);
       while (pool.size() % 4) pool.push_back(0);
       o.inv_norm = 1.0 / in.norm_radius;
+      features |= FEAT_EXTRA;          // the Forbes code lives in the general kernel only (olb_math.cuh::newton_sag)
     } else if (in.kind == OLB_GEOM_ZERNIKE) {
       if (!in_pool(in.coef_off, 4 * in.n_coef)) { res.error = "Zernike block outside pool"; return res; }
       if (!(in.norm_radius > 0)) { res.error = "Zernike norm_radius must be positive"; return res; }
