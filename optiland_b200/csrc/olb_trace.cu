@@ -7,7 +7,8 @@
 // ray per recorded surface.  The reference does the same work with ~190
 // eager element-wise launches per surface.  Optional in-kernel stages:
 // launch-state generation from pupil coordinates (8f-1), polarization matrices, spot / OPD
-// moments (8f-2).  Backward: one adjoint kernel (trace_bwd_kernel).
+// moments and the wavefront (OPD-map) epilogue (8f-2), many systems per launch (8f-4: blockIdx.y =
+// system, each CTA stages its own system's table).  Backward: one adjoint kernel (trace_bwd_kernel).
 //
 // No tensor cores: there is no contraction on this path.  The roofline is HBM.
 #include <cuda_runtime.h>
@@ -730,7 +731,7 @@ static int launch_feat(const TraceArgs& a, uint32_t features, cudaStream_t strea
 // fp32 x 4 rays/thread exists only for the closed-form feature sets (code size, registers).
 template <typename T, int RPT>
 static int launch_feat_cf(const TraceArgs& a, uint32_t features, cudaStream_t stream) {
-  if (features & FEAT_POL) return fail(OLB_ERR_UNSUPPORTED, "polarized trace not built in this version");
+  if (features & FEAT_POL) return fail(OLB_ERR_UNSUPPORTED, "polarized tables run one ray per thread (internal dispatch error)");
   if (features == 0) return launch_instance<T, RPT, 0u>(a, stream);
 #ifdef OLB_NEWTON_RPT4
   if (features == FEAT_NEWTON) return launch_instance<T, RPT, FEAT_NEWTON>(a, stream);
