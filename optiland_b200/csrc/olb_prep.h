@@ -472,5 +472,70 @@ static inline PrepResult prepare_table(const OlbTable& tab) {
   return res;
 }
 
+// ---- batched systems: B perturbed copies of one template -----------------------------------
+// `params`: n_systems x n_surfaces blocks of OLB_BP_COUNT doubles with ABSOLUTE values (include/olb.h).  Every
+// system is prepared like a single table; the blobs must come out the same size (same structure) and are laid
+// side by side; each header is stamped with the UNION of the feature bits (one kernel variant serves them all).
+struct BatchPrep {
+  std::vector<unsigned char> all64, all32;
+  uint32_t features = 0, hints = 0;
+  int32_t bytes_f64 = 0, bytes_f32 = 0;
+  bool unsupported = false;
+  std::string error;
+};
+
+static BatchPrep prepare_batch(const OlbTable& tmpl, const double* params, int n_systems) {
+  BatchPrep out;
+  if (tmpl.n_wl != 1) { out.error = "batched tables support one wavelength"; out.unsupported = true; return out; }
+  const int S = tmpl.n_surfaces;
+  std::vector<OlbSurface> surf(tmpl.surfaces, tmpl.surfaces + S);
+  std::vector<double> pool(tmpl.pool, tmpl.pool + tmpl.pool_len);
+  OlbTable t = tmpl;
+  t.surfaces = surf.data();
+  t.pool = pool.data();
+  for (int b = 0; b < n_systems; ++b) {
+    for (int s = 0; s < S; ++s) {
+      const double* p = params + ((size_t)b * S + s) * OLB_BP_COUNT;
+      OlbSurface& o = surf[s];
+      const OlbSurface& o0 = tmpl.surfaces[s];
+      if (o0.kind == OLB_GEOM_NOOP) continue;
+      o.t[0] = p[OLB_BP_TX]; o.t[1] = p[OLB_BP_TY]; o.t[2] = p[OLB_BP_TZ];
+      for (int q = 0; q < 9; ++q) o.R[q] = p[OLB_BP_R + q];
+      if (o0.kind != OLB_GEOM_PLANE) {
+        o.radius = p[OLB_BP_CURV] == 0 ? INFINITY : 1.0 / p[OLB_BP_CURV];
+        if (o0.kind != OLB_GEOM_TOROIDAL) o.conic = p[OLB_BP_CONIC];
+      }
+      // media block (one wavelength): {n1, n2, k1, coating n1, coating n2}; without a Fresnel coating the last two
+      // mirror n1 / n2 (table.py::pack)
+      pool[o0.media_off + 0] = p[OLB_BP_N1];
+      pool[o0.media_off + 1] = p[OLB_BP_N2];
+      if (o0.coating != OLB_COAT_FRESNEL) {
+        pool[o0.media_off + 3] = p[OLB_BP_N1];
+        pool[o0.media_off + 4] = p[OLB_BP_N2];
+      }
+      if (o0.kind == OLB_GEOM_EVEN_ASPHERE)
+        for (int j = 0; j < o0.n_coef && j < OLB_BP_MAX_COEF; ++j) pool[o0.coef_off + j] = p[OLB_BP_COEF + j];
+    }
+    PrepResult pr = prepare_table(t);
+    if (!pr.error.empty()) { out.error = "system " + std::to_string(b) + ": " + pr.error; return out; }
+    if (b == 0) {
+      out.bytes_f64 = (int32_t)pr.blob_f64.size();
+      out.bytes_f32 = (int32_t)pr.blob_f32.size();
+    } else if ((int32_t)pr.blob_f64.size() != out.bytes_f64 || (int32_t)pr.blob_f32.size() != out.bytes_f32) {
+      out.error = "batched systems must share one table structure";
+      return out;
+    }
+    out.features |= pr.features;
+    out.hints |= pr.hints;
+    out.all64.insert(out.all64.end(), pr.blob_f64.begin(), pr.blob_f64.end());
+    out.all32.insert(out.all32.end(), pr.blob_f32.begin(), pr.blob_f32.end());
+  }
+  for (int b = 0; b < n_systems; ++b) {
+    reinterpret_cast<PrepHeader*>(out.all64.data() + (size_t)b * out.bytes_f64)->features = out.features;
+    reinterpret_cast<PrepHeader*>(out.all32.data() + (size_t)b * out.bytes_f32)->features = out.features;
+  }
+  return out;
+}
+
 }  // namespace olb
 #endif  // OLB_PREP_H_

@@ -947,50 +947,14 @@ static int build_batch(const OlbTable* tmpl, const double* params, int32_t n_sys
                        std::vector<unsigned char>& all32, OlbDeviceTable& h) {
   if (!tmpl || !params) return fail(OLB_ERR_INVALID_ARG, "template table or params is NULL");
   if (n_systems < 1 || n_systems > 65535) return fail(OLB_ERR_INVALID_ARG, "n_systems must be in [1, 65535]");
-  if (tmpl->n_wl != 1) return fail(OLB_ERR_UNSUPPORTED, "batched tables support one wavelength");
-  const int S = tmpl->n_surfaces;
-  std::vector<OlbSurface> surf(tmpl->surfaces, tmpl->surfaces + S);
-  std::vector<double> pool(tmpl->pool, tmpl->pool + tmpl->pool_len);
-  OlbTable t = *tmpl;
-  t.surfaces = surf.data();
-  t.pool = pool.data();
-  uint32_t features = 0;
-  for (int b = 0; b < n_systems; ++b) {
-    for (int s = 0; s < S; ++s) {
-      const double* p = params + ((size_t)b * S + s) * OLB_BP_COUNT;
-      OlbSurface& o = surf[s];
-      const OlbSurface& o0 = tmpl->surfaces[s];
-      if (o0.kind == OLB_GEOM_NOOP) continue;
-      o.t[0] = p[OLB_BP_TX]; o.t[1] = p[OLB_BP_TY]; o.t[2] = p[OLB_BP_TZ];
-      for (int q = 0; q < 9; ++q) o.R[q] = p[OLB_BP_R + q];
-      if (o0.kind != OLB_GEOM_PLANE) {
-        o.radius = p[OLB_BP_CURV] == 0 ? INFINITY : 1.0 / p[OLB_BP_CURV];
-        if (o0.kind != OLB_GEOM_TOROIDAL) o.conic = p[OLB_BP_CONIC];
-      }
-      pool[o0.media_off + 0] = p[OLB_BP_N1];
-      pool[o0.media_off + 1] = p[OLB_BP_N2];
-      if (o0.kind == OLB_GEOM_EVEN_ASPHERE)
-        for (int j = 0; j < o0.n_coef && j < OLB_BP_MAX_COEF; ++j) pool[o0.coef_off + j] = p[OLB_BP_COEF + j];
-    }
-    PrepResult pr = prepare_table(t);
-    if (!pr.error.empty()) return fail(OLB_ERR_TABLE, "system " + std::to_string(b) + ": " + pr.error);
-    if (b == 0) {
-      h.bytes_f64 = (int32_t)pr.blob_f64.size(); h.bytes_f32 = (int32_t)pr.blob_f32.size();
-      h.bwd_supported = 0; h.bwd_slots = 0;
-    } else if ((int32_t)pr.blob_f64.size() != h.bytes_f64 || (int32_t)pr.blob_f32.size() != h.bytes_f32) {
-      return fail(OLB_ERR_TABLE, "batched systems must share one table structure");
-    }
-    features |= pr.features;
-    h.hints |= (int32_t)pr.hints;
-    all64.insert(all64.end(), pr.blob_f64.begin(), pr.blob_f64.end());
-    all32.insert(all32.end(), pr.blob_f32.begin(), pr.blob_f32.end());
-  }
-  // every blob must name the union of the features (the kernel variant is chosen once)
-  for (int b = 0; b < n_systems; ++b) {
-    reinterpret_cast<PrepHeader*>(all64.data() + (size_t)b * h.bytes_f64)->features = features;
-    reinterpret_cast<PrepHeader*>(all32.data() + (size_t)b * h.bytes_f32)->features = features;
-  }
-  h.magic = WS_MAGIC; h.features = features; h.n_surfaces = S; h.n_wl = 1; h.n_systems = n_systems;
+  BatchPrep bp = prepare_batch(*tmpl, params, n_systems);     // olb_prep.h (host logic, also checked on the CPU)
+  if (!bp.error.empty()) return fail(bp.unsupported ? OLB_ERR_UNSUPPORTED : OLB_ERR_TABLE, bp.error);
+  all64.swap(bp.all64);
+  all32.swap(bp.all32);
+  h.bytes_f64 = bp.bytes_f64; h.bytes_f32 = bp.bytes_f32;
+  h.bwd_supported = 0; h.bwd_slots = 0;
+  h.hints = (int32_t)bp.hints;
+  h.magic = WS_MAGIC; h.features = bp.features; h.n_surfaces = tmpl->n_surfaces; h.n_wl = 1; h.n_systems = n_systems;
   h.stride_f64 = h.bytes_f64; h.stride_f32 = h.bytes_f32;
   h.off_f64 = 64; h.off_f32 = 64 + (int32_t)all64.size();
   return OLB_OK;

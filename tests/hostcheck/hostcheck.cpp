@@ -154,6 +154,29 @@ int olbhc_wavefront(int64_t n, double** fin, const double* Px, const double* Py,
                     out[0][k], out[1][k], out[2][k], out[3][k]);
   return 0;
 }
+// host logic of the batched-systems upload (olb_prep.h::prepare_batch): copy system `b`'s prepared blob
+// (which = 0: fp64, 1: fp32) into out; returns its size, or -1 on error (message in err)
+int olbhc_batch_blob(const OlbTable* tmpl, const double* params, int n_systems, int b, int which, unsigned char* out,
+                     int out_cap, unsigned* features, char* err, int err_len) {
+  BatchPrep bp = prepare_batch(*tmpl, params, n_systems);
+  if (!bp.error.empty()) { snprintf(err, err_len, "%s", bp.error.c_str()); return -1; }
+  const int nb = which == 0 ? bp.bytes_f64 : bp.bytes_f32;
+  if (b < 0 || b >= n_systems || nb > out_cap) { snprintf(err, err_len, "bad system index / buffer"); return -1; }
+  const std::vector<unsigned char>& all = which == 0 ? bp.all64 : bp.all32;
+  memcpy(out, all.data() + (size_t)b * nb, nb);
+  *features = bp.features;
+  return nb;
+}
+int olbhc_single_blob(const OlbTable* tab, int which, unsigned char* out, int out_cap, unsigned* features, char* err,
+                      int err_len) {
+  PrepResult pr = prepare_table(*tab);
+  if (!pr.error.empty()) { snprintf(err, err_len, "%s", pr.error.c_str()); return -1; }
+  const std::vector<unsigned char>& blob = which == 0 ? pr.blob_f64 : pr.blob_f32;
+  if ((int)blob.size() > out_cap) { snprintf(err, err_len, "buffer too small"); return -1; }
+  memcpy(out, blob.data(), blob.size());
+  *features = pr.features;
+  return (int)blob.size();
+}
 int olbhc_features(const OlbTable* tab) {
   PrepResult pr = prepare_table(*tab);
   return pr.error.empty() ? (int)pr.features : -1;
