@@ -429,15 +429,15 @@ OLB_HD void newton_slopes(T x, T y, const PrepSurface<T>& S, const T* pool, T& f
   T sag, g;
   conic_sag_slope(r2, S, sag, g);
   if (S.kind == OLB_GEOM_EVEN_ASPHERE) {
-    const T* c = pool + S.coef_off;
+    const T* d = pool + S.poly_d_off;       // 2(i+1) C_i, prepared on the host
     T h = 0;
-    for (int i = S.n_coef - 1; i >= 0; --i) h = o_fma(h, r2, (T)(2 * (i + 1)) * c[i]);
+    for (int i = S.n_coef - 1; i >= 0; --i) h = o_fma(h, r2, d[i]);
     g += h;
     fx = x * g; fy = y * g;
   } else if (S.kind == OLB_GEOM_ODD_ASPHERE) {
-    const T* c = pool + S.coef_off;
+    const T* d = pool + S.poly_d_off;       // (i+1) C_i, prepared on the host
     T r = o_sqrt(r2), h = 0;
-    for (int i = S.n_coef - 1; i >= 0; --i) h = o_fma(h, r, (T)(i + 1) * c[i]);
+    for (int i = S.n_coef - 1; i >= 0; --i) h = o_fma(h, r, d[i]);
     // terms (i+1) x C_i r^(i-1); non-finite terms are zeroed by the reference (r == 0)
     T hr = r > 0 ? o_div(h, r) : (T)0;
     g += hr;
@@ -482,13 +482,47 @@ OLB_HD void newton_slopes(T x, T y, const PrepSurface<T>& S, const T* pool, T& f
 // iterate sits on the noise floor of f, which for fp32 polynomial sags lies above the
 // floor estimate) keeping the better of the last two iterates -- so fp32 cannot spin
 // to max_iter.
+// Sag and slopes at the same point (one Newton iteration needs both).  Even / odd aspheres share the conic
+// square root and r^2 between the two (returns with fx, fy set); for the other families only the sag is
+// evaluated here and newton_distance calls newton_slopes once the convergence test has passed.
 template <typename T, uint32_t FEAT = 0xffffffffu>
+OLB_HD T newton_sag_slopes(T x, T y, const PrepSurface<T>& S, const T* pool, T& fx, T& fy, int& status) {
+  if (S.kind == OLB_GEOM_EVEN_ASPHERE || S.kind == OLB_GEOM_ODD_ASPHERE) {
+    const T r2 = o_fma(x, x, y * y);
+    T sag, g;
+    conic_sag_slope(r2, S, sag, g);
+    const T* c = pool + S.coef_off;
+    const T* d = pool + S.poly_d_off;
+    T h = 0, hd = 0;
+    if (S.kind == OLB_GEOM_EVEN_ASPHERE) {
+      for (int i = S.n_coef - 1; i >= 0; --i) { h = o_fma(h, r2, c[i]); hd = o_fma(hd, r2, d[i]); }
+      sag = o_fma(h, r2, sag);
+      g += hd;
+    } else {
+      const T r = o_sqrt(r2);
+      for (int i = S.n_coef - 1; i >= 0; --i) { h = o_fma(h, r, c[i]); hd = o_fma(hd, r, d[i]); }
+      sag = o_fma(h, r, sag);
+      g += r > 0 ? o_div(hd, r) : (T)0;
+    }
+    fx = x * g; fy = y * g;
+    return sag;
+  }
+  fx = 0; fy = 0;                       // (not an asphere: never reached from newton_distance<.., ASPH = true>)
+  return newton_sag<T, FEAT>(x, y, S, pool, status);
+}
+
+// ASPH: the surface is an even / odd asphere (compile-time, so that each family's loop carries only its own code)
+template <typename T, uint32_t FEAT = 0xffffffffu, bool ASPH = false>
 OLB_HD T newton_distance(T x, T y, T z, T L, T M, T N, const PrepSurface<T>& S, const T* pool, int& status) {
   T t = conic_distance(x, y, z, L, M, N, S);
   T t_prev = t, f_prev = (T)INFINITY;
+  constexpr bool asphere = ASPH;
   for (int it = 0; it < S.max_iter; ++it) {
     T xi = o_fma(t, L, x), yi = o_fma(t, M, y), zi = o_fma(t, N, z);
-    T sag = newton_sag<T, FEAT>(xi, yi, S, pool, status);
+    T fx = 0, fy = 0;
+    T sag;
+    if constexpr (ASPH) sag = newton_sag_slopes<T, FEAT>(xi, yi, S, pool, fx, fy, status);
+    else sag = newton_sag<T, FEAT>(xi, yi, S, pool, status);
     T f = sag - zi;
     T af = o_abs(f);
     if (!(af == af)) break;  // NaN stays NaN (the reference would spin to max_iter on it)
@@ -500,8 +534,7 @@ OLB_HD T newton_distance(T x, T y, T z, T L, T M, T N, const PrepSurface<T>& S, 
       if (!(af < f_prev)) t = t_prev;
       break;
     }
-    T fx, fy;
-    newton_slopes<T, FEAT>(xi, yi, S, pool, fx, fy);
+    if (!asphere) newton_slopes<T, FEAT>(xi, yi, S, pool, fx, fy);
     // f'(t) = fx L + fy M - N  with fx = -nx/nz = dz/dx  (newton_raphson.py:155-161)
     T df = o_fma(fx, L, o_fma(fy, M, -N));
     T dfs = o_abs(df) > (T)1e-14 ? df : (T)1e-14;
@@ -517,12 +550,13 @@ OLB_HD T newton_distance(T x, T y, T z, T L, T M, T N, const PrepSurface<T>& S, 
 // shrinks them by 30 % but the spills around the call cost more than the I-cache misses saved
 // (fp32 +4..27 %, fp64 +10..25 % slower; profiles/tune_r1.md, sweep 8), so it stays inlined.
 template <typename T> struct NewtonHit { T t, fx, fy; int status; };
-template <typename T, uint32_t FEAT = 0xffffffffu>
+template <typename T, uint32_t FEAT = 0xffffffffu, bool ASPH = false>
 OLB_HD_CALL NewtonHit<T> newton_hit(T x, T y, T z, T L, T M, T N, const PrepSurface<T>* S, const T* pool) {
   NewtonHit<T> h;
   h.status = 0;
-  h.t = newton_distance<T, FEAT>(x, y, z, L, M, N, *S, pool, h.status);
-  newton_slopes<T, FEAT>(o_fma(h.t, L, x), o_fma(h.t, M, y), *S, pool, h.fx, h.fy);
+  h.t = newton_distance<T, FEAT, ASPH>(x, y, z, L, M, N, *S, pool, h.status);
+  if constexpr (ASPH) (void)newton_sag_slopes<T, FEAT>(o_fma(h.t, L, x), o_fma(h.t, M, y), *S, pool, h.fx, h.fy, h.status);
+  else newton_slopes<T, FEAT>(o_fma(h.t, L, x), o_fma(h.t, M, y), *S, pool, h.fx, h.fy);
   return h;
 }
 
@@ -640,7 +674,7 @@ OLB_HD void polar_update(Ray<T>& r, const PrepSurface<T>& S, T ncoat, T cosi) {
 // The surface step.  FEAT gates code that most systems never need (register pressure, code
 // size); KIND (0 plane, 1 sphere/conic closed form, 2 Newton family) is resolved by the caller
 // ONCE per surface, outside the per-ray loop, so the hot loop carries no geometry branches.
-enum { KIND_PLANE = 0, KIND_CONIC = 1, KIND_NEWTON = 2 };
+enum { KIND_PLANE = 0, KIND_CONIC = 1, KIND_NEWTON = 2, KIND_ASPHERE = 3 };   // NEWTON: any family (generic loop); ASPHERE: even / odd only (fused loop)
 template <typename T, uint32_t FEAT, int KIND>
 OLB_HD void surface_step_k(Ray<T>& r, const PrepSurface<T>& S, const T* pool, bool from_global, int& status) {
   // -- localize (coordinate_system.py:73-89), from global or from the previous local frame
@@ -662,7 +696,7 @@ OLB_HD void surface_step_k(Ray<T>& r, const PrepSurface<T>& S, const T* pool, bo
   } else if (KIND == KIND_CONIC) {
     t = conic_distance(r.x, r.y, r.z, r.L, r.M, r.N, S);
   } else {
-    NewtonHit<T> h = newton_hit<T, FEAT>(r.x, r.y, r.z, r.L, r.M, r.N, &S, pool);
+    NewtonHit<T> h = newton_hit<T, FEAT, KIND == KIND_ASPHERE>(r.x, r.y, r.z, r.L, r.M, r.N, &S, pool);
     t = h.t; nfx = h.fx; nfy = h.fy;
     status |= h.status;
   }
@@ -744,7 +778,12 @@ template <typename T, uint32_t FEAT>
 OLB_HD void surface_step(Ray<T>& r, const PrepSurface<T>& S, const T* pool, bool from_global, int& status) {
   if (S.kind == OLB_GEOM_PLANE) surface_step_k<T, FEAT, KIND_PLANE>(r, S, pool, from_global, status);
   else if (S.kind == OLB_GEOM_STANDARD) surface_step_k<T, FEAT, KIND_CONIC>(r, S, pool, from_global, status);
-  else if (FEAT & FEAT_NEWTON) surface_step_k<T, FEAT, KIND_NEWTON>(r, S, pool, from_global, status);
+  else if constexpr ((FEAT & FEAT_NEWTON) != 0) {
+    // without FEAT_FREEFORM every Newton surface of the table is an even / odd asphere: the fused loop; with
+    // it, one generic loop serves all families (two loops in one kernel cost more I-cache than the fusion saves)
+    if constexpr ((FEAT & FEAT_FREEFORM) != 0) surface_step_k<T, FEAT, KIND_NEWTON>(r, S, pool, from_global, status);
+    else surface_step_k<T, FEAT, KIND_ASPHERE>(r, S, pool, from_global, status);
+  }
 }
 
 // Local -> global for the record (coordinate_system.py:91-107).

@@ -28,9 +28,10 @@ namespace olb {
 // Feature bits: which code paths a table needs (selects the kernel instantiation).
 enum : uint32_t {
   FEAT_ROT = 1u << 0,      // some surface has a rotated pose
-  FEAT_NEWTON = 1u << 1,   // even/odd asphere, polynomial, Zernike (Newton iteration)
+  FEAT_NEWTON = 1u << 1,   // a Newton-iteration surface (alone: even / odd aspheres only)
   FEAT_EXTRA = 1u << 2,    // non-radial aperture programs, simple coatings, L0/M0/N0 output
   FEAT_POL = 1u << 3,      // polarized rays (P matrix) / Fresnel coatings
+  FEAT_FREEFORM = 1u << 4, // polynomial / Zernike / Chebyshev / biconic / toroidal / Forbes surfaces (with NEWTON)
 };
 
 struct PrepHeader {
@@ -277,7 +278,7 @@ static inline PrepResult prepare_table(const OlbTable& tab) {
     const bool newton = in.kind >= OLB_GEOM_EVEN_ASPHERE;
     if (newton) {
       features |= FEAT_NEWTON;
-      if (in.kind > OLB_GEOM_ODD_ASPHERE) res.hints |= HINT_POLY_NEWTON;
+      if (in.kind != OLB_GEOM_EVEN_ASPHERE && in.kind != OLB_GEOM_ODD_ASPHERE) { res.hints |= HINT_POLY_NEWTON; features |= FEAT_FREEFORM; }
       if (in.max_iter < 0) { res.error = "negative max_iter"; return res; }
     }
     if (in.kind == OLB_GEOM_EVEN_ASPHERE || in.kind == OLB_GEOM_ODD_ASPHERE) {
@@ -285,6 +286,11 @@ static inline PrepResult prepare_table(const OlbTable& tab) {
       o.n_coef = in.n_coef;
       o.coef_off = (int)pool.size();
       for (int i = 0; i < in.n_coef; ++i) pool.push_back(tab.pool[in.coef_off + i]);
+      while (pool.size() % 4) pool.push_back(0);
+      // slope coefficients, so that the Newton loop does one FMA per term: 2(i+1) C_i (even), (i+1) C_i (odd)
+      o.poly_d_off = (int)pool.size();
+      const double step = in.kind == OLB_GEOM_EVEN_ASPHERE ? 2.0 : 1.0;
+      for (int i = 0; i < in.n_coef; ++i) pool.push_back(step * (i + 1) * tab.pool[in.coef_off + i]);
       while (pool.size() % 4) pool.push_back(0);
     } else if (in.kind == OLB_GEOM_POLYNOMIAL) {
       const int cols = in.aux0 > 0 ? in.aux0 : 1;

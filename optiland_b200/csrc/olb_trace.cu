@@ -304,8 +304,16 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<T, RPT, FEAT>::v)) trace_ker
 #pragma unroll
           for (int k = 0; k < RPT; ++k) surface_step_k<T, FEAT, KIND_CONIC>(r[k], S, pool, fg, status);
         } else if constexpr ((FEAT & FEAT_NEWTON) != 0) {
-#pragma unroll  // (the launcher gives Newton tables RPT <= 2, so this stays inside the I-cache)
-          for (int k = 0; k < RPT; ++k) surface_step_k<T, FEAT, KIND_NEWTON>(r[k], S, pool, fg, status);
+          // (the launcher gives Newton tables RPT <= 2, so the unrolled bodies stay inside the I-cache.)
+          // Asphere-only tables (no FEAT_FREEFORM) run the fused sag + slope loop; tables with a polynomial-family
+          // surface run ONE generic loop for all their Newton surfaces.
+          if constexpr ((FEAT & FEAT_FREEFORM) != 0) {
+#pragma unroll
+            for (int k = 0; k < RPT; ++k) surface_step_k<T, FEAT, KIND_NEWTON>(r[k], S, pool, fg, status);
+          } else {
+#pragma unroll
+            for (int k = 0; k < RPT; ++k) surface_step_k<T, FEAT, KIND_ASPHERE>(r[k], S, pool, fg, status);
+          }
         }
         have_frame = true;
       }
@@ -716,16 +724,19 @@ static int launch_instance(const TraceArgs& a, cudaStream_t stream) {
   return OLB_OK;
 }
 
+constexpr uint32_t FEAT_GENERAL = FEAT_ROT | FEAT_NEWTON | FEAT_EXTRA | FEAT_FREEFORM;
+
 template <typename T, int RPT>
 static int launch_feat(const TraceArgs& a, uint32_t features, cudaStream_t stream) {
   if (features & FEAT_POL) {
-    if constexpr (RPT == 1) return launch_instance<T, 1, FEAT_ROT | FEAT_NEWTON | FEAT_EXTRA | FEAT_POL>(a, stream);
+    if constexpr (RPT == 1) return launch_instance<T, 1, FEAT_GENERAL | FEAT_POL>(a, stream);
     else return fail(OLB_ERR_UNSUPPORTED, "polarized trace uses one ray per thread");
   }
   if (features == 0) return launch_instance<T, RPT, 0u>(a, stream);
   if (features == FEAT_ROT) return launch_instance<T, RPT, FEAT_ROT>(a, stream);
-  if (features == FEAT_NEWTON) return launch_instance<T, RPT, FEAT_NEWTON>(a, stream);
-  return launch_instance<T, RPT, FEAT_ROT | FEAT_NEWTON | FEAT_EXTRA>(a, stream);
+  if (features == FEAT_NEWTON) return launch_instance<T, RPT, FEAT_NEWTON>(a, stream);                        // aspheres
+  if (features == (FEAT_NEWTON | FEAT_FREEFORM)) return launch_instance<T, RPT, FEAT_NEWTON | FEAT_FREEFORM>(a, stream);
+  return launch_instance<T, RPT, FEAT_GENERAL>(a, stream);
 }
 
 // fp32 x 4 rays/thread exists only for the closed-form feature sets (code size, registers).
@@ -733,10 +744,6 @@ template <typename T, int RPT>
 static int launch_feat_cf(const TraceArgs& a, uint32_t features, cudaStream_t stream) {
   if (features & FEAT_POL) return fail(OLB_ERR_UNSUPPORTED, "polarized tables run one ray per thread (internal dispatch error)");
   if (features == 0) return launch_instance<T, RPT, 0u>(a, stream);
-#ifdef OLB_NEWTON_RPT4
-  if (features == FEAT_NEWTON) return launch_instance<T, RPT, FEAT_NEWTON>(a, stream);
-  if (features != FEAT_ROT) return launch_instance<T, RPT, FEAT_ROT | FEAT_NEWTON | FEAT_EXTRA>(a, stream);
-#endif
   return launch_instance<T, RPT, FEAT_ROT>(a, stream);
 }
 
@@ -869,9 +876,7 @@ static int trace_impl(const OlbDeviceTable* wh, int32_t first, int32_t last, con
   // (2 rays/thread is 5-45 % slower there: profiles/tune_r1.md, sweeps 7 and 8)
   const bool poly_newton = (wh->hints & (int32_t)HINT_POLY_NEWTON) != 0;
   int rpt = force_rpt > 0 ? force_rpt : (sizeof(T) == 4 ? (closed_form ? 4 : (poly_newton ? 1 : 2)) : 1);
-#ifndef OLB_NEWTON_RPT4
   if (!closed_form && rpt > 2) rpt = 2;
-#endif
   if constexpr (sizeof(T) == 4) {
     if (rpt >= 4 && vec_ok) return launch_feat_cf<T, 4>(a, features, stream);
     if (rpt >= 2 && rec_stride_ok2) return launch_feat<T, 2>(a, features, stream);

@@ -68,15 +68,16 @@ static int run(const OlbTable* tab, int first, int last, int64_t n, T** ray, T**
   const unsigned char* blob = sizeof(T) == 8 ? pr.blob_f64.data() : pr.blob_f32.data();
   if ((pr.features & FEAT_POL) && !pmat) { snprintf(err, err_len, "table needs polarized rays (p)"); return OLB_ERR_INVALID_ARG; }
   if (pmat) {
-    walk<T, FEAT_ROT | FEAT_NEWTON | FEAT_EXTRA | FEAT_POL>(blob, first, last, n, ray, rec, l0, pmat, status);
+    walk<T, FEAT_ROT | FEAT_NEWTON | FEAT_EXTRA | FEAT_FREEFORM | FEAT_POL>(blob, first, last, n, ray, rec, l0, pmat, status);
     return OLB_OK;
   }
-  // exercise the same three instantiations the launcher picks from
+  // exercise the same instantiations the launcher picks from
   uint32_t f = pr.features | (l0 ? FEAT_EXTRA : 0u);
   if (f == 0) walk<T, 0u>(blob, first, last, n, ray, rec, l0, nullptr, status);
   else if (f == FEAT_ROT) walk<T, FEAT_ROT>(blob, first, last, n, ray, rec, l0, nullptr, status);
   else if (f == FEAT_NEWTON) walk<T, FEAT_NEWTON>(blob, first, last, n, ray, rec, l0, nullptr, status);
-  else walk<T, FEAT_ROT | FEAT_NEWTON | FEAT_EXTRA>(blob, first, last, n, ray, rec, l0, nullptr, status);
+  else if (f == (FEAT_NEWTON | FEAT_FREEFORM)) walk<T, FEAT_NEWTON | FEAT_FREEFORM>(blob, first, last, n, ray, rec, l0, nullptr, status);
+  else walk<T, FEAT_ROT | FEAT_NEWTON | FEAT_EXTRA | FEAT_FREEFORM>(blob, first, last, n, ray, rec, l0, nullptr, status);
   return OLB_OK;
 }
 
