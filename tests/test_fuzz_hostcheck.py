@@ -1,0 +1,90 @@
+"""Randomised differential test: random sequential systems (planes, conics, even / odd aspheres, polynomial,
+tilts and decenters, mirrors, aperture trees, simple coatings, absorbing media, two wavelengths) traced by the
+device math compiled for the host (tests/hostcheck) and by the NumPy oracle (itself pinned on the reference's
+goldens).  Catches divergences the fixed fixtures do not reach: root selection, NaN patterns, clip / coating
+order, frame chaining."""
+import numpy as np
+import pytest
+
+from oracle import trace_oracle as O
+from oracle.hostcheck_api import run_hostcheck
+from optiland_b200 import table as T
+from tests._util import REC
+from tests.test_hostcheck import hc  # noqa: F401  (fixture)
+
+
+def random_system(rng, n_surf):
+    wl = np.array([0.48, 0.65])
+    specs = [T.SurfaceSpec(kind=T.GEOM_NOOP, n1=np.ones(2), n2=np.ones(2), k1=np.zeros(2))]
+    z = 0.0
+    n_prev = np.ones(2)
+    for s in range(1, n_surf):
+        z += rng.uniform(2.0, 12.0)
+        kind = rng.choice([T.GEOM_PLANE, T.GEOM_STANDARD, T.GEOM_STANDARD, T.GEOM_EVEN_ASPHERE, T.GEOM_ODD_ASPHERE,
+                           T.GEOM_POLYNOMIAL])
+        last = s == n_surf - 1
+        mirror = (not last) and rng.random() < 0.15
+        if last:
+            n_next = n_prev
+        elif mirror:
+            n_next = n_prev
+        else:
+            base = rng.choice([1.0, 1.5, 1.7])
+            n_next = np.array([base + 0.01 * (base > 1), base]) if base > 1 else np.ones(2)
+        sp = dict(kind=int(kind), t=np.array([rng.normal(0, 0.2), rng.normal(0, 0.2), z]), reflective=bool(mirror),
+                  n1=n_prev.copy(), n2=n_next.copy(), k1=np.where(n_prev > 1, rng.choice([0.0, 2e-7]), 0.0) * np.ones(2))
+        if rng.random() < 0.4:
+            sp["R"] = T.rotation_matrix(*rng.normal(0, 0.03, 3)) + 0.0
+        if kind != T.GEOM_PLANE:
+            sp["radius"] = float(rng.choice([-1, 1]) * rng.uniform(25, 120))
+            sp["conic"] = float(rng.choice([0.0, -1.0, rng.normal(0, 0.5)]))
+        if kind in (T.GEOM_EVEN_ASPHERE, T.GEOM_ODD_ASPHERE, T.GEOM_POLYNOMIAL):
+            sp["tol"], sp["max_iter"] = 1e-12, 60
+        if kind == T.GEOM_EVEN_ASPHERE:
+            sp["coefficients"] = rng.normal(0, 1, 3) * np.array([1e-4, 1e-6, 1e-8])
+        elif kind == T.GEOM_ODD_ASPHERE:
+            sp["coefficients"] = rng.normal(0, 1, 4) * np.array([0.0, 1e-4, 1e-5, 1e-6])
+        elif kind == T.GEOM_POLYNOMIAL:
+            C = rng.normal(0, 1, (3, 3)) * 1e-4
+            C[0, 0] = 0.0
+            sp["coefficients"] = C
+        r = rng.random()
+        if r < 0.25:
+            sp["aperture"] = T.aperture_radial(rng.uniform(4, 9), rng.choice([0.0, 0.5]))
+        elif r < 0.4:
+            sp["aperture"] = T.aperture_combine(T.AP_DIFFERENCE, T.aperture_rect(-8, 8, -7, 9),
+                                                T.aperture_ellipse(1.0, 0.6, 0.3, -0.2))
+        if rng.random() < 0.2:
+            sp["coating"], sp["coat_t"], sp["coat_r"] = T.COAT_SIMPLE, 0.97, 0.9
+        specs.append(T.SurfaceSpec(**sp))
+        if mirror:      # keep going forward in z for simplicity: fold the sign of the next spacing instead
+            z -= rng.uniform(4.0, 10.0) * 2
+        n_prev = n_next
+    return T.SurfaceTable(specs, wl)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_systems_host_math_vs_oracle(hc, seed):
+    rng = np.random.default_rng(1000 + seed)
+    table = random_system(rng, int(rng.integers(4, 10)))
+    n = 96
+    x, y = rng.uniform(-5, 5, n), rng.uniform(-5, 5, n)
+    L, M = rng.normal(0, 0.05, n), rng.normal(0, 0.05, n)
+    N = np.sqrt(1 - L**2 - M**2)
+    rays = dict(x=x, y=y, z=np.full(n, -5.0), L=L, M=M, N=N, i=np.ones(n), w=rng.choice(table.wavelengths, n))
+    _, orec, ost = O.trace(table, rays)
+    scale = max(1.0, float(np.nanmax(np.abs(np.where(np.isfinite(orec["z"]), orec["z"], 0)))))
+    out, rec, st = run_hostcheck(hc, table, rays, np.float64)[:3]
+    assert st == ost
+    for k in REC:
+        a, b = rec[k], orec[k]
+        assert np.array_equal(np.isnan(a), np.isnan(b)), (seed, k, "NaN pattern")
+        m = np.isfinite(b)
+        if m.any():
+            assert np.max(np.abs(a[m] - b[m])) <= 2e-10 * scale, (seed, k, float(np.max(np.abs(a[m] - b[m]))))
+    # fp32: same NaN pattern on well-conditioned rays is not guaranteed; check the bulk
+    out32, rec32, _ = run_hostcheck(hc, table, rays, np.float32)[:3]
+    fin = np.isfinite(orec["x"][-1]) & np.isfinite(rec32["x"][-1])
+    if fin.sum() > n // 2:
+        d = np.abs(rec32["x"][-1][fin] - orec["x"][-1][fin])
+        assert np.percentile(d, 90) <= 2e-4 * scale, (seed, float(np.percentile(d, 90)))
