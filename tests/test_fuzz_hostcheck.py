@@ -37,7 +37,10 @@ def random_system(rng, n_surf):
             sp["R"] = T.rotation_matrix(*rng.normal(0, 0.03, 3)) + 0.0
         if kind != T.GEOM_PLANE:
             sp["radius"] = float(rng.choice([-1, 1]) * rng.uniform(25, 120))
-            sp["conic"] = float(rng.choice([0.0, -1.0, rng.normal(0, 0.5)]))
+            # (not near k = -1 with near-axial rays: there a = (1 + k) N^2 + L^2 + M^2 -> 0 and the REFERENCE's
+            # quadratic (-b +- sqrt(d)) / 2a loses ~8 digits by cancellation -- the kernel's stable form does
+            # not, so the two differ by 1e-8 mm there; a == 0 exactly is covered by test_degenerate_conic_roots)
+            sp["conic"] = float(rng.choice([0.0, -0.6, rng.uniform(-0.7, 0.7)]))
         if kind in (T.GEOM_EVEN_ASPHERE, T.GEOM_ODD_ASPHERE, T.GEOM_POLYNOMIAL):
             sp["tol"], sp["max_iter"] = 1e-12, 60
         if kind == T.GEOM_EVEN_ASPHERE:
@@ -81,7 +84,7 @@ def test_random_systems_host_math_vs_oracle(hc, seed):
         assert np.array_equal(np.isnan(a), np.isnan(b)), (seed, k, "NaN pattern")
         m = np.isfinite(b)
         if m.any():
-            assert np.max(np.abs(a[m] - b[m])) <= 2e-10 * scale, (seed, k, float(np.max(np.abs(a[m] - b[m]))))
+            assert np.max(np.abs(a[m] - b[m])) <= 1e-11 * scale, (seed, k, float(np.max(np.abs(a[m] - b[m]))))
     # fp32: same NaN pattern on well-conditioned rays is not guaranteed; check the bulk
     out32, rec32, _ = run_hostcheck(hc, table, rays, np.float32)[:3]
     fin = np.isfinite(orec["x"][-1]) & np.isfinite(rec32["x"][-1])
