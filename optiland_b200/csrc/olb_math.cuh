@@ -221,6 +221,7 @@ OLB_HD void poly2_eval(const T* C, int rows, int cols, bool tri, T x, T y, T& P,
     const T* row = C + i * cols;
     const int jmax = tri ? (rows - 1 - i) : (cols - 1);
     T q = 0, qy = 0;
+#pragma unroll 4
     for (int j = jmax; j >= 0; --j) {
       qy = o_fma(qy, y, q);
       q = o_fma(q, y, row[j]);
@@ -237,6 +238,7 @@ OLB_HD T poly2_value(const T* C, int rows, int cols, bool tri, T x, T y) {
     const T* row = C + i * cols;
     const int jmax = tri ? (rows - 1 - i) : (cols - 1);
     T q = 0;
+#pragma unroll 4
     for (int j = jmax; j >= 0; --j) q = o_fma(q, y, row[j]);
     P = o_fma(P, x, q);
   }
