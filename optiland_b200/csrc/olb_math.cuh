@@ -278,6 +278,7 @@ OLB_HD void toroidal_yz(T y, const PrepSurface<T>& S, const T* pool, T& zy, T& d
   }
   const T* a = pool + S.coef_off;
   T h = 0, hd = 0;
+#pragma unroll 4
   for (int i = S.n_coef - 1; i >= 0; --i) {
     h = o_fma(h, y2, a[i]);
     hd = o_fma(hd, y2, (T)(2 * (i + 1)) * a[i]);
@@ -295,6 +296,7 @@ OLB_HD void forbes_q_sum(const T* b, int nc, T x, T& S, T& dS) {
   const T p = (T)2 - (T)4 * x;
   T a1 = 0, a2 = 0, d1 = 0, d2 = 0;          // alpha_{n+1}, alpha_{n+2}, alpha'_{n+1}, alpha'_{n+2}
   T a0 = 0, d0 = 0;
+#pragma unroll 4
   for (int n = nc - 1; n >= 0; --n) {
     a0 = b[n] + p * a1 - a2;
     d0 = p * d1 - d2 - (T)4 * a1;
@@ -497,11 +499,13 @@ OLB_HD T newton_sag_slopes(T x, T y, const PrepSurface<T>& S, const T* pool, T& 
     const T* d = pool + S.poly_d_off;
     T h = 0, hd = 0;
     if (S.kind == OLB_GEOM_EVEN_ASPHERE) {
+#pragma unroll 4
       for (int i = S.n_coef - 1; i >= 0; --i) { h = o_fma(h, r2, c[i]); hd = o_fma(hd, r2, d[i]); }
       sag = o_fma(h, r2, sag);
       g += hd;
     } else {
       const T r = o_sqrt(r2);
+#pragma unroll 4
       for (int i = S.n_coef - 1; i >= 0; --i) { h = o_fma(h, r, c[i]); hd = o_fma(hd, r, d[i]); }
       sag = o_fma(h, r, sag);
       g += r > 0 ? o_div(hd, r) : (T)0;
