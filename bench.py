@@ -263,11 +263,11 @@ def run_ours(args):
     t_hi = time.perf_counter()
     launches = lib.olb_launch_count() - launches0
     total_ms = t_start.elapsed_time(t_end)
-    # nvidia-smi samples every 20 ms: a short timed region (small --steps) may hold no sample at all, so the
-    # SAME step keeps running, untimed, until the load window is >= 0.2 s; the clocks line says so
+    # nvidia-smi samples every 20 ms: a short timed region (small --steps) may hold no sample at all; then the
+    # SAME step keeps running, untimed, until the load window is >= 0.1 s, and the clocks line says so
     clock_extra = 0
     t_clock_hi = t_hi
-    while t_clock_hi - t_lo < 0.2:
+    while t_clock_hi - t_lo < 0.1:
         rr, rec = step()
         torch.cuda.synchronize()
         clock_extra += 1
@@ -362,7 +362,7 @@ def run_ours(args):
         clocks = sampler.stop(t_lo, t_clock_hi)
         clocks["window"] = ("timed region" if clock_extra == 0 else
                             f"timed region + {clock_extra} further untimed steps of the same launch (the timed region "
-                            f"of {total_ms:.1f} ms is shorter than nvidia-smi's sampling period)")
+                            f"of {total_ms:.1f} ms is too short for nvidia-smi's 20 ms sampling)")
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
