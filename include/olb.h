@@ -384,14 +384,14 @@ int olb_trace_host_pupil_f64(const OlbDeviceTable* table, int32_t first, int32_t
  * dLoss/d(surface parameters) into grad_params: n_surfaces blocks of OLB_GP_COUNT doubles,
  *   [OLB_GP_TX..TZ] pose translation t, [OLB_GP_CURV] curvature 1/radius (d/dradius =
  *   -curv^2 * this), [OLB_GP_CONIC] k, [OLB_GP_N1] n1, [OLB_GP_N2] n2,
- *   [OLB_GP_COEF + j] even-asphere coefficient C_j (j < OLB_GP_MAX_COEF),
+ *   [OLB_GP_COEF + j] even- / odd-asphere coefficient C_j (j < OLB_GP_MAX_COEF),
  *   [OLB_GP_R + 3 i + j] pose rotation matrix entry R_ij (tilted poses only; the caller chains it to the
  *   Euler angles, R = Rz Ry Rx, coordinate_system.py:121-143).
  * Everything is recomputed from the forward call's inputs and records (nothing else is
  * saved): `rays_in` is the launch state the forward call consumed (x,y,z,L,M,N,i), `rec` its
  * full records for the same [first, last).  grad_rec pointers may be NULL individually
  * (that quantity has zero gradient); grad_rays_in (x,y,z,L,M,N,i,opd) may be NULL.
- * Supported tables (OlbDeviceTable.bwd_supported): plane / standard / even-asphere geometry, any
+ * Supported tables (OlbDeviceTable.bwd_supported): plane / standard / even- and odd-asphere geometry, any
  * pose (translation gradients, and for tilted poses dLoss/dR for the caller to chain to the tilt angles), any
  * aperture tree, no or simple coating, one wavelength; otherwise OLB_ERR_UNSUPPORTED.  Rays that are NaN at a surface carry no gradient.
  * grad_row_mask: bit r set = record row r of grad_rec may be non-zero (rows with a clear bit

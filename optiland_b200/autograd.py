@@ -8,7 +8,7 @@ the forward is ONE kernel launch and the backward ONE launch of the hand-derived
 
 Parameters enter as one tensor ``params`` of shape (S, GP_COUNT) (fp64) laid out like the C ABI's
 gradient block: columns ``GP_TX, GP_TY, GP_TZ`` pose translation, ``GP_CURV`` curvature 1/radius,
-``GP_CONIC``, ``GP_N1``, ``GP_N2``, ``GP_COEF + j`` even-asphere coefficients, ``GP_R + 3 i + j`` the pose
+``GP_CONIC``, ``GP_N1``, ``GP_N2``, ``GP_COEF + j`` even- / odd-asphere coefficients, ``GP_R + 3 i + j`` the pose
 rotation matrix (gradients only for tilted poses).  Callers build it from their own leaf tensors with ordinary
 torch ops (e.g. ``params[s, GP_CURV] = 1 / radius``, ``R = Rz(rz) @ Ry(ry) @ Rx(rx)``), so the chain rule to radii,
 thicknesses, tilt angles ... is autograd's job.
@@ -42,10 +42,10 @@ def table_to_params(table: T.SurfaceTable) -> torch.Tensor:
         p[s, GP_CONIC] = spec.conic
         p[s, GP_N1], p[s, GP_N2] = spec.n1[0], spec.n2[0]
         p[s, GP_R:GP_R + 9] = np.asarray(spec.R, dtype=np.float64).reshape(9)
-        if spec.kind == T.GEOM_EVEN_ASPHERE:
+        if spec.kind in (T.GEOM_EVEN_ASPHERE, T.GEOM_ODD_ASPHERE):
             k = len(spec.coefficients)
             if k > GP_MAX_COEF:
-                raise ValueError(f"more than {GP_MAX_COEF} even-asphere coefficients")
+                raise ValueError(f"more than {GP_MAX_COEF} asphere coefficients")
             p[s, GP_COEF:GP_COEF + k] = spec.coefficients
     return torch.from_numpy(p)
 
@@ -58,10 +58,10 @@ def params_to_table(table: T.SurfaceTable, params: torch.Tensor) -> T.SurfaceTab
         ch = dict(t=p[s, GP_TX:GP_TZ + 1].copy(), n1=np.array([p[s, GP_N1]]), n2=np.array([p[s, GP_N2]]))
         if spec.kind != T.GEOM_NOOP:
             ch["R"] = p[s, GP_R:GP_R + 9].reshape(3, 3).copy()
-        if spec.kind in (T.GEOM_STANDARD, T.GEOM_EVEN_ASPHERE):
+        if spec.kind in (T.GEOM_STANDARD, T.GEOM_EVEN_ASPHERE, T.GEOM_ODD_ASPHERE):
             ch["radius"] = float("inf") if p[s, GP_CURV] == 0 else 1.0 / p[s, GP_CURV]
             ch["conic"] = float(p[s, GP_CONIC])
-        if spec.kind == T.GEOM_EVEN_ASPHERE:
+        if spec.kind in (T.GEOM_EVEN_ASPHERE, T.GEOM_ODD_ASPHERE):
             ch["coefficients"] = p[s, GP_COEF:GP_COEF + len(spec.coefficients)].copy()
         specs.append(dataclasses.replace(spec, **ch))
     return T.SurfaceTable(specs, table.wavelengths)

@@ -891,6 +891,22 @@ OLB_HD bool surface_backward(const PrepSurface<T>& S, const T* pool, T xg0, T yg
       }
       g += asph_p;
       gp += asph_pp;
+    } else if (S.kind == OLB_GEOM_ODD_ASPHERE) {
+      // sag = conic + sum C_i r^(i+1): slope factor g += sum (i+1) C_i r^(i-1) (0 at r == 0, as the forward pass),
+      // d g / d r2 = sum (i+1)(i-1)/2 C_i r^(i-3)
+      const T* cf = pool + S.coef_off;
+      const T rr = o_sqrt(r2);
+      if (rr > 0) {
+        const T ir = o_rcp(rr);
+        T pw = ir;                                 // r^(i-1)
+        for (int j = 0; j < S.n_coef; ++j) {
+          asph_p = o_fma((T)(j + 1) * cf[j], pw, asph_p);
+          asph_pp = o_fma((T)0.5 * (T)((j + 1) * (j - 1)) * cf[j], pw * ir * ir, asph_pp);
+          pw *= rr;
+        }
+      }
+      g += asph_p;
+      gp += asph_pp;
     }
   }
   const T fx = x1 * g, fy = y1 * g;
@@ -998,6 +1014,15 @@ OLB_HD bool surface_backward(const PrepSurface<T>& S, const T* pool, T xg0, T yg
       for (int j = 0; j < GP_MAX_COEF; ++j) {    // compile-time bound: pg[] stays in registers
         if (j < S.n_coef) pg[GP_COEF + j] += q * pw * r2 + ag * (T)(2 * (j + 1)) * pw;  // d sag/dC_j = r2^(j+1); d g/dC_j = 2(j+1) r2^j
         pw *= r2;
+      }
+    } else if (S.kind == OLB_GEOM_ODD_ASPHERE) {
+      const T rr = o_sqrt(r2);
+      T pw = rr > 0 ? o_rcp(rr) : (T)0;          // r^(j-1); the slope term vanishes at r == 0 like the forward pass
+      T pws = rr;                                // r^(j+1)
+#pragma unroll
+      for (int j = 0; j < GP_MAX_COEF; ++j) {
+        if (j < S.n_coef) pg[GP_COEF + j] += q * pws + ag * (T)(j + 1) * pw;   // d sag/dC_j = r^(j+1); d g/dC_j = (j+1) r^(j-1)
+        pw *= rr; pws *= rr;
       }
     }
   }

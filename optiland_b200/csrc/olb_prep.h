@@ -461,7 +461,8 @@ static inline PrepResult prepare_table(const OlbTable& tab) {
   for (int s = 0; s < tab.n_surfaces; ++s) {
     ps[s].gslot = gslot;
     // 7 scalars + even-asphere coefficients + (tilted pose) the 9 entries of dLoss/dR
-    ps[s].gslots = ps[s].kind == OLB_GEOM_NOOP ? 0 : 7 + (ps[s].kind == OLB_GEOM_EVEN_ASPHERE ? ps[s].n_coef : 0) +
+    const bool asph = ps[s].kind == OLB_GEOM_EVEN_ASPHERE || ps[s].kind == OLB_GEOM_ODD_ASPHERE;
+    ps[s].gslots = ps[s].kind == OLB_GEOM_NOOP ? 0 : 7 + (asph ? ps[s].n_coef : 0) +
                                                          ((ps[s].flags & OLB_SF_ROTATED) ? 9 : 0);
     gslot += ps[s].gslots;
   }
@@ -469,7 +470,7 @@ static inline PrepResult prepare_table(const OlbTable& tab) {
   for (int s = 0; s < tab.n_surfaces; ++s) {
     const PrepSurface<double>& o = ps[s];
     const bool kind_ok = o.kind == OLB_GEOM_NOOP || o.kind == OLB_GEOM_PLANE || o.kind == OLB_GEOM_STANDARD ||
-                         (o.kind == OLB_GEOM_EVEN_ASPHERE && o.n_coef <= 12);
+                         ((o.kind == OLB_GEOM_EVEN_ASPHERE || o.kind == OLB_GEOM_ODD_ASPHERE) && o.n_coef <= 12);
     if (!kind_ok || o.coating == OLB_COAT_FRESNEL || tab.n_wl != 1)
       res.bwd_supported = false;
   }

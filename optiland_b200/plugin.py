@@ -238,7 +238,8 @@ def _live_params(surfaces, table, wavelength):
         if spec.kind != T.GEOM_NOOP:
             g = surf.geometry
             cs = g.cs
-            if cs.reference_cs is not None or spec.kind not in (T.GEOM_PLANE, T.GEOM_STANDARD, T.GEOM_EVEN_ASPHERE):
+            if cs.reference_cs is not None or spec.kind not in (T.GEOM_PLANE, T.GEOM_STANDARD, T.GEOM_EVEN_ASPHERE,
+                                                                T.GEOM_ODD_ASPHERE):
                 return None
             # pose rotation: constants (identity for an untilted surface -- the reference skips zero rotations
             # altogether, `if self.rz:` coordinate_system.py:84-89, so zero angles get no gradient there either);
@@ -262,7 +263,7 @@ def _live_params(surfaces, table, wavelength):
             flat_r.append(scalar(g.radius, like) if curved else one)
             vals[GP_N1] = scalar(surf.material_pre.n(wavelength), like)
             vals[GP_N2] = scalar(surf.material_post.n(wavelength), like)
-            if spec.kind == T.GEOM_EVEN_ASPHERE:
+            if spec.kind in (T.GEOM_EVEN_ASPHERE, T.GEOM_ODD_ASPHERE):
                 if len(g.coefficients) > GP_MAX_COEF:
                     return None
                 for j, cj in enumerate(g.coefficients):

@@ -42,7 +42,7 @@ def test_random_systems_kernel_vs_oracle(seed):
 
 @pytest.mark.parametrize("seed", range(6))
 def test_random_systems_backward_kernel_vs_finite_differences(seed):
-    """Adjoint kernel on random plane / conic / even-asphere systems with tilts, decenters, mirrors, aperture
+    """Adjoint kernel on random plane / conic / even- and odd-asphere systems with tilts, decenters, mirrors, aperture
     trees and simple coatings: parameter gradients of a random linear functional of the image-surface records
     against central differences of the forward kernel (fp64)."""
     from optiland_b200 import autograd as AG
@@ -55,9 +55,9 @@ def test_random_systems_backward_kernel_vs_finite_differences(seed):
     for s in full.surfaces:      # one wavelength, kinds inside the adjoint's scope
         import dataclasses
         ch = {k: getattr(s, k)[:1].copy() for k in ("n1", "n2", "k1")}
-        if s.kind in (T.GEOM_ODD_ASPHERE, T.GEOM_POLYNOMIAL):
+        if s.kind == T.GEOM_POLYNOMIAL:
             ch.update(kind=T.GEOM_STANDARD, coefficients=np.zeros(0))
-        if s.kind == T.GEOM_EVEN_ASPHERE:
+        if s.kind in (T.GEOM_EVEN_ASPHERE, T.GEOM_ODD_ASPHERE):
             ch["tol"] = 1e-14
         specs.append(dataclasses.replace(s, **ch))
     table = T.SurfaceTable(specs, full.wavelengths[:1])
@@ -88,8 +88,8 @@ def test_random_systems_backward_kernel_vs_finite_differences(seed):
         slots = [AG.GP_TZ, AG.GP_TX]
         if spec.kind != T.GEOM_PLANE:
             slots += [AG.GP_CURV, AG.GP_CONIC]
-        if spec.kind == T.GEOM_EVEN_ASPHERE:
-            slots.append(AG.GP_COEF)
+        if spec.kind in (T.GEOM_EVEN_ASPHERE, T.GEOM_ODD_ASPHERE):
+            slots.append(AG.GP_COEF + 1)
         if spec.rotated:
             slots.append(AG.GP_R + 1)
         for q in slots:
