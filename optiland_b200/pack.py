@@ -72,10 +72,14 @@ class _Prefetch:
         self.surfaces = surfaces
         self.wavelengths = wavelengths
         self.keep = []          # keeps the tensors alive so that id() stays unique while the table is in use
+        import torch
+
+        self._tensor = torch.Tensor
 
     def _add(self, v):
-        if hasattr(v, "detach") and hasattr(v, "numel") and v.numel() == 1 and v.dtype.is_floating_point:
-            self.keep.append(v)
+        if isinstance(v, self._tensor):
+            if v.numel() == 1 and v.dtype.is_floating_point:
+                self.keep.append(v)
         elif isinstance(v, (list, tuple)):
             for u in v:
                 self._add(u)
@@ -138,7 +142,7 @@ class _Prefetch:
             for ts in groups.values():
                 import torch
 
-                vals = torch.stack([t.detach().reshape(()) for t in ts]).double().cpu().numpy()
+                vals = torch.stack([t if t.ndim == 0 else t.reshape(()) for t in ts]).detach().double().cpu().numpy()
                 for t, v in zip(ts, vals):
                     resolved[id(t)] = float(v)
             _tls.resolved = resolved
