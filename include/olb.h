@@ -310,6 +310,20 @@ typedef struct OlbPupilLaunch {
   double target0[3];
   double target_scale[2];
   double intensity;
+  /* Per-ray FIELD coordinates (RealRayTracer.trace_generic, raytrace/real_ray_tracer.py:120-154: Hx, Hy, Px, Py
+   * arrays).  With Hx / Hy non-NULL the origin and the target also move with the ray's field point:
+   *     g(H) = tan(field_arg * H)  (field_mode 1: angle fields, field_arg = radians(max_field))
+   *            H                   (field_mode 2: object-height fields)
+   *     p0.x += origin_field[0] * g(Hx),  p0.y += origin_field[1] * g(Hy)
+   *     p1.x += target_field[0] * g(Hx),  p1.y += target_field[1] * g(Hy)      (telecentric: target follows origin)
+   * origin0 / target0 are then the H = 0 values.  NULL (field_mode 0): one field for all rays, as above. */
+  const void* Hx;
+  const void* Hy;
+  int32_t field_mode;
+  int32_t reserved;
+  double field_arg;
+  double origin_field[2];
+  double target_field[2];
 } OlbPupilLaunch;
 
 /*

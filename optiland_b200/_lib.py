@@ -52,7 +52,9 @@ class OlbRecords(C.Structure):
 
 class OlbPupilLaunch(C.Structure):
     _fields_ = [("Px", C.c_void_p), ("Py", C.c_void_p), ("origin0", C.c_double * 3), ("origin_scale", C.c_double * 2),
-                ("target0", C.c_double * 3), ("target_scale", C.c_double * 2), ("intensity", C.c_double)]
+                ("target0", C.c_double * 3), ("target_scale", C.c_double * 2), ("intensity", C.c_double),
+                ("Hx", C.c_void_p), ("Hy", C.c_void_p), ("field_mode", C.c_int32), ("reserved", C.c_int32),
+                ("field_arg", C.c_double), ("origin_field", C.c_double * 2), ("target_field", C.c_double * 2)]
 
 
 class OlbWavefrontRef(C.Structure):

@@ -111,11 +111,13 @@ OLB_HD double opd_value_f64(const Ray<float>& r) { return (double)r.opd + (doubl
 // Launch state of one ray from its pupil point (include/olb.h: OlbPupilLaunch; reference:
 // rays/ray_aiming/paraxial.py:85-105 on top of fields/field_types/angle.py:40-57).
 template <typename T>
-OLB_HD void pupil_launch(Ray<T>& r, T Px, T Py, const T* o0, const T* os, const T* t0, const T* ts, T inten) {
-  r.x = o_fma(os[0], Px, o0[0]);
-  r.y = o_fma(os[1], Py, o0[1]);
+OLB_HD void pupil_launch(Ray<T>& r, T Px, T Py, const T* o0, const T* os, const T* t0, const T* ts, T inten,
+                         T ofx = 0, T ofy = 0, T tfx = 0, T tfy = 0) {
+  // (ofx, ofy, tfx, tfy): per-ray field offsets of origin and target, 0 for a single-field launch
+  r.x = o_fma(os[0], Px, o0[0]) + ofx;
+  r.y = o_fma(os[1], Py, o0[1]) + ofy;
   r.z = o0[2];
-  T dx = o_fma(ts[0], Px, t0[0]) - r.x, dy = o_fma(ts[1], Py, t0[1]) - r.y, dz = t0[2] - r.z;
+  T dx = (o_fma(ts[0], Px, t0[0]) + tfx) - r.x, dy = (o_fma(ts[1], Py, t0[1]) + tfy) - r.y, dz = t0[2] - r.z;
   T mag = o_sqrt(o_fma(dx, dx, o_fma(dy, dy, dz * dz)));
   const bool zero = mag < (T)1e-9;
   T inv = o_rcp(zero ? (T)1 : mag);

@@ -78,6 +78,10 @@ struct TraceArgs {
   // launch state from pupil coordinates (OlbPupilLaunch) when px != nullptr
   const void* px; const void* py;
   double lo0[3], los[2], lt0[3], lts[2], linten;
+  // per-ray field coordinates (trace_generic): origin / target offsets lof * g(H), ltf * g(H)
+  const void* hx; const void* hy;
+  int32_t fmode; int32_t fpad;
+  double farg, lof[2], ltf[2];
   // fused moments epilogue (OLB_TF_MOMENTS)
   double* moments;
   double mcx, mcy;
@@ -210,8 +214,23 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<T, RPT, FEAT>::v)) trace_ker
         load_rays<T, RPT>((const T*)a.py, bin, valid, v);
         const T o0[3] = {(T)a.lo0[0], (T)a.lo0[1], (T)a.lo0[2]}, os[2] = {(T)a.los[0], (T)a.los[1]};
         const T t0[3] = {(T)a.lt0[0], (T)a.lt0[1], (T)a.lt0[2]}, ts[2] = {(T)a.lts[0], (T)a.lts[1]};
+        if (a.hx != nullptr) {
+          // field point per ray: angle fields move origin (and target) by tan(H * max_field), object heights by H
+          T hxv[RPT], hyv[RPT];
+          load_rays<T, RPT>((const T*)a.hx, bin, valid, hxv);
+          load_rays<T, RPT>((const T*)a.hy, bin, valid, hyv);
 #pragma unroll
-        for (int k = 0; k < RPT; ++k) pupil_launch<T>(r[k], pv[k], v[k], o0, os, t0, ts, (T)a.linten);
+          for (int k = 0; k < RPT; ++k) {
+            // fp64 tangent for both element types: a field angle feeds a lever arm of hundreds of mm
+            const double gx = a.fmode == 1 ? tan(a.farg * (double)hxv[k]) : (double)hxv[k];
+            const double gy = a.fmode == 1 ? tan(a.farg * (double)hyv[k]) : (double)hyv[k];
+            pupil_launch<T>(r[k], pv[k], v[k], o0, os, t0, ts, (T)a.linten, (T)(a.lof[0] * gx), (T)(a.lof[1] * gy),
+                            (T)(a.ltf[0] * gx), (T)(a.ltf[1] * gy));
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < RPT; ++k) pupil_launch<T>(r[k], pv[k], v[k], o0, os, t0, ts, (T)a.linten);
+        }
       } else {
       load_rays<T, RPT>((const T*)a.x, bin, valid, v);
 #pragma unroll
@@ -824,6 +843,13 @@ static int trace_impl(const OlbDeviceTable* wh, int32_t first, int32_t last, con
     for (int q = 0; q < 3; ++q) { a.lo0[q] = launch->origin0[q]; a.lt0[q] = launch->target0[q]; }
     for (int q = 0; q < 2; ++q) { a.los[q] = launch->origin_scale[q]; a.lts[q] = launch->target_scale[q]; }
     a.linten = launch->intensity;
+    if (launch->Hx || launch->Hy) {
+      if (!launch->Hx || !launch->Hy) return fail(OLB_ERR_INVALID_ARG, "launch.Hx and launch.Hy go together");
+      if (!aligned16(launch->Hx) || !aligned16(launch->Hy)) return fail(OLB_ERR_ALIGNMENT, "launch.Hx / Hy not 16-byte aligned");
+      if (launch->field_mode != 1 && launch->field_mode != 2) return fail(OLB_ERR_INVALID_ARG, "launch.field_mode must be 1 (angle) or 2 (object height)");
+      a.hx = launch->Hx; a.hy = launch->Hy; a.fmode = launch->field_mode; a.farg = launch->field_arg;
+      for (int q = 0; q < 2; ++q) { a.lof[q] = launch->origin_field[q]; a.ltf[q] = launch->target_field[q]; }
+    }
   }
   uint32_t features = wh->features;
   if (flags & OLB_TF_POLARIZED) features |= FEAT_POL;
@@ -1102,6 +1128,8 @@ static int trace_host_impl(const OlbDeviceTable* table, int32_t first, int32_t l
   OlbRays pupil_in{};
   if (launch) {   // slots 0/1 carry Px/Py instead of x/y; the rest of the launch state is generated on the device
     if (!launch->Px || !launch->Py) return fail(OLB_ERR_INVALID_ARG, "launch.Px / launch.Py is NULL");
+    if (launch->Hx || launch->Hy)
+      return fail(OLB_ERR_UNSUPPORTED, "per-ray field arrays (launch.Hx / Hy) are not built for the host-buffer entry points");
     pupil_in.x = const_cast<void*>(launch->Px); pupil_in.y = const_cast<void*>(launch->Py);
     pupil_in.w = h_out ? h_out->w : nullptr;
     h_in = &pupil_in;

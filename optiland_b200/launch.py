@@ -17,6 +17,14 @@ def _sqrt(v):
     return v.sqrt() if hasattr(v, "sqrt") else v ** 0.5
 
 
+def _tan(v):
+    if hasattr(v, "tan"):
+        return v.tan()
+    import numpy as np
+
+    return np.tan(v)
+
+
 def launch_infinite_angle(Px, Py, sc: dict):
     """Return x0, y0, z0, L, M, N for pupil coordinates (Px, Py) and launch scalars ``sc``."""
     EPL, EPD, offset = sc["EPL"], sc["EPD"], sc["offset"]
@@ -71,12 +79,45 @@ def pupil_affine(sc: dict) -> dict:
 
 def launch_from_affine(Px, Py, aff: dict):
     """x0, y0, z0, L, M, N from the affine form -- the arithmetic of the kernel's ``pupil_launch``
-    (olb_math.cuh), on numpy arrays or torch tensors."""
-    x0 = Px * aff["origin_scale"][0] + aff["origin0"][0]
-    y0 = Py * aff["origin_scale"][1] + aff["origin0"][1]
+    (olb_math.cuh), on numpy arrays or torch tensors (incl. the per-ray field offsets of pupil_affine_fields)."""
+    ofx = ofy = tfx = tfy = 0.0
+    if aff.get("fields") is not None:
+        Hx, Hy = aff["fields"]
+        if int(aff["field_mode"]) == 1:
+            gx, gy = _tan(Hx * aff["field_arg"]), _tan(Hy * aff["field_arg"])
+        else:
+            gx, gy = Hx, Hy
+        ofx, ofy = aff["origin_field"][0] * gx, aff["origin_field"][1] * gy
+        tfx, tfy = aff["target_field"][0] * gx, aff["target_field"][1] * gy
+    x0 = Px * aff["origin_scale"][0] + aff["origin0"][0] + ofx
+    y0 = Py * aff["origin_scale"][1] + aff["origin0"][1] + ofy
     z0 = Px * 0 + aff["origin0"][2]
-    dx = Px * aff["target_scale"][0] + aff["target0"][0] - x0
-    dy = Py * aff["target_scale"][1] + aff["target0"][1] - y0
+    dx = Px * aff["target_scale"][0] + aff["target0"][0] + tfx - x0
+    dy = Py * aff["target_scale"][1] + aff["target0"][1] + tfy - y0
     dz = aff["target0"][2] - z0
     mag = _sqrt(dx ** 2 + dy ** 2 + dz ** 2)
     return x0, y0, z0, dx / mag, dy / mag, dz / mag
+
+
+def pupil_affine_fields(sc: dict, Hx, Hy) -> dict:
+    """Per-ray field points (``RealRayTracer.trace_generic``, raytrace/real_ray_tracer.py:120-154): the affine
+    form of the H = 0 field plus the field-dependent offsets of origin and target (include/olb.h
+    ``OlbPupilLaunch.Hx``).  ``sc`` = ``pack.launch_scalars(optic, 0, 0)`` of an optic WITHOUT vignetting factors
+    (they would make the pupil scale field-dependent).  ``Hx``, ``Hy``: arrays of the kernel's element type."""
+    if sc["vx"] != 1.0 or sc["vy"] != 1.0:
+        raise ValueError("per-ray fields need an optic without vignetting factors")
+    base = pupil_affine({**sc, "Hx": 0.0, "Hy": 0.0} if int(sc.get("mode", 0)) == 0 else sc)
+    mode = int(sc.get("mode", 0))
+    aff = dict(base)
+    aff["fields"] = (Hx, Hy)
+    if mode == 0:                      # infinite object, angle field: origin slides by -tan(field) (offset + EPL)
+        k = -(sc["offset"] + sc["EPL"])
+        aff.update(field_mode=1, field_arg=math.radians(sc["max_field"]), origin_field=(k, k), target_field=(0.0, 0.0))
+    elif float(sc.get("field_kind", 2.0)) == 1.0:   # finite object, angle field (angle.py:49-58): x0 = -tan(field) (EPL - z0)
+        k = -(sc["EPL"] - sc["z0"])
+        aff.update(field_mode=1, field_arg=math.radians(sc["max_field"]), origin_field=(k, k),
+                   target_field=(k, k) if mode == 2 else (0.0, 0.0))
+    else:                              # object-height field (object_height.py:37-44): x0 = max_field * Hx
+        k = sc["max_field"]
+        aff.update(field_mode=2, field_arg=0.0, origin_field=(k, k), target_field=(k, k) if mode == 2 else (0.0, 0.0))
+    return aff

@@ -365,7 +365,8 @@ def launch_scalars(optic, Hx: float, Hy: float) -> dict:
     zero = be.array([0.0])
     x0, y0, z0 = fd.get_ray_origins(optic, float(Hx), float(Hy), zero, zero, vx, vy)
     sc = {"x0": _f(_arr(x0).reshape(-1)[0]), "y0": _f(_arr(y0).reshape(-1)[0]), "z0": _f(_arr(z0).reshape(-1)[0]),
-          "vx": vx, "vy": vy, "Hx": float(Hx), "Hy": float(Hy)}
+          "vx": vx, "vy": vy, "Hx": float(Hx), "Hy": float(Hy), "max_field": _f(optic.fields.max_field),
+          "field_kind": 1.0 if name == "AngleField" else 2.0}
     if optic.obj_space_telecentric:
         if name == "AngleField" or not optic.aperture.supports_telecentric:
             raise UnsupportedSurface("launch_scalars: the reference raises for this telecentric configuration")

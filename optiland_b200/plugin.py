@@ -122,13 +122,18 @@ class CudaEngine:
 
         return torch.is_tensor(t) and t.is_cuda and t.dtype in (torch.float32, torch.float64) and t.ndim == 1
 
-    def trace_pupil(self, table: T.SurfaceTable, Px, Py, affine: dict):
-        """Launch state generated in-kernel from the pupil samples (olb_trace_pupil_*).  Returns the record
-        dict; the final state is its last row."""
+    def trace_pupil(self, table: T.SurfaceTable, Px, Py, affine: dict, wavelength=None):
+        """Launch state generated in-kernel from the pupil samples (olb_trace_pupil_*; with ``affine["fields"]``
+        also from per-ray field points).  ``wavelength``: per-ray array for a multi-wavelength table.  Returns the
+        record dict; the final state is its last row."""
         from .trace import trace_pupil_device
 
         dt = self.device_table(table, Px.device)
-        _, rec = trace_pupil_device(dt, Px.detach().contiguous(), Py.detach().contiguous(), affine, 0, table.num_surfaces)
+        if affine.get("fields") is not None:
+            affine = dict(affine, fields=tuple(t.detach().contiguous() for t in affine["fields"]))
+        w = wavelength.detach().contiguous() if wavelength is not None else None
+        _, rec = trace_pupil_device(dt, Px.detach().contiguous(), Py.detach().contiguous(), affine, 0, table.num_surfaces,
+                                    wavelength=w)
         return rec
 
     def trace_wavefront(self, table: T.SurfaceTable, Px, Py, affine: dict, ref: dict) -> dict:
@@ -431,6 +436,75 @@ def install(engine=None, alias: str | None = None) -> None:
                 last_surface.material_post.propagation_model.propagate(rays, last_surface.thickness)
             return rays
 
+        def trace_optic_generic(self, tracer, Hx, Hy, Px, Py, wavelength):
+            """``RealRayTracer.trace_generic`` (raytrace/real_ray_tracer.py:120-154) for per-ray (Hx, Hy, Px, Py[, lambda])
+            arrays with the launch state generated on the device.  Needs an optic without vignetting factors (they
+            make the pupil scale field dependent), the paraxial aimer, no apodization / polarization.  Returns the
+            traced ``RealRays`` or None to decline."""
+            import numpy as _np
+            from optiland.rays import RealRays
+
+            from .launch import pupil_affine_fields
+            from .pack import launch_scalars
+
+            optic = tracer.optic
+            engine = _state["engine"]
+            if getattr(_tls, "in_reference", False) or _wants_grad(self, list(optic.surfaces.surfaces)):
+                return None
+            if optic.polarization != "ignore" or optic.apodization:
+                return None
+            if getattr(tracer, "ray_aiming_config", {}).get("mode", "paraxial") != "paraxial":
+                return None
+            try:
+                if _np.any(_np.asarray(be.to_numpy(optic.fields.vx)) != 0) or _np.any(_np.asarray(be.to_numpy(optic.fields.vy)) != 0):
+                    return None
+            except Exception:
+                return None
+            tracer._validate_normalized_coordinates(Hx, Hy, "field")
+            tracer._validate_normalized_coordinates(Px, Py, "pupil")
+            Hx, Hy, Px, Py = tracer._validate_array_size(Hx, Hy, Px, Py)
+            if not all(engine.accepts_tensor(t) for t in (Hx, Hy, Px, Py)) or len({t.shape for t in (Hx, Hy, Px, Py)}) != 1:
+                return None
+            if any(t.dtype != Px.dtype for t in (Hx, Hy)):
+                return None
+            n = Px.shape[0]
+            w = None
+            if be.is_array_like(wavelength) and be.size(wavelength) > 1:
+                w = be.to_tensor(wavelength, device=Px.device) if hasattr(be, "to_tensor") else wavelength
+                if not engine.accepts_tensor(w) or w.shape != Px.shape:
+                    return None
+                w = w.to(Px.dtype)
+                wls = _unique_wavelengths(w)
+                if wls is None:
+                    return None
+            else:
+                wls = _np.array([float(_np.asarray(be.to_numpy(be.atleast_1d(wavelength))).reshape(-1)[0])])
+            try:
+                obj_geom = getattr(optic.object_surface, "geometry", None)
+                if not bool(optic.object_surface.is_infinite) and type(obj_geom).__name__ != "Plane":
+                    return None          # a curved object surface makes z0 field dependent
+                sc = launch_scalars(optic, 0.0, 0.0)
+                table = pack_surface_group(optic.surfaces, wls)
+                aff = pupil_affine_fields(sc, Hx, Hy)
+            except (UnsupportedSurface, TypeError, ValueError):
+                return None
+            if any(s.coating == T.COAT_FRESNEL for s in table.surfaces):
+                return None
+            rec = engine.trace_pupil(table, Px, Py, aff, wavelength=w if len(wls) > 1 else None)
+            optic.surfaces.reset()
+            for row, surf in enumerate(optic.surfaces.surfaces):
+                for attr, key in _REC_ATTR:
+                    setattr(surf, attr, rec[key][row])
+            wl_arr = w if w is not None else be.ones_like(rec["x"][-1]) * float(wls[0])
+            rays = RealRays(rec["x"][-1], rec["y"][-1], rec["z"][-1], rec["L"][-1], rec["M"][-1], rec["N"][-1],
+                            rec["intensity"][-1], wl_arr)
+            rays.opd = rec["opd"][-1]
+            _set_pre_interaction_direction(rays, table, rec, 0, table.num_surfaces,
+                                           (rec["L"][0], rec["M"][0], rec["N"][0]))
+            last_surface = optic.surfaces[-1]   # tail of trace_generic (real_ray_tracer.py:145-152)
+            last_surface.material_post.propagation_model.propagate(rays, last_surface.thickness)
+            return rays
+
         def wavefront_chief_ray(self, strategy, field, wavelength):
             """``ChiefRayStrategy.compute_wavefront_data`` (wavefront/strategy.py:152-213) with steps 3-5 -- the
             full-grid trace, the path length to the reference sphere, the OPD in waves and the exit-pupil
@@ -538,6 +612,16 @@ def install(engine=None, alias: str | None = None) -> None:
                 return rays
         return orig_tracer_trace(self, Hx, Hy, wavelength, num_rays, distribution)
 
+    orig_tracer_generic = RealRayTracer.trace_generic
+
+    def tracer_generic(self, Hx, Hy, Px, Py, wavelength):
+        backend = registry.get(be.get_backend())
+        if hasattr(backend, "trace_optic_generic") and _state.get("fuse_launch", True):
+            rays = backend.trace_optic_generic(self, Hx, Hy, Px, Py, wavelength)
+            if rays is not None:
+                return rays
+        return orig_tracer_generic(self, Hx, Hy, Px, Py, wavelength)
+
     # f-3: the Huygens-Fresnel summation strategy of the torch backend (psf/huygens_fresnel_strategies.py:183-273)
     from optiland.psf.huygens_fresnel_strategies import TorchSummation
 
@@ -577,8 +661,9 @@ def install(engine=None, alias: str | None = None) -> None:
     SurfaceGroup.trace = group_trace
     Surface.trace = surface_trace
     RealRayTracer.trace = tracer_trace
+    RealRayTracer.trace_generic = tracer_generic
     _state.update(installed=True, orig_group_trace=orig_group_trace, orig_surface_trace=orig_surface_trace,
-                  orig_tracer_trace=orig_tracer_trace, orig_hf_compute=orig_hf_compute, orig_chief_compute=orig_chief_compute,
+                  orig_tracer_trace=orig_tracer_trace, orig_tracer_generic=orig_tracer_generic, orig_hf_compute=orig_hf_compute, orig_chief_compute=orig_chief_compute,
                   old_backend=old, alias=alias, fuse_launch=True, fuse_wavefront=True)
 
 
@@ -595,6 +680,7 @@ def uninstall() -> None:
     SurfaceGroup.trace = _state["orig_group_trace"]
     Surface.trace = _state["orig_surface_trace"]
     RealRayTracer.trace = _state["orig_tracer_trace"]
+    RealRayTracer.trace_generic = _state["orig_tracer_generic"]
     from optiland.psf.huygens_fresnel_strategies import TorchSummation
 
     TorchSummation.compute = _state["orig_hf_compute"]

@@ -217,6 +217,14 @@ def _c_launch(affine: dict, Px, Py):
     la.target0 = (C.c_double * 3)(*affine["target0"])
     la.target_scale = (C.c_double * 2)(*affine["target_scale"])
     la.intensity = float(affine.get("intensity", 1.0))
+    fields = affine.get("fields")
+    if fields is not None:      # per-ray field coordinates (Hx, Hy device arrays): launch.pupil_affine_fields
+        Hx, Hy = fields
+        la.Hx, la.Hy = Hx.data_ptr(), Hy.data_ptr()
+        la.field_mode = int(affine["field_mode"])
+        la.field_arg = float(affine.get("field_arg", 0.0))
+        la.origin_field = (C.c_double * 2)(*affine["origin_field"])
+        la.target_field = (C.c_double * 2)(*affine["target_field"])
     return la
 
 

@@ -390,6 +390,30 @@ def case_huygens():
           f"{os.path.getsize(path) / 1024:.0f} KiB")
 
 
+def case_generic_fields():
+    """trace_generic-shaped batches (raytrace/real_ray_tracer.py:120-154): per-ray field points (and wavelengths):
+    infinite-object angle fields (config 5's shape: several fields x several wavelengths in one call), an
+    object-height field on a finite object, and the telecentric lithography lens."""
+    from optiland.samples.lithography import UVProjectionLens
+
+    rng = np.random.default_rng(77)
+    n = 450
+    for name, lens, wls in (("generic_dgauss", DoubleGauss(), [0.4861, 0.5876, 0.6563]),
+                            ("generic_finite_height", finite_relay("object_height"), [0.5876]),
+                            ("generic_finite_angle", finite_relay("angle"), [0.5876]),
+                            ("generic_litho", UVProjectionLens(), [0.248])):
+        Px, Py = disk(n, seed=12)
+        Hx = np.round(rng.uniform(-0.6, 0.6, n), 3)
+        Hy = np.round(rng.uniform(-1.0, 1.0, n), 3)
+        keep = Hx**2 + Hy**2 <= 1.0
+        Hx, Hy = np.where(keep, Hx, 0.0), np.where(keep, Hy, 0.5)
+        wl = np.asarray(wls)[rng.integers(0, len(wls), n)]
+        rays = gen(lens, Hx, Hy, Px, Py, wl)
+        sc = launch_scalars(lens, 0.0, 0.0)
+        run_case(name, lens, rays, wls, extra={"Px": Px, "Py": Py, "Hx": Hx, "Hy": Hy,
+                                                **{"launch_" + k: v for k, v in sc.items()}})
+
+
 def case_forbes():
     """Forbes Q (slope-orthogonal) radial aspheres (geometries/forbes/geometry.py:187-366): a singlet with two
     forbes_qbfs surfaces (one with a conic base), rays reaching beyond the normalisation radius on the second
@@ -510,6 +534,7 @@ def main():
     case_more_geometries()
     case_huygens()
     case_finite_objects()
+    case_generic_fields()
     case_forbes()
     case_wavefront()
     case_autograd()
@@ -562,6 +587,9 @@ if __name__ == "__main__":
         case_more_geometries()
     elif len(sys.argv) > 1 and sys.argv[1] == "autograd":
         case_autograd()
+    elif len(sys.argv) > 1 and sys.argv[1] == "generic":
+        be.set_backend("numpy")
+        case_generic_fields()
     elif len(sys.argv) > 1 and sys.argv[1] == "forbes":
         be.set_backend("numpy")
         case_forbes()

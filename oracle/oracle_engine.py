@@ -41,21 +41,20 @@ class OracleEngine:
 
         return torch.is_tensor(t) and t.ndim == 1
 
-    def trace_pupil(self, table, Px, Py, affine):
+    def trace_pupil(self, table, Px, Py, affine, wavelength=None):
         import torch
 
         from oracle import trace_oracle as O
+        from optiland_b200.launch import launch_from_affine
 
         self.calls.append(("pupil", table.num_surfaces, int(Px.numel())))
         px, py = Px.detach().double().numpy(), Py.detach().double().numpy()
-        x0 = affine["origin0"][0] + affine["origin_scale"][0] * px
-        y0 = affine["origin0"][1] + affine["origin_scale"][1] * py
-        d = np.stack([affine["target0"][0] + affine["target_scale"][0] * px - x0,
-                      affine["target0"][1] + affine["target_scale"][1] * py - y0,
-                      np.full_like(px, affine["target0"][2] - affine["origin0"][2])])
-        d = d / np.linalg.norm(d, axis=0)
-        inp = dict(x=x0, y=y0, z=np.full_like(px, affine["origin0"][2]), L=d[0], M=d[1], N=d[2],
-                   i=np.full_like(px, affine.get("intensity", 1.0)), w=np.full_like(px, table.wavelengths[0]))
+        aff = dict(affine)
+        if aff.get("fields") is not None:
+            aff["fields"] = tuple(t.detach().double().numpy() for t in aff["fields"])
+        x, y, z, L, M, N = launch_from_affine(px, py, aff)
+        w = wavelength.detach().double().numpy() if wavelength is not None else np.full_like(px, table.wavelengths[0])
+        inp = dict(x=x, y=y, z=z, L=L, M=M, N=N, i=np.full_like(px, affine.get("intensity", 1.0)), w=w)
         _, rec, status = O.trace(table, inp)
         return {k: torch.from_numpy(v).to(Px.dtype) for k, v in rec.items()}
 

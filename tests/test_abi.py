@@ -113,3 +113,21 @@ def test_every_launch_mode_reproduces_the_reference_ray_generator(name):
         np.testing.assert_allclose(g, c.rays[key], rtol=0, atol=1e-12 * c.scale, err_msg=key)
     if int(sc.get("mode", 0)) != 0:
         assert aff["origin_scale"] == (0.0, 0.0)      # every ray starts at the object point
+
+
+GENERIC_CASES = ["generic_dgauss", "generic_finite_height", "generic_finite_angle", "generic_litho"]
+
+
+@pytest.mark.parametrize("name", GENERIC_CASES)
+def test_per_ray_field_launch_reproduces_trace_generic_rays(name):
+    """trace_generic-shaped batches: with per-ray field arrays the launch form (launch.pupil_affine_fields, scalars
+    of the H = 0 field) equals the rays RayGenerator + ParaxialRayAimer produced for (Hx, Hy, Px, Py) arrays."""
+    from optiland_b200.launch import launch_from_affine, pupil_affine_fields
+    from tests._util import Case
+
+    c = Case(name)
+    sc = {k[9:]: float(c.z[k]) for k in c.z.files if k.startswith("x_launch_")}
+    aff = pupil_affine_fields(sc, c.extra("Hx"), c.extra("Hy"))
+    got = launch_from_affine(c.extra("Px"), c.extra("Py"), aff)
+    for g, key in zip(got, "xyzLMN"):
+        np.testing.assert_allclose(g, c.rays[key], rtol=0, atol=1e-12 * c.scale, err_msg=key)

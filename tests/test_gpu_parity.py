@@ -465,6 +465,27 @@ def test_pupil_launch_mode_matches_reference(name, dtype):
         assert np.array_equal(h_out[k].numpy(), getattr(rays, k).cpu().numpy(), equal_nan=True), k
 
 
+@pytest.mark.parametrize("name", ["generic_dgauss", "generic_finite_height", "generic_finite_angle", "generic_litho"])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_per_ray_field_launch_matches_reference_trace_generic(name, dtype):
+    """f-1 for trace_generic-shaped batches: launch state generated in-kernel from per-ray (Hx, Hy, Px, Py) [and a
+    per-ray wavelength] == the reference's RayGenerator + SurfaceGroup.trace records."""
+    from optiland_b200.launch import pupil_affine_fields
+    from optiland_b200.trace import DeviceTable, trace_pupil_device
+
+    c = Case(name)
+    sc = {k[9:]: float(c.z[k]) for k in c.z.files if k.startswith("x_launch_")}
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to("cuda", dtype)  # noqa: E731
+    aff = pupil_affine_fields(sc, dev(c.extra("Hx")), dev(c.extra("Hy")))
+    dt = DeviceTable(c.table)
+    w = dev(c.rays["w"]) if c.table.n_wl > 1 else None
+    rays, rec = trace_pupil_device(dt, dev(c.extra("Px")), dev(c.extra("Py")), aff, 0, c.table.num_surfaces, wavelength=w)
+    f64 = dtype == torch.float64
+    tol = 1e-11 * c.scale if f64 else 2e-6 * c.scale
+    for k in REC:
+        assert max_abs_err(_np(rec[k]), c.rec[k]) <= (tol if k not in ("L", "M", "N") or f64 else 5e-6), k
+
+
 def test_c_abi_error_codes_on_device_calls():
     """Bad arguments are reported through return codes + olb_last_error, never by crashing."""
     import ctypes as C

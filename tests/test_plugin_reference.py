@@ -106,6 +106,45 @@ def test_optic_trace_fused_launch_for_finite_and_telecentric_objects(plugin):
             np.testing.assert_allclose(be.to_numpy(getattr(rays, k)), v, rtol=0, atol=1e-11 * scale, err_msg=k)
 
 
+def test_trace_generic_with_per_ray_fields_and_wavelengths(plugin):
+    """trace_generic (config 5's call shape: per-ray Hx, Hy, Px, Py and wavelength arrays) goes through the fused
+    launch with per-ray field points and reproduces the NumPy reference; a system with vignetting factors declines."""
+    P, eng, be = plugin
+    from optiland.samples.objectives import DoubleGauss
+    from optiland.samples.lithography import UVProjectionLens
+
+    from oracle.make_golden import finite_relay
+
+    rng = np.random.default_rng(3)
+    n = 60
+    Px, Py = rng.uniform(-0.7, 0.7, n), rng.uniform(-0.7, 0.7, n)
+    Hx, Hy = rng.uniform(-0.5, 0.5, n), rng.uniform(-0.8, 0.8, n)
+    for make, wls, S in ((DoubleGauss, [0.4861, 0.5876, 0.6563], 13), (lambda: finite_relay("object_height"), [0.5876], 5),
+                         (UVProjectionLens, [0.248], 44)):
+        wl = np.asarray(wls)[rng.integers(0, len(wls), n)]
+
+        def trace(lens):
+            a = lambda v: be.array(v)  # noqa: E731
+            return lens.trace_generic(a(Hx), a(Hy), a(Px), a(Py), a(wl) if len(wls) > 1 else float(wls[0]))
+
+        ref_rec, ref_fin = _numpy_reference(make, trace)
+        lens = make()
+        n0 = len(eng.calls)
+        rays = trace(lens)
+        assert ("pupil", S, n) in [c[:3] for c in eng.calls[n0:]], (eng.calls[n0:], P.stats())
+        scale = max(1.0, float(np.nanmax(np.abs(ref_rec["z"]))))
+        for k, v in ref_rec.items():
+            np.testing.assert_allclose(be.to_numpy(getattr(lens.surfaces, k)), v, rtol=0, atol=1e-11 * scale, err_msg=k)
+        for k, v in ref_fin.items():
+            np.testing.assert_allclose(be.to_numpy(getattr(rays, k)), v, rtol=0, atol=1e-11 * scale, err_msg=k)
+    # vignetting factors make the pupil scale field dependent: the reference's own path must run
+    lens = DoubleGauss()
+    lens.fields.fields[1].vy = 0.1
+    n0 = len(eng.calls)
+    lens.trace_generic(be.array(Hx), be.array(Hy), be.array(Px), be.array(Py), 0.5876)
+    assert all(c[0] != "pupil" for c in eng.calls[n0:])
+
+
 def test_wavefront_analysis_uses_the_fused_epilogue(plugin):
     """f-2: Wavefront(strategy='chief_ray') under the plugin == the NumPy reference, and the full-grid trace
     went through the wavefront capability (5 values per ray, no records)."""
