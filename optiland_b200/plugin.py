@@ -438,9 +438,8 @@ def install(engine=None, alias: str | None = None) -> None:
 
         def trace_optic_generic(self, tracer, Hx, Hy, Px, Py, wavelength):
             """``RealRayTracer.trace_generic`` (raytrace/real_ray_tracer.py:120-154) for per-ray (Hx, Hy, Px, Py[, lambda])
-            arrays with the launch state generated on the device.  Needs an optic without vignetting factors (they
-            make the pupil scale field dependent), the paraxial aimer, no apodization / polarization.  Returns the
-            traced ``RealRays`` or None to decline."""
+            arrays with the launch state generated on the device.  Needs the paraxial aimer and no apodization /
+            polarization.  Returns the traced ``RealRays`` or None to decline."""
             import numpy as _np
             from optiland.rays import RealRays
 
@@ -456,12 +455,19 @@ def install(engine=None, alias: str | None = None) -> None:
             if getattr(tracer, "ray_aiming_config", {}).get("mode", "paraxial") != "paraxial":
                 return None
             try:
-                if _np.any(_np.asarray(be.to_numpy(optic.fields.vx)) != 0) or _np.any(_np.asarray(be.to_numpy(optic.fields.vy)) != 0):
-                    return None
+                has_vig = bool(_np.any(_np.asarray(be.to_numpy(optic.fields.vx)) != 0)
+                               or _np.any(_np.asarray(be.to_numpy(optic.fields.vy)) != 0))
             except Exception:
                 return None
             tracer._validate_normalized_coordinates(Hx, Hy, "field")
             tracer._validate_normalized_coordinates(Px, Py, "pupil")
+            if has_vig:
+                # vignetting factors (nearest-neighbour over the defined fields, fields/field_group.py:93-122) scale
+                # the pupil point TWICE on this path: once in trace_generic (real_ray_tracer.py:134-137) and once
+                # more in the aimer (ray_aiming/paraxial.py:72-96) -- reproduced, as a per-ray pre-scale of (Px, Py)
+                vxf, vyf = optic.fields.get_vig_factor(Hx, Hy)
+                Px = Px * (1 - vxf) * (1 - vxf)
+                Py = Py * (1 - vyf) * (1 - vyf)
             Hx, Hy, Px, Py = tracer._validate_array_size(Hx, Hy, Px, Py)
             if not all(engine.accepts_tensor(t) for t in (Hx, Hy, Px, Py)) or len({t.shape for t in (Hx, Hy, Px, Py)}) != 1:
                 return None
@@ -484,6 +490,7 @@ def install(engine=None, alias: str | None = None) -> None:
                 if not bool(optic.object_surface.is_infinite) and type(obj_geom).__name__ != "Plane":
                     return None          # a curved object surface makes z0 field dependent
                 sc = launch_scalars(optic, 0.0, 0.0)
+                sc["vx"] = sc["vy"] = 1.0            # (the factors are already in Px, Py)
                 table = pack_surface_group(optic.surfaces, wls)
                 aff = pupil_affine_fields(sc, Hx, Hy)
             except (UnsupportedSurface, TypeError, ValueError):

@@ -137,12 +137,25 @@ def test_trace_generic_with_per_ray_fields_and_wavelengths(plugin):
             np.testing.assert_allclose(be.to_numpy(getattr(lens.surfaces, k)), v, rtol=0, atol=1e-11 * scale, err_msg=k)
         for k, v in ref_fin.items():
             np.testing.assert_allclose(be.to_numpy(getattr(rays, k)), v, rtol=0, atol=1e-11 * scale, err_msg=k)
-    # vignetting factors make the pupil scale field dependent: the reference's own path must run
-    lens = DoubleGauss()
-    lens.fields.fields[1].vy = 0.1
+    # vignetting factors (nearest-neighbour per ray, applied twice on this path by the reference): reproduced
+    def make_vig():
+        lens = DoubleGauss()
+        lens.fields.fields[1].vy = 0.1
+        lens.fields.fields[2].vx = 0.05
+        return lens
+
+    def trace_v(lens):
+        a = lambda v: be.array(v)  # noqa: E731
+        return lens.trace_generic(a(Hx), a(Hy), a(Px), a(Py), 0.5876)
+
+    ref_rec, ref_fin = _numpy_reference(make_vig, trace_v)
+    lens = make_vig()
     n0 = len(eng.calls)
-    lens.trace_generic(be.array(Hx), be.array(Hy), be.array(Px), be.array(Py), 0.5876)
-    assert all(c[0] != "pupil" for c in eng.calls[n0:])
+    rays = trace_v(lens)
+    assert ("pupil", 13, n) in [c[:3] for c in eng.calls[n0:]]
+    for k, v in ref_rec.items():
+        np.testing.assert_allclose(be.to_numpy(getattr(lens.surfaces, k)), v, rtol=0, atol=1e-10, err_msg=k)
+    assert float(np.max(np.abs(ref_rec["x"][1] - np.asarray(_numpy_reference(DoubleGauss, trace_v)[0]["x"][1])))) > 1e-3
 
 
 def test_wavefront_analysis_uses_the_fused_epilogue(plugin):
