@@ -54,6 +54,12 @@ def stats(reset: bool = False) -> dict:
     return out
 
 
+def _dev_array(t):
+    """Detached, contiguous and 16-byte aligned (a view into a larger tensor may start anywhere)."""
+    t = t.detach().contiguous()
+    return t.clone() if t.data_ptr() % 16 else t
+
+
 class CudaEngine:
     """Runs a packed table on the GPU through libolb (``optiland_b200.trace``)."""
 
@@ -130,10 +136,9 @@ class CudaEngine:
 
         dt = self.device_table(table, Px.device)
         if affine.get("fields") is not None:
-            affine = dict(affine, fields=tuple(t.detach().contiguous() for t in affine["fields"]))
-        w = wavelength.detach().contiguous() if wavelength is not None else None
-        _, rec = trace_pupil_device(dt, Px.detach().contiguous(), Py.detach().contiguous(), affine, 0, table.num_surfaces,
-                                    wavelength=w)
+            affine = dict(affine, fields=tuple(_dev_array(t) for t in affine["fields"]))
+        w = _dev_array(wavelength) if wavelength is not None else None
+        _, rec = trace_pupil_device(dt, _dev_array(Px), _dev_array(Py), affine, 0, table.num_surfaces, wavelength=w)
         return rec
 
     def trace_wavefront(self, table: T.SurfaceTable, Px, Py, affine: dict, ref: dict) -> dict:
@@ -142,7 +147,7 @@ class CudaEngine:
         from .trace import trace_wavefront_device
 
         dt = self.device_table(table, Px.device)
-        return trace_wavefront_device(dt, Px.detach().contiguous(), Py.detach().contiguous(), affine, ref)
+        return trace_wavefront_device(dt, _dev_array(Px), _dev_array(Py), affine, ref)
 
     def huygens_psf(self, image_x, image_y, image_z, pupil_x, pupil_y, pupil_z, pupil_amp, pupil_opd, wavelength, Rp):
         """Huygens-Fresnel summation on the GPU (olb_huygens_psf_f64); None to decline (CPU tensors)."""
