@@ -91,3 +91,69 @@ def test_random_systems_host_math_vs_oracle(hc, seed):
     if fin.sum() > n // 2:
         d = np.abs(rec32["x"][-1][fin] - orec["x"][-1][fin])
         assert np.percentile(d, 90) <= 2e-4 * scale, (seed, float(np.percentile(d, 90)))
+
+
+def random_freeform_system(rng):
+    """3-5 surfaces drawn from the polynomial-family / biconic / toroidal / Forbes / Zernike kinds with random
+    parameters (Zernike term tables are taken from the reference-generated fixtures and rescaled term by term)."""
+    from tests._util import Case
+
+    zspec = [s for s in Case(str(rng.choice(["zernike_fringe", "zernike_noll", "zernike_standard"]))).table.surfaces
+             if s.kind == T.GEOM_ZERNIKE][0]
+    specs = [T.SurfaceSpec(kind=T.GEOM_NOOP)]
+    z = 0.0
+    n_prev = 1.0
+    n_surf = int(rng.integers(3, 6))
+    for s in range(1, n_surf + 1):
+        z += rng.uniform(3.0, 9.0)
+        last = s == n_surf
+        n_next = n_prev if last else float(rng.choice([1.0, 1.5, 1.7]))
+        kind = int(rng.choice([T.GEOM_CHEBYSHEV, T.GEOM_BICONIC, T.GEOM_TOROIDAL, T.GEOM_FORBES_QBFS, T.GEOM_ZERNIKE,
+                               T.GEOM_POLYNOMIAL]))
+        sp = dict(kind=kind, t=np.array([rng.normal(0, 0.1), rng.normal(0, 0.1), z]), n1=[n_prev], n2=[n_next],
+                  radius=float(rng.choice([-1, 1]) * rng.uniform(40, 150)), conic=float(rng.uniform(-0.6, 0.4)),
+                  tol=1e-12, max_iter=60)
+        if rng.random() < 0.3:
+            sp["R"] = T.rotation_matrix(*rng.normal(0, 0.02, 3)) + 0.0
+        if kind == T.GEOM_CHEBYSHEV:
+            sp.update(coefficients=rng.normal(0, 3e-4, (3, 4)), norm_radius=float(rng.uniform(12, 16)), norm_y=float(rng.uniform(12, 16)))
+            sp["coefficients"][0, 0] = 0.0
+        elif kind == T.GEOM_BICONIC:
+            sp.update(radius_y=float(rng.choice([-1, 1]) * rng.uniform(40, 150)), conic_y=float(rng.uniform(-1.2, 0.4)))
+        elif kind == T.GEOM_TOROIDAL:
+            sp.update(conic=0.0, radius_y=float(rng.choice([-1, 1]) * rng.uniform(60, 200)), conic_y=float(rng.uniform(-0.6, 0.4)),
+                      coefficients=rng.normal(0, 1, 2) * np.array([1e-5, 1e-7]))
+        elif kind == T.GEOM_FORBES_QBFS:
+            sp.update(coefficients=rng.normal(0, 0.02, int(rng.integers(1, 6))), norm_radius=float(rng.uniform(7, 14)))
+        elif kind == T.GEOM_ZERNIKE:
+            terms = zspec.coefficients.reshape(-1, 4).copy()
+            terms[:, 2:] *= rng.uniform(0.2, 1.5, (terms.shape[0], 1))
+            sp.update(coefficients=terms, norm_radius=float(rng.uniform(12, 16)))
+        else:
+            C = rng.normal(0, 1e-4, (4, 3))
+            C[0, 0] = 0.0
+            sp.update(coefficients=C)
+        specs.append(T.SurfaceSpec(**sp))
+        n_prev = n_next
+    return T.SurfaceTable(specs, [0.55])
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_freeform_systems_host_math_vs_oracle(hc, seed):
+    rng = np.random.default_rng(3000 + seed)
+    table = random_freeform_system(rng)
+    n = 128
+    x, y = rng.uniform(-4, 4, n), rng.uniform(-4, 4, n)
+    L, M = rng.normal(0, 0.03, n), rng.normal(0, 0.03, n)
+    rays = dict(x=x, y=y, z=np.full(n, -3.0), L=L, M=M, N=np.sqrt(1 - L**2 - M**2), i=np.ones(n), w=np.full(n, 0.55))
+    _, orec, ost = O.trace(table, rays)
+    assert ost == 0
+    out, rec, st = run_hostcheck(hc, table, rays, np.float64)[:3]
+    assert st == 0
+    scale = max(1.0, float(np.nanmax(np.abs(np.where(np.isfinite(orec["z"]), orec["z"], 0)))))
+    for k in REC:
+        a, b = rec[k], orec[k]
+        assert np.array_equal(np.isnan(a), np.isnan(b)), (seed, k, "NaN pattern")
+        m = np.isfinite(b)
+        # Newton: per-ray convergence + one polishing step vs the reference's global stop at tol = 1e-12
+        assert np.max(np.abs(a[m] - b[m])) <= 1e-11 * scale + 1e-10, (seed, k, float(np.max(np.abs(a[m] - b[m]))))

@@ -101,3 +101,28 @@ def test_random_systems_backward_kernel_vs_finite_differences(seed):
             assert g[s_, q].item() == pytest.approx(fd, rel=5e-4, abs=2e-6 * gmax), (seed, s_, q, g[s_, q].item(), fd)
             checked += 1
     assert checked >= 6
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_freeform_systems_kernel_vs_oracle(seed):
+    """Random Chebyshev / biconic / toroidal / Forbes / Zernike / polynomial systems through the kernel."""
+    from oracle import trace_oracle as O
+    from optiland_b200.trace import RealRays, SurfaceGroup
+    from tests.test_fuzz_hostcheck import random_freeform_system
+
+    rng = np.random.default_rng(3000 + seed)
+    table = random_freeform_system(rng)
+    n = 777
+    x, y = rng.uniform(-4, 4, n), rng.uniform(-4, 4, n)
+    L, M = rng.normal(0, 0.03, n), rng.normal(0, 0.03, n)
+    N = np.sqrt(1 - L**2 - M**2)
+    rays = dict(x=x, y=y, z=np.full(n, -3.0), L=L, M=M, N=N, i=np.ones(n), w=np.full(n, 0.55))
+    _, orec, _ = O.trace(table, rays)
+    scale = max(1.0, float(np.nanmax(np.abs(np.where(np.isfinite(orec["z"]), orec["z"], 0)))))
+    sg = SurfaceGroup(table)
+    sg.trace(RealRays(x, y, rays["z"], L, M, N, rays["i"], rays["w"], dtype=torch.float64))
+    for k in REC:
+        a, b = getattr(sg, k).cpu().numpy(), orec[k]
+        assert np.array_equal(np.isnan(a), np.isnan(b)), (seed, k)
+        m = np.isfinite(b)
+        assert np.max(np.abs(a[m] - b[m])) <= 1e-11 * scale + 1e-10, (seed, k, float(np.max(np.abs(a[m] - b[m]))))
