@@ -266,6 +266,48 @@ def case_polarized():
                     "state": np.array([1.0 / np.sqrt(1.25), 0.5 / np.sqrt(1.25), 0.0, 0.3])})
 
 
+def tilted_fold_lens(fresnel=False):
+    lens = _optic.Optic()
+    lens.surfaces.add(index=0, radius=be.inf, thickness=be.inf)
+    lens.surfaces.add(index=1, radius=50.0, thickness=5.0, material="N-BK7", is_stop=True,
+                      dx=0.3, dy=-0.2, rx=0.02, ry=-0.015)
+    lens.surfaces.add(index=2, radius=-80.0, thickness=30.0, rz=0.4, rx=-0.01, conic=-0.8)
+    lens.surfaces.add(index=3, radius=be.inf, thickness=-25.0, material="mirror", rx=np.pi / 4)
+    lens.surfaces.add(index=4, radius=be.inf, thickness=0.0, rx=np.pi / 2, dy=0.5,
+                      aperture=pa.RectangularAperture(-3.0, 3.5, -2.0, 4.0))
+    lens.set_aperture(aperture_type="EPD", value=10.0)
+    lens.fields.set_type(field_type="angle")
+    lens.fields.add(y=0)
+    lens.fields.add(y=3)
+    lens.wavelengths.add(value=0.6, is_primary=True)
+    if fresnel:
+        lens.surfaces.set_fresnel_coatings()
+        lens.set_polarization(PolarizationState(is_polarized=True, Ex=0.6, Ey=0.8, phase_x=0.2, phase_y=-0.4))
+    return lens
+
+
+def case_polarized_tilted():
+    """Polarization through tilted / decentered surfaces and a fold mirror with Fresnel coatings: pins the
+    reflect branch of the Jones matrices (jones.py:71-117) and the reference's local-frame P update across
+    rotated poses."""
+    import copy
+
+    lens = tilted_fold_lens(fresnel=True)
+    Px, Py = disk(300, seed=14)
+    rays = gen(lens, 0.0, 1.0, Px, Py, 0.6)
+    assert type(rays).__name__ == "PolarizedRays"
+    i0 = np.array(rays._i0)
+    k0 = np.stack([np.array(rays._L0), np.array(rays._M0), np.array(rays._N0)])
+    probe = copy.deepcopy(rays)
+    lens2 = tilted_fold_lens(fresnel=True)
+    lens2.surfaces.trace(probe)
+    probe.update_intensity(lens2.polarization_state)
+    n = np.sqrt(0.6**2 + 0.8**2)
+    run_case("tilted_fold_polarized", lens, rays, [0.6], polarized=True,
+             extra={"i0": i0, "k0": k0, "final_intensity": np.array(probe.i),
+                    "state": np.array([0.6 / n, 0.8 / n, 0.2, -0.4])})
+
+
 def case_tilted():
     """Decentered / tilted surfaces incl. a fold mirror (rotated poses, reflect)."""
     lens = _optic.Optic()
@@ -529,6 +571,7 @@ def main():
     case_hubble()
     case_zernike()
     case_polarized()
+    case_polarized_tilted()
     case_tilted()
     case_misc()
     case_more_geometries()
@@ -587,6 +630,9 @@ if __name__ == "__main__":
         case_more_geometries()
     elif len(sys.argv) > 1 and sys.argv[1] == "autograd":
         case_autograd()
+    elif len(sys.argv) > 1 and sys.argv[1] == "poltilt":
+        be.set_backend("numpy")
+        case_polarized_tilted()
     elif len(sys.argv) > 1 and sys.argv[1] == "generic":
         be.set_backend("numpy")
         case_generic_fields()

@@ -194,7 +194,7 @@ def test_host_buffer_path_matches_device_path():
         assert np.array_equal(a, b, equal_nan=True), k
 
 
-@pytest.mark.parametrize("name", ["zernike_polarized_c5", "cooke_polarized"])
+@pytest.mark.parametrize("name", ["zernike_polarized_c5", "cooke_polarized", "tilted_fold_polarized"])
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
 def test_polarized_trace_vs_reference_golden(name, dtype):
     """Config 5: P-matrix propagation + Fresnel coatings (+ Zernike surface, 3 wavelengths) and the

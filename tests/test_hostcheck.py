@@ -124,7 +124,7 @@ def test_degenerate_conic_roots(hc, dtype):
         assert max_abs_err(rec[k], orec[k]) <= tol, (k, max_abs_err(rec[k], orec[k]))
 
 
-@pytest.mark.parametrize("name", ["zernike_polarized_c5", "cooke_polarized"])
+@pytest.mark.parametrize("name", ["zernike_polarized_c5", "cooke_polarized", "tilted_fold_polarized"])
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 def test_device_math_polarized_vs_reference(hc, name, dtype):
     """P-matrix update (PolarizedRays.update) + Fresnel Jones matrices vs. the reference."""
