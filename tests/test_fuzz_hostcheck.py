@@ -198,3 +198,70 @@ def test_random_polarized_systems_host_math_vs_oracle(hc, seed):
     assert fin.sum() > n // 2
     assert np.array_equal(np.isfinite(out["p"]).all(axis=(1, 2)), fin)
     assert np.max(np.abs(out["p"][fin] - oout["p"][fin])) <= 1e-10, (seed, float(np.max(np.abs(out["p"][fin] - oout["p"][fin]))))
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_systems_adjoint_vs_finite_differences(hc, seed):
+    """The adjoint (olb_math.cuh::surface_backward on the host) on random plane / conic / even- and odd-asphere
+    systems with tilts, decenters, mirrors, aperture trees, simple coatings and absorbing media: launch-state and
+    parameter gradients of a random linear functional of ALL records against central differences of the oracle."""
+    import dataclasses
+
+    from oracle.hostcheck_api import run_backward
+
+    rng = np.random.default_rng(9000 + seed)
+    full = random_system(rng, int(rng.integers(4, 8)))
+    specs = []
+    for s in full.surfaces:
+        ch = {k: getattr(s, k)[:1].copy() for k in ("n1", "n2", "k1")}
+        if s.kind == T.GEOM_POLYNOMIAL:
+            ch.update(kind=T.GEOM_STANDARD, coefficients=np.zeros(0))
+        if s.kind in (T.GEOM_EVEN_ASPHERE, T.GEOM_ODD_ASPHERE):
+            ch["tol"] = 1e-14
+        specs.append(dataclasses.replace(s, **ch))
+    table = T.SurfaceTable(specs, full.wavelengths[:1])
+    n = 40
+    r = 0.8 + 2.5 * np.sqrt(rng.random(n))            # away from the cone tip of odd aspheres
+    th = 2 * np.pi * rng.random(n)
+    L, M = rng.normal(0, 0.03, n), rng.normal(0, 0.03, n)
+    rays = dict(x=r * np.cos(th), y=r * np.sin(th), z=np.full(n, -5.0), L=L, M=M, N=np.sqrt(1 - L**2 - M**2),
+                i=np.ones(n), w=np.full(n, table.wavelengths[0]))
+    S = table.num_surfaces
+    _, rec, _ = O.trace(table, rays)
+    live = np.isfinite(rec["x"]).all(axis=0) & (rec["intensity"] > 0).all(axis=0)   # smooth region only
+    if live.sum() < 8:
+        pytest.skip("random system clips almost every ray")
+    rays = {k: v[live] for k, v in rays.items()}
+    n = int(live.sum())
+    weights = {k: rng.normal(size=(S, n)) for k in REC}
+    _, rec, _ = O.trace(table, rays)
+    gin, gpar = run_backward(hc, table, rays, rec, weights)
+
+    def loss(tab, rr):
+        _, rc, _ = O.trace(tab, rr)
+        return sum(float(np.sum(weights[k] * rc[k])) for k in REC)
+
+    dirs = {k: rng.normal(size=n) for k in ("x", "y", "L", "M")}
+    h = 1e-7
+    up = {k: (v + h * dirs[k] if k in dirs else v) for k, v in rays.items()}
+    dn = {k: (v - h * dirs[k] if k in dirs else v) for k, v in rays.items()}
+    fd_dir = (loss(table, up) - loss(table, dn)) / (2 * h)
+    an_dir = sum(float(np.sum(gin[k] * dirs[k])) for k in dirs)
+    assert an_dir == pytest.approx(fd_dir, rel=2e-4, abs=1e-7 * (abs(fd_dir) + 1)), (seed, an_dir, fd_dir)
+    gmax = float(np.abs(gpar).max())
+    checked = 0
+    for s_, spec in enumerate(table.surfaces):
+        if spec.kind == T.GEOM_NOOP:
+            continue
+        tz = spec.t.copy(); tz[2] += 1e-6
+        tzm = spec.t.copy(); tzm[2] -= 1e-6
+        fd = (loss(table.replace_surface(s_, t=tz), rays) - loss(table.replace_surface(s_, t=tzm), rays)) / 2e-6
+        assert gpar[s_, 2] == pytest.approx(fd, rel=5e-4, abs=2e-6 * gmax), (seed, s_, "tz", gpar[s_, 2], fd)
+        checked += 1
+        if spec.kind != T.GEOM_PLANE:
+            hk = 1e-5
+            fd = (loss(table.replace_surface(s_, conic=spec.conic + hk), rays)
+                  - loss(table.replace_surface(s_, conic=spec.conic - hk), rays)) / (2 * hk)
+            assert gpar[s_, 4] == pytest.approx(fd, rel=5e-4, abs=2e-6 * gmax), (seed, s_, "conic", gpar[s_, 4], fd)
+            checked += 1
+    assert checked >= 3
