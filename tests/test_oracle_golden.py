@@ -113,3 +113,32 @@ def test_known_answers_reflect():
     np.testing.assert_allclose([out["L"][0], out["M"][0], out["N"][0]], [L, M, -N], rtol=1e-15)
     np.testing.assert_allclose(out["z"], [0.0], atol=1e-16)
     np.testing.assert_allclose(out["opd"], [2.0 / N], rtol=1e-15)
+
+
+def test_known_answers_p_matrix_update():
+    """/root/reference/tests/test_rays.py:599-640 (PolarizedRays.update): identity Jones matrix with k0 == k1, with
+    k0 tilted 0.1 in y against k1 = +z, and the jones=None form."""
+    eye = np.eye(3)[None].astype(complex)
+    one = np.array
+    P = O.polarized_update(eye.copy(), one([0.0]), one([0.0]), one([1.0]), one([0.0]), one([0.0]), one([1.0]), eye.copy())
+    np.testing.assert_allclose(P, eye, atol=1e-15)
+    n0 = np.sqrt(1 - 0.1**2)
+    want = np.array([[[1.0, 0.0, 0.0], [0.0, 0.99498744, -0.1], [0.0, 0.1, 0.99498744]]])
+    P2 = O.polarized_update(P.copy(), one([0.0]), one([0.1]), one([n0]), one([0.0]), one([0.0]), one([1.0]), eye.copy())
+    np.testing.assert_allclose(P2.real, want, atol=1e-8)
+    np.testing.assert_allclose(P2.imag, 0, atol=1e-15)
+    P3 = O.polarized_update(P2.copy(), one([0.0]), one([0.0]), one([1.0]), one([0.0]), one([0.0]), one([1.0]), None)
+    np.testing.assert_allclose(P3.real, want, atol=1e-8)
+
+
+def test_known_answers_fresnel_jones():
+    """/root/reference/tests/test_jones.py:37-62 (JonesFresnel.calculate_matrix, n1 = 1.0, n2 = 1.5, aoi = 0.2)."""
+    aoi = np.array([0.2])
+    J = O.fresnel_jones(aoi, np.array([1.0]), np.array([1.5]), True, 1)
+    np.testing.assert_allclose(J[0, 0, 0].real, -0.20541108217641596, rtol=1e-12)
+    np.testing.assert_allclose(J[0, 1, 1].real, -0.19457669033430527, rtol=1e-12)
+    np.testing.assert_allclose(J[0, 2, 2].real, -1.0)
+    J = O.fresnel_jones(aoi, np.array([1.0]), np.array([1.5]), False, 1)
+    np.testing.assert_allclose(J[0, 0, 0].real, 0.7945889178235841, rtol=1e-12)
+    np.testing.assert_allclose(J[0, 1, 1].real, 0.7963844602228702, rtol=1e-12)
+    np.testing.assert_allclose(J[0, 2, 2].real, 1.0)
