@@ -439,3 +439,27 @@ def test_huygens_psf_strategy_is_routed_through_the_engine(plugin):
     got = HuygensPSF(CookeTriplet(), field=(0, 0.7), wavelength=0.55, num_rays=24, image_size=16).psf
     assert any(c[0] == "psf" for c in eng.calls[n0:])
     np.testing.assert_allclose(be.to_numpy(got), ref, rtol=0, atol=1e-8 * ref.max())
+
+
+def test_launch_form_reproduces_the_reference_ray_generator_known_answers():
+    """/root/reference/tests/test_rays.py:685-714: TessarLens, H = (0.5, 0.5), P = (0.1, 0.1), (0.2, 0.2) -- the
+    reference's hard-coded launch rays, reproduced by pack.launch_scalars + launch.pupil_affine (the form the kernel
+    evaluates)."""
+    from oracle.ref_import import import_reference
+
+    import_reference()
+    import optiland.backend as be
+    from optiland.samples.objectives import TessarLens
+
+    from optiland_b200.launch import launch_from_affine, pupil_affine
+    from optiland_b200.pack import launch_scalars
+
+    be.set_backend("numpy")
+    sc = launch_scalars(TessarLens(), 0.5, 0.5)
+    x, y, z, L, M, N = launch_from_affine(np.array([0.1, 0.2]), np.array([0.1, 0.2]), pupil_affine(sc))
+    np.testing.assert_allclose(x, [-0.23535066, -0.1909309], atol=1e-8)
+    np.testing.assert_allclose(y, [-0.23535066, -0.1909309], atol=1e-8)
+    np.testing.assert_allclose(z, [-0.88839505, -0.88839505], atol=1e-8)
+    np.testing.assert_allclose(L, [0.17519154, 0.17519154], atol=1e-8)
+    np.testing.assert_allclose(M, [0.17519154, 0.17519154], atol=1e-8)
+    np.testing.assert_allclose(N, [0.96882189, 0.96882189], atol=1e-8)
