@@ -265,3 +265,23 @@ def test_random_systems_adjoint_vs_finite_differences(hc, seed):
             assert gpar[s_, 4] == pytest.approx(fd, rel=5e-4, abs=2e-6 * gmax), (seed, s_, "conic", gpar[s_, 4], fd)
             checked += 1
     assert checked >= 3
+
+
+@pytest.mark.parametrize("seed", range(20))
+def test_random_tables_survive_the_abi_layout(seed):
+    """SurfaceTable -> OlbSurface[] + pool (the C ABI layout) -> SurfaceTable is the identity on random tables of
+    every geometry kind, and the (de)serialised form used by the fixtures packs to the same bytes."""
+    rng = np.random.default_rng(11000 + seed)
+    table = random_system(rng, int(rng.integers(3, 9))) if seed % 2 else random_freeform_system(rng)
+    surf, pool = table.pack()
+    back = T.SurfaceTable.unpack(surf, pool, table.wavelengths)
+    s2, p2 = back.pack()
+    assert surf.tobytes() == s2.tobytes() and pool.tobytes() == p2.tobytes()
+    again = T.SurfaceTable.from_arrays(table.to_arrays())
+    s3, p3 = again.pack()
+    assert surf.tobytes() == s3.tobytes() and pool.tobytes() == p3.tobytes()
+    for a, b in zip(table.surfaces, back.surfaces):
+        assert a.kind == b.kind and a.reflective == b.reflective and a.coating == b.coating
+        np.testing.assert_array_equal(a.t, b.t)
+        np.testing.assert_array_equal(a.R, b.R)
+        np.testing.assert_array_equal(np.ravel(a.coefficients), np.ravel(b.coefficients))
