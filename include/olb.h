@@ -235,6 +235,9 @@ typedef struct OlbRecords {
                                           the reference raises ValueError
                                           (optiland/geometries/zernike.py:254-266) */
 
+#define OLB_ST_K_PARALLEL_X (1 << 2)    /* polarized intensity epilogue: a launch direction parallel to the x axis; the
+                                          reference raises ValueError (optiland/rays/polarized_rays.py:216-218)     */
+
 int olb_version(void);
 /* Copies the calling thread's last error message into buf (NUL terminated). */
 int olb_last_error(char* buf, int buf_len);
@@ -468,6 +471,41 @@ int olb_trace_wavefront_f64(const OlbDeviceTable* table, int32_t first, int32_t 
                             const OlbPupilLaunch* launch, const OlbRays* rays, const OlbRecords* rec,
                             int64_t n_rays, uint32_t flags, const OlbWavefrontRef* ref,
                             const OlbWavefrontOut* out, int32_t* status, void* stream);
+
+/*
+ * Polarized call shapes (config 5): PolarizedRays through the fused launch / the wavefront epilogue, with the
+ * intensity epilogue of RealRayTracer.trace in-kernel.
+ *
+ * `pol` describes optic.polarization_state (optiland/rays/polarization_state.py:15-56) and asks for
+ * PolarizedRays.update_intensity (optiland/rays/polarized_rays.py:122-133 with _get_3d_electric_field :204-233):
+ *     p = (k x xhat) / |k x xhat|,  s = p x k          (k = the ray's LAUNCH direction)
+ *     E0 = Ex e^{i phase_x} s + Ey e^{i phase_y} p ;  i = sum_states |P E0|^2 * i0 / n_states
+ * (unpolarized light = the two orthogonal states (1, 0) and (0, 1), is_polarized == 0).  The updated intensity goes
+ * to pol->intensity (device, n_rays) when given, otherwise into the final state's rays.i; the RECORD rows keep the
+ * geometric intensity, as in the reference (only rays.i is updated, raytrace/real_ray_tracer.py:112-113).  The
+ * wavefront epilogue's out.intensity receives the updated value.  A launch direction parallel to xhat sets
+ * OLB_ST_K_PARALLEL_X (the reference raises).
+ *
+ * OLB_TF_POLARIZED is implied.  `launch` (optional) as in olb_trace_pupil_*: P then starts as the identity
+ * (PolarizedRays.__init__, :50) and rays.p is output only -- and may be NULL when pol is given (the P matrices are
+ * then not written at all: 72 / 144 B per ray saved).  `ref` / `out` (optional, together) as in
+ * olb_trace_wavefront_*.  pol may be NULL (plain polarized trace: P matrices only).
+ */
+typedef struct OlbPolarization {
+  int32_t is_polarized;     /* 0: unpolarized (mean of two orthogonal states); 1: (Ex, Ey, phase_x, phase_y) */
+  int32_t reserved;
+  double Ex, Ey;            /* normalised amplitudes (PolarizationState normalises them, :53-56)            */
+  double phase_x, phase_y;  /* radians                                                                      */
+  void* intensity;          /* optional device output, n_rays elements of the kernel's type                 */
+} OlbPolarization;
+int olb_trace_polarized_f32(const OlbDeviceTable* table, int32_t first, int32_t last,
+                            const OlbPupilLaunch* launch, const OlbRays* rays, const OlbRecords* rec,
+                            int64_t n_rays, uint32_t flags, const OlbPolarization* pol,
+                            const OlbWavefrontRef* ref, const OlbWavefrontOut* out, int32_t* status, void* stream);
+int olb_trace_polarized_f64(const OlbDeviceTable* table, int32_t first, int32_t last,
+                            const OlbPupilLaunch* launch, const OlbRays* rays, const OlbRecords* rec,
+                            int64_t n_rays, uint32_t flags, const OlbPolarization* pol,
+                            const OlbWavefrontRef* ref, const OlbWavefrontOut* out, int32_t* status, void* stream);
 
 /*
  * Batched many-systems trace: B perturbed copies of one template system -- the shape of

@@ -66,6 +66,11 @@ class OlbWavefrontOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("opd", "pupil_x", "pupil_y", "pupil_z", "intensity")]
 
 
+class OlbPolarization(C.Structure):
+    _fields_ = [("is_polarized", C.c_int32), ("reserved", C.c_int32), ("Ex", C.c_double), ("Ey", C.c_double),
+                ("phase_x", C.c_double), ("phase_y", C.c_double), ("intensity", C.c_void_p)]
+
+
 class OlbDeviceTable(C.Structure):
     _fields_ = [
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("magic", C.c_uint32),
@@ -114,6 +119,12 @@ SYMBOLS = {
     "olb_trace_wavefront_f64": (C.c_int, [_P(OlbDeviceTable), C.c_int32, C.c_int32, _P(OlbPupilLaunch), _P(OlbRays),
                                           _P(OlbRecords), C.c_int64, C.c_uint32, _P(OlbWavefrontRef), _P(OlbWavefrontOut),
                                           C.c_void_p, C.c_void_p]),
+    "olb_trace_polarized_f32": (C.c_int, [_P(OlbDeviceTable), C.c_int32, C.c_int32, _P(OlbPupilLaunch), _P(OlbRays),
+                                          _P(OlbRecords), C.c_int64, C.c_uint32, _P(OlbPolarization), _P(OlbWavefrontRef),
+                                          _P(OlbWavefrontOut), C.c_void_p, C.c_void_p]),
+    "olb_trace_polarized_f64": (C.c_int, [_P(OlbDeviceTable), C.c_int32, C.c_int32, _P(OlbPupilLaunch), _P(OlbRays),
+                                          _P(OlbRecords), C.c_int64, C.c_uint32, _P(OlbPolarization), _P(OlbWavefrontRef),
+                                          _P(OlbWavefrontOut), C.c_void_p, C.c_void_p]),
     "olb_table_batch_workspace_bytes": (C.c_int64, [_P(OlbTable), C.c_int32]),
     "olb_table_upload_batch": (C.c_int, [_P(OlbTable), C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p,
                                          _P(OlbDeviceTable)]),

@@ -92,7 +92,9 @@ class _TraceFn(torch.autograd.Function):
                                 "non plane/standard/even-asphere geometry, non-radial aperture, Fresnel coating)")
         n = x.numel()
         S = table.num_surfaces
+        # (a slice / view of a larger tensor may start anywhere: the C ABI wants 16-byte aligned arrays)
         ins = [t.detach().contiguous() for t in (x, y, z, L, M, N, i, opd)]
+        ins = [t.clone() if t.data_ptr() % 16 else t for t in ins]
         vec = 4 if dtype == torch.float32 else 2
         stride = n if n % vec == 0 else (n + 63) // 64 * 64
         buf = torch.empty((8, S, stride), dtype=dtype, device=x.device)
@@ -120,6 +122,7 @@ class _TraceFn(torch.autograd.Function):
         dtype = buf.dtype
         if ctx.rows is None:
             gbufs = [None if g is None else g.to(dtype).contiguous() for g in grads]
+            gbufs = [g.clone() if (g is not None and g.data_ptr() % 16) else g for g in gbufs]
             mask = (1 << 64) - 1
         else:
             # dense (S, n) gradient arrays are allocated WITHOUT a fill; only the rows named in the mask

@@ -615,8 +615,11 @@ template <typename T> OLB_HD Cx<T> c_div(Cx<T> a, Cx<T> b) {
 
 // P := O_out * J * O_in * P for one ray.  k0 = (L0,M0,N0), k1 = (L,M,N) in the surface's local
 // frame (the reference mixes local frames across tilted surfaces; reproduced).  `cosi` = |n.k0|.
+// The matrix lives wherever the caller keeps it: element q (q = 2 (3 row + col) + {0: Re, 1: Im}) at P[q * ps] --
+// the kernel holds it in shared memory ([q][thread], conflict-free, ps = block size) so that the 18 values are
+// not carried in registers across the geometry step; the host check passes Ray::P with ps = 1.
 template <typename T>
-OLB_HD void polar_update(Ray<T>& r, const PrepSurface<T>& S, T ncoat, T cosi) {
+OLB_HD void polar_update(Ray<T>& r, T* P, int ps, const PrepSurface<T>& S, T ncoat, T cosi) {
   const T k0[3] = {r.L0, r.M0, r.N0}, k1[3] = {r.L, r.M, r.N};
   // s = k0 x k1, with the reference's fallback when k0 || k1 (polarized_rays.py:151-163).  At an
   // index-matched surface (the image surface: n1 == n2) k1 == k0 and s must come out exactly 0.
@@ -667,16 +670,56 @@ OLB_HD void polar_update(Ray<T>& r, const PrepSurface<T>& S, T ncoat, T cosi) {
   // P := M P, column by column
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    Cx<T> col[3] = {{r.P[2 * c], r.P[2 * c + 1]}, {r.P[2 * (3 + c)], r.P[2 * (3 + c) + 1]}, {r.P[2 * (6 + c)], r.P[2 * (6 + c) + 1]}};
+    Cx<T> col[3] = {{P[(2 * c) * ps], P[(2 * c + 1) * ps]}, {P[(2 * (3 + c)) * ps], P[(2 * (3 + c) + 1) * ps]},
+                    {P[(2 * (6 + c)) * ps], P[(2 * (6 + c) + 1) * ps]}};
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
       Cx<T> v = c_mul(Mx[3 * a], col[0]);
       Cx<T> w1 = c_mul(Mx[3 * a + 1], col[1]);
       Cx<T> w2 = c_mul(Mx[3 * a + 2], col[2]);
-      r.P[2 * (3 * a + c)] = v.re + w1.re + w2.re;
-      r.P[2 * (3 * a + c) + 1] = v.im + w1.im + w2.im;
+      P[(2 * (3 * a + c)) * ps] = v.re + w1.re + w2.re;
+      P[(2 * (3 * a + c) + 1) * ps] = v.im + w1.im + w2.im;
     }
   }
+}
+
+// PolarizedRays.update_intensity (optiland/rays/polarized_rays.py:122-133 with _get_3d_electric_field :204-233):
+//   p = (k x xhat) / |k x xhat|,  s = p x k   (k = LAUNCH direction; the reference raises when k || xhat)
+//   E0 = ax s + ay p  with the complex amplitudes ax = Ex e^{i phase_x}, ay = Ey e^{i phase_y}
+//   i  = sum_states |P E0|^2 * i0 / n_states ;  unpolarized light = the two states (ax, ay) = (1, 0) and (0, 1).
+// mode 1: one polarized state (ax, ay given as re / im pairs); mode 2: unpolarized.
+template <typename T>
+OLB_HD T polarized_intensity(const T* P, int ps, T kx, T ky, T kz, T i0, int mode, const T* ax, const T* ay, int& status) {
+  // k x (1, 0, 0) = (0, kz, -ky)
+  const T nrm = o_sqrt(o_fma(kz, kz, ky * ky));
+  if (nrm == 0) status |= OLB_ST_K_PARALLEL_X;
+  const T inv = o_rcp(nrm);
+  const T pv[3] = {(T)0, kz * inv, -ky * inv};
+  const T k[3] = {kx, ky, kz};
+  T sv[3];
+  o_cross(pv, k, sv);
+  T total = 0;
+  const int n_states = mode == 2 ? 2 : 1;
+  for (int st = 0; st < n_states; ++st) {
+    // amplitudes of this state
+    const T axr = mode == 2 ? (st == 0 ? (T)1 : (T)0) : ax[0], axi = mode == 2 ? (T)0 : ax[1];
+    const T ayr = mode == 2 ? (st == 0 ? (T)0 : (T)1) : ay[0], ayi = mode == 2 ? (T)0 : ay[1];
+    T er[3], ei[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { er[c] = o_fma(axr, sv[c], ayr * pv[c]); ei[c] = o_fma(axi, sv[c], ayi * pv[c]); }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      T re = 0, im = 0;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const T pr = P[(2 * (3 * a + c)) * ps], pi = P[(2 * (3 * a + c) + 1) * ps];
+        re += pr * er[c] - pi * ei[c];
+        im += pr * ei[c] + pi * er[c];
+      }
+      total += o_fma(re, re, im * im);
+    }
+  }
+  return total * i0 / (T)n_states;
 }
 
 // The surface step.  FEAT gates code that most systems never need (register pressure, code
@@ -684,7 +727,8 @@ OLB_HD void polar_update(Ray<T>& r, const PrepSurface<T>& S, T ncoat, T cosi) {
 // ONCE per surface, outside the per-ray loop, so the hot loop carries no geometry branches.
 enum { KIND_PLANE = 0, KIND_CONIC = 1, KIND_NEWTON = 2, KIND_ASPHERE = 3 };   // NEWTON: any family (generic loop); ASPHERE: even / odd only (fused loop)
 template <typename T, uint32_t FEAT, int KIND>
-OLB_HD void surface_step_k(Ray<T>& r, const PrepSurface<T>& S, const T* pool, bool from_global, int& status) {
+OLB_HD void surface_step_k(Ray<T>& r, const PrepSurface<T>& S, const T* pool, bool from_global, int& status,
+                           T* Pm = nullptr, int Pstride = 1) {
   // -- localize (coordinate_system.py:73-89), from global or from the previous local frame
   if (FEAT & FEAT_ROT) {
     if (from_global) apply_affine(S.Ag, S.bg, (S.flags & PSF_ROT_IN_G) != 0, r.x, r.y, r.z, r.L, r.M, r.N);
@@ -777,20 +821,27 @@ OLB_HD void surface_step_k(Ray<T>& r, const PrepSurface<T>& S, const T* pool, bo
   if ((FEAT & FEAT_EXTRA) && S.coating == OLB_COAT_SIMPLE)
     r.i *= (S.flags & OLB_SF_REFLECT) ? S.coat_r : S.coat_t;
   // -- polarization: rays.update() / coating.interact -> rays.update(jones)  (base.py:119-128)
-  if (FEAT & FEAT_POL) polar_update(r, S, med[MED_CN] + bad, o_abs(o_fma(r.L0, nx, o_fma(r.M0, ny, r.N0 * nz))));
+  // A SimpleCoating only scales the intensity: coating.interact never reaches rays.update(), so the P matrix
+  // keeps its value across that surface (base.py:119-128: update() runs only in the no-coating branch).
+  if (FEAT & FEAT_POL) {
+    if (S.coating != OLB_COAT_SIMPLE)
+      polar_update(r, Pm ? Pm : r.P, Pm ? Pstride : 1, S, med[MED_CN] + bad,
+                   o_abs(o_fma(r.L0, nx, o_fma(r.M0, ny, r.N0 * nz))));
+  }
 }
 
 // Runtime dispatch on the geometry kind (one ray).  The CUDA kernel does this dispatch once
 // per surface around its per-ray loop instead; the host-check uses this form.
 template <typename T, uint32_t FEAT>
-OLB_HD void surface_step(Ray<T>& r, const PrepSurface<T>& S, const T* pool, bool from_global, int& status) {
-  if (S.kind == OLB_GEOM_PLANE) surface_step_k<T, FEAT, KIND_PLANE>(r, S, pool, from_global, status);
-  else if (S.kind == OLB_GEOM_STANDARD) surface_step_k<T, FEAT, KIND_CONIC>(r, S, pool, from_global, status);
+OLB_HD void surface_step(Ray<T>& r, const PrepSurface<T>& S, const T* pool, bool from_global, int& status,
+                         T* Pm = nullptr, int Pstride = 1) {
+  if (S.kind == OLB_GEOM_PLANE) surface_step_k<T, FEAT, KIND_PLANE>(r, S, pool, from_global, status, Pm, Pstride);
+  else if (S.kind == OLB_GEOM_STANDARD) surface_step_k<T, FEAT, KIND_CONIC>(r, S, pool, from_global, status, Pm, Pstride);
   else if constexpr ((FEAT & FEAT_NEWTON) != 0) {
     // without FEAT_FREEFORM every Newton surface of the table is an even / odd asphere: the fused loop; with
     // it, one generic loop serves all families (two loops in one kernel cost more I-cache than the fusion saves)
-    if constexpr ((FEAT & FEAT_FREEFORM) != 0) surface_step_k<T, FEAT, KIND_NEWTON>(r, S, pool, from_global, status);
-    else surface_step_k<T, FEAT, KIND_ASPHERE>(r, S, pool, from_global, status);
+    if constexpr ((FEAT & FEAT_FREEFORM) != 0) surface_step_k<T, FEAT, KIND_NEWTON>(r, S, pool, from_global, status, Pm, Pstride);
+    else surface_step_k<T, FEAT, KIND_ASPHERE>(r, S, pool, from_global, status, Pm, Pstride);
   }
 }
 

@@ -36,8 +36,8 @@ namespace olb {
 template <typename T, int RPT, uint32_t FEAT> struct MinBlocks { static constexpr int v = OLB_MIN_BLOCKS; };
 #else
 template <typename T, int RPT, uint32_t FEAT> struct MinBlocks {
-  // polarized: 18 more live values per ray (the P matrix) -> give ptxas 128 (fp32) / 255 (fp64) registers
-  static constexpr int v = (FEAT & 8u) ? (sizeof(T) == 4 ? 2 : 1) : ((sizeof(T) * RPT <= 8) ? 3 : 2);
+  // polarized: the P matrix lives in shared memory, so both precisions fit 2 CTAs per SM (<= 128 registers)
+  static constexpr int v = (FEAT & 8u) ? 2 : ((sizeof(T) * RPT <= 8) ? 3 : 2);
 };
 #endif
 static constexpr int BLOCK = OLB_BLOCK;
@@ -93,7 +93,14 @@ struct TraceArgs {
   // wavefront epilogue (olb_trace_wavefront_*) when wf_opd != nullptr
   void* wf_opd; void* wf_px; void* wf_py; void* wf_pz; void* wf_i;
   WavefrontRef wf;
+  // polarized intensity epilogue (OlbPolarization): 0 off, 1 one polarized state, 2 unpolarized
+  int32_t pol_mode; int32_t pol_pad;
+  double pol_ax[2], pol_ay[2];     // complex amplitudes Ex e^{i phase_x}, Ey e^{i phase_y}
+  void* pol_i;                     // optional separate output of the updated intensity
 };
+
+// Shared-memory slots per thread of a polarized kernel: the P matrix (18) + launch direction (3) + launch intensity
+constexpr int POL_SLOTS = 22;
 
 // ---- vector access helpers -------------------------------------------------------------
 template <typename T, int RPT> struct Vec;
@@ -188,6 +195,10 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<T, RPT, FEAT>::v)) trace_ker
   const T* pool = reinterpret_cast<const T*>(surf + H->n_surf);
   const int n_wl = H->n_wl;
   const T* wl = pool + H->pad[0];
+  // Polarized kernels keep each ray's P matrix (and its launch direction / intensity for the intensity epilogue)
+  // in shared memory, [slot][thread]: conflict-free, and the 18 + 4 values are not live registers across the
+  // geometry step (the register-resident form needed 204 registers in fp64: one CTA per SM).
+  T* Psm = reinterpret_cast<T*>(tab + (((size_t)a.blob_bytes + 15) & ~size_t(15))) + threadIdx.x;
 
   const int64_t n = a.sys_rays > 0 ? a.sys_rays : a.n_rays;     // rays of THIS system
   const int64_t seg = (int64_t)sys * n;                         // where its outputs start
@@ -275,15 +286,18 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<T, RPT, FEAT>::v)) trace_ker
       static_assert(RPT == 1, "polarized kernels process one ray per thread");
       if (a.tflags & OLB_TF_POL_IDENTITY) {
 #pragma unroll
-        for (int q = 0; q < 18; ++q) r[0].P[q] = (q == 0 || q == 8 || q == 16) ? (T)1 : (T)0;
+        for (int q = 0; q < 18; ++q) Psm[q * BLOCK] = (q == 0 || q == 8 || q == 16) ? (T)1 : (T)0;
       } else {
         using V2 = typename Vec<T, 2>::type;
         const V2* src = reinterpret_cast<const V2*>((const T*)a.p + base * 18);
 #pragma unroll
         for (int q = 0; q < 9; ++q) {
           V2 v = __ldcs(src + q);
-          r[0].P[2 * q] = v.x; r[0].P[2 * q + 1] = v.y;
+          Psm[(2 * q) * BLOCK] = v.x; Psm[(2 * q + 1) * BLOCK] = v.y;
         }
+      }
+      if (a.pol_mode != 0) {   // what update_intensity needs from the LAUNCH state (polarized_rays.py:51-55)
+        Psm[18 * BLOCK] = r[0].L; Psm[19 * BLOCK] = r[0].M; Psm[20 * BLOCK] = r[0].N; Psm[21 * BLOCK] = r[0].i;
       }
     }
 
@@ -318,20 +332,20 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<T, RPT, FEAT>::v)) trace_ker
         const bool fg = !have_frame;
         if (S.kind == OLB_GEOM_PLANE) {
 #pragma unroll
-          for (int k = 0; k < RPT; ++k) surface_step_k<T, FEAT, KIND_PLANE>(r[k], S, pool, fg, status);
+          for (int k = 0; k < RPT; ++k) surface_step_k<T, FEAT, KIND_PLANE>(r[k], S, pool, fg, status, Psm, BLOCK);
         } else if (S.kind == OLB_GEOM_STANDARD) {
 #pragma unroll
-          for (int k = 0; k < RPT; ++k) surface_step_k<T, FEAT, KIND_CONIC>(r[k], S, pool, fg, status);
+          for (int k = 0; k < RPT; ++k) surface_step_k<T, FEAT, KIND_CONIC>(r[k], S, pool, fg, status, Psm, BLOCK);
         } else if constexpr ((FEAT & FEAT_NEWTON) != 0) {
           // (the launcher gives Newton tables RPT <= 2, so the unrolled bodies stay inside the I-cache.)
           // Asphere-only tables (no FEAT_FREEFORM) run the fused sag + slope loop; tables with a polynomial-family
           // surface run ONE generic loop for all their Newton surfaces.
           if constexpr ((FEAT & FEAT_FREEFORM) != 0) {
 #pragma unroll
-            for (int k = 0; k < RPT; ++k) surface_step_k<T, FEAT, KIND_NEWTON>(r[k], S, pool, fg, status);
+            for (int k = 0; k < RPT; ++k) surface_step_k<T, FEAT, KIND_NEWTON>(r[k], S, pool, fg, status, Psm, BLOCK);
           } else {
 #pragma unroll
-            for (int k = 0; k < RPT; ++k) surface_step_k<T, FEAT, KIND_ASPHERE>(r[k], S, pool, fg, status);
+            for (int k = 0; k < RPT; ++k) surface_step_k<T, FEAT, KIND_ASPHERE>(r[k], S, pool, fg, status, Psm, BLOCK);
           }
         }
         have_frame = true;
@@ -374,6 +388,16 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<T, RPT, FEAT>::v)) trace_ker
         }
       }
     }
+    if constexpr ((FEAT & FEAT_POL) != 0) {
+      if (a.pol_mode != 0) {
+        // PolarizedRays.update_intensity on the final P matrix; the record rows above keep the geometric intensity
+        const T ax[2] = {(T)a.pol_ax[0], (T)a.pol_ax[1]}, ay[2] = {(T)a.pol_ay[0], (T)a.pol_ay[1]};
+        const T inew = polarized_intensity<T>(Psm, BLOCK, Psm[18 * BLOCK], Psm[19 * BLOCK], Psm[20 * BLOCK], Psm[21 * BLOCK],
+                                              a.pol_mode, ax, ay, status);
+        r[0].i = inew;
+        if (a.pol_i != nullptr) __stcs((T*)a.pol_i + base, inew);
+      }
+    }
     if (a.wf_opd != nullptr) {
       // OPD map against the reference sphere + exit-pupil intercepts, from the GLOBAL final state; the
       // pupil samples are re-read for the launch-plane tilt term (they were consumed by the launch)
@@ -414,12 +438,14 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<T, RPT, FEAT>::v)) trace_ker
       store_rays<T, RPT>((T*)a.opd, base, valid, v);
     }
     if constexpr ((FEAT & FEAT_POL) != 0) {
-      using V2 = typename Vec<T, 2>::type;
-      V2* dst = reinterpret_cast<V2*>((T*)a.p + base * 18);
+      if (a.p != nullptr) {
+        using V2 = typename Vec<T, 2>::type;
+        V2* dst = reinterpret_cast<V2*>((T*)a.p + base * 18);
 #pragma unroll
-      for (int q = 0; q < 9; ++q) {
-        V2 v; v.x = r[0].P[2 * q]; v.y = r[0].P[2 * q + 1];
-        __stcs(dst + q, v);
+        for (int q = 0; q < 9; ++q) {
+          V2 v; v.x = Psm[(2 * q) * BLOCK]; v.y = Psm[(2 * q + 1) * BLOCK];
+          __stcs(dst + q, v);
+        }
       }
     }
     if constexpr ((FEAT & FEAT_EXTRA) != 0) {
@@ -698,7 +724,8 @@ static int trace_bwd_impl(const OlbDeviceTable* wh, int32_t first, int32_t last,
 template <typename T, int RPT, uint32_t FEAT>
 static int launch_instance(const TraceArgs& a, cudaStream_t stream) {
   auto kern = trace_kernel<T, RPT, FEAT>;
-  const size_t smem = 16 + (size_t)a.blob_bytes;
+  const size_t smem = (FEAT & FEAT_POL) ? 16 + (((size_t)a.blob_bytes + 15) & ~size_t(15)) + (size_t)POL_SLOTS * BLOCK * sizeof(T)
+                                        : 16 + (size_t)a.blob_bytes;
   static thread_local int cached_dev = -1;
   static thread_local int num_sms = 0;
   static thread_local int blocks_per_sm = 0;
@@ -773,7 +800,7 @@ static int trace_impl(const OlbDeviceTable* wh, int32_t first, int32_t last, con
                       const OlbRecords* rec, int64_t n_rays, uint32_t flags, int32_t* status,
                       cudaStream_t stream, const OlbPupilLaunch* launch = nullptr, const double* center = nullptr,
                       double* moments = nullptr, int64_t rays_per_system = 0, const OlbWavefrontRef* wref = nullptr,
-                      const OlbWavefrontOut* wout = nullptr) {
+                      const OlbWavefrontOut* wout = nullptr, const OlbPolarization* pol = nullptr) {
   if (!wh || wh->magic != WS_MAGIC || !wh->workspace)
     return fail(OLB_ERR_INVALID_ARG, "table handle was not initialised by olb_table_upload");
   const unsigned char* workspace_dev = (const unsigned char*)wh->workspace;
@@ -791,7 +818,7 @@ static int trace_impl(const OlbDeviceTable* wh, int32_t first, int32_t last, con
   if (launch) {
     if (!launch->Px || !launch->Py) return fail(OLB_ERR_INVALID_ARG, "launch.Px / launch.Py is NULL");
     if (!aligned16(launch->Px) || !aligned16(launch->Py)) return fail(OLB_ERR_ALIGNMENT, "launch.Px / Py not 16-byte aligned");
-    if (flags & OLB_TF_POLARIZED) return fail(OLB_ERR_UNSUPPORTED, "pupil launch with polarized rays is not built");
+    if (flags & OLB_TF_POLARIZED) flags |= OLB_TF_POL_IDENTITY;   // PolarizedRays.__init__: P starts as the identity
   }
   if (wh->n_wl > 1) {
     if (!rays->w) return fail(OLB_ERR_INVALID_ARG, "rays.w is NULL but the table has several wavelengths");
@@ -830,8 +857,8 @@ static int trace_impl(const OlbDeviceTable* wh, int32_t first, int32_t last, con
       return fail(OLB_ERR_INVALID_ARG, "wavefront: radius, n_image and wavelength must be positive");
     if ((wref->tilt[0] != 0 || wref->tilt[1] != 0) && !launch)
       return fail(OLB_ERR_INVALID_ARG, "wavefront: the launch-plane tilt term needs the pupil samples (launch)");
-    if (rays_per_system > 0 || (flags & OLB_TF_POLARIZED))
-      return fail(OLB_ERR_UNSUPPORTED, "wavefront epilogue with batched systems / polarized rays is not built");
+    if (rays_per_system > 0)
+      return fail(OLB_ERR_UNSUPPORTED, "wavefront epilogue with batched systems is not built");
     if (last != wh->n_surfaces) return fail(OLB_ERR_INVALID_ARG, "wavefront: the trace must end on the image surface");
     a.wf_opd = wout->opd; a.wf_px = wout->pupil_x; a.wf_py = wout->pupil_y; a.wf_pz = wout->pupil_z; a.wf_i = wout->intensity;
     for (int q = 0; q < 3; ++q) a.wf.c[q] = wref->center[q];
@@ -853,6 +880,16 @@ static int trace_impl(const OlbDeviceTable* wh, int32_t first, int32_t last, con
   }
   uint32_t features = wh->features;
   if (flags & OLB_TF_POLARIZED) features |= FEAT_POL;
+  if (pol) {
+    if (!(flags & OLB_TF_POLARIZED)) return fail(OLB_ERR_INVALID_ARG, "polarization epilogue needs OLB_TF_POLARIZED");
+    if (pol->intensity && !aligned16(pol->intensity)) return fail(OLB_ERR_ALIGNMENT, "pol.intensity not 16-byte aligned");
+    if ((flags & OLB_TF_NO_FINAL) && !pol->intensity && !wout)
+      return fail(OLB_ERR_INVALID_ARG, "polarization epilogue with OLB_TF_NO_FINAL needs pol.intensity (or the wavefront outputs)");
+    a.pol_mode = pol->is_polarized ? 1 : 2;
+    a.pol_ax[0] = pol->Ex * cos(pol->phase_x); a.pol_ax[1] = pol->Ex * sin(pol->phase_x);
+    a.pol_ay[0] = pol->Ey * cos(pol->phase_y); a.pol_ay[1] = pol->Ey * sin(pol->phase_y);
+    a.pol_i = pol->intensity;
+  }
   if (rays->L0 || rays->M0 || rays->N0) {
     if (!(rays->L0 && rays->M0 && rays->N0)) return fail(OLB_ERR_INVALID_ARG, "L0/M0/N0 must be all set or all NULL");
     if (!aligned16(rays->L0) || !aligned16(rays->M0) || !aligned16(rays->N0))
@@ -893,8 +930,11 @@ static int trace_impl(const OlbDeviceTable* wh, int32_t first, int32_t last, con
     if (!(flags & OLB_TF_POLARIZED))
       return fail(OLB_ERR_INVALID_ARG, "table has Fresnel coatings: needs OLB_TF_POLARIZED and rays.p "
                                        "(the reference raises for polarization == 'ignore', ray_generator.py:90-94)");
-    if (!rays->p) return fail(OLB_ERR_INVALID_ARG, "OLB_TF_POLARIZED needs rays.p");
-    if (!aligned16(rays->p)) return fail(OLB_ERR_ALIGNMENT, "rays.p not 16-byte aligned");
+    // rays.p may be omitted only when nothing would be lost: P starts as the identity and the intensity epilogue
+    // consumes the final matrix in-kernel
+    if (!rays->p && !((flags & OLB_TF_POL_IDENTITY) && pol))
+      return fail(OLB_ERR_INVALID_ARG, "OLB_TF_POLARIZED needs rays.p");
+    if (rays->p && !aligned16(rays->p)) return fail(OLB_ERR_ALIGNMENT, "rays.p not 16-byte aligned");
     return launch_feat<T, 1>(a, features, stream);
   }
   const bool closed_form = (features & ~FEAT_ROT) == 0;
@@ -1091,6 +1131,23 @@ int olb_trace_wavefront_f64(const OlbDeviceTable* table, int32_t first, int32_t 
                             launch, nullptr, nullptr, 0, ref, out);
 }
 
+int olb_trace_polarized_f32(const OlbDeviceTable* table, int32_t first, int32_t last, const OlbPupilLaunch* launch,
+                            const OlbRays* rays, const OlbRecords* rec, int64_t n_rays, uint32_t flags,
+                            const OlbPolarization* pol, const OlbWavefrontRef* ref, const OlbWavefrontOut* out,
+                            int32_t* status, void* stream) {
+  OlbRays none{};
+  return trace_impl<float>(table, first, last, rays ? rays : &none, rec, n_rays, flags | OLB_TF_POLARIZED, status,
+                           (cudaStream_t)stream, launch, nullptr, nullptr, 0, ref, out, pol);
+}
+int olb_trace_polarized_f64(const OlbDeviceTable* table, int32_t first, int32_t last, const OlbPupilLaunch* launch,
+                            const OlbRays* rays, const OlbRecords* rec, int64_t n_rays, uint32_t flags,
+                            const OlbPolarization* pol, const OlbWavefrontRef* ref, const OlbWavefrontOut* out,
+                            int32_t* status, void* stream) {
+  OlbRays none{};
+  return trace_impl<double>(table, first, last, rays ? rays : &none, rec, n_rays, flags | OLB_TF_POLARIZED, status,
+                            (cudaStream_t)stream, launch, nullptr, nullptr, 0, ref, out, pol);
+}
+
 int olb_trace_moments_f32(const OlbDeviceTable* table, int32_t first, int32_t last, const OlbPupilLaunch* launch,
                           const OlbRays* rays, const OlbRecords* rec, int64_t n_rays, uint32_t flags,
                           const double center[2], double* moments, int32_t* status, void* stream) {
@@ -1152,8 +1209,18 @@ static int trace_host_impl(const OlbDeviceTable* table, int32_t first, int32_t l
   for (int s = 0; s < NS; ++s)
     for (int k = 0; k < 9; ++k) slot[s][k] = (T*)scratch + ((int64_t)s * 9 + k) * chunk_al;
 
-  cudaStream_t st[NS];
-  for (int s = 0; s < NS; ++s) OLB_CUDA(cudaStreamCreateWithFlags(&st[s], cudaStreamNonBlocking));
+  // The NS copy / compute streams are created once per (host thread, device) and reused by every later call:
+  // creating and destroying them per call cost ~60 us and a device-wide synchronisation point each time.
+  static thread_local cudaStream_t tl_streams[16][NS];
+  static thread_local bool tl_have[16] = {};
+  int dev = 0;
+  OLB_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 16) return fail(OLB_ERR_INVALID_ARG, "device ordinal beyond 15");
+  if (!tl_have[dev]) {
+    for (int s = 0; s < NS; ++s) OLB_CUDA(cudaStreamCreateWithFlags(&tl_streams[dev][s], cudaStreamNonBlocking));
+    tl_have[dev] = true;
+  }
+  cudaStream_t* st = tl_streams[dev];
   int result = OLB_OK;
   int64_t done = 0;
   int ci = 0;
@@ -1169,7 +1236,8 @@ static int trace_host_impl(const OlbDeviceTable* table, int32_t first, int32_t l
       if (e != cudaSuccess) { result = fail(OLB_ERR_CUDA, cudaGetErrorString(e)); break; }
     }
     if (result) break;
-    cudaError_t e = cudaMemsetAsync(slot[s][8], 0, (size_t)m * sizeof(T), q);
+    cudaError_t e = cudaSuccess;
+    if (!launch) e = cudaMemsetAsync(slot[s][8], 0, (size_t)m * sizeof(T), q);   // (pupil launch: opd starts at 0 in-kernel)
     if (e != cudaSuccess) { result = fail(OLB_ERR_CUDA, cudaGetErrorString(e)); break; }
     OlbRays d{};
     d.x = slot[s][0]; d.y = slot[s][1]; d.z = slot[s][2]; d.L = slot[s][3]; d.M = slot[s][4]; d.N = slot[s][5];
@@ -1205,7 +1273,6 @@ static int trace_host_impl(const OlbDeviceTable* table, int32_t first, int32_t l
   for (int s = 0; s < NS; ++s) {
     cudaError_t e = cudaStreamSynchronize(st[s]);
     if (e != cudaSuccess && !result) result = fail(OLB_ERR_CUDA, cudaGetErrorString(e));
-    cudaStreamDestroy(st[s]);
   }
   return result;
 }

@@ -77,3 +77,52 @@ def global_rms_spot_radius(x: torch.Tensor, y: torch.Tensor, intensity: torch.Te
     cx, cy = sx / cnt, sy / cnt
     d2 = torch.where(m, (x.double() - cx) ** 2 + (y.double() - cy) ** 2, zero).sum().reshape(1)
     return float(np.sqrt(float(_allreduce_sum(d2, group)[0]) / cnt))
+
+
+def _parse_cpulist(text: str) -> list[int]:
+    cpus: list[int] = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        if "-" in part:
+            lo, hi = part.split("-")
+            cpus.extend(range(int(lo), int(hi) + 1))
+        else:
+            cpus.append(int(part))
+    return cpus
+
+
+def gpu_numa_node(device_index: int) -> int | None:
+    """NUMA node the GPU's PCIe root sits on (sysfs), or None when the platform does not say."""
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        return node if node >= 0 else None
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        return None
+
+
+def bind_to_gpu_numa(device_index: int) -> dict:
+    """Pin this process (one process per GPU) to the CPUs of its GPU's NUMA node BEFORE it allocates pinned host
+    buffers: first-touch then places the staging memory on the socket whose PCIe root complex the GPU hangs off, so
+    the H2D / D2H legs of the host-buffer entry points (olb_trace_host_*) do not cross the inter-socket link and the
+    8 ranks of one node do not all draw on one socket's memory controllers.  torchrun does not do this (it only sets
+    OMP_NUM_THREADS=1).  Returns what was done, for the bench line."""
+    import os
+
+    node = gpu_numa_node(device_index)
+    info = {"numa_node": node, "cpus": None}
+    if node is None:
+        return info
+    try:
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = _parse_cpulist(f.read())
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info["cpus"] = len(allowed)
+    except (OSError, ValueError):
+        pass
+    return info

@@ -293,6 +293,12 @@ def pack_surface(surface, wavelengths) -> T.SurfaceSpec:
         spec.aperture = pack_aperture(surface.aperture)
 
     mpre, mpost = surface.material_pre, surface.material_post
+    for mat in (mpre, mpost):
+        # the kernel propagates in straight lines (propagation/homogeneous.py:30-57); a GRIN medium raises
+        # NotImplementedError in the reference (propagation/grin.py) and must not be traced as homogeneous here
+        pm = getattr(mat, "propagation_model", None)
+        if pm is not None and _cls(pm) != "HomogeneousPropagation":
+            raise UnsupportedSurface(f"propagation model {_cls(pm)}")
     spec.n1 = _index_table(mpre, wavelengths, "n")
     spec.k1 = _index_table(mpre, wavelengths, "k")
     spec.n2 = _index_table(mpost, wavelengths, "n")

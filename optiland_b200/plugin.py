@@ -30,7 +30,13 @@ from collections import OrderedDict
 import numpy as np
 
 from . import table as T
+from ._lib import OlbError
 from .pack import UnsupportedSurface, pack_surface, pack_surface_group
+
+# what packing / uploading a table may raise for a system outside the kernel's scope (aperture tree deeper than the
+# evaluator's stack, polynomial order beyond the prepared tables, table larger than shared memory ...): every one
+# of them hands the call back to the reference's own Python body instead of escaping from SurfaceGroup.trace
+_PACK_ERRORS = (UnsupportedSurface, ValueError, TypeError, OlbError)
 
 _REC_ATTR = (("x", "x"), ("y", "y"), ("z", "z"), ("L", "L"), ("M", "M"), ("N", "N"),
              ("intensity", "intensity"), ("opd", "opd"))
@@ -66,6 +72,15 @@ class CudaEngine:
     def __init__(self, cache_size: int = 8):
         self._cache: OrderedDict[bytes, object] = OrderedDict()
         self._cache_size = cache_size
+        # what went through the engine, newest last: (n_surfaces, n_rays) for a plain trace, otherwise
+        # (kind, ...) with kind in {"pupil", "wavefront", "psf", "grad", "moments", "batch"} -- the answer to
+        # "did my call really run on the kernel?" (tests, plugin.stats())
+        self.calls: list = []
+
+    def _note(self, *what):
+        self.calls.append(what)
+        if len(self.calls) > 65536:
+            del self.calls[:32768]
 
     def accepts(self, rays) -> bool:
         import torch
@@ -115,6 +130,7 @@ class CudaEngine:
         shell.L0 = shell.M0 = shell.N0 = None
         shell.is_normalized = True
         dt = self.device_table(table, shell.x.device)
+        self._note(table.num_surfaces, int(shell.x.numel()))
         rec = trace_device(dt, shell, first, last, record=True)
         for k in ("x", "y", "z", "L", "M", "N", "i", "opd"):
             setattr(rays, k, getattr(shell, k))
@@ -138,6 +154,7 @@ class CudaEngine:
         if affine.get("fields") is not None:
             affine = dict(affine, fields=tuple(_dev_array(t) for t in affine["fields"]))
         w = _dev_array(wavelength) if wavelength is not None else None
+        self._note("pupil", table.num_surfaces, int(Px.numel()))
         _, rec = trace_pupil_device(dt, _dev_array(Px), _dev_array(Py), affine, 0, table.num_surfaces, wavelength=w)
         return rec
 
@@ -147,6 +164,7 @@ class CudaEngine:
         from .trace import trace_wavefront_device
 
         dt = self.device_table(table, Px.device)
+        self._note("wavefront", table.num_surfaces, int(Px.numel()))
         return trace_wavefront_device(dt, _dev_array(Px), _dev_array(Py), affine, ref)
 
     def huygens_psf(self, image_x, image_y, image_z, pupil_x, pupil_y, pupil_z, pupil_amp, pupil_opd, wavelength, Rp):
@@ -157,6 +175,7 @@ class CudaEngine:
 
         if not (torch.is_tensor(image_x) and image_x.is_cuda):
             return None
+        self._note("psf", int(image_x.numel()), int(pupil_x.numel()))
         return huygens_fresnel_psf(image_x, image_y, image_z, pupil_x, pupil_y, pupil_z, pupil_amp, pupil_opd,
                                    wavelength, Rp).to(image_x.dtype)
 
@@ -168,6 +187,7 @@ class CudaEngine:
         dt = self.device_table(table, rays.x.device)
         if not dt.c.bwd_supported:
             return None
+        self._note("grad", table.num_surfaces, int(rays.x.numel()))
         ins = [getattr(rays, k) for k in ("x", "y", "z", "L", "M", "N", "i", "opd")]
         # one (N,) output per (quantity, row): the backward pass then touches only the rows the loss reads
         # (a dense (S, N) output would make autograd zero-fill and the kernel re-read every row), and ``dt``
@@ -178,6 +198,15 @@ class CudaEngine:
         for k, key in (("x", "x"), ("y", "y"), ("z", "z"), ("L", "L"), ("M", "M"), ("N", "N"), ("i", "intensity"), ("opd", "opd")):
             setattr(rays, k, rec[key][-1])
         return rec
+
+
+def _prepare(engine, table, device) -> None:
+    """Prepare + upload ``table`` now (cached by content) so that a table the library rejects -- OLB_ERR_TABLE /
+    OLB_ERR_UNSUPPORTED from olb_table_upload -- surfaces as an OlbError HERE, inside the caller's try block, and
+    turns into a decline rather than an exception out of the reference's trace call."""
+    dt = getattr(engine, "device_table", None)
+    if dt is not None:
+        dt(table, device)
 
 
 def _unique_wavelengths(w):
@@ -215,6 +244,39 @@ def _set_pre_interaction_direction(rays, table, rec, first, last, launch_dir):
     else:
         L0, M0, N0 = Lg, Mg, Ng
     rays.L0, rays.M0, rays.N0 = L0, M0, N0
+
+
+def _tail_propagate(be, rays, last_surface, wavelengths, w=None) -> None:
+    """Tail of ``RealRayTracer.trace`` / ``trace_generic`` (raytrace/real_ray_tracer.py:105-110, :145-152): propagate
+    the traced rays by the image surface's ``thickness`` through ``material_post``.
+
+    The reference's ``HomogeneousPropagation.propagate`` (propagation/homogeneous.py:30-57) asks the material for
+    ``k(rays.w)`` with the PER-RAY wavelength array, whose cache key is ``tuple(np.ravel(to_numpy(w)))``
+    (materials/base.py:73-79): a device-to-host copy and a 10^7-element Python tuple per call.  The same arithmetic
+    with k looked up per DISTINCT wavelength (the values the kernel's table holds), and nothing at all for the usual
+    thickness 0 in a transparent medium (x + 0 L == x).  Other propagation models run the reference's own code."""
+    pm = last_surface.material_post.propagation_model
+    if type(pm).__name__ != "HomogeneousPropagation":
+        pm.propagate(rays, last_surface.thickness)
+        return
+    t = last_surface.thickness
+    t_val = float(np.asarray(be.to_numpy(t)).reshape(-1)[0])
+    ks = [float(np.asarray(be.to_numpy(last_surface.material_post.k(float(wl)))).reshape(-1)[0]) for wl in wavelengths]
+    if t_val != 0.0 or getattr(t, "requires_grad", False):
+        rays.x = rays.x + t * rays.L
+        rays.y = rays.y + t * rays.M
+        rays.z = rays.z + t * rays.N
+    if any(k > 0 for k in ks) and t_val != 0.0:
+        if len(ks) == 1 or w is None:
+            alpha = 4 * np.pi * ks[0] / float(wavelengths[0])
+            rays.i = rays.i * be.exp(-alpha * t * 1e3 * be.ones_like(rays.i))
+        else:
+            k = be.zeros_like(rays.i)
+            for wl, kv in zip(wavelengths, ks):
+                k = be.where(w == wl, kv * be.ones_like(k), k)
+            rays.i = rays.i * be.exp(-(4 * np.pi * k / w) * t * 1e3)
+    if not rays.is_normalized:
+        rays.normalize()
 
 
 def _live_params(surfaces, table, wavelength):
@@ -323,12 +385,18 @@ def _try_trace(backend, surfaces, rays, table_builder) -> bool:
     engine = _state["engine"]
     if not engine.accepts(rays):
         return _decline("rays not resident on a CUDA device (or not fp32/fp64)")
+    if not getattr(rays, "is_normalized", True):
+        # a previous surface left un-normalised direction cosines (thin_lens_interaction_model.py:111) and
+        # HomogeneousPropagation.propagate would renormalise them first (propagation/homogeneous.py:55-56); the
+        # kernel assumes unit directions
+        return _decline("rays.is_normalized is False")
     wl = _unique_wavelengths(rays.w)
     if wl is None:
         return _decline(f"more than {T.MAX_WAVELENGTHS} distinct wavelengths")
     try:
         table = table_builder(wl)
-    except UnsupportedSurface as e:
+        _prepare(engine, table, rays.x.device)         # upload errors (OlbError) decline as well
+    except _PACK_ERRORS as e:
         return _decline(f"unsupported: {e}")
     if not polarized and any(s.coating == T.COAT_FRESNEL for s in table.surfaces):
         # the reference raises for this combination (ray_generator.py:90-94)
@@ -421,7 +489,9 @@ def install(engine=None, alias: str | None = None) -> None:
             try:
                 sc = launch_scalars(optic, hx, hy)
                 table = pack_surface_group(optic.surfaces, [float(wavelength)])
-            except (UnsupportedSurface, TypeError, ValueError):
+                _prepare(engine, table, Px.device)
+            except _PACK_ERRORS as e:
+                _decline(f"fused launch unsupported: {e}")
                 return None
             if any(s.coating == T.COAT_FRESNEL for s in table.surfaces):
                 return None
@@ -437,8 +507,7 @@ def install(engine=None, alias: str | None = None) -> None:
                                            (rec["L"][0], rec["M"][0], rec["N"][0]))
             # tail of RealRayTracer.trace (raytrace/real_ray_tracer.py:105-118)
             if optic.image_surface:
-                last_surface = optic.surfaces[-1]
-                last_surface.material_post.propagation_model.propagate(rays, last_surface.thickness)
+                _tail_propagate(be, rays, optic.surfaces[-1], [float(wavelength)])
             return rays
 
         def trace_optic_generic(self, tracer, Hx, Hy, Px, Py, wavelength):
@@ -497,8 +566,10 @@ def install(engine=None, alias: str | None = None) -> None:
                 sc = launch_scalars(optic, 0.0, 0.0)
                 sc["vx"] = sc["vy"] = 1.0            # (the factors are already in Px, Py)
                 table = pack_surface_group(optic.surfaces, wls)
+                _prepare(engine, table, Px.device)
                 aff = pupil_affine_fields(sc, Hx, Hy)
-            except (UnsupportedSurface, TypeError, ValueError):
+            except _PACK_ERRORS as e:
+                _decline(f"fused launch unsupported: {e}")
                 return None
             if any(s.coating == T.COAT_FRESNEL for s in table.surfaces):
                 return None
@@ -513,8 +584,8 @@ def install(engine=None, alias: str | None = None) -> None:
             rays.opd = rec["opd"][-1]
             _set_pre_interaction_direction(rays, table, rec, 0, table.num_surfaces,
                                            (rec["L"][0], rec["M"][0], rec["N"][0]))
-            last_surface = optic.surfaces[-1]   # tail of trace_generic (real_ray_tracer.py:145-152)
-            last_surface.material_post.propagation_model.propagate(rays, last_surface.thickness)
+            # tail of trace_generic (real_ray_tracer.py:145-152)
+            _tail_propagate(be, rays, optic.surfaces[-1], [float(v) for v in wls], w if len(wls) > 1 else None)
             return rays
 
         def wavefront_chief_ray(self, strategy, field, wavelength):
@@ -538,6 +609,14 @@ def install(engine=None, alias: str | None = None) -> None:
                 return None
             if getattr(optic.ray_tracer, "ray_aiming_config", {}).get("mode", "paraxial") != "paraxial":
                 return None
+            try:
+                # the reference propagates the traced rays by the image surface's thickness before the wavefront
+                # strategy reads them (real_ray_tracer.py:105-110); the fused epilogue works on the image-surface
+                # record, so a non-zero thickness goes back to the reference path
+                if float(_np.asarray(be.to_numpy(optic.surfaces[-1].thickness)).reshape(-1)[0]) != 0.0:
+                    return None
+            except Exception:
+                return None
             dist = strategy.distribution
             Px, Py = dist.x, dist.y
             if not (engine.accepts_tensor(Px) and engine.accepts_tensor(Py)):
@@ -546,7 +625,9 @@ def install(engine=None, alias: str | None = None) -> None:
                 hx, hy = float(field[0]), float(field[1])
                 sc = launch_scalars(optic, hx, hy)
                 table = pack_surface_group(optic.surfaces, [float(wavelength)])
-            except (UnsupportedSurface, TypeError, ValueError):
+                _prepare(engine, table, Px.device)
+            except _PACK_ERRORS as e:
+                _decline(f"fused launch unsupported: {e}")
                 return None
             if any(s.coating == T.COAT_FRESNEL for s in table.surfaces):
                 return None

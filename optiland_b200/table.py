@@ -54,6 +54,7 @@ _AP_OPERANDS = {AP_RADIAL: 2, AP_OFFSET_RADIAL: 4, AP_RECT: 4, AP_ELLIPSE: 4,
 TF_POLARIZED = 1 << 0
 ST_ZERNIKE_RANGE = 1 << 0
 ST_CHEBYSHEV_RANGE = 1 << 1
+ST_K_PARALLEL_X = 1 << 2
 
 MAX_SURFACES = 64
 MAX_WAVELENGTHS = 16

@@ -138,14 +138,58 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
+def _status_word(dtab: "DeviceTable", device, force: bool = False):
+    """Device int32 the kernels OR their OLB_ST_* bits into -- only for tables / call shapes that can raise them."""
+    return torch.zeros(1, dtype=torch.int32, device=device) if (dtab.has_zernike or force) else None
+
+
+def _raise_status(status) -> None:
+    """The reference's ValueErrors for out-of-range freeform coordinates, from the kernel's status word; shared by
+    every entry point (plain, pupil-launch, wavefront, moments) so that none of them returns extrapolated numbers."""
+    if status is None:
+        return
+    st = int(status.item())
+    if st & T.ST_ZERNIKE_RANGE:
+        # same exception, same message as optiland/geometries/zernike.py:254-266
+        raise ValueError(
+            "Zernike coordinates must be normalized to [-1, 1]. Consider updating the normalization "
+            "radius to 1.1x the surface aperture.")
+    if st & T.ST_CHEBYSHEV_RANGE:
+        # optiland/geometries/chebyshev.py:230-244
+        raise ValueError(
+            "Chebyshev input coordinates must be normalized to [-1, 1]. Consider updating the "
+            "normalization factors.")
+    if st & T.ST_K_PARALLEL_X:
+        # optiland/rays/polarized_rays.py:216-218
+        raise ValueError("k-vector parallel to x-axis is not currently supported.")
+
+
+def _c_polarization(state, intensity_out=None):
+    """OlbPolarization from ``state`` = None / "unpolarized" (the mean of two orthogonal states) or
+    (Ex, Ey, phase_x, phase_y) (normalised as PolarizationState does, polarization_state.py:53-56)."""
+    c = _lib.OlbPolarization()
+    if state is None or state == "unpolarized":
+        c.is_polarized = 0
+    else:
+        Ex, Ey, phx, phy = (float(v) for v in state)
+        mag = (Ex * Ex + Ey * Ey) ** 0.5
+        c.is_polarized, c.Ex, c.Ey, c.phase_x, c.phase_y = 1, Ex / mag, Ey / mag, phx, phy
+    c.intensity = intensity_out.data_ptr() if intensity_out is not None else None
+    return c
+
+
 def trace_device(dtab: DeviceTable, rays: RealRays, first: int, last: int, record: bool = True,
-                 want_l0: bool = False):
+                 want_l0: bool = False, polarization=False):
     """One call of olb_trace_f32/f64.  Returns the dict of (rows, N) record tensors (or None).
 
     With ``record`` the final state is NOT written a second time: ``rays.x`` .. ``rays.opd``
     become views of the last record row (OLB_TF_NO_FINAL), saving 32-64 B/ray of HBM traffic.
     The reference never mutates these arrays in place (it re-assigns attributes), so the
     aliasing is not observable through its API.
+
+    ``polarization`` (PolarizedRays only): None / "unpolarized" / (Ex, Ey, phase_x, phase_y) runs
+    PolarizedRays.update_intensity as the kernel's epilogue (olb_trace_polarized_*): ``rays.i`` becomes
+    sum |P E0|^2 i0 / n_states while the record rows keep the geometric intensity.
     """
     lib = dtab.lib
     n = len(rays)
@@ -184,28 +228,30 @@ def trace_device(dtab: DeviceTable, rays: RealRays, first: int, last: int, recor
         w=rays.w.data_ptr() if dtab.table.n_wl > 1 else None, opd=rays.opd.data_ptr(),
         L0=rays.L0.data_ptr() if want_l0 else None, M0=rays.M0.data_ptr() if want_l0 else None,
         N0=rays.N0.data_ptr() if want_l0 else None, p=p_ptr)
-    status = torch.zeros(1, dtype=torch.int32, device=rays.device) if dtab.has_zernike else None
+    pol_i, c_pol = None, None
+    if polarization is not False:
+        if not isinstance(rays, PolarizedRays):
+            raise ValueError("the intensity epilogue needs PolarizedRays")
+        pol_i = torch.empty_like(rays.x)
+        c_pol = _c_polarization(polarization, pol_i)
+    status = _status_word(dtab, rays.device, force=c_pol is not None)
     with torch.cuda.device(rays.device):
         stream = torch.cuda.current_stream(rays.device).cuda_stream
-        rc = fn(C.byref(dtab.c), first, last, C.byref(c_rays), C.byref(c_rec) if c_rec is not None else None,
-                n, flags, _ptr(status), C.c_void_p(stream))
+        if c_pol is not None:
+            rc = getattr(lib, f"olb_trace_polarized_{sfx}")(
+                C.byref(dtab.c), first, last, None, C.byref(c_rays), C.byref(c_rec) if c_rec is not None else None,
+                n, flags, C.byref(c_pol), None, None, _ptr(status), C.c_void_p(stream))
+        else:
+            rc = fn(C.byref(dtab.c), first, last, C.byref(c_rays), C.byref(c_rec) if c_rec is not None else None,
+                    n, flags, _ptr(status), C.c_void_p(stream))
     _lib.check(rc, f"olb_trace_{sfx}")
-    if status is not None:
-        st = int(status.item())
-        if st & T.ST_ZERNIKE_RANGE:
-            # same exception, same message as optiland/geometries/zernike.py:254-266
-            raise ValueError(
-                "Zernike coordinates must be normalized to [-1, 1]. Consider updating the normalization "
-                "radius to 1.1x the surface aperture.")
-        if st & T.ST_CHEBYSHEV_RANGE:
-            # optiland/geometries/chebyshev.py:230-244
-            raise ValueError(
-                "Chebyshev input coordinates must be normalized to [-1, 1]. Consider updating the "
-                "normalization factors.")
+    _raise_status(status)
     if recs is not None:
         rays.x, rays.y, rays.z = recs["x"][-1], recs["y"][-1], recs["z"][-1]
         rays.L, rays.M, rays.N = recs["L"][-1], recs["M"][-1], recs["N"][-1]
         rays.i, rays.opd = recs["intensity"][-1], recs["opd"][-1]
+    if pol_i is not None:
+        rays.i = pol_i
     return recs
 
 
@@ -229,9 +275,16 @@ def _c_launch(affine: dict, Px, Py):
 
 
 def trace_pupil_device(dtab: DeviceTable, Px: torch.Tensor, Py: torch.Tensor, affine: dict, first: int, last: int,
-                       wavelength: torch.Tensor | None = None):
+                       wavelength: torch.Tensor | None = None, polarization=False):
     """olb_trace_pupil_*: launch state generated in-kernel from pupil coordinates (one field), full
-    records.  Returns (rays, records): ``rays`` is a ``RealRays`` view of the last record row."""
+    records.  Returns (rays, records): ``rays`` is a ``RealRays`` view of the last record row.
+
+    ``polarization`` (config 5's call shape, olb_trace_polarized_*): False = RealRays; otherwise PolarizedRays are
+    traced -- "matrix": only the P matrices (``rays.p``); None / "unpolarized" / (Ex, Ey, phase_x, phase_y): also the
+    intensity epilogue of RealRayTracer.trace in-kernel, ``rays.i`` = sum |P E0|^2 i0 / n_states (the record rows keep
+    the geometric intensity, as in the reference)."""
+    if polarization is not False:
+        return _trace_pupil_polarized(dtab, Px, Py, affine, first, last, wavelength, polarization)
     lib = dtab.lib
     n = Px.numel()
     dtype = Px.dtype
@@ -244,11 +297,13 @@ def trace_pupil_device(dtab: DeviceTable, Px: torch.Tensor, Py: torch.Tensor, af
     c_rec = _lib.OlbRecords(*[buf[j].data_ptr() for j in range(8)], stride)
     la = _c_launch(affine, Px.contiguous(), Py.contiguous())
     out = _lib.OlbRays(w=wavelength.data_ptr() if (wavelength is not None and dtab.table.n_wl > 1) else None)
+    status = _status_word(dtab, Px.device)
     with torch.cuda.device(Px.device):
         stream = torch.cuda.current_stream(Px.device).cuda_stream
         rc = getattr(lib, f"olb_trace_pupil_{sfx}")(C.byref(dtab.c), first, last, C.byref(la), C.byref(out),
-                                                    C.byref(c_rec), n, _lib.TF_NO_FINAL, None, C.c_void_p(stream))
+                                                    C.byref(c_rec), n, _lib.TF_NO_FINAL, _ptr(status), C.c_void_p(stream))
     _lib.check(rc, f"olb_trace_pupil_{sfx}")
+    _raise_status(status)
     rays = RealRays.__new__(RealRays)
     rays.x, rays.y, rays.z = recs["x"][-1], recs["y"][-1], recs["z"][-1]
     rays.L, rays.M, rays.N = recs["L"][-1], recs["M"][-1], recs["N"][-1]
@@ -259,11 +314,51 @@ def trace_pupil_device(dtab: DeviceTable, Px: torch.Tensor, Py: torch.Tensor, af
     return rays, recs
 
 
+def _trace_pupil_polarized(dtab, Px, Py, affine, first, last, wavelength, polarization):
+    lib = dtab.lib
+    n = Px.numel()
+    dtype = Px.dtype
+    sfx = _DTYPES[dtype]
+    rows = last - first
+    vec = 4 if dtype == torch.float32 else 2
+    stride = (n + 63) // 64 * 64 if n % vec else n
+    buf = torch.empty((8, rows, stride), dtype=dtype, device=Px.device)
+    recs = {k: buf[j, :, :n] for j, k in enumerate(_REC_KEYS)}
+    c_rec = _lib.OlbRecords(*[buf[j].data_ptr() for j in range(8)], stride)
+    la = _c_launch(affine, Px.contiguous(), Py.contiguous())
+    cdt = torch.complex64 if dtype == torch.float32 else torch.complex128
+    p = torch.empty((n, 3, 3), dtype=cdt, device=Px.device)
+    out = _lib.OlbRays(w=wavelength.data_ptr() if (wavelength is not None and dtab.table.n_wl > 1) else None,
+                       p=torch.view_as_real(p).data_ptr())
+    inten, c_pol = None, None
+    if polarization != "matrix":
+        inten = torch.empty(n, dtype=dtype, device=Px.device)
+        c_pol = _c_polarization(polarization, inten)
+    status = _status_word(dtab, Px.device, force=c_pol is not None)
+    with torch.cuda.device(Px.device):
+        stream = torch.cuda.current_stream(Px.device).cuda_stream
+        rc = getattr(lib, f"olb_trace_polarized_{sfx}")(
+            C.byref(dtab.c), first, last, C.byref(la), C.byref(out), C.byref(c_rec), n, _lib.TF_NO_FINAL,
+            C.byref(c_pol) if c_pol is not None else None, None, None, _ptr(status), C.c_void_p(stream))
+    _lib.check(rc, f"olb_trace_polarized_{sfx}")
+    _raise_status(status)
+    rays = PolarizedRays.__new__(PolarizedRays)
+    rays.x, rays.y, rays.z = recs["x"][-1], recs["y"][-1], recs["z"][-1]
+    rays.L, rays.M, rays.N = recs["L"][-1], recs["M"][-1], recs["N"][-1]
+    rays.i = inten if inten is not None else recs["intensity"][-1]
+    rays.opd = recs["opd"][-1]
+    rays.w = wavelength
+    rays.p = p
+    rays.L0 = rays.M0 = rays.N0 = None
+    rays.is_normalized = True
+    return rays, recs
+
+
 WAVEFRONT_KEYS = ("opd", "pupil_x", "pupil_y", "pupil_z", "intensity")
 
 
 def trace_wavefront_device(dtab: DeviceTable, Px: torch.Tensor, Py: torch.Tensor, affine: dict, ref: dict,
-                           wavelength: torch.Tensor | None = None) -> dict:
+                           wavelength: torch.Tensor | None = None, polarization=False) -> dict:
     """olb_trace_wavefront_*: trace one field's pupil grid and write ONLY the wavefront data -- OPD in waves
     against the spherical reference ``ref`` = {center (3), radius, n_image, tilt (2), opd_ref, wavelength_um},
     the exit-pupil intercepts and the image-surface intensity -- no records, no final state
@@ -283,23 +378,40 @@ def trace_wavefront_device(dtab: DeviceTable, Px: torch.Tensor, Py: torch.Tensor
     c_ref.opd_ref, c_ref.wavelength_um = float(ref["opd_ref"]), float(ref["wavelength_um"])
     la = _c_launch(affine, Px.contiguous(), Py.contiguous())
     rays = _lib.OlbRays(w=wavelength.data_ptr() if (wavelength is not None and dtab.table.n_wl > 1) else None)
+    polarized = polarization is not False
+    status = _status_word(dtab, Px.device, force=polarized)
     with torch.cuda.device(Px.device):
         stream = torch.cuda.current_stream(Px.device).cuda_stream
-        rc = getattr(lib, f"olb_trace_wavefront_{sfx}")(
-            C.byref(dtab.c), 0, dtab.table.num_surfaces, C.byref(la), C.byref(rays), None, n, _lib.TF_NO_FINAL,
-            C.byref(c_ref), C.byref(c_out), None, C.c_void_p(stream))
+        if polarized:
+            # PolarizedRays through the wavefront epilogue (config 5): the P matrices never leave the SM; the
+            # `intensity` output is PolarizedRays.update_intensity's value (what the reference's strategy reads)
+            c_pol = _c_polarization(polarization)
+            rc = getattr(lib, f"olb_trace_polarized_{sfx}")(
+                C.byref(dtab.c), 0, dtab.table.num_surfaces, C.byref(la), C.byref(rays), None, n, _lib.TF_NO_FINAL,
+                C.byref(c_pol), C.byref(c_ref), C.byref(c_out), _ptr(status), C.c_void_p(stream))
+        else:
+            rc = getattr(lib, f"olb_trace_wavefront_{sfx}")(
+                C.byref(dtab.c), 0, dtab.table.num_surfaces, C.byref(la), C.byref(rays), None, n, _lib.TF_NO_FINAL,
+                C.byref(c_ref), C.byref(c_out), _ptr(status), C.c_void_p(stream))
     _lib.check(rc, f"olb_trace_wavefront_{sfx}")
+    _raise_status(status)
     return {k: buf[j, :n] for j, k in enumerate(WAVEFRONT_KEYS)}
 
 
 def trace_moments_device(dtab: DeviceTable, n: int, dtype, rays: RealRays | None = None, pupil=None,
-                         center=(0.0, 0.0), moments: torch.Tensor | None = None, wavelength=None) -> torch.Tensor:
+                         center=(0.0, 0.0), moments: torch.Tensor | None = None, wavelength=None,
+                         status: torch.Tensor | None = None) -> torch.Tensor:
     """olb_trace_moments_*: trace WITHOUT writing any per-ray output and accumulate the spot / OPD moments
     of the image-surface intercepts in-kernel (8 fp64 values on the device; see include/olb.h).  Either
-    ``rays`` (launch-state arrays, left untouched) or ``pupil`` = (Px, Py, affine)."""
+    ``rays`` (launch-state arrays, left untouched) or ``pupil`` = (Px, Py, affine).  ``status``: a caller-owned
+    device int32 for the OLB_ST_* bits (a caller that pipelines several launches checks it once at the end with
+    ``_raise_status``); by default one is made and checked here for tables that can raise them."""
     lib = dtab.lib
     sfx = _DTYPES[dtype]
     dev = dtab.device
+    own_status = status is None
+    if own_status:
+        status = _status_word(dtab, dev)
     if moments is None:
         moments = torch.zeros(8, dtype=torch.float64, device=dev)
     la = None
@@ -320,8 +432,10 @@ def trace_moments_device(dtab: DeviceTable, n: int, dtype, rays: RealRays | None
         stream = torch.cuda.current_stream(dev).cuda_stream
         rc = getattr(lib, f"olb_trace_moments_{sfx}")(
             C.byref(dtab.c), 0, dtab.table.num_surfaces, C.byref(la) if la is not None else None, C.byref(c_rays), None,
-            n, _lib.TF_NO_FINAL, cen, C.c_void_p(moments.data_ptr()), None, C.c_void_p(stream))
+            n, _lib.TF_NO_FINAL, cen, C.c_void_p(moments.data_ptr()), _ptr(status), C.c_void_p(stream))
     _lib.check(rc, f"olb_trace_moments_{sfx}")
+    if own_status:
+        _raise_status(status)
     return moments
 
 

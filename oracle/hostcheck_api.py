@@ -99,3 +99,29 @@ def run_wavefront(hc, fin: dict, Px, Py, ref: dict) -> dict:
                             C.c_void_p(py.ctypes.data), C.c_void_p(r.ctypes.data), (C.c_void_p * 4)(*[a.ctypes.data for a in out]))
     assert rc == 0
     return dict(zip(("opd", "pupil_x", "pupil_y", "pupil_z"), out))
+
+
+def run_pol_intensity(hc, P, k0, i0, state=None):
+    """olb_math.cuh::polarized_intensity (the polarized kernels' intensity epilogue) on the CPU.  ``P``: (n, 3, 3)
+    complex, ``k0``: (3, n) launch direction, ``state``: None (unpolarized) or (Ex, Ey, phase_x, phase_y)."""
+    n = P.shape[0]
+    pm = np.ascontiguousarray(P, dtype=np.complex128).view(np.float64).reshape(n, 18)
+    kx, ky, kz = (np.ascontiguousarray(v, dtype=np.float64) for v in k0)
+    i0 = np.ascontiguousarray(i0, dtype=np.float64)
+    out = np.empty(n)
+    if state is None:
+        mode, ax, ay = 2, np.zeros(2), np.zeros(2)
+    else:
+        Ex, Ey, phx, phy = state
+        mag = np.hypot(Ex, Ey)
+        mode = 1
+        ax = np.array([Ex / mag * np.cos(phx), Ex / mag * np.sin(phx)])
+        ay = np.array([Ey / mag * np.cos(phy), Ey / mag * np.sin(phy)])
+    status = C.c_int(0)
+    hc.olbhc_pol_intensity.restype = C.c_int
+    rc = hc.olbhc_pol_intensity(C.c_int64(n), C.c_void_p(pm.ctypes.data), C.c_void_p(kx.ctypes.data),
+                                C.c_void_p(ky.ctypes.data), C.c_void_p(kz.ctypes.data), C.c_void_p(i0.ctypes.data),
+                                C.c_int(mode), C.c_void_p(ax.ctypes.data), C.c_void_p(ay.ctypes.data),
+                                C.c_void_p(out.ctypes.data), C.byref(status))
+    assert rc == 0
+    return out, status.value

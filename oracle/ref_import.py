@@ -5,9 +5,11 @@ seaborn at module import time on the trace path
 (``optiland/backend/numpy_backend.py:13``, ``optiland/physical_apertures/base.py:18``),
 none of which is installed in this image.  ``import_reference()`` installs a
 ``sys.meta_path`` finder that serves inert stub modules for those plotting
-packages and puts the reference on ``sys.path``.  Nothing of the reference is
-copied.  The reference does not exist on the GPU box, so this helper is used
-only by ``oracle/make_golden.py`` and by CPU tests that skip when it is absent.
+packages and puts the reference on ``sys.path``.  Nothing of the reference enters the
+repository's history.  ``/root/reference`` does not exist on the GPU box; ``scripts/make_ref.sh`` stages
+an unmodified copy under ``oracle/_ref/`` (git-ignored, shipped by gpurun), which is what this helper
+finds there.  Used by ``oracle/make_golden.py``, the plugin tests (CPU: oracle engine; ``-m gpu``: the real
+CUDA engine under live Optiland objects) and ``bench.py``'s reference arm / ``e2e_optic_trace`` key.
 """
 from __future__ import annotations
 
@@ -18,7 +20,21 @@ import sys
 import types
 from unittest import mock
 
-REFERENCE_ROOT = os.environ.get("OPTILAND_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root() -> str:
+    env = os.environ.get("OPTILAND_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", os.path.join(_HERE, "_ref")):
+        if os.path.isdir(os.path.join(cand, "optiland")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
+REFERENCE_TESTS = os.path.join(REFERENCE_ROOT, "tests")
 _STUB_ROOTS = ("matplotlib", "mpl_toolkits", "vtk", "vtkmodules", "seaborn")
 
 

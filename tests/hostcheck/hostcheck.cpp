@@ -144,6 +144,16 @@ int olbhc_trace_f32(const OlbTable* tab, int first, int last, int64_t n, float**
                     float* pmat, int* status, char* err, int err_len) {
   return run<float>(tab, first, last, n, ray, rec, l0, pmat, status, err, err_len);
 }
+// intensity epilogue of the polarized kernels (olb_math.cuh::polarized_intensity) over n rays: pmat = [n][18],
+// k = launch direction (3 arrays), i0, mode 1 (one state, ax / ay complex amplitudes) or 2 (unpolarized)
+int olbhc_pol_intensity(int64_t n, const double* pmat, const double* kx, const double* ky, const double* kz,
+                        const double* i0, int mode, const double* ax, const double* ay, double* out, int* status) {
+  int st = 0;
+  for (int64_t k = 0; k < n; ++k)
+    out[k] = polarized_intensity<double>(pmat + k * 18, 1, kx[k], ky[k], kz[k], i0[k], mode, ax, ay, st);
+  *status = st;
+  return 0;
+}
 // wavefront epilogue (olb_math.cuh::wavefront_point) over n rays: fin = x y z L M N opd (fp64), ref = the 9
 // doubles of WavefrontRef, out = opd_wv, pupil_x, pupil_y, pupil_z
 int olbhc_wavefront(int64_t n, double** fin, const double* Px, const double* Py, const double* ref, double** out) {

@@ -201,6 +201,50 @@ def test_random_polarized_systems_host_math_vs_oracle(hc, seed):
 
 
 @pytest.mark.parametrize("seed", range(8))
+def test_random_polarized_systems_with_mixed_coatings(hc, seed):
+    """Polarized rays through systems that MIX coatings: none (rays.update() with the identity Jones matrix), Fresnel
+    (update with the Fresnel Jones matrix) and SimpleCoating, which only scales the intensity and never reaches
+    rays.update() (interactions/base.py:119-128) -- the P matrix must skip that surface."""
+    import dataclasses
+
+    rng = np.random.default_rng(7700 + seed)
+    base = random_system(rng, int(rng.integers(4, 8)))
+    specs, kinds = [], []
+    for j, s in enumerate(base.surfaces):
+        ch = {k: getattr(s, k)[:1].copy() for k in ("n1", "n2", "k1")}
+        if s.kind != T.GEOM_NOOP:
+            pick = (j + seed) % 3
+            if pick == 0:
+                ch.update(coating=T.COAT_FRESNEL, coat_n1=ch["n1"].copy(), coat_n2=ch["n2"].copy(), coat_t=1.0, coat_r=0.0)
+            elif pick == 1:
+                ch.update(coating=T.COAT_SIMPLE, coat_t=0.9, coat_r=0.8)
+            else:
+                ch.update(coating=T.COAT_NONE, coat_t=1.0, coat_r=0.0)
+            kinds.append(pick)
+            if s.kind in (T.GEOM_ODD_ASPHERE, T.GEOM_POLYNOMIAL, T.GEOM_EVEN_ASPHERE):
+                ch["tol"] = 1e-12
+            if s.kind != T.GEOM_PLANE and not s.reflective and float(ch["n1"][0]) == float(ch["n2"][0]):
+                ch.update(kind=T.GEOM_PLANE, coefficients=np.zeros(0), radius=float("inf"), conic=0.0)
+        specs.append(dataclasses.replace(s, **ch))
+    assert 1 in kinds
+    table = T.SurfaceTable(specs, base.wavelengths[:1])
+    n = 48
+    x, y = rng.uniform(-4, 4, n), rng.uniform(-4, 4, n)
+    L, M = rng.normal(0, 0.05, n), rng.normal(0, 0.05, n)
+    rays = dict(x=x, y=y, z=np.full(n, -5.0), L=L, M=M, N=np.sqrt(1 - L**2 - M**2), i=np.ones(n),
+                w=np.full(n, table.wavelengths[0]))
+    p0 = np.tile(np.eye(3, dtype=np.complex128), (n, 1, 1))
+    oout, orec, _ = O.trace(table, dict(rays, p=p0.copy()), polarized=True)
+    out, rec, st = run_hostcheck(hc, table, rays, np.float64, pmat=p0)
+    fin = np.isfinite(oout["p"]).all(axis=(1, 2))
+    assert fin.sum() > n // 2
+    assert np.array_equal(np.isfinite(out["p"]).all(axis=(1, 2)), fin)
+    assert np.max(np.abs(out["p"][fin] - oout["p"][fin])) <= 1e-10, (seed, float(np.max(np.abs(out["p"][fin] - oout["p"][fin]))))
+    m = np.isfinite(orec["intensity"])
+    assert np.max(np.abs(rec["intensity"][m] - orec["intensity"][m])) <= 1e-12
+
+
+@pytest.mark.parametrize("seed", range(8))
 def test_random_systems_adjoint_vs_finite_differences(hc, seed):
     """The adjoint (olb_math.cuh::surface_backward on the host) on random plane / conic / even- and odd-asphere
     systems with tilts, decenters, mirrors, aperture trees, simple coatings and absorbing media: launch-state and

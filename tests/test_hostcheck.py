@@ -141,3 +141,28 @@ def test_device_math_polarized_vs_reference(hc, name, dtype):
     for k in ("x", "y", "opd"):
         assert max_abs_err(rec[k], c.rec[k]) <= tol, k
     assert np.max(np.abs(out["p"] - c.out["p"])) <= ptol
+
+
+@pytest.mark.parametrize("name", ["zernike_polarized_c5", "cooke_polarized", "tilted_fold_polarized"])
+def test_device_math_polarized_intensity_epilogue(hc, name):
+    """PolarizedRays.update_intensity as the kernels evaluate it (olb_math.cuh::polarized_intensity) against the
+    reference's value (fixture) and the oracle, for the fixture's own state and for a second, elliptical one."""
+    from oracle import trace_oracle as O
+    from oracle.hostcheck_api import run_pol_intensity
+    from tests._util import Case as _Case
+
+    c = _Case(name)
+    P, k0, i0 = c.out["p"], c.extra("k0"), c.extra("i0")
+    state = tuple(c.extra("state")) if "x_state" in c.z else None
+    want = c.extra("final_intensity") if state is not None else c.extra("final_intensity_unpolarized")
+    got, st = run_pol_intensity(hc, P, k0, i0, state)
+    assert st == 0 and np.max(np.abs(got - want)) <= 1e-13
+    for other in ((0.3, 1.0, 0.7, -0.4), None):
+        got, _ = run_pol_intensity(hc, P, k0, i0, other)
+        mag = np.hypot(other[0], other[1]) if other else 1.0
+        want = O.polarized_intensity(P, k0[0], k0[1], k0[2], i0, (other[0] / mag, other[1] / mag, other[2], other[3]) if other else None)
+        assert np.max(np.abs(got - want)) <= 1e-13
+    # a launch direction along x: the reference raises, the kernel sets a status bit
+    kx = np.array([[1.0], [0.0], [0.0]])
+    _, st = run_pol_intensity(hc, P[:1], kx, i0[:1], None)
+    assert st & T.ST_K_PARALLEL_X

@@ -1,10 +1,13 @@
-"""Host logic of the Optiland plugin (backend registration, SurfaceGroup.trace / Surface.trace
-wrappers, packing of LIVE reference objects, record hand-back, declining) exercised against the
-unmodified reference.  Runs only where /root/reference exists (the build container).
+"""The Optiland plugin (backend registration, RealRayTracer / SurfaceGroup.trace / Surface.trace wrappers, packing of
+LIVE reference objects, record hand-back, autograd, declining) exercised against the unmodified reference: the build
+container's /root/reference, or the copy scripts/make_ref.sh stages under oracle/_ref/ for the GPU box.
 
-There is no GPU here, so the device call is replaced by a TEST-ONLY engine that evaluates the
-packed table with the NumPy oracle; everything else is the product code path.  The same packed
-tables run on the real kernel in tests/test_gpu_parity.py.
+Every test runs twice:
+* ``[oracle]`` (CPU, ``-m "not gpu"``): there is no GPU in the build container, so the device call is replaced by a
+  TEST-ONLY engine that evaluates the packed table with the NumPy oracle; everything else is the product code path;
+* ``[cuda]`` (``-m gpu``, on the B200): the PRODUCT engine (``plugin.CudaEngine`` -> libolb.so) under
+  ``be.set_device("cuda")`` with live Optiland objects -- ``Optic.trace``, ``SpotDiagram``, ``Wavefront``, the
+  optimiser's autograd step and the aimers call the CUDA kernels unchanged, compared with the reference's NumPy path.
 """
 import numpy as np
 import pytest
@@ -17,21 +20,33 @@ pytestmark = pytest.mark.skipif(not reference_available(), reason="reference not
 from oracle.oracle_engine import OracleEngine  # noqa: E402
 
 
-@pytest.fixture()
-def plugin():
+@pytest.fixture(params=["oracle", pytest.param("cuda", marks=pytest.mark.gpu)])
+def plugin(request):
     from oracle.ref_import import import_reference
 
     import_reference()
     import optiland.backend as be
 
+    from optiland_b200 import _lib
     from optiland_b200 import plugin as P
 
     be.set_backend("torch")
     be.set_precision("float64")
     be.grad_mode.disable()
-    eng = OracleEngine()
+    launches0 = 0
+    if request.param == "cuda":
+        be.set_device("cuda")
+        eng = P.CudaEngine()
+        launches0 = _lib.load().olb_launch_count()
+    else:
+        eng = OracleEngine()
     P.install(engine=eng)
+    P.stats(reset=True)
     yield P, eng, be
+    if request.param == "cuda":
+        # the calls the test counted really were kernel launches of libolb.so
+        assert not eng.calls or _lib.load().olb_launch_count() > launches0
+        be.set_device("cpu")
     P.uninstall()
     be.set_backend("numpy")
 
@@ -306,7 +321,7 @@ def test_polarized_trace_with_fresnel_coatings(plugin):
     rays = trace(lens)
     assert len(eng.calls) == n0 + 1 and type(rays).__name__ == "PolarizedRays"
     np.testing.assert_allclose(be.to_numpy(rays.i), ref_i, atol=1e-12)
-    np.testing.assert_allclose(rays.p.detach().numpy(), ref_p, atol=1e-12)
+    np.testing.assert_allclose(rays.p.detach().cpu().numpy(), ref_p, atol=1e-12)
     assert float(ref_i.max()) < 0.8  # Fresnel losses really applied
 
 

@@ -19,18 +19,24 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 FILES = ["test_surface_group.py", "test_wavefront.py", "analysis/test_spot_reference.py"]  # scripts/ref_sweep.sh: all
 
 
-def _run(fname, install, nograd=False):
+def _run(fname, install, nograd=False, cuda=False, with_ids=False):
+    from oracle.ref_import import REFERENCE_TESTS
+
     env = dict(os.environ, OLB_SWEEP_INSTALL="1" if install else "0", PYTHONPATH=ROOT,
-               OLB_SWEEP_NOGRAD="1" if nograd else "0")
+               OLB_SWEEP_NOGRAD="1" if nograd else "0", OLB_SWEEP_DEVICE="cuda" if cuda else "cpu")
     os.makedirs("/tmp/olb_sweep_root", exist_ok=True)
     out = subprocess.run(
         [sys.executable, "-m", "pytest", "-p", "oracle.sweep_plugin", "-p", "no:cacheprovider", "-q", "--no-header",
-         "--rootdir=/tmp/olb_sweep_root", "-c", "/dev/null", f"/root/reference/tests/{fname}",
+         "-rfE", "--rootdir=/tmp/olb_sweep_root", "-c", "/dev/null", os.path.join(REFERENCE_TESTS, fname),
          "-k", "torch and not view and not draw and not plot"],
-        cwd="/tmp/olb_sweep_root", env=env, capture_output=True, text=True, timeout=600).stdout
+        cwd="/tmp/olb_sweep_root", env=env, capture_output=True, text=True, timeout=1500).stdout
     counts = {k: int(v) for v, k in re.findall(r"(\d+) (passed|failed|error)", out)}
     calls = re.search(r"capability calls: (\d+) \(differentiable: (\d+), fused launch: (\d+)\)", out)
-    return counts, tuple(int(v) for v in calls.groups()) if calls else (0, 0, 0)
+    calls = tuple(int(v) for v in calls.groups()) if calls else (0, 0, 0)
+    if with_ids:
+        bad = sorted(set(re.findall(r"^(?:FAILED|ERROR) (\S+)", out, flags=re.M)))
+        return counts, calls, bad, out
+    return counts, calls
 
 
 @pytest.mark.timeout(900)
@@ -53,3 +59,33 @@ def test_reference_tests_unchanged_with_plugin_grad_mode_off(fname):
     ours, calls = _run(fname, install=True, nograd=True)
     assert stock.get("passed", 0) > 0 and ours == stock, (fname, stock, ours)
     assert calls[1] == 0 and calls[2] > 0, calls
+
+
+GPU_FILES = ["test_surface_group.py", "test_wavefront.py", "analysis/test_spot_reference.py", "test_analysis.py",
+             "test_operand.py", "test_torch_optimization.py", "test_tolerancing.py"]
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(3000)
+@pytest.mark.parametrize("nograd", [False, True], ids=["grad_on", "grad_off"])
+@pytest.mark.parametrize("fname", GPU_FILES)
+def test_reference_tests_unchanged_with_cuda_engine(fname, nograd):
+    """ON THE B200: the reference's own test files with the torch backend moved to the GPU, stock vs. plugin installed
+    over the PRODUCT engine (CudaEngine -> libolb.so).  Same set of passing tests (the reference's goldens hold through
+    the kernels), and the capability really carried the calls.  (The stock arm itself fails a few tests on a CUDA
+    device -- the reference's tests convert tensors with np.asarray -- which is why the SETS are compared.)"""
+    stock, _, bad_stock, _ = _run(fname, install=False, nograd=nograd, cuda=True, with_ids=True)
+    ours, calls, bad_ours, log = _run(fname, install=True, nograd=nograd, cuda=True, with_ids=True)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "ref_sweep_cuda.txt"), "a") as f:
+        f.write(f"{fname} nograd={int(nograd)}: stock {stock} | plugin {ours} | capability calls {calls}\n")
+        for line in log.splitlines():
+            if line.startswith("[olb sweep]"):
+                f.write("    " + line + "\n")
+        if set(bad_ours) != set(bad_stock):
+            f.write(f"    only failing with the plugin: {sorted(set(bad_ours) - set(bad_stock))}\n")
+            f.write(f"    only failing stock: {sorted(set(bad_stock) - set(bad_ours))}\n")
+    assert stock.get("passed", 0) > 0, stock
+    assert set(bad_ours) <= set(bad_stock), sorted(set(bad_ours) - set(bad_stock))
+    assert ours.get("passed", 0) >= stock.get("passed", 0)
+    assert calls[0] > 0, "the capability was never exercised"
