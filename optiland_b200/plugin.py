@@ -51,6 +51,13 @@ def _decline(reason: str):
     return False
 
 
+def _fused_decline(reason: str):
+    """A fused entry point (Optic.trace / trace_generic / Wavefront) hands the call to the next level down -- the
+    reference's RayGenerator followed by the SurfaceGroup.trace capability -- and says why (``stats()``)."""
+    _decline("fused launch: " + reason)
+    return None
+
+
 def stats(reset: bool = False) -> dict:
     """{reason: count} of the calls the capability declined since install / the last reset --
     the answer to "why was my trace not accelerated?"."""
@@ -144,10 +151,12 @@ class CudaEngine:
 
         return torch.is_tensor(t) and t.is_cuda and t.dtype in (torch.float32, torch.float64) and t.ndim == 1
 
-    def trace_pupil(self, table: T.SurfaceTable, Px, Py, affine: dict, wavelength=None):
+    def trace_pupil(self, table: T.SurfaceTable, Px, Py, affine: dict, wavelength=None, polarization=False):
         """Launch state generated in-kernel from the pupil samples (olb_trace_pupil_*; with ``affine["fields"]``
         also from per-ray field points).  ``wavelength``: per-ray array for a multi-wavelength table.  Returns the
-        record dict; the final state is its last row."""
+        record dict; the final state is its last row.  ``polarization``: False, or the optic's polarization state
+        (None = unpolarized, or (Ex, Ey, phase_x, phase_y)) -- PolarizedRays are traced (olb_trace_polarized_*) and
+        the dict also holds ``"p"`` (the (N, 3, 3) complex matrices) and ``"i_pol"`` (update_intensity's result)."""
         from .trace import trace_pupil_device
 
         dt = self.device_table(table, Px.device)
@@ -155,17 +164,20 @@ class CudaEngine:
             affine = dict(affine, fields=tuple(_dev_array(t) for t in affine["fields"]))
         w = _dev_array(wavelength) if wavelength is not None else None
         self._note("pupil", table.num_surfaces, int(Px.numel()))
-        _, rec = trace_pupil_device(dt, _dev_array(Px), _dev_array(Py), affine, 0, table.num_surfaces, wavelength=w)
+        rays, rec = trace_pupil_device(dt, _dev_array(Px), _dev_array(Py), affine, 0, table.num_surfaces, wavelength=w,
+                                       polarization=polarization)
+        if polarization is not False:
+            rec = dict(rec, p=rays.p, i_pol=rays.i)
         return rec
 
-    def trace_wavefront(self, table: T.SurfaceTable, Px, Py, affine: dict, ref: dict) -> dict:
+    def trace_wavefront(self, table: T.SurfaceTable, Px, Py, affine: dict, ref: dict, polarized: bool = False) -> dict:
         """One field's pupil grid -> OPD map + exit-pupil intercepts + intensity, nothing else written
-        (olb_trace_wavefront_*)."""
+        (olb_trace_wavefront_*); ``polarized``: PolarizedRays, the result also holds the P matrices ``"p"``."""
         from .trace import trace_wavefront_device
 
         dt = self.device_table(table, Px.device)
         self._note("wavefront", table.num_surfaces, int(Px.numel()))
-        return trace_wavefront_device(dt, _dev_array(Px), _dev_array(Py), affine, ref)
+        return trace_wavefront_device(dt, _dev_array(Px), _dev_array(Py), affine, ref, polarized=polarized)
 
     def huygens_psf(self, image_x, image_y, image_z, pupil_x, pupil_y, pupil_z, pupil_amp, pupil_opd, wavelength, Rp):
         """Huygens-Fresnel summation on the GPU (olb_huygens_psf_f64); None to decline (CPU tensors)."""
@@ -277,6 +289,44 @@ def _tail_propagate(be, rays, last_surface, wavelengths, w=None) -> None:
             rays.i = rays.i * be.exp(-(4 * np.pi * k / w) * t * 1e3)
     if not rays.is_normalized:
         rays.normalize()
+
+
+def _pol_state(be, optic):
+    """(polarized, state) of ``optic.polarization`` (optic/optic.py:189-207): (False, False) for "ignore";
+    (True, None) for unpolarized light; (True, (Ex, Ey, phase_x, phase_y)) for a polarized state."""
+    if optic.polarization == "ignore":
+        return False, False
+    st = optic.polarization_state
+    if not st.is_polarized:
+        return True, None
+
+    def f(v):
+        return float(np.asarray(be.to_numpy(v)).reshape(-1)[0])
+
+    return True, (f(st.Ex), f(st.Ey), f(st.phase_x), f(st.phase_y))
+
+
+def _make_rays(be, rec, wl_arr, polarized: bool):
+    """The reference's ray object for a fused launch: ``RealRays``, or ``PolarizedRays`` carrying the kernel's P
+    matrices, the updated intensity and the launch state update_intensity / get_exit_fields refer to
+    (rays/polarized_rays.py:47-55; record row 0 is the object surface's record of the launch state)."""
+    from optiland.rays import PolarizedRays, RealRays
+
+    if not polarized:
+        rays = RealRays(rec["x"][-1], rec["y"][-1], rec["z"][-1], rec["L"][-1], rec["M"][-1], rec["N"][-1],
+                        rec["intensity"][-1], wl_arr)
+        rays.opd = rec["opd"][-1]
+        return rays
+    rays = PolarizedRays.__new__(PolarizedRays)      # (its __init__ would tile an (N, 3, 3) identity first)
+    rays.x, rays.y, rays.z = rec["x"][-1], rec["y"][-1], rec["z"][-1]
+    rays.L, rays.M, rays.N = rec["L"][-1], rec["M"][-1], rec["N"][-1]
+    rays.i, rays.w, rays.opd = rec["i_pol"], wl_arr, rec["opd"][-1]
+    rays.p = rec["p"]
+    rays._i0 = rec["intensity"][0]
+    rays._L0, rays._M0, rays._N0 = rec["L"][0], rec["M"][0], rec["N"][0]
+    rays.L0 = rays.M0 = rays.N0 = None
+    rays.is_normalized = True
+    return rays
 
 
 def _live_params(surfaces, table, wavelength):
@@ -453,13 +503,13 @@ def install(engine=None, alias: str | None = None) -> None:
 
         def trace_optic(self, tracer, Hx, Hy, wavelength, num_rays, distribution):
             """``RealRayTracer.trace`` for ONE field with the launch state generated on the device
-            (SURVEY.md 8f-1): returns the traced ``RealRays`` or None to decline.  Covers what
+            (SURVEY.md 8f-1): returns the traced rays or None to decline.  Covers what
             ``RayGenerator.generate_rays`` + ``ParaxialRayAimer`` + ``field_definition.get_ray_origins`` do for one
             field point (infinite-object angle field, finite object with an object-height / angle field,
-            object-space telecentric system) without apodization / polarization."""
+            object-space telecentric system) without apodization; with ``optic.polarization`` set the rays are
+            ``PolarizedRays`` (Fresnel coatings included) and ``update_intensity`` runs as the kernel's epilogue."""
             import numpy as _np
             from optiland.distribution import create_distribution
-            from optiland.rays import RealRays
 
             from .launch import pupil_affine
             from .pack import launch_scalars
@@ -472,12 +522,14 @@ def install(engine=None, alias: str | None = None) -> None:
                     float(_np.asarray(be.to_numpy(be.atleast_1d(Hy))).reshape(-1)[0])
                 single = be.size(be.atleast_1d(Hx)) == 1 and be.size(be.atleast_1d(Hy)) == 1
             except Exception:
-                return None
-            if not single or optic.polarization != "ignore" or optic.apodization:
-                return None
+                return _fused_decline("field coordinates are not plain numbers")
+            if not single:
+                return _fused_decline("several field points in one Optic.trace call")
+            if optic.apodization:
+                return _fused_decline("apodization")
             # the aimer is (re)configured lazily inside generate_rays from this dict (ray_generator.py:67-71)
             if getattr(tracer, "ray_aiming_config", {}).get("mode", "paraxial") != "paraxial":
-                return None
+                return _fused_decline("non-paraxial ray aiming")
             tracer._validate_normalized_coordinates(Hx, Hy, "field")
             if isinstance(distribution, str):
                 distribution = create_distribution(distribution)
@@ -485,37 +537,42 @@ def install(engine=None, alias: str | None = None) -> None:
             Px, Py = distribution.x, distribution.y
             engine = _state["engine"]
             if not (engine.accepts_tensor(Px) and engine.accepts_tensor(Py)):
-                return None
+                return _fused_decline("pupil samples not resident on a CUDA device (or not fp32/fp64)")
+            polarized, state = _pol_state(be, optic)
             try:
                 sc = launch_scalars(optic, hx, hy)
                 table = pack_surface_group(optic.surfaces, [float(wavelength)])
                 _prepare(engine, table, Px.device)
             except _PACK_ERRORS as e:
-                _decline(f"fused launch unsupported: {e}")
-                return None
-            if any(s.coating == T.COAT_FRESNEL for s in table.surfaces):
-                return None
-            rec = engine.trace_pupil(table, Px, Py, pupil_affine(sc))
+                return _fused_decline(f"unsupported: {e}")
+            if not polarized and any(s.coating == T.COAT_FRESNEL for s in table.surfaces):
+                return None          # the reference raises for this combination (ray_generator.py:90-94)
+            if table.surfaces[0].kind != T.GEOM_NOOP:
+                return _fused_decline("first surface is not an object surface")
+            rec = engine.trace_pupil(table, Px, Py, pupil_affine(sc), polarization=state) if polarized else \
+                engine.trace_pupil(table, Px, Py, pupil_affine(sc))
             optic.surfaces.reset()
             for row, surf in enumerate(optic.surfaces.surfaces):
                 for attr, key in _REC_ATTR:
                     setattr(surf, attr, rec[key][row])
-            rays = RealRays(rec["x"][-1], rec["y"][-1], rec["z"][-1], rec["L"][-1], rec["M"][-1], rec["N"][-1],
-                            rec["intensity"][-1], be.ones_like(rec["x"][-1]) * wavelength)
-            rays.opd = rec["opd"][-1]
+            rays = _make_rays(be, rec, be.ones_like(rec["x"][-1]) * wavelength, polarized)
             _set_pre_interaction_direction(rays, table, rec, 0, table.num_surfaces,
                                            (rec["L"][0], rec["M"][0], rec["N"][0]))
-            # tail of RealRayTracer.trace (raytrace/real_ray_tracer.py:105-118)
+            # tail of RealRayTracer.trace (raytrace/real_ray_tracer.py:105-118); update_intensity already ran in-kernel
+            # (it overwrites rays.i from P and the launch intensity alone, so the order with the propagate is immaterial
+            # unless the image space absorbs -- then the reference's own order is restored below)
             if optic.image_surface:
+                i_before = rays.i
                 _tail_propagate(be, rays, optic.surfaces[-1], [float(wavelength)])
+                if polarized and rays.i is not i_before:
+                    rays.i = i_before
             return rays
 
         def trace_optic_generic(self, tracer, Hx, Hy, Px, Py, wavelength):
             """``RealRayTracer.trace_generic`` (raytrace/real_ray_tracer.py:120-154) for per-ray (Hx, Hy, Px, Py[, lambda])
-            arrays with the launch state generated on the device.  Needs the paraxial aimer and no apodization /
-            polarization.  Returns the traced ``RealRays`` or None to decline."""
+            arrays with the launch state generated on the device.  Needs the paraxial aimer and no apodization;
+            ``optic.polarization`` set -> ``PolarizedRays`` (config 5's call shape).  Returns the traced rays or None."""
             import numpy as _np
-            from optiland.rays import RealRays
 
             from .launch import pupil_affine_fields
             from .pack import launch_scalars
@@ -524,15 +581,15 @@ def install(engine=None, alias: str | None = None) -> None:
             engine = _state["engine"]
             if getattr(_tls, "in_reference", False) or _wants_grad(self, list(optic.surfaces.surfaces)):
                 return None
-            if optic.polarization != "ignore" or optic.apodization:
-                return None
+            if optic.apodization:
+                return _fused_decline("apodization")
             if getattr(tracer, "ray_aiming_config", {}).get("mode", "paraxial") != "paraxial":
-                return None
+                return _fused_decline("non-paraxial ray aiming")
             try:
                 has_vig = bool(_np.any(_np.asarray(be.to_numpy(optic.fields.vx)) != 0)
                                or _np.any(_np.asarray(be.to_numpy(optic.fields.vy)) != 0))
             except Exception:
-                return None
+                return _fused_decline("vignetting factors are not plain numbers")
             tracer._validate_normalized_coordinates(Hx, Hy, "field")
             tracer._validate_normalized_coordinates(Px, Py, "pupil")
             if has_vig:
@@ -544,44 +601,45 @@ def install(engine=None, alias: str | None = None) -> None:
                 Py = Py * (1 - vyf) * (1 - vyf)
             Hx, Hy, Px, Py = tracer._validate_array_size(Hx, Hy, Px, Py)
             if not all(engine.accepts_tensor(t) for t in (Hx, Hy, Px, Py)) or len({t.shape for t in (Hx, Hy, Px, Py)}) != 1:
-                return None
+                return _fused_decline("field / pupil arrays not resident on a CUDA device (or of different shapes)")
             if any(t.dtype != Px.dtype for t in (Hx, Hy)):
-                return None
-            n = Px.shape[0]
+                return _fused_decline("field and pupil arrays of different precision")
             w = None
             if be.is_array_like(wavelength) and be.size(wavelength) > 1:
                 w = be.to_tensor(wavelength, device=Px.device) if hasattr(be, "to_tensor") else wavelength
                 if not engine.accepts_tensor(w) or w.shape != Px.shape:
-                    return None
+                    return _fused_decline("wavelength array not resident on the device / wrong shape")
                 w = w.to(Px.dtype)
                 wls = _unique_wavelengths(w)
                 if wls is None:
-                    return None
+                    return _fused_decline(f"more than {T.MAX_WAVELENGTHS} distinct wavelengths")
             else:
                 wls = _np.array([float(_np.asarray(be.to_numpy(be.atleast_1d(wavelength))).reshape(-1)[0])])
+            polarized, state = _pol_state(be, optic)
             try:
                 obj_geom = getattr(optic.object_surface, "geometry", None)
                 if not bool(optic.object_surface.is_infinite) and type(obj_geom).__name__ != "Plane":
-                    return None          # a curved object surface makes z0 field dependent
+                    return _fused_decline("curved object surface")          # (it makes z0 field dependent)
                 sc = launch_scalars(optic, 0.0, 0.0)
                 sc["vx"] = sc["vy"] = 1.0            # (the factors are already in Px, Py)
                 table = pack_surface_group(optic.surfaces, wls)
                 _prepare(engine, table, Px.device)
                 aff = pupil_affine_fields(sc, Hx, Hy)
             except _PACK_ERRORS as e:
-                _decline(f"fused launch unsupported: {e}")
-                return None
-            if any(s.coating == T.COAT_FRESNEL for s in table.surfaces):
-                return None
-            rec = engine.trace_pupil(table, Px, Py, aff, wavelength=w if len(wls) > 1 else None)
+                return _fused_decline(f"unsupported: {e}")
+            if not polarized and any(s.coating == T.COAT_FRESNEL for s in table.surfaces):
+                return None          # the reference raises (ray_generator.py:90-94)
+            if table.surfaces[0].kind != T.GEOM_NOOP:
+                return _fused_decline("first surface is not an object surface")
+            # (trace_generic does NOT run update_intensity, real_ray_tracer.py:143-152: P matrices only)
+            kw = {"polarization": "matrix"} if polarized else {}
+            rec = engine.trace_pupil(table, Px, Py, aff, wavelength=w if len(wls) > 1 else None, **kw)
             optic.surfaces.reset()
             for row, surf in enumerate(optic.surfaces.surfaces):
                 for attr, key in _REC_ATTR:
                     setattr(surf, attr, rec[key][row])
             wl_arr = w if w is not None else be.ones_like(rec["x"][-1]) * float(wls[0])
-            rays = RealRays(rec["x"][-1], rec["y"][-1], rec["z"][-1], rec["L"][-1], rec["M"][-1], rec["N"][-1],
-                            rec["intensity"][-1], wl_arr)
-            rays.opd = rec["opd"][-1]
+            rays = _make_rays(be, rec, wl_arr, polarized)
             _set_pre_interaction_direction(rays, table, rec, 0, table.num_surfaces,
                                            (rec["L"][0], rec["M"][0], rec["N"][0]))
             # tail of trace_generic (real_ray_tracer.py:145-152)
@@ -592,11 +650,16 @@ def install(engine=None, alias: str | None = None) -> None:
             """``ChiefRayStrategy.compute_wavefront_data`` (wavefront/strategy.py:152-213) with steps 3-5 -- the
             full-grid trace, the path length to the reference sphere, the OPD in waves and the exit-pupil
             intercepts -- fused into one launch that writes 5 values per ray.  Steps 1-2 (chief
-            ray, reference sphere, reference OPD) run as in the reference.  Returns WavefrontData or None."""
+            ray, reference sphere, reference OPD) run as in the reference; with ``optic.polarization`` set the launch
+            also writes the P matrices and step 6 (exit fields, strategy.py:193-203) runs the reference's own code on
+            them.  Returns WavefrontData or None.
+
+            Side effect that differs from the reference: afterwards ``optic.surfaces`` holds the records of the 1-ray
+            chief trace, not of the full pupil grid (the fused launch writes no records)."""
             import numpy as _np
             from optiland.wavefront.wavefront_data import WavefrontData
 
-            from .launch import pupil_affine
+            from .launch import launch_from_affine, pupil_affine
             from .pack import launch_scalars
 
             optic = strategy.optic
@@ -605,31 +668,31 @@ def install(engine=None, alias: str | None = None) -> None:
                 return None
             if getattr(_tls, "in_reference", False) or _wants_grad(self, list(optic.surfaces.surfaces)):
                 return None
-            if optic.polarization != "ignore" or optic.apodization:
-                return None
+            if optic.apodization:
+                return _fused_decline("wavefront: apodization")
             if getattr(optic.ray_tracer, "ray_aiming_config", {}).get("mode", "paraxial") != "paraxial":
-                return None
+                return _fused_decline("wavefront: non-paraxial ray aiming")
             try:
                 # the reference propagates the traced rays by the image surface's thickness before the wavefront
                 # strategy reads them (real_ray_tracer.py:105-110); the fused epilogue works on the image-surface
                 # record, so a non-zero thickness goes back to the reference path
                 if float(_np.asarray(be.to_numpy(optic.surfaces[-1].thickness)).reshape(-1)[0]) != 0.0:
-                    return None
+                    return _fused_decline("wavefront: image surface with a thickness")
             except Exception:
                 return None
             dist = strategy.distribution
             Px, Py = dist.x, dist.y
             if not (engine.accepts_tensor(Px) and engine.accepts_tensor(Py)):
-                return None
+                return _fused_decline("wavefront: pupil samples not resident on a CUDA device")
+            polarized, state = _pol_state(be, optic)
             try:
                 hx, hy = float(field[0]), float(field[1])
                 sc = launch_scalars(optic, hx, hy)
                 table = pack_surface_group(optic.surfaces, [float(wavelength)])
                 _prepare(engine, table, Px.device)
             except _PACK_ERRORS as e:
-                _decline(f"fused launch unsupported: {e}")
-                return None
-            if any(s.coating == T.COAT_FRESNEL for s in table.surfaces):
+                return _fused_decline(f"wavefront unsupported: {e}")
+            if not polarized and any(s.coating == T.COAT_FRESNEL for s in table.surfaces):
                 return None
             # steps 1-2, the reference's own code on ONE ray (strategy.py:160-170)
             chief = optic.trace_generic(*field, Px=0.0, Py=0.0, wavelength=wavelength)
@@ -651,9 +714,22 @@ def install(engine=None, alias: str | None = None) -> None:
 
             ref = {"center": [f(c) for c in geometry.center], "radius": f(geometry.radius), "n_image": f(strategy.n_image),
                    "tilt": tilt, "opd_ref": f(opd_ref), "wavelength_um": float(wavelength)}
-            out = engine.trace_wavefront(table, Px, Py, pupil_affine(sc), ref)
+            aff = pupil_affine(sc)
+            kwargs = {}
+            if polarized:
+                out = engine.trace_wavefront(table, Px, Py, aff, ref, polarized=True)
+                # step 6 (strategy.py:193-203): the reference's own get_exit_fields on the kernel's P matrices
+                from optiland.rays import PolarizedRays
+
+                shell = PolarizedRays.__new__(PolarizedRays)
+                _, _, _, shell._L0, shell._M0, shell._N0 = launch_from_affine(Px, Py, aff)
+                shell._i0 = be.ones_like(Px) * float(aff.get("intensity", 1.0))
+                shell.p = out["p"]
+                kwargs = {"prt_matrix": out["p"], "E_exits": shell.get_exit_fields(optic.polarization_state)}
+            else:
+                out = engine.trace_wavefront(table, Px, Py, aff, ref)
             return WavefrontData(pupil_x=out["pupil_x"], pupil_y=out["pupil_y"], pupil_z=out["pupil_z"], opd=out["opd"],
-                                 intensity=out["intensity"], radius=geometry.radius)
+                                 intensity=out["intensity"], radius=geometry.radius, **kwargs)
 
         def trace_surface(self, surface, rays) -> bool:
             if type(surface).__name__ not in ("Surface", "ImageSurface"):

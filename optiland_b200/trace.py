@@ -358,7 +358,7 @@ WAVEFRONT_KEYS = ("opd", "pupil_x", "pupil_y", "pupil_z", "intensity")
 
 
 def trace_wavefront_device(dtab: DeviceTable, Px: torch.Tensor, Py: torch.Tensor, affine: dict, ref: dict,
-                           wavelength: torch.Tensor | None = None, polarization=False) -> dict:
+                           wavelength: torch.Tensor | None = None, polarized: bool = False) -> dict:
     """olb_trace_wavefront_*: trace one field's pupil grid and write ONLY the wavefront data -- OPD in waves
     against the spherical reference ``ref`` = {center (3), radius, n_image, tilt (2), opd_ref, wavelength_um},
     the exit-pupil intercepts and the image-surface intensity -- no records, no final state
@@ -378,24 +378,30 @@ def trace_wavefront_device(dtab: DeviceTable, Px: torch.Tensor, Py: torch.Tensor
     c_ref.opd_ref, c_ref.wavelength_um = float(ref["opd_ref"]), float(ref["wavelength_um"])
     la = _c_launch(affine, Px.contiguous(), Py.contiguous())
     rays = _lib.OlbRays(w=wavelength.data_ptr() if (wavelength is not None and dtab.table.n_wl > 1) else None)
-    polarized = polarization is not False
-    status = _status_word(dtab, Px.device, force=polarized)
+    status = _status_word(dtab, Px.device)
+    p = None
     with torch.cuda.device(Px.device):
         stream = torch.cuda.current_stream(Px.device).cuda_stream
         if polarized:
-            # PolarizedRays through the wavefront epilogue (config 5): the P matrices never leave the SM; the
-            # `intensity` output is PolarizedRays.update_intensity's value (what the reference's strategy reads)
-            c_pol = _c_polarization(polarization)
+            # PolarizedRays through the wavefront epilogue (config 5).  The strategy reads the GEOMETRIC intensity
+            # of the image-surface record (wavefront/strategy.py:181) -- no intensity epilogue -- and hands the
+            # polarization ray-tracing matrices on (strategy.py:197-203): `p` is written, 5 + 18 values per ray.
+            cdt = torch.complex64 if dtype == torch.float32 else torch.complex128
+            p = torch.empty((n, 3, 3), dtype=cdt, device=Px.device)
+            rays.p = torch.view_as_real(p).data_ptr()
             rc = getattr(lib, f"olb_trace_polarized_{sfx}")(
                 C.byref(dtab.c), 0, dtab.table.num_surfaces, C.byref(la), C.byref(rays), None, n, _lib.TF_NO_FINAL,
-                C.byref(c_pol), C.byref(c_ref), C.byref(c_out), _ptr(status), C.c_void_p(stream))
+                None, C.byref(c_ref), C.byref(c_out), _ptr(status), C.c_void_p(stream))
         else:
             rc = getattr(lib, f"olb_trace_wavefront_{sfx}")(
                 C.byref(dtab.c), 0, dtab.table.num_surfaces, C.byref(la), C.byref(rays), None, n, _lib.TF_NO_FINAL,
                 C.byref(c_ref), C.byref(c_out), _ptr(status), C.c_void_p(stream))
     _lib.check(rc, f"olb_trace_wavefront_{sfx}")
     _raise_status(status)
-    return {k: buf[j, :n] for j, k in enumerate(WAVEFRONT_KEYS)}
+    out = {k: buf[j, :n] for j, k in enumerate(WAVEFRONT_KEYS)}
+    if p is not None:
+        out["p"] = p
+    return out
 
 
 def trace_moments_device(dtab: DeviceTable, n: int, dtype, rays: RealRays | None = None, pupil=None,

@@ -581,6 +581,8 @@ def main():
     case_forbes()
     case_wavefront()
     case_autograd()
+    case_config_shapes()
+    case_c3_grad_full_size()
 
 
 def case_autograd():
@@ -621,8 +623,150 @@ def case_autograd():
     print("telephoto_c3_grad", out)
 
 
+def case_config_shapes():
+    """BASELINE.json's configurations at their STATED shapes (round-2 fixtures; each holds only what a full-size
+    comparison needs -- expected statistics, not the per-ray records):
+
+    * ``c1_cooke_64rings``: config 1 as stated -- Cooke triplet, 3 fields x 1 wavelength, hexapolar pupil with 64 rings
+      (12 481 points per field): the reference's SpotDiagram RMS / geometric radii and centroids;
+    * ``c5_opd_maps``: config 5 as stated -- Zernike freeform + Fresnel coatings + unpolarized PolarizedRays, 5 fields x
+      3 wavelengths: the reference's Wavefront (chief-ray strategy) OPD map, exit-pupil intercepts, intensity and P
+      matrices for every (field, wavelength), with the reference-sphere scalars of steps 1-2;
+    * ``generic_polarized_c5``: the same system in trace_generic's call shape (per-ray fields and wavelengths),
+      with launch scalars -- what the 32 M-ray sharded run replays from global ray indices;
+    * ``telephoto_c3_4M_grad``: config 3's gradient at its stated size -- d(RMS spot)/d(radius, conic, z) over the
+      3 998 611-ray hexapolar pupil (1 154 rings) from the reference's own torch-CPU fp64 autograd, accumulated over
+      chunks (the loss depends on the rays only through sum x, sum y, sum (x^2 + y^2), which are additive)."""
+    from optiland.analysis import SpotDiagram
+    from optiland.distribution import create_distribution
+    from optiland.wavefront import Wavefront
+
+    # ---- C1 at 64 rings ---------------------------------------------------------------------------
+    lens = CookeTriplet()
+    spot = SpotDiagram(lens, wavelengths=[0.55], num_rings=64, distribution="hexapolar")
+    rms = np.array(spot.rms_spot_radius(), dtype=np.float64)          # (3 fields, 1 wavelength)
+    geo = np.array(spot.geometric_spot_radius(), dtype=np.float64)
+    cen = np.array([[np.asarray(c, dtype=np.float64) for c in spot.centroid()]])
+    chief = np.array([[float(np.ravel(v)[0]) for v in c] for c in spot._get_reference_centers(spot.data)])
+    spot_c = SpotDiagram(lens, wavelengths=[0.55], num_rings=64, distribution="hexapolar", reference="centroid")
+    rms_c = np.array(spot_c.rms_spot_radius(), dtype=np.float64)
+    d = create_distribution("hexapolar")
+    d.generate_points(64)
+    out = dict(pack_surface_group(lens.surfaces, [0.55]).to_arrays())
+    fields = lens.fields.get_field_coords()
+    for j, (hx, hy) in enumerate(fields):
+        out.update({f"f{j}_launch_{k}": v for k, v in launch_scalars(lens, float(hx), float(hy)).items()})
+    out.update(spot_rms=rms, spot_geo=geo, centroid=np.squeeze(cen), chief_center=chief, spot_rms_centroid=rms_c,
+               n_rings=64, n_pupil=np.size(d.x),
+               fields=np.array(fields, dtype=np.float64), wavelength=0.55)
+    path = os.path.join(OUT, "c1_cooke_64rings_ref.npz")
+    np.savez_compressed(path, **out)
+    print("c1_cooke_64rings", rms.ravel(), f"{np.size(d.x)} pupil points per field, {os.path.getsize(path) / 1024:.0f} KiB")
+
+    # ---- C5: OPD maps, 5 fields x 3 wavelengths -------------------------------------------------
+    fields5 = [(0.0, 0.0), (0.0, 0.5), (0.0, 1.0), (0.5, 0.5), (-0.7, 0.3)]
+    wls = [0.48, 0.55, 0.65]
+    lens = zernike_singlet("fringe", fresnel=True)
+    w = Wavefront(lens, fields=fields5, wavelengths=wls, num_rays=8, distribution="hexapolar", strategy="chief_ray")
+    out = {"fields": np.array(fields5), "wavelengths": np.array(wls), "Px": np.array(w.distribution.x),
+           "Py": np.array(w.distribution.y)}
+    worst_rms = 0.0
+    for fi, f in enumerate(fields5):
+        for wi, wl in enumerate(wls):
+            tag = f"f{fi}w{wi}"
+            data = w.get_data(f, wl)
+            ref = wavefront_ref_scalars(lens, w.strategy, f, wl)
+            if fi == 0:
+                out.update({f"w{wi}_{k}": v for k, v in pack_surface_group(lens.surfaces, [wl]).to_arrays().items()})
+            out.update({f"{tag}_launch_{k}": v for k, v in launch_scalars(lens, f[0], f[1]).items()})
+            out.update({f"{tag}_ref_{k}": v for k, v in ref.items()})
+            out.update({f"{tag}_opd": np.array(data.opd), f"{tag}_pupil_x": np.array(data.pupil_x),
+                        f"{tag}_pupil_y": np.array(data.pupil_y), f"{tag}_pupil_z": np.array(data.pupil_z),
+                        f"{tag}_intensity": np.array(data.intensity), f"{tag}_p": np.array(data.prt_matrix)})
+            worst_rms = max(worst_rms, float(np.std(np.array(data.opd))))
+    path = os.path.join(OUT, "c5_opd_maps_ref.npz")
+    np.savez_compressed(path, **out)
+    print(f"c5_opd_maps: 15 maps x {np.size(w.distribution.x)} points, largest OPD rms {worst_rms:.3f} waves, "
+          f"{os.path.getsize(path) / 1024:.0f} KiB")
+
+    # ---- C5 in trace_generic's call shape ----------------------------------------------------------
+    lens = zernike_singlet("fringe", fresnel=True)
+    Pxg, Pyg = disk(40, seed=21, rmax=0.95)
+    Hx = np.repeat([f[0] for f in fields5], 3 * Pxg.size)
+    Hy = np.repeat([f[1] for f in fields5], 3 * Pxg.size)
+    wl = np.tile(np.repeat(wls, Pxg.size), 5)
+    Px, Py = np.tile(Pxg, 15), np.tile(Pyg, 15)
+    rays = gen(lens, Hx, Hy, Px, Py, wl)
+    sc = launch_scalars(lens, 0.0, 0.0)
+    k0 = np.stack([np.array(rays._L0), np.array(rays._M0), np.array(rays._N0)])
+    run_case("generic_polarized_c5", lens, rays, wls, polarized=True,
+             extra={"Px": Px, "Py": Py, "Hx": Hx, "Hy": Hy, "i0": np.array(rays._i0), "k0": k0,
+                    **{"launch_" + k: v for k, v in sc.items()}})
+
+
+def case_c3_grad_full_size():
+    """See case_config_shapes: the config-3 gradient over the full 1 154-ring hexapolar pupil, chunked."""
+    import torch
+    from optiland.distribution import create_distribution
+
+    be.set_backend("numpy")
+    d = create_distribution("hexapolar")
+    d.generate_points(1154)
+    Px_all, Py_all = np.array(d.x), np.array(d.y)
+    n = Px_all.size
+    be.set_backend("torch")
+    be.set_precision("float64")
+    be.grad_mode.enable()
+    try:
+        lens = reverse_telephoto_asphere(1e-10)
+        # launch rays at fixed values (the hot path's gradient, as in case_autograd)
+        names = [("radius", 1), ("radius", 2), ("radius", 13), ("k", 1), ("k", 13), ("z", 1), ("z", 13)]
+
+        def leaf(kind, s):
+            g = lens.surfaces.surfaces[s].geometry
+            return g.cs.z if kind == "z" else getattr(g, kind)
+
+        leaves = [leaf(k, s) for k, s in names]
+        sums = np.zeros(3)
+        gsum = np.zeros((3, len(leaves)))
+        chunk = 250_000
+        for lo in range(0, n, chunk):
+            rays = gen(lens, 0.0, 0.7, be.array(Px_all[lo:lo + chunk]), be.array(Py_all[lo:lo + chunk]), 0.5876)
+            rays = RealRays(*[getattr(rays, k).detach() for k in ("x", "y", "z", "L", "M", "N", "i", "w")])
+            lens.surfaces.trace(rays)
+            x = lens.surfaces.x[-1, :]
+            y = lens.surfaces.y[-1, :]
+            parts = [x.sum(), y.sum(), (x * x + y * y).sum()]
+            for q, v in enumerate(parts):
+                g = torch.autograd.grad(v, leaves, retain_graph=q < 2, allow_unused=True)
+                gsum[q] += [0.0 if t is None else float(t) for t in g]
+                sums[q] += float(v.detach())
+            print(f"  c3 grad chunk {lo // chunk + 1}/{(n + chunk - 1) // chunk}", flush=True)
+        cx, cy = sums[0] / n, sums[1] / n
+        var = sums[2] / n - cx * cx - cy * cy
+        loss = np.sqrt(var)
+        # d var = d(S2)/n - 2 cx d(Sx)/n - 2 cy d(Sy)/n ;  d loss = d var / (2 loss)
+        dvar = gsum[2] / n - 2 * cx * gsum[0] / n - 2 * cy * gsum[1] / n
+        dloss = dvar / (2 * loss)
+        out = {"loss": loss, "n_rays": n, "n_rings": 1154, "centroid": np.array([cx, cy])}
+        for (kind, s), v in zip(names, dloss):
+            out[f"d_{'conic' if kind == 'k' else kind}_{s}"] = v
+    finally:
+        be.grad_mode.disable()
+        be.set_backend("numpy")
+    out.update({"launch_" + k: v for k, v in launch_scalars(reverse_telephoto_asphere(1e-10), 0.0, 0.7).items()})
+    path = os.path.join(OUT, "telephoto_c3_4M_grad.npz")
+    np.savez_compressed(path, **{k: np.asarray(v) for k, v in out.items()})
+    print("telephoto_c3_4M_grad", {k: (float(v) if np.ndim(v) == 0 else v) for k, v in out.items()})
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "huygens":
+    if len(sys.argv) > 1 and sys.argv[1] == "shapes":
+        be.set_backend("numpy")
+        case_config_shapes()
+    elif len(sys.argv) > 1 and sys.argv[1] == "c3full":
+        case_c3_grad_full_size()
+    elif len(sys.argv) > 1 and sys.argv[1] == "huygens":
         be.set_backend("numpy")
         case_huygens()
     elif len(sys.argv) > 1 and sys.argv[1] == "more":

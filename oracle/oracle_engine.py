@@ -41,7 +41,7 @@ class OracleEngine:
 
         return torch.is_tensor(t) and t.ndim == 1
 
-    def trace_pupil(self, table, Px, Py, affine, wavelength=None):
+    def trace_pupil(self, table, Px, Py, affine, wavelength=None, polarization=False):
         import torch
 
         from oracle import trace_oracle as O
@@ -54,11 +54,23 @@ class OracleEngine:
             aff["fields"] = tuple(t.detach().double().numpy() for t in aff["fields"])
         x, y, z, L, M, N = launch_from_affine(px, py, aff)
         w = wavelength.detach().double().numpy() if wavelength is not None else np.full_like(px, table.wavelengths[0])
-        inp = dict(x=x, y=y, z=z, L=L, M=M, N=N, i=np.full_like(px, affine.get("intensity", 1.0)), w=w)
-        _, rec, status = O.trace(table, inp)
-        return {k: torch.from_numpy(v).to(Px.dtype) for k, v in rec.items()}
+        i0 = np.full_like(px, affine.get("intensity", 1.0))
+        inp = dict(x=x, y=y, z=z, L=L, M=M, N=N, i=i0, w=w)
+        if polarization is False:
+            _, rec, status = O.trace(table, inp)
+            return {k: torch.from_numpy(v).to(Px.dtype) for k, v in rec.items()}
+        inp["p"] = np.tile(np.eye(3, dtype=np.complex128), (px.size, 1, 1))
+        out, rec, status = O.trace(table, inp, polarized=True)
+        res = {k: torch.from_numpy(v).to(Px.dtype) for k, v in rec.items()}
+        cdt = torch.complex128 if Px.dtype == torch.float64 else torch.complex64
+        res["p"] = torch.from_numpy(out["p"]).to(cdt)
+        if polarization == "matrix":
+            res["i_pol"] = res["intensity"][-1]
+        else:
+            res["i_pol"] = torch.from_numpy(O.polarized_intensity(out["p"], L, M, N, i0, polarization)).to(Px.dtype)
+        return res
 
-    def trace_wavefront(self, table, Px, Py, affine, ref):
+    def trace_wavefront(self, table, Px, Py, affine, ref, polarized=False):
         import torch
 
         from oracle import trace_oracle as O
@@ -69,9 +81,14 @@ class OracleEngine:
         x, y, z, L, M, N = launch_from_affine(px, py, affine)
         inp = dict(x=x, y=y, z=z, L=L, M=M, N=N, i=np.full_like(px, affine.get("intensity", 1.0)),
                    w=np.full_like(px, table.wavelengths[0]))
-        fin, _, _ = O.trace(table, inp)
+        if polarized:
+            inp["p"] = np.tile(np.eye(3, dtype=np.complex128), (px.size, 1, 1))
+        fin, _, _ = O.trace(table, inp, polarized=polarized)
         out = O.wavefront_reference_sphere(fin, px, py, ref)
-        return {k: torch.from_numpy(np.asarray(v)).to(Px.dtype) for k, v in out.items()}
+        res = {k: torch.from_numpy(np.asarray(v)).to(Px.dtype) for k, v in out.items()}
+        if polarized:
+            res["p"] = torch.from_numpy(fin["p"]).to(torch.complex128 if Px.dtype == torch.float64 else torch.complex64)
+        return res
 
     def huygens_psf(self, image_x, image_y, image_z, pupil_x, pupil_y, pupil_z, pupil_amp, pupil_opd, wavelength, Rp):
         import torch

@@ -34,9 +34,10 @@ def test_oracle_matches_reference_polarized(name):
     if "x_state" in c.z:
         inten = O.polarized_intensity(out["p"], k0[0], k0[1], k0[2], c.extra("i0"), tuple(c.extra("state")))
         assert np.max(np.abs(inten - c.extra("final_intensity"))) < 1e-13
-    else:
+    elif "x_final_intensity_unpolarized" in c.z:
         inten = O.polarized_intensity(out["p"], k0[0], k0[1], k0[2], c.extra("i0"), None)
         assert np.max(np.abs(inten - c.extra("final_intensity_unpolarized"))) < 1e-13
+    # (trace_generic-shaped fixtures hold no updated intensity: that call never runs update_intensity)
 
 
 @pytest.mark.parametrize("name", ERROR_CASES)

@@ -325,6 +325,112 @@ def test_polarized_trace_with_fresnel_coatings(plugin):
     assert float(ref_i.max()) < 0.8  # Fresnel losses really applied
 
 
+def _c5_lens(state=None):
+    """Config 5's system: Zernike freeform singlet + Fresnel coatings + PolarizedRays (oracle/make_golden.py)."""
+    from optiland.rays import PolarizationState
+
+    from oracle.make_golden import zernike_singlet
+
+    lens = zernike_singlet("fringe", fresnel=True)
+    if state is not None:
+        lens.updater.set_polarization(PolarizationState(is_polarized=True, Ex=state[0], Ey=state[1], phase_x=state[2],
+                                                        phase_y=state[3]))
+    return lens
+
+
+@pytest.mark.parametrize("state", [None, (1.0, 0.5, 0.0, 0.3)], ids=["unpolarized", "elliptical"])
+def test_config5_polarized_call_shapes_go_through_the_fused_launch(plugin, state):
+    """Config 5 through the drop-in, zero declines: Optic.trace and trace_generic (per-ray fields and wavelengths) on
+    the Zernike + Fresnel system with optic.polarization set produce PolarizedRays from ONE fused launch each --
+    records, P matrices and the update_intensity epilogue -- equal to the NumPy reference."""
+    P, eng, be = plugin
+    rng = np.random.default_rng(11)
+    n = 90
+    Px, Py = rng.uniform(-0.6, 0.6, n), rng.uniform(-0.6, 0.6, n)
+    Hx, Hy = rng.uniform(-0.7, 0.7, n), rng.uniform(-1.0, 1.0, n)
+    wl = np.asarray([0.48, 0.55, 0.65])[rng.integers(0, 3, n)]
+
+    def t_single(lens):
+        return lens.trace(Hx=0.0, Hy=1.0, wavelength=0.55, num_rays=6, distribution="hexapolar")
+
+    def t_generic(lens):
+        a = lambda v: be.array(v)  # noqa: E731
+        return lens.trace_generic(a(Hx), a(Hy), a(Px), a(Py), a(wl))
+
+    for trace, n_rays in ((t_single, None), (t_generic, n)):
+        be.set_backend("numpy")
+        ref = _c5_lens(state)
+        r_ref = trace(ref)
+        want = {k: np.array(getattr(r_ref, k)) for k in ("x", "y", "z", "L", "M", "N", "i", "opd", "p")}
+        want_rec = {k: np.array(getattr(ref.surfaces, k)) for k in ("x", "y", "opd", "intensity")}
+        be.set_backend("torch")
+        P.stats(reset=True)
+        n0 = len(eng.calls)
+        lens = _c5_lens(state)
+        rays = trace(lens)
+        new = eng.calls[n0:]
+        assert len(new) == 1 and new[0][0] == "pupil", (new, P.stats())
+        assert P.stats() == {} and type(rays).__name__ == "PolarizedRays"
+        for k in ("x", "y", "z", "L", "M", "N", "opd"):
+            np.testing.assert_allclose(be.to_numpy(getattr(rays, k)), want[k], rtol=0, atol=2e-9, err_msg=k)
+        np.testing.assert_allclose(be.to_numpy(rays.i), want["i"], rtol=0, atol=1e-11)
+        np.testing.assert_allclose(rays.p.detach().cpu().numpy(), want["p"], rtol=0, atol=1e-10)
+        for k, v in want_rec.items():
+            np.testing.assert_allclose(be.to_numpy(getattr(lens.surfaces, k)), v, rtol=0, atol=2e-9, err_msg=k)
+        if trace is t_single:
+            assert float(want["i"].max()) < 0.97          # update_intensity ran: Fresnel losses applied
+        else:
+            assert float(want["i"].min()) > 0.99          # trace_generic leaves the geometric intensity (no update)
+        # the reference's own methods keep working on the returned object
+        ef = rays.get_exit_fields(lens.polarization_state)
+        be.set_backend("numpy")
+        ef_ref = r_ref.get_exit_fields(ref.polarization_state)
+        be.set_backend("torch")
+        for a, b in zip(ef, ef_ref):
+            np.testing.assert_allclose(a.detach().cpu().numpy(), np.array(b), rtol=0, atol=1e-10)
+
+
+def test_config5_opd_maps_five_fields_three_wavelengths(plugin):
+    """Config 5 as BASELINE.json states it: the Wavefront analysis (chief-ray strategy) of the polarized Zernike +
+    Fresnel system for 5 fields x 3 wavelengths; every OPD map within 1e-5 waves of the NumPy reference, the exit
+    fields and P matrices handed on, every map from one fused wavefront launch and nothing declined."""
+    P, eng, be = plugin
+    from optiland.wavefront import Wavefront
+
+    fields = [(0.0, 0.0), (0.0, 0.5), (0.0, 1.0), (0.5, 0.5), (-0.7, 0.3)]
+    wls = [0.48, 0.55, 0.65]
+
+    def run(lens):
+        w = Wavefront(lens, fields=fields, wavelengths=wls, num_rays=10, distribution="hexapolar", strategy="chief_ray")
+        out = {}
+        for f in fields:
+            for wl in wls:
+                d = w.get_data(f, wl)
+                out[(f, wl)] = {k: np.array(be.to_numpy(getattr(d, k)), dtype=np.float64)
+                                for k in ("opd", "pupil_x", "pupil_y", "pupil_z", "intensity")}
+                out[(f, wl)]["p"] = np.array(d.prt_matrix.detach().cpu().numpy() if hasattr(d.prt_matrix, "detach") else d.prt_matrix)
+                out[(f, wl)]["E"] = [np.array(e.detach().cpu().numpy() if hasattr(e, "detach") else e) for e in d.E_exits]
+        return out
+
+    be.set_backend("numpy")
+    want = run(_c5_lens())
+    be.set_backend("torch")
+    P.stats(reset=True)
+    n0 = len(eng.calls)
+    got = run(_c5_lens())
+    assert sum(1 for c in eng.calls[n0:] if c[0] == "wavefront") == 15, eng.calls[n0:]
+    assert P.stats() == {}, P.stats()
+    worst = 0.0
+    for key in want:
+        worst = max(worst, float(np.max(np.abs(got[key]["opd"] - want[key]["opd"]))))
+        for k in ("pupil_x", "pupil_y", "pupil_z", "intensity"):
+            np.testing.assert_allclose(got[key][k], want[key][k], rtol=0, atol=1e-9, err_msg=str((key, k)))
+        np.testing.assert_allclose(got[key]["p"], want[key]["p"], rtol=0, atol=1e-10)
+        for a, b in zip(got[key]["E"], want[key]["E"]):
+            np.testing.assert_allclose(a, b, rtol=0, atol=1e-10)
+    assert worst <= 1e-5, worst          # waves: BASELINE.json config 5's tolerance
+
+
 def test_autograd_through_the_capability_matches_reference_eager_graph(plugin):
     """Config 3 through the drop-in: with be.grad_mode on, d(RMS spot)/d(radius, conic, thickness-z) obtained
     via Optic.trace -> capability (one custom autograd Function) equals the reference's own eager autograd,
