@@ -270,9 +270,12 @@ int64_t olb_table_workspace_bytes(const OlbTable* table);
 /*
  * Validate `table` (HOST memory), precompute everything that is uniform over rays
  * (flattened poses, surface-to-surface transforms, n1/n2 per wavelength, monomial form
- * of Zernike sums) and copy the result into `workspace` (DEVICE) on `stream`;
- * synchronises `stream`.  Replaces the per-call Python walk over live surface objects;
- * call again whenever a surface parameter changes.
+ * of Zernike sums) and copy the result into `workspace` (DEVICE) on `stream`, asynchronously: work launched
+ * on `stream` afterwards sees the table; other streams must be ordered behind it by the caller.  Replaces the
+ * per-call Python walk over live surface objects; call again whenever a surface parameter changes.
+ * A workspace that is too small is OLB_ERR_INVALID_ARG with the message "workspace too small (need N bytes)":
+ * callers that skip olb_table_workspace_bytes (it prepares the table a second time) and pass a generous buffer
+ * can retry on that.
  */
 int olb_table_upload(const OlbTable* table, void* workspace, int64_t workspace_bytes,
                      void* stream, OlbDeviceTable* out);

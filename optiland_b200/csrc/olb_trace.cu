@@ -1002,13 +1002,17 @@ int olb_table_upload(const OlbTable* table, void* workspace, int64_t workspace_b
   h.stride_f64 = h.bytes_f64;
   h.stride_f32 = h.bytes_f32;
   const int64_t need = 64 + (int64_t)h.bytes_f64 + h.bytes_f32;
-  if (workspace_bytes < need) return fail(OLB_ERR_INVALID_ARG, "workspace too small");
+  if (workspace_bytes < need)
+    return fail(OLB_ERR_INVALID_ARG, "workspace too small (need " + std::to_string(need) + " bytes)");
   std::vector<unsigned char> staging((size_t)need, 0);
   std::memcpy(staging.data() + h.off_f64, pr.blob_f64.data(), pr.blob_f64.size());
   std::memcpy(staging.data() + h.off_f32, pr.blob_f32.data(), pr.blob_f32.size());
   cudaStream_t st = (cudaStream_t)stream;
+  // Pageable source: cudaMemcpyAsync returns once the bytes have been staged for DMA, so `staging` may be freed
+  // right away and no stream synchronisation is needed -- the trace launched next on `stream` is ordered behind
+  // the copy.  (The synchronise that used to sit here cost every parameter change of an optimisation loop a full
+  // pipeline drain.)
   OLB_CUDA(cudaMemcpyAsync(workspace, staging.data(), (size_t)need, cudaMemcpyHostToDevice, st));
-  OLB_CUDA(cudaStreamSynchronize(st));
   *out = h;
   return OLB_OK;
 }
@@ -1054,7 +1058,7 @@ int olb_table_upload_batch(const OlbTable* template_table, const double* params,
   cudaStream_t st = (cudaStream_t)stream;
   OLB_CUDA(cudaMemcpyAsync((unsigned char*)workspace + h.off_f64, a64.data(), a64.size(), cudaMemcpyHostToDevice, st));
   OLB_CUDA(cudaMemcpyAsync((unsigned char*)workspace + h.off_f32, a32.data(), a32.size(), cudaMemcpyHostToDevice, st));
-  OLB_CUDA(cudaStreamSynchronize(st));
+  // (pageable sources: both calls return after staging; see olb_table_upload)
   *out = h;
   return OLB_OK;
 }

@@ -104,11 +104,10 @@ class CudaEngine:
     def device_table(self, table: T.SurfaceTable, device):
         from .trace import DeviceTable
 
-        surf, pool = table.pack()
-        key = surf.tobytes() + pool.tobytes() + table.wavelengths.tobytes() + str(device).encode()
+        key = table.content_key() + str(device).encode()
         dt = self._cache.get(key)
         if dt is None:
-            dt = DeviceTable(table, device, packed=(surf, pool))
+            dt = DeviceTable(table, device, packed=table.packed())
             self._cache[key] = dt
             while len(self._cache) > self._cache_size:
                 self._cache.popitem(last=False)
@@ -219,6 +218,54 @@ def _prepare(engine, table, device) -> None:
     dt = getattr(engine, "device_table", None)
     if dt is not None:
         dt(table, device)
+
+
+_launch_cache: OrderedDict = OrderedDict()
+
+
+def _object_key(obj) -> tuple:
+    """What a finite object contributes to the launch state (its pose and shape are not part of the traced table)."""
+    from .pack import _f
+
+    if bool(obj.is_infinite):
+        return ()
+    g = obj.geometry
+    cs = g.cs
+    return (type(g).__name__, _f(cs.x), _f(cs.y), _f(cs.z), _f(cs.rx), _f(cs.ry), _f(cs.rz),
+            _f(getattr(g, "radius", float("inf"))), _f(getattr(g, "k", 0.0)))
+
+
+def _launch_scalars_cached(be, optic, table, hx: float, hy: float) -> dict:
+    """``pack.launch_scalars`` memoised on everything it depends on.
+
+    The scalars (entrance-pupil position / diameter, the object-space offset, the object point of a finite-object
+    field) come from the reference's own paraxial layer -- ``optic.paraxial.EPL() / EPD()``,
+    ``field_definition.get_ray_origins`` -- which walks the surface list in Python several times per call
+    (``SurfaceGroup.positions`` alone builds a RealRays object per surface): ~15 ms per ``Optic.trace`` on the
+    Double-Gauss, two orders of magnitude more than the fused launch it parameterises.  They are pure functions of the
+    system prescription (the packed table's bytes: poses, curvatures, media), the system aperture, the field
+    definition / field list with its vignetting factors, the primary wavelength and the field point, so that is the
+    key; any change to the live objects changes the key."""
+    from .pack import _f, launch_scalars
+
+    try:
+        ap = optic.aperture
+        fd = optic.fields.field_definition
+        key = (table.content_key(), type(ap).__name__, _f(ap.value), type(fd).__name__,
+               tuple((_f(f.x), _f(f.y), _f(f.vx), _f(f.vy)) for f in optic.fields.fields),
+               float(optic.primary_wavelength), bool(optic.obj_space_telecentric), bool(optic.object_surface.is_infinite),
+               _object_key(optic.object_surface), float(hx), float(hy), str(be.get_precision()))
+    except Exception:      # an attribute this build of the reference does not have: no caching
+        return launch_scalars(optic, hx, hy)
+    sc = _launch_cache.get(key)
+    if sc is None:
+        sc = launch_scalars(optic, hx, hy)
+        _launch_cache[key] = sc
+        while len(_launch_cache) > 256:
+            _launch_cache.popitem(last=False)
+    else:
+        _launch_cache.move_to_end(key)
+    return dict(sc)
 
 
 def _unique_wavelengths(w):
@@ -540,8 +587,8 @@ def install(engine=None, alias: str | None = None) -> None:
                 return _fused_decline("pupil samples not resident on a CUDA device (or not fp32/fp64)")
             polarized, state = _pol_state(be, optic)
             try:
-                sc = launch_scalars(optic, hx, hy)
                 table = pack_surface_group(optic.surfaces, [float(wavelength)])
+                sc = _launch_scalars_cached(be, optic, table, hx, hy)
                 _prepare(engine, table, Px.device)
             except _PACK_ERRORS as e:
                 return _fused_decline(f"unsupported: {e}")
@@ -620,9 +667,9 @@ def install(engine=None, alias: str | None = None) -> None:
                 obj_geom = getattr(optic.object_surface, "geometry", None)
                 if not bool(optic.object_surface.is_infinite) and type(obj_geom).__name__ != "Plane":
                     return _fused_decline("curved object surface")          # (it makes z0 field dependent)
-                sc = launch_scalars(optic, 0.0, 0.0)
-                sc["vx"] = sc["vy"] = 1.0            # (the factors are already in Px, Py)
                 table = pack_surface_group(optic.surfaces, wls)
+                sc = _launch_scalars_cached(be, optic, table, 0.0, 0.0)
+                sc["vx"] = sc["vy"] = 1.0            # (the factors are already in Px, Py)
                 _prepare(engine, table, Px.device)
                 aff = pupil_affine_fields(sc, Hx, Hy)
             except _PACK_ERRORS as e:
@@ -687,8 +734,8 @@ def install(engine=None, alias: str | None = None) -> None:
             polarized, state = _pol_state(be, optic)
             try:
                 hx, hy = float(field[0]), float(field[1])
-                sc = launch_scalars(optic, hx, hy)
                 table = pack_surface_group(optic.surfaces, [float(wavelength)])
+                sc = _launch_scalars_cached(be, optic, table, hx, hy)
                 _prepare(engine, table, Px.device)
             except _PACK_ERRORS as e:
                 return _fused_decline(f"wavefront unsupported: {e}")

@@ -262,6 +262,23 @@ class SurfaceTable:
             pool.append(0.0)
         return surf, np.asarray(pool, dtype=np.float64)
 
+    def packed(self):
+        """``pack()`` computed once per table object (a table is not mutated after it is built)."""
+        pk = self.__dict__.get("_packed")
+        if pk is None:
+            pk = self.pack()
+            self.__dict__["_packed"] = pk
+        return pk
+
+    def content_key(self) -> bytes:
+        """Every value the kernels read, as bytes: equal keys <=> identical prepared tables."""
+        key = self.__dict__.get("_content_key")
+        if key is None:
+            surf, pool = self.packed()
+            key = surf.tobytes() + pool.tobytes() + np.asarray(self.wavelengths, dtype=np.float64).tobytes()
+            self.__dict__["_content_key"] = key
+        return key
+
     # ---- (de)serialisation for the golden fixtures ------------------------
     def to_arrays(self, prefix: str = "tab_") -> dict[str, np.ndarray]:
         surf, pool = self.pack()

@@ -111,22 +111,35 @@ class PolarizedRays(RealRays):
 class DeviceTable:
     """A ``SurfaceTable`` prepared and resident on one GPU (olb_table_upload)."""
 
+    DEFAULT_WORKSPACE = 48 * 1024
+
     def __init__(self, table: T.SurfaceTable, device=None, packed=None):
         _require_cuda()
         self.lib = _lib.load()
         self.table = table
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.host = _lib.HostTable(table, packed)   # ``packed``: a (surf, pool) pair the caller already made
-        nbytes = self.lib.olb_table_workspace_bytes(C.byref(self.host.c))
-        if nbytes < 0:
-            _lib.check(int(nbytes), "olb_table_workspace_bytes")
-        self.workspace = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
         self.c = _lib.OlbDeviceTable()
-        with torch.cuda.device(self.device):
-            stream = torch.cuda.current_stream(self.device).cuda_stream
-            rc = self.lib.olb_table_upload(C.byref(self.host.c), self.workspace.data_ptr(), int(nbytes),
-                                           C.c_void_p(stream), C.byref(self.c))
+        # ONE preparation per upload: a generous workspace instead of asking olb_table_workspace_bytes first (which
+        # prepares the table just to measure it); the rare table that needs more says so and is retried
+        nbytes = self.DEFAULT_WORKSPACE
+        for attempt in range(2):
+            self.workspace = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+            with torch.cuda.device(self.device):
+                stream = torch.cuda.current_stream(self.device).cuda_stream
+                rc = self.lib.olb_table_upload(C.byref(self.host.c), self.workspace.data_ptr(), int(nbytes),
+                                               C.c_void_p(stream), C.byref(self.c))
+            if rc != 0 and attempt == 0 and "workspace too small" in _lib.last_error():
+                nbytes = self.lib.olb_table_workspace_bytes(C.byref(self.host.c))
+                if nbytes < 0:
+                    _lib.check(int(nbytes), "olb_table_workspace_bytes")
+                continue
+            break
         _lib.check(rc, "olb_table_upload")
+        # the upload is asynchronous on the current stream: launches on that stream are ordered behind it; users of
+        # OTHER streams (the host-buffer pipeline, side streams) wait on this event first
+        self.ready = torch.cuda.Event()
+        self.ready.record(torch.cuda.current_stream(self.device))
         self.has_zernike = any(s.kind in (T.GEOM_ZERNIKE, T.GEOM_CHEBYSHEV) for s in table.surfaces)
 
     @property
@@ -520,6 +533,7 @@ def trace_host(dtab: DeviceTable, h_in: dict, h_out: dict, n: int, dtype=torch.f
     sfx = _DTYPES[dtype]
     es = 4 if dtype == torch.float32 else 8
     last = dtab.table.num_surfaces if last is None else last
+    dtab.ready.synchronize()        # the library's copy / compute streams are not ordered behind the upload's stream
     need = int(lib.olb_host_scratch_bytes(es, chunk))
     if scratch is None or scratch.numel() < need:
         scratch = torch.empty(need, dtype=torch.uint8, device=dtab.device)

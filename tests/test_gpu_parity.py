@@ -53,21 +53,20 @@ def _fp32_err(a, b):
 
 @pytest.mark.parametrize("name", REAL_CASES)
 def test_f32_kernel_vs_reference_golden(name):
-    """fp32 kernel vs fp64 reference: 2e-6 x system scale for intercepts and OPD, 5e-6 for
-    direction cosines (98 % of entries; ill-conditioned grazing rays get 100x)."""
+    """fp32 kernel vs the fp64 reference, EVERY record entry: within 3x of what the fp32 arithmetic achieves on this
+    fixture (tests/golden/f32_achieved.json; e.g. Double-Gauss: intercepts 9.4e-6 mm, OPD 7.6e-5 mm = 0.13 waves,
+    direction cosines 8e-7) -- a regression of the arithmetic by more than that fails here."""
     from optiland_b200.trace import SurfaceGroup
+    from tests._util import f32_bounds, fp32_errors
 
     c = Case(name)
     sg = SurfaceGroup(c.table)
     rays = _rays(c, torch.float32)
     sg.trace(rays)
-    ptol = 2e-6 * c.scale + 2.0 * newton_tol(c)
-    for k in ("x", "y", "z", "opd"):
-        p98, worst = _fp32_err(_np(getattr(sg, k)), c.rec[k])
-        assert p98 <= ptol and worst <= 100 * ptol, (k, p98, worst, ptol)
-    for k in ("L", "M", "N"):
-        p98, worst = _fp32_err(_np(getattr(sg, k)), c.rec[k])
-        assert p98 <= 5e-6 and worst <= 5e-4, (k, p98, worst)
+    got = fp32_errors({k: _np(getattr(sg, k)) for k in REC}, c.rec)
+    bound = f32_bounds(name)
+    for k, v in got.items():
+        assert v <= 3.0 * bound[k] + 1e-9, (k, v, bound[k])
 
 
 @pytest.mark.parametrize("name", ERROR_CASES)
@@ -206,12 +205,15 @@ def test_polarized_trace_vs_reference_golden(name, dtype):
     rays = PolarizedRays(r["x"], r["y"], r["z"], r["L"], r["M"], r["N"], r["i"], r["w"], dtype=dtype)
     sg = SurfaceGroup(c.table)
     sg.trace(rays)
+    from tests._util import f32_bounds
+
     f64 = dtype == torch.float64
-    tol = 1e-11 * c.scale + 2 * newton_tol(c) if f64 else 2e-6 * c.scale
+    b32 = f32_bounds(name)
+    tol = 1e-11 * c.scale + 2 * newton_tol(c)
     for k in ("x", "y", "opd"):
-        assert max_abs_err(_np(getattr(sg, k)), c.rec[k]) <= tol, k
+        assert max_abs_err(_np(getattr(sg, k)), c.rec[k]) <= (tol if f64 else 3 * b32["opd" if k == "opd" else "pos"]), k
     p = rays.p.to(torch.complex128).cpu().numpy()
-    assert np.max(np.abs(p - c.out["p"])) <= (1e-11 if f64 else 2e-5)
+    assert np.max(np.abs(p - c.out["p"])) <= (1e-11 if f64 else 3 * b32["p"])
     if "x_state" in c.z:
         rays.update_intensity(tuple(c.extra("state")))
         ref_i = c.extra("final_intensity")
@@ -223,7 +225,7 @@ def test_polarized_trace_vs_reference_golden(name, dtype):
     rays2 = PolarizedRays(r["x"], r["y"], r["z"], r["L"], r["M"], r["N"], r["i"], r["w"], dtype=dtype)
     sg.trace(rays2, skip=0, stop=2, record=False)
     sg.trace(rays2, skip=2)
-    assert np.max(np.abs(rays2.p.to(torch.complex128).cpu().numpy() - c.out["p"])) <= (1e-11 if f64 else 2e-5)
+    assert np.max(np.abs(rays2.p.to(torch.complex128).cpu().numpy() - c.out["p"])) <= (1e-11 if f64 else 3 * b32["p"])
 
 
 def test_fresnel_table_without_polarized_rays_is_an_error():

@@ -45,34 +45,17 @@ def test_device_math_f64_vs_reference(hc, name):
 
 @pytest.mark.parametrize("name", REAL_CASES)
 def test_device_math_f32_vs_reference(hc, name):
+    """fp32 arithmetic vs the reference's fp64 records: every entry within 3x of the error this arithmetic achieves
+    on the fixture (tests/golden/f32_achieved.json, scripts/f32_achieved.py) -- not a scale-based guess."""
+    from tests._util import f32_bounds, fp32_errors
+
     c = Case(name)
     _, rec, status = run_hostcheck(hc, c.table, c.rays, np.float32)
     assert status == 0
-    # fp32: 2e-6 of the system scale for positions / OPD, 5e-6 for direction cosines -- for
-    # 98 % of the entries; grazing / near-TIR rays are ill-conditioned (their fp64 value moves
-    # by more than that under a 1-ulp input change), so the worst 2 % get 100x the budget.
-    ptol = 2e-6 * c.scale + 2.0 * newton_tol(c)
-    for k in ("x", "y", "z", "opd"):
-        p98, worst = _fp32_err(rec[k], c.rec[k])
-        assert p98 <= ptol and worst <= 100 * ptol, (k, p98, worst, ptol)
-    for k in ("L", "M", "N"):
-        p98, worst = _fp32_err(rec[k], c.rec[k])
-        assert p98 <= 5e-6 and worst <= 5e-4, (k, p98, worst)
-    p98, _ = _fp32_err(rec["intensity"], c.rec["intensity"])
-    assert p98 <= 1e-5
-
-
-def _fp32_err(a, b):
-    """(98th percentile, max) of |a-b| over entries finite in both; fp32 may turn a grazing
-    ray into NaN where fp64 does not (and vice versa): at most 2 % such disagreements."""
-    a = np.asarray(a, dtype=np.float64)
-    m = np.isfinite(a) & np.isfinite(b)
-    mismatch = np.mean(np.isfinite(a) != np.isfinite(b))
-    assert mismatch <= 0.02, mismatch
-    d = np.sort(np.abs(a[m] - b[m]))
-    if not d.size:
-        return 0.0, 0.0
-    return float(d[int(0.98 * (d.size - 1))]), float(d[-1])
+    got = fp32_errors(rec, c.rec)
+    bound = f32_bounds(name)
+    for k, v in got.items():
+        assert v <= 3.0 * bound[k] + 1e-9, (k, v, bound[k])
 
 
 @pytest.mark.parametrize("name", ERROR_CASES)
@@ -134,12 +117,13 @@ def test_device_math_polarized_vs_reference(hc, name, dtype):
     p0 = np.tile(np.eye(3, dtype=np.complex128), (c.n, 1, 1))
     out, rec, status = run_hostcheck(hc, c.table, c.rays, dtype, pmat=p0)
     assert status == 0
-    if dtype == np.float64:
-        tol, ptol = 1e-11 * c.scale + 2 * newton_tol(c), 1e-11
-    else:
-        tol, ptol = 2e-6 * c.scale, 2e-5
+    from tests._util import f32_bounds
+
+    b32 = f32_bounds(name)
+    f64 = dtype == np.float64
+    tol, ptol = 1e-11 * c.scale + 2 * newton_tol(c), (1e-11 if f64 else 3 * b32["p"])
     for k in ("x", "y", "opd"):
-        assert max_abs_err(rec[k], c.rec[k]) <= tol, k
+        assert max_abs_err(rec[k], c.rec[k]) <= (tol if f64 else 3 * b32["opd" if k == "opd" else "pos"]), k
     assert np.max(np.abs(out["p"] - c.out["p"])) <= ptol
 
 
