@@ -592,6 +592,77 @@ def run_ours(args):
     run_sharded("c4_hubble_16M_f64", "hubble_c4", 16_000_000, torch.float64,
                 "config 4: Hubble (2 conic mirrors + obscuration), 16 M rays fp64 split over the ranks, full records")
 
+    # config 5 at its stated size and call shape: 5 fields x 3 wavelengths, per-ray (Hx, Hy, Px, Py, lambda) arrays,
+    # Zernike freeform + Fresnel coatings + unpolarized PolarizedRays, 32 M rays split over the ranks; the ray's field,
+    # wavelength and pupil point are functions of its GLOBAL index
+    def run_c5(total=32_000_000):
+        from optiland_b200.launch import pupil_affine_fields
+
+        cc, ssc = load_case("generic_polarized_c5")
+        tab = cc.table
+        if world > 1:
+            from optiland_b200.distributed import broadcast_table
+
+            tab = broadcast_table(tab if rank == 0 else None, src=0)
+        dtb = DeviceTable(tab, dev)
+        lo, hi = shard_range(total, rank, world)
+        dt = torch.float64
+        j = torch.arange(lo, hi, device=dev, dtype=torch.int64)
+        block = total // 15
+        blk = torch.clamp(j // block, max=14)
+        fields = torch.tensor([(0.0, 0.0), (0.0, 0.5), (0.0, 1.0), (0.5, 0.5), (-0.7, 0.3)], device=dev, dtype=dt)
+        wl3 = torch.tensor([float(v) for v in tab.wavelengths], device=dev, dtype=dt)
+        Hx, Hy = fields[blk // 3, 0].contiguous(), fields[blk // 3, 1].contiguous()
+        w = wl3[blk % 3].contiguous()
+        jj = (j - blk * block).double()
+        rr_ = 0.95 * torch.sqrt((jj + 0.5) / block).clamp(max=1.0)
+        th_ = jj * (np.pi * (3.0 - np.sqrt(5.0)))
+        Px, Py = (rr_ * torch.cos(th_)).contiguous(), (rr_ * torch.sin(th_)).contiguous()
+        del j, blk, jj, rr_, th_
+        affc = pupil_affine_fields(ssc, Hx, Hy)
+        Sx = tab.num_surfaces
+        tot_ms, _, _ = timed_steps(lambda: trace_pupil_device(dtb, Px, Py, affc, 0, Sx, wavelength=w, polarization=None), s_steps)
+        sharded["c5_polarized_zernike_32M_f64"] = (
+            tot_ms / s_steps, total, Sx,
+            "config 5: Zernike freeform + Fresnel coatings + unpolarized PolarizedRays, 5 fields x 3 wavelengths as per-ray "
+            "arrays (trace_generic's call shape), 32 M rays fp64 split over the ranks: fused launch, full records, P matrices "
+            "and the update_intensity epilogue")
+
+    run_c5()
+    torch.cuda.empty_cache()
+
+    # config 3's differentiable step over a fixed 4 M rays: forward + adjoint kernels per shard, 4-scalar all-reduce for
+    # the loss, all-reduce(sum) of the parameter gradients
+    def run_c3_grad(total=4_000_000):
+        from optiland_b200 import autograd as AG
+        from optiland_b200.distributed import sharded_rms_spot_loss_and_grad
+
+        cc, _ = load_case("telephoto_c3_tol1e-6")
+        tab = cc.table
+        if world > 1:
+            from optiland_b200.distributed import broadcast_table
+
+            tab = broadcast_table(tab if rank == 0 else None, src=0)
+        lo, hi = shard_range(total, rank, world)
+        gen = torch.Generator(device=dev).manual_seed(99)
+        idx = torch.randint(0, cc.n, (total,), device=dev, generator=gen)[lo:hi]
+        rr_ = {k: torch.from_numpy(v).to(dev)[idx] for k, v in cc.rays.items()}
+        rays = RealRays(rr_["x"], rr_["y"], rr_["z"], rr_["L"], rr_["M"], rr_["N"], rr_["i"], rr_["w"], dtype=torch.float32, device=dev)
+        params = AG.table_to_params(tab).to(dev).requires_grad_(True)
+
+        def trace_fn(p):
+            rec = AG.trace_differentiable(tab, p, fresh(rays), rows=(-1,))
+            return rec["x"], rec["y"]
+
+        tot_ms, _, _ = timed_steps(lambda: sharded_rms_spot_loss_and_grad(trace_fn, params), s_steps)
+        sharded["c3_grad_step_4M_f32"] = (
+            tot_ms / s_steps, total, tab.num_surfaces,
+            "config 3: reverse telephoto with 2 even aspheres, forward + adjoint kernels over a fixed 4 M rays split over the "
+            "ranks + all-reduce of the loss moments and of the (S, 28) parameter-gradient block; wall time of the whole step")
+
+    run_c3_grad()
+    torch.cuda.empty_cache()
+
     # ---- max over ranks ----------------------------------------------------------------
     names = list(sharded)
     vals = [total_ms, kern_ms, e2e_s * 1e3, e2e_state_s * 1e3, spot_s * 1e3, o_total, o_kern, ot_ms] + [sharded[k][0] for k in names]

@@ -247,6 +247,87 @@ OLB_HD T poly2_value(const T* C, int rows, int cols, bool tri, T x, T y) {
   return P;
 }
 
+// Triangular tables of a COMPILE-TIME width W (Zernike sums: prepare_table pads the monomial table to W in {4, 8,
+// 12}).  The same nested Horner as poly2_value / poly2_eval, operation for operation (padding only prepends zero
+// terms), but fully unrolled: every coefficient is a load at a constant offset and every term one FMA (value) or two
+// (partials), where the runtime-sized loops spent ~8 instructions per term on index arithmetic, compare and branch --
+// 60 % of the Zernike kernel's instructions (profiles/r2_zernike_f32_ncu_summary.txt).
+// Row i of a W-wide table (W a multiple of 4, the table 16-byte aligned: prepare_table): the W - i leading
+// coefficients with 128-bit shared-memory loads -- 12 loads for W = 8 where scalar loads need 36.
+template <typename T> struct alignas(16) CoefVec { T v[16 / sizeof(T)]; };
+template <typename T, int W, int I>
+OLB_HD void tri_row(const T* C, T (&row)[W]) {
+  constexpr int PER = 16 / (int)sizeof(T);
+  constexpr int NV = (W - I + PER - 1) / PER;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+  for (int q = 0; q < NV; ++q) {
+    const CoefVec<T> v = *reinterpret_cast<const CoefVec<T>*>(C + I * W + q * PER);
+#pragma unroll
+    for (int k = 0; k < PER; ++k) row[q * PER + k] = v.v[k];
+  }
+#else
+  for (int j = 0; j < NV * PER; ++j) row[j] = C[I * W + j];
+#endif
+}
+template <typename T, int W, int I>
+struct TriRows {
+  static OLB_HD void value(const T* C, T x, T y, T& P) {
+    T row[W];
+    tri_row<T, W, I>(C, row);
+    T q = 0;
+#pragma unroll
+    for (int j = W - 1 - I; j >= 0; --j) q = o_fma(q, y, row[j]);
+    P = o_fma(P, x, q);
+    if constexpr (I > 0) TriRows<T, W, I - 1>::value(C, x, y, P);
+  }
+  static OLB_HD void grad(const T* C, T x, T y, T& P, T& Px, T& Py) {
+    T row[W];
+    tri_row<T, W, I>(C, row);
+    T q = 0, qy = 0;
+#pragma unroll
+    for (int j = W - 1 - I; j >= 0; --j) {
+      qy = o_fma(qy, y, q);
+      q = o_fma(q, y, row[j]);
+    }
+    Px = o_fma(Px, x, P);
+    P = o_fma(P, x, q);
+    Py = o_fma(Py, x, qy);
+    if constexpr (I > 0) TriRows<T, W, I - 1>::grad(C, x, y, P, Px, Py);
+  }
+};
+template <typename T, int W>
+OLB_HD T tri_value(const T* C, T x, T y) {
+  T P = 0;
+  TriRows<T, W, W - 1>::value(C, x, y, P);
+  return P;
+}
+template <typename T, int W>
+OLB_HD void tri_grad(const T* C, T x, T y, T& Px, T& Py) {
+  T P = 0;
+  Px = 0; Py = 0;
+  TriRows<T, W, W - 1>::grad(C, x, y, P, Px, Py);
+}
+// warp-uniform dispatch on the table width (one case is executed per surface; the others are never fetched)
+template <typename T>
+OLB_HD T poly_tri_value(const T* C, int W, T x, T y) {
+  switch (W) {
+    case 4: return tri_value<T, 4>(C, x, y);
+    case 8: return tri_value<T, 8>(C, x, y);
+    case 12: return tri_value<T, 12>(C, x, y);
+    default: return poly2_value(C, W, W, true, x, y);
+  }
+}
+template <typename T>
+OLB_HD void poly_tri_grad(const T* C, int W, T x, T y, T& Px, T& Py) {
+  switch (W) {
+    case 4: tri_grad<T, 4>(C, x, y, Px, Py); break;
+    case 8: tri_grad<T, 8>(C, x, y, Px, Py); break;
+    case 12: tri_grad<T, 12>(C, x, y, Px, Py); break;
+    default: { T P; poly2_eval(C, W, W, true, x, y, P, Px, Py); }
+  }
+}
+
 // Sag of a Newton-family surface at (x, y).  `status` collects OLB_ST_* bits.
 //   even asphere  even_asphere.py:93-109   conic + sum C_i r2^(i+1)
 //   odd asphere   odd_asphere.py:86-101    conic + sum C_i r^(i+1)
@@ -398,7 +479,8 @@ OLB_HD T newton_sag(T x, T y, const PrepSurface<T>& S, const T* pool, int& statu
       if (S.kind == OLB_GEOM_ZERNIKE) status |= OLB_ST_ZERNIKE_RANGE;
       if (S.kind == OLB_GEOM_CHEBYSHEV) status |= OLB_ST_CHEBYSHEV_RANGE;
     }
-    sag += poly2_value(pool + S.coef_off, S.poly_rows, S.poly_cols, (S.flags & PSF_POLY_TRI) != 0, xn, yn);
+    if (S.flags & PSF_POLY_TRI) sag += poly_tri_value(pool + S.coef_off, S.poly_rows, xn, yn);
+    else sag += poly2_value(pool + S.coef_off, S.poly_rows, S.poly_cols, false, xn, yn);
   }
   return sag;
 }
@@ -451,7 +533,8 @@ OLB_HD void newton_slopes(T x, T y, const PrepSurface<T>& S, const T* pool, T& f
   } else {
     T xn = x * S.inv_norm, yn = y * S.inv_norm_y;
     T P, Px, Py;
-    poly2_eval(pool + S.poly_d_off, S.poly_rows, S.poly_cols, (S.flags & PSF_POLY_TRI) != 0, xn, yn, P, Px, Py);
+    if (S.flags & PSF_POLY_TRI) poly_tri_grad(pool + S.poly_d_off, S.poly_rows, xn, yn, Px, Py);
+    else poly2_eval(pool + S.poly_d_off, S.poly_rows, S.poly_cols, false, xn, yn, P, Px, Py);
     if (S.kind == OLB_GEOM_ZERNIKE) {
       // The reference forms dZ/dx = A drho/dx + B dphi/dx with REGULARISED chain-rule factors
       //   drho/dx = xn / (R (rho + eps)),  dphi/dx = -yn / (R (rho^2 + eps)),  eps = 1e-14
@@ -558,14 +641,68 @@ OLB_HD T newton_distance(T x, T y, T z, T L, T M, T N, const PrepSurface<T>& S, 
 // shrinks them by 30 % but the spills around the call cost more than the I-cache misses saved
 // (fp32 +4..27 %, fp64 +10..25 % slower; profiles/tune_r1.md, sweep 8), so it stays inlined.
 template <typename T> struct NewtonHit { T t, fx, fy; int status; };
-template <typename T, uint32_t FEAT = 0xffffffffu, bool ASPH = false>
-OLB_HD_CALL NewtonHit<T> newton_hit(T x, T y, T z, T L, T M, T N, const PrepSurface<T>* S, const T* pool) {
+
+// The generic families (polynomial / Zernike / Chebyshev / biconic / toroidal / Forbes): the SAME iteration as
+// newton_distance followed by the slopes at the hit point, arranged so that the kernel holds ONE copy of the sag code
+// and ONE copy of the slope code (the unrolled polynomial evaluators are large): every exit of the loop -- converged
+// and polished, stalled on the noise floor (possibly stepping back to the previous iterate), NaN, max_iter -- leaves
+// through the slope evaluation at the final t.
+template <typename T, uint32_t FEAT>
+OLB_HD NewtonHit<T> newton_hit_generic(T x, T y, T z, T L, T M, T N, const PrepSurface<T>& S, const T* pool) {
   NewtonHit<T> h;
   h.status = 0;
-  h.t = newton_distance<T, FEAT, ASPH>(x, y, z, L, M, N, *S, pool, h.status);
-  if constexpr (ASPH) (void)newton_sag_slopes<T, FEAT>(o_fma(h.t, L, x), o_fma(h.t, M, y), *S, pool, h.fx, h.fy, h.status);
-  else newton_slopes<T, FEAT>(o_fma(h.t, L, x), o_fma(h.t, M, y), *S, pool, h.fx, h.fy);
+  T t = conic_distance(x, y, z, L, M, N, S);
+  T t_prev = t, f_prev = (T)INFINITY;
+  bool final_pass = S.max_iter <= 0;
+  int it = 0;
+  T fx = 0, fy = 0;
+  for (;;) {
+    const T xi = o_fma(t, L, x), yi = o_fma(t, M, y);
+    T f = 0, af = 0;
+    bool conv = false;
+    if (!final_pass) {
+      const T zi = o_fma(t, N, z);
+      const T sag = newton_sag<T, FEAT>(xi, yi, S, pool, h.status);
+      f = sag - zi;
+      af = o_abs(f);
+      if (!(af == af)) {
+        final_pass = true;                       // NaN stays NaN (the reference would spin to max_iter on it)
+      } else {
+        T tol = S.tol;
+        const T floor_ = (T)8 * Eps<T>::v * (o_abs(zi) + o_abs(sag));
+        if (floor_ > tol) tol = floor_;
+        conv = af < tol;
+        if (!conv && !(af < (T)0.5 * f_prev)) {  // stalled on the noise floor (or diverging)
+          final_pass = true;
+          if (!(af < f_prev)) { t = t_prev; continue; }   // keep the better iterate: slopes there
+        }
+      }
+    }
+    newton_slopes<T, FEAT>(xi, yi, S, pool, fx, fy);
+    if (final_pass) break;
+    // f'(t) = fx L + fy M - N  with fx = -nx/nz = dz/dx  (newton_raphson.py:155-161)
+    const T df = o_fma(fx, L, o_fma(fy, M, -N));
+    const T dfs = o_abs(df) > (T)1e-14 ? df : (T)1e-14;
+    t_prev = t; f_prev = af;
+    t -= o_div(f, dfs);
+    ++it;
+    if (conv || it >= S.max_iter) final_pass = true;   // conv: that was the polishing step
+  }
+  h.t = t; h.fx = fx; h.fy = fy;
   return h;
+}
+
+template <typename T, uint32_t FEAT = 0xffffffffu, bool ASPH = false>
+OLB_HD_CALL NewtonHit<T> newton_hit(T x, T y, T z, T L, T M, T N, const PrepSurface<T>* S, const T* pool) {
+  if constexpr (!ASPH) {
+    return newton_hit_generic<T, FEAT>(x, y, z, L, M, N, *S, pool);
+  } else {
+    NewtonHit<T> h;
+    h.status = 0;
+    h.t = newton_distance<T, FEAT, ASPH>(x, y, z, L, M, N, *S, pool, h.status);
+    (void)newton_sag_slopes<T, FEAT>(o_fma(h.t, L, x), o_fma(h.t, M, y), *S, pool, h.fx, h.fy, h.status);
+    return h;
+  }
 }
 
 // Aperture program (postfix) -> inside?   physical_apertures/*.py, see include/olb.h.
@@ -825,8 +962,9 @@ OLB_HD void surface_step_k(Ray<T>& r, const PrepSurface<T>& S, const T* pool, bo
   // keeps its value across that surface (base.py:119-128: update() runs only in the no-coating branch).
   if (FEAT & FEAT_POL) {
     if (S.coating != OLB_COAT_SIMPLE)
-      polar_update(r, Pm ? Pm : r.P, Pm ? Pstride : 1, S, med[MED_CN] + bad,
-                   o_abs(o_fma(r.L0, nx, o_fma(r.M0, ny, r.N0 * nz))));
+      // (Pm is the caller's matrix storage -- never a pointer into `r`: taking r.P's address here would force the
+      // whole ray state into local memory in the kernel)
+      polar_update(r, Pm, Pstride, S, med[MED_CN] + bad, o_abs(o_fma(r.L0, nx, o_fma(r.M0, ny, r.N0 * nz))));
   }
 }
 

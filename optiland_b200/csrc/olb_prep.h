@@ -67,6 +67,7 @@ struct PrepSurface {
   int32_t poly_d_off;  // pool offset of the derivative-source table (Zernike quirk)
   int32_t gslot;       // backward: first per-thread gradient accumulator slot of this surface
   int32_t gslots;      //           number of slots (7 + n_coef [+ 9 for a tilted pose]; 0 for NOOP)
+  int32_t pad16[2];    // keeps sizeof a multiple of 16 (256 / 448 bytes): the pool behind the array stays 16-byte aligned
   // incoming transform from GLOBAL coordinates: p_loc = Ag * p + bg
   T Ag[9], bg[3];
   // incoming transform from the PREVIOUS surface's local frame: p_loc = Ar * p + br
@@ -77,6 +78,10 @@ struct PrepSurface {
   T tol, coat_t, coat_r, inv_norm;  // inv_norm = 1 / norm_radius (Chebyshev: 1 / norm_x)
   T inv_norm_y, curv_y, kp1_y, r_rot;  // Chebyshev 1/norm_y; biconic cy, 1+ky; toroidal: c_yz, 1+k_yz, R_rot
 };
+// the pool starts right behind the PrepSurface array: 16-byte alignment of its (4-element aligned) blocks needs this
+static_assert(sizeof(PrepSurface<float>) % 16 == 0 && sizeof(PrepSurface<double>) % 16 == 0, "PrepSurface must keep the pool 16-byte aligned");
+static_assert(sizeof(PrepHeader) % 16 == 0, "PrepHeader must keep the table 16-byte aligned");
+
 
 enum : uint32_t {
   PSF_ROT_IN_G = 1u << 8,    // Ag != I
@@ -389,14 +394,20 @@ static inline PrepResult prepare_table(const OlbTable& tab) {
         if (n < 0 || (m < 0 ? -m : m) > n || ((n - m) & 1) || n > 23) { res.error = "bad Zernike (n, m)"; return res; }
         if (n > deg) deg = n;
       }
-      const int W = deg + 1;
+      // table width padded to one of the compile-time sizes of olb_math.cuh::poly_tri_value (zero rows / columns:
+      // the nested Horner is unchanged); wider tables run the runtime-sized loops
+      int degp = deg;
+      for (int wp : {4, 8, 12})
+        if (deg + 1 <= wp) { degp = wp - 1; break; }
+      const int W = degp + 1;
       std::vector<double> S(W * W, 0.0), D(W * W, 0.0);
       for (int i = 0; i < in.n_coef; ++i) {
         const double* tm = tab.pool + in.coef_off + 4 * i;
-        zernike_add_monomials((int)tm[0], (int)tm[1], tm[2], deg, S.data());  // c * N_nm
-        zernike_add_monomials((int)tm[0], (int)tm[1], tm[3], deg, D.data());  // c (quirk: no N_nm)
+        zernike_add_monomials((int)tm[0], (int)tm[1], tm[2], degp, S.data());  // c * N_nm
+        zernike_add_monomials((int)tm[0], (int)tm[1], tm[3], degp, D.data());  // c (quirk: no N_nm)
       }
       o.poly_rows = W; o.poly_cols = W; o.flags |= PSF_POLY_TRI;
+      while (pool.size() % 4) pool.push_back(0);     // 16-byte aligned rows: the kernel loads them as vectors
       o.coef_off = (int)pool.size();
       pool.insert(pool.end(), S.begin(), S.end());
       while (pool.size() % 4) pool.push_back(0);

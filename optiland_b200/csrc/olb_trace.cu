@@ -775,8 +775,17 @@ constexpr uint32_t FEAT_GENERAL = FEAT_ROT | FEAT_NEWTON | FEAT_EXTRA | FEAT_FRE
 template <typename T, int RPT>
 static int launch_feat(const TraceArgs& a, uint32_t features, cudaStream_t stream) {
   if (features & FEAT_POL) {
-    if constexpr (RPT == 1) return launch_instance<T, 1, FEAT_GENERAL | FEAT_POL>(a, stream);
-    else return fail(OLB_ERR_UNSUPPORTED, "polarized trace uses one ray per thread");
+    if constexpr (RPT == 1) {
+      // lean polarized variants for the common systems: the general kernel's code does not fit the instruction
+      // cache (no_instruction was the second largest stall of the Zernike + Fresnel configuration)
+      const uint32_t g = features & ~FEAT_POL;
+      if (g == 0) return launch_instance<T, 1, FEAT_POL>(a, stream);                                   // planes / conics
+      if ((g & ~(FEAT_NEWTON | FEAT_FREEFORM)) == 0)
+        return launch_instance<T, 1, FEAT_NEWTON | FEAT_FREEFORM | FEAT_POL>(a, stream);               // + Newton families
+      return launch_instance<T, 1, FEAT_GENERAL | FEAT_POL>(a, stream);
+    } else {
+      return fail(OLB_ERR_UNSUPPORTED, "polarized trace uses one ray per thread");
+    }
   }
   if (features == 0) return launch_instance<T, RPT, 0u>(a, stream);
   if (features == FEAT_ROT) return launch_instance<T, RPT, FEAT_ROT>(a, stream);

@@ -79,6 +79,43 @@ def global_rms_spot_radius(x: torch.Tensor, y: torch.Tensor, intensity: torch.Te
     return float(np.sqrt(float(_allreduce_sum(d2, group)[0]) / cnt))
 
 
+def sharded_rms_spot_loss_and_grad(trace_fn, params: torch.Tensor, group=None):
+    """One step of the sharded autograd configuration (config 3 over several GPUs): every rank traces
+    ITS shard of the rays differentiably -- ``trace_fn(params) -> (x, y)`` image-surface intercepts that are autograd
+    outputs of ``params`` (``optiland_b200.autograd.trace_differentiable`` on the rank's rays) -- and gets back the
+    GLOBAL loss = RMS spot radius about the global centroid (optimization/operand/ray.py:299-342) and the GLOBAL
+    dLoss/dparams.
+
+    Exchange: one all-reduce of 4 scalars (n, sum x, sum y, sum x^2 + y^2) for the loss and one all-reduce(sum) of
+    the (S, GP_COUNT) parameter-gradient block -- a few hundred doubles, latency-bound on NVLink.  No per-ray data
+    crosses GPUs.  The chain rule through the global centroid needs no extra exchange: with V = mean |p - c|^2 and
+    c = mean p, dV/dp_i = 2 (p_i - c) / n (the dependence through c cancels), so each rank back-propagates
+    (p_i - c) / (n L) through its own shard."""
+    x, y = trace_fn(params)
+    xd, yd = x.detach().double(), y.detach().double()
+    m = torch.isfinite(xd) & torch.isfinite(yd)
+    zero = torch.zeros((), dtype=torch.float64, device=xd.device)
+    sums = torch.stack([m.sum().double(), torch.where(m, xd, zero).sum(), torch.where(m, yd, zero).sum(),
+                        torch.where(m, xd * xd + yd * yd, zero).sum()])
+    sums = _allreduce_sum(sums, group)
+    n, sx, sy, s2 = (float(v) for v in sums)
+    cx, cy = sx / n, sy / n
+    var = s2 / n - cx * cx - cy * cy
+    if not var > 0:      # (catastrophic cancellation of the one-pass form on a far off-axis spot: two-pass)
+        d2 = torch.where(m, (xd - cx) ** 2 + (yd - cy) ** 2, zero).sum().reshape(1)
+        var = float(_allreduce_sum(d2, group)[0]) / n
+    loss = var ** 0.5
+    mask = m.to(x.dtype)
+    surrogate = (mask * ((x - cx) ** 2 + (y - cy) ** 2)).sum() / (2.0 * n * loss)
+    (g,) = torch.autograd.grad(surrogate, params, allow_unused=True)
+    g = torch.zeros_like(params) if g is None else g
+    if dist.is_available() and dist.is_initialized():
+        gd = g.to(_comm_device(group)).contiguous()
+        dist.all_reduce(gd, op=dist.ReduceOp.SUM, group=group)
+        g = gd.to(params.device)
+    return loss, g
+
+
 def _parse_cpulist(text: str) -> list[int]:
     cpus: list[int] = []
     for part in text.strip().split(","):

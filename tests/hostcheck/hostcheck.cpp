@@ -40,7 +40,7 @@ static void walk(const unsigned char* blob, int first, int last, int64_t n, T** 
     for (int s = first; s < last; ++s) {
       const PrepSurface<T>& S = surf[s];
       const bool noop = S.kind == OLB_GEOM_NOOP;
-      if (!noop) { surface_step<T, FEAT>(r, S, pool, !have_frame, status); have_frame = true; }
+      if (!noop) { surface_step<T, FEAT>(r, S, pool, !have_frame, status, r.P, 1); have_frame = true; }
       const bool record = rec != nullptr && !(S.flags & OLB_SF_NORECORD);
       if ((record || s == last - 1) && !noop) to_global<T, FEAT>(r, S, g[0], g[1], g[2], g[3], g[4], g[5]);
       if (record) {

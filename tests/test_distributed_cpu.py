@@ -73,3 +73,56 @@ def test_two_rank_gloo_table_broadcast_and_moments():
     for g in got:
         assert g[5] == c.table.num_surfaces
         assert g[4] == pytest.approx(ref_rms, rel=1e-12)
+
+
+def _grad_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from optiland_b200.distributed import sharded_rms_spot_loss_and_grad
+
+        n = 1001
+        lo, hi = shard_range(n, rank, world)
+        px, py, params0 = _toy_problem(n)
+        params = params0.clone().requires_grad_(True)
+        loss, g = sharded_rms_spot_loss_and_grad(lambda p: _toy_trace(p, px[lo:hi], py[lo:hi]), params)
+        q.put((rank, loss, g.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def _toy_problem(n):
+    g = torch.Generator().manual_seed(5)
+    px, py = torch.rand(n, generator=g, dtype=torch.float64) - 0.5, torch.rand(n, generator=g, dtype=torch.float64) - 0.5
+    params = torch.tensor([[0.3, -0.2, 1.5], [0.7, 0.1, -0.4]], dtype=torch.float64)
+    return px, py, params
+
+
+def _toy_trace(p, px, py):
+    """A smooth stand-in for the per-rank differentiable trace (the real one is the CUDA forward + adjoint kernels)."""
+    x = p[0, 0] * px + p[0, 1] * py ** 2 + p[1, 2] * torch.sin(p[0, 2] * px) + 12.0
+    y = p[1, 0] * py + p[1, 1] * px * py + 0.1 * p[0, 2] * px ** 3 - 7.0
+    return x, y
+
+
+@pytest.mark.timeout(120)
+def test_two_rank_sharded_gradient_step_equals_single_process():
+    """The all-reduce of the parameter gradients (sharded config-3 step): 2 ranks over gloo == 1 process."""
+    px, py, params0 = _toy_problem(1001)
+    params = params0.clone().requires_grad_(True)
+    x, y = _toy_trace(params, px, py)
+    loss = torch.sqrt(torch.mean((x - x.mean()) ** 2 + (y - y.mean()) ** 2))
+    loss.backward()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted((q.get(timeout=100) for _ in procs), key=lambda t: t[0])
+    for p in procs:
+        p.join(30)
+        assert p.exitcode == 0
+    for _, l, g in got:
+        assert l == pytest.approx(float(loss), rel=1e-12)
+        np.testing.assert_allclose(g, params.grad.numpy(), rtol=1e-10, atol=1e-14)
