@@ -303,9 +303,8 @@ OLB_HD T tri_value(const T* C, T x, T y) {
   return P;
 }
 template <typename T, int W>
-OLB_HD void tri_grad(const T* C, T x, T y, T& Px, T& Py) {
-  T P = 0;
-  Px = 0; Py = 0;
+OLB_HD void tri_grad(const T* C, T x, T y, T& P, T& Px, T& Py) {
+  P = 0; Px = 0; Py = 0;
   TriRows<T, W, W - 1>::grad(C, x, y, P, Px, Py);
 }
 // warp-uniform dispatch on the table width (one case is executed per surface; the others are never fetched)
@@ -319,12 +318,12 @@ OLB_HD T poly_tri_value(const T* C, int W, T x, T y) {
   }
 }
 template <typename T>
-OLB_HD void poly_tri_grad(const T* C, int W, T x, T y, T& Px, T& Py) {
+OLB_HD void poly_tri_grad(const T* C, int W, T x, T y, T& P, T& Px, T& Py) {
   switch (W) {
-    case 4: tri_grad<T, 4>(C, x, y, Px, Py); break;
-    case 8: tri_grad<T, 8>(C, x, y, Px, Py); break;
-    case 12: tri_grad<T, 12>(C, x, y, Px, Py); break;
-    default: { T P; poly2_eval(C, W, W, true, x, y, P, Px, Py); }
+    case 4: tri_grad<T, 4>(C, x, y, P, Px, Py); break;
+    case 8: tri_grad<T, 8>(C, x, y, P, Px, Py); break;
+    case 12: tri_grad<T, 12>(C, x, y, P, Px, Py); break;
+    default: poly2_eval(C, W, W, true, x, y, P, Px, Py);
   }
 }
 
@@ -533,7 +532,7 @@ OLB_HD void newton_slopes(T x, T y, const PrepSurface<T>& S, const T* pool, T& f
   } else {
     T xn = x * S.inv_norm, yn = y * S.inv_norm_y;
     T P, Px, Py;
-    if (S.flags & PSF_POLY_TRI) poly_tri_grad(pool + S.poly_d_off, S.poly_rows, xn, yn, Px, Py);
+    if (S.flags & PSF_POLY_TRI) poly_tri_grad(pool + S.poly_d_off, S.poly_rows, xn, yn, P, Px, Py);
     else poly2_eval(pool + S.poly_d_off, S.poly_rows, S.poly_cols, false, xn, yn, P, Px, Py);
     if (S.kind == OLB_GEOM_ZERNIKE) {
       // The reference forms dZ/dx = A drho/dx + B dphi/dx with REGULARISED chain-rule factors
@@ -656,13 +655,32 @@ OLB_HD NewtonHit<T> newton_hit_generic(T x, T y, T z, T L, T M, T N, const PrepS
   bool final_pass = S.max_iter <= 0;
   int it = 0;
   T fx = 0, fy = 0;
+  // Zernike surfaces ITERATE with the exact partials of the sag polynomial, obtained in the same pass as its value.
+  // The reference iterates with its own slope function, whose Zernike part omits the normalisation constants
+  // (zernike/base.py:104-136) -- an inexact f' that makes its Newton iteration converge only linearly (~4
+  // evaluations where 2 suffice).  The fixed point f(t) = 0 does not depend on the slope used to reach it, so the
+  // intersection is the same to within the stopping tolerance; the NORMAL at the hit point still comes from the
+  // reference's slope function (newton_slopes, below).
+  const bool zern = S.kind == OLB_GEOM_ZERNIKE && (S.flags & PSF_POLY_TRI) != 0;
   for (;;) {
     const T xi = o_fma(t, L, x), yi = o_fma(t, M, y);
     T f = 0, af = 0;
     bool conv = false;
     if (!final_pass) {
       const T zi = o_fma(t, N, z);
-      const T sag = newton_sag<T, FEAT>(xi, yi, S, pool, h.status);
+      T sag;
+      if (zern) {
+        T g, P, Px, Py;
+        conic_sag_slope(o_fma(xi, xi, yi * yi), S, sag, g);
+        const T xn = xi * S.inv_norm, yn = yi * S.inv_norm_y;
+        if (o_abs(xn) > (T)1 || o_abs(yn) > (T)1) h.status |= OLB_ST_ZERNIKE_RANGE;
+        poly_tri_grad(pool + S.coef_off, S.poly_rows, xn, yn, P, Px, Py);
+        sag += P;
+        fx = o_fma(xi, g, Px * S.inv_norm);
+        fy = o_fma(yi, g, Py * S.inv_norm_y);
+      } else {
+        sag = newton_sag<T, FEAT>(xi, yi, S, pool, h.status);
+      }
       f = sag - zi;
       af = o_abs(f);
       if (!(af == af)) {
@@ -678,7 +696,7 @@ OLB_HD NewtonHit<T> newton_hit_generic(T x, T y, T z, T L, T M, T N, const PrepS
         }
       }
     }
-    newton_slopes<T, FEAT>(xi, yi, S, pool, fx, fy);
+    if (final_pass || !zern) newton_slopes<T, FEAT>(xi, yi, S, pool, fx, fy);
     if (final_pass) break;
     // f'(t) = fx L + fy M - N  with fx = -nx/nz = dz/dx  (newton_raphson.py:155-161)
     const T df = o_fma(fx, L, o_fma(fy, M, -N));
