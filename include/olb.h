@@ -111,6 +111,9 @@ extern "C" {
 #define OLB_TF_SHARED_INPUT (1u << 4) /* batched trace: every system traces the SAME rays_per_system launch rays */
 #define OLB_TF_MOMENTS     (1u << 3)  /* accumulate OlbMoments over the traced batch (fused analysis
                                          epilogue); see olb_trace_moments_*          */
+#define OLB_TF_MOMENTS_GLOBAL (1u << 5) /* moments of the GLOBAL (x, y) of the last traced surface instead of its local frame */
+#define OLB_TF_MOMENTS_ALL (1u << 6)  /* moments over EVERY ray (no i > 0 / finite mask): a NaN ray makes the sums NaN, like
+                                         be.mean over the record row in the rms_spot_size operand (operand/ray.py:337-341) */
 #define OLB_TF_NO_FINAL    (1u << 1)  /* do not write the final state back into rays.x..opd:
                                          the caller takes it from the last record row (saves
                                          32-64 B/ray of HBM writes; needs rec)              */
@@ -350,7 +353,9 @@ int olb_trace_pupil_f64(const OlbDeviceTable* table, int32_t first, int32_t last
  * optiland/analysis/spot_diagram/core.py:462-481), over rays with intensity > 0 and finite intercepts
  * (the mask of core.py:471-472), relative to `center`:
  *   m[0] = count, m[1] = sum (x - cx), m[2] = sum (y - cy), m[3] = sum ((x-cx)^2 + (y-cy)^2),
- *   m[4] = sum intensity, m[5] = sum opd, m[6] = sum opd^2, m[7] = reserved
+ *   m[4] = sum intensity, m[5] = sum opd, m[6] = sum opd^2,
+ *   m[7] = number of rays with intensity > 0 whose intercept is NOT finite (the reference's mask keeps them, so its
+ *          statistics are NaN whenever this is non-zero)
  * accumulated in fp64 INTO `moments` (device, 8 doubles; the caller zeroes it).  From these follow the
  * centroid, the RMS spot radius about the centroid or about `center` (rms_spot_radius, core.py:357-370)
  * and the OPD mean / variance without writing or re-reading any per-ray array: rec may be NULL and

@@ -25,6 +25,8 @@ TF_NO_FINAL = 1 << 1
 TF_POL_IDENTITY = 1 << 2
 TF_MOMENTS = 1 << 3
 TF_SHARED_INPUT = 1 << 4
+TF_MOMENTS_GLOBAL = 1 << 5
+TF_MOMENTS_ALL = 1 << 6
 BP_TX, BP_TY, BP_TZ, BP_R, BP_CURV, BP_CONIC, BP_N1, BP_N2, BP_COEF, BP_MAX_COEF = 0, 1, 2, 3, 12, 13, 14, 15, 16, 12
 BP_COUNT = BP_COEF + BP_MAX_COEF
 GP_TX, GP_TY, GP_TZ, GP_CURV, GP_CONIC, GP_N1, GP_N2, GP_COEF, GP_MAX_COEF = 0, 1, 2, 3, 4, 5, 6, 7, 12

@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<T, RPT, FEAT>::v)) trace_ker
   const int64_t n_tiles = (n + per_tile - 1) / per_tile;
   const int first = a.first, last = a.last;
   int status = 0;
-  double mom[7] = {0, 0, 0, 0, 0, 0, 0};   // OLB_TF_MOMENTS: per-thread partial sums
+  double mom[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // OLB_TF_MOMENTS: per-thread partial sums
 
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t local = (tile * BLOCK + threadIdx.x) * RPT;
@@ -376,15 +376,21 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<T, RPT, FEAT>::v)) trace_ker
     }
 
     if (a.tflags & OLB_TF_MOMENTS) {
-      // intercepts in the LAST surface's local frame (r.x, r.y), mask i > 0 and finite
+      // intercepts on the LAST traced surface: its local frame (r.x, r.y) with the mask i > 0 and finite (what
+      // SpotDiagram transforms to and keeps), or -- OLB_TF_MOMENTS_GLOBAL / _ALL -- global coordinates / every ray
+      // (what the rms_spot_size operand averages: a NaN ray then makes the sums NaN, as in the reference)
+      const bool glob = (a.tflags & OLB_TF_MOMENTS_GLOBAL) != 0, all = (a.tflags & OLB_TF_MOMENTS_ALL) != 0;
 #pragma unroll
       for (int k = 0; k < RPT; ++k) {
         if (k >= valid) continue;
-        const double dx = (double)r[k].x - a.mcx, dy = (double)r[k].y - a.mcy;
+        const double dx = (double)(glob ? gx[k] : r[k].x) - a.mcx, dy = (double)(glob ? gy[k] : r[k].y) - a.mcy;
         const double ii = (double)r[k].i, oo = (double)opd_value(r[k]);
-        if (ii > 0 && dx - dx == 0 && dy - dy == 0) {
+        const bool finite = dx - dx == 0 && dy - dy == 0;
+        if (all || (ii > 0 && finite)) {
           mom[0] += 1.0; mom[1] += dx; mom[2] += dy; mom[3] += dx * dx + dy * dy; mom[4] += ii;
           mom[5] += oo; mom[6] += oo * oo;
+        } else if (ii > 0) {
+          mom[7] += 1.0;          // kept by the reference's mask (i > 0) but not finite: its statistics are NaN
         }
       }
     }
@@ -467,7 +473,7 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<T, RPT, FEAT>::v)) trace_ker
   if (a.tflags & OLB_TF_MOMENTS) {
     // CTA reduction: warp tree, then one fp64 atomic per moment and warp (uniform branch: launch argument)
 #pragma unroll
-    for (int q = 0; q < 7; ++q) {
+    for (int q = 0; q < 8; ++q) {
       double v = mom[q];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -24,6 +24,7 @@ the reference's own code, which is what runs today.
 """
 from __future__ import annotations
 
+import sys
 import threading
 from collections import OrderedDict
 
@@ -177,6 +178,18 @@ class CudaEngine:
         dt = self.device_table(table, Px.device)
         self._note("wavefront", table.num_surfaces, int(Px.numel()))
         return trace_wavefront_device(dt, _dev_array(Px), _dev_array(Py), affine, ref, polarized=polarized)
+
+    def spot_moments(self, table: T.SurfaceTable, Px, Py, affine: dict, center=(0.0, 0.0), last=None,
+                     global_xy: bool = False, every_ray: bool = False) -> list:
+        """Launch generation + trace + moment sums in ONE kernel, nothing written per ray (olb_trace_moments_*):
+        the 8 sums of include/olb.h as Python floats (one 64-byte read-back)."""
+        from .trace import trace_moments_device
+
+        dt = self.device_table(table, Px.device)
+        self._note("moments", table.num_surfaces, int(Px.numel()))
+        m = trace_moments_device(dt, int(Px.numel()), Px.dtype, pupil=(_dev_array(Px), _dev_array(Py), affine),
+                                 center=center, last=last, global_xy=global_xy, every_ray=every_ray)
+        return [float(v) for v in m.cpu()]
 
     def huygens_psf(self, image_x, image_y, image_z, pupil_x, pupil_y, pupil_z, pupil_amp, pupil_opd, wavelength, Rp):
         """Huygens-Fresnel summation on the GPU (olb_huygens_psf_f64); None to decline (CPU tensors)."""
@@ -872,6 +885,11 @@ def install(engine=None, alias: str | None = None) -> None:
         backend = registry.get(be.get_backend())
         return bool(backend.grad_mode.requires_grad) or any(getattr(t, "requires_grad", False) for t in tensors)
 
+    # f-2: spot statistics from the moments epilogue (RayOperand.rms_spot_size, SpotDiagram.rms_spot_radius / centroid)
+    from . import spot as _spot
+
+    saved_spot = _spot.install(sys.modules[__name__], registry, be)
+
     TorchSummation.grad_wanted = _grad_wanted
     TorchSummation.compute = hf_compute
     SurfaceGroup.trace = group_trace
@@ -880,7 +898,7 @@ def install(engine=None, alias: str | None = None) -> None:
     RealRayTracer.trace_generic = tracer_generic
     _state.update(installed=True, orig_group_trace=orig_group_trace, orig_surface_trace=orig_surface_trace,
                   orig_tracer_trace=orig_tracer_trace, orig_tracer_generic=orig_tracer_generic, orig_hf_compute=orig_hf_compute, orig_chief_compute=orig_chief_compute,
-                  old_backend=old, alias=alias, fuse_launch=True, fuse_wavefront=True)
+                  old_backend=old, alias=alias, fuse_launch=True, fuse_wavefront=True, fuse_spot=True, saved_spot=saved_spot)
 
 
 def uninstall() -> None:
@@ -903,6 +921,10 @@ def uninstall() -> None:
     from optiland.wavefront.strategy import ChiefRayStrategy
 
     ChiefRayStrategy.compute_wavefront_data = _state["orig_chief_compute"]
+    if _state.get("saved_spot") is not None:
+        from . import spot as _spot
+
+        _spot.uninstall(_state["saved_spot"])
     if _state.get("old_backend") is not None:
         registry["torch"] = _state["old_backend"]
     if _state.get("alias"):

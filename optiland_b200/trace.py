@@ -268,6 +268,14 @@ def trace_device(dtab: DeviceTable, rays: RealRays, first: int, last: int, recor
     return recs
 
 
+def _aligned(t):
+    """Contiguous and 16-byte aligned (a slice of a larger tensor may start anywhere; the C ABI wants aligned arrays)."""
+    if t is None:
+        return None
+    t = t.contiguous()
+    return t.clone() if t.data_ptr() % 16 else t
+
+
 def _c_launch(affine: dict, Px, Py):
     la = _lib.OlbPupilLaunch()
     la.Px, la.Py = Px.data_ptr(), Py.data_ptr()
@@ -296,6 +304,9 @@ def trace_pupil_device(dtab: DeviceTable, Px: torch.Tensor, Py: torch.Tensor, af
     traced -- "matrix": only the P matrices (``rays.p``); None / "unpolarized" / (Ex, Ey, phase_x, phase_y): also the
     intensity epilogue of RealRayTracer.trace in-kernel, ``rays.i`` = sum |P E0|^2 i0 / n_states (the record rows keep
     the geometric intensity, as in the reference)."""
+    Px, Py, wavelength = _aligned(Px), _aligned(Py), _aligned(wavelength)
+    if affine.get("fields") is not None:
+        affine = dict(affine, fields=tuple(_aligned(t) for t in affine["fields"]))
     if polarization is not False:
         return _trace_pupil_polarized(dtab, Px, Py, affine, first, last, wavelength, polarization)
     lib = dtab.lib
@@ -376,6 +387,7 @@ def trace_wavefront_device(dtab: DeviceTable, Px: torch.Tensor, Py: torch.Tensor
     against the spherical reference ``ref`` = {center (3), radius, n_image, tilt (2), opd_ref, wavelength_um},
     the exit-pupil intercepts and the image-surface intensity -- no records, no final state
     (optiland/wavefront/strategy.py:152-213).  Returns {key: (N,) tensor} for WAVEFRONT_KEYS."""
+    Px, Py, wavelength = _aligned(Px), _aligned(Py), _aligned(wavelength)
     lib = dtab.lib
     n = Px.numel()
     dtype = Px.dtype
@@ -419,10 +431,12 @@ def trace_wavefront_device(dtab: DeviceTable, Px: torch.Tensor, Py: torch.Tensor
 
 def trace_moments_device(dtab: DeviceTable, n: int, dtype, rays: RealRays | None = None, pupil=None,
                          center=(0.0, 0.0), moments: torch.Tensor | None = None, wavelength=None,
-                         status: torch.Tensor | None = None) -> torch.Tensor:
+                         status: torch.Tensor | None = None, last: int | None = None, global_xy: bool = False,
+                         every_ray: bool = False) -> torch.Tensor:
     """olb_trace_moments_*: trace WITHOUT writing any per-ray output and accumulate the spot / OPD moments
     of the image-surface intercepts in-kernel (8 fp64 values on the device; see include/olb.h).  Either
-    ``rays`` (launch-state arrays, left untouched) or ``pupil`` = (Px, Py, affine).  ``status``: a caller-owned
+    ``rays`` (launch-state arrays, left untouched) or ``pupil`` = (Px, Py, affine).  ``last``: stop after surface
+    ``last - 1`` (the moments are of THAT surface); ``global_xy`` / ``every_ray``: OLB_TF_MOMENTS_GLOBAL / _ALL.  ``status``: a caller-owned
     device int32 for the OLB_ST_* bits (a caller that pipelines several launches checks it once at the end with
     ``_raise_status``); by default one is made and checked here for tables that can raise them."""
     lib = dtab.lib
@@ -437,6 +451,7 @@ def trace_moments_device(dtab: DeviceTable, n: int, dtype, rays: RealRays | None
     c_rays = _lib.OlbRays()
     if pupil is not None:
         Px, Py, affine = pupil
+        Px, Py, wavelength = _aligned(Px), _aligned(Py), _aligned(wavelength)
         la = _c_launch(affine, Px, Py)
         if wavelength is not None and dtab.table.n_wl > 1:
             c_rays.w = wavelength.data_ptr()
@@ -447,11 +462,12 @@ def trace_moments_device(dtab: DeviceTable, n: int, dtype, rays: RealRays | None
         if dtab.table.n_wl > 1:
             c_rays.w = rays.w.data_ptr()
     cen = (C.c_double * 2)(float(center[0]), float(center[1]))
+    flags = _lib.TF_NO_FINAL | (_lib.TF_MOMENTS_GLOBAL if global_xy else 0) | (_lib.TF_MOMENTS_ALL if every_ray else 0)
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
         rc = getattr(lib, f"olb_trace_moments_{sfx}")(
-            C.byref(dtab.c), 0, dtab.table.num_surfaces, C.byref(la) if la is not None else None, C.byref(c_rays), None,
-            n, _lib.TF_NO_FINAL, cen, C.c_void_p(moments.data_ptr()), _ptr(status), C.c_void_p(stream))
+            C.byref(dtab.c), 0, dtab.table.num_surfaces if last is None else last, C.byref(la) if la is not None else None,
+            C.byref(c_rays), None, n, flags, cen, C.c_void_p(moments.data_ptr()), _ptr(status), C.c_void_p(stream))
     _lib.check(rc, f"olb_trace_moments_{sfx}")
     if own_status:
         _raise_status(status)

@@ -70,6 +70,31 @@ class OracleEngine:
             res["i_pol"] = torch.from_numpy(O.polarized_intensity(out["p"], L, M, N, i0, polarization)).to(Px.dtype)
         return res
 
+    def spot_moments(self, table, Px, Py, affine, center=(0.0, 0.0), last=None, global_xy=False, every_ray=False):
+        from oracle import trace_oracle as O
+        from optiland_b200.launch import launch_from_affine
+
+        self.calls.append(("moments", table.num_surfaces, int(Px.numel())))
+        px, py = Px.detach().double().numpy(), Py.detach().double().numpy()
+        x, y, z, L, M, N = launch_from_affine(px, py, affine)
+        inp = dict(x=x, y=y, z=z, L=L, M=M, N=N, i=np.full_like(px, affine.get("intensity", 1.0)),
+                   w=np.full_like(px, table.wavelengths[0]))
+        last = table.num_surfaces if last is None else last
+        fin, rec, _ = O.trace(table, inp, 0, last)
+        gx, gy, ii, oo = rec["x"][-1], rec["y"][-1], rec["intensity"][-1], rec["opd"][-1]
+        if not global_xy:
+            s = table.surfaces[last - 1]
+            d = np.stack([gx - s.t[0], gy - s.t[1], rec["z"][-1] - s.t[2]])
+            loc = np.asarray(s.R).T @ d
+            gx, gy = loc[0], loc[1]
+        dx, dy = gx - center[0], gy - center[1]
+        fin_ok = np.isfinite(dx) & np.isfinite(dy)
+        keep = np.ones_like(fin_ok) if every_ray else ((ii > 0) & fin_ok)
+        m = [float(keep.sum()), float(dx[keep].sum()), float(dy[keep].sum()), float((dx[keep] ** 2 + dy[keep] ** 2).sum()),
+             float(ii[keep].sum()), float(oo[keep].sum()), float((oo[keep] ** 2).sum()),
+             0.0 if every_ray else float(((ii > 0) & ~fin_ok).sum())]
+        return m
+
     def trace_wavefront(self, table, Px, Py, affine, ref, polarized=False):
         import torch
 

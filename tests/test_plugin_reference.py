@@ -226,6 +226,57 @@ def test_spot_diagram_runs_unchanged_on_top(plugin):
             assert float(rms[f][w]) == pytest.approx(golden[f][w], rel=1e-9)
 
 
+def test_spot_statistics_from_the_moments_epilogue(plugin):
+    """f-2 wired in: SpotDiagram.rms_spot_radius / centroid and the rms_spot_size operand are served by moment launches
+    (no per-ray output); the per-ray spot data appears only when something reads it."""
+    P, eng, be = plugin
+    from optiland.analysis import SpotDiagram
+    from optiland.optimization.operand.ray import RayOperand
+    from optiland.samples.objectives import CookeTriplet
+    from optiland.samples.telescopes import HubbleTelescope
+
+    golden = [[0.003791335461448, 0.004293689564257, 0.006195618755672],
+              [0.01582480029344623, 0.016918412809703662, 0.019221165873836682],
+              [0.013236232767092956, 0.012116688566406967, 0.013648684944411313]]
+    for reference in ("chief_ray", "centroid"):
+        be.set_backend("numpy")
+        ref_spot = SpotDiagram(CookeTriplet(), reference=reference)
+        want = np.array(ref_spot.rms_spot_radius(), dtype=np.float64)
+        want_c = np.array(ref_spot.centroid(), dtype=np.float64)
+        be.set_backend("torch")
+        n0 = len(eng.calls)
+        spot = SpotDiagram(CookeTriplet(), reference=reference)
+        rms = spot.rms_spot_radius()
+        cen = spot.centroid()
+        kinds = [c[0] for c in eng.calls[n0:]]
+        assert kinds.count("moments") >= 9
+        assert not any(c[0] == "pupil" and c[2] > 1 for c in eng.calls[n0:])      # no full-grid records were traced
+        got = np.array([[float(v) for v in row] for row in rms])
+        np.testing.assert_allclose(got, want, rtol=1e-9)
+        np.testing.assert_allclose(np.array([[float(v) for v in c] for c in cen]), want_c, rtol=0, atol=1e-10)
+        if reference == "chief_ray":
+            np.testing.assert_allclose(got, np.array(golden), rtol=1e-9)          # tests/test_analysis.py:88-102
+        # reading the data materialises it: one record launch per spot, same numbers as the reference's eager arrays
+        geo = spot.geometric_spot_radius()
+        be.set_backend("numpy")
+        want_geo = np.array(ref_spot.geometric_spot_radius(), dtype=np.float64)
+        be.set_backend("torch")
+        np.testing.assert_allclose(np.array([[float(v) for v in row] for row in geo]), want_geo, rtol=1e-9)
+        assert any(c[0] == "pupil" and c[2] > 1 for c in eng.calls[n0:])
+    # the operand: single wavelength and "all", image surface and an inner surface; Hubble has an obscuration
+    for make, args in ((CookeTriplet, dict(surface_number=-1, Hx=0.0, Hy=0.7, num_rays=8, wavelength=0.55)),
+                       (CookeTriplet, dict(surface_number=4, Hx=0.0, Hy=1.0, num_rays=6, wavelength="all")),
+                       (HubbleTelescope, dict(surface_number=-1, Hx=0.0, Hy=1.0, num_rays=8, wavelength=0.55))):
+        be.set_backend("numpy")
+        want = float(RayOperand.rms_spot_size(make(), distribution="hexapolar", **args))
+        be.set_backend("torch")
+        n0 = len(eng.calls)
+        got = float(RayOperand.rms_spot_size(make(), distribution="hexapolar", **args))
+        assert all(c[0] == "moments" for c in eng.calls[n0:]) and len(eng.calls) > n0, eng.calls[n0:]
+        assert got == pytest.approx(want, rel=1e-9)
+    assert not any("spot moments" in k for k in P.stats()), P.stats()
+
+
 def test_declines_and_falls_back_to_reference_python(plugin):
     P, eng, be = plugin
     from optiland.samples.objectives import CookeTriplet

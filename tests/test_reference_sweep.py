@@ -50,7 +50,7 @@ def test_reference_tests_unchanged_with_plugin(fname):
 
 
 @pytest.mark.timeout(900)
-@pytest.mark.parametrize("fname", ["analysis/test_spot_reference.py", "test_wavefront.py"])
+@pytest.mark.parametrize("fname", ["analysis/test_spot_reference.py", "test_wavefront.py", "test_operand.py"])
 def test_reference_tests_unchanged_with_plugin_grad_mode_off(fname):
     """Same with be.grad_mode left off (the reference's conftest normally turns it on): now the plain trace
     and the fused in-kernel launch generation (RealRayTracer.trace wrapper) carry the calls; for
@@ -62,7 +62,7 @@ def test_reference_tests_unchanged_with_plugin_grad_mode_off(fname):
 
 
 GPU_FILES = ["test_surface_group.py", "test_wavefront.py", "analysis/test_spot_reference.py", "test_analysis.py",
-             "test_operand.py", "test_torch_optimization.py", "test_tolerancing.py"]
+             "test_operand.py", "test_torch_optimization.py", "test_tolerancing.py", "optimization/test_batched_evaluator.py"]
 
 
 @pytest.mark.gpu
