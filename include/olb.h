@@ -390,7 +390,9 @@ int olb_trace_host_f64(const OlbDeviceTable* table, int32_t first, int32_t last,
                        void* dev_scratch, int64_t dev_scratch_bytes, uint32_t flags,
                        int32_t* status);
 /* Same pipeline with the launch state generated on the device from HOST pupil arrays
- * (launch->Px, launch->Py are host pointers): 8 B/ray cross PCIe instead of 28-32 B/ray. */
+ * (launch->Px, launch->Py are host pointers): 8 B/ray cross PCIe instead of 28-32 B/ray.  launch->Hx / Hy (host
+ * arrays, optional, together) give every ray its own field point -- RealRayTracer.trace_generic's call shape; for a
+ * table with several wavelengths the per-ray wavelengths are read from h_out->w (host). */
 int olb_trace_host_pupil_f32(const OlbDeviceTable* table, int32_t first, int32_t last,
                              const OlbPupilLaunch* launch, const OlbRays* h_out,
                              const OlbRecords* rec, int64_t n_rays, int64_t chunk_rays,

@@ -1204,9 +1204,10 @@ static int trace_host_impl(const OlbDeviceTable* table, int32_t first, int32_t l
   OlbRays pupil_in{};
   if (launch) {   // slots 0/1 carry Px/Py instead of x/y; the rest of the launch state is generated on the device
     if (!launch->Px || !launch->Py) return fail(OLB_ERR_INVALID_ARG, "launch.Px / launch.Py is NULL");
-    if (launch->Hx || launch->Hy)
-      return fail(OLB_ERR_UNSUPPORTED, "per-ray field arrays (launch.Hx / Hy) are not built for the host-buffer entry points");
+    if ((launch->Hx == nullptr) != (launch->Hy == nullptr)) return fail(OLB_ERR_INVALID_ARG, "launch.Hx and launch.Hy go together");
+    // per-ray field points (trace_generic's call shape): two more host arrays ride in the z / L slots
     pupil_in.x = const_cast<void*>(launch->Px); pupil_in.y = const_cast<void*>(launch->Py);
+    pupil_in.z = const_cast<void*>(launch->Hx); pupil_in.L = const_cast<void*>(launch->Hy);
     pupil_in.w = h_out ? h_out->w : nullptr;
     h_in = &pupil_in;
   }
@@ -1248,9 +1249,10 @@ static int trace_host_impl(const OlbDeviceTable* table, int32_t first, int32_t l
     const int s = ci % NS;
     cudaStream_t q = st[s];
     // slot reuse is ordered by the stream itself (chunk ci and ci+2 share stream + slot)
+    const bool per_ray_fields = launch && launch->Hx != nullptr;
     for (int k = 0; k < 8; ++k) {
       if (k == 7 && !need_w) continue;
-      if (launch && k >= 2 && k != 7) continue;
+      if (launch && k >= 2 && k != 7 && !(per_ray_fields && k <= 3)) continue;
       cudaError_t e = cudaMemcpyAsync(slot[s][k], (const T*)in[k] + done, (size_t)m * sizeof(T), cudaMemcpyHostToDevice, q);
       if (e != cudaSuccess) { result = fail(OLB_ERR_CUDA, cudaGetErrorString(e)); break; }
     }
@@ -1276,6 +1278,7 @@ static int trace_host_impl(const OlbDeviceTable* table, int32_t first, int32_t l
       dl = *launch;
       dl.Px = slot[s][0];
       dl.Py = slot[s][1];
+      if (per_ray_fields) { dl.Hx = slot[s][2]; dl.Hy = slot[s][3]; }   // (read by each thread before it writes z / L)
     }
     result = trace_impl<T>(&wh, first, last, &d, rp, m, flags & ~uint32_t(OLB_TF_NO_FINAL), status, q,
                            launch ? &dl : nullptr);

@@ -234,6 +234,33 @@ def _prepare(engine, table, device) -> None:
 
 
 _launch_cache: OrderedDict = OrderedDict()
+_dist_cache: OrderedDict = OrderedDict()
+_DETERMINISTIC_DISTRIBUTIONS = ("hexapolar", "uniform", "line_x", "line_y", "positive_line_x", "positive_line_y", "cross", "ring")
+
+
+def _distribution(be, name: str, num_rays):
+    """``create_distribution(name).generate_points(num_rays)`` (optiland/distribution.py:415-446), memoised for the
+    deterministic patterns: the reference regenerates the same pupil grid on every ``Optic.trace`` call -- a Python loop
+    over the rings of a hexapolar pattern (distribution.py:209-220), 64 iterations for SpotDiagram's 64 rings, 1 154
+    for a 4 M-ray pupil -- which costs more than the fused launch it feeds.  The arrays are shared read-only (no
+    consumer mutates ``distribution.x`` in place)."""
+    from optiland.distribution import create_distribution
+
+    if name not in _DETERMINISTIC_DISTRIBUTIONS:
+        d = create_distribution(name)
+        d.generate_points(num_rays)
+        return d
+    key = (name, int(num_rays), str(be.get_precision()), str(be.get_device()) if hasattr(be, "get_device") else "")
+    d = _dist_cache.get(key)
+    if d is None:
+        d = create_distribution(name)
+        d.generate_points(num_rays)
+        _dist_cache[key] = d
+        while len(_dist_cache) > 32:
+            _dist_cache.popitem(last=False)
+    else:
+        _dist_cache.move_to_end(key)
+    return d
 
 
 def _object_key(obj) -> tuple:
@@ -569,10 +596,8 @@ def install(engine=None, alias: str | None = None) -> None:
             object-space telecentric system) without apodization; with ``optic.polarization`` set the rays are
             ``PolarizedRays`` (Fresnel coatings included) and ``update_intensity`` runs as the kernel's epilogue."""
             import numpy as _np
-            from optiland.distribution import create_distribution
 
             from .launch import pupil_affine
-            from .pack import launch_scalars
 
             optic = tracer.optic
             if getattr(_tls, "in_reference", False) or _wants_grad(self, list(optic.surfaces.surfaces)):
@@ -592,8 +617,7 @@ def install(engine=None, alias: str | None = None) -> None:
                 return _fused_decline("non-paraxial ray aiming")
             tracer._validate_normalized_coordinates(Hx, Hy, "field")
             if isinstance(distribution, str):
-                distribution = create_distribution(distribution)
-                distribution.generate_points(num_rays)
+                distribution = _distribution(be, distribution, num_rays)
             Px, Py = distribution.x, distribution.y
             engine = _state["engine"]
             if not (engine.accepts_tensor(Px) and engine.accepts_tensor(Py)):

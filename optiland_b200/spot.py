@@ -103,8 +103,6 @@ def _scalar(be, v) -> float:
 
 def _fused_inputs(P, backend, be, optic, Hx, Hy, wavelength, num_rays, distribution):
     """(table, Px, Py, affine) of a single-field, single-wavelength fused launch, or None (with the reason counted)."""
-    from optiland.distribution import create_distribution
-
     from .launch import pupil_affine
     from .pack import pack_surface_group
 
@@ -124,8 +122,7 @@ def _fused_inputs(P, backend, be, optic, Hx, Hy, wavelength, num_rays, distribut
     if getattr(optic.ray_tracer, "ray_aiming_config", {}).get("mode", "paraxial") != "paraxial":
         return P._fused_decline("spot moments: non-paraxial ray aiming")
     if isinstance(distribution, str):
-        distribution = create_distribution(distribution)
-        distribution.generate_points(num_rays)
+        distribution = P._distribution(be, distribution, num_rays)
     Px, Py = distribution.x, distribution.y
     if not (engine.accepts_tensor(Px) and engine.accepts_tensor(Py)):
         return P._fused_decline("spot moments: pupil samples not resident on a CUDA device")
@@ -158,11 +155,7 @@ def rms_spot_size(P, backend, be, optic, surface_number, Hx, Hy, num_rays, wavel
     else:
         wls, ref = [float(wavelength)], 0
     if isinstance(distribution, str):
-        from optiland.distribution import create_distribution
-
-        d = create_distribution(distribution)
-        d.generate_points(num_rays)
-        distribution = d
+        distribution = P._distribution(be, distribution, num_rays)
     jobs = []
     for wl in wls:
         inp = _fused_inputs(P, backend, be, optic, Hx, Hy, wl, num_rays, distribution)

@@ -554,6 +554,9 @@ def trace_host(dtab: DeviceTable, h_in: dict, h_out: dict, n: int, dtype=torch.f
     if scratch is None or scratch.numel() < need:
         scratch = torch.empty(need, dtype=torch.uint8, device=dtab.device)
     c_out = _lib.OlbRays(**{k: h_out[k].data_ptr() for k in ("x", "y", "z", "L", "M", "N", "i", "opd")})
+    if affine is not None and dtab.table.n_wl > 1:
+        # (pupil launch: the per-ray wavelengths travel in h_out.w -- include/olb.h, olb_trace_host_pupil_*)
+        c_out.w = (h_in["w"] if "w" in h_in else h_out["w"]).data_ptr()
     if affine is not None:
         # HOST pupil arrays in (8 B/ray over PCIe), launch state generated on the device
         la = _c_launch(affine, h_in["Px"], h_in["Py"])

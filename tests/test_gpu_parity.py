@@ -193,6 +193,38 @@ def test_host_buffer_path_matches_device_path():
         assert np.array_equal(a, b, equal_nan=True), k
 
 
+@pytest.mark.parametrize("name", ["generic_dgauss", "generic_litho"])
+def test_host_buffer_pupil_launch_with_per_ray_fields(name):
+    """olb_trace_host_pupil_* with launch.Hx / Hy (trace_generic's call shape from HOST arrays: pupil and field
+    coordinates + wavelengths cross PCIe, the launch state is generated on the device) == the device-resident launch,
+    bit for bit, and the reference's records within tolerance."""
+    from optiland_b200.launch import pupil_affine_fields
+    from optiland_b200.trace import DeviceTable, trace_host, trace_pupil_device
+
+    c = Case(name)
+    sc = {k[9:]: float(c.z[k]) for k in c.z.files if k.startswith("x_launch_")}
+    n = 200_003
+    rng = np.random.default_rng(2)
+    idx = rng.integers(0, c.n, size=n)
+    host = {k: torch.from_numpy(np.ascontiguousarray(c.extra(k)[idx])).pin_memory() for k in ("Px", "Py", "Hx", "Hy")}
+    w_host = torch.from_numpy(np.ascontiguousarray(c.rays["w"][idx])).pin_memory()
+    h_out = {k: torch.empty(n, dtype=torch.float64).pin_memory() for k in ("x", "y", "z", "L", "M", "N", "i", "opd")}
+    h_out["w"] = w_host
+    dt = DeviceTable(c.table)
+    aff_h = pupil_affine_fields(sc, host["Hx"], host["Hy"])
+    trace_host(dt, {"Px": host["Px"], "Py": host["Py"], "w": w_host}, h_out, n, torch.float64, chunk=50_000, affine=aff_h)
+    dev = {k: v.cuda() for k, v in host.items()}
+    rays, rec = trace_pupil_device(dt, dev["Px"], dev["Py"], pupil_affine_fields(sc, dev["Hx"], dev["Hy"]), 0,
+                                   c.table.num_surfaces, wavelength=w_host.cuda() if c.table.n_wl > 1 else None)
+    for k in ("x", "y", "z", "L", "M", "N", "i", "opd"):
+        assert np.array_equal(h_out[k].numpy(), getattr(rays, k).cpu().numpy(), equal_nan=True), k
+    # and against the reference: the fixture's own rays are among the resampled ones
+    first = {int(j): q for q, j in reversed(list(enumerate(idx)))}
+    sel = np.array([first[j] for j in sorted(first)])
+    want = c.out["y"][np.array(sorted(first))]
+    assert np.nanmax(np.abs(h_out["y"].numpy()[sel] - want)) <= 1e-11 * c.scale
+
+
 @pytest.mark.parametrize("name", ["zernike_polarized_c5", "cooke_polarized", "tilted_fold_polarized"])
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
 def test_polarized_trace_vs_reference_golden(name, dtype):

@@ -613,6 +613,24 @@ def test_huygens_psf_strategy_is_routed_through_the_engine(plugin):
     np.testing.assert_allclose(be.to_numpy(got), ref, rtol=0, atol=1e-8 * ref.max())
 
 
+def test_fft_psf_takes_its_pupil_function_from_the_fused_wavefront_epilogue(plugin):
+    """FFTPSF (psf/fft.py:123-200): its pupil function A exp(-2 pi i OPD) on the uniform pupil grid comes from
+    ``Wavefront.get_data`` -- under the plugin ONE fused launch (launch generation + trace + OPD against the reference
+    sphere + intensity, 5 values per grid point); the gridding itself is five element-wise ops on the num_rays^2 grid in
+    front of the library FFT and stays the reference's.  Same PSF as the NumPy reference."""
+    P, eng, be = plugin
+    from optiland.psf import FFTPSF
+    from optiland.samples.objectives import CookeTriplet
+
+    be.set_backend("numpy")
+    ref = np.array(FFTPSF(CookeTriplet(), field=(0, 0.7), wavelength=0.55, num_rays=64, grid_size=128).psf)
+    be.set_backend("torch")
+    n0 = len(eng.calls)
+    got = FFTPSF(CookeTriplet(), field=(0, 0.7), wavelength=0.55, num_rays=64, grid_size=128).psf
+    assert any(c[0] == "wavefront" for c in eng.calls[n0:]), eng.calls[n0:]
+    np.testing.assert_allclose(be.to_numpy(got), ref, rtol=0, atol=2e-6 * ref.max())
+
+
 def test_launch_form_reproduces_the_reference_ray_generator_known_answers():
     """/root/reference/tests/test_rays.py:685-714: TessarLens, H = (0.5, 0.5), P = (0.1, 0.1), (0.2, 0.2) -- the
     reference's hard-coded launch rays, reproduced by pack.launch_scalars + launch.pupil_affine (the form the kernel
