@@ -52,6 +52,19 @@ def _decline(reason: str):
     return False
 
 
+_RESET_ATTRS = ("y", "u", "x", "z", "L", "M", "N", "intensity", "aoi", "opd")
+
+
+def _reset_records(be, surface_group) -> None:
+    """``SurfaceGroup.reset()`` (surfaces/surface_group.py:373-380 -> standard_surface.py:285-299) without its 11
+    allocations per surface: every attribute gets ONE shared empty array (143 ``be.empty(0)`` calls on the Double-Gauss,
+    0.5 ms on a CUDA device, were the largest single item of a small ``Optic.trace`` through the plugin)."""
+    e = be.empty(0)
+    for surf in surface_group.surfaces:
+        for attr in _RESET_ATTRS:
+            setattr(surf, attr, e)
+
+
 def _fused_decline(reason: str):
     """A fused entry point (Optic.trace / trace_generic / Wavefront) hands the call to the next level down -- the
     reference's RayGenerator followed by the SurfaceGroup.trace capability -- and says why (``stats()``)."""
@@ -635,7 +648,7 @@ def install(engine=None, alias: str | None = None) -> None:
                 return _fused_decline("first surface is not an object surface")
             rec = engine.trace_pupil(table, Px, Py, pupil_affine(sc), polarization=state) if polarized else \
                 engine.trace_pupil(table, Px, Py, pupil_affine(sc))
-            optic.surfaces.reset()
+            _reset_records(be, optic.surfaces)
             for row, surf in enumerate(optic.surfaces.surfaces):
                 for attr, key in _REC_ATTR:
                     setattr(surf, attr, rec[key][row])
@@ -718,7 +731,7 @@ def install(engine=None, alias: str | None = None) -> None:
             # (trace_generic does NOT run update_intensity, real_ray_tracer.py:143-152: P matrices only)
             kw = {"polarization": "matrix"} if polarized else {}
             rec = engine.trace_pupil(table, Px, Py, aff, wavelength=w if len(wls) > 1 else None, **kw)
-            optic.surfaces.reset()
+            _reset_records(be, optic.surfaces)
             for row, surf in enumerate(optic.surfaces.surfaces):
                 for attr, key in _REC_ATTR:
                     setattr(surf, attr, rec[key][row])
@@ -836,7 +849,7 @@ def install(engine=None, alias: str | None = None) -> None:
     def group_trace(self, rays, skip=0):
         backend = registry.get(be.get_backend())
         if hasattr(backend, "trace_surfaces") and not getattr(_tls, "in_reference", False):
-            self.reset()
+            _reset_records(be, self)
             if backend.trace_surfaces(self, rays, skip, len(self.surfaces)):
                 return rays
         _tls.in_reference = True
@@ -909,6 +922,23 @@ def install(engine=None, alias: str | None = None) -> None:
         backend = registry.get(be.get_backend())
         return bool(backend.grad_mode.requires_grad) or any(getattr(t, "requires_grad", False) for t in tensors)
 
+    # A helper of the reference's paraxial layer that dominates every trace of a CHANGED system: the launch scalars
+    # (EPL, EPD, the object-space offset) read ``SurfaceGroup.positions`` eight times, and each read builds one
+    # RealRays object per surface just to globalize the point (0, 0, 0) (coordinate_system.py:109-120) -- 21 of the
+    # 24 ms of an Optic.trace after a parameter change (profiles/r2_profile_small_changed.txt).  For a frame without a
+    # parent the globalized origin IS (cs.x, cs.y, cs.z) (rotating the zero vector changes nothing), with the same
+    # autograd connectivity; nested frames keep the reference's code.
+    from optiland.coordinate_system import CoordinateSystem
+
+    orig_position = CoordinateSystem.position_in_gcs
+
+    def _position_in_gcs(self):
+        if self.reference_cs is None and _state.get("fast_positions", True):
+            return be.atleast_1d(self.x) + 0.0, be.atleast_1d(self.y) + 0.0, be.atleast_1d(self.z) + 0.0
+        return orig_position.fget(self)
+
+    CoordinateSystem.position_in_gcs = property(_position_in_gcs)
+
     # f-2: spot statistics from the moments epilogue (RayOperand.rms_spot_size, SpotDiagram.rms_spot_radius / centroid)
     from . import spot as _spot
 
@@ -922,7 +952,8 @@ def install(engine=None, alias: str | None = None) -> None:
     RealRayTracer.trace_generic = tracer_generic
     _state.update(installed=True, orig_group_trace=orig_group_trace, orig_surface_trace=orig_surface_trace,
                   orig_tracer_trace=orig_tracer_trace, orig_tracer_generic=orig_tracer_generic, orig_hf_compute=orig_hf_compute, orig_chief_compute=orig_chief_compute,
-                  old_backend=old, alias=alias, fuse_launch=True, fuse_wavefront=True, fuse_spot=True, saved_spot=saved_spot)
+                  old_backend=old, alias=alias, fuse_launch=True, fuse_wavefront=True, fuse_spot=True, saved_spot=saved_spot,
+                  orig_position=orig_position, fast_positions=True)
 
 
 def uninstall() -> None:
@@ -949,6 +980,10 @@ def uninstall() -> None:
         from . import spot as _spot
 
         _spot.uninstall(_state["saved_spot"])
+    if _state.get("orig_position") is not None:
+        from optiland.coordinate_system import CoordinateSystem
+
+        CoordinateSystem.position_in_gcs = _state["orig_position"]
     if _state.get("old_backend") is not None:
         registry["torch"] = _state["old_backend"]
     if _state.get("alias"):
