@@ -1,16 +1,17 @@
 """TEST INFRASTRUCTURE ONLY -- CPU restatement (NumPy, fp64) of Optiland's real-ray trace loop.
 
 This is the parity oracle for libolb.  It is NOT part of the product: only
-``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
-``--impl reference`` legs may import it; the product path
+``tests/``, ``__graft_entry__.smoke()`` and ``bench.py`` (its parity gate, and the
+``cpu_baseline_port`` / fallback ``--impl reference`` legs) may import it; the product path
 (``optiland_b200.*``) never does and fails loudly without the CUDA library.
 
-Parity is PINNED: ``tests/test_oracle_vs_reference.py`` (run in the build
-container, where /root/reference is importable) checks this restatement against
-the unmodified reference on the sample systems, and ``tests/test_oracle_golden.py``
-checks it against the committed fixtures in ``tests/golden/`` which were produced
-by the unmodified reference (``oracle/make_golden.py``) and against the reference's
-own hard-coded known-answer vectors (tests/test_geometries.py etc.).
+Parity is PINNED: ``tests/test_oracle_golden.py`` checks this restatement against the
+committed fixtures in ``tests/golden/``, which were produced by the unmodified reference
+(``oracle/make_golden.py``, run in the build container where /root/reference is
+importable), and against the reference's own hard-coded known-answer vectors
+(tests/test_geometries.py etc.); ``tests/test_plugin_reference.py[oracle]`` runs it
+under the live reference's own objects (test-only engine, ``oracle/oracle_engine.py``)
+and compares with the reference's NumPy backend call by call.
 
 Each function cites the reference file:line (relative to /root/reference) whose
 arithmetic it restates, operation for operation, so that fp64 results agree with
