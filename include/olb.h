@@ -259,7 +259,8 @@ typedef struct OlbDeviceTable {
   int32_t n_wl;
   int32_t off_f64, bytes_f64;   /* fp64 blob inside workspace */
   int32_t off_f32, bytes_f32;   /* fp32 blob inside workspace */
-  int32_t bwd_supported;        /* 1 if olb_trace_bwd_* covers every surface of the table */
+  int32_t bwd_supported;        /* 1 if olb_trace_bwd_* covers every surface of the table; 2: covered, and the table has
+                                   polynomial / Zernike surfaces whose gradients need olb_trace_bwd_tables_*       */
   int32_t bwd_slots;            /* gradient accumulator slots per thread (backward kernel)   */
   int32_t n_systems;            /* 1, or the number of systems of a batched table            */
   int32_t stride_f64;           /* bytes between consecutive systems' fp64 / fp32 blobs      */
@@ -329,11 +330,22 @@ typedef struct OlbPupilLaunch {
   const void* Hx;
   const void* Hy;
   int32_t field_mode;
-  int32_t reserved;
+  int32_t n_vig;             /* number of entries of `vig` (0: no vignetting factors), <= OLB_MAX_VIG_FIELDS              */
   double field_arg;
   double origin_field[2];
   double target_field[2];
+  /* Vignetting factors per ray, looked up in-kernel (with Hx / Hy): FieldGroup.get_vig_factor
+   * (optiland/fields/field_group.py:93-122) is a nearest-neighbour lookup over the DEFINED fields; vig[j] =
+   * {Hx_j, Hy_j, vx_j, vy_j} (normalised field coordinates).  The ray's pupil point is scaled by (1 - vx, 1 - vy),
+   * `vig_power` times in succession: RealRayTracer.trace_generic applies the factors once itself
+   * (raytrace/real_ray_tracer.py:134-137) and the paraxial aimer once more (rays/ray_aiming/paraxial.py:72-96), so that
+   * call shape passes 2.  Nearest = smallest squared distance in fp64, the first of equals (torch's cdist + argmin;
+   * exact ties between two fields are resolved by rounding there and by a k-d tree in the NumPy backend). */
+  int32_t vig_power;
+  int32_t reserved;
+  double vig[16][4];
 } OlbPupilLaunch;
+#define OLB_MAX_VIG_FIELDS 16
 
 /*
  * As olb_trace_*, but the launch state comes from `launch`.  `out` receives the final state
@@ -443,6 +455,29 @@ int olb_trace_bwd_f64(const OlbDeviceTable* table, int32_t first, int32_t last,
                       const OlbRays* rays_in, const OlbRecords* rec, const OlbRecords* grad_rec,
                       const OlbRays* grad_rays_in, double* grad_params, int64_t n_rays,
                       uint64_t grad_row_mask, void* stream);
+
+/*
+ * The same with TABLE gradients for the polynomial families (OlbDeviceTable.bwd_supported == 2: the table holds
+ * OLB_GEOM_POLYNOMIAL / OLB_GEOM_ZERNIKE surfaces of at most 12 x 12 monomials).  The adjoint goes through the
+ * intersection by the implicit-function theorem with the TRUE gradient of the sag polynomial and through the normal with
+ * the Hessian of the reference's slope polynomial (whose Zernike form omits the normalisation constants,
+ * optiland/zernike/base.py:104-136).  grad_tables: n_surfaces blocks of OLB_GT_PER_SURFACE doubles, ACCUMULATED --
+ *   [0 .. 143]   dLoss/dS_ij, S = the prepared sag table   (sag += sum_ij S_ij xn^i yn^j, entry i * 12 + j)
+ *   [144 .. 287] dLoss/dD_ij, D = the prepared slope table
+ * in which the user's coefficients are linear: polynomial C_ij = S_ij = D_ij; Zernike S = sum_k c_k N_k M_k,
+ * D = sum_k c_k M_k with M_k the monomial expansion of the unit term (optiland_b200.table.zernike_monomials), so
+ * dLoss/dc_k = N_k <M_k, dLoss/dS> + <M_k, dLoss/dD>.  (Zernike variables: optiland/geometries/zernike.py:182-252.)
+ */
+#define OLB_GT_DIM 12
+#define OLB_GT_PER_SURFACE (2 * OLB_GT_DIM * OLB_GT_DIM)
+int olb_trace_bwd_tables_f32(const OlbDeviceTable* table, int32_t first, int32_t last,
+                             const OlbRays* rays_in, const OlbRecords* rec, const OlbRecords* grad_rec,
+                             const OlbRays* grad_rays_in, double* grad_params, double* grad_tables, int64_t n_rays,
+                             uint64_t grad_row_mask, void* stream);
+int olb_trace_bwd_tables_f64(const OlbDeviceTable* table, int32_t first, int32_t last,
+                             const OlbRays* rays_in, const OlbRecords* rec, const OlbRecords* grad_rec,
+                             const OlbRays* grad_rays_in, double* grad_params, double* grad_tables, int64_t n_rays,
+                             uint64_t grad_row_mask, void* stream);
 
 /*
  * Fused wavefront epilogue (second half): instead of (or besides) records / the final state,

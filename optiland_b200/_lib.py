@@ -32,6 +32,8 @@ BP_COUNT = BP_COEF + BP_MAX_COEF
 GP_TX, GP_TY, GP_TZ, GP_CURV, GP_CONIC, GP_N1, GP_N2, GP_COEF, GP_MAX_COEF = 0, 1, 2, 3, 4, 5, 6, 7, 12
 GP_R = GP_COEF + GP_MAX_COEF      # 9 entries: dLoss/dR of a tilted pose (row-major)
 GP_COUNT = GP_R + 9
+GT_DIM = 12
+GT_PER_SURFACE = 2 * GT_DIM * GT_DIM
 
 
 class OlbTable(C.Structure):
@@ -55,8 +57,9 @@ class OlbRecords(C.Structure):
 class OlbPupilLaunch(C.Structure):
     _fields_ = [("Px", C.c_void_p), ("Py", C.c_void_p), ("origin0", C.c_double * 3), ("origin_scale", C.c_double * 2),
                 ("target0", C.c_double * 3), ("target_scale", C.c_double * 2), ("intensity", C.c_double),
-                ("Hx", C.c_void_p), ("Hy", C.c_void_p), ("field_mode", C.c_int32), ("reserved", C.c_int32),
-                ("field_arg", C.c_double), ("origin_field", C.c_double * 2), ("target_field", C.c_double * 2)]
+                ("Hx", C.c_void_p), ("Hy", C.c_void_p), ("field_mode", C.c_int32), ("n_vig", C.c_int32),
+                ("field_arg", C.c_double), ("origin_field", C.c_double * 2), ("target_field", C.c_double * 2),
+                ("vig_power", C.c_int32), ("reserved", C.c_int32), ("vig", (C.c_double * 4) * 16)]
 
 
 class OlbWavefrontRef(C.Structure):
@@ -99,6 +102,12 @@ SYMBOLS = {
                                     _P(OlbRecords), _P(OlbRays), C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p]),
     "olb_trace_bwd_f64": (C.c_int, [_P(OlbDeviceTable), C.c_int32, C.c_int32, _P(OlbRays), _P(OlbRecords),
                                     _P(OlbRecords), _P(OlbRays), C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p]),
+    "olb_trace_bwd_tables_f32": (C.c_int, [_P(OlbDeviceTable), C.c_int32, C.c_int32, _P(OlbRays), _P(OlbRecords),
+                                           _P(OlbRecords), _P(OlbRays), C.c_void_p, C.c_void_p, C.c_int64, C.c_uint64,
+                                           C.c_void_p]),
+    "olb_trace_bwd_tables_f64": (C.c_int, [_P(OlbDeviceTable), C.c_int32, C.c_int32, _P(OlbRays), _P(OlbRecords),
+                                           _P(OlbRecords), _P(OlbRays), C.c_void_p, C.c_void_p, C.c_int64, C.c_uint64,
+                                           C.c_void_p]),
     "olb_trace_pupil_f32": (C.c_int, [_P(OlbDeviceTable), C.c_int32, C.c_int32, _P(OlbPupilLaunch), _P(OlbRays),
                                       _P(OlbRecords), C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p]),
     "olb_trace_pupil_f64": (C.c_int, [_P(OlbDeviceTable), C.c_int32, C.c_int32, _P(OlbPupilLaunch), _P(OlbRays),

@@ -50,9 +50,73 @@ def table_to_params(table: T.SurfaceTable) -> torch.Tensor:
     return torch.from_numpy(p)
 
 
-def params_to_table(table: T.SurfaceTable, params: torch.Tensor) -> T.SurfaceTable:
-    """``table`` with its differentiable parameters replaced by the VALUES in ``params``."""
+POLY_KINDS = (T.GEOM_POLYNOMIAL, T.GEOM_ZERNIKE)
+
+
+def zernike_norms(spec) -> np.ndarray:
+    """N_nm per Zernike term: from the packer when it ran on live objects, else c N / c (1 where c == 0)."""
+    if spec.zernike_norms is not None:
+        return np.asarray(spec.zernike_norms, dtype=np.float64)
+    cf = spec.coefficients.reshape(-1, 4)
+    with np.errstate(all="ignore"):
+        return np.where(cf[:, 3] != 0, cf[:, 2] / np.where(cf[:, 3] != 0, cf[:, 3], 1.0), 1.0)
+
+
+def table_to_coefs(table: T.SurfaceTable) -> torch.Tensor | None:
+    """(S, K) fp64 tensor of the USER coefficients of the polynomial-family surfaces (Zernike: c_k in term order;
+    polynomial: C_ij row-major), zero-padded to the longest; None when the table has none."""
+    rows = []
+    for spec in table.surfaces:
+        if spec.kind == T.GEOM_ZERNIKE:
+            rows.append(spec.coefficients.reshape(-1, 4)[:, 3].copy())
+        elif spec.kind == T.GEOM_POLYNOMIAL:
+            rows.append(np.atleast_2d(spec.coefficients).ravel().copy())
+        else:
+            rows.append(np.zeros(0))
+    K = max(len(r) for r in rows)
+    if K == 0:
+        return None
+    out = np.zeros((len(rows), K))
+    for s, r in enumerate(rows):
+        out[s, :len(r)] = r
+    return torch.from_numpy(out)
+
+
+def _coef_maps(table: T.SurfaceTable):
+    """Per polynomial-family surface the linear map (table gradients -> coefficient gradients), cached on the table:
+    Zernike: stacks N_k M_k and M_k (K, 12, 12); polynomial: the (rows, cols) shape."""
+    maps = table.__dict__.get("_coef_maps")
+    if maps is None:
+        maps = {}
+        for s, spec in enumerate(table.surfaces):
+            if spec.kind == T.GEOM_ZERNIKE:
+                cf = spec.coefficients.reshape(-1, 4)
+                M = np.stack([T.zernike_monomials(int(n), int(m), _lib.GT_DIM) for n, m in cf[:, :2]]) if len(cf) else np.zeros((0, 12, 12))
+                maps[s] = ("zernike", M * zernike_norms(spec)[:, None, None], M)
+            elif spec.kind == T.GEOM_POLYNOMIAL:
+                maps[s] = ("polynomial", np.atleast_2d(spec.coefficients).shape)
+        table.__dict__["_coef_maps"] = maps
+    return maps
+
+
+def tables_to_coef_grads(table: T.SurfaceTable, gtab: np.ndarray, K: int) -> np.ndarray:
+    """(S, 2, 12, 12) table gradients of olb_trace_bwd_tables_* -> (S, K) gradients of the user coefficients."""
+    out = np.zeros((table.num_surfaces, K))
+    for s, m in _coef_maps(table).items():
+        if m[0] == "zernike":
+            g = np.tensordot(m[1], gtab[s, 0], axes=2) + np.tensordot(m[2], gtab[s, 1], axes=2)
+            out[s, :len(g)] = g
+        else:
+            r, c = m[1]
+            out[s, :r * c] = (gtab[s, 0, :r, :c] + gtab[s, 1, :r, :c]).ravel()
+    return out
+
+
+def params_to_table(table: T.SurfaceTable, params: torch.Tensor, coefs: torch.Tensor | None = None) -> T.SurfaceTable:
+    """``table`` with its differentiable parameters replaced by the VALUES in ``params`` (and, for polynomial-family
+    surfaces, the user coefficients in ``coefs``)."""
     p = params.detach().double().cpu().numpy()
+    cv = coefs.detach().double().cpu().numpy() if coefs is not None else None
     specs = []
     for s, spec in enumerate(table.surfaces):
         ch = dict(t=p[s, GP_TX:GP_TZ + 1].copy(), n1=np.array([p[s, GP_N1]]), n2=np.array([p[s, GP_N2]]))
@@ -63,6 +127,19 @@ def params_to_table(table: T.SurfaceTable, params: torch.Tensor) -> T.SurfaceTab
             ch["conic"] = float(p[s, GP_CONIC])
         if spec.kind in (T.GEOM_EVEN_ASPHERE, T.GEOM_ODD_ASPHERE):
             ch["coefficients"] = p[s, GP_COEF:GP_COEF + len(spec.coefficients)].copy()
+        if spec.kind in POLY_KINDS:
+            ch["radius"] = float("inf") if p[s, GP_CURV] == 0 else 1.0 / p[s, GP_CURV]
+            ch["conic"] = float(p[s, GP_CONIC])
+            if cv is not None:
+                if spec.kind == T.GEOM_ZERNIKE:
+                    cf = spec.coefficients.reshape(-1, 4).copy()
+                    cf[:, 3] = cv[s, :len(cf)]
+                    cf[:, 2] = cf[:, 3] * zernike_norms(spec)
+                    ch["coefficients"] = cf
+                    ch["zernike_norms"] = zernike_norms(spec)
+                else:
+                    shp = np.atleast_2d(spec.coefficients).shape
+                    ch["coefficients"] = cv[s, :shp[0] * shp[1]].reshape(shp).copy()
         specs.append(dataclasses.replace(spec, **ch))
     return T.SurfaceTable(specs, table.wavelengths)
 
@@ -73,7 +150,7 @@ class _TraceFn(torch.autograd.Function):
     tensor per (quantity, row) -- the backward pass then reads gradients only for those rows."""
 
     @staticmethod
-    def forward(ctx, template, device_tables, rows, params, x, y, z, L, M, N, i, opd):
+    def forward(ctx, template, device_tables, rows, params, coefs, x, y, z, L, M, N, i, opd):
         ctx.set_materialize_grads(False)
         lib = _lib.load()
         dtype = x.dtype
@@ -84,12 +161,12 @@ class _TraceFn(torch.autograd.Function):
             dtab = device_tables[0]
             table = dtab.table
         else:
-            table = params_to_table(template, params)
+            table = params_to_table(template, params, coefs)
             dtab = DeviceTable(table, x.device)
             device_tables.append(dtab)
         if not dtab.c.bwd_supported:
-            raise _lib.OlbError("differentiable trace: table not supported by olb_trace_bwd_* (rotated pose, "
-                                "non plane/standard/even-asphere geometry, non-radial aperture, Fresnel coating)")
+            raise _lib.OlbError("differentiable trace: table not supported by olb_trace_bwd_* (a geometry other than plane / "
+                                "standard / even- and odd-asphere / polynomial / Zernike, a Fresnel coating, several wavelengths)")
         n = x.numel()
         S = table.num_surfaces
         # (a slice / view of a larger tensor may start anywhere: the C ABI wants 16-byte aligned arrays)
@@ -108,6 +185,7 @@ class _TraceFn(torch.autograd.Function):
         ctx.dtab, ctx.ins, ctx.buf, ctx.stride, ctx.sfx = dtab, ins, buf, stride, sfx
         ctx.rows = None if rows is None else tuple(r % S for r in rows)
         ctx.params_on_device = params.is_cuda
+        ctx.coefs_meta = None if coefs is None else (coefs.shape[1], coefs.is_cuda, coefs.dtype)
         ctx.needs_ray_grad = any(t.requires_grad for t in (x, y, z, L, M, N, i, opd))
         if ctx.rows is None:
             return tuple(buf[j, :, :n] for j in range(8))
@@ -152,26 +230,41 @@ class _TraceFn(torch.autograd.Function):
         gin = [torch.empty_like(ins[0]) for _ in range(8)] if ctx.needs_ray_grad else None
         c_gin = _lib.OlbRays(**{k: t.data_ptr() for k, t in zip(("x", "y", "z", "L", "M", "N", "i", "opd"), gin)}) if gin else None
         gpar = torch.zeros((S, GP_COUNT), dtype=torch.float64, device=buf.device)
+        tables = int(dtab.c.bwd_supported) == 2
+        gtab = torch.zeros((S, 2, _lib.GT_DIM, _lib.GT_DIM), dtype=torch.float64, device=buf.device) if tables else None
         with torch.cuda.device(buf.device):
             stream = torch.cuda.current_stream(buf.device).cuda_stream
-            rc = getattr(lib, f"olb_trace_bwd_{ctx.sfx}")(
-                C.byref(dtab.c), 0, S, C.byref(c_in), C.byref(c_rec), C.byref(c_grec),
-                C.byref(c_gin) if c_gin is not None else None, C.c_void_p(gpar.data_ptr()), n,
-                C.c_uint64(mask & ((1 << 64) - 1)), C.c_void_p(stream))
+            if tables:
+                # polynomial / Zernike surfaces: table gradients as well (olb_trace_bwd_tables_*)
+                rc = getattr(lib, f"olb_trace_bwd_tables_{ctx.sfx}")(
+                    C.byref(dtab.c), 0, S, C.byref(c_in), C.byref(c_rec), C.byref(c_grec),
+                    C.byref(c_gin) if c_gin is not None else None, C.c_void_p(gpar.data_ptr()),
+                    C.c_void_p(gtab.data_ptr()), n, C.c_uint64(mask & ((1 << 64) - 1)), C.c_void_p(stream))
+            else:
+                rc = getattr(lib, f"olb_trace_bwd_{ctx.sfx}")(
+                    C.byref(dtab.c), 0, S, C.byref(c_in), C.byref(c_rec), C.byref(c_grec),
+                    C.byref(c_gin) if c_gin is not None else None, C.c_void_p(gpar.data_ptr()), n,
+                    C.c_uint64(mask & ((1 << 64) - 1)), C.c_void_p(stream))
         _lib.check(rc, f"olb_trace_bwd_{ctx.sfx}")
         gi = gin if gin is not None else [None] * 8
-        return (None, None, None, gpar if ctx.params_on_device else gpar.cpu(), *gi)
+        gcoef = None
+        if ctx.coefs_meta is not None and tables:
+            # the tables are linear in the user's coefficients: a few hundred doubles, mapped on the host
+            K, on_dev, cdt = ctx.coefs_meta
+            gc = torch.from_numpy(tables_to_coef_grads(dtab.table, gtab.cpu().numpy(), K)).to(cdt)
+            gcoef = gc.to(buf.device) if on_dev else gc
+        return (None, None, None, gpar if ctx.params_on_device else gpar.cpu(), gcoef, *gi)
 
 
-def trace_differentiable(template: T.SurfaceTable, params: torch.Tensor, rays, rows=None):
+def trace_differentiable(template: T.SurfaceTable, params: torch.Tensor, rays, rows=None, coefs: torch.Tensor | None = None):
     """Trace ``rays`` (an ``optiland_b200.trace.RealRays``) through ``template`` with parameter VALUES
-    taken from ``params``.  Returns a dict of record tensors that are autograd outputs of ``params``
+    taken from ``params`` (and ``coefs``: the user coefficients of polynomial / Zernike surfaces, ``table_to_coefs``).  Returns a dict of record tensors that are autograd outputs of ``params``
     (and of the ray tensors when they require grad): (S, N) arrays when ``rows`` is None, otherwise
     only the requested rows -- (N,) tensors for a single row, lists of (N,) tensors for several --
     which keeps the backward pass from touching gradients of rows the loss never reads."""
     holder: list = []
     rows_t = None if rows is None else tuple(int(r) for r in rows)
-    outs = _TraceFn.apply(template, holder, rows_t, params, rays.x, rays.y, rays.z, rays.L, rays.M, rays.N, rays.i, rays.opd)
+    outs = _TraceFn.apply(template, holder, rows_t, params, coefs, rays.x, rays.y, rays.z, rays.L, rays.M, rays.N, rays.i, rays.opd)
     if rows_t is None:
         return dict(zip(_REC_KEYS, outs))
     nr = len(rows_t)

@@ -247,6 +247,29 @@ OLB_HD T poly2_value(const T* C, int rows, int cols, bool tri, T x, T y) {
   return P;
 }
 
+// Value, gradient and Hessian of a bivariate polynomial table in one nested Horner pass (backward pass only: the
+// adjoint of the surface normal needs the second partials of the slope polynomial).
+template <typename T>
+OLB_HD void poly2_hess(const T* C, int rows, int cols, bool tri, T x, T y, T& P, T& Px, T& Py, T& Pxx, T& Pxy, T& Pyy) {
+  P = 0; Px = 0; Py = 0; Pxx = 0; Pxy = 0; Pyy = 0;
+  for (int i = rows - 1; i >= 0; --i) {
+    const T* row = C + i * cols;
+    const int jmax = tri ? (rows - 1 - i) : (cols - 1);
+    T q = 0, q1 = 0, q2 = 0;
+    for (int j = jmax; j >= 0; --j) {
+      q2 = o_fma(q2, y, (T)2 * q1);
+      q1 = o_fma(q1, y, q);
+      q = o_fma(q, y, row[j]);
+    }
+    Pxx = o_fma(Pxx, x, (T)2 * Px);
+    Px = o_fma(Px, x, P);
+    P = o_fma(P, x, q);
+    Pxy = o_fma(Pxy, x, Py);
+    Py = o_fma(Py, x, q1);
+    Pyy = o_fma(Pyy, x, q2);
+  }
+}
+
 // Triangular tables of a COMPILE-TIME width W (Zernike sums: prepare_table pads the monomial table to W in {4, 8,
 // 12}).  The same nested Horner as poly2_value / poly2_eval, operation for operation (padding only prepends zero
 // terms), but fully unrolled: every coefficient is a load at a constant offset and every term one FMA (value) or two
@@ -1044,6 +1067,23 @@ enum { GP_TX = 0, GP_TY = 1, GP_TZ = 2, GP_CURV = 3, GP_CONIC = 4, GP_N1 = 5, GP
 template <typename T>
 struct Adjoint { T x, y, z, L, M, N, i, opd; };
 
+// What a polynomial-family surface (polynomial / Zernike: bivariate monomial tables S for the sag and D for the slopes)
+// contributes to the gradient of its TABLES: dLoss/dS_ij = q xn^i yn^j and dLoss/dD_ij = ax i xn^(i-1) yn^j +
+// ay j xn^i yn^(j-1).  The caller accumulates them (warp reduction in the kernel); the host maps the table gradients
+// back to the user's coefficients, in which the tables are linear.
+template <typename T> struct PolyAdj { T q, ax, ay, xn, yn; int active; };
+
+// Table gradients of the polynomial families (olb_trace_bwd_tables_*): per surface two blocks (sag table S, slope table
+// D) of GT_DIM x GT_DIM doubles, entry (i, j) <-> xn^i yn^j; tables wider than GT_DIM are outside the adjoint's scope.
+enum { GT_DIM = 12, GT_BLOCK = GT_DIM * GT_DIM, GT_PER_SURFACE = 2 * GT_BLOCK };
+
+// One ray's contribution to entry (i, j) of the two tables (see PolyAdj): xi = xn^i, xim = xn^(i-1), yj, yjm likewise.
+template <typename T>
+OLB_HD void poly_table_terms(const PolyAdj<T>& pa, int i, int j, T xi, T xim, T yj, T yjm, T& vS, T& vD) {
+  vS = pa.q * xi * yj;
+  vD = pa.ax * (T)i * xim * yj + pa.ay * (T)j * xi * yjm;
+}
+
 // pre: state BEFORE the surface in GLOBAL coordinates (record row s-1 or the launch state);
 // (x1g, y1g, z1g): position AFTER the surface (record row s), global.
 // a: in = dLoss/d(state after the surface, global); out = dLoss/d(state before it, global).
@@ -1055,8 +1095,10 @@ struct Adjoint { T x, y, z, L, M, N, i, opd; };
 // Returns false (and leaves `a` zeroed) when the ray is not finite at this surface (NaN in band: no gradient).
 template <typename T>
 OLB_HD bool surface_backward(const PrepSurface<T>& S, const T* pool, T xg0, T yg0, T zg0, T L, T M, T N, T i0,
-                             T x1g, T y1g, T z1g, Adjoint<T>& a, T* pg, T* gR = nullptr, int gR_stride = 1) {
+                             T x1g, T y1g, T z1g, Adjoint<T>& a, T* pg, T* gR = nullptr, int gR_stride = 1,
+                             PolyAdj<T>* padj = nullptr) {
   // (L, M, N are taken by value: they are rotated into the local frame below for tilted poses)
+  if (padj) padj->active = 0;
   const T* med = pool + S.media_off;  // one wavelength
   const T n1 = med[MED_N1], u = med[MED_U];
   const T n2 = o_div(n1, u);
@@ -1118,7 +1160,41 @@ OLB_HD bool surface_backward(const PrepSurface<T>& S, const T* pool, T xg0, T yg
       gp += asph_pp;
     }
   }
-  const T fx = x1 * g, fy = y1 * g;
+  T fx = x1 * g, fy = y1 * g;           // the reference's slope function (-> normal)
+  T Fx = fx, Fy = fy;                   // the true gradient of the sag (-> implicit-function theorem)
+  T jxx = 0, jxy = 0, jyx = 0, jyy = 0; // non-radial part of d(fx, fy)/d(x, y)
+  T pax = 1, pay = 1, pxn = 0, pyn = 0;
+  const bool polyfam = S.kind == OLB_GEOM_POLYNOMIAL || S.kind == OLB_GEOM_ZERNIKE;
+  if (polyfam) {
+    const bool tri = (S.flags & PSF_POLY_TRI) != 0;
+    pxn = x1 * S.inv_norm; pyn = y1 * S.inv_norm_y;
+    T Ps, Sx, Sy;
+    poly2_eval(pool + S.coef_off, S.poly_rows, S.poly_cols, tri, pxn, pyn, Ps, Sx, Sy);
+    Fx = o_fma(Sx, S.inv_norm, fx);
+    Fy = o_fma(Sy, S.inv_norm_y, fy);
+    T Pd, Dx, Dy, Dxx, Dxy, Dyy;
+    poly2_hess(pool + S.poly_d_off, S.poly_rows, S.poly_cols, tri, pxn, pyn, Pd, Dx, Dy, Dxx, Dxy, Dyy);
+    T Dxs = Dx, Dys = Dy;
+    if (S.kind == OLB_GEOM_ZERNIKE) {
+      // the forward pass's regularised chain rule (newton_slopes); its factors a, b = 1 - O(1e-14 / rho) are treated
+      // as constants of the adjoint
+      const T eps = (T)1e-14;
+      const T rho2 = o_fma(pxn, pxn, pyn * pyn);
+      if (rho2 == 0) { Dxs = 0; Dys = 0; Dxx = 0; Dxy = 0; Dyy = 0; }
+      else {
+        const T rho = o_sqrt(rho2);
+        const T a_ = o_div(rho, rho + eps), b_ = o_div(rho2, rho2 + eps), inv = o_rcp(rho2);
+        const T xx = pxn * pxn, yy = pyn * pyn, xy = pxn * pyn * (a_ - b_);
+        Dxs = o_fma(Dx, o_fma(a_, xx, b_ * yy), Dy * xy) * inv;
+        Dys = o_fma(Dy, o_fma(a_, yy, b_ * xx), Dx * xy) * inv;
+      }
+    }
+    pax = S.inv_norm; pay = S.inv_norm_y;
+    fx = o_fma(Dxs, pax, fx);
+    fy = o_fma(Dys, pay, fy);
+    jxx = pax * S.inv_norm * Dxx; jxy = pax * S.inv_norm_y * Dxy;
+    jyx = pay * S.inv_norm * Dxy; jyy = pay * S.inv_norm_y * Dyy;
+  }
   const T invG = plane ? (T)1 : o_rsqrt(o_fma(fx, fx, o_fma(fy, fy, (T)1)));
   // unit normal: plane (0,0,+1) (plane.py:90-109), otherwise (fx, fy, -1)/|.|
   const T nx = plane ? (T)0 : fx * invG, ny = plane ? (T)0 : fy * invG, nz = plane ? (T)1 : -invG;
@@ -1184,6 +1260,11 @@ OLB_HD bool surface_backward(const PrepSurface<T>& S, const T* pool, T xg0, T yg
     const T ar2 = ag * gp;
     ax1 = o_fma(afx, g, (T)2 * x1 * ar2);
     ay1 = o_fma(afy, g, (T)2 * y1 * ar2);
+    if (polyfam) {
+      ax1 += o_fma(afx, jxx, afy * jyx);
+      ay1 += o_fma(afx, jxy, afy * jyy);
+      if (padj) { padj->ax = afx * pax; padj->ay = afy * pay; }
+    }
   }
   // ---- clip / absorption / OPD ------------------------------------------------------------------
   T at = 0;
@@ -1205,11 +1286,12 @@ OLB_HD bool surface_backward(const PrepSurface<T>& S, const T* pool, T xg0, T yg
   adL = o_fma(t, apx, adL); adM = o_fma(t, apy, adM); adN = o_fma(t, apz, adN);
   at += o_fma(apx, L, o_fma(apy, M, apz * N));
   // ---- intersection (implicit function theorem) -------------------------------------------------------
-  const T D = o_fma(fx, L, o_fma(fy, M, -N));
+  const T D = o_fma(Fx, L, o_fma(Fy, M, -N));
   const T q = -o_div(at, D);
-  apx = o_fma(q, fx, apx); apy = o_fma(q, fy, apy); apz -= q;
+  apx = o_fma(q, Fx, apx); apy = o_fma(q, Fy, apy); apz -= q;
   const T qt = q * t;
-  adL = o_fma(qt, fx, adL); adM = o_fma(qt, fy, adM); adN -= qt;
+  adL = o_fma(qt, Fx, adL); adM = o_fma(qt, Fy, adM); adN -= qt;
+  if (polyfam && padj) { padj->q = q; padj->xn = pxn; padj->yn = pyn; padj->active = 1; }
   if (!plane) {
     const T is = o_rcp(sconic), is3 = is * is * is, ops = (T)1 + sconic;
     // d sag / d c = r2 / (s (1+s)) ; d sag / d k = c^3 r2^2 / (2 s (1+s)^2)

@@ -151,6 +151,8 @@ struct PrepResult {
   uint32_t features = 0;
   uint32_t hints = 0;          // HINT_* (launch policy only, never semantics)
   bool bwd_supported = true;   // every surface is covered by surface_backward (olb_math.cuh)
+  bool bwd_tables = false;     // ... and some surface is a polynomial / Zernike one: its TABLE gradients are wanted
+                               // (olb_trace_bwd_tables_*)
   int total_gslots = 0;        // per-thread gradient accumulator slots the backward kernel needs
   std::string error;
 };
@@ -480,8 +482,10 @@ static inline PrepResult prepare_table(const OlbTable& tab) {
   res.total_gslots = gslot;
   for (int s = 0; s < tab.n_surfaces; ++s) {
     const PrepSurface<double>& o = ps[s];
+    const bool polyfam = (o.kind == OLB_GEOM_POLYNOMIAL || o.kind == OLB_GEOM_ZERNIKE) && o.poly_rows <= 12 && o.poly_cols <= 12;
     const bool kind_ok = o.kind == OLB_GEOM_NOOP || o.kind == OLB_GEOM_PLANE || o.kind == OLB_GEOM_STANDARD ||
-                         ((o.kind == OLB_GEOM_EVEN_ASPHERE || o.kind == OLB_GEOM_ODD_ASPHERE) && o.n_coef <= 12);
+                         ((o.kind == OLB_GEOM_EVEN_ASPHERE || o.kind == OLB_GEOM_ODD_ASPHERE) && o.n_coef <= 12) || polyfam;
+    if (polyfam) res.bwd_tables = true;
     if (!kind_ok || o.coating == OLB_COAT_FRESNEL || tab.n_wl != 1)
       res.bwd_supported = false;
   }

@@ -80,8 +80,10 @@ struct TraceArgs {
   double lo0[3], los[2], lt0[3], lts[2], linten;
   // per-ray field coordinates (trace_generic): origin / target offsets lof * g(H), ltf * g(H)
   const void* hx; const void* hy;
-  int32_t fmode; int32_t fpad;
+  int32_t fmode; int32_t n_vig;
   double farg, lof[2], ltf[2];
+  int32_t vig_power; int32_t vpad;
+  double vig[OLB_MAX_VIG_FIELDS][4];   // per-ray vignetting factors: nearest defined field (Hx, Hy, vx, vy)
   // fused moments epilogue (OLB_TF_MOMENTS)
   double* moments;
   double mcx, mcy;
@@ -230,6 +232,21 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<T, RPT, FEAT>::v)) trace_ker
           T hxv[RPT], hyv[RPT];
           load_rays<T, RPT>((const T*)a.hx, bin, valid, hxv);
           load_rays<T, RPT>((const T*)a.hy, bin, valid, hyv);
+          if (a.n_vig > 0) {
+            // FieldGroup.get_vig_factor: nearest defined field; the pupil point shrinks by (1 - vx, 1 - vy)
+#pragma unroll
+            for (int k = 0; k < RPT; ++k) {
+              int best = 0;
+              double bd = 1e300;
+              for (int j = 0; j < a.n_vig; ++j) {
+                const double dx = (double)hxv[k] - a.vig[j][0], dy = (double)hyv[k] - a.vig[j][1];
+                const double d2 = dx * dx + dy * dy;
+                if (d2 < bd) { bd = d2; best = j; }
+              }
+              const T sx = (T)1 - (T)a.vig[best][2], sy = (T)1 - (T)a.vig[best][3];
+              for (int q = 0; q < a.vig_power; ++q) { pv[k] = pv[k] * sx; v[k] = v[k] * sy; }
+            }
+          }
 #pragma unroll
           for (int k = 0; k < RPT; ++k) {
             // fp64 tangent for both element types: a field angle feeds a lever arm of hundreds of mm
@@ -495,6 +512,7 @@ struct BwdArgs {
   const void* grec[8];   // dLoss/d records (entries may be null)
   void* gin[8];          // dLoss/d launch state (may be null as a whole: gin[0] == null)
   double* gparams;       // n_surf * GP_COUNT, accumulated
+  double* gtab;          // n_surf * GT_PER_SURFACE, accumulated: table gradients of polynomial / Zernike surfaces (or null)
 };
 
 // One ray per thread per tile.  Parameter gradients: PRIVATE fp32/fp64 accumulators per thread in
@@ -531,7 +549,7 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(T) == 8 ? OLB_BWD_MINB64 : 2)) 
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t k = tile * BLOCK + threadIdx.x;
     const bool valid = k < n;
-    if (SMEM_ACC && !valid) continue;    // (the warp-reduce path needs the whole warp)
+    if (SMEM_ACC && !valid && a.gtab == nullptr) continue;    // (warp reductions need the whole warp)
     const int64_t kk = valid ? k : 0;
     Adjoint<T> ad{0, 0, 0, 0, 0, 0, 0, 0};
     // Software-pipelined walk from the image surface back to the first one.  Surface s needs the state
@@ -586,6 +604,8 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(T) == 8 ? OLB_BWD_MINB64 : 2)) 
         load_state(s - 1, pren);
       }
       ad.x += g8[0]; ad.y += g8[1]; ad.z += g8[2]; ad.L += g8[3]; ad.M += g8[4]; ad.N += g8[5]; ad.i += g8[6]; ad.opd += g8[7];
+      PolyAdj<T> pa;
+      pa.active = 0;
       if (!noop) {   // (a NOOP surface records its input unchanged: the adjoint passes through)
         T pg[GP_SCALARS];
 #pragma unroll
@@ -597,7 +617,7 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(T) == 8 ? OLB_BWD_MINB64 : 2)) 
           T* mine = tacc + (int64_t)S.gslot * BLOCK + threadIdx.x;
           if (valid)
             surface_backward<T>(S, pool, pre[0], pre[1], pre[2], pre[3], pre[4], pre[5], pre[6], post[0], post[1], post[2],
-                                ad, pg, tilted ? mine + (GP_COEF + ncoef) * BLOCK : nullptr, BLOCK);
+                                ad, pg, tilted ? mine + (GP_COEF + ncoef) * BLOCK : nullptr, BLOCK, &pa);
           // pose, curvature, conic, n1, n2: every surface has these 7; only even aspheres have more
 #pragma unroll
           for (int q = 0; q < GP_COEF; ++q) mine[q * BLOCK] += pg[q];
@@ -610,7 +630,7 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(T) == 8 ? OLB_BWD_MINB64 : 2)) 
           T r9[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
           if (valid)
             surface_backward<T>(S, pool, pre[0], pre[1], pre[2], pre[3], pre[4], pre[5], pre[6], post[0], post[1], post[2],
-                                ad, pg, tilted ? r9 : nullptr, 1);
+                                ad, pg, tilted ? r9 : nullptr, 1, &pa);
 #pragma unroll
           for (int q = 0; q < GP_SCALARS; ++q) {
             if (q >= GP_COEF + ncoef) break;
@@ -628,6 +648,35 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(T) == 8 ? OLB_BWD_MINB64 : 2)) 
               if (lane == 0 && v != 0) atomicAdd(&wacc[s * GP_COUNT + GP_R + q], (double)v);
             }
           }
+        }
+      }
+      if (a.gtab != nullptr && (S.kind == OLB_GEOM_POLYNOMIAL || S.kind == OLB_GEOM_ZERNIKE)) {
+        // Table gradients of a polynomial-family surface (warp-uniform branch; every lane takes part in the
+        // reductions, inactive rays contribute zeros): dLoss/dS_ij += q xn^i yn^j, dLoss/dD_ij += ax i xn^(i-1) yn^j +
+        // ay j xn^i yn^(j-1); one fp64 atomic per entry and warp.
+        double* gS = a.gtab + (size_t)s * GT_PER_SURFACE;
+        double* gD = gS + GT_BLOCK;
+        const bool tri = (S.flags & PSF_POLY_TRI) != 0;
+        const bool on = pa.active != 0;
+        T xi = 1, xim = 0;
+        for (int i = 0; i < S.poly_rows; ++i) {
+          T yj = 1, yjm = 0;
+          const int jmax = tri ? (S.poly_rows - 1 - i) : (S.poly_cols - 1);
+          for (int j = 0; j <= jmax; ++j) {
+            T vS = 0, vD = 0;
+            if (on) poly_table_terms(pa, i, j, xi, xim, yj, yjm, vS, vD);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              vS += __shfl_xor_sync(0xffffffffu, vS, o);
+              vD += __shfl_xor_sync(0xffffffffu, vD, o);
+            }
+            if (lane == 0) {
+              if (vS != 0) atomicAdd(&gS[i * GT_DIM + j], (double)vS);
+              if (vD != 0) atomicAdd(&gD[i * GT_DIM + j], (double)vD);
+            }
+            if (on) { yjm = yj; yj *= pa.yn; }
+          }
+          if (on) { xim = xi; xi *= pa.xn; }
         }
       }
       post[0] = pre[0]; post[1] = pre[1]; post[2] = pre[2];
@@ -671,12 +720,14 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(T) == 8 ? OLB_BWD_MINB64 : 2)) 
 template <typename T>
 static int trace_bwd_impl(const OlbDeviceTable* wh, int32_t first, int32_t last, const OlbRays* rays_in,
                           const OlbRecords* rec, const OlbRecords* grec, const OlbRays* gin, double* gparams,
-                          int64_t n_rays, uint64_t grow_mask, cudaStream_t stream) {
+                          int64_t n_rays, uint64_t grow_mask, cudaStream_t stream, double* gtab = nullptr) {
   if (!wh || wh->magic != WS_MAGIC || !wh->workspace)
     return fail(OLB_ERR_INVALID_ARG, "table handle was not initialised by olb_table_upload");
   if (!wh->bwd_supported)
-    return fail(OLB_ERR_UNSUPPORTED, "backward: table not supported (a non plane/standard/even-asphere geometry, "
-                                     "a Fresnel coating or several wavelengths)");
+    return fail(OLB_ERR_UNSUPPORTED, "backward: table not supported (a geometry other than plane / standard / even- and "
+                                     "odd-asphere / polynomial / Zernike, a Fresnel coating or several wavelengths)");
+  if (wh->bwd_supported == 2 && !gtab)
+    return fail(OLB_ERR_UNSUPPORTED, "backward: the table has polynomial / Zernike surfaces: use olb_trace_bwd_tables_* (grad_tables)");
   if (!rays_in || !rec || !gparams) return fail(OLB_ERR_INVALID_ARG, "rays_in, rec and grad_params are required");
   if (first < 0 || last > wh->n_surfaces || first > last) return fail(OLB_ERR_INVALID_ARG, "bad surface range");
   if (n_rays <= 0 || first == last) return OLB_OK;
@@ -701,6 +752,7 @@ static int trace_bwd_impl(const OlbDeviceTable* wh, int32_t first, int32_t last,
     for (int q = 0; q < 8; ++q) { if (!go[q]) return fail(OLB_ERR_INVALID_ARG, "grad_rays_in needs all 8 arrays"); a.gin[q] = go[q]; }
   }
   a.gparams = gparams;
+  a.gtab = wh->bwd_supported == 2 ? gtab : nullptr;
   a.grow_mask = grow_mask;
   a.n_slots = wh->bwd_slots;
   const size_t base_smem = 16 + (((size_t)a.blob_bytes + 15) & ~size_t(15));
@@ -891,6 +943,11 @@ static int trace_impl(const OlbDeviceTable* wh, int32_t first, int32_t last, con
       if (launch->field_mode != 1 && launch->field_mode != 2) return fail(OLB_ERR_INVALID_ARG, "launch.field_mode must be 1 (angle) or 2 (object height)");
       a.hx = launch->Hx; a.hy = launch->Hy; a.fmode = launch->field_mode; a.farg = launch->field_arg;
       for (int q = 0; q < 2; ++q) { a.lof[q] = launch->origin_field[q]; a.ltf[q] = launch->target_field[q]; }
+      if (launch->n_vig < 0 || launch->n_vig > OLB_MAX_VIG_FIELDS) return fail(OLB_ERR_INVALID_ARG, "launch.n_vig out of range");
+      if (launch->n_vig > 0 && (launch->vig_power < 1 || launch->vig_power > 2)) return fail(OLB_ERR_INVALID_ARG, "launch.vig_power must be 1 or 2");
+      a.n_vig = launch->n_vig; a.vig_power = launch->vig_power;
+      for (int j = 0; j < launch->n_vig; ++j)
+        for (int q = 0; q < 4; ++q) a.vig[j][q] = launch->vig[j][q];
     }
   }
   uint32_t features = wh->features;
@@ -1010,7 +1067,7 @@ int olb_table_upload(const OlbTable* table, void* workspace, int64_t workspace_b
   h.bytes_f64 = (int32_t)pr.blob_f64.size();
   h.off_f32 = 64 + h.bytes_f64;
   h.bytes_f32 = (int32_t)pr.blob_f32.size();
-  h.bwd_supported = pr.bwd_supported ? 1 : 0;
+  h.bwd_supported = pr.bwd_supported ? (pr.bwd_tables ? 2 : 1) : 0;
   h.bwd_slots = pr.total_gslots;
   h.n_systems = 1;
   h.hints = (int32_t)pr.hints;
@@ -1116,6 +1173,21 @@ int olb_trace_bwd_f64(const OlbDeviceTable* table, int32_t first, int32_t last, 
                       double* grad_params, int64_t n_rays, uint64_t grad_row_mask, void* stream) {
   return trace_bwd_impl<double>(table, first, last, rays_in, rec, grad_rec, grad_rays_in, grad_params, n_rays,
                                 grad_row_mask, (cudaStream_t)stream);
+}
+
+int olb_trace_bwd_tables_f32(const OlbDeviceTable* table, int32_t first, int32_t last, const OlbRays* rays_in,
+                             const OlbRecords* rec, const OlbRecords* grad_rec, const OlbRays* grad_rays_in,
+                             double* grad_params, double* grad_tables, int64_t n_rays, uint64_t grad_row_mask, void* stream) {
+  if (!grad_tables) return fail(OLB_ERR_INVALID_ARG, "grad_tables is NULL");
+  return trace_bwd_impl<float>(table, first, last, rays_in, rec, grad_rec, grad_rays_in, grad_params, n_rays,
+                               grad_row_mask, (cudaStream_t)stream, grad_tables);
+}
+int olb_trace_bwd_tables_f64(const OlbDeviceTable* table, int32_t first, int32_t last, const OlbRays* rays_in,
+                             const OlbRecords* rec, const OlbRecords* grad_rec, const OlbRays* grad_rays_in,
+                             double* grad_params, double* grad_tables, int64_t n_rays, uint64_t grad_row_mask, void* stream) {
+  if (!grad_tables) return fail(OLB_ERR_INVALID_ARG, "grad_tables is NULL");
+  return trace_bwd_impl<double>(table, first, last, rays_in, rec, grad_rec, grad_rays_in, grad_params, n_rays,
+                                grad_row_mask, (cudaStream_t)stream, grad_tables);
 }
 
 int olb_trace_pupil_f32(const OlbDeviceTable* table, int32_t first, int32_t last, const OlbPupilLaunch* launch,

@@ -83,6 +83,17 @@ def launch_from_affine(Px, Py, aff: dict):
     ofx = ofy = tfx = tfy = 0.0
     if aff.get("fields") is not None:
         Hx, Hy = aff["fields"]
+        if aff.get("vig") is not None:       # nearest defined field's vignetting factors (numpy arrays only: test mirror)
+            import numpy as np
+
+            tab, power = aff["vig"]
+            tab = np.asarray(tab, dtype=np.float64).reshape(-1, 4)
+            hx, hy = np.asarray(Hx, dtype=np.float64), np.asarray(Hy, dtype=np.float64)
+            d2 = (hx[:, None] - tab[None, :, 0]) ** 2 + (hy[:, None] - tab[None, :, 1]) ** 2
+            best = np.argmin(d2, axis=1)
+            for _ in range(int(power)):
+                Px = Px * (1 - tab[best, 2])
+                Py = Py * (1 - tab[best, 3])
         if int(aff["field_mode"]) == 1:
             gx, gy = _tan(Hx * aff["field_arg"]), _tan(Hy * aff["field_arg"])
         else:

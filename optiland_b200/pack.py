@@ -287,6 +287,7 @@ def pack_surface(surface, wavelengths) -> T.SurfaceSpec:
             # the reference forms coeff * N_nm first (optiland/zernike/base.py:63-68)
             terms.append((float(n), float(m), c * norm, c))
         spec.coefficients = np.array(terms, dtype=np.float64).reshape(-1, 4)
+        spec.zernike_norms = np.array([_f(z._norm_constant(int(n), int(m))) for (n, m) in z.indices], dtype=np.float64)
         spec.norm_radius = _f(g.norm_radius)
 
     if surface.aperture is not None:

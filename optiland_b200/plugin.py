@@ -216,7 +216,7 @@ class CudaEngine:
         return huygens_fresnel_psf(image_x, image_y, image_z, pupil_x, pupil_y, pupil_z, pupil_amp, pupil_opd,
                                    wavelength, Rp).to(image_x.dtype)
 
-    def trace_grad(self, table: T.SurfaceTable, params, rays):
+    def trace_grad(self, table: T.SurfaceTable, params, rays, coefs=None):
         """Differentiable trace of Optiland's ``rays``: records are autograd outputs of ``params`` and of
         the ray tensors.  None if the table is outside olb_trace_bwd_*'s scope."""
         from . import autograd as AG
@@ -230,7 +230,7 @@ class CudaEngine:
         # (a dense (S, N) output would make autograd zero-fill and the kernel re-read every row), and ``dt``
         # -- packed from the same live values ``params`` was read from -- is reused instead of re-preparing
         S = table.num_surfaces
-        outs = AG._TraceFn.apply(table, [dt], tuple(range(S)), params, *ins)
+        outs = AG._TraceFn.apply(table, [dt], tuple(range(S)), params, coefs, *ins)
         rec = {k: list(outs[j * S:(j + 1) * S]) for j, k in enumerate(("x", "y", "z", "L", "M", "N", "intensity", "opd"))}
         for k, key in (("x", "x"), ("y", "y"), ("z", "z"), ("L", "L"), ("M", "M"), ("N", "N"), ("i", "intensity"), ("opd", "opd")):
             setattr(rays, k, rec[key][-1])
@@ -461,7 +461,7 @@ def _live_params(surfaces, table, wavelength):
             g = surf.geometry
             cs = g.cs
             if cs.reference_cs is not None or spec.kind not in (T.GEOM_PLANE, T.GEOM_STANDARD, T.GEOM_EVEN_ASPHERE,
-                                                                T.GEOM_ODD_ASPHERE):
+                                                                T.GEOM_ODD_ASPHERE, T.GEOM_POLYNOMIAL, T.GEOM_ZERNIKE):
                 return None
             # pose rotation: constants (identity for an untilted surface -- the reference skips zero rotations
             # altogether, `if self.rz:` coordinate_system.py:84-89, so zero angles get no gradient there either);
@@ -500,6 +500,37 @@ def _live_params(surfaces, table, wavelength):
     return torch.cat([P[:, :GP_CURV], curv[:, None], P[:, GP_CURV + 1:]], dim=1)
 
 
+def _live_coefs(surfaces, table):
+    """(S, K) fp64 tensor of the USER coefficients of the polynomial-family surfaces (Zernike ``geometry.zernike.coeffs``,
+    polynomial ``geometry.coefficients``), stacked from the LIVE tensors so that the table gradients of
+    olb_trace_bwd_tables_* flow back to the optimiser's variables (optimization/variable/zernike_coeff.py,
+    polynomial_coeff.py); None when the table has no such surface."""
+    import torch
+
+    rows, K, dev = [], 0, None
+    for surf, spec in zip(surfaces, table.surfaces):
+        r = None
+        if spec.kind == T.GEOM_ZERNIKE:
+            r = surf.geometry.zernike.coeffs
+        elif spec.kind == T.GEOM_POLYNOMIAL:
+            c = surf.geometry.coefficients
+            r = c if torch.is_tensor(c) else torch.stack([torch.stack([torch.as_tensor(v) for v in row]) for row in c])
+        if r is not None:
+            r = (r if torch.is_tensor(r) else torch.as_tensor(np.asarray(r, dtype=np.float64))).reshape(-1).to(torch.float64)
+            K = max(K, r.numel())
+            dev = r.device
+        rows.append(r)
+    if K == 0:
+        return None
+    out = []
+    for r in rows:
+        if r is None:
+            out.append(torch.zeros(K, dtype=torch.float64, device=dev))
+        else:
+            out.append(torch.cat([r.to(dev), torch.zeros(K - r.numel(), dtype=torch.float64, device=dev)]) if r.numel() < K else r.to(dev))
+    return torch.stack(out)
+
+
 def _wants_grad(backend, surfaces, rays=None) -> bool:
     """True when the call must stay differentiable: ``be.grad_mode`` is on, or some tensor involved --
     a ray array or a live surface parameter -- requires grad even though the global switch is off (the
@@ -518,7 +549,7 @@ def _wants_grad(backend, surfaces, rays=None) -> bool:
             continue
         cs = g.cs
         vals = [getattr(g, "radius", None), getattr(g, "k", None), cs.x, cs.y, cs.z, cs.rx, cs.ry, cs.rz]
-        coefs = getattr(g, "coefficients", None)
+        coefs = getattr(g, "coefficients", None)     # (Zernike: the property returns geometry.zernike.coeffs)
         if coefs is not None:
             vals += [coefs] if hasattr(coefs, "requires_grad") else list(np.ravel(np.asarray(coefs, dtype=object)))
         if any(rg(v) for v in vals):
@@ -562,7 +593,8 @@ def _try_trace(backend, surfaces, rays, table_builder) -> bool:
         params = _live_params(surfaces, table, float(wl[0]))
         if params is None:
             return _decline("gradients wanted: a surface outside the adjoint's scope")
-        rec = engine.trace_grad(table, params, rays)
+        coefs = _live_coefs(surfaces, table)
+        rec = engine.trace_grad(table, params, rays, coefs) if coefs is not None else engine.trace_grad(table, params, rays)
         if rec is None:
             return _decline("gradients wanted: table outside the adjoint's scope")
     else:
@@ -689,13 +721,26 @@ def install(engine=None, alias: str | None = None) -> None:
                 return _fused_decline("vignetting factors are not plain numbers")
             tracer._validate_normalized_coordinates(Hx, Hy, "field")
             tracer._validate_normalized_coordinates(Px, Py, "pupil")
+            vig = None
             if has_vig:
                 # vignetting factors (nearest-neighbour over the defined fields, fields/field_group.py:93-122) scale
                 # the pupil point TWICE on this path: once in trace_generic (real_ray_tracer.py:134-137) and once
-                # more in the aimer (ray_aiming/paraxial.py:72-96) -- reproduced, as a per-ray pre-scale of (Px, Py)
-                vxf, vyf = optic.fields.get_vig_factor(Hx, Hy)
-                Px = Px * (1 - vxf) * (1 - vxf)
-                Py = Py * (1 - vyf) * (1 - vyf)
+                # more in the aimer (ray_aiming/paraxial.py:72-96) -- reproduced, looked up per ray IN the kernel
+                # from the table of defined fields (OlbPupilLaunch.vig, vig_power = 2)
+                try:
+                    from .pack import _f
+
+                    mf = _f(optic.fields.max_field)
+                    norm = mf if mf != 0 else 1.0
+                    vig = (_np.array([[_f(f.x) / norm, _f(f.y) / norm, _f(f.vx), _f(f.vy)] for f in optic.fields.fields]), 2)
+                    if len(vig[0]) > 16:
+                        vig = None
+                except Exception:
+                    vig = None
+                if vig is None:      # (more than 16 fields, exotic field objects): the factors as eager ops
+                    vxf, vyf = optic.fields.get_vig_factor(Hx, Hy)
+                    Px = Px * (1 - vxf) * (1 - vxf)
+                    Py = Py * (1 - vyf) * (1 - vyf)
             Hx, Hy, Px, Py = tracer._validate_array_size(Hx, Hy, Px, Py)
             if not all(engine.accepts_tensor(t) for t in (Hx, Hy, Px, Py)) or len({t.shape for t in (Hx, Hy, Px, Py)}) != 1:
                 return _fused_decline("field / pupil arrays not resident on a CUDA device (or of different shapes)")
@@ -722,6 +767,8 @@ def install(engine=None, alias: str | None = None) -> None:
                 sc["vx"] = sc["vy"] = 1.0            # (the factors are already in Px, Py)
                 _prepare(engine, table, Px.device)
                 aff = pupil_affine_fields(sc, Hx, Hy)
+                if vig is not None:
+                    aff["vig"] = vig
             except _PACK_ERRORS as e:
                 return _fused_decline(f"unsupported: {e}")
             if not polarized and any(s.coating == T.COAT_FRESNEL for s in table.surfaces):

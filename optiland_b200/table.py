@@ -105,6 +105,9 @@ class SurfaceSpec:
     coat_n1: np.ndarray | None = None
     coat_n2: np.ndarray | None = None
     record: bool = True
+    # ZERNIKE only, host side only (not packed): the normalisation constants N_nm per term, for mapping table
+    # gradients back to the coefficients when a coefficient is exactly 0 (c * N_nm then does not reveal N_nm)
+    zernike_norms: np.ndarray | None = None
 
     def __post_init__(self):
         self.t = np.asarray(self.t, dtype=np.float64).reshape(3)
@@ -383,3 +386,27 @@ def rotation_matrix(rx: float, ry: float, rz: float) -> np.ndarray:
     Ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
     Rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
     return Rz @ Ry @ Rx
+
+
+def zernike_monomials(n: int, m: int, width: int) -> np.ndarray:
+    """Monomial expansion of the UNIT Zernike term R_n^|m|(rho) {cos, sin}(|m| phi) (m >= 0: cos, m < 0: sin) as a
+    (width, width) table M[i, j] ~ xn^i yn^j -- the Python twin of olb_prep.h::zernike_add_monomials (exact integer
+    arithmetic in doubles).  The prepared sag table of a Zernike surface is S = sum_k c_k N_k M_k and its slope table
+    D = sum_k c_k M_k (the reference's derivative path omits N_k), so table gradients map back to the coefficients by
+    dL/dc_k = N_k <M_k, dL/dS> + <M_k, dL/dD>  (optiland_b200.autograd)."""
+    from math import comb, factorial
+
+    ma = abs(m)
+    out = np.zeros((width, width), dtype=np.float64)
+    for k in range((n - ma) // 2 + 1):
+        rc = (-1.0 if k & 1 else 1.0) * factorial(n - k) / (factorial(k) * factorial((n + ma) // 2 - k) * factorial((n - ma) // 2 - k))
+        q = (n - ma) // 2 - k
+        for a in range(q + 1):
+            ca = comb(q, a)
+            for j in range(ma + 1):
+                imag = (j & 1) != 0
+                if (m >= 0) == imag:
+                    continue
+                sgn = -1.0 if (j >> 1) & 1 else 1.0
+                out[2 * a + (ma - j), 2 * (q - a) + j] += rc * ca * comb(ma, j) * sgn
+    return out

@@ -292,6 +292,16 @@ def _c_launch(affine: dict, Px, Py):
         la.field_arg = float(affine.get("field_arg", 0.0))
         la.origin_field = (C.c_double * 2)(*affine["origin_field"])
         la.target_field = (C.c_double * 2)(*affine["target_field"])
+        vig = affine.get("vig")
+        if vig is not None:        # ((n, 4) array of {Hx, Hy, vx, vy} of the defined fields, power): in-kernel lookup
+            tab, power = vig
+            tab = np.asarray(tab, dtype=np.float64).reshape(-1, 4)
+            if len(tab) > 16:
+                raise ValueError("more than 16 defined fields with vignetting factors")
+            la.n_vig, la.vig_power = len(tab), int(power)
+            for j, row in enumerate(tab):
+                for q in range(4):
+                    la.vig[j][q] = float(row[q])
     return la
 
 

@@ -63,7 +63,7 @@ def run_hostcheck(hc, table, rays, dtype, first=0, last=None, want_l0=False, pma
     return out, dict(zip(REC, rec)), status.value
 
 
-def run_backward(hc, table, rays, rec, grec, dtype=np.float64):
+def run_backward(hc, table, rays, rec, grec, dtype=np.float64, tables=False):
     ht = _lib.HostTable(table)
     n = rays["x"].size
     S = table.num_surfaces
@@ -77,6 +77,13 @@ def run_backward(hc, table, rays, rec, grec, dtype=np.float64):
     P9 = (C.c_void_p * 9)(*[a.ctypes.data for a in rin])
     P8 = lambda arrs: (C.c_void_p * 8)(*[(a.ctypes.data if a is not None else None) for a in arrs])  # noqa: E731
     err = C.create_string_buffer(256)
+    if tables:
+        gtab = np.zeros((S, 2, 12, 12), dtype=np.float64)
+        fn = hc.olbhc_backward_tables_f64 if dtype == np.float64 else hc.olbhc_backward_tables_f32
+        rc = fn(C.byref(ht.c), 0, S, C.c_int64(n), P9, P8(recs), P8(grecs), P8(gin), C.c_void_p(gpar.ctypes.data),
+                C.c_void_p(gtab.ctypes.data), err, 256)
+        assert rc == 0, err.value
+        return dict(zip(("x", "y", "z", "L", "M", "N", "i", "opd"), gin)), gpar, gtab
     fn = hc.olbhc_backward_f64 if dtype == np.float64 else hc.olbhc_backward_f32
     rc = fn(C.byref(ht.c), 0, S, C.c_int64(n), P9, P8(recs), P8(grecs), P8(gin), C.c_void_p(gpar.ctypes.data), err, 256)
     assert rc == 0, err.value

@@ -126,7 +126,7 @@ class OracleEngine:
                                        amp, pupil_opd.detach().double().numpy(), wavelength, Rp)
         return torch.from_numpy(psf).to(image_x.dtype)
 
-    def trace_grad(self, table, params, rays):
+    def trace_grad(self, table, params, rays, coefs=None):
         """TEST-ONLY differentiable engine: oracle forward + the CPU instantiation of the device adjoint
         (tests/hostcheck) -- the arithmetic of olb_trace_bwd_* without a GPU."""
         import torch
@@ -146,11 +146,14 @@ class OracleEngine:
         self.calls.append(("grad", table.num_surfaces, int(rays.x.numel())))
         keys = ("x", "y", "z", "L", "M", "N", "i", "opd")
 
+        has_tables = any(sp.kind in AG.POLY_KINDS for sp in table.surfaces)
+        cf_in = coefs if coefs is not None else torch.zeros((table.num_surfaces, 1), dtype=torch.float64)
+
         class Fn(torch.autograd.Function):
             @staticmethod
-            def forward(ctx, params, *ins):
+            def forward(ctx, params, cf, *ins):
                 ctx.set_materialize_grads(False)
-                tab = AG.params_to_table(table, params)
+                tab = AG.params_to_table(table, params, cf if coefs is not None else None)
                 inp = {k: t.detach().double().numpy() for k, t in zip(keys, ins)}
                 inp["w"] = rays.w.detach().double().numpy()
                 _, rec, _ = O.trace(tab, inp)
@@ -161,10 +164,15 @@ class OracleEngine:
             def backward(ctx, *grads):
                 grec = {k: (None if g is None else g.double().numpy()) for k, g in
                         zip(("x", "y", "z", "L", "M", "N", "intensity", "opd"), grads)}
-                gin, gpar = run_backward(hc, ctx.tab, ctx.inp, ctx.rec, grec)
-                return (torch.from_numpy(gpar), *[torch.from_numpy(gin[k]) for k in keys])
+                if has_tables:
+                    gin, gpar, gtab = run_backward(hc, ctx.tab, ctx.inp, ctx.rec, grec, tables=True)
+                    gcf = torch.from_numpy(AG.tables_to_coef_grads(ctx.tab, gtab, cf_in.shape[1])) if coefs is not None else None
+                else:
+                    gin, gpar = run_backward(hc, ctx.tab, ctx.inp, ctx.rec, grec)
+                    gcf = None
+                return (torch.from_numpy(gpar), gcf, *[torch.from_numpy(gin[k]) for k in keys])
 
-        outs = Fn.apply(params, *[getattr(rays, k) for k in keys])
+        outs = Fn.apply(params, cf_in, *[getattr(rays, k) for k in keys])
         rec = dict(zip(("x", "y", "z", "L", "M", "N", "intensity", "opd"), outs))
         for k, key in zip(keys, ("x", "y", "z", "L", "M", "N", "intensity", "opd")):
             setattr(rays, k, rec[key][-1])

@@ -85,10 +85,12 @@ static int run(const OlbTable* tab, int first, int last, int64_t n, T** ray, T**
 template <typename T>
 static int run_backward(const OlbTable* tab, int first, int last, int64_t n, T** ray_in /*x y z L M N i w opd*/,
                         T** rec /*8 x rows*n*/, T** grec /*8, entries may be null*/, T** gin /*8 out*/,
-                        double* gparams /*n_surf*GP_COUNT, accumulated*/, char* err, int err_len) {
+                        double* gparams /*n_surf*GP_COUNT, accumulated*/, char* err, int err_len,
+                        double* gtab = nullptr /*n_surf*GT_PER_SURFACE, accumulated (polynomial families)*/) {
   PrepResult pr = prepare_table(*tab);
   if (!pr.error.empty()) { snprintf(err, err_len, "%s", pr.error.c_str()); return OLB_ERR_TABLE; }
   if (!pr.bwd_supported) { snprintf(err, err_len, "table outside the adjoint's scope"); return OLB_ERR_UNSUPPORTED; }
+  if (pr.bwd_tables && !gtab) { snprintf(err, err_len, "polynomial-family table: gradient tables required"); return OLB_ERR_UNSUPPORTED; }
   const unsigned char* blob = sizeof(T) == 8 ? pr.blob_f64.data() : pr.blob_f32.data();
   const PrepHeader* H = reinterpret_cast<const PrepHeader*>(blob);
   const PrepSurface<T>* surf = reinterpret_cast<const PrepSurface<T>*>(blob + sizeof(PrepHeader));
@@ -111,8 +113,27 @@ static int run_backward(const OlbTable* tab, int first, int last, int64_t n, T**
       if (s == first) { for (int q = 0; q < 7; ++q) pre[q] = ray_in[q][k]; }
       else { for (int q = 0; q < 7; ++q) pre[q] = rec[q][off - n]; }
       T pg[GP_SCALARS] = {0}, r9[9] = {0};
+      PolyAdj<T> pa{};
       surface_backward<T>(S, pool, pre[0], pre[1], pre[2], pre[3], pre[4], pre[5], pre[6], rec[0][off], rec[1][off],
-                          rec[2][off], a, pg, (S.flags & OLB_SF_ROTATED) ? r9 : nullptr, 1);
+                          rec[2][off], a, pg, (S.flags & OLB_SF_ROTATED) ? r9 : nullptr, 1, &pa);
+      if (pa.active && gtab) {
+        double* gS = gtab + (int64_t)s * GT_PER_SURFACE;
+        double* gD = gS + GT_BLOCK;
+        const bool tri = (S.flags & PSF_POLY_TRI) != 0;
+        T xi = 1, xim = 0;
+        for (int i = 0; i < S.poly_rows; ++i) {
+          T yj = 1, yjm = 0;
+          const int jmax = tri ? (S.poly_rows - 1 - i) : (S.poly_cols - 1);
+          for (int j = 0; j <= jmax; ++j) {
+            T vS, vD;
+            poly_table_terms(pa, i, j, xi, xim, yj, yjm, vS, vD);
+            gS[i * GT_DIM + j] += (double)vS;
+            gD[i * GT_DIM + j] += (double)vD;
+            yjm = yj; yj *= pa.yn;
+          }
+          xim = xi; xi *= pa.xn;
+        }
+      }
       for (int q = 0; q < GP_SCALARS; ++q) gparams[(int64_t)s * GP_COUNT + q] += (double)pg[q];
       for (int q = 0; q < 9; ++q) gparams[(int64_t)s * GP_COUNT + GP_R + q] += (double)r9[q];
     }
@@ -132,6 +153,15 @@ int olbhc_backward_f32(const OlbTable* tab, int first, int last, int64_t n, floa
   return run_backward<float>(tab, first, last, n, ray_in, rec, grec, gin, gparams, err, err_len);
 }
 int olbhc_gp_count() { return GP_COUNT; }
+int olbhc_gt_per_surface() { return GT_PER_SURFACE; }
+int olbhc_backward_tables_f64(const OlbTable* tab, int first, int last, int64_t n, double** ray_in, double** rec,
+                              double** grec, double** gin, double* gparams, double* gtab, char* err, int err_len) {
+  return run_backward<double>(tab, first, last, n, ray_in, rec, grec, gin, gparams, err, err_len, gtab);
+}
+int olbhc_backward_tables_f32(const OlbTable* tab, int first, int last, int64_t n, float** ray_in, float** rec,
+                              float** grec, float** gin, double* gparams, double* gtab, char* err, int err_len) {
+  return run_backward<float>(tab, first, last, n, ray_in, rec, grec, gin, gparams, err, err_len, gtab);
+}
 int olbhc_bwd_supported(const OlbTable* tab) {
   PrepResult pr = prepare_table(*tab);
   return pr.error.empty() && pr.bwd_supported ? 1 : 0;

@@ -387,6 +387,58 @@ def test_autograd_ray_input_gradients_and_unsupported_tables():
         assert ang.grad[q].item() == pytest.approx(fd, rel=2e-5, abs=1e-8), q
 
 
+@pytest.mark.parametrize("name", ["zernike_fringe", "zernike_standard", "misc_apertures_coatings"])
+def test_polynomial_family_adjoint_kernel(name):
+    """olb_trace_bwd_tables_* on the GPU (Zernike / polynomial surfaces): gradients of a random linear functional of all
+    records w.r.t. the launch state, the surface parameters and the USER coefficients (table gradients mapped back)
+    against the CPU instantiation of the same adjoint, which tests/test_hostcheck_backward.py holds to finite differences
+    of the oracle; fp32 against fp64."""
+    import dataclasses
+
+    from oracle import trace_oracle as O
+    from oracle.hostcheck_api import load, run_backward
+    from optiland_b200 import autograd as AG
+    from optiland_b200.trace import RealRays
+
+    c = Case(name)
+    if not any(s.kind in AG.POLY_KINDS for s in c.table.surfaces):
+        pytest.skip("no polynomial-family surface")
+    rng = np.random.default_rng(4)
+    n = min(c.n, 256)
+    sel = rng.choice(c.n, size=n, replace=False)
+    rays_np = {k: v[sel].copy() for k, v in c.rays.items()}
+    table = T.SurfaceTable([dataclasses.replace(s, tol=1e-13) if s.kind in T.NEWTON_KINDS else s for s in c.table.surfaces],
+                           c.table.wavelengths)
+    S = table.num_surfaces
+    w = {k: rng.normal(size=(S, n)) for k in REC}
+    _, rec, _ = O.trace(table, rays_np)
+    gin, gpar, gtab = run_backward(load(), table, rays_np, rec, w, tables=True)
+    K = AG.table_to_coefs(table).shape[1]
+    gcoef = AG.tables_to_coef_grads(table, gtab, K)
+
+    def run(dtype):
+        params = AG.table_to_params(table).cuda().requires_grad_(True)
+        coefs = AG.table_to_coefs(table).cuda().requires_grad_(True)
+        rr = RealRays(*[rays_np[k] for k in ("x", "y", "z", "L", "M", "N", "i", "w")], dtype=dtype)
+        for k in ("x", "y", "z", "L", "M", "N"):
+            getattr(rr, k).requires_grad_(True)
+        out = AG.trace_differentiable(table, params, rr, coefs=coefs)
+        loss = sum((out[k].double() * torch.from_numpy(w[k]).cuda()).sum() for k in REC)
+        loss.backward()
+        return params.grad.cpu().numpy(), coefs.grad.cpu().numpy(), {k: getattr(rr, k).grad.double().cpu().numpy() for k in ("x", "y", "L")}
+
+    gp64, gc64, gr64 = run(torch.float64)
+    scale = max(np.abs(gpar).max(), np.abs(gcoef).max())
+    assert np.max(np.abs(gp64 - gpar)) <= 1e-8 * scale
+    assert np.max(np.abs(gc64 - gcoef)) <= 1e-8 * scale
+    for k in gr64:
+        assert np.max(np.abs(gr64[k] - gin[k])) <= 1e-8 * max(1.0, np.abs(gin[k]).max())
+    assert np.abs(gc64).max() > 0
+    gp32, gc32, _ = run(torch.float32)
+    assert np.max(np.abs(gc32 - gc64)) <= 2e-2 * np.abs(gc64).max()
+    assert np.max(np.abs(gp32 - gp64)) <= 2e-2 * scale
+
+
 def test_autograd_selected_rows_equals_dense():
     """rows=(-1,) (gradient read only for the image-surface row) gives the same gradients as the dense form."""
     from optiland_b200 import autograd as AG

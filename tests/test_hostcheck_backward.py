@@ -220,3 +220,85 @@ def test_odd_asphere_adjoint_matches_finite_differences(hc):
         for what, slot, hh in tests:
             ref = fd(table, rays, weights, s, what, hh)
             assert gpar[s, slot] == pytest.approx(ref, rel=2e-4, abs=1e-6 * gmax), (s, what, gpar[s, slot], ref)
+
+
+@pytest.mark.parametrize("name", ["zernike_fringe", "zernike_noll", "misc_apertures_coatings"])
+def test_polynomial_family_adjoint_matches_finite_differences(hc, name):
+    """The adjoint through Zernike / polynomial surfaces (olb_trace_bwd_tables_*: implicit-function theorem with the true
+    sag gradient, the Hessian of the reference's slope polynomial for the normal, table gradients mapped back to the user
+    coefficients): launch-state gradients, curvature / conic / pose of the freeform surface and EVERY coefficient against
+    central differences of the oracle."""
+    c = Case(name)
+    kinds = [s.kind for s in c.table.surfaces]
+    if not any(k in (T.GEOM_ZERNIKE, T.GEOM_POLYNOMIAL) for k in kinds):
+        pytest.skip("no polynomial-family surface in this fixture")
+    rng = np.random.default_rng(1)
+    sel = rng.choice(c.n, size=min(c.n, 48), replace=False)
+    rays = {k: v[sel].copy() for k, v in c.rays.items()}
+    n = sel.size
+    S = c.table.num_surfaces
+    specs = []
+    for s in c.table.surfaces:      # forward-differentiable oracle; other Newton kinds / odd features are not in these fixtures
+        specs.append(dataclasses.replace(s, tol=1e-14) if s.kind in T.NEWTON_KINDS else s)
+    table = T.SurfaceTable(specs, c.table.wavelengths)
+    weights = {k: rng.normal(size=(S, n)) for k in REC}
+    _, rec, st = O.trace(table, rays)
+    assert st == 0
+    gin, gpar, gtab = run_backward(hc, table, rays, rec, weights, tables=True)
+    gmax = max(np.abs(gpar).max(), np.abs(gtab).max())
+    # launch state
+    dirs = {k: rng.normal(size=n) for k in ("x", "y", "z", "L", "M", "N", "i", "opd")}
+    h = 1e-6
+
+    def shifted(sign):
+        r = {k: v.copy() for k, v in rays.items()}
+        r["opd"] = np.zeros(n)
+        for k, d in dirs.items():
+            r[k] = r[k] + sign * h * d
+        return r
+
+    fd_dir = (loss_fn(table, shifted(+1), weights) - loss_fn(table, shifted(-1), weights)) / (2 * h)
+    assert sum(float(np.sum(gin[k] * dirs[k])) for k in dirs) == pytest.approx(fd_dir, rel=2e-4)
+    checked = 0
+    for s, spec in enumerate(table.surfaces):
+        if spec.kind not in (T.GEOM_ZERNIKE, T.GEOM_POLYNOMIAL):
+            continue
+        for what, slot, hh in (("tz", GP["TZ"], 1e-6), ("tx", GP["TX"], 1e-6), ("conic", GP["CONIC"], 1e-5),
+                               ("curv", GP["CURV"], 1e-5 * abs(1.0 / spec.radius))):
+            ref = fd(table, rays, weights, s, what, hh)
+            assert gpar[s, slot] == pytest.approx(ref, rel=2e-4, abs=1e-6 * gmax), (s, what, gpar[s, slot], ref)
+            checked += 1
+        coefs = spec.coefficients
+        if spec.kind == T.GEOM_ZERNIKE:
+            W = int(max(coefs[:, 0])) + 1
+            for k, (nn, mm, cN, cc) in enumerate(coefs):
+                Mk = T.zernike_monomials(int(nn), int(mm), 12)
+                Nk = cN / cc if cc != 0 else 1.0
+                got = Nk * float(np.sum(Mk * gtab[s, 0])) + float(np.sum(Mk * gtab[s, 1]))
+                hh = 1e-6
+
+                def with_coef(delta, k=k, Nk=Nk):
+                    cf = coefs.copy()
+                    cf[k, 3] += delta
+                    cf[k, 2] += delta * Nk
+                    return table.replace_surface(s, coefficients=cf)
+
+                ref = (loss_fn(with_coef(hh), rays, weights) - loss_fn(with_coef(-hh), rays, weights)) / (2 * hh)
+                assert got == pytest.approx(ref, rel=3e-4, abs=1e-6 * gmax), (s, k, nn, mm, got, ref)
+                checked += 1
+        else:
+            rows, cols = coefs.shape
+            for i in range(rows):
+                for j in range(cols):
+                    got = gtab[s, 0, i, j] + gtab[s, 1, i, j]
+                    hh = 1e-6
+
+                    def with_c(delta, i=i, j=j):
+                        cf = coefs.copy()
+                        cf[i, j] += delta
+                        return table.replace_surface(s, coefficients=cf)
+
+                    ref = (loss_fn(with_c(hh), rays, weights) - loss_fn(with_c(-hh), rays, weights)) / (2 * hh)
+                    assert got == pytest.approx(ref, rel=3e-4, abs=1e-6 * gmax), (s, i, j, got, ref)
+                    checked += 1
+    assert checked >= 8
