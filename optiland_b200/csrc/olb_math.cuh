@@ -1093,12 +1093,14 @@ OLB_HD void poly_table_terms(const PolyAdj<T>& pa, int i, int j, T xi, T xim, T 
 // autograd graph gets the gradients of the tilt angles.  It is written straight to the caller's accumulators
 // (shared memory in the kernel) so that the 9 values never live in registers.
 // Returns false (and leaves `a` zeroed) when the ray is not finite at this surface (NaN in band: no gradient).
-template <typename T>
+// POLY == false compiles the polynomial-family branches out (tables without such surfaces: olb_trace_bwd_* keeps the
+// register budget and speed it had before they existed).
+template <typename T, bool POLY = true>
 OLB_HD bool surface_backward(const PrepSurface<T>& S, const T* pool, T xg0, T yg0, T zg0, T L, T M, T N, T i0,
                              T x1g, T y1g, T z1g, Adjoint<T>& a, T* pg, T* gR = nullptr, int gR_stride = 1,
                              PolyAdj<T>* padj = nullptr) {
   // (L, M, N are taken by value: they are rotated into the local frame below for tilted poses)
-  if (padj) padj->active = 0;
+  if (POLY && padj) padj->active = 0;
   const T* med = pool + S.media_off;  // one wavelength
   const T n1 = med[MED_N1], u = med[MED_U];
   const T n2 = o_div(n1, u);
@@ -1164,7 +1166,7 @@ OLB_HD bool surface_backward(const PrepSurface<T>& S, const T* pool, T xg0, T yg
   T Fx = fx, Fy = fy;                   // the true gradient of the sag (-> implicit-function theorem)
   T jxx = 0, jxy = 0, jyx = 0, jyy = 0; // non-radial part of d(fx, fy)/d(x, y)
   T pax = 1, pay = 1, pxn = 0, pyn = 0;
-  const bool polyfam = S.kind == OLB_GEOM_POLYNOMIAL || S.kind == OLB_GEOM_ZERNIKE;
+  const bool polyfam = POLY && (S.kind == OLB_GEOM_POLYNOMIAL || S.kind == OLB_GEOM_ZERNIKE);
   if (polyfam) {
     const bool tri = (S.flags & PSF_POLY_TRI) != 0;
     pxn = x1 * S.inv_norm; pyn = y1 * S.inv_norm_y;

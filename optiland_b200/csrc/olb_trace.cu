@@ -523,7 +523,8 @@ struct BwdArgs {
 #ifndef OLB_BWD_MINB64
 #define OLB_BWD_MINB64 2
 #endif
-template <typename T, bool SMEM_ACC>
+// POLY: the table holds polynomial / Zernike surfaces (table gradients wanted); false compiles those paths out.
+template <typename T, bool SMEM_ACC, bool POLY>
 __global__ void __launch_bounds__(BLOCK, (sizeof(T) == 8 ? OLB_BWD_MINB64 : 2)) trace_bwd_kernel(const __grid_constant__ BwdArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
@@ -549,7 +550,7 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(T) == 8 ? OLB_BWD_MINB64 : 2)) 
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t k = tile * BLOCK + threadIdx.x;
     const bool valid = k < n;
-    if (SMEM_ACC && !valid && a.gtab == nullptr) continue;    // (warp reductions need the whole warp)
+    if (SMEM_ACC && !POLY && !valid) continue;    // (warp reductions need the whole warp)
     const int64_t kk = valid ? k : 0;
     Adjoint<T> ad{0, 0, 0, 0, 0, 0, 0, 0};
     // Software-pipelined walk from the image surface back to the first one.  Surface s needs the state
@@ -616,8 +617,8 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(T) == 8 ? OLB_BWD_MINB64 : 2)) 
         if (SMEM_ACC) {
           T* mine = tacc + (int64_t)S.gslot * BLOCK + threadIdx.x;
           if (valid)
-            surface_backward<T>(S, pool, pre[0], pre[1], pre[2], pre[3], pre[4], pre[5], pre[6], post[0], post[1], post[2],
-                                ad, pg, tilted ? mine + (GP_COEF + ncoef) * BLOCK : nullptr, BLOCK, &pa);
+            surface_backward<T, POLY>(S, pool, pre[0], pre[1], pre[2], pre[3], pre[4], pre[5], pre[6], post[0], post[1], post[2],
+                                      ad, pg, tilted ? mine + (GP_COEF + ncoef) * BLOCK : nullptr, BLOCK, POLY ? &pa : nullptr);
           // pose, curvature, conic, n1, n2: every surface has these 7; only even aspheres have more
 #pragma unroll
           for (int q = 0; q < GP_COEF; ++q) mine[q * BLOCK] += pg[q];
@@ -629,8 +630,8 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(T) == 8 ? OLB_BWD_MINB64 : 2)) 
         } else {
           T r9[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
           if (valid)
-            surface_backward<T>(S, pool, pre[0], pre[1], pre[2], pre[3], pre[4], pre[5], pre[6], post[0], post[1], post[2],
-                                ad, pg, tilted ? r9 : nullptr, 1, &pa);
+            surface_backward<T, POLY>(S, pool, pre[0], pre[1], pre[2], pre[3], pre[4], pre[5], pre[6], post[0], post[1], post[2],
+                                      ad, pg, tilted ? r9 : nullptr, 1, POLY ? &pa : nullptr);
 #pragma unroll
           for (int q = 0; q < GP_SCALARS; ++q) {
             if (q >= GP_COEF + ncoef) break;
@@ -650,7 +651,7 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(T) == 8 ? OLB_BWD_MINB64 : 2)) 
           }
         }
       }
-      if (a.gtab != nullptr && (S.kind == OLB_GEOM_POLYNOMIAL || S.kind == OLB_GEOM_ZERNIKE)) {
+      if (POLY && a.gtab != nullptr && (S.kind == OLB_GEOM_POLYNOMIAL || S.kind == OLB_GEOM_ZERNIKE)) {
         // Table gradients of a polynomial-family surface (warp-uniform branch; every lane takes part in the
         // reductions, inactive rays contribute zeros): dLoss/dS_ij += q xn^i yn^j, dLoss/dD_ij += ax i xn^(i-1) yn^j +
         // ay j xn^i yn^(j-1); one fp64 atomic per entry and warp.
@@ -759,7 +760,9 @@ static int trace_bwd_impl(const OlbDeviceTable* wh, int32_t first, int32_t last,
   const size_t smem_acc = base_smem + (size_t)wh->bwd_slots * BLOCK * sizeof(T);
   const size_t smem_warp = base_smem + (size_t)wh->n_surfaces * GP_COUNT * sizeof(double);
   const bool use_smem_acc = smem_acc <= 110 * 1024;   // 2 CTAs per SM still fit
-  auto kern = use_smem_acc ? trace_bwd_kernel<T, true> : trace_bwd_kernel<T, false>;
+  const bool poly = a.gtab != nullptr;
+  auto kern = use_smem_acc ? (poly ? trace_bwd_kernel<T, true, true> : trace_bwd_kernel<T, true, false>)
+                           : (poly ? trace_bwd_kernel<T, false, true> : trace_bwd_kernel<T, false, false>);
   const size_t smem = use_smem_acc ? smem_acc : smem_warp;
   if (smem > 48 * 1024) OLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, num_sms = 0, per_sm = 0;

@@ -58,22 +58,29 @@ def forward_case(name, n, label, cls=RealRays):
     print(json.dumps(out), flush=True)
 
 
-def autograd_case(n):
-    c = Case("telephoto_c3_tol1e-6")
+def autograd_case(n, name="telephoto_c3_tol1e-6",
+                  label="C3 reverse telephoto + 2 even aspheres: forward + backward (d RMS spot / d all parameters)"):
+    c = Case(name)
     S = c.table.num_surfaces
-    out = {"config": "C3 reverse telephoto + 2 even aspheres: forward + backward (d RMS spot / d all parameters)",
-           "rays": n, "surfaces": S}
+    out = {"config": label, "rays": n, "surfaces": S}
     for dtype, tag in ((torch.float32, "f32"), (torch.float64, "f64")):
         base = resample(c, n, dtype)
         params = AG.table_to_params(c.table).requires_grad_(True)
+        coefs = AG.table_to_coefs(c.table)          # Zernike / polynomial coefficients (None without such surfaces)
+        if coefs is not None:
+            coefs = coefs.requires_grad_(True)
 
         def step():
             rr = RealRays.__new__(RealRays)
             rr.__dict__.update(base.__dict__)
-            rec = AG.trace_differentiable(c.table, params, rr, rows=(-1,))
+            rec = AG.trace_differentiable(c.table, params, rr, rows=(-1,), coefs=coefs)
             x, y = rec["x"], rec["y"]
+            m = torch.isfinite(x) & torch.isfinite(y)
+            x, y = torch.where(m, x, 0), torch.where(m, y, 0)
             loss = torch.sqrt(torch.mean((x - x.mean()) ** 2 + (y - y.mean()) ** 2))
             params.grad = None
+            if coefs is not None:
+                coefs.grad = None
             loss.backward()
 
         ms = timeit(step, k=10)
@@ -141,6 +148,8 @@ CASES = {
                                   "C5: Zernike + Fresnel coatings + polarized, 3 wavelengths, 4M rays/GPU", PolarizedRays),
     "c5shape": lambda: c5_call_shape_case(4_000_000),
     "c3grad": lambda: autograd_case(4_000_000),
+    "zerngrad": lambda: autograd_case(4_000_000, "zernike_fringe", "Zernike freeform singlet: forward + backward incl. d/d Zernike "
+                                      "coefficients (olb_trace_bwd_tables_*)"),
 }
 
 if __name__ == "__main__":

@@ -338,8 +338,9 @@ def test_autograd_ray_input_gradients_and_unsupported_tables():
     fd = (img_y(h) - img_y(-h)) / (2 * h)
     ok = torch.isfinite(fd) & m
     assert float((gy[ok] - fd[ok]).abs().max()) < 1e-6 * float(fd[ok].abs().max() + 1)
-    # a Zernike system is outside the backward kernel's scope: loud error, no silent wrong gradient
-    t = Case("zernike_fringe")
+    # Chebyshev / biconic / toroidal surfaces are outside the backward kernel's scope: loud error, no
+    # silent wrong gradient  (Zernike / polynomial surfaces ARE covered: test_polynomial_family_adjoint_kernel)
+    t = Case("cheb_biconic_toroidal")
     rr = RealRays(*[t.rays[k] for k in ("x", "y", "z", "L", "M", "N", "i", "w")], dtype=torch.float64)
     with pytest.raises(_lib.OlbError, match="not supported"):
         AG.trace_differentiable(t.table, AG.table_to_params(t.table), rr)
@@ -709,7 +710,11 @@ def test_plugin_cuda_engine_on_optiland_shaped_rays():
     tr = types.SimpleNamespace(**{k: torch.from_numpy(t.rays[k]).cuda() for k in ("x", "y", "z", "L", "M", "N", "i", "w")})
     tr.opd = torch.zeros_like(tr.x)
     assert eng.trace_grad(t.table, AG.table_to_params(t.table).cuda(), tr) is not None  # tilted poses are in scope
-    z = Case("zernike_fringe")
+    z = Case("zernike_fringe")      # Zernike / polynomial surfaces: in scope since round 2 (olb_trace_bwd_tables_*)
+    zr = types.SimpleNamespace(**{k: torch.from_numpy(z.rays[k]).cuda() for k in ("x", "y", "z", "L", "M", "N", "i", "w")})
+    zr.opd = torch.zeros_like(zr.x)
+    assert eng.trace_grad(z.table, AG.table_to_params(z.table).cuda(), zr, coefs=AG.table_to_coefs(z.table).cuda()) is not None
+    z = Case("cheb_biconic_toroidal")   # ... Chebyshev / biconic / toroidal are not: the engine declines -> reference path
     zr = types.SimpleNamespace(**{k: torch.from_numpy(z.rays[k]).cuda() for k in ("x", "y", "z", "L", "M", "N", "i", "w")})
     zr.opd = torch.zeros_like(zr.x)
     assert eng.trace_grad(z.table, torch.zeros((z.table.num_surfaces, AG.GP_COUNT), device="cuda"), zr) is None
