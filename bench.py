@@ -261,6 +261,15 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append((time.perf_counter(), line.strip()))
 
+    def wait_first(self, timeout):
+        """Block (bounded) until nvidia-smi has delivered its first sample."""
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.lines and time.perf_counter() - t0 < timeout:
+            time.sleep(0.01)
+
+    def count(self, t_lo):
+        return sum(1 for t, _ in list(self.lines) if t >= t_lo) if self.proc is not None else 1 << 30
+
     def stop(self, t_lo=None, t_hi=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -432,15 +441,17 @@ def run_ours(args):
         barrier()
         return t0e.elapsed_time(t1e), float(np.mean([a.elapsed_time(b) for a, b in ev])), out
 
-    for _ in range(max(args.warmup, 3)):
-        rr, rec = step()
-    del rr, rec
-    barrier()
-
+    # nvidia-smi needs up to a second or two to enumerate the GPUs of an 8-GPU box before its first sample: it is
+    # started BEFORE the warm-up so that it is already streaming when the timed region begins
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-        time.sleep(0.1)
+    for _ in range(max(args.warmup, 3)):
+        rr, rec = step()
+    del rr, rec
+    if rank == 0:
+        sampler.wait_first(3.0)
+    barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches0 = lib.olb_launch_count()
     barrier()
@@ -461,7 +472,7 @@ def run_ours(args):
     # SAME step keeps running, untimed, until the load window is >= 0.1 s, and the clocks line says so
     clock_extra = 0
     t_clock_hi = t_hi
-    while t_clock_hi - t_lo < 0.1:
+    while t_clock_hi - t_lo < 0.1 or (rank == 0 and sampler.count(t_lo) < 3 and t_clock_hi - t_lo < 3.0):
         rr, rec = step()
         torch.cuda.synchronize()
         clock_extra += 1

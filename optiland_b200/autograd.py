@@ -144,6 +144,67 @@ def params_to_table(table: T.SurfaceTable, params: torch.Tensor, coefs: torch.Te
     return T.SurfaceTable(specs, table.wavelengths)
 
 
+class _ParamPacker:
+    """``params_to_table(template, params).packed()`` without building SurfaceSpec objects: the template's packed
+    arrays (C ABI layout, table.py ``pack``) with the parameter VALUES written in place by a handful of vectorised
+    numpy assignments -- the per-step host cost of an optimisation loop (4 M-ray step: 0.16 ms of dataclass copies +
+    re-packing, profiles/r2_c3_step_breakdown.json).  Same bytes as the slow path (tests/test_autograd_cpu.py)."""
+
+    def __init__(self, template: T.SurfaceTable):
+        surf, pool = template.packed()
+        self.surf0, self.pool0 = surf, pool
+        kinds = np.array([s.kind for s in template.surfaces])
+        self.rot = np.nonzero(kinds != T.GEOM_NOOP)[0]
+        self.curved = np.nonzero(np.isin(kinds, (T.GEOM_STANDARD, T.GEOM_EVEN_ASPHERE, T.GEOM_ODD_ASPHERE) + POLY_KINDS))[0]
+        ci, cs, ck = [], [], []
+        for s, spec in enumerate(template.surfaces):
+            if spec.kind in (T.GEOM_EVEN_ASPHERE, T.GEOM_ODD_ASPHERE):
+                k = len(spec.coefficients)
+                ci += list(range(int(surf["coef_off"][s]), int(surf["coef_off"][s]) + k))
+                cs += [s] * k
+                ck += list(range(GP_COEF, GP_COEF + k))
+        self.coef_pool, self.coef_s, self.coef_k = (np.asarray(a, dtype=np.int64) for a in (ci, cs, ck))
+        # media block of a surface (one wavelength): n1, n2, k1, coating n1, coating n2  (table.py pack)
+        self.media = surf["media_off"].astype(np.int64)
+        self.cn1 = np.array([s.coat_n1 is None for s in template.surfaces])
+        self.cn2 = np.array([s.coat_n2 is None for s in template.surfaces])
+
+    def __call__(self, p: np.ndarray):
+        surf, pool = self.surf0.copy(), self.pool0.copy()
+        surf["t"] = p[:, GP_TX:GP_TZ + 1]
+        if len(self.rot):
+            R = surf["R"]
+            R[self.rot] = p[self.rot, GP_R:GP_R + 9]
+            surf["R"] = R
+            # SurfaceSpec.flags: ROTATED <=> R differs from the identity (table.py)
+            fl = surf["flags"]
+            is_rot = np.any(R != np.eye(3).reshape(9), axis=1)
+            surf["flags"] = np.where(is_rot, fl | T.SF_ROTATED, fl & ~np.uint32(T.SF_ROTATED)).astype(fl.dtype)
+        if len(self.curved):
+            cv = p[self.curved, GP_CURV]
+            rad = surf["radius"]
+            with np.errstate(divide="ignore"):
+                rad[self.curved] = np.where(cv == 0, np.inf, 1.0 / np.where(cv == 0, 1.0, cv))
+            surf["radius"] = rad
+            kc = surf["conic"]
+            kc[self.curved] = p[self.curved, GP_CONIC]
+            surf["conic"] = kc
+        if len(self.coef_pool):
+            pool[self.coef_pool] = p[self.coef_s, self.coef_k]
+        pool[self.media] = p[:, GP_N1]
+        pool[self.media + 1] = p[:, GP_N2]
+        pool[self.media[self.cn1] + 3] = p[self.cn1, GP_N1]
+        pool[self.media[self.cn2] + 4] = p[self.cn2, GP_N2]
+        return surf, pool
+
+
+def _packed_from_params(template: T.SurfaceTable, params: torch.Tensor):
+    pk = template.__dict__.get("_param_packer")
+    if pk is None:
+        pk = template.__dict__["_param_packer"] = _ParamPacker(template)
+    return pk(params.detach().double().cpu().numpy())
+
+
 class _TraceFn(torch.autograd.Function):
     """forward(template, holder, rows, params, x, y, z, L, M, N, i, opd).  ``rows`` = None: the 8 outputs
     are the full (S, N) record arrays; ``rows`` = tuple of row indices: 8 * len(rows) outputs, one (N,)
@@ -160,6 +221,11 @@ class _TraceFn(torch.autograd.Function):
             # (the plugin packs it from the live objects the parameters were read from)
             dtab = device_tables[0]
             table = dtab.table
+        elif coefs is None and template.n_wl == 1:
+            # (the DeviceTable's ``table`` stays the TEMPLATE: same structure, the values are those of ``params``)
+            table = template
+            dtab = DeviceTable(template, x.device, packed=_packed_from_params(template, params))
+            device_tables.append(dtab)
         else:
             table = params_to_table(template, params, coefs)
             dtab = DeviceTable(table, x.device)

@@ -1119,8 +1119,9 @@ OLB_HD bool surface_backward(const PrepSurface<T>& S, const T* pool, T xg0, T yg
   }
   const T dd = o_fma(L, L, o_fma(M, M, N * N));
   const T t = o_div(o_fma(x1 - x0, L, o_fma(y1 - y0, M, (z1 - z0) * N)), dd);
-  const T chk = x1 + y1 + z1 + L + M + N + t;
-  if (!(chk == chk) || chk - chk != 0) {  // NaN / inf anywhere
+  // t is built from every input (both intercepts and the direction): a NaN / inf in any of them makes it non-finite
+  // (inf * 0 and inf - inf are NaN), so one test covers them all
+  if (!(t - t == 0)) {
     a.x = a.y = a.z = a.L = a.M = a.N = a.i = a.opd = 0;
     return false;
   }

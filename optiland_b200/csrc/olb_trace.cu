@@ -518,13 +518,15 @@ struct BwdArgs {
 // One ray per thread per tile.  Parameter gradients: PRIVATE fp32/fp64 accumulators per thread in
 // shared memory, laid out [slot][thread] (bank-conflict free), summed over all the rays the thread
 // processes in its persistent loop; reduced across the CTA once at the end (warp tree + one fp64
-// global atomic per slot and CTA).  When a table needs more slots than shared memory holds
-// (SMEM_ACC == false) each surface's contributions are warp-reduced immediately instead.
+// global atomic per slot and CTA)  (ACC == 2).  When the table needs more slots than two resident CTAs can hold that
+// way (fp64 with more than ~50 slots: configuration 3), neighbouring lanes share one accumulator after ONE shuffle
+// (ACC == 1: [slot][thread / 2], half the shared memory); beyond that each surface's contributions are
+// warp-reduced immediately (ACC == 0: five shuffles per value).
 #ifndef OLB_BWD_MINB64
 #define OLB_BWD_MINB64 2
 #endif
 // POLY: the table holds polynomial / Zernike surfaces (table gradients wanted); false compiles those paths out.
-template <typename T, bool SMEM_ACC, bool POLY>
+template <typename T, int ACC, bool POLY>
 __global__ void __launch_bounds__(BLOCK, (sizeof(T) == 8 ? OLB_BWD_MINB64 : 2)) trace_bwd_kernel(const __grid_constant__ BwdArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
@@ -534,11 +536,14 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(T) == 8 ? OLB_BWD_MINB64 : 2)) 
   const PrepSurface<T>* surf = reinterpret_cast<const PrepSurface<T>*>(tab + sizeof(PrepHeader));
   const T* pool = reinterpret_cast<const T*>(surf + H->n_surf);
   unsigned char* after = tab + ((a.blob_bytes + 15) & ~15);
-  T* tacc = reinterpret_cast<T*>(after);                 // SMEM_ACC: [n_slots][BLOCK]
-  double* wacc = reinterpret_cast<double*>(after);       // !SMEM_ACC: [n_surf * GP_COUNT]
+  constexpr bool SMEM_ACC = ACC == 2;                    // one accumulator column per thread
+  constexpr bool PAIR_ACC = ACC == 1;                    // ... per pair of neighbouring lanes
+  constexpr int ACC_COLS = SMEM_ACC ? BLOCK : BLOCK / 2;
+  T* tacc = reinterpret_cast<T*>(after);                 // ACC 2 / 1: [n_slots][ACC_COLS]
+  double* wacc = reinterpret_cast<double*>(after);       // ACC 0: [n_surf * GP_COUNT]
   const int n_slots = a.n_slots;
-  if (SMEM_ACC) {
-    for (int q = threadIdx.x; q < n_slots * BLOCK; q += BLOCK) tacc[q] = 0;
+  if (ACC != 0) {
+    for (int q = threadIdx.x; q < n_slots * ACC_COLS; q += BLOCK) tacc[q] = 0;
   } else {
     for (int q = threadIdx.x; q < a.n_surf * GP_COUNT; q += BLOCK) wacc[q] = 0.0;
   }
@@ -627,6 +632,27 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(T) == 8 ? OLB_BWD_MINB64 : 2)) 
             for (int q = GP_COEF; q < GP_SCALARS; ++q)
               if (q < GP_COEF + ncoef) mine[q * BLOCK] += pg[q];
           }
+        } else if (PAIR_ACC) {
+          T r9[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+          if (valid)
+            surface_backward<T, POLY>(S, pool, pre[0], pre[1], pre[2], pre[3], pre[4], pre[5], pre[6], post[0], post[1], post[2],
+                                      ad, pg, tilted ? r9 : nullptr, 1, POLY ? &pa : nullptr);
+          // lanes 2k and 2k+1 share column k: one shuffle, the even lane accumulates
+          T* mine = tacc + (int64_t)S.gslot * ACC_COLS + (threadIdx.x >> 1);
+          const bool even = (lane & 1) == 0;
+#pragma unroll
+          for (int q = 0; q < GP_SCALARS; ++q) {
+            if (q >= GP_COEF + ncoef) break;
+            const T v = pg[q] + __shfl_xor_sync(0xffffffffu, pg[q], 1);
+            if (even) mine[q * ACC_COLS] += v;
+          }
+          if (tilted) {
+#pragma unroll
+            for (int q = 0; q < 9; ++q) {
+              const T v = r9[q] + __shfl_xor_sync(0xffffffffu, r9[q], 1);
+              if (even) mine[(GP_COEF + ncoef + q) * ACC_COLS] += v;
+            }
+          }
         } else {
           T r9[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
           if (valid)
@@ -695,15 +721,15 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(T) == 8 ? OLB_BWD_MINB64 : 2)) 
     }
   }
   __syncthreads();
-  if (SMEM_ACC) {
-    // CTA reduction: warp w sums slots w, w+8, ...: 8 values per lane, tree, one fp64 atomic
+  if (ACC != 0) {
+    // CTA reduction: warp w sums slots w, w+8, ...: 8 (4) values per lane, tree, one fp64 atomic
     const int warp = threadIdx.x >> 5;
     for (int s = 0; s < a.n_surf; ++s) {
       const PrepSurface<T>& S = surf[s];
       for (int q = warp; q < S.gslots; q += BLOCK / 32) {
-        const T* col = tacc + (int64_t)(S.gslot + q) * BLOCK;
+        const T* col = tacc + (int64_t)(S.gslot + q) * ACC_COLS;
         double v = 0;
-        for (int j = lane; j < BLOCK; j += 32) v += (double)col[j];
+        for (int j = lane; j < ACC_COLS; j += 32) v += (double)col[j];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         // slot -> parameter: scalars and coefficients in place, the tilted pose's 9 slots -> GP_R ..
@@ -759,11 +785,16 @@ static int trace_bwd_impl(const OlbDeviceTable* wh, int32_t first, int32_t last,
   const size_t base_smem = 16 + (((size_t)a.blob_bytes + 15) & ~size_t(15));
   const size_t smem_acc = base_smem + (size_t)wh->bwd_slots * BLOCK * sizeof(T);
   const size_t smem_warp = base_smem + (size_t)wh->n_surfaces * GP_COUNT * sizeof(double);
-  const bool use_smem_acc = smem_acc <= 110 * 1024;   // 2 CTAs per SM still fit
+  const size_t smem_pair = base_smem + (size_t)wh->bwd_slots * (BLOCK / 2) * sizeof(T);
+  // 2 CTAs per SM must still fit: 228 KB per SM, 1 KB of it reserved per resident CTA -> 113 KB each
+  static const int force_acc = [] { const char* e = getenv("OLB_BWD_ACC"); return e ? atoi(e) : -1; }();   // (profiling)
+  int acc = smem_acc <= 113 * 1024 ? 2 : (smem_pair <= 113 * 1024 ? 1 : 0);
+  if (force_acc >= 0 && force_acc < acc) acc = force_acc;
   const bool poly = a.gtab != nullptr;
-  auto kern = use_smem_acc ? (poly ? trace_bwd_kernel<T, true, true> : trace_bwd_kernel<T, true, false>)
-                           : (poly ? trace_bwd_kernel<T, false, true> : trace_bwd_kernel<T, false, false>);
-  const size_t smem = use_smem_acc ? smem_acc : smem_warp;
+  auto kern = acc == 2 ? (poly ? trace_bwd_kernel<T, 2, true> : trace_bwd_kernel<T, 2, false>)
+            : acc == 1 ? (poly ? trace_bwd_kernel<T, 1, true> : trace_bwd_kernel<T, 1, false>)
+                       : (poly ? trace_bwd_kernel<T, 0, true> : trace_bwd_kernel<T, 0, false>);
+  const size_t smem = acc == 2 ? smem_acc : acc == 1 ? smem_pair : smem_warp;
   if (smem > 48 * 1024) OLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, num_sms = 0, per_sm = 0;
   OLB_CUDA(cudaGetDevice(&dev));

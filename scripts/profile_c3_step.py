@@ -2,7 +2,7 @@
 host table build + upload, forward kernel, the loss in eager torch, its autograd, the adjoint kernel, the D2H of the
 gradient block.  Device segments are timed with CUDA events, host segments with perf_counter after a synchronize.
 
-    python scripts/profile_c3_step.py [n_rays]
+    python scripts/profile_c3_step.py [n_rays [golden case]]     # e.g. 4000000 zernike_fringe
 """
 import json
 import os
@@ -20,11 +20,15 @@ from tests._util import Case  # noqa: E402
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 4_000_000
-    c = Case("telephoto_c3_tol1e-6")
-    out = {"rays": n, "surfaces": c.table.num_surfaces}
+    name = sys.argv[2] if len(sys.argv) > 2 else "telephoto_c3_tol1e-6"
+    c = Case(name)
+    out = {"system": name, "rays": n, "surfaces": c.table.num_surfaces}
     for dtype, tag in ((torch.float32, "f32"), (torch.float64, "f64")):
         base = resample(c, n, dtype)
         params = AG.table_to_params(c.table).requires_grad_(True)
+        coefs = AG.table_to_coefs(c.table)
+        if coefs is not None:
+            coefs = coefs.requires_grad_(True)
         seg = {}
 
         def mark(name, t0):
@@ -38,18 +42,28 @@ def main():
             t = time.perf_counter()
             if measure:
                 # the two host pieces of trace_differentiable's forward, timed on their own
-                table = AG.params_to_table(c.table, params)
-                t = mark("host_params_to_table", t)
-                DeviceTable(table, "cuda:0")
+                if coefs is None:
+                    packed = AG._packed_from_params(c.table, params)
+                    t = mark("host_pack_params", t)
+                    DeviceTable(c.table, "cuda:0", packed=packed)
+                else:
+                    table = AG.params_to_table(c.table, params, coefs)
+                    t = mark("host_pack_params", t)
+                    DeviceTable(table, "cuda:0")
                 t = mark("host_prepare_upload", t)
-            rec = AG.trace_differentiable(c.table, params, rr, rows=(-1,))
+            rec = AG.trace_differentiable(c.table, params, rr, rows=(-1,), coefs=coefs)
             if measure:
                 t = mark("forward_total(incl. the two above again)", t)
             x, y = rec["x"], rec["y"]
+            if coefs is not None:       # (a freeform fixture has rays that miss: NaN in band)
+                m = torch.isfinite(x) & torch.isfinite(y)
+                x, y = torch.where(m, x, 0), torch.where(m, y, 0)
             loss = torch.sqrt(torch.mean((x - x.mean()) ** 2 + (y - y.mean()) ** 2))
             if measure:
                 t = mark("loss_eager", t)
             params.grad = None
+            if coefs is not None:
+                coefs.grad = None
             loss.backward()
             if measure:
                 t = mark("backward_total(autograd of the loss + adjoint kernel + D2H)", t)

@@ -68,3 +68,27 @@ def test_cuda_resident_parameters_are_fetched_in_one_copy(name):
     rays.opd = torch.zeros_like(rays.x)
     rec = eng.trace(got, rays, 0, got.num_surfaces)
     np.testing.assert_allclose(rec["x"].cpu().numpy(), c.rec["x"], rtol=0, atol=1e-11 * c.scale, equal_nan=True)
+
+
+@pytest.mark.parametrize("name", ["telephoto_c3_tol1e-6", "dgauss_c2", "hubble_c4", "tilted_fold", "misc_apertures_coatings",
+                                  "zernike_fringe", "aspheric_singlet", "cooke_polarized"])
+def test_vectorised_parameter_packer_equals_params_to_table(name):
+    """autograd._ParamPacker (the per-step host path of the differentiable trace) writes the parameter values into the
+    template's packed arrays: byte-identical to rebuilding the table surface by surface."""
+    from optiland_b200 import autograd as AG
+
+    c = Case(name)
+    if c.table.n_wl != 1:
+        pytest.skip("one wavelength per differentiable trace")
+    rng = np.random.default_rng(3)
+    p0 = AG.table_to_params(c.table)
+    for trial in range(3):
+        p = p0.clone()
+        if trial:
+            p = p * torch.from_numpy(1 + 1e-3 * rng.standard_normal(p.shape)) + torch.from_numpy(1e-4 * rng.standard_normal(p.shape))
+            p[:, AG.GP_CURV][rng.random(len(p)) < 0.2] = 0.0        # flat surfaces: radius = inf
+        slow = AG.params_to_table(c.table, p)
+        sa, pa = slow.pack()
+        sb, pb = AG._packed_from_params(c.table, p)
+        assert sa.tobytes() == sb.tobytes()
+        assert pa.tobytes() == pb.tobytes()
