@@ -50,7 +50,21 @@ def table_to_params(table: T.SurfaceTable) -> torch.Tensor:
     return torch.from_numpy(p)
 
 
-POLY_KINDS = (T.GEOM_POLYNOMIAL, T.GEOM_ZERNIKE)
+POLY_KINDS = (T.GEOM_POLYNOMIAL, T.GEOM_ZERNIKE, T.GEOM_CHEBYSHEV)
+
+
+def chebyshev_monomials(n: int) -> np.ndarray:
+    """(n, n) matrix Tc with T_i(x) = sum_p Tc[i, p] x**p (T_0 = 1, T_1 = x, T_{i+1} = 2 x T_i - T_{i-1}): the
+    expansion the table upload applies to a Chebyshev surface (csrc/olb_prep.h)."""
+    Tc = np.zeros((n, n))
+    if n > 0:
+        Tc[0, 0] = 1.0
+    if n > 1:
+        Tc[1, 1] = 1.0
+    for i in range(2, n):
+        Tc[i, 1:] = 2.0 * Tc[i - 1, :-1]
+        Tc[i] -= Tc[i - 2]
+    return Tc
 
 
 def zernike_norms(spec) -> np.ndarray:
@@ -64,12 +78,12 @@ def zernike_norms(spec) -> np.ndarray:
 
 def table_to_coefs(table: T.SurfaceTable) -> torch.Tensor | None:
     """(S, K) fp64 tensor of the USER coefficients of the polynomial-family surfaces (Zernike: c_k in term order;
-    polynomial: C_ij row-major), zero-padded to the longest; None when the table has none."""
+    polynomial and Chebyshev: C_ij row-major), zero-padded to the longest; None when the table has none."""
     rows = []
     for spec in table.surfaces:
         if spec.kind == T.GEOM_ZERNIKE:
             rows.append(spec.coefficients.reshape(-1, 4)[:, 3].copy())
-        elif spec.kind == T.GEOM_POLYNOMIAL:
+        elif spec.kind in (T.GEOM_POLYNOMIAL, T.GEOM_CHEBYSHEV):
             rows.append(np.atleast_2d(spec.coefficients).ravel().copy())
         else:
             rows.append(np.zeros(0))
@@ -95,6 +109,10 @@ def _coef_maps(table: T.SurfaceTable):
                 maps[s] = ("zernike", M * zernike_norms(spec)[:, None, None], M)
             elif spec.kind == T.GEOM_POLYNOMIAL:
                 maps[s] = ("polynomial", np.atleast_2d(spec.coefficients).shape)
+            elif spec.kind == T.GEOM_CHEBYSHEV:
+                shp = np.atleast_2d(spec.coefficients).shape
+                Tc = chebyshev_monomials(max(shp))
+                maps[s] = ("chebyshev", shp, Tc[:shp[0], :shp[0]], Tc[:shp[1], :shp[1]])
         table.__dict__["_coef_maps"] = maps
     return maps
 
@@ -106,6 +124,11 @@ def tables_to_coef_grads(table: T.SurfaceTable, gtab: np.ndarray, K: int) -> np.
         if m[0] == "zernike":
             g = np.tensordot(m[1], gtab[s, 0], axes=2) + np.tensordot(m[2], gtab[s, 1], axes=2)
             out[s, :len(g)] = g
+        elif m[0] == "chebyshev":
+            # ONE monomial table P_pq = sum_ij C_ij Tc[i, p] Tc[j, q] serves the sag and the slopes
+            r, c = m[1]
+            g = gtab[s, 0, :r, :c] + gtab[s, 1, :r, :c]
+            out[s, :r * c] = (m[2] @ g @ m[3].T).ravel()
         else:
             r, c = m[1]
             out[s, :r * c] = (gtab[s, 0, :r, :c] + gtab[s, 1, :r, :c]).ravel()
@@ -137,7 +160,7 @@ def params_to_table(table: T.SurfaceTable, params: torch.Tensor, coefs: torch.Te
                     cf[:, 2] = cf[:, 3] * zernike_norms(spec)
                     ch["coefficients"] = cf
                     ch["zernike_norms"] = zernike_norms(spec)
-                else:
+                else:                                   # polynomial, Chebyshev: C_ij row-major
                     shp = np.atleast_2d(spec.coefficients).shape
                     ch["coefficients"] = cv[s, :shp[0] * shp[1]].reshape(shp).copy()
         specs.append(dataclasses.replace(spec, **ch))

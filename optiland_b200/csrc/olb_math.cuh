@@ -1073,6 +1073,12 @@ struct Adjoint { T x, y, z, L, M, N, i, opd; };
 // back to the user's coefficients, in which the tables are linear.
 template <typename T> struct PolyAdj { T q, ax, ay, xn, yn; int active; };
 
+// The geometry kinds whose sag / slope polynomials are bivariate monomial tables covered by the adjoint.  (A Chebyshev
+// surface is expanded into monomials of (x / norm_x, y / norm_y) on upload, olb_prep.h: ONE table serves sag and slopes.)
+OLB_HD bool poly_family_kind(int kind) {
+  return kind == OLB_GEOM_POLYNOMIAL || kind == OLB_GEOM_ZERNIKE || kind == OLB_GEOM_CHEBYSHEV;
+}
+
 // Table gradients of the polynomial families (olb_trace_bwd_tables_*): per surface two blocks (sag table S, slope table
 // D) of GT_DIM x GT_DIM doubles, entry (i, j) <-> xn^i yn^j; tables wider than GT_DIM are outside the adjoint's scope.
 enum { GT_DIM = 12, GT_BLOCK = GT_DIM * GT_DIM, GT_PER_SURFACE = 2 * GT_BLOCK };
@@ -1167,7 +1173,7 @@ OLB_HD bool surface_backward(const PrepSurface<T>& S, const T* pool, T xg0, T yg
   T Fx = fx, Fy = fy;                   // the true gradient of the sag (-> implicit-function theorem)
   T jxx = 0, jxy = 0, jyx = 0, jyy = 0; // non-radial part of d(fx, fy)/d(x, y)
   T pax = 1, pay = 1, pxn = 0, pyn = 0;
-  const bool polyfam = POLY && (S.kind == OLB_GEOM_POLYNOMIAL || S.kind == OLB_GEOM_ZERNIKE);
+  const bool polyfam = POLY && poly_family_kind(S.kind);
   if (polyfam) {
     const bool tri = (S.flags & PSF_POLY_TRI) != 0;
     pxn = x1 * S.inv_norm; pyn = y1 * S.inv_norm_y;
@@ -1192,7 +1198,11 @@ OLB_HD bool surface_backward(const PrepSurface<T>& S, const T* pool, T xg0, T yg
         Dys = o_fma(Dy, o_fma(a_, yy, b_ * xx), Dx * xy) * inv;
       }
     }
-    pax = S.inv_norm; pay = S.inv_norm_y;
+    // the reference's Chebyshev slope function leaves the chain-rule factors 1 / norm_x, 1 / norm_y out
+    // (chebyshev.py:171-181; newton_slopes above reproduces it): the NORMAL is differentiated as the forward pass
+    // computes it, the intersection (Fx, Fy) by the true gradient of the sag
+    const bool cheb = S.kind == OLB_GEOM_CHEBYSHEV;
+    pax = cheb ? (T)1 : S.inv_norm; pay = cheb ? (T)1 : S.inv_norm_y;
     fx = o_fma(Dxs, pax, fx);
     fy = o_fma(Dys, pay, fy);
     jxx = pax * S.inv_norm * Dxx; jxy = pax * S.inv_norm_y * Dxy;

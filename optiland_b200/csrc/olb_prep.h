@@ -482,7 +482,8 @@ static inline PrepResult prepare_table(const OlbTable& tab) {
   res.total_gslots = gslot;
   for (int s = 0; s < tab.n_surfaces; ++s) {
     const PrepSurface<double>& o = ps[s];
-    const bool polyfam = (o.kind == OLB_GEOM_POLYNOMIAL || o.kind == OLB_GEOM_ZERNIKE) && o.poly_rows <= 12 && o.poly_cols <= 12;
+    const bool polyfam = (o.kind == OLB_GEOM_POLYNOMIAL || o.kind == OLB_GEOM_ZERNIKE || o.kind == OLB_GEOM_CHEBYSHEV) &&
+                         o.poly_rows <= 12 && o.poly_cols <= 12;
     const bool kind_ok = o.kind == OLB_GEOM_NOOP || o.kind == OLB_GEOM_PLANE || o.kind == OLB_GEOM_STANDARD ||
                          ((o.kind == OLB_GEOM_EVEN_ASPHERE || o.kind == OLB_GEOM_ODD_ASPHERE) && o.n_coef <= 12) || polyfam;
     if (polyfam) res.bwd_tables = true;

@@ -677,7 +677,7 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(T) == 8 ? OLB_BWD_MINB64 : 2)) 
           }
         }
       }
-      if (POLY && a.gtab != nullptr && (S.kind == OLB_GEOM_POLYNOMIAL || S.kind == OLB_GEOM_ZERNIKE)) {
+      if (POLY && a.gtab != nullptr && poly_family_kind(S.kind)) {
         // Table gradients of a polynomial-family surface (warp-uniform branch; every lane takes part in the
         // reductions, inactive rays contribute zeros): dLoss/dS_ij += q xn^i yn^j, dLoss/dD_ij += ax i xn^(i-1) yn^j +
         // ay j xn^i yn^(j-1); one fp64 atomic per entry and warp.

@@ -461,7 +461,8 @@ def _live_params(surfaces, table, wavelength):
             g = surf.geometry
             cs = g.cs
             if cs.reference_cs is not None or spec.kind not in (T.GEOM_PLANE, T.GEOM_STANDARD, T.GEOM_EVEN_ASPHERE,
-                                                                T.GEOM_ODD_ASPHERE, T.GEOM_POLYNOMIAL, T.GEOM_ZERNIKE):
+                                                                T.GEOM_ODD_ASPHERE, T.GEOM_POLYNOMIAL, T.GEOM_ZERNIKE,
+                                                                T.GEOM_CHEBYSHEV):
                 return None
             # pose rotation: constants (identity for an untilted surface -- the reference skips zero rotations
             # altogether, `if self.rz:` coordinate_system.py:84-89, so zero angles get no gradient there either);
@@ -502,9 +503,9 @@ def _live_params(surfaces, table, wavelength):
 
 def _live_coefs(surfaces, table):
     """(S, K) fp64 tensor of the USER coefficients of the polynomial-family surfaces (Zernike ``geometry.zernike.coeffs``,
-    polynomial ``geometry.coefficients``), stacked from the LIVE tensors so that the table gradients of
+    polynomial / Chebyshev ``geometry.coefficients``), stacked from the LIVE tensors so that the table gradients of
     olb_trace_bwd_tables_* flow back to the optimiser's variables (optimization/variable/zernike_coeff.py,
-    polynomial_coeff.py); None when the table has no such surface."""
+    polynomial_coeff.py, chebyshev_coeff.py); None when the table has no such surface."""
     import torch
 
     rows, K, dev = [], 0, None
@@ -512,7 +513,7 @@ def _live_coefs(surfaces, table):
         r = None
         if spec.kind == T.GEOM_ZERNIKE:
             r = surf.geometry.zernike.coeffs
-        elif spec.kind == T.GEOM_POLYNOMIAL:
+        elif spec.kind in (T.GEOM_POLYNOMIAL, T.GEOM_CHEBYSHEV):
             c = surf.geometry.coefficients
             r = c if torch.is_tensor(c) else torch.stack([torch.stack([torch.as_tensor(v) for v in row]) for row in c])
         if r is not None:

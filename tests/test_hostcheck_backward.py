@@ -302,3 +302,70 @@ def test_polynomial_family_adjoint_matches_finite_differences(hc, name):
                     assert got == pytest.approx(ref, rel=3e-4, abs=1e-6 * gmax), (s, i, j, got, ref)
                     checked += 1
     assert checked >= 8
+
+
+def chebyshev_table():
+    """The Chebyshev surface of the `cheb_biconic_toroidal` fixture (4 x 4 coefficients, norm_x != norm_y, conic base)
+    in front of two plain conics (the biconic / toroidal surfaces of the fixture are outside the adjoint's scope)."""
+    c = Case("cheb_biconic_toroidal")
+    specs = []
+    for s in c.table.surfaces:
+        if s.kind in (T.GEOM_BICONIC, T.GEOM_TOROIDAL):
+            s = dataclasses.replace(s, kind=T.GEOM_STANDARD, coefficients=np.zeros(0), conic=0.2)
+        elif s.kind in T.NEWTON_KINDS:
+            s = dataclasses.replace(s, tol=1e-14)
+        specs.append(s)
+    return c, T.SurfaceTable(specs, c.table.wavelengths)
+
+
+def test_chebyshev_adjoint_matches_finite_differences(hc):
+    """The adjoint through a Chebyshev surface: the table upload expands sum C_ij T_i(x / norm_x) T_j(y / norm_y) into ONE
+    monomial table that serves sag and slopes; the reference's slope function omits the chain-rule factors 1 / norm
+    (chebyshev.py:171-181), the forward pass reproduces that and the adjoint differentiates the normal AS COMPUTED while
+    the intersection uses the true sag gradient.  Launch state, pose / curvature / conic and every C_ij against central
+    differences of the oracle (which evaluates the reference's cos(n arccos x) form)."""
+    from optiland_b200 import autograd as AG
+
+    c, table = chebyshev_table()
+    ht = _lib.HostTable(table)
+    assert hc.olbhc_bwd_supported(C.byref(ht.c))
+    rng = np.random.default_rng(5)
+    sel = rng.choice(c.n, size=48, replace=False)
+    rays = {k: v[sel].copy() for k, v in c.rays.items()}
+    n = sel.size
+    S = table.num_surfaces
+    weights = {k: rng.normal(size=(S, n)) for k in REC}
+    _, rec, st = O.trace(table, rays)
+    assert st == 0 and np.isfinite(rec["x"]).all()
+    gin, gpar, gtab = run_backward(hc, table, rays, rec, weights, tables=True)
+    gmax = max(np.abs(gpar).max(), np.abs(gtab).max())
+    dirs = {k: rng.normal(size=n) for k in ("x", "y", "z", "L", "M", "N", "i", "opd")}
+    h = 1e-6
+
+    def shifted(sign):
+        r = {k: v.copy() for k, v in rays.items()}
+        r["opd"] = np.zeros(n)
+        for k, d in dirs.items():
+            r[k] = r[k] + sign * h * d
+        return r
+
+    fd_dir = (loss_fn(table, shifted(+1), weights) - loss_fn(table, shifted(-1), weights)) / (2 * h)
+    assert sum(float(np.sum(gin[k] * dirs[k])) for k in dirs) == pytest.approx(fd_dir, rel=2e-4)
+    s = [j for j, sp in enumerate(table.surfaces) if sp.kind == T.GEOM_CHEBYSHEV][0]
+    spec = table.surfaces[s]
+    for what, slot, hh in (("tz", GP["TZ"], 1e-6), ("tx", GP["TX"], 1e-6), ("conic", GP["CONIC"], 1e-5),
+                           ("curv", GP["CURV"], 1e-5 * abs(1.0 / spec.radius)), ("n2", GP["N2"], 1e-6)):
+        ref = fd(table, rays, weights, s, what, hh)
+        assert gpar[s, slot] == pytest.approx(ref, rel=2e-4, abs=1e-6 * gmax), (what, gpar[s, slot], ref)
+    coefs = np.atleast_2d(spec.coefficients)
+    K = coefs.size
+    gc = AG.tables_to_coef_grads(table, gtab, K)[s].reshape(coefs.shape)
+    for i in range(coefs.shape[0]):
+        for j in range(coefs.shape[1]):
+            def with_c(delta, i=i, j=j):
+                cf = coefs.copy()
+                cf[i, j] += delta
+                return table.replace_surface(s, coefficients=cf)
+
+            ref = (loss_fn(with_c(1e-6), rays, weights) - loss_fn(with_c(-1e-6), rays, weights)) / 2e-6
+            assert gc[i, j] == pytest.approx(ref, rel=3e-4, abs=1e-6 * gmax), (i, j, gc[i, j], ref)

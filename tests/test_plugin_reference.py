@@ -578,10 +578,11 @@ def test_autograd_tilt_and_decenter_variables_match_reference_eager_graph(plugin
 
 def test_autograd_zernike_and_polynomial_coefficient_variables(plugin):
     """Freeform optimisation variables through the capability: d(RMS spot)/d(Zernike coefficient), d/d(polynomial
-    coefficient), d/d(radius, conic) of the freeform surface -- forward kernel + the polynomial-family adjoint
+    coefficient), d/d(Chebyshev coefficient), d/d(radius, conic) of the freeform surface -- forward kernel + the polynomial-family adjoint
     (olb_trace_bwd_tables_*: table gradients mapped back to the live coefficient tensors) -- equal the reference's own
     eager autograd, with the coefficients set the way ZernikeCoeffVariable / PolynomialCoeffVariable set them
-    (optimization/variable/zernike_coeff.py:71-95: ``geometry.coefficients[i] = value``)."""
+    (optimization/variable/zernike_coeff.py:71-95: ``geometry.coefficients[i] = value``; polynomial_coeff.py:77-81 and its
+    subclass chebyshev_coeff.py: ``geometry.coefficients[i][j] = value``)."""
     import torch
 
     P, eng, be = plugin
@@ -594,6 +595,21 @@ def test_autograd_zernike_and_polynomial_coefficient_variables(plugin):
         lens.surfaces.add(index=0, radius=be.inf, thickness=be.inf)
         lens.surfaces.add(index=1, radius=35.0, thickness=5.0, material="N-BK7", is_stop=True, surface_type="polynomial",
                           conic=-0.3, coefficients=[[0.0, 1e-3, -2e-4], [2e-3, -3e-4, 1e-5], [4e-4, 2e-5, -1e-6]], tol=1e-12)
+        lens.surfaces.add(index=2, radius=-70.0, thickness=40.0)
+        lens.surfaces.add(index=3)
+        lens.set_aperture(aperture_type="EPD", value=12.0)
+        lens.fields.set_type(field_type="angle")
+        lens.fields.add(y=0)
+        lens.fields.add(y=4)
+        lens.wavelengths.add(value=0.55, is_primary=True)
+        return lens
+
+    def make_cheb():
+        lens = _optic.Optic()
+        lens.surfaces.add(index=0, radius=be.inf, thickness=be.inf)
+        lens.surfaces.add(index=1, radius=40.0, thickness=5.0, material="N-BK7", is_stop=True, surface_type="chebyshev",
+                          conic=-0.2, coefficients=[[0.0, 2e-3, -5e-4], [1e-3, -4e-4, 1e-4], [3e-4, 1e-4, -5e-5]],
+                          norm_x=9.0, norm_y=11.0, tol=1e-12)
         lens.surfaces.add(index=2, radius=-70.0, thickness=40.0)
         lens.surfaces.add(index=3)
         lens.set_aperture(aperture_type="EPD", value=12.0)
@@ -651,7 +667,8 @@ def test_autograd_zernike_and_polynomial_coefficient_variables(plugin):
 
     be.grad_mode.enable()
     try:
-        for make, kind in ((lambda: zernike_singlet("fringe"), "zernike"), (make_poly, "polynomial")):
+        for make, kind in ((lambda: zernike_singlet("fringe"), "zernike"), (make_poly, "polynomial"),
+                           (make_cheb, "chebyshev")):
             P.install(engine=eng)
             P.stats(reset=True)
             n0 = len(eng.calls)
