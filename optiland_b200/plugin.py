@@ -558,6 +558,49 @@ def _wants_grad(backend, surfaces, rays=None) -> bool:
     return False
 
 
+def _trace_grad_per_wavelength(engine, surfaces, rays, table_builder, wl):
+    """Differentiable trace of a batch that mixes several wavelengths (``trace_generic`` with a per-ray wavelength
+    array while gradients are wanted).  The adjoint kernel works on one medium table per call, and the indices
+    n(lambda_j) are DIFFERENT differentiable functions of the live material tensors (``AbbeMaterial.index / abbe``,
+    ``IdealMaterial.index``), so the batch is split by wavelength: one forward + one adjoint launch per wavelength on
+    the rays that carry it, each with its own live parameter block, and the records are put back in the caller's ray
+    order by one differentiable gather per (quantity, row).  Returns the record dict of per-row tensors, or None when
+    some wavelength's table is outside the adjoint's scope (nothing has been modified then)."""
+    import torch
+
+    from types import SimpleNamespace
+
+    w = rays.w.detach()
+    keys = ("x", "y", "z", "L", "M", "N", "i", "opd")
+    groups = []
+    for wj in wl:
+        idx = torch.nonzero(w == float(wj)).reshape(-1)
+        table_j = table_builder(np.array([float(wj)], dtype=np.float64))
+        _prepare(engine, table_j, rays.x.device)
+        params = _live_params(surfaces, table_j, float(wj))
+        if params is None:
+            return None
+        groups.append((idx, table_j, params, _live_coefs(surfaces, table_j)))
+    parts = []
+    for idx, table_j, params, coefs in groups:
+        sub = SimpleNamespace(**{k: getattr(rays, k)[idx] for k in keys}, w=rays.w[idx])
+        rec_j = engine.trace_grad(table_j, params, sub, coefs) if coefs is not None else engine.trace_grad(table_j, params, sub)
+        if rec_j is None:
+            return None
+        parts.append(rec_j)
+    # position of every original ray inside the concatenation of the groups
+    order = torch.cat([g[0] for g in groups])
+    inv = torch.empty_like(order)
+    inv[order] = torch.arange(order.numel(), device=order.device)
+    S = len(surfaces)
+    rec = {}
+    for key in ("x", "y", "z", "L", "M", "N", "intensity", "opd"):
+        rec[key] = [torch.cat([p[key][row] for p in parts])[inv] for row in range(S)]
+    for k, key in (("x", "x"), ("y", "y"), ("z", "z"), ("L", "L"), ("M", "M"), ("N", "N"), ("i", "intensity"), ("opd", "opd")):
+        setattr(rays, k, rec[key][-1])
+    return rec
+
+
 def _try_trace(backend, surfaces, rays, table_builder) -> bool:
     """Common body of the two wrappers.  ``surfaces``: the Surface objects to be traced (in
     order); ``table_builder(wavelengths)`` packs them.  Returns False to decline."""
@@ -589,15 +632,23 @@ def _try_trace(backend, surfaces, rays, table_builder) -> bool:
         # (optimization/operand/ray.py:299-342 differentiates through a recorded row).  One custom
         # Function (forward kernel + adjoint kernel) replaces the eager graph; tables outside the
         # adjoint's scope go back to the reference's eager path.
-        if polarized or table.n_wl != 1:
-            return _decline("gradients wanted: polarized rays or several wavelengths in one call")
-        params = _live_params(surfaces, table, float(wl[0]))
-        if params is None:
-            return _decline("gradients wanted: a surface outside the adjoint's scope")
-        coefs = _live_coefs(surfaces, table)
-        rec = engine.trace_grad(table, params, rays, coefs) if coefs is not None else engine.trace_grad(table, params, rays)
-        if rec is None:
-            return _decline("gradients wanted: table outside the adjoint's scope")
+        if polarized:
+            return _decline("gradients wanted: polarized rays")
+        if table.n_wl != 1:
+            try:
+                rec = _trace_grad_per_wavelength(engine, surfaces, rays, table_builder, wl)
+            except _PACK_ERRORS as e:
+                return _decline(f"unsupported: {e}")
+            if rec is None:
+                return _decline("gradients wanted: a surface / table outside the adjoint's scope")
+        else:
+            params = _live_params(surfaces, table, float(wl[0]))
+            if params is None:
+                return _decline("gradients wanted: a surface outside the adjoint's scope")
+            coefs = _live_coefs(surfaces, table)
+            rec = engine.trace_grad(table, params, rays, coefs) if coefs is not None else engine.trace_grad(table, params, rays)
+            if rec is None:
+                return _decline("gradients wanted: table outside the adjoint's scope")
     else:
         rec = engine.trace(table, rays, 0, table.num_surfaces)
     for row, surf in enumerate(surfaces):

@@ -697,6 +697,73 @@ def test_autograd_zernike_and_polynomial_coefficient_variables(plugin):
         be.grad_mode.disable()
 
 
+def test_autograd_trace_generic_with_several_wavelengths_in_one_call(plugin):
+    """``trace_generic`` with a per-ray wavelength array while gradients are wanted: the batch is split by wavelength
+    (one forward + one adjoint launch each, with that wavelength's live indices) and the records come back in the
+    caller's ray order.  Loss = RMS spot over all rays; gradients w.r.t. a radius, a thickness (surface z), a conic, the
+    Abbe material's index AND Abbe number (n(lambda) differs per wavelength and is a differentiable function of both:
+    materials/abbe.py:45-76, the polynomial model's leaves) equal the reference's own eager autograd."""
+    import torch
+
+    P, eng, be = plugin
+    from optiland import optic as _optic
+    from optiland.materials import AbbeMaterial
+
+    def make():
+        lens = _optic.Optic()
+        lens.surfaces.add(index=0, radius=be.inf, thickness=be.inf)
+        lens.surfaces.add(index=1, radius=45.0, thickness=6.0, material=AbbeMaterial(1.62, 45.0, model="polynomial"), is_stop=True, conic=-0.4)
+        lens.surfaces.add(index=2, radius=-60.0, thickness=3.0, material="SF5")
+        lens.surfaces.add(index=3, radius=-150.0, thickness=60.0)
+        lens.surfaces.add(index=4)
+        lens.set_aperture(aperture_type="EPD", value=14.0)
+        lens.fields.set_type(field_type="angle")
+        lens.fields.add(y=0)
+        lens.fields.add(y=5)
+        for wv, prim in ((0.4861, False), (0.5876, True), (0.6563, False)):
+            lens.wavelengths.add(value=wv, is_primary=prim)
+        return lens
+
+    rng = np.random.default_rng(3)
+    n = 60
+    r, th = np.sqrt(rng.uniform(size=n)), rng.uniform(0, 2 * np.pi, size=n)
+    Px, Py = r * np.cos(th), r * np.sin(th)
+    Hy = rng.choice([0.0, 0.7, 1.0], size=n)
+    wv = rng.choice([0.4861, 0.5876, 0.6563], size=n)        # interleaved: the regrouping has to undo a real permutation
+
+    def run(lens):
+        dev = lens.surfaces.surfaces[1].geometry.radius.device
+        t = lambda a: torch.as_tensor(a, dtype=torch.float64, device=dev)  # noqa: E731
+        cs2 = lens.surfaces.surfaces[2].geometry.cs
+        cs2.z = torch.tensor(float(cs2.z), dtype=torch.float64, device=dev, requires_grad=True)   # a leaf, like a thickness variable
+        rays = lens.trace_generic(t(np.zeros(n)), t(Hy), t(Px), t(Py), t(wv))
+        x, y = lens.surfaces.x[-1, :], lens.surfaces.y[-1, :]
+        loss = torch.sqrt(torch.mean((x - torch.mean(x)) ** 2 + (y - torch.mean(y)) ** 2)) + 1e-3 * torch.mean(lens.surfaces.opd[-1, :])
+        loss.backward()
+        g1, mat = lens.surfaces.surfaces[1].geometry, lens.surfaces.surfaces[1].material_post
+        out = {"loss": float(loss.detach()), "radius1": float(g1.radius.grad), "conic1": float(g1.k.grad),
+               "z2": float(lens.surfaces.surfaces[2].geometry.cs.z.grad), "index": float(mat.model.index.grad),
+               "abbe": float(mat.model.abbe.grad)}
+        return out, be.to_numpy(rays.x), be.to_numpy(lens.surfaces.y)
+
+    be.grad_mode.enable()
+    try:
+        P.stats(reset=True)
+        n0 = len(eng.calls)
+        got, gx, gy = run(make())
+        grads = [c for c in eng.calls[n0:] if c[0] == "grad"]
+        assert len(grads) == 3 and sum(c[2] for c in grads) == n, (grads, P.stats())
+        assert not P.stats(), P.stats()
+        P.uninstall()                       # the reference's own eager graph
+        ref, rx, ry = run(make())
+    finally:
+        be.grad_mode.disable()
+    assert np.allclose(gx, rx, rtol=0, atol=1e-10) and np.allclose(gy, ry, rtol=0, atol=1e-10, equal_nan=True)
+    assert got["loss"] == pytest.approx(ref["loss"], rel=1e-10)
+    for k in ref:
+        assert got[k] == pytest.approx(ref[k], rel=5e-6), (k, got[k], ref[k])
+
+
 def test_surface_group_trace_capability_when_launch_fusion_is_off(plugin):
     """With the RealRayTracer.trace wrapper disabled the SurfaceGroup.trace wrapper carries the call
     (launch rays from the reference's own RayGenerator)."""
