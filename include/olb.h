@@ -602,6 +602,34 @@ int olb_huygens_psf_f64(const double* image_x, const double* image_y, const doub
                         int32_t n_pupil, double wavelength_mm, double Rp, double* psf, double* field,
                         void* stream);
 
+/*
+ * FFT-PSF gridding (reference: ScalarFFTPSF._generate_pupils, _pad_pupils, _compute_psf,
+ * optiland/psf/fft.py:123-227) -- the element-wise passes on either side of the library FFT, one kernel each.
+ *
+ * olb_fft_pupil_*: the zero-PADDED complex pupil function of one wavelength, grid_size x grid_size (row-major, re/im
+ * interleaved: torch.complex128 / complex64), written in one pass:
+ *     P[pad + pr, pad + pc] = sqrt(intensity[k]) * exp(-i 2 pi opd_waves[k]),  k = cell_ray[pr * num_rays + pc] >= 0
+ *     0 elsewhere;  pad = (grid_size - num_rays) / 2  (be.pad's pad_before, fft.py:216-225)
+ * `cell_ray` (num_rays^2 DEVICE int32): index of the wavefront sample of each cell of the num_rays x num_rays pupil
+ * grid, -1 outside the unit disk (the reference's masked assignment `P[R2 <= 1] = ...`, fft.py:141-157, in gather
+ * form; the k-th in-disk cell in row-major order holds sample k).  opd_waves / intensity: n_samples DEVICE values
+ * (WavefrontData.opd in waves, .intensity).  NaN / negative intensity propagate as in the reference.
+ *
+ * olb_fft_psf_accumulate_*: `amp` = fft2 of that array (the caller's library FFT); folds |amp|^2, the fftshift
+ * (out[(i + n/2) % n] = in[i] on both axes) and the sum over wavelengths into one pass:
+ *     psf[shift(r), shift(c)] = (first ? 0 : psf[...]) + |amp[r, c]|^2,  then  / div * mul  when `last`
+ * (the reference's `sum(...) / norm_factor * 100`, fft.py:184-191).  psf: grid_size^2 DEVICE reals.
+ * All asynchronous on `stream`; pupil / amp must be aligned to one complex element.
+ */
+int olb_fft_pupil_f64(const double* opd_waves, const double* intensity, int64_t n_samples, const int32_t* cell_ray,
+                      int32_t num_rays, int32_t grid_size, double* pupil, void* stream);
+int olb_fft_pupil_f32(const float* opd_waves, const float* intensity, int64_t n_samples, const int32_t* cell_ray,
+                      int32_t num_rays, int32_t grid_size, float* pupil, void* stream);
+int olb_fft_psf_accumulate_f64(const double* amp, int32_t grid_size, int32_t first, int32_t last, double div, double mul,
+                               double* psf, void* stream);
+int olb_fft_psf_accumulate_f32(const float* amp, int32_t grid_size, int32_t first, int32_t last, double div, double mul,
+                               float* psf, void* stream);
+
 /* Number of kernel launches issued by this process through the library
  * (for bench.py's gpu_launches claim). */
 int64_t olb_launch_count(void);

@@ -146,6 +146,10 @@ SYMBOLS = {
     "olb_huygens_psf_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_double,
                                       C.c_void_p, C.c_void_p, C.c_void_p]),
+    "olb_fft_pupil_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "olb_fft_pupil_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "olb_fft_psf_accumulate_f64": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_void_p, C.c_void_p]),
+    "olb_fft_psf_accumulate_f32": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_void_p, C.c_void_p]),
     "olb_host_scratch_bytes": (C.c_int64, [C.c_int32, C.c_int64]),
     "olb_trace_host_f32": (C.c_int, [_P(OlbDeviceTable), C.c_int32, C.c_int32, _P(OlbRays), _P(OlbRays),
                                      _P(OlbRecords), C.c_int64, C.c_int64, C.c_void_p, C.c_int64,

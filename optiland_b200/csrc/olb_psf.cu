@@ -18,6 +18,7 @@
 #include <string>
 
 #include "../../include/olb.h"
+#include "olb_fftpsf.cuh"
 
 namespace olb {
 int fail_psf(int code, const char* msg);   // olb_trace.cu
@@ -127,4 +128,101 @@ extern "C" int olb_huygens_psf_f64(const double* image_x, const double* image_y,
   if (e != cudaSuccess) return fail_psf(OLB_ERR_CUDA, cudaGetErrorString(e));
   count_launch();
   return OLB_OK;
+}
+
+
+// =============================================================================================================
+// FFT-PSF gridding (second half; per-cell arithmetic and the reference citations: olb_fftpsf.cuh).
+// Both kernels are one streaming pass: HBM-bound, 16 B (fp64) / 8 B (fp32) per cell written (pupil) resp. read +
+// one real written (psf); grid-stride over the cells with 8 CTAs of 256 threads per SM.
+// =============================================================================================================
+namespace olb {
+
+template <typename T> struct Cplx;
+template <> struct Cplx<double> { using type = double2; };
+template <> struct Cplx<float> { using type = float2; };
+
+template <typename T>
+__global__ void __launch_bounds__(256) fft_pupil_kernel(const T* __restrict__ opd, const T* __restrict__ intensity,
+                                                        const int32_t* __restrict__ cell_ray, int32_t num_rays,
+                                                        int32_t grid_size, int32_t pad, typename Cplx<T>::type* __restrict__ pupil) {
+  const int64_t cells = (int64_t)grid_size * grid_size;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < cells; k += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t r = (int32_t)(k / grid_size), c = (int32_t)(k - (int64_t)r * grid_size);
+    T re, im;
+    fft_pupil_cell<T>(r, c, num_rays, pad, cell_ray, opd, intensity, re, im);
+    typename Cplx<T>::type v;
+    v.x = re; v.y = im;
+    pupil[k] = v;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) fft_psf_kernel(const typename Cplx<T>::type* __restrict__ amp, int32_t grid_size,
+                                                      int first, int last, T div, T mul, T* __restrict__ psf) {
+  const int64_t cells = (int64_t)grid_size * grid_size;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < cells; k += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t r = (int32_t)(k / grid_size), c = (int32_t)(k - (int64_t)r * grid_size);
+    const typename Cplx<T>::type a = amp[k];                      // coalesced read of the spectrum ...
+    const int64_t o = (int64_t)fftshift_index(r, grid_size) * grid_size + fftshift_index(c, grid_size);
+    psf[o] = fft_psf_cell<T>(first ? (T)0 : psf[o], a.x, a.y, first != 0, last != 0, div, mul);  // ... shifted (still row-contiguous) write
+  }
+}
+
+static unsigned stream_grid(int64_t cells) {
+  const int64_t want = (cells + 255) / 256;
+  const int64_t cap = 148 * 8;
+  return (unsigned)(want < cap ? (want < 1 ? 1 : want) : cap);
+}
+
+template <typename T>
+static int fft_pupil_impl(const T* opd, const T* intensity, int64_t n_samples, const int32_t* cell_ray, int32_t num_rays,
+                          int32_t grid_size, T* pupil, void* stream, const char* name) {
+  if (!opd || !intensity || !cell_ray || !pupil) return fail_psf(OLB_ERR_INVALID_ARG, (std::string(name) + ": NULL argument").c_str());
+  if (num_rays <= 0 || grid_size < num_rays || n_samples < 0 || n_samples > (int64_t)num_rays * num_rays)
+    return fail_psf(OLB_ERR_INVALID_ARG, (std::string(name) + ": need 0 < num_rays <= grid_size and n_samples <= num_rays^2").c_str());
+  if ((reinterpret_cast<uintptr_t>(pupil) % (2 * sizeof(T))) != 0)
+    return fail_psf(OLB_ERR_ALIGNMENT, (std::string(name) + ": pupil must be aligned to one complex element").c_str());
+  const int64_t cells = (int64_t)grid_size * grid_size;
+  fft_pupil_kernel<T><<<stream_grid(cells), 256, 0, (cudaStream_t)stream>>>(
+      opd, intensity, cell_ray, num_rays, grid_size, (grid_size - num_rays) / 2, reinterpret_cast<typename Cplx<T>::type*>(pupil));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail_psf(OLB_ERR_CUDA, cudaGetErrorString(e));
+  count_launch();
+  return OLB_OK;
+}
+
+template <typename T>
+static int fft_psf_impl(const T* amp, int32_t grid_size, int first, int last, double div, double mul, T* psf, void* stream,
+                        const char* name) {
+  if (!amp || !psf) return fail_psf(OLB_ERR_INVALID_ARG, (std::string(name) + ": NULL argument").c_str());
+  if (grid_size <= 0) return fail_psf(OLB_ERR_INVALID_ARG, (std::string(name) + ": grid_size must be positive").c_str());
+  if ((reinterpret_cast<uintptr_t>(amp) % (2 * sizeof(T))) != 0)
+    return fail_psf(OLB_ERR_ALIGNMENT, (std::string(name) + ": amp must be aligned to one complex element").c_str());
+  const int64_t cells = (int64_t)grid_size * grid_size;
+  fft_psf_kernel<T><<<stream_grid(cells), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const typename Cplx<T>::type*>(amp), grid_size, first, last, (T)div, (T)mul, psf);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail_psf(OLB_ERR_CUDA, cudaGetErrorString(e));
+  count_launch();
+  return OLB_OK;
+}
+
+}  // namespace olb
+
+extern "C" int olb_fft_pupil_f64(const double* opd_waves, const double* intensity, int64_t n_samples, const int32_t* cell_ray,
+                                 int32_t num_rays, int32_t grid_size, double* pupil, void* stream) {
+  return olb::fft_pupil_impl<double>(opd_waves, intensity, n_samples, cell_ray, num_rays, grid_size, pupil, stream, "olb_fft_pupil_f64");
+}
+extern "C" int olb_fft_pupil_f32(const float* opd_waves, const float* intensity, int64_t n_samples, const int32_t* cell_ray,
+                                 int32_t num_rays, int32_t grid_size, float* pupil, void* stream) {
+  return olb::fft_pupil_impl<float>(opd_waves, intensity, n_samples, cell_ray, num_rays, grid_size, pupil, stream, "olb_fft_pupil_f32");
+}
+extern "C" int olb_fft_psf_accumulate_f64(const double* amp, int32_t grid_size, int32_t first, int32_t last, double div,
+                                          double mul, double* psf, void* stream) {
+  return olb::fft_psf_impl<double>(amp, grid_size, first, last, div, mul, psf, stream, "olb_fft_psf_accumulate_f64");
+}
+extern "C" int olb_fft_psf_accumulate_f32(const float* amp, int32_t grid_size, int32_t first, int32_t last, double div,
+                                          double mul, float* psf, void* stream) {
+  return olb::fft_psf_impl<float>(amp, grid_size, first, last, div, mul, psf, stream, "olb_fft_psf_accumulate_f32");
 }

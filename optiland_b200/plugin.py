@@ -216,6 +216,22 @@ class CudaEngine:
         return huygens_fresnel_psf(image_x, image_y, image_z, pupil_x, pupil_y, pupil_z, pupil_amp, pupil_opd,
                                    wavelength, Rp).to(image_x.dtype)
 
+    def fft_pupil(self, opd_waves, intensity, cell_ray, num_rays: int, grid_size: int):
+        """Padded complex pupil function of one wavelength in one pass (olb_fft_pupil_*); None to decline."""
+        from .psf import fft_pupil
+
+        if not (self.accepts_tensor(opd_waves) and self.accepts_tensor(intensity)):
+            return None
+        self._note("fft_pupil", int(num_rays), int(grid_size))
+        return fft_pupil(opd_waves, intensity, cell_ray, num_rays, grid_size)
+
+    def fft_psf_accumulate(self, amp, psf, first: bool, last: bool, div: float, mul: float):
+        """|spectrum|^2 + fftshift + sum over wavelengths + normalisation in one pass (olb_fft_psf_accumulate_*)."""
+        from .psf import fft_psf_accumulate
+
+        self._note("fft_psf", int(amp.shape[-1]))
+        return fft_psf_accumulate(amp, psf, first, last, div, mul)
+
     def trace_grad(self, table: T.SurfaceTable, params, rays, coefs=None):
         """Differentiable trace of Optiland's ``rays``: records are autograd outputs of ``params`` and of
         the ray tensors.  None if the table is outside olb_trace_bwd_*'s scope."""
@@ -1043,6 +1059,11 @@ def install(engine=None, alias: str | None = None) -> None:
 
     saved_spot = _spot.install(sys.modules[__name__], registry, be)
 
+    # f-3 (second half): the FFT-PSF's gridding passes on either side of the library FFT (psf/fft.py:123-227)
+    from . import fftpsf as _fftpsf
+
+    saved_fft = _fftpsf.install(sys.modules[__name__], registry, be)
+
     TorchSummation.grad_wanted = _grad_wanted
     TorchSummation.compute = hf_compute
     SurfaceGroup.trace = group_trace
@@ -1051,7 +1072,7 @@ def install(engine=None, alias: str | None = None) -> None:
     RealRayTracer.trace_generic = tracer_generic
     _state.update(installed=True, orig_group_trace=orig_group_trace, orig_surface_trace=orig_surface_trace,
                   orig_tracer_trace=orig_tracer_trace, orig_tracer_generic=orig_tracer_generic, orig_hf_compute=orig_hf_compute, orig_chief_compute=orig_chief_compute,
-                  old_backend=old, alias=alias, fuse_launch=True, fuse_wavefront=True, fuse_spot=True, saved_spot=saved_spot,
+                  old_backend=old, alias=alias, fuse_launch=True, fuse_wavefront=True, fuse_spot=True, fuse_fft_psf=True, saved_spot=saved_spot, saved_fft=saved_fft,
                   orig_position=orig_position, fast_positions=True)
 
 
@@ -1079,6 +1100,10 @@ def uninstall() -> None:
         from . import spot as _spot
 
         _spot.uninstall(_state["saved_spot"])
+    if _state.get("saved_fft") is not None:
+        from . import fftpsf as _fftpsf
+
+        _fftpsf.uninstall(_state["saved_fft"])
     if _state.get("orig_position") is not None:
         from optiland.coordinate_system import CoordinateSystem
 

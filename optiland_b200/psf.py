@@ -45,3 +45,48 @@ def huygens_fresnel_psf(image_x, image_y, image_z, pupil_x, pupil_y, pupil_z, pu
     if return_field:
         return psf, torch.view_as_complex(field.reshape(n_img, 2)).reshape(shape)
     return psf
+
+
+# ---- FFT-PSF gridding (second half): the element-wise passes on either side of the library FFT ----------
+_SFX = {torch.float64: "f64", torch.float32: "f32"}
+_CPLX = {torch.float64: torch.complex128, torch.float32: torch.complex64}
+
+
+def fft_pupil(opd_waves, intensity, cell_ray, num_rays: int, grid_size: int):
+    """The zero-PADDED complex pupil function of one wavelength, (grid_size, grid_size) complex, in ONE pass
+    (``olb_fft_pupil_*``): what ``ScalarFFTPSF._generate_pupils`` + ``_pad_pupils`` build with a masked assignment,
+    a reshape and ``be.pad`` (/root/reference/optiland/psf/fft.py:123-227).  ``opd_waves`` / ``intensity``: the
+    WavefrontData arrays (CUDA, fp32 or fp64); ``cell_ray``: int32 (num_rays^2) sample index per pupil-grid cell, -1
+    outside the unit disk."""
+    dtype = opd_waves.dtype
+    if dtype not in _SFX or not opd_waves.is_cuda:
+        raise _lib.OlbError("fft_pupil: CUDA fp32 / fp64 arrays expected; there is no CPU fallback")
+    lib = _lib.load()
+    opd = opd_waves.detach().contiguous()
+    inten = intensity.detach().to(dtype).contiguous()
+    cell = cell_ray.contiguous()
+    out = torch.empty((grid_size, grid_size), dtype=_CPLX[dtype], device=opd.device)
+    with torch.cuda.device(opd.device):
+        stream = torch.cuda.current_stream(opd.device).cuda_stream
+        rc = getattr(lib, f"olb_fft_pupil_{_SFX[dtype]}")(opd.data_ptr(), inten.data_ptr(), opd.numel(), cell.data_ptr(),
+                                                          int(num_rays), int(grid_size), out.data_ptr(), C.c_void_p(stream))
+    _lib.check(rc, "olb_fft_pupil")
+    return out
+
+
+def fft_psf_accumulate(amp, psf, first: bool, last: bool, div: float = 1.0, mul: float = 1.0):
+    """``psf[fftshift] (+)= |amp|^2`` (and ``/ div * mul`` on the last wavelength) in one pass over the spectrum
+    (``olb_fft_psf_accumulate_*``; fft.py:184-191).  ``amp``: (g, g) complex CUDA tensor, ``psf``: (g, g) real, updated
+    in place and returned."""
+    rdt = psf.dtype
+    if rdt not in _SFX or not amp.is_cuda or amp.dtype != _CPLX[rdt]:
+        raise _lib.OlbError("fft_psf_accumulate: CUDA complex64 / complex128 spectrum with a matching real psf expected")
+    lib = _lib.load()
+    amp = amp.contiguous()
+    g = amp.shape[-1]
+    with torch.cuda.device(amp.device):
+        stream = torch.cuda.current_stream(amp.device).cuda_stream
+        rc = getattr(lib, f"olb_fft_psf_accumulate_{_SFX[rdt]}")(amp.data_ptr(), int(g), int(bool(first)), int(bool(last)),
+                                                                 float(div), float(mul), psf.data_ptr(), C.c_void_p(stream))
+    _lib.check(rc, "olb_fft_psf_accumulate")
+    return psf

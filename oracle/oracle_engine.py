@@ -126,6 +126,43 @@ class OracleEngine:
                                        amp, pupil_opd.detach().double().numpy(), wavelength, Rp)
         return torch.from_numpy(psf).to(image_x.dtype)
 
+    def fft_pupil(self, opd_waves, intensity, cell_ray, num_rays, grid_size):
+        """TEST-ONLY: the gridding kernel's per-cell function (csrc/olb_fftpsf.cuh) looped on the CPU (tests/hostcheck)."""
+        import ctypes as C
+
+        import torch
+
+        from oracle.hostcheck_api import load
+
+        hc = load()
+        self.calls.append(("fft_pupil", int(num_rays), int(grid_size)))
+        f64 = opd_waves.dtype == torch.float64
+        npdt = np.float64 if f64 else np.float32
+        opd = np.ascontiguousarray(opd_waves.detach().cpu().numpy().astype(npdt))
+        inten = np.ascontiguousarray(intensity.detach().cpu().numpy().astype(npdt))
+        cell = np.ascontiguousarray(cell_ray.detach().cpu().numpy().astype(np.int32))
+        out = np.empty((grid_size, grid_size, 2), dtype=npdt)
+        fn = hc.olbhc_fft_pupil_f64 if f64 else hc.olbhc_fft_pupil_f32
+        fn(C.c_void_p(opd.ctypes.data), C.c_void_p(inten.ctypes.data), C.c_void_p(cell.ctypes.data), C.c_int32(num_rays),
+           C.c_int32(grid_size), C.c_void_p(out.ctypes.data))
+        return torch.view_as_complex(torch.from_numpy(out))
+
+    def fft_psf_accumulate(self, amp, psf, first, last, div, mul):
+        import ctypes as C
+
+        import torch
+
+        from oracle.hostcheck_api import load
+
+        hc = load()
+        self.calls.append(("fft_psf", int(amp.shape[-1])))
+        a = np.ascontiguousarray(torch.view_as_real(amp.detach().to(torch.complex128).contiguous()).numpy())
+        acc = np.ascontiguousarray(psf.detach().double().numpy())
+        hc.olbhc_fft_psf_accumulate_f64(C.c_void_p(a.ctypes.data), C.c_int32(amp.shape[-1]), C.c_int32(int(first)),
+                                        C.c_int32(int(last)), C.c_double(div), C.c_double(mul), C.c_void_p(acc.ctypes.data))
+        psf.copy_(torch.from_numpy(acc).to(psf.dtype))
+        return psf
+
     def trace_grad(self, table, params, rays, coefs=None):
         """TEST-ONLY differentiable engine: oracle forward + the CPU instantiation of the device adjoint
         (tests/hostcheck) -- the arithmetic of olb_trace_bwd_* without a GPU."""

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../optiland_b200/csrc/olb_math.cuh"
+#include "../../optiland_b200/csrc/olb_fftpsf.cuh"
 
 using namespace olb;
 
@@ -221,5 +222,41 @@ int olbhc_single_blob(const OlbTable* tab, int which, unsigned char* out, int ou
 int olbhc_features(const OlbTable* tab) {
   PrepResult pr = prepare_table(*tab);
   return pr.error.empty() ? (int)pr.features : -1;
+}
+
+// FFT-PSF gridding (olb_fftpsf.cuh): the kernels' per-cell functions looped over the grid on the CPU
+int olbhc_fft_pupil_f64(const double* opd, const double* inten, const int32_t* cell_ray, int32_t num_rays, int32_t grid,
+                        double* pupil /* grid*grid*2 */) {
+  const int32_t pad = (grid - num_rays) / 2;
+  for (int32_t r = 0; r < grid; ++r)
+    for (int32_t c = 0; c < grid; ++c) {
+      double re, im;
+      fft_pupil_cell<double>(r, c, num_rays, pad, cell_ray, opd, inten, re, im);
+      pupil[2 * ((int64_t)r * grid + c)] = re;
+      pupil[2 * ((int64_t)r * grid + c) + 1] = im;
+    }
+  return OLB_OK;
+}
+int olbhc_fft_pupil_f32(const float* opd, const float* inten, const int32_t* cell_ray, int32_t num_rays, int32_t grid,
+                        float* pupil) {
+  const int32_t pad = (grid - num_rays) / 2;
+  for (int32_t r = 0; r < grid; ++r)
+    for (int32_t c = 0; c < grid; ++c) {
+      float re, im;
+      fft_pupil_cell<float>(r, c, num_rays, pad, cell_ray, opd, inten, re, im);
+      pupil[2 * ((int64_t)r * grid + c)] = re;
+      pupil[2 * ((int64_t)r * grid + c) + 1] = im;
+    }
+  return OLB_OK;
+}
+int olbhc_fft_psf_accumulate_f64(const double* amp, int32_t grid, int32_t first, int32_t last, double div, double mul,
+                                 double* psf) {
+  for (int32_t r = 0; r < grid; ++r)
+    for (int32_t c = 0; c < grid; ++c) {
+      const int64_t k = (int64_t)r * grid + c;
+      const int64_t o = (int64_t)fftshift_index(r, grid) * grid + fftshift_index(c, grid);
+      psf[o] = fft_psf_cell<double>(first ? 0.0 : psf[o], amp[2 * k], amp[2 * k + 1], first != 0, last != 0, div, mul);
+    }
+  return OLB_OK;
 }
 }

@@ -338,8 +338,8 @@ def test_autograd_ray_input_gradients_and_unsupported_tables():
     fd = (img_y(h) - img_y(-h)) / (2 * h)
     ok = torch.isfinite(fd) & m
     assert float((gy[ok] - fd[ok]).abs().max()) < 1e-6 * float(fd[ok].abs().max() + 1)
-    # Chebyshev / biconic / toroidal surfaces are outside the backward kernel's scope: loud error, no
-    # silent wrong gradient  (Zernike / polynomial surfaces ARE covered: test_polynomial_family_adjoint_kernel)
+    # biconic / toroidal surfaces are outside the backward kernel's scope: loud error, no silent wrong
+    # gradient  (Zernike / polynomial / Chebyshev surfaces ARE covered: test_polynomial_family_adjoint_kernel)
     t = Case("cheb_biconic_toroidal")
     rr = RealRays(*[t.rays[k] for k in ("x", "y", "z", "L", "M", "N", "i", "w")], dtype=torch.float64)
     with pytest.raises(_lib.OlbError, match="not supported"):
@@ -388,9 +388,9 @@ def test_autograd_ray_input_gradients_and_unsupported_tables():
         assert ang.grad[q].item() == pytest.approx(fd, rel=2e-5, abs=1e-8), q
 
 
-@pytest.mark.parametrize("name", ["zernike_fringe", "zernike_standard", "misc_apertures_coatings"])
+@pytest.mark.parametrize("name", ["zernike_fringe", "zernike_standard", "misc_apertures_coatings", "chebyshev"])
 def test_polynomial_family_adjoint_kernel(name):
-    """olb_trace_bwd_tables_* on the GPU (Zernike / polynomial surfaces): gradients of a random linear functional of all
+    """olb_trace_bwd_tables_* on the GPU (Zernike / polynomial / Chebyshev surfaces): gradients of a random linear functional of all
     records w.r.t. the launch state, the surface parameters and the USER coefficients (table gradients mapped back)
     against the CPU instantiation of the same adjoint, which tests/test_hostcheck_backward.py holds to finite differences
     of the oracle; fp32 against fp64."""
@@ -401,7 +401,13 @@ def test_polynomial_family_adjoint_kernel(name):
     from optiland_b200 import autograd as AG
     from optiland_b200.trace import RealRays
 
-    c = Case(name)
+    if name == "chebyshev":
+        from tests.test_hostcheck_backward import chebyshev_table
+
+        c, cheb = chebyshev_table()
+        c.table = cheb
+    else:
+        c = Case(name)
     if not any(s.kind in AG.POLY_KINDS for s in c.table.surfaces):
         pytest.skip("no polynomial-family surface")
     rng = np.random.default_rng(4)

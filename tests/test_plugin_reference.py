@@ -802,21 +802,46 @@ def test_huygens_psf_strategy_is_routed_through_the_engine(plugin):
 
 
 def test_fft_psf_takes_its_pupil_function_from_the_fused_wavefront_epilogue(plugin):
-    """FFTPSF (psf/fft.py:123-200): its pupil function A exp(-2 pi i OPD) on the uniform pupil grid comes from
-    ``Wavefront.get_data`` -- under the plugin ONE fused launch (launch generation + trace + OPD against the reference
-    sphere + intensity, 5 values per grid point); the gridding itself is five element-wise ops on the num_rays^2 grid in
-    front of the library FFT and stays the reference's.  Same PSF as the NumPy reference."""
+    """FFTPSF (psf/fft.py:123-227): its wavefront data comes from ``Wavefront.get_data`` -- under the plugin ONE fused
+    launch (launch generation + trace + OPD against the reference sphere + intensity) -- and the gridding passes on
+    either side of the library FFT are one kernel each: ``olb_fft_pupil_*`` writes the zero-padded pupil function
+    A exp(-2 pi i OPD) (masked scatter + reshape + pad), ``olb_fft_psf_accumulate_*`` reads the spectrum once (|.|^2,
+    fftshift, sum over wavelengths, normalisation).  Same PSF as the NumPy reference; ``self.pupils`` keeps its
+    meaning (num_rays x num_rays complex arrays) and equals the reference's."""
     P, eng, be = plugin
     from optiland.psf import FFTPSF
     from optiland.samples.objectives import CookeTriplet
 
-    be.set_backend("numpy")
-    ref = np.array(FFTPSF(CookeTriplet(), field=(0, 0.7), wavelength=0.55, num_rays=64, grid_size=128).psf)
-    be.set_backend("torch")
-    n0 = len(eng.calls)
-    got = FFTPSF(CookeTriplet(), field=(0, 0.7), wavelength=0.55, num_rays=64, grid_size=128).psf
-    assert any(c[0] == "wavefront" for c in eng.calls[n0:]), eng.calls[n0:]
-    np.testing.assert_allclose(be.to_numpy(got), ref, rtol=0, atol=2e-6 * ref.max())
+    for kw in (dict(field=(0, 0.7), wavelength=0.55, num_rays=64, grid_size=128),
+               dict(field=(0, 1.0), wavelength=0.48, num_rays=33, grid_size=77)):       # odd sizes (pad 22 / 22, shift 38)
+        be.set_backend("numpy")
+        r = FFTPSF(CookeTriplet(), **kw)
+        ref, ref_pupils = np.array(r.psf), [np.array(p) for p in r.pupils]
+        be.set_backend("torch")
+        n0 = len(eng.calls)
+        P.stats(reset=True)
+        psf = FFTPSF(CookeTriplet(), **kw)
+        kinds = [c[0] for c in eng.calls[n0:]]
+        assert "wavefront" in kinds and kinds.count("fft_pupil") == len(ref_pupils) == kinds.count("fft_psf"), kinds
+        np.testing.assert_allclose(be.to_numpy(psf.psf), ref, rtol=0, atol=2e-6 * ref.max())
+        assert len(psf.pupils) == len(ref_pupils)
+        for got_p, ref_p in zip(psf.pupils, ref_pupils):
+            assert tuple(got_p.shape) == ref_p.shape
+            np.testing.assert_allclose(be.to_numpy(got_p), ref_p, rtol=0, atol=1e-6)
+        assert float(psf._get_normalization()) == float(np.sum(np.abs(ref_pupils[0]) > 0) ** 2)
+        # a caller that REPLACES the pupils gets the reference's own code on them (no stale padded buffers)
+        psf.pupils = [p * 0.5 for p in psf.pupils]
+        n1 = len(eng.calls)
+        np.testing.assert_allclose(be.to_numpy(psf._compute_psf()), 0.25 * ref, rtol=0, atol=2e-6 * ref.max())
+        assert not [c for c in eng.calls[n1:] if c[0] == "fft_psf"]
+    # gradients wanted: the reference's eager ops
+    be.grad_mode.enable()
+    try:
+        n2 = len(eng.calls)
+        FFTPSF(CookeTriplet(), field=(0, 0.0), wavelength=0.55, num_rays=32, grid_size=64)
+        assert not [c for c in eng.calls[n2:] if c[0] in ("fft_pupil", "fft_psf")]
+    finally:
+        be.grad_mode.disable()
 
 
 def test_launch_form_reproduces_the_reference_ray_generator_known_answers():
