@@ -50,11 +50,12 @@ def test_reference_tests_unchanged_with_plugin(fname):
 
 
 @pytest.mark.timeout(900)
-@pytest.mark.parametrize("fname", ["analysis/test_spot_reference.py", "test_wavefront.py", "test_operand.py"])
+@pytest.mark.parametrize("fname", ["analysis/test_spot_reference.py", "test_wavefront.py", "test_operand.py", "test_fft_psf.py"])
 def test_reference_tests_unchanged_with_plugin_grad_mode_off(fname):
     """Same with be.grad_mode left off (the reference's conftest normally turns it on): now the plain trace
     and the fused in-kernel launch generation (RealRayTracer.trace wrapper) carry the calls; for
-    test_wavefront.py the reference's OPD goldens are then computed by the fused wavefront epilogue."""
+    test_wavefront.py the reference's OPD goldens are then computed by the fused wavefront epilogue, for test_fft_psf.py
+    the PSFs by the wavefront epilogue + the two FFT-PSF gridding kernels (optiland_b200/fftpsf.py)."""
     stock, _ = _run(fname, install=False, nograd=True)
     ours, calls = _run(fname, install=True, nograd=True)
     assert stock.get("passed", 0) > 0 and ours == stock, (fname, stock, ours)
@@ -62,7 +63,8 @@ def test_reference_tests_unchanged_with_plugin_grad_mode_off(fname):
 
 
 GPU_FILES = ["test_surface_group.py", "test_wavefront.py", "analysis/test_spot_reference.py", "test_analysis.py",
-             "test_operand.py", "test_torch_optimization.py", "test_tolerancing.py", "optimization/test_batched_evaluator.py"]
+             "test_operand.py", "test_torch_optimization.py", "test_tolerancing.py", "optimization/test_batched_evaluator.py",
+             "test_fft_psf.py"]
 
 
 # Reference tests whose pinned number is the reference's own rounding noise, which the kernel does not reproduce:
