@@ -260,7 +260,7 @@ typedef struct OlbDeviceTable {
   int32_t off_f64, bytes_f64;   /* fp64 blob inside workspace */
   int32_t off_f32, bytes_f32;   /* fp32 blob inside workspace */
   int32_t bwd_supported;        /* 1 if olb_trace_bwd_* covers every surface of the table; 2: covered, and the table has
-                                   polynomial / Zernike surfaces whose gradients need olb_trace_bwd_tables_*       */
+                                   polynomial / Zernike / Chebyshev surfaces whose gradients need olb_trace_bwd_tables_* */
   int32_t bwd_slots;            /* gradient accumulator slots per thread (backward kernel)   */
   int32_t n_systems;            /* 1, or the number of systems of a batched table            */
   int32_t stride_f64;           /* bytes between consecutive systems' fp64 / fp32 blobs      */
@@ -432,7 +432,9 @@ int olb_trace_host_pupil_f64(const OlbDeviceTable* table, int32_t first, int32_t
  * (that quantity has zero gradient); grad_rays_in (x,y,z,L,M,N,i,opd) may be NULL.
  * Supported tables (OlbDeviceTable.bwd_supported): plane / standard / even- and odd-asphere geometry, any
  * pose (translation gradients, and for tilted poses dLoss/dR for the caller to chain to the tilt angles), any
- * aperture tree, no or simple coating, one wavelength; otherwise OLB_ERR_UNSUPPORTED.  Rays that are NaN at a surface carry no gradient.
+ * aperture tree, no or simple coating, one wavelength per call (a batch that mixes wavelengths is split by the caller:
+ * one table, one forward and one adjoint launch per wavelength, optiland_b200.plugin._trace_grad_per_wavelength);
+ * otherwise OLB_ERR_UNSUPPORTED.  Rays that are NaN at a surface carry no gradient.
  * grad_row_mask: bit r set = record row r of grad_rec may be non-zero (rows with a clear bit
  * are not read); pass ~0 when unknown.
  */
@@ -458,7 +460,7 @@ int olb_trace_bwd_f64(const OlbDeviceTable* table, int32_t first, int32_t last,
 
 /*
  * The same with TABLE gradients for the polynomial families (OlbDeviceTable.bwd_supported == 2: the table holds
- * OLB_GEOM_POLYNOMIAL / OLB_GEOM_ZERNIKE surfaces of at most 12 x 12 monomials).  The adjoint goes through the
+ * OLB_GEOM_POLYNOMIAL / OLB_GEOM_ZERNIKE / OLB_GEOM_CHEBYSHEV surfaces of at most 12 x 12 monomials).  The adjoint goes through the
  * intersection by the implicit-function theorem with the TRUE gradient of the sag polynomial and through the normal with
  * the Hessian of the reference's slope polynomial (whose Zernike form omits the normalisation constants,
  * optiland/zernike/base.py:104-136).  grad_tables: n_surfaces blocks of OLB_GT_PER_SURFACE doubles, ACCUMULATED --
@@ -466,7 +468,10 @@ int olb_trace_bwd_f64(const OlbDeviceTable* table, int32_t first, int32_t last,
  *   [144 .. 287] dLoss/dD_ij, D = the prepared slope table
  * in which the user's coefficients are linear: polynomial C_ij = S_ij = D_ij; Zernike S = sum_k c_k N_k M_k,
  * D = sum_k c_k M_k with M_k the monomial expansion of the unit term (optiland_b200.table.zernike_monomials), so
- * dLoss/dc_k = N_k <M_k, dLoss/dS> + <M_k, dLoss/dD>.  (Zernike variables: optiland/geometries/zernike.py:182-252.)
+ * dLoss/dc_k = N_k <M_k, dLoss/dS> + <M_k, dLoss/dD>  (Zernike variables: optiland/geometries/zernike.py:182-252);
+ * Chebyshev: ONE table S = D = P with P_pq = sum_ij C_ij Tc[i][p] Tc[j][q] (Tc: monomial coefficients of T_n), its slope
+ * entering the normal WITHOUT the factors 1 / norm_x, 1 / norm_y (the reference's form, chebyshev.py:171-181), so
+ * dLoss/dC_ij = sum_pq Tc[i][p] (dLoss/dS + dLoss/dD)_pq Tc[j][q].
  */
 #define OLB_GT_DIM 12
 #define OLB_GT_PER_SURFACE (2 * OLB_GT_DIM * OLB_GT_DIM)

@@ -255,7 +255,7 @@ class _TraceFn(torch.autograd.Function):
             device_tables.append(dtab)
         if not dtab.c.bwd_supported:
             raise _lib.OlbError("differentiable trace: table not supported by olb_trace_bwd_* (a geometry other than plane / "
-                                "standard / even- and odd-asphere / polynomial / Zernike, a Fresnel coating, several wavelengths)")
+                                "standard / even- and odd-asphere / polynomial / Zernike / Chebyshev, a Fresnel coating, several wavelengths in one table)")
         n = x.numel()
         S = table.num_surfaces
         # (a slice / view of a larger tensor may start anywhere: the C ABI wants 16-byte aligned arrays)
@@ -324,7 +324,7 @@ class _TraceFn(torch.autograd.Function):
         with torch.cuda.device(buf.device):
             stream = torch.cuda.current_stream(buf.device).cuda_stream
             if tables:
-                # polynomial / Zernike surfaces: table gradients as well (olb_trace_bwd_tables_*)
+                # polynomial / Zernike / Chebyshev surfaces: table gradients as well (olb_trace_bwd_tables_*)
                 rc = getattr(lib, f"olb_trace_bwd_tables_{ctx.sfx}")(
                     C.byref(dtab.c), 0, S, C.byref(c_in), C.byref(c_rec), C.byref(c_grec),
                     C.byref(c_gin) if c_gin is not None else None, C.c_void_p(gpar.data_ptr()),
@@ -347,7 +347,7 @@ class _TraceFn(torch.autograd.Function):
 
 def trace_differentiable(template: T.SurfaceTable, params: torch.Tensor, rays, rows=None, coefs: torch.Tensor | None = None):
     """Trace ``rays`` (an ``optiland_b200.trace.RealRays``) through ``template`` with parameter VALUES
-    taken from ``params`` (and ``coefs``: the user coefficients of polynomial / Zernike surfaces, ``table_to_coefs``).  Returns a dict of record tensors that are autograd outputs of ``params``
+    taken from ``params`` (and ``coefs``: the user coefficients of polynomial / Zernike / Chebyshev surfaces, ``table_to_coefs``).  Returns a dict of record tensors that are autograd outputs of ``params``
     (and of the ray tensors when they require grad): (S, N) arrays when ``rows`` is None, otherwise
     only the requested rows -- (N,) tensors for a single row, lists of (N,) tensors for several --
     which keeps the backward pass from touching gradients of rows the loss never reads."""
