@@ -1003,6 +1003,31 @@ def install(engine=None, alias: str | None = None) -> None:
                 return rays
         return orig_tracer_generic(self, Hx, Hy, Px, Py, wavelength)
 
+    # f-4: the iterative ray aimer re-traces ALL its rays from the first surface to the stop on every Broyden
+    # iteration, one ``Surface.trace`` call per surface (rays/ray_aiming/iterative.py:339-367): through the per-surface
+    # wrapper that is (stop + 1) packs, uploads and launches per iteration.  Here the whole subset is ONE table and ONE
+    # launch of the SurfaceGroup capability over [start, stop]; records land on the same Surface objects.
+    from optiland.rays.ray_aiming.iterative import IterativeRayAimer
+
+    orig_trace_subset = IterativeRayAimer._trace_subset
+
+    def aimer_trace_subset(self, x, y, z, L, M, N, wl, stop, is_inf):
+        backend = registry.get(be.get_backend())
+        if (hasattr(backend, "trace_surfaces") and _state.get("fuse_aimer", True)
+                and not getattr(_tls, "in_reference", False)):
+            from optiland.rays import RealRays as _RefRealRays
+
+            rays = _RefRealRays(x, y, z, L, M, N, intensity=be.ones_like(x), wavelength=wl)
+            start = 1 if is_inf else 0
+            group = self.optic.surfaces
+            for surf in list(group.surfaces)[start:stop + 1]:
+                surf.reset()                       # what every Surface.trace starts with (standard_surface.py:200-215)
+            if backend.trace_surfaces(group, rays, start, stop + 1):
+                return rays
+        return orig_trace_subset(self, x, y, z, L, M, N, wl, stop, is_inf)
+
+    IterativeRayAimer._trace_subset = aimer_trace_subset
+
     # f-3: the Huygens-Fresnel summation strategy of the torch backend (psf/huygens_fresnel_strategies.py:183-273)
     from optiland.psf.huygens_fresnel_strategies import TorchSummation
 
@@ -1072,7 +1097,7 @@ def install(engine=None, alias: str | None = None) -> None:
     RealRayTracer.trace_generic = tracer_generic
     _state.update(installed=True, orig_group_trace=orig_group_trace, orig_surface_trace=orig_surface_trace,
                   orig_tracer_trace=orig_tracer_trace, orig_tracer_generic=orig_tracer_generic, orig_hf_compute=orig_hf_compute, orig_chief_compute=orig_chief_compute,
-                  old_backend=old, alias=alias, fuse_launch=True, fuse_wavefront=True, fuse_spot=True, fuse_fft_psf=True, saved_spot=saved_spot, saved_fft=saved_fft,
+                  old_backend=old, alias=alias, fuse_launch=True, fuse_wavefront=True, fuse_spot=True, fuse_fft_psf=True, fuse_aimer=True, orig_trace_subset=orig_trace_subset, saved_spot=saved_spot, saved_fft=saved_fft,
                   orig_position=orig_position, fast_positions=True)
 
 
@@ -1100,6 +1125,10 @@ def uninstall() -> None:
         from . import spot as _spot
 
         _spot.uninstall(_state["saved_spot"])
+    if _state.get("orig_trace_subset") is not None:
+        from optiland.rays.ray_aiming.iterative import IterativeRayAimer
+
+        IterativeRayAimer._trace_subset = _state["orig_trace_subset"]
     if _state.get("saved_fft") is not None:
         from . import fftpsf as _fftpsf
 

@@ -311,7 +311,11 @@ def test_declines_and_falls_back_to_reference_python(plugin):
 
 
 def test_per_surface_entry_used_by_ray_aimers(plugin):
-    """Surface.trace (one surface) is what iterative ray aiming calls (ray_aiming/iterative.py:366)."""
+    """Iterative ray aiming (rays/ray_aiming/iterative.py): every Broyden iteration re-traces all rays from the first
+    surface to the stop with one ``Surface.trace`` call per surface (:339-367).  Under the plugin the subset is ONE
+    table and ONE launch (``IterativeRayAimer._trace_subset`` wrapper -> SurfaceGroup capability over [start, stop]);
+    with that fusion switched off the per-surface wrapper carries the calls (one-surface tables), as it does for the
+    stop-radius strategy (initialization.py:150).  Both equal the NumPy reference."""
     P, eng, be = plugin
     from optiland.samples.objectives import CookeTriplet
 
@@ -320,12 +324,22 @@ def test_per_surface_entry_used_by_ray_aimers(plugin):
         return lens.trace(0.0, 0.7, 0.55, 4, "hexapolar")
 
     ref_rec, ref_fin = _numpy_reference(CookeTriplet, trace)
-    n0 = len(eng.calls)
-    lens = CookeTriplet()
-    rays = trace(lens)
-    assert any(c[0] == 1 for c in eng.calls[n0:])  # single-surface tables were traced
-    np.testing.assert_allclose(be.to_numpy(rays.y), ref_fin["y"], atol=1e-9)
-    np.testing.assert_allclose(be.to_numpy(lens.surfaces.x), ref_rec["x"], atol=1e-9)
+    stop = CookeTriplet().surfaces.stop_index
+    for fused in (True, False):
+        P._state["fuse_aimer"] = fused
+        n0 = len(eng.calls)
+        lens = CookeTriplet()
+        rays = trace(lens)
+        sizes = [c[0] for c in eng.calls[n0:] if isinstance(c[0], int)]
+        if fused:
+            assert sizes.count(stop) >= 2, sizes            # surfaces 1 .. stop in one table, once per aimer iteration
+        else:
+            assert sizes.count(1) >= 2 * stop and stop not in sizes[:-1], sizes   # single-surface tables
+        np.testing.assert_allclose(be.to_numpy(rays.y), ref_fin["y"], atol=1e-9)
+        np.testing.assert_allclose(be.to_numpy(lens.surfaces.x), ref_rec["x"], atol=1e-9)
+    # the only thing handed down a level: the in-kernel launch generation covers paraxial aiming only, so the
+    # reference's aimer produced the launch rays (through the wrappers above) and SurfaceGroup.trace carried the trace
+    assert set(P.stats()) <= {"fused launch: non-paraxial ray aiming"}, P.stats()
 
 
 def test_multi_wavelength_and_zernike_error(plugin):
