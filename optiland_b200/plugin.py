@@ -106,12 +106,19 @@ class CudaEngine:
     def accepts(self, rays) -> bool:
         import torch
 
-        keys = ("x", "y", "z", "L", "M", "N", "i", "w", "opd")
+        keys = ("x", "y", "z", "L", "M", "N", "i", "opd")
         ts = [getattr(rays, k, None) for k in keys]
-        if any(not torch.is_tensor(t) for t in ts):
+        w = getattr(rays, "w", None)
+        if any(not torch.is_tensor(t) for t in ts) or not torch.is_tensor(w):
             return False
         t0 = ts[0]
         if not t0.is_cuda or t0.dtype not in (torch.float32, torch.float64) or t0.ndim != 1:
+            return False
+        # ``w`` may be ONE value for the whole batch: RealRays(..., wavelength=0.55) keeps a 1-element array that the
+        # reference's ops broadcast (real_rays.py:79; the iterative ray aimer builds its rays that way,
+        # ray_aiming/iterative.py:361)
+        if not (w.is_cuda and w.dtype == t0.dtype and w.device == t0.device and w.ndim == 1
+                and (w.shape == t0.shape or w.numel() == 1)):
             return False
         return all(t.is_cuda and t.dtype == t0.dtype and t.shape == t0.shape and t.device == t0.device for t in ts)
 
@@ -142,8 +149,12 @@ class CudaEngine:
             # always carries the complex form
             cdt = torch.complex64 if rays.x.dtype == torch.float32 else torch.complex128
             shell.p = rays.p.detach().to(cdt).contiguous()
+        n = rays.x.numel()
         for k in ("x", "y", "z", "L", "M", "N", "i", "w", "opd"):
-            t = getattr(rays, k).detach().contiguous()
+            t = getattr(rays, k).detach()
+            if k == "w" and t.numel() == 1 and n != 1:
+                t = t.expand(n)                    # one wavelength for the whole batch (accepts())
+            t = t.contiguous()
             if t.data_ptr() % 16:
                 t = t.clone()
             setattr(shell, k, t)
@@ -926,6 +937,12 @@ def install(engine=None, alias: str | None = None) -> None:
 
             ref = {"center": [f(c) for c in geometry.center], "radius": f(geometry.radius), "n_image": f(strategy.n_image),
                    "tilt": tilt, "opd_ref": f(opd_ref), "wavelength_um": float(wavelength)}
+            # a degenerate system (chief ray lost: NaN reference sphere, tests/test_fft_psf.py::test_invalid_working_FNO
+            # moves the object to z = -1e100) has no sphere to fuse against -- the C ABI rejects a non-positive / NaN
+            # radius: the reference's own ops carry the NaNs on
+            chk = ref["center"] + [ref["radius"], ref["n_image"], ref["opd_ref"], tilt[0], tilt[1]]
+            if not all(_np.isfinite(v) for v in chk) or not (ref["radius"] > 0 and ref["n_image"] > 0):
+                return _fused_decline("wavefront: chief-ray reference sphere not finite")
             aff = pupil_affine(sc)
             kwargs = {}
             if polarized:
