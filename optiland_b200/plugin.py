@@ -821,6 +821,18 @@ def install(engine=None, alias: str | None = None) -> None:
                     Px = Px * (1 - vxf) * (1 - vxf)
                     Py = Py * (1 - vyf) * (1 - vyf)
             Hx, Hy, Px, Py = tracer._validate_array_size(Hx, Hy, Px, Py)
+            # _validate_array_size expands Python numbers only; a 0-d / 1-element ARRAY among longer ones (np.float32
+            # field coordinates, be.array(0.7), ...) is left to the broadcasting of the reference's element-wise ops
+            # (ray_generator.py:47-99).  Same values here: sizes 1 and n are brought to (n,) before the launch.
+            try:
+                sizes = [int(be.size(t)) for t in (Hx, Hy, Px, Py)]
+                n_max = max(sizes)
+                if all(sz in (1, n_max) for sz in sizes) and any(getattr(t, "ndim", 1) != 1 or sz != n_max
+                                                                 for t, sz in zip((Hx, Hy, Px, Py), sizes)):
+                    Hx, Hy, Px, Py = (t.reshape(-1).expand(n_max) if sz == 1 and n_max > 1 else t.reshape(-1)
+                                      for t, sz in zip((Hx, Hy, Px, Py), sizes))
+            except Exception:
+                pass                                  # not tensors: the check below declines
             if not all(engine.accepts_tensor(t) for t in (Hx, Hy, Px, Py)) or len({t.shape for t in (Hx, Hy, Px, Py)}) != 1:
                 return _fused_decline("field / pupil arrays not resident on a CUDA device (or of different shapes)")
             if any(t.dtype != Px.dtype for t in (Hx, Hy)):

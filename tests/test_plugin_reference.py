@@ -171,6 +171,21 @@ def test_trace_generic_with_per_ray_fields_and_wavelengths(plugin):
     for k, v in ref_rec.items():
         np.testing.assert_allclose(be.to_numpy(getattr(lens.surfaces, k)), v, rtol=0, atol=1e-10, err_msg=k)
     assert float(np.max(np.abs(ref_rec["x"][1] - np.asarray(_numpy_reference(DoubleGauss, trace_v)[0]["x"][1])))) > 1e-3
+    # mixed shapes: Python floats, 0-d and 1-element arrays beside (n,) arrays -- the reference's element-wise ops
+    # broadcast them (real_ray_tracer.py:175-194 expands Python numbers only); the fused launch brings them to (n,)
+    def trace_mixed(lens):
+        return lens.trace_generic(0.0, be.array(0.7), be.array(Px), be.array([0.25]), 0.5876)
+
+    ref_rec, ref_fin = _numpy_reference(DoubleGauss, trace_mixed)
+    lens = DoubleGauss()
+    n0 = len(eng.calls)
+    P.stats(reset=True)
+    rays = trace_mixed(lens)
+    assert ("pupil", 13, n) in [c[:3] for c in eng.calls[n0:]] and not P.stats(), (eng.calls[n0:], P.stats())
+    for k, v in ref_rec.items():
+        np.testing.assert_allclose(be.to_numpy(getattr(lens.surfaces, k)), v, rtol=0, atol=1e-10, err_msg=k)
+    for k, v in ref_fin.items():
+        np.testing.assert_allclose(be.to_numpy(getattr(rays, k)), v, rtol=0, atol=1e-10, err_msg=k)
 
 
 def test_wavefront_analysis_uses_the_fused_epilogue(plugin):
