@@ -456,6 +456,31 @@ def _make_rays(be, rec, wl_arr, polarized: bool):
     return rays
 
 
+def _live_frame(cs, scalar, zero):
+    """Effective pose of a (possibly nested) coordinate system as torch values built from its LIVE tensors:
+    ``t`` (3,) and ``R`` (3, 3) or None for the identity -- ``get_effective_transform`` (coordinate_system.py:145-165)
+    with autograd connectivity.  An angle that is exactly 0 enters as a constant (the reference's localize / globalize
+    skip such rotations, ``if self.rz:`` coordinate_system.py:84-104, so it gets no gradient there either)."""
+    import torch
+
+    t = torch.stack([scalar(cs.x), scalar(cs.y), scalar(cs.z)])
+    ang = [scalar(v) if float(scalar(v).detach()) != 0.0 else zero for v in (cs.rx, cs.ry, cs.rz)]
+    R = None
+    if any(a is not zero for a in ang):
+        rx, ry, rz = ang
+        cx, sx, cy, sy, cz, sz = torch.cos(rx), torch.sin(rx), torch.cos(ry), torch.sin(ry), torch.cos(rz), torch.sin(rz)
+        R = torch.stack([cz * cy, cz * sy * sx - sz * cx, cz * sy * cx + sz * sx,
+                         sz * cy, sz * sy * sx + cz * cx, sz * sy * cx - cz * sx,
+                         -sy, cy * sx, cy * cx]).reshape(3, 3)
+    parent = getattr(cs, "reference_cs", None)
+    if parent is None:
+        return t, R
+    tp, Rp = _live_frame(parent, scalar, zero)
+    t_eff = tp + (Rp @ t if Rp is not None else t)
+    R_eff = Rp if R is None else (R if Rp is None else Rp @ R)
+    return t_eff, R_eff
+
+
 def _live_params(surfaces, table, wavelength):
     """(S, GP_COUNT) fp64 tensor of the differentiable parameters, built with torch ops FROM THE LIVE
     tensors of the Optiland objects (geometry.cs.x/y/z, geometry.radius, geometry.k,
@@ -487,15 +512,25 @@ def _live_params(surfaces, table, wavelength):
         if spec.kind != T.GEOM_NOOP:
             g = surf.geometry
             cs = g.cs
-            if cs.reference_cs is not None or spec.kind not in (T.GEOM_PLANE, T.GEOM_STANDARD, T.GEOM_EVEN_ASPHERE,
-                                                                T.GEOM_ODD_ASPHERE, T.GEOM_POLYNOMIAL, T.GEOM_ZERNIKE,
-                                                                T.GEOM_CHEBYSHEV):
+            if spec.kind not in (T.GEOM_PLANE, T.GEOM_STANDARD, T.GEOM_EVEN_ASPHERE, T.GEOM_ODD_ASPHERE,
+                                 T.GEOM_POLYNOMIAL, T.GEOM_ZERNIKE, T.GEOM_CHEBYSHEV):
                 return None
+            nested = cs.reference_cs is not None
+            if nested:
+                # a frame defined relative to another one (coordinate breaks of imported systems,
+                # fileio/zemax/reader/converter.py:120-190): the effective pose t = t_p + R_p t_c, R = R_p R_c
+                # (coordinate_system.py:145-165) composed from the LIVE tensors of every level
+                t_eff, R_eff = _live_frame(cs, lambda v: scalar(v, like), zero)
             # pose rotation: constants (identity for an untilted surface -- the reference skips zero rotations
             # altogether, `if self.rz:` coordinate_system.py:84-89, so zero angles get no gradient there either);
             # for a tilted pose R = Rz Ry Rx is formed from the LIVE angle tensors (coordinate_system.py:121-143)
             # so that the adjoint kernel's dLoss/dR reaches tilt variables
-            if spec.rotated:
+            if nested:
+                if spec.rotated and R_eff is not None:
+                    Rm = tuple(R_eff[q // 3, q % 3] for q in range(9))
+                else:
+                    Rm = (one, zero, zero, zero, one, zero, zero, zero, one)
+            elif spec.rotated:
                 # (an angle that is exactly 0 is skipped by the reference even on a tilted surface: constant)
                 rx, ry, rz = (scalar(v, like) if float(scalar(v, like).detach()) != 0.0 else zero for v in (cs.rx, cs.ry, cs.rz))
                 cx, sx, cy, sy, cz, sz = torch.cos(rx), torch.sin(rx), torch.cos(ry), torch.sin(ry), torch.cos(rz), torch.sin(rz)
@@ -506,7 +541,10 @@ def _live_params(surfaces, table, wavelength):
                 Rm = (one, zero, zero, zero, one, zero, zero, zero, one)
             for q in range(9):
                 vals[GP_R + q] = Rm[q]
-            vals[GP_TX], vals[GP_TX + 1], vals[GP_TX + 2] = scalar(cs.x, like), scalar(cs.y, like), scalar(cs.z, like)
+            if nested:
+                vals[GP_TX], vals[GP_TX + 1], vals[GP_TX + 2] = t_eff[0], t_eff[1], t_eff[2]
+            else:
+                vals[GP_TX], vals[GP_TX + 1], vals[GP_TX + 2] = scalar(cs.x, like), scalar(cs.y, like), scalar(cs.z, like)
             curved = spec.kind != T.GEOM_PLANE and np.isfinite(spec.radius)
             if spec.kind != T.GEOM_PLANE:
                 vals[GP_CONIC] = scalar(g.k, like)
@@ -577,6 +615,10 @@ def _wants_grad(backend, surfaces, rays=None) -> bool:
             continue
         cs = g.cs
         vals = [getattr(g, "radius", None), getattr(g, "k", None), cs.x, cs.y, cs.z, cs.rx, cs.ry, cs.rz]
+        parent = getattr(cs, "reference_cs", None)
+        while parent is not None:                    # nested frames: the pose depends on every level
+            vals += [parent.x, parent.y, parent.z, parent.rx, parent.ry, parent.rz]
+            parent = getattr(parent, "reference_cs", None)
         coefs = getattr(g, "coefficients", None)     # (Zernike: the property returns geometry.zernike.coeffs)
         if coefs is not None:
             vals += [coefs] if hasattr(coefs, "requires_grad") else list(np.ravel(np.asarray(coefs, dtype=object)))

@@ -605,6 +605,82 @@ def test_autograd_tilt_and_decenter_variables_match_reference_eager_graph(plugin
     assert ref["rz1"] == 0 and got["rz1"] == 0                           # zero angle: skipped by the reference
 
 
+def test_nested_coordinate_frames_forward_and_autograd(plugin):
+    """Frames defined relative to another frame (``CoordinateSystem.reference_cs``: the coordinate breaks of imported
+    systems, fileio/zemax/reader/converter.py:120-190).  Forward: the packer flattens the chain
+    (``get_effective_transform``, coordinate_system.py:145-165) and the records equal the NumPy reference.  Gradients
+    (be.grad_mode): the effective pose t = t_p + R_p t_c, R = R_p R_c is composed from the LIVE tensors of every level
+    (``plugin._live_frame``), so d(RMS spot)/d(parent tilt, parent decenter, child tilt, child z) through the adjoint
+    kernel's dLoss/dt and dLoss/dR equal the reference's own eager autograd."""
+    import torch
+
+    P, eng, be = plugin
+    from optiland import optic as _optic
+    from optiland.coordinate_system import CoordinateSystem
+
+    def make():
+        lens = _optic.Optic()
+        lens.surfaces.add(index=0, radius=be.inf, thickness=be.inf)
+        lens.surfaces.add(index=1, radius=40.0, thickness=5.0, material="N-BK7", is_stop=True)
+        lens.surfaces.add(index=2, radius=-55.0, thickness=3.0, conic=-0.5)
+        lens.surfaces.add(index=3, radius=-30.0, thickness=4.0, material="SF5")
+        lens.surfaces.add(index=4, radius=-80.0, thickness=45.0)
+        lens.surfaces.add(index=5)
+        lens.set_aperture(aperture_type="EPD", value=9.0)
+        lens.fields.set_type(field_type="angle")
+        lens.fields.add(y=0)
+        lens.fields.add(y=3)
+        lens.wavelengths.add(value=0.6, is_primary=True)
+        # surfaces 3 and 4 live in a tilted / decentered carrier frame; surface 4 is tilted once more inside it
+        carrier = CoordinateSystem(x=0.15, y=-0.1, z=8.0, rx=0.02, ry=-0.015, rz=0.3)
+        lens.surfaces.surfaces[3].geometry.cs = CoordinateSystem(x=0.0, y=0.0, z=0.0, reference_cs=carrier)
+        lens.surfaces.surfaces[4].geometry.cs = CoordinateSystem(x=-0.05, y=0.02, z=4.0, rx=-0.01, ry=0.025, rz=0.0,
+                                                               reference_cs=carrier)
+        return lens, carrier
+
+    def trace(lens):
+        return lens.trace(0.0, 1.0, 0.6, 6, "hexapolar")
+
+    ref_rec, ref_fin = _numpy_reference(lambda: make()[0], trace)
+    lens, _ = make()
+    n0 = len(eng.calls)
+    P.stats(reset=True)
+    rays = trace(lens)
+    assert len(eng.calls) > n0 and not P.stats(), P.stats()
+    for k, v in ref_rec.items():
+        np.testing.assert_allclose(be.to_numpy(getattr(lens.surfaces, k)), v, rtol=0, atol=1e-10, err_msg=k)
+    np.testing.assert_allclose(be.to_numpy(rays.opd), ref_fin["opd"], rtol=0, atol=1e-10)
+
+    def run():
+        lens, carrier = make()
+        c4 = lens.surfaces.surfaces[4].geometry.cs
+        trace(lens)
+        x, y = lens.surfaces.x[-1, :], lens.surfaces.y[-1, :]
+        loss = torch.sqrt(torch.mean((x - torch.mean(x)) ** 2 + (y - torch.mean(y)) ** 2)) + 1e-3 * torch.mean(lens.surfaces.opd[-1, :])
+        loss.backward()
+        out = {"loss": float(loss.detach())}
+        for name, t in (("carrier.x", carrier.x), ("carrier.z", carrier.z), ("carrier.rx", carrier.rx), ("carrier.ry", carrier.ry),
+                        ("carrier.rz", carrier.rz), ("c4.x", c4.x), ("c4.z", c4.z), ("c4.rx", c4.rx), ("c4.ry", c4.ry),
+                        ("radius4", lens.surfaces.surfaces[4].geometry.radius)):
+            out[name] = float(t.grad)
+        return out
+
+    be.grad_mode.enable()
+    try:
+        n1 = len(eng.calls)
+        P.stats(reset=True)
+        got = run()
+        assert any(c[0] == "grad" for c in eng.calls[n1:]) and not P.stats(), (eng.calls[n1:], P.stats())
+        P.uninstall()                       # the reference's own eager graph
+        ref = run()
+    finally:
+        be.grad_mode.disable()
+    assert got["loss"] == pytest.approx(ref["loss"], rel=1e-10)
+    scale = max(abs(v) for k, v in ref.items() if k != "loss")
+    for k in ref:
+        assert got[k] == pytest.approx(ref[k], rel=5e-6, abs=1e-9 * scale), (k, got[k], ref[k])
+
+
 def test_autograd_zernike_and_polynomial_coefficient_variables(plugin):
     """Freeform optimisation variables through the capability: d(RMS spot)/d(Zernike coefficient), d/d(polynomial
     coefficient), d/d(Chebyshev coefficient), d/d(radius, conic) of the freeform surface -- forward kernel + the polynomial-family adjoint
