@@ -31,6 +31,11 @@ GP_R = _lib.GP_R
 GP_COUNT = _lib.GP_COUNT
 
 
+# kinds whose 1-D coefficient list rides in the GP_COEF columns: even / odd asphere C_j, Forbes Q^bfs a_m (the kernel
+# differentiates with respect to the Clenshaw-basis b_m; _TraceFn.backward maps the gradient back, forbes_basis_matrix)
+COEF_KINDS = (T.GEOM_EVEN_ASPHERE, T.GEOM_ODD_ASPHERE, T.GEOM_FORBES_QBFS)
+
+
 def table_to_params(table: T.SurfaceTable) -> torch.Tensor:
     """(S, GP_COUNT) fp64 tensor of the differentiable parameters of ``table`` (one wavelength)."""
     if table.n_wl != 1:
@@ -42,10 +47,10 @@ def table_to_params(table: T.SurfaceTable) -> torch.Tensor:
         p[s, GP_CONIC] = spec.conic
         p[s, GP_N1], p[s, GP_N2] = spec.n1[0], spec.n2[0]
         p[s, GP_R:GP_R + 9] = np.asarray(spec.R, dtype=np.float64).reshape(9)
-        if spec.kind in (T.GEOM_EVEN_ASPHERE, T.GEOM_ODD_ASPHERE):
+        if spec.kind in COEF_KINDS:
             k = len(spec.coefficients)
             if k > GP_MAX_COEF:
-                raise ValueError(f"more than {GP_MAX_COEF} asphere coefficients")
+                raise ValueError(f"more than {GP_MAX_COEF} asphere / Forbes coefficients")
             p[s, GP_COEF:GP_COEF + k] = spec.coefficients
     return torch.from_numpy(p)
 
@@ -65,6 +70,39 @@ def chebyshev_monomials(n: int) -> np.ndarray:
         Tc[i, 1:] = 2.0 * Tc[i - 1, :-1]
         Tc[i] -= Tc[i - 2]
     return Tc
+
+
+def forbes_basis_matrix(nc: int) -> np.ndarray:
+    """Upper-banded (nc, nc) matrix A of the Forbes Q^bfs change of basis ``A b = a`` between the user's coefficients a_m
+    and the coefficients b_m the Clenshaw recurrence runs on: A[i, i] = f_i, A[i, i+1] = g_i, A[i, i+2] = h_i
+    (G. W. Forbes, Opt. Express 18, 19700 (2010), eqs. A.14-A.16; /root/reference/optiland/geometries/forbes/qpoly.py:56-115;
+    the table upload solves it by back-substitution, csrc/olb_prep.h).  The adjoint kernel returns dLoss/db_m in the
+    coefficient slots; dLoss/da = A^-T dLoss/db."""
+    f, g, h = np.zeros(nc + 2), np.zeros(nc + 2), np.zeros(nc + 2)
+    for n in range(nc):
+        if n == 0:
+            f[0] = 2.0
+        elif n == 1:
+            g[0] = -0.5
+            f[1] = np.sqrt(19.0) / 2.0
+        else:
+            h[n - 2] = -n * (n - 1) / (2.0 * f[n - 2])
+            g[n - 1] = -(1.0 + g[n - 2] * h[n - 2]) / f[n - 1]
+            f[n] = np.sqrt(n * (n + 1) + 3.0 - g[n - 1] ** 2 - h[n - 2] ** 2)
+    A = np.zeros((nc, nc))
+    for i in range(nc):
+        A[i, i] = f[i]
+        if i + 1 < nc:
+            A[i, i + 1] = g[i]
+        if i + 2 < nc:
+            A[i, i + 2] = h[i]
+    return A
+
+
+def forbes_coef_grads(gb: np.ndarray) -> np.ndarray:
+    """dLoss/da_m of a Forbes Q^bfs surface from the kernel's dLoss/db_m (``forbes_basis_matrix``)."""
+    nc = len(gb)
+    return np.linalg.solve(forbes_basis_matrix(nc).T, gb) if nc else gb
 
 
 def zernike_norms(spec) -> np.ndarray:
@@ -145,10 +183,10 @@ def params_to_table(table: T.SurfaceTable, params: torch.Tensor, coefs: torch.Te
         ch = dict(t=p[s, GP_TX:GP_TZ + 1].copy(), n1=np.array([p[s, GP_N1]]), n2=np.array([p[s, GP_N2]]))
         if spec.kind != T.GEOM_NOOP:
             ch["R"] = p[s, GP_R:GP_R + 9].reshape(3, 3).copy()
-        if spec.kind in (T.GEOM_STANDARD, T.GEOM_EVEN_ASPHERE, T.GEOM_ODD_ASPHERE):
+        if spec.kind in (T.GEOM_STANDARD,) + COEF_KINDS:
             ch["radius"] = float("inf") if p[s, GP_CURV] == 0 else 1.0 / p[s, GP_CURV]
             ch["conic"] = float(p[s, GP_CONIC])
-        if spec.kind in (T.GEOM_EVEN_ASPHERE, T.GEOM_ODD_ASPHERE):
+        if spec.kind in COEF_KINDS:
             ch["coefficients"] = p[s, GP_COEF:GP_COEF + len(spec.coefficients)].copy()
         if spec.kind in POLY_KINDS:
             ch["radius"] = float("inf") if p[s, GP_CURV] == 0 else 1.0 / p[s, GP_CURV]
@@ -178,10 +216,10 @@ class _ParamPacker:
         self.surf0, self.pool0 = surf, pool
         kinds = np.array([s.kind for s in template.surfaces])
         self.rot = np.nonzero(kinds != T.GEOM_NOOP)[0]
-        self.curved = np.nonzero(np.isin(kinds, (T.GEOM_STANDARD, T.GEOM_EVEN_ASPHERE, T.GEOM_ODD_ASPHERE) + POLY_KINDS))[0]
+        self.curved = np.nonzero(np.isin(kinds, (T.GEOM_STANDARD,) + COEF_KINDS + POLY_KINDS))[0]
         ci, cs, ck = [], [], []
         for s, spec in enumerate(template.surfaces):
-            if spec.kind in (T.GEOM_EVEN_ASPHERE, T.GEOM_ODD_ASPHERE):
+            if spec.kind in COEF_KINDS:
                 k = len(spec.coefficients)
                 ci += list(range(int(surf["coef_off"][s]), int(surf["coef_off"][s]) + k))
                 cs += [s] * k
@@ -228,6 +266,18 @@ def _packed_from_params(template: T.SurfaceTable, params: torch.Tensor):
     return pk(params.detach().double().cpu().numpy())
 
 
+_forbes_cache: dict = {}
+
+
+def _forbes_inv_t(nc: int, device) -> torch.Tensor:
+    """A^-T of ``forbes_basis_matrix(nc)`` as a device tensor (cached): dLoss/da = A^-T dLoss/db."""
+    key = (nc, str(device))
+    m = _forbes_cache.get(key)
+    if m is None:
+        m = _forbes_cache[key] = torch.from_numpy(np.linalg.inv(forbes_basis_matrix(nc)).T.copy()).to(device)
+    return m
+
+
 class _TraceFn(torch.autograd.Function):
     """forward(template, holder, rows, params, x, y, z, L, M, N, i, opd).  ``rows`` = None: the 8 outputs
     are the full (S, N) record arrays; ``rows`` = tuple of row indices: 8 * len(rows) outputs, one (N,)
@@ -255,7 +305,7 @@ class _TraceFn(torch.autograd.Function):
             device_tables.append(dtab)
         if not dtab.c.bwd_supported:
             raise _lib.OlbError("differentiable trace: table not supported by olb_trace_bwd_* (a geometry other than plane / "
-                                "standard / even- and odd-asphere / polynomial / Zernike / Chebyshev, a Fresnel coating, several wavelengths in one table)")
+                                "standard / even- and odd-asphere / polynomial / Zernike / Chebyshev / Forbes Q-bfs, a Fresnel coating, several wavelengths in one table)")
         n = x.numel()
         S = table.num_surfaces
         # (a slice / view of a larger tensor may start anywhere: the C ABI wants 16-byte aligned arrays)
@@ -335,6 +385,11 @@ class _TraceFn(torch.autograd.Function):
                     C.byref(c_gin) if c_gin is not None else None, C.c_void_p(gpar.data_ptr()), n,
                     C.c_uint64(mask & ((1 << 64) - 1)), C.c_void_p(stream))
         _lib.check(rc, f"olb_trace_bwd_{ctx.sfx}")
+        for s, spec in enumerate(dtab.table.surfaces):
+            if spec.kind == T.GEOM_FORBES_QBFS and len(spec.coefficients):
+                # the kernel's coefficient slots hold dLoss/db_m (Clenshaw basis): back to the user's a_m, on the device
+                nc = len(spec.coefficients)
+                gpar[s, GP_COEF:GP_COEF + nc] = _forbes_inv_t(nc, gpar.device) @ gpar[s, GP_COEF:GP_COEF + nc]
         gi = gin if gin is not None else [None] * 8
         gcoef = None
         if ctx.coefs_meta is not None and tables:

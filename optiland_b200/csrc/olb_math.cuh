@@ -1079,6 +1079,31 @@ OLB_HD bool poly_family_kind(int kind) {
   return kind == OLB_GEOM_POLYNOMIAL || kind == OLB_GEOM_ZERNIKE || kind == OLB_GEOM_CHEBYSHEV;
 }
 
+// Number of per-surface COEFFICIENT gradient slots behind the 7 scalars (pg[GP_COEF ..]): the even- / odd-asphere
+// coefficients C_j, or the Clenshaw-basis coefficients b_m of a Forbes Q^bfs surface (the host maps dLoss/db to the user's
+// a_m through the transposed change of basis, optiland_b200/autograd.py).
+template <typename T>
+OLB_HD int coef_grad_slots(const PrepSurface<T>& S) {
+  return (S.kind == OLB_GEOM_EVEN_ASPHERE || S.kind == OLB_GEOM_ODD_ASPHERE || S.kind == OLB_GEOM_FORBES_QBFS) ? S.n_coef : 0;
+}
+
+// Forbes Clenshaw sum with its first TWO derivatives (adjoint only; forbes_q_sum serves the forward pass):
+// alpha''_n = p alpha''_{n+1} - alpha''_{n+2} - 8 alpha'_{n+1}  (differentiate alpha'_n = p alpha'_{n+1} - alpha'_{n+2}
+// - 4 alpha_{n+1} once more, dp/dx = -4), d2S/dx2 = 2 (alpha''_0 + alpha''_1).
+template <typename T>
+OLB_HD void forbes_q_sum2(const T* b, int nc, T x, T& S, T& dS, T& d2S) {
+  const T p = (T)2 - (T)4 * x;
+  T a0 = 0, a1 = 0, a2 = 0, d0 = 0, d1 = 0, d2 = 0, e0 = 0, e1 = 0, e2 = 0;
+  for (int n = nc - 1; n >= 0; --n) {
+    a0 = b[n] + p * a1 - a2;
+    d0 = p * d1 - d2 - (T)4 * a1;
+    e0 = p * e1 - e2 - (T)8 * d1;
+    if (n > 0) { a2 = a1; a1 = a0; d2 = d1; d1 = d0; e2 = e1; e1 = e0; }
+  }
+  if (nc > 1) { S = (T)2 * (a0 + a1); dS = (T)2 * (d0 + d1); d2S = (T)2 * (e0 + e1); }
+  else { S = (T)2 * a0; dS = (T)2 * d0; d2S = (T)2 * e0; }
+}
+
 // Table gradients of the polynomial families (olb_trace_bwd_tables_*): per surface two blocks (sag table S, slope table
 // D) of GT_DIM x GT_DIM doubles, entry (i, j) <-> xn^i yn^j; tables wider than GT_DIM are outside the adjoint's scope.
 enum { GT_DIM = 12, GT_BLOCK = GT_DIM * GT_DIM, GT_PER_SURFACE = 2 * GT_BLOCK };
@@ -1136,6 +1161,9 @@ OLB_HD bool surface_backward(const PrepSurface<T>& S, const T* pool, T xg0, T yg
   const T r2 = o_fma(x1, x1, y1 * y1);
   T g = 0, gp = 0, sconic = 1, c = 0, kp1 = S.kp1;
   T asph_p = 0, asph_pp = 0;
+  // Forbes Q^bfs departure P(w) = pre phi S (see below): the pieces shared by the slope factor and the parameter gradients
+  T fb_a = 0, fb_pre = 0, fb_dpre = 0, fb_phi = 1, fb_dphi = 0, fb_da = 1, fb_S = 0, fb_dS = 0;
+  bool fb_on = false;
   if (!plane) {
     c = S.curv;
     sconic = o_sqrt(o_fma(-kp1 * r2, c * c, (T)1));
@@ -1167,6 +1195,36 @@ OLB_HD bool surface_backward(const PrepSurface<T>& S, const T* pool, T xg0, T yg
       }
       g += asph_p;
       gp += asph_pp;
+    } else if (POLY && S.kind == OLB_GEOM_FORBES_QBFS) {
+      // Forbes Q^bfs: sag = conic + P(w), P = pre(w) phi(w) S(a w) with w = r^2, a = 1 / norm_radius^2, pre = a w (1 - a w),
+      // phi = sqrt(na / da), na = 1 - k c^2 w, da = 1 - (1 + k) c^2 w (forbes/geometry.py:187-366; forbes_sag above).
+      // A rotationally symmetric sag: slope factor g = 2 sag'(w), so g += 2 P', gp += 2 P''  (the reference's analytic
+      // slope IS the sag's derivative up to its 1e-12 guards, so the same g serves the normal and the
+      // implicit-function theorem).  phi' = c^2 / (2 phi da^2); phi'' = c^4 / 4 (k (na da)^-3/2 + 3 (1 + k) na^-1/2 da^-5/2).
+      // Outside the normalisation radius (and for an all-zero coefficient set) the surface is the bare conic, as in the
+      // forward pass.  (POLY: Forbes tables run on the olb_trace_bwd_tables_* variant of the kernel.)
+      fb_a = S.inv_norm * S.inv_norm;
+      const T usq = r2 * fb_a;
+      if (S.n_coef > 0 && usq < (T)1) {
+        fb_on = true;
+        T d2S;
+        forbes_q_sum2(pool + S.coef_off, S.n_coef, usq, fb_S, fb_dS, d2S);
+        const T c2 = c * c;
+        const T na = (T)1 - S.conic * c2 * r2;
+        fb_da = (T)1 - kp1 * c2 * r2;
+        fb_phi = o_sqrt(o_div(na, fb_da));
+        const T ida = o_rcp(fb_da), ina = o_rcp(na);
+        fb_dphi = o_div(c2 * ida * ida, (T)2 * fb_phi);
+        const T rn = o_sqrt(ina), rd = o_sqrt(ida);             // na^-1/2, da^-1/2
+        const T d2phi = (T)0.25 * c2 * c2 * (S.conic * rn * ina * rd * ida + (T)3 * kp1 * rn * rd * ida * ida);
+        fb_pre = usq * ((T)1 - usq);
+        fb_dpre = fb_a * ((T)1 - (T)2 * usq);
+        const T d2pre = (T)-2 * fb_a * fb_a;
+        const T Sp = fb_a * fb_dS, Spp = fb_a * fb_a * d2S;       // dS/dw, d2S/dw2
+        g += (T)2 * (fb_dpre * fb_phi * fb_S + fb_pre * fb_dphi * fb_S + fb_pre * fb_phi * Sp);
+        gp += (T)2 * (d2pre * fb_phi * fb_S + (T)2 * fb_dpre * fb_dphi * fb_S + (T)2 * fb_dpre * fb_phi * Sp
+                      + fb_pre * d2phi * fb_S + (T)2 * fb_pre * fb_dphi * Sp + fb_pre * fb_phi * Spp);
+      }
     }
   }
   T fx = x1 * g, fy = y1 * g;           // the reference's slope function (-> normal)
@@ -1327,6 +1385,36 @@ OLB_HD bool surface_backward(const PrepSurface<T>& S, const T* pool, T xg0, T yg
       for (int j = 0; j < GP_MAX_COEF; ++j) {
         if (j < S.n_coef) pg[GP_COEF + j] += q * pws + ag * (T)(j + 1) * pw;   // d sag/dC_j = r^(j+1); d g/dC_j = (j+1) r^(j-1)
         pw *= rr; pws *= rr;
+      }
+    } else if (POLY && fb_on) {
+      // Forbes departure: curvature and conic enter P through phi only,
+      //   dphi/dc = c w / (phi da^2),                      dphi/dk = c^4 w^2 / (2 phi da^2),
+      //   dphi'/dc = c/(phi da^2) - c^3 w/(2 phi^3 da^4) + 2 (1+k) c^3 w/(phi da^3),
+      //   dphi'/dk = -c^6 w^2/(4 phi^3 da^4) + c^4 w/(phi da^3),
+      // dP/dtheta = pre S dphi/dtheta,  dP'/dtheta = (pre' S + pre S') dphi/dtheta + pre S dphi'/dtheta;  g carries 2 P'.
+      const T w = r2, ida = o_rcp(fb_da), ida2 = ida * ida, iphi = o_rcp(fb_phi), iphi3 = iphi * iphi * iphi;
+      const T c2 = c * c, c3 = c2 * c, c4 = c2 * c2;
+      const T dphi_dc = c * w * ida2 * iphi;
+      const T dphi_dk = (T)0.5 * c4 * w * w * ida2 * iphi;
+      const T ddphi_dc = c * ida2 * iphi - (T)0.5 * c3 * w * ida2 * ida2 * iphi3 + (T)2 * kp1 * c3 * w * ida2 * ida * iphi;
+      const T ddphi_dk = (T)-0.25 * c4 * c2 * w * w * ida2 * ida2 * iphi3 + c4 * w * ida2 * ida * iphi;
+      const T Sp = fb_a * fb_dS;
+      const T A = fb_dpre * fb_S + fb_pre * Sp, B = fb_pre * fb_S;
+      pg[GP_CURV] += q * B * dphi_dc + ag * (T)2 * (A * dphi_dc + B * ddphi_dc);
+      pg[GP_CONIC] += q * B * dphi_dk + ag * (T)2 * (A * dphi_dk + B * ddphi_dk);
+      // the Clenshaw-basis coefficients: S = sum_m b_m B_m(usq), B_m = 2 (U_m + U_{m-1})(p), p = 2 - 4 usq,
+      // U_0 = 1, U_1 = p, U_{m+1} = p U_m - U_{m-1}:  dP/db_m = pre phi B_m,  dP'/db_m = (pre' phi + pre phi') B_m + pre phi a B_m'
+      const T p = (T)2 - (T)4 * w * fb_a;
+      const T k0 = fb_pre * fb_phi, k1 = fb_dpre * fb_phi + fb_pre * fb_dphi;
+      T Um1 = 0, U = 1, dUm1 = 0, dU = 0;        // U_{m-1}, U_m and their derivatives with respect to p
+#pragma unroll
+      for (int m = 0; m < GP_MAX_COEF; ++m) {
+        if (m < S.n_coef) {
+          const T Bm = (T)2 * (U + Um1), dBm = (T)-8 * (dU + dUm1);          // B_m and dB_m / d usq
+          pg[GP_COEF + m] += q * k0 * Bm + ag * (T)2 * (k1 * Bm + k0 * fb_a * dBm);
+        }
+        const T Un = p * U - Um1, dUn = U + p * dU - dUm1;
+        Um1 = U; U = Un; dUm1 = dU; dU = dUn;
       }
     }
   }

@@ -474,7 +474,9 @@ static inline PrepResult prepare_table(const OlbTable& tab) {
   for (int s = 0; s < tab.n_surfaces; ++s) {
     ps[s].gslot = gslot;
     // 7 scalars + even-asphere coefficients + (tilted pose) the 9 entries of dLoss/dR
-    const bool asph = ps[s].kind == OLB_GEOM_EVEN_ASPHERE || ps[s].kind == OLB_GEOM_ODD_ASPHERE;
+    // (a Forbes Q^bfs surface carries the gradients of its Clenshaw-basis coefficients in the same slots)
+    const bool asph = ps[s].kind == OLB_GEOM_EVEN_ASPHERE || ps[s].kind == OLB_GEOM_ODD_ASPHERE ||
+                      ps[s].kind == OLB_GEOM_FORBES_QBFS;
     ps[s].gslots = ps[s].kind == OLB_GEOM_NOOP ? 0 : 7 + (asph ? ps[s].n_coef : 0) +
                                                          ((ps[s].flags & OLB_SF_ROTATED) ? 9 : 0);
     gslot += ps[s].gslots;
@@ -486,8 +488,10 @@ static inline PrepResult prepare_table(const OlbTable& tab) {
                          o.poly_rows <= 12 && o.poly_cols <= 12;
     const bool kind_ok = o.kind == OLB_GEOM_NOOP || o.kind == OLB_GEOM_PLANE || o.kind == OLB_GEOM_STANDARD ||
                          ((o.kind == OLB_GEOM_EVEN_ASPHERE || o.kind == OLB_GEOM_ODD_ASPHERE) && o.n_coef <= 12) || polyfam;
-    if (polyfam) res.bwd_tables = true;
-    if (!kind_ok || o.coating == OLB_COAT_FRESNEL || tab.n_wl != 1)
+    // Forbes Q^bfs: covered by the general (olb_trace_bwd_tables_*) variant of the adjoint kernel, at most 12 terms
+    const bool forbes = o.kind == OLB_GEOM_FORBES_QBFS && tab.surfaces[s].n_coef <= 12;
+    if (polyfam || forbes) res.bwd_tables = true;
+    if (!(kind_ok || forbes) || o.coating == OLB_COAT_FRESNEL || tab.n_wl != 1)
       res.bwd_supported = false;
   }
   build_blob<double>(tab, pools, ps, features, res.blob_f64);

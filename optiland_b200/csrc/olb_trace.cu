@@ -617,7 +617,7 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(T) == 8 ? OLB_BWD_MINB64 : 2)) 
 #pragma unroll
         for (int q = 0; q < GP_SCALARS; ++q) pg[q] = 0;
         // slots of this surface: 7 scalars, its even-asphere coefficients, then dLoss/dR (9) if the pose is tilted
-        const int ncoef = (S.kind == OLB_GEOM_EVEN_ASPHERE || S.kind == OLB_GEOM_ODD_ASPHERE) ? S.n_coef : 0;
+        const int ncoef = coef_grad_slots(S);
         const bool tilted = (S.flags & OLB_SF_ROTATED) != 0;
         if (SMEM_ACC) {
           T* mine = tacc + (int64_t)S.gslot * BLOCK + threadIdx.x;
@@ -733,7 +733,7 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(T) == 8 ? OLB_BWD_MINB64 : 2)) 
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         // slot -> parameter: scalars and coefficients in place, the tilted pose's 9 slots -> GP_R ..
-        const int ncoef = (S.kind == OLB_GEOM_EVEN_ASPHERE || S.kind == OLB_GEOM_ODD_ASPHERE) ? S.n_coef : 0;
+        const int ncoef = coef_grad_slots(S);
         const int qp = q < GP_COEF + ncoef ? q : GP_R + (q - GP_COEF - ncoef);
         if (lane == 0 && v != 0) atomicAdd(&a.gparams[s * GP_COUNT + qp], v);
       }

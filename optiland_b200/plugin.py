@@ -513,8 +513,15 @@ def _live_params(surfaces, table, wavelength):
             g = surf.geometry
             cs = g.cs
             if spec.kind not in (T.GEOM_PLANE, T.GEOM_STANDARD, T.GEOM_EVEN_ASPHERE, T.GEOM_ODD_ASPHERE,
-                                 T.GEOM_POLYNOMIAL, T.GEOM_ZERNIKE, T.GEOM_CHEBYSHEV):
+                                 T.GEOM_POLYNOMIAL, T.GEOM_ZERNIKE, T.GEOM_CHEBYSHEV, T.GEOM_FORBES_QBFS):
                 return None
+            # normalisation radii are constants of the adjoint.  One that an optimiser drives (NormalizationRadiusVariable,
+            # optimization/variable/norm_radius.py: the value written is an nn.Parameter or computed from one) needs the
+            # reference's eager graph; a plain be.array leaf -- every array is one under be.grad_mode -- does not
+            for a in ("norm_radius", "norm_x", "norm_y"):
+                v = getattr(g, a, None)
+                if getattr(v, "requires_grad", False) and (v.grad_fn is not None or isinstance(v, torch.nn.Parameter)):
+                    return None
             nested = cs.reference_cs is not None
             if nested:
                 # a frame defined relative to another one (coordinate breaks of imported systems,
@@ -556,6 +563,14 @@ def _live_params(surfaces, table, wavelength):
                     return None
                 for j, cj in enumerate(g.coefficients):
                     vals[GP_COEF + j] = scalar(cj, like)
+            elif spec.kind == T.GEOM_FORBES_QBFS:
+                # radial_terms {order n: a_n} (forbes/geometry.py:242-274; ForbesQNormalSlopeCoeffVariable writes
+                # geom.radial_terms[n]); missing orders are constant zeros
+                terms = g.radial_terms or {}
+                if terms and max(int(n_) for n_ in terms) + 1 > GP_MAX_COEF:
+                    return None
+                for n_, cj in terms.items():
+                    vals[GP_COEF + int(n_)] = scalar(cj, like)
             vals[GP_CURV] = one if curved else zero      # selector: 1 -> 1/radius, 0 -> 0
         else:
             flat_r.append(one)
@@ -619,6 +634,9 @@ def _wants_grad(backend, surfaces, rays=None) -> bool:
         while parent is not None:                    # nested frames: the pose depends on every level
             vals += [parent.x, parent.y, parent.z, parent.rx, parent.ry, parent.rz]
             parent = getattr(parent, "reference_cs", None)
+        rt = getattr(g, "radial_terms", None)        # Forbes Q^bfs: {order: tensor}
+        if isinstance(rt, dict):
+            vals += list(rt.values())
         coefs = getattr(g, "coefficients", None)     # (Zernike: the property returns geometry.zernike.coeffs)
         if coefs is not None:
             vals += [coefs] if hasattr(coefs, "requires_grad") else list(np.ravel(np.asarray(coefs, dtype=object)))

@@ -183,7 +183,7 @@ class OracleEngine:
         self.calls.append(("grad", table.num_surfaces, int(rays.x.numel())))
         keys = ("x", "y", "z", "L", "M", "N", "i", "opd")
 
-        has_tables = any(sp.kind in AG.POLY_KINDS for sp in table.surfaces)
+        has_tables = any(sp.kind in AG.POLY_KINDS or sp.kind == AG.T.GEOM_FORBES_QBFS for sp in table.surfaces)
         cf_in = coefs if coefs is not None else torch.zeros((table.num_surfaces, 1), dtype=torch.float64)
 
         class Fn(torch.autograd.Function):
@@ -207,6 +207,10 @@ class OracleEngine:
                 else:
                     gin, gpar = run_backward(hc, ctx.tab, ctx.inp, ctx.rec, grec)
                     gcf = None
+                for s_, sp in enumerate(ctx.tab.surfaces):      # Forbes: dLoss/db (Clenshaw basis) -> dLoss/da, as _TraceFn.backward
+                    if sp.kind == AG.T.GEOM_FORBES_QBFS and len(sp.coefficients):
+                        nc = len(sp.coefficients)
+                        gpar[s_, AG.GP_COEF:AG.GP_COEF + nc] = AG.forbes_coef_grads(gpar[s_, AG.GP_COEF:AG.GP_COEF + nc])
                 return (torch.from_numpy(gpar), gcf, *[torch.from_numpy(gin[k]) for k in keys])
 
         outs = Fn.apply(params, cf_in, *[getattr(rays, k) for k in keys])

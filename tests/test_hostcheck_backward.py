@@ -369,3 +369,56 @@ def test_chebyshev_adjoint_matches_finite_differences(hc):
 
             ref = (loss_fn(with_c(1e-6), rays, weights) - loss_fn(with_c(-1e-6), rays, weights)) / 2e-6
             assert gc[i, j] == pytest.approx(ref, rel=3e-4, abs=1e-6 * gmax), (i, j, gc[i, j], ref)
+
+
+def test_forbes_qbfs_adjoint_matches_finite_differences(hc):
+    """The adjoint through Forbes Q^bfs surfaces (forbes/geometry.py:187-366): slope factor and its r^2-derivative from the
+    Clenshaw sum with two derivatives, curvature / conic entering the departure through phi, coefficient gradients in the
+    Clenshaw basis mapped back to the user's a_m by the transposed change of basis (``autograd.forbes_basis_matrix``).
+    Launch state, pose, curvature, conic and every a_m of both surfaces of the `forbes_qbfs` fixture (conic -0.4 and 0,
+    6 and 5 terms) against central differences of the oracle."""
+    from optiland_b200 import autograd as AG
+
+    c = Case("forbes_qbfs")
+    table = T.SurfaceTable([dataclasses.replace(s, tol=1e-14) if s.kind in T.NEWTON_KINDS else s for s in c.table.surfaces],
+                           c.table.wavelengths)
+    ht = _lib.HostTable(table)
+    assert hc.olbhc_bwd_supported(C.byref(ht.c))
+    rng = np.random.default_rng(7)
+    sel = rng.choice(c.n, size=48, replace=False)
+    rays = {k: v[sel].copy() for k, v in c.rays.items()}
+    n = sel.size
+    S = table.num_surfaces
+    weights = {k: rng.normal(size=(S, n)) for k in REC}
+    _, rec, st = O.trace(table, rays)
+    assert st == 0 and np.isfinite(rec["x"]).all()
+    gin, gpar, gtab = run_backward(hc, table, rays, rec, weights, tables=True)
+    gmax = np.abs(gpar).max()
+    dirs = {k: rng.normal(size=n) for k in ("x", "y", "z", "L", "M", "N", "i", "opd")}
+    h = 1e-6
+
+    def shifted(sign):
+        r = {k: v.copy() for k, v in rays.items()}
+        r["opd"] = np.zeros(n)
+        for k, d in dirs.items():
+            r[k] = r[k] + sign * h * d
+        return r
+
+    fd_dir = (loss_fn(table, shifted(+1), weights) - loss_fn(table, shifted(-1), weights)) / (2 * h)
+    assert sum(float(np.sum(gin[k] * dirs[k])) for k in dirs) == pytest.approx(fd_dir, rel=2e-4)
+    checked = 0
+    for s, spec in enumerate(table.surfaces):
+        if spec.kind != T.GEOM_FORBES_QBFS:
+            continue
+        for what, slot, hh in (("tz", GP["TZ"], 1e-6), ("tx", GP["TX"], 1e-6), ("conic", GP["CONIC"], 1e-5),
+                               ("curv", GP["CURV"], 1e-5 * abs(1.0 / spec.radius)), ("n2", GP["N2"], 1e-6)):
+            ref = fd(table, rays, weights, s, what, hh)
+            assert gpar[s, slot] == pytest.approx(ref, rel=2e-4, abs=1e-6 * gmax), (s, what, gpar[s, slot], ref)
+            checked += 1
+        nc = len(spec.coefficients)
+        ga = AG.forbes_coef_grads(gpar[s, GP["COEF"]:GP["COEF"] + nc])
+        for m in range(nc):
+            ref = fd(table, rays, weights, s, f"coef{m}", 1e-6)
+            assert ga[m] == pytest.approx(ref, rel=3e-4, abs=1e-6 * gmax), (s, m, ga[m], ref)
+            checked += 1
+    assert checked == 2 * 5 + 6 + 5
