@@ -1,10 +1,10 @@
 """Forbes Q^bfs surfaces in the adjoint (olb_math.cuh::surface_backward, the Forbes branch).
 
-This file sorts LAST on purpose: the Forbes branch was written after the round's GPU budget had been spent, so its two
-``-m gpu`` tests (the kernel against the CPU instantiation of the same adjoint, and the plugin path on the product engine)
-have not run on a B200 yet -- the CPU side (finite differences of the oracle in tests/test_hostcheck_backward.py, the plugin
-path over the test-only oracle engine against the reference's own eager autograd, below) is green.  Everything that WAS
-verified on hardware runs before it."""
+The branch was written after most of the round's GPU budget had been spent, which is why these tests sit in a file of
+their own that sorts last; the final minute of the budget then ran them on a B200 (``profiles/r2b_gputests_forbes.log``:
+the kernel in fp64 and fp32 against the CPU instantiation of the same adjoint, and the plugin path on the product engine
+against the reference's own eager autograd -- 3 passed).  CPU side: finite differences of the oracle in
+tests/test_hostcheck_backward.py, and the plugin path over the test-only oracle engine, below."""
 import dataclasses
 
 import numpy as np
