@@ -260,7 +260,7 @@ typedef struct OlbDeviceTable {
   int32_t off_f64, bytes_f64;   /* fp64 blob inside workspace */
   int32_t off_f32, bytes_f32;   /* fp32 blob inside workspace */
   int32_t bwd_supported;        /* 1 if olb_trace_bwd_* covers every surface of the table; 2: covered, and the table has
-                                   polynomial / Zernike / Chebyshev surfaces whose gradients need olb_trace_bwd_tables_* */
+                                   polynomial / Zernike / Chebyshev / Forbes surfaces, which need olb_trace_bwd_tables_* */
   int32_t bwd_slots;            /* gradient accumulator slots per thread (backward kernel)   */
   int32_t n_systems;            /* 1, or the number of systems of a batched table            */
   int32_t stride_f64;           /* bytes between consecutive systems' fp64 / fp32 blobs      */
@@ -472,6 +472,11 @@ int olb_trace_bwd_f64(const OlbDeviceTable* table, int32_t first, int32_t last,
  * Chebyshev: ONE table S = D = P with P_pq = sum_ij C_ij Tc[i][p] Tc[j][q] (Tc: monomial coefficients of T_n), its slope
  * entering the normal WITHOUT the factors 1 / norm_x, 1 / norm_y (the reference's form, chebyshev.py:171-181), so
  * dLoss/dC_ij = sum_pq Tc[i][p] (dLoss/dS + dLoss/dD)_pq Tc[j][q].
+ * OLB_GEOM_FORBES_QBFS surfaces (at most 12 radial terms) are covered by this entry point as well (they use none of the
+ * table blocks): grad_params[OLB_GP_COEF + m] receives dLoss/db_m, b = the coefficients of the basis the Clenshaw
+ * recurrence runs on (A b = a with the upper-banded f / g / h matrix of Forbes, Opt. Express 18, 19700 (2010),
+ * eqs. A.14-A.16; optiland/geometries/forbes/qpoly.py:56-115), so dLoss/da = A^-T dLoss/db
+ * (optiland_b200.autograd.forbes_basis_matrix).
  */
 #define OLB_GT_DIM 12
 #define OLB_GT_PER_SURFACE (2 * OLB_GT_DIM * OLB_GT_DIM)
