@@ -433,6 +433,30 @@ def _pol_state(be, optic):
     return True, (f(st.Ex), f(st.Ey), f(st.phase_x), f(st.phase_y))
 
 
+def _apodization_factor(be, engine, optic, Px, Py):
+    """Per-ray launch intensity of an apodized pupil (``RayGenerator.generate_rays``, rays/ray_generator.py:83-87:
+    ``apodization.get_intensity(Px, Py)``), or None without apodization; False when it cannot be used on the device."""
+    if not optic.apodization:
+        return None
+    a = optic.apodization.get_intensity(Px, Py)
+    if not engine.accepts_tensor(a) or a.shape != Px.shape or a.dtype != Px.dtype:
+        return False
+    return a
+
+
+def _apply_apodization(rec, apod) -> None:
+    """The kernel launches with unit intensity; every operation on the intensity along the path is a multiplication
+    (absorption, coating transmittance, the polarized epilogue's sum |P E|^2 i0) or a reset to 0 (clipping), so the
+    records of an apodized launch are the unit-intensity records times the per-ray factor: one pass over the (S, N)
+    intensity rows instead of a per-ray intensity input to the launch.  (Out of place: the polarized epilogue's
+    result may alias the last intensity row.)"""
+    if apod is None:
+        return
+    if "i_pol" in rec:
+        rec["i_pol"] = rec["i_pol"] * apod
+    rec["intensity"] = rec["intensity"] * apod
+
+
 def _make_rays(be, rec, wl_arr, polarized: bool):
     """The reference's ray object for a fused launch: ``RealRays``, or ``PolarizedRays`` carrying the kernel's P
     matrices, the updated intensity and the launch state update_intensity / get_exit_fields refer to
@@ -777,7 +801,7 @@ def install(engine=None, alias: str | None = None) -> None:
             (SURVEY.md 8f-1): returns the traced rays or None to decline.  Covers what
             ``RayGenerator.generate_rays`` + ``ParaxialRayAimer`` + ``field_definition.get_ray_origins`` do for one
             field point (infinite-object angle field, finite object with an object-height / angle field,
-            object-space telecentric system) without apodization; with ``optic.polarization`` set the rays are
+            object-space telecentric system), apodized or not; with ``optic.polarization`` set the rays are
             ``PolarizedRays`` (Fresnel coatings included) and ``update_intensity`` runs as the kernel's epilogue."""
             import numpy as _np
 
@@ -794,8 +818,6 @@ def install(engine=None, alias: str | None = None) -> None:
                 return _fused_decline("field coordinates are not plain numbers")
             if not single:
                 return _fused_decline("several field points in one Optic.trace call")
-            if optic.apodization:
-                return _fused_decline("apodization")
             # the aimer is (re)configured lazily inside generate_rays from this dict (ray_generator.py:67-71)
             if getattr(tracer, "ray_aiming_config", {}).get("mode", "paraxial") != "paraxial":
                 return _fused_decline("non-paraxial ray aiming")
@@ -806,6 +828,9 @@ def install(engine=None, alias: str | None = None) -> None:
             engine = _state["engine"]
             if not (engine.accepts_tensor(Px) and engine.accepts_tensor(Py)):
                 return _fused_decline("pupil samples not resident on a CUDA device (or not fp32/fp64)")
+            apod = _apodization_factor(be, engine, optic, Px, Py)      # (the UNSCALED pupil: real_ray_tracer.py:86-101)
+            if apod is False:
+                return _fused_decline("apodization factor not resident on the device")
             polarized, state = _pol_state(be, optic)
             try:
                 table = pack_surface_group(optic.surfaces, [float(wavelength)])
@@ -819,6 +844,7 @@ def install(engine=None, alias: str | None = None) -> None:
                 return _fused_decline("first surface is not an object surface")
             rec = engine.trace_pupil(table, Px, Py, pupil_affine(sc), polarization=state) if polarized else \
                 engine.trace_pupil(table, Px, Py, pupil_affine(sc))
+            _apply_apodization(rec, apod)
             _reset_records(be, optic.surfaces)
             for row, surf in enumerate(optic.surfaces.surfaces):
                 for attr, key in _REC_ATTR:
@@ -838,7 +864,8 @@ def install(engine=None, alias: str | None = None) -> None:
 
         def trace_optic_generic(self, tracer, Hx, Hy, Px, Py, wavelength):
             """``RealRayTracer.trace_generic`` (raytrace/real_ray_tracer.py:120-154) for per-ray (Hx, Hy, Px, Py[, lambda])
-            arrays with the launch state generated on the device.  Needs the paraxial aimer and no apodization;
+            arrays with the launch state generated on the device.  Needs the paraxial aimer (an apodized pupil is
+            served unless vignetting factors are set as well);
             ``optic.polarization`` set -> ``PolarizedRays`` (config 5's call shape).  Returns the traced rays or None."""
             import numpy as _np
 
@@ -849,8 +876,6 @@ def install(engine=None, alias: str | None = None) -> None:
             engine = _state["engine"]
             if getattr(_tls, "in_reference", False) or _wants_grad(self, list(optic.surfaces.surfaces)):
                 return None
-            if optic.apodization:
-                return _fused_decline("apodization")
             if getattr(tracer, "ray_aiming_config", {}).get("mode", "paraxial") != "paraxial":
                 return _fused_decline("non-paraxial ray aiming")
             try:
@@ -858,6 +883,10 @@ def install(engine=None, alias: str | None = None) -> None:
                                or _np.any(_np.asarray(be.to_numpy(optic.fields.vy)) != 0))
             except Exception:
                 return _fused_decline("vignetting factors are not plain numbers")
+            if optic.apodization and has_vig:
+                # (the factor is evaluated on the pupil point scaled ONCE by the vignetting factor,
+                # real_ray_tracer.py:132-141 -> ray_generator.py:83-85, while the kernel applies the factor itself)
+                return _fused_decline("apodization together with vignetting factors")
             tracer._validate_normalized_coordinates(Hx, Hy, "field")
             tracer._validate_normalized_coordinates(Px, Py, "pupil")
             vig = None
@@ -897,6 +926,9 @@ def install(engine=None, alias: str | None = None) -> None:
                 return _fused_decline("field / pupil arrays not resident on a CUDA device (or of different shapes)")
             if any(t.dtype != Px.dtype for t in (Hx, Hy)):
                 return _fused_decline("field and pupil arrays of different precision")
+            apod = _apodization_factor(be, engine, optic, Px, Py)
+            if apod is False:
+                return _fused_decline("apodization factor not resident on the device")
             w = None
             if be.is_array_like(wavelength) and be.size(wavelength) > 1:
                 w = be.to_tensor(wavelength, device=Px.device) if hasattr(be, "to_tensor") else wavelength
@@ -929,6 +961,7 @@ def install(engine=None, alias: str | None = None) -> None:
             # (trace_generic does NOT run update_intensity, real_ray_tracer.py:143-152: P matrices only)
             kw = {"polarization": "matrix"} if polarized else {}
             rec = engine.trace_pupil(table, Px, Py, aff, wavelength=w if len(wls) > 1 else None, **kw)
+            _apply_apodization(rec, apod)
             _reset_records(be, optic.surfaces)
             for row, surf in enumerate(optic.surfaces.surfaces):
                 for attr, key in _REC_ATTR:

@@ -188,6 +188,49 @@ def test_trace_generic_with_per_ray_fields_and_wavelengths(plugin):
         np.testing.assert_allclose(be.to_numpy(getattr(rays, k)), v, rtol=0, atol=1e-10, err_msg=k)
 
 
+def test_apodized_pupil_goes_through_the_fused_launch(plugin):
+    """An apodized pupil (``optic.apodization``: the ray generator launches with intensity
+    ``apodization.get_intensity(Px, Py)``, rays/ray_generator.py:83-87).  The kernel launches with unit intensity and every
+    operation on the intensity along the path is a product or a reset to zero, so the plugin scales the intensity records
+    by the per-ray factor afterwards -- ``Optic.trace`` and ``trace_generic`` stay ONE fused launch, unpolarized and
+    polarized (Fresnel coatings: the factor also multiplies update_intensity's result), and equal the NumPy reference."""
+    P, eng, be = plugin
+    from optiland.apodization import GaussianApodization
+    from optiland.samples.objectives import DoubleGauss
+
+    rng = np.random.default_rng(8)
+    n = 40
+    Pxs, Pys = rng.uniform(-0.7, 0.7, n), rng.uniform(-0.7, 0.7, n)
+    Hys = rng.uniform(0.0, 1.0, n)
+
+    def make(polarized):
+        def f():
+            lens = DoubleGauss()
+            lens.set_apodization(GaussianApodization(sigma=0.6))
+            lens.surfaces.surfaces[3].aperture = None
+            if polarized:
+                from optiland.rays import PolarizationState
+
+                lens.surfaces.set_fresnel_coatings()
+                lens.set_polarization(PolarizationState(is_polarized=False))
+            return lens
+        return f
+
+    for polarized in (False, True):
+        for trace in (lambda lens: lens.trace(0.0, 0.7, 0.5876, 6, "hexapolar"),
+                      lambda lens: lens.trace_generic(be.array(np.zeros(n)), be.array(Hys), be.array(Pxs), be.array(Pys), 0.5876)):
+            ref_rec, ref_fin = _numpy_reference(make(polarized), trace)
+            assert ref_rec["intensity"][0].min() < 0.9 * ref_rec["intensity"][0].max()      # the pupil really is apodized
+            lens = make(polarized)()
+            n0 = len(eng.calls)
+            P.stats(reset=True)
+            rays = trace(lens)
+            assert any(c[0] == "pupil" for c in eng.calls[n0:]) and not P.stats(), (eng.calls[n0:], P.stats())
+            for k, v in ref_rec.items():
+                np.testing.assert_allclose(be.to_numpy(getattr(lens.surfaces, k)), v, rtol=1e-12, atol=1e-10, err_msg=k)
+            np.testing.assert_allclose(be.to_numpy(rays.i), ref_fin["i"], rtol=1e-12, atol=1e-14)
+
+
 def test_wavefront_analysis_uses_the_fused_epilogue(plugin):
     """f-2: Wavefront(strategy='chief_ray') under the plugin == the NumPy reference, and the full-grid trace
     went through the wavefront capability (5 values per ray, no records)."""
