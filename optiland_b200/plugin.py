@@ -996,8 +996,8 @@ def install(engine=None, alias: str | None = None) -> None:
                 return None
             if getattr(_tls, "in_reference", False) or _wants_grad(self, list(optic.surfaces.surfaces)):
                 return None
-            if optic.apodization:
-                return _fused_decline("wavefront: apodization")
+            if optic.apodization and optic.polarization != "ignore":
+                return _fused_decline("wavefront: apodization together with polarization")
             if getattr(optic.ray_tracer, "ray_aiming_config", {}).get("mode", "paraxial") != "paraxial":
                 return _fused_decline("wavefront: non-paraxial ray aiming")
             try:
@@ -1012,6 +1012,9 @@ def install(engine=None, alias: str | None = None) -> None:
             Px, Py = dist.x, dist.y
             if not (engine.accepts_tensor(Px) and engine.accepts_tensor(Py)):
                 return _fused_decline("wavefront: pupil samples not resident on a CUDA device")
+            apod = _apodization_factor(be, engine, optic, Px, Py)      # scales WavefrontData.intensity only (the OPD
+            if apod is False:                                          # does not depend on the launch intensity)
+                return _fused_decline("wavefront: apodization factor not resident on the device")
             polarized, state = _pol_state(be, optic)
             try:
                 hx, hy = float(field[0]), float(field[1])
@@ -1062,6 +1065,8 @@ def install(engine=None, alias: str | None = None) -> None:
                 kwargs = {"prt_matrix": out["p"], "E_exits": shell.get_exit_fields(optic.polarization_state)}
             else:
                 out = engine.trace_wavefront(table, Px, Py, aff, ref)
+                if apod is not None:
+                    out = dict(out, intensity=out["intensity"] * apod)
             return WavefrontData(pupil_x=out["pupil_x"], pupil_y=out["pupil_y"], pupil_z=out["pupil_z"], opd=out["opd"],
                                  intensity=out["intensity"], radius=geometry.radius, **kwargs)
 

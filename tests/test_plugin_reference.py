@@ -240,7 +240,15 @@ def test_wavefront_analysis_uses_the_fused_epilogue(plugin):
 
     from oracle.make_golden import finite_relay
 
-    for make, field, wl in ((CookeTriplet, (0.0, 0.7), 0.55), (lambda: finite_relay("object_height"), (0.0, 1.0), 0.5876)):
+    def apodized_cooke():
+        from optiland.apodization import GaussianApodization
+
+        lens = CookeTriplet()
+        lens.set_apodization(GaussianApodization(sigma=0.7))      # scales WavefrontData.intensity; same OPD
+        return lens
+
+    for make, field, wl in ((CookeTriplet, (0.0, 0.7), 0.55), (lambda: finite_relay("object_height"), (0.0, 1.0), 0.5876),
+                            (apodized_cooke, (0.0, 1.0), 0.55)):
         def run(lens):
             w = Wavefront(lens, fields=[field], wavelengths=[wl], num_rays=8, distribution="hexapolar", strategy="chief_ray")
             d = w.get_data(field, wl)
