@@ -103,7 +103,14 @@ class CudaEngine:
         if len(self.calls) > 65536:
             del self.calls[:32768]
 
+    # (class attribute so that the CPU tests can exercise ``accepts`` on host tensors: tests/test_pack_fast_path.py)
+    _on_device = staticmethod(lambda t: t.is_cuda)
+
     def accepts(self, rays) -> bool:
+        """Can this ray object be handed to the kernels as it is?  Nine 1-D arrays of one floating type on one CUDA
+        device and of one length -- except ``w``, which may be ONE value for the whole batch:
+        ``RealRays(..., wavelength=0.55)`` keeps a 1-element array that the reference's ops broadcast (real_rays.py:79;
+        the iterative ray aimer builds its rays that way, ray_aiming/iterative.py:361)."""
         import torch
 
         keys = ("x", "y", "z", "L", "M", "N", "i", "opd")
@@ -112,15 +119,13 @@ class CudaEngine:
         if any(not torch.is_tensor(t) for t in ts) or not torch.is_tensor(w):
             return False
         t0 = ts[0]
-        if not t0.is_cuda or t0.dtype not in (torch.float32, torch.float64) or t0.ndim != 1:
+        dev = self._on_device
+        if not dev(t0) or t0.dtype not in (torch.float32, torch.float64) or t0.ndim != 1:
             return False
-        # ``w`` may be ONE value for the whole batch: RealRays(..., wavelength=0.55) keeps a 1-element array that the
-        # reference's ops broadcast (real_rays.py:79; the iterative ray aimer builds its rays that way,
-        # ray_aiming/iterative.py:361)
-        if not (w.is_cuda and w.dtype == t0.dtype and w.device == t0.device and w.ndim == 1
+        if not (dev(w) and w.dtype == t0.dtype and w.device == t0.device and w.ndim == 1
                 and (w.shape == t0.shape or w.numel() == 1)):
             return False
-        return all(t.is_cuda and t.dtype == t0.dtype and t.shape == t0.shape and t.device == t0.device for t in ts)
+        return all(dev(t) and t.dtype == t0.dtype and t.shape == t0.shape and t.device == t0.device for t in ts)
 
     def device_table(self, table: T.SurfaceTable, device):
         from .trace import DeviceTable

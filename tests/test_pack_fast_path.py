@@ -92,3 +92,32 @@ def test_vectorised_parameter_packer_equals_params_to_table(name):
         sb, pb = AG._packed_from_params(c.table, p)
         assert sa.tobytes() == sb.tobytes()
         assert pa.tobytes() == pb.tobytes()
+
+
+def test_cuda_engine_accepts_rule_on_host_tensors(monkeypatch):
+    """``CudaEngine.accepts`` (which rays may be handed to the kernels) exercised without a GPU: the residency predicate
+    is swapped for one that takes host tensors.  The rule that round 2's first GPU run of the ray-aimer test uncovered --
+    ``RealRays(..., wavelength=0.55)`` keeps a 1-element ``w`` (real_rays.py:79), which used to be rejected, so every
+    trace of the iterative aimer silently went back to the reference's eager ops on a GPU -- is pinned here."""
+    from optiland_b200 import plugin as P
+
+    monkeypatch.setattr(P.CudaEngine, "_on_device", staticmethod(lambda t: True))
+    eng = P.CudaEngine()
+    n = 61
+
+    def rays(**over):
+        r = {k: torch.zeros(n, dtype=torch.float64) for k in ("x", "y", "z", "L", "M", "N", "i", "w", "opd")}
+        r.update(over)
+        return types.SimpleNamespace(**r)
+
+    assert eng.accepts(rays())
+    assert eng.accepts(rays(w=torch.tensor([0.55], dtype=torch.float64)))              # one wavelength for the batch
+    assert not eng.accepts(rays(w=torch.tensor(0.55, dtype=torch.float64)))            # 0-d: the reference makes it 1-D
+    assert not eng.accepts(rays(w=torch.zeros(7, dtype=torch.float64)))                # neither 1 nor n values
+    assert not eng.accepts(rays(w=torch.tensor([0.55], dtype=torch.float32)))          # mixed precision
+    assert not eng.accepts(rays(i=torch.zeros(1, dtype=torch.float64)))                # only w may be broadcast
+    assert not eng.accepts(rays(x=np.zeros(n)))                                        # NumPy-resident rays
+    assert not eng.accepts(rays(x=torch.zeros(n, dtype=torch.float16)))
+    assert not eng.accepts(types.SimpleNamespace(x=torch.zeros(n)))                    # ParaxialRays-like objects
+    monkeypatch.setattr(P.CudaEngine, "_on_device", staticmethod(lambda t: t.is_cuda))
+    assert not P.CudaEngine().accepts(rays())                                          # host tensors, real predicate
