@@ -311,6 +311,100 @@ def test_random_systems_adjoint_vs_finite_differences(hc, seed):
     assert checked >= 3
 
 
+@pytest.mark.parametrize("seed", range(10))
+def test_random_freeform_systems_adjoint_vs_finite_differences(hc, seed):
+    """The adjoint on random FREEFORM systems inside its scope -- Chebyshev, Forbes Q^bfs, Zernike and polynomial surfaces
+    with decenters and (30 %) tilts: the directional derivative with respect to the launch state, the pose and conic of
+    every surface, and a random direction in the space of ALL user coefficients of every freeform surface (table / basis
+    gradients mapped back by optiland_b200.autograd: Zernike N_k M_k, Chebyshev T_n expansion, Forbes A^-T) against
+    central differences of the oracle."""
+    import dataclasses
+
+    from oracle.hostcheck_api import run_backward
+    from optiland_b200 import autograd as AG
+
+    rng = np.random.default_rng(13000 + seed)
+    full = random_freeform_system(rng)
+    specs = []
+    for s in full.surfaces:
+        if s.kind in (T.GEOM_BICONIC, T.GEOM_TOROIDAL):          # outside the adjoint's scope
+            s = dataclasses.replace(s, kind=T.GEOM_STANDARD, coefficients=np.zeros(0))
+        if s.kind in T.NEWTON_KINDS:
+            s = dataclasses.replace(s, tol=1e-14)
+        specs.append(s)
+    table = T.SurfaceTable(specs, full.wavelengths)
+    n = 48
+    x, y = rng.uniform(-3.5, 3.5, n), rng.uniform(-3.5, 3.5, n)
+    L, M = rng.normal(0, 0.03, n), rng.normal(0, 0.03, n)
+    rays = dict(x=x, y=y, z=np.full(n, -3.0), L=L, M=M, N=np.sqrt(1 - L**2 - M**2), i=np.ones(n), w=np.full(n, 0.55))
+    S = table.num_surfaces
+    _, rec, st = O.trace(table, rays)
+    assert st == 0
+    live = np.isfinite(rec["x"]).all(axis=0)
+    assert live.sum() >= n // 2
+    rays = {k: v[live] for k, v in rays.items()}
+    n = int(live.sum())
+    weights = {k: rng.normal(size=(S, n)) for k in REC}
+    _, rec, _ = O.trace(table, rays)
+    gin, gpar, gtab = run_backward(hc, table, rays, rec, weights, tables=True)
+
+    def loss(tab, rr=rays):
+        _, rc, _ = O.trace(tab, rr)
+        return sum(float(np.sum(weights[k] * rc[k])) for k in REC)
+
+    dirs = {k: rng.normal(size=n) for k in ("x", "y", "L", "M")}
+    h = 1e-7
+    up = {k: (v + h * dirs[k] if k in dirs else v) for k, v in rays.items()}
+    dn = {k: (v - h * dirs[k] if k in dirs else v) for k, v in rays.items()}
+    fd_dir = (loss(table, up) - loss(table, dn)) / (2 * h)
+    an_dir = sum(float(np.sum(gin[k] * dirs[k])) for k in dirs)
+    assert an_dir == pytest.approx(fd_dir, rel=3e-4, abs=1e-7 * (abs(fd_dir) + 1)), (seed, an_dir, fd_dir)
+    gmax = float(max(np.abs(gpar).max(), np.abs(gtab).max()))
+    K = AG.table_to_coefs(table)
+    gcoef = AG.tables_to_coef_grads(table, gtab, K.shape[1]) if K is not None else None
+    kinds = set()
+    for s_, spec in enumerate(table.surfaces):
+        if spec.kind == T.GEOM_NOOP:
+            continue
+        kinds.add(spec.kind)
+        for what, slot, hh in (("tz", 2, 1e-6), ("tx", 0, 1e-6), ("conic", 4, 1e-5)):
+            if what == "conic":
+                a, b = table.replace_surface(s_, conic=spec.conic + hh), table.replace_surface(s_, conic=spec.conic - hh)
+            else:
+                d = np.zeros(3); d[0 if what == "tx" else 2] = hh
+                a, b = table.replace_surface(s_, t=spec.t + d), table.replace_surface(s_, t=spec.t - d)
+            fd = (loss(a) - loss(b)) / (2 * hh)
+            assert gpar[s_, slot] == pytest.approx(fd, rel=5e-4, abs=3e-6 * gmax), (seed, s_, spec.kind, what, gpar[s_, slot], fd)
+        # a random direction in coefficient space
+        if spec.kind == T.GEOM_FORBES_QBFS:
+            nc = len(spec.coefficients)
+            d = rng.normal(size=nc)
+            got = float(AG.forbes_coef_grads(gpar[s_, AG.GP_COEF:AG.GP_COEF + nc]) @ d)
+            mk = lambda e: table.replace_surface(s_, coefficients=spec.coefficients + e * d)  # noqa: E731
+        elif spec.kind == T.GEOM_ZERNIKE:
+            cf = spec.coefficients.reshape(-1, 4)
+            d = rng.normal(size=len(cf))
+            got = float(gcoef[s_, :len(cf)] @ d)
+            Nk = AG.zernike_norms(spec)
+
+            def mk(e, cf=cf, d=d, Nk=Nk, s_=s_):
+                c2 = cf.copy()
+                c2[:, 3] += e * d
+                c2[:, 2] += e * d * Nk
+                return table.replace_surface(s_, coefficients=c2)
+        elif spec.kind in (T.GEOM_CHEBYSHEV, T.GEOM_POLYNOMIAL):
+            C = np.atleast_2d(spec.coefficients)
+            d = rng.normal(size=C.shape)
+            got = float(gcoef[s_, :C.size] @ d.ravel())
+            mk = lambda e, C=C, d=d, s_=s_: table.replace_surface(s_, coefficients=C + e * d)  # noqa: E731
+        else:
+            continue
+        hh = 1e-6 * (1.0 if spec.kind != T.GEOM_FORBES_QBFS else 1e-1)
+        fd = (loss(mk(hh)) - loss(mk(-hh))) / (2 * hh)
+        assert got == pytest.approx(fd, rel=5e-4, abs=3e-6 * gmax), (seed, s_, spec.kind, "coefficients", got, fd)
+    assert kinds - {T.GEOM_STANDARD}
+
+
 @pytest.mark.parametrize("seed", range(20))
 def test_random_tables_survive_the_abi_layout(seed):
     """SurfaceTable -> OlbSurface[] + pool (the C ABI layout) -> SurfaceTable is the identity on random tables of
