@@ -520,7 +520,9 @@ def _live_params(surfaces, table, wavelength):
     from .autograd import GP_COEF, GP_CONIC, GP_COUNT, GP_CURV, GP_MAX_COEF, GP_N1, GP_N2, GP_R, GP_TX
 
     def scalar(v, like):
-        t = v if torch.is_tensor(v) else torch.as_tensor(float(v))
+        # (dtype given: torch.as_tensor(<Python float>) would be float32 -- a parameter set as a plain number,
+        # e.g. by optic.updater.set_radius(22.89, 1), must not lose 8 digits on its way into the fp64 table)
+        t = v if torch.is_tensor(v) else torch.as_tensor(float(v), dtype=torch.float64)
         return t.to(dtype=torch.float64, device=like.device).reshape(())
 
     like = None
@@ -624,7 +626,9 @@ def _live_coefs(surfaces, table):
             r = surf.geometry.zernike.coeffs
         elif spec.kind in (T.GEOM_POLYNOMIAL, T.GEOM_CHEBYSHEV):
             c = surf.geometry.coefficients
-            r = c if torch.is_tensor(c) else torch.stack([torch.stack([torch.as_tensor(v) for v in row]) for row in c])
+            r = c if torch.is_tensor(c) else torch.stack([torch.stack([
+                v.to(torch.float64) if torch.is_tensor(v) else torch.as_tensor(float(v), dtype=torch.float64) for v in row])
+                for row in c])
         if r is not None:
             r = (r if torch.is_tensor(r) else torch.as_tensor(np.asarray(r, dtype=np.float64))).reshape(-1).to(torch.float64)
             K = max(K, r.numel())
