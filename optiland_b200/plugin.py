@@ -42,6 +42,37 @@ _PACK_ERRORS = (UnsupportedSurface, ValueError, TypeError, OlbError)
 _REC_ATTR = (("x", "x"), ("y", "y"), ("z", "z"), ("L", "L"), ("M", "M"), ("N", "N"),
              ("intensity", "intensity"), ("opd", "opd"))
 _tls = threading.local()
+
+
+class _FrozenTables:
+    """Context in which the optic is known not to change -- one ``aim_rays`` call of the iterative / robust ray aimer
+    (rays/ray_aiming/iterative.py, robust.py: hundreds to thousands of subset traces of the SAME system while only the
+    launch parameters move; the robust aimer of ``WideAngle170FOV`` issues ~1500 per ``Optic.trace``).  Inside it a packed
+    table is built once per (surfaces, range, wavelengths) instead of once per trace: packing the live objects (~1 ms) is
+    what such a trace costs on a GPU, the kernel takes ~20 us.  Re-entrant; the outermost exit drops everything."""
+
+    def __enter__(self):
+        self.outer = getattr(_tls, "frozen", None)
+        if self.outer is None:
+            _tls.frozen = {}
+        return self
+
+    def __exit__(self, *exc):
+        if self.outer is None:
+            _tls.frozen = None
+        return False
+
+
+def _frozen(key, owner, build):
+    """``build()`` memoised on ``key`` while a _FrozenTables context is active (``owner`` is kept alive with the entry so
+    that an ``id()`` in the key cannot be recycled)."""
+    fr = getattr(_tls, "frozen", None)
+    if fr is None:
+        return build()
+    hit = fr.get(key)
+    if hit is None:
+        hit = fr[key] = (owner, build())
+    return hit[1]
 _state: dict = {"installed": False, "declines": {}}
 
 
@@ -800,8 +831,11 @@ def install(engine=None, alias: str | None = None) -> None:
                 return False
 
             def build(wl):
-                full = pack_surface_group(surface_group, wl)
-                return T.SurfaceTable(full.surfaces[start:stop], full.wavelengths)
+                def pack():
+                    full = pack_surface_group(surface_group, wl)
+                    return T.SurfaceTable(full.surfaces[start:stop], full.wavelengths)
+
+                return _frozen(("group", id(surface_group), start, stop, tuple(float(w) for w in wl)), surface_group, pack)
 
             return _try_trace(self, surfaces, rays, build)
 
@@ -1083,7 +1117,8 @@ def install(engine=None, alias: str | None = None) -> None:
             if type(surface).__name__ not in ("Surface", "ImageSurface"):
                 return False
             return _try_trace(self, [surface], rays,
-                              lambda wl: T.SurfaceTable([pack_surface(surface, wl)], wl))
+                              lambda wl: _frozen(("surface", id(surface), tuple(float(w) for w in wl)), surface,
+                                                 lambda: T.SurfaceTable([pack_surface(surface, wl)], wl)))
 
     registry = be.__getattr__.__globals__["_backends"]  # same hook as tests/test_backend.py:79-85
     old = registry.get("torch")
@@ -1164,6 +1199,19 @@ def install(engine=None, alias: str | None = None) -> None:
 
     IterativeRayAimer._trace_subset = aimer_trace_subset
 
+    from optiland.rays.ray_aiming.robust import RobustRayAimer
+
+    orig_aim = {cls: cls.aim_rays for cls in (IterativeRayAimer, RobustRayAimer)}
+
+    def _make_aim(orig):
+        def aim_rays(self, *args, **kwargs):
+            with _FrozenTables():              # the optic does not change inside one aiming call
+                return orig(self, *args, **kwargs)
+        return aim_rays
+
+    for cls, orig in orig_aim.items():
+        cls.aim_rays = _make_aim(orig)
+
     # f-3: the Huygens-Fresnel summation strategy of the torch backend (psf/huygens_fresnel_strategies.py:183-273)
     from optiland.psf.huygens_fresnel_strategies import TorchSummation
 
@@ -1233,7 +1281,7 @@ def install(engine=None, alias: str | None = None) -> None:
     RealRayTracer.trace_generic = tracer_generic
     _state.update(installed=True, orig_group_trace=orig_group_trace, orig_surface_trace=orig_surface_trace,
                   orig_tracer_trace=orig_tracer_trace, orig_tracer_generic=orig_tracer_generic, orig_hf_compute=orig_hf_compute, orig_chief_compute=orig_chief_compute,
-                  old_backend=old, alias=alias, fuse_launch=True, fuse_wavefront=True, fuse_spot=True, fuse_fft_psf=True, fuse_aimer=True, orig_trace_subset=orig_trace_subset, saved_spot=saved_spot, saved_fft=saved_fft,
+                  old_backend=old, alias=alias, fuse_launch=True, fuse_wavefront=True, fuse_spot=True, fuse_fft_psf=True, fuse_aimer=True, orig_trace_subset=orig_trace_subset, orig_aim=orig_aim, saved_spot=saved_spot, saved_fft=saved_fft,
                   orig_position=orig_position, fast_positions=True)
 
 
@@ -1265,6 +1313,8 @@ def uninstall() -> None:
         from optiland.rays.ray_aiming.iterative import IterativeRayAimer
 
         IterativeRayAimer._trace_subset = _state["orig_trace_subset"]
+    for cls, orig in (_state.get("orig_aim") or {}).items():
+        cls.aim_rays = orig
     if _state.get("saved_fft") is not None:
         from . import fftpsf as _fftpsf
 
