@@ -73,6 +73,8 @@ def _frozen(key, owner, build):
     if hit is None:
         hit = fr[key] = (owner, build())
     return hit[1]
+
+
 _state: dict = {"installed": False, "declines": {}}
 
 
@@ -793,10 +795,11 @@ def _try_trace(backend, surfaces, rays, table_builder) -> bool:
             if rec is None:
                 return _decline("gradients wanted: a surface / table outside the adjoint's scope")
         else:
-            params = _live_params(surfaces, table, float(wl[0]))
+            # (inside one aiming call the live tensors do not change either: one parameter block, one graph node)
+            params = _frozen(("params", id(table)), table, lambda: _live_params(surfaces, table, float(wl[0])))
             if params is None:
                 return _decline("gradients wanted: a surface outside the adjoint's scope")
-            coefs = _live_coefs(surfaces, table)
+            coefs = _frozen(("coefs", id(table)), table, lambda: _live_coefs(surfaces, table))
             rec = engine.trace_grad(table, params, rays, coefs) if coefs is not None else engine.trace_grad(table, params, rays)
             if rec is None:
                 return _decline("gradients wanted: table outside the adjoint's scope")
