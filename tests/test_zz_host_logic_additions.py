@@ -225,3 +225,65 @@ def test_imported_zemax_systems(plugin, name):
         for k, v in w.items():
             np.testing.assert_allclose(be.to_numpy(getattr(lens.surfaces, k)), v, rtol=0, atol=1e-11 * scale + 1e-10, err_msg=f"{name} {k}")
     assert len(eng.calls) - n0 == len(want) and not P.stats(), (eng.calls[n0:], P.stats())
+
+
+FIELD_TYPES = ("angle", "object_height", "paraxial_image_height", "real_image_height")
+APERTURES = {"EPD": 8.0, "imageFNO": 6.0, "objectNA": 0.06, "float_by_stop_size": 3.5}
+DISTRIBUTIONS = (("hexapolar", 4), ("uniform", 7), ("line_x", 9), ("line_y", 9), ("positive_line_x", 5),
+                 ("positive_line_y", 5), ("cross", 7), ("ring", 8))
+
+
+@pytest.mark.parametrize("finite", [False, True], ids=["infinite_object", "finite_object"])
+@pytest.mark.parametrize("field_type", FIELD_TYPES)
+def test_every_field_type_aperture_type_and_pupil_distribution(plugin, finite, field_type):
+    """The launch side of ``Optic.trace`` across the reference's options: 2 conjugates x 4 field types
+    (fields/field_types/*.py) x 4 system-aperture types (aperture/*.py) x 8 deterministic pupil distributions
+    (distribution.py:415-441; 'random' / 'sobol' draw from different generators on the NumPy and torch backends) on a
+    doublet -- records under the plugin == the NumPy reference.  Angle and object-height fields go through the in-kernel
+    launch generation; the image-height field types (their launch needs the reference's solve) decline it and run on the
+    SurfaceGroup capability -- no other decline is allowed."""
+    P, eng, be = plugin
+    from optiland import optic as _optic
+
+    if field_type == "object_height" and not finite:
+        pytest.skip("the reference raises: an object-height field needs a finite object")
+
+    def build(ap_type):
+        lens = _optic.Optic()
+        lens.surfaces.add(index=0, radius=be.inf, thickness=(60.0 if finite else be.inf))
+        lens.surfaces.add(index=1, radius=32.0, thickness=5.0, material="N-BK7")
+        lens.surfaces.add(index=2, radius=-48.0, thickness=2.0, is_stop=True)
+        lens.surfaces.add(index=3, radius=-30.0, thickness=2.5, material="SF5")
+        lens.surfaces.add(index=4, radius=-90.0, thickness=55.0)
+        lens.surfaces.add(index=5)
+        lens.set_aperture(aperture_type=ap_type, value=APERTURES[ap_type])
+        lens.fields.set_type(field_type=field_type)
+        lens.fields.add(y=0.0)
+        lens.fields.add(y={"angle": 4.0, "object_height": 3.0, "paraxial_image_height": 2.5, "real_image_height": 2.5}[field_type])
+        lens.wavelengths.add(value=0.55, is_primary=True)
+        return lens
+
+    keys = ("x", "y", "z", "L", "M", "N", "opd", "intensity")
+    for ap_type in APERTURES:
+        be.set_backend("numpy")
+        ref = build(ap_type)
+        want = {}
+        for dn, nr in DISTRIBUTIONS:
+            ref.trace(0.0, 1.0, 0.55, nr, dn)
+            want[dn] = {k: np.array(getattr(ref.surfaces, k)) for k in keys}
+        be.set_backend("torch")
+        lens = build(ap_type)
+        P.stats(reset=True)
+        n0 = len(eng.calls)
+        for dn, nr in DISTRIBUTIONS:
+            lens.trace(0.0, 1.0, 0.55, nr, dn)
+            for k, v in want[dn].items():
+                g = be.to_numpy(getattr(lens.surfaces, k))
+                assert g.shape == v.shape and np.array_equal(np.isnan(g), np.isnan(v)), (ap_type, dn, k)
+                np.testing.assert_allclose(g, v, rtol=0, atol=1e-10, err_msg=f"{ap_type} {dn} {k}")
+        fused = [c for c in eng.calls[n0:] if c[0] == "pupil"]
+        if field_type in ("angle", "object_height"):
+            assert len(fused) == len(DISTRIBUTIONS) and not P.stats(), (ap_type, P.stats())
+        else:
+            assert len(eng.calls) - n0 >= len(DISTRIBUTIONS)
+            assert all(k.startswith("fused launch: unsupported: launch_scalars: field type") for k in P.stats()), P.stats()
