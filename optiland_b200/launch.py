@@ -69,6 +69,9 @@ def pupil_affine(sc: dict) -> dict:
     if mode == 1:        # paraxial.py:90-96: aim at the paraxial entrance pupil
         return {"origin0": o0, "origin_scale": (0.0, 0.0), "target0": (0.0, 0.0, sc["EPL"]),
                 "target_scale": (sc["EPD"] * sc["vx"] / 2, sc["EPD"] * sc["vy"] / 2), "intensity": 1.0}
+    if mode == 3:        # infinite object, image-height field types: the origin slides with the pupil point (mode 0's form)
+        return {"origin0": o0, "origin_scale": (sc["EPD"] / 2 * sc["vx"], sc["EPD"] / 2 * sc["vy"]), "target0": (0.0, 0.0, sc["EPL"]),
+                "target_scale": (sc["EPD"] * sc["vx"] / 2, sc["EPD"] * sc["vy"] / 2), "intensity": 1.0}
     if mode == 2:        # paraxial.py:82-88: telecentric object space
         sin = sc["sin"]
         z1 = math.sqrt(1 - sin ** 2) / sin + sc["z0"]
@@ -117,6 +120,8 @@ def pupil_affine_fields(sc: dict, Hx, Hy) -> dict:
     (they would make the pupil scale field-dependent).  ``Hx``, ``Hy``: arrays of the kernel's element type."""
     if sc["vx"] != 1.0 or sc["vy"] != 1.0:
         raise ValueError("per-ray fields need an optic without vignetting factors")
+    if int(sc.get("mode", 0)) == 3 or float(sc.get("field_kind", 2.0)) == 0.0:
+        raise ValueError("per-ray fields need an angle or object-height field (image-height fields: one field point per launch)")
     base = pupil_affine({**sc, "Hx": 0.0, "Hy": 0.0} if int(sc.get("mode", 0)) == 0 else sc)
     mode = int(sc.get("mode", 0))
     aff = dict(base)

@@ -343,7 +343,10 @@ def launch_scalars(optic, Hx: float, Hy: float) -> dict:
         pupil point.
     mode 1: finite object (angle or object-height field): every ray starts at the field's object point
         (x0, y0, z0) and aims at the paraxial entrance pupil.
-    mode 2: finite object, object-space telecentric: target = origin + (Px vx, Py vy, cot(asin NA))."""
+    mode 2: finite object, object-space telecentric: target = origin + (Px vx, Py vy, cot(asin NA)).
+    mode 3: infinite object, an image-height field type: like mode 0 with the pupil-centre origin (x0, y0, z0) taken
+        from the reference's own field definition; finite objects of those field types are mode 1.  ``field_kind`` 0
+        marks them: one field point per launch only (``launch.pupil_affine_fields`` refuses per-ray field points)."""
     import optiland.backend as be  # only called where the reference is importable
 
     fd = optic.fields.field_definition
@@ -365,6 +368,25 @@ def launch_scalars(optic, Hx: float, Hy: float) -> dict:
             "Hx": float(Hx),
             "Hy": float(Hy),
         }
+    if name in ("ParaxialImageHeightField", "RealImageHeightField"):
+        # Image-height field types (fields/field_types/paraxial_image_height.py, real_image_height.py): the object angle /
+        # height that lands on the requested image height comes from the reference's own code -- a paraxial unit-ray
+        # scaling, or a real chief-ray solve (which itself traces through the capability) -- asked for ONE probe pair
+        # of pupil points; the launch then has the same closed form as an angle / object-height field: the origin
+        # slides with the pupil point by (EPD/2 vx, EPD/2 vy) for an infinite object and is fixed for a finite one.
+        # (The reference solves per RAY, for N copies of the same field point.)
+        if optic.obj_space_telecentric:
+            raise UnsupportedSurface(f"launch_scalars: telecentric object space with field type {name}")
+        pr = be.array([0.0, 1.0])
+        xo, yo, zo = (_arr(v).reshape(-1) for v in fd.get_ray_origins(optic, be.array([float(Hx)] * 2), be.array([float(Hy)] * 2), pr, pr, vx, vy))
+        EPL, EPD = _f(optic.paraxial.EPL()), _f(optic.paraxial.EPD())
+        sx, sy = (EPD / 2 * vx, EPD / 2 * vy) if infinite else (0.0, 0.0)
+        tol = 1e-9 * (1.0 + abs(EPD))
+        if not (abs(xo[1] - xo[0] - sx) <= tol and abs(yo[1] - yo[0] - sy) <= tol and abs(zo[1] - zo[0]) <= tol
+                and all(math.isfinite(float(v)) for v in (xo[0], yo[0], zo[0]))):
+            raise UnsupportedSurface(f"launch_scalars: field type {name}: the origin is not the expected function of the pupil point")
+        return {"mode": 3.0 if infinite else 1.0, "x0": float(xo[0]), "y0": float(yo[0]), "z0": float(zo[0]), "EPL": EPL, "EPD": EPD,
+                "vx": vx, "vy": vy, "Hx": float(Hx), "Hy": float(Hy), "max_field": _f(optic.fields.max_field), "field_kind": 0.0}
     if infinite or name not in ("AngleField", "ObjectHeightField"):
         raise UnsupportedSurface(f"launch_scalars: field type {name} with an {'in' if infinite else ''}finite object")
     # finite object: the origin does not depend on the pupil point; ask the reference's own field definition
