@@ -122,6 +122,8 @@ class _Prefetch:
                     continue
                 for wl in self.wavelengths:
                     for what in ("n", "k"):
+                        if catalogue_value(mat, what, wl) is not None:
+                            continue             # a catalogue glass already asked at this wavelength: nothing to fetch
                         try:
                             # the reference caches these per wavelength (materials/base.py:98-149), so the
                             # later call in _index_table returns the same object
@@ -189,19 +191,48 @@ def pack_aperture(ap) -> np.ndarray:
     raise UnsupportedSurface(f"aperture type {name}")
 
 
+# Catalogue glasses (materials/material.py, material_file.py): n(lambda), k(lambda) are functions of the data file alone --
+# nothing an optimiser or a user can change on the object -- so their values at a wavelength are memoised ON the material
+# object.  The reference's own per-wavelength cache (materials/base.py:98-149) does this job only while be.grad_mode is off:
+# with it on every result "requires grad" (be.array(wavelength) does) and is recomputed -- one dispersion formula, ~10
+# element-wise ops, per surface side per call, which on a CUDA device made packing the dominant cost of a small
+# differentiable step.  Other material classes (IdealMaterial, AbbeMaterial, ...: parameters an optimiser may drive) are
+# always asked.
+_CATALOGUE_MATERIALS = ("Material", "MaterialFile")
+
+
+def catalogue_value(material, what: str, wl: float):
+    """Memoised n / k of a catalogue glass at ``wl`` (float), or None for any other material class / a memo miss."""
+    if _cls(material) not in _CATALOGUE_MATERIALS:
+        return None
+    memo = material.__dict__.get("_olb_index_memo")
+    return None if memo is None else memo.get((what, float(wl)))
+
+
+def _remember(material, what: str, wl: float, value: float) -> None:
+    if _cls(material) in _CATALOGUE_MATERIALS:
+        material.__dict__.setdefault("_olb_index_memo", {})[(what, float(wl))] = float(value)
+
+
 def _index_table(material, wavelengths, what: str) -> np.ndarray:
     fn = getattr(material, what)
     out = np.empty(len(wavelengths), dtype=np.float64)
     pre = getattr(_tls, "resolved", None)
     for j, wl in enumerate(wavelengths):
+        known = catalogue_value(material, what, wl)
+        if known is not None:
+            out[j] = known
+            continue
         v = fn(float(wl))
         if pre is not None and id(v) in pre:
             out[j] = pre[id(v)]
+            _remember(material, what, wl, out[j])
             continue
         v = _arr(v)
         if np.iscomplexobj(v):
             raise UnsupportedSurface("complex refractive index")
         out[j] = float(v.reshape(-1)[0])
+        _remember(material, what, wl, out[j])
     return out
 
 

@@ -551,6 +551,7 @@ def _live_params(surfaces, table, wavelength):
     import torch
 
     from .autograd import GP_COEF, GP_CONIC, GP_COUNT, GP_CURV, GP_MAX_COEF, GP_N1, GP_N2, GP_R, GP_TX
+    from .pack import catalogue_value
 
     def scalar(v, like):
         # (dtype given: torch.as_tensor(<Python float>) would be float32 -- a parameter set as a plain number,
@@ -620,8 +621,11 @@ def _live_params(surfaces, table, wavelength):
             if spec.kind != T.GEOM_PLANE:
                 vals[GP_CONIC] = scalar(g.k, like)
             flat_r.append(scalar(g.radius, like) if curved else one)
-            vals[GP_N1] = scalar(surf.material_pre.n(wavelength), like)
-            vals[GP_N2] = scalar(surf.material_post.n(wavelength), like)
+            # (a catalogue glass is a constant: the packed table already holds its index at this wavelength -- asking the
+            # material again would re-evaluate its dispersion formula, pack.catalogue_value)
+            for slot, mat, packed in ((GP_N1, surf.material_pre, spec.n1), (GP_N2, surf.material_post, spec.n2)):
+                known = catalogue_value(mat, "n", wavelength)
+                vals[slot] = scalar(float(packed[0]) if known is not None and len(packed) == 1 else mat.n(wavelength), like)
             if spec.kind in (T.GEOM_EVEN_ASPHERE, T.GEOM_ODD_ASPHERE):
                 if len(g.coefficients) > GP_MAX_COEF:
                     return None
