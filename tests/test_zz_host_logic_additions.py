@@ -291,3 +291,56 @@ def test_every_field_type_aperture_type_and_pupil_distribution(plugin, finite, f
             # point -> the launch scalars decline and the SurfaceGroup capability carries the trace
             assert len(eng.calls) - n0 >= len(DISTRIBUTIONS)
             assert all(k.startswith("fused launch: unsupported: launch_scalars: field type") for k in P.stats()), P.stats()
+
+
+def test_catalogue_glass_indices_are_memoised_and_other_materials_are_not():
+    """``pack.catalogue_value``: n / k of a catalogue glass (``Material`` / ``MaterialFile``: functions of the data file
+    alone) are remembered on the material object, so that packing under ``be.grad_mode`` -- where the reference's own
+    per-wavelength cache is bypassed (materials/base.py:118-121) -- does not re-evaluate a dispersion formula per surface
+    side per call; the values are those a fresh evaluation gives; ``IdealMaterial`` / ``AbbeMaterial`` (parameters an
+    optimiser may drive) are asked every time."""
+    from oracle.ref_import import import_reference
+
+    import_reference()
+    import optiland.backend as be
+    from optiland.materials import AbbeMaterial, IdealMaterial, Material
+    from optiland.samples.objectives import CookeTriplet
+
+    from optiland_b200 import pack as PK
+
+    be.set_backend("torch")
+    be.set_precision("float64")
+    be.grad_mode.enable()
+    try:
+        lens = CookeTriplet()
+        glass = lens.surfaces.surfaces[1].material_post
+        assert type(glass).__name__ in PK._CATALOGUE_MATERIALS
+        calls = {"n": 0}
+        orig = type(glass)._calculate_n
+
+        def counted(self, *a, **k):
+            calls["n"] += 1
+            return orig(self, *a, **k)
+
+        type(glass)._calculate_n = counted
+        try:
+            t1 = PK.pack_surface_group(lens.surfaces, np.array([0.55]))
+            first = calls["n"]
+            t2 = PK.pack_surface_group(lens.surfaces, np.array([0.55]))
+            assert first > 0 and calls["n"] == first          # the second pack evaluated no dispersion formula
+            t3 = PK.pack_surface_group(lens.surfaces, np.array([0.48, 0.55]))
+            assert calls["n"] > first                          # a new wavelength is asked (once)
+        finally:
+            type(glass)._calculate_n = orig
+        s1, p1 = t1.pack()
+        s2, p2 = t2.pack()
+        assert s1.tobytes() == s2.tobytes() and p1.tobytes() == p2.tobytes()
+        fresh = float(Material(glass.name).n(0.55)) if hasattr(glass, "name") else None
+        if fresh is not None:
+            assert PK.catalogue_value(glass, "n", 0.55) == fresh == t3.surfaces[1].n2[1]
+        for other in (IdealMaterial(n=1.5), AbbeMaterial(1.6, 50.0, model="polynomial")):
+            PK._index_table(other, [0.55], "n")
+            assert PK.catalogue_value(other, "n", 0.55) is None and "_olb_index_memo" not in other.__dict__
+    finally:
+        be.grad_mode.disable()
+        be.set_backend("numpy")
