@@ -1270,6 +1270,43 @@ def install(engine=None, alias: str | None = None) -> None:
 
     CoordinateSystem.position_in_gcs = property(_position_in_gcs)
 
+    # Inside ONE ``RayGenerator.generate_rays`` call the optic does not change, yet the reference recomputes the entrance
+    # pupil diameter three times and its location twice -- each a paraxial trace in Python -- and the surface positions a
+    # dozen times (ray_aiming/paraxial.py:33-106, fields/field_types/angle.py:17-120): 40 % of a small differentiable
+    # step on the CPU, more on a GPU where every one of those element-wise ops is a kernel launch.  For the duration of
+    # that call the three are memoised per object -- the SAME tensors are handed out again, so values and autograd
+    # connectivity are exactly the reference's.
+    from optiland.paraxial import Paraxial
+    from optiland.rays.ray_generator import RayGenerator
+
+    orig_generate = RayGenerator.generate_rays
+    orig_epl, orig_epd = Paraxial.EPL, Paraxial.EPD
+    orig_positions = SurfaceGroup.positions
+
+    def _memo(key, owner, compute):
+        memo = getattr(_tls, "paraxial_memo", None)
+        if memo is None or not _state.get("memo_paraxial", True):
+            return compute()
+        hit = memo.get(key)
+        if hit is None:
+            hit = memo[key] = (owner, compute())
+        return hit[1]
+
+    def generate_rays(self, *args, **kwargs):
+        outer = getattr(_tls, "paraxial_memo", None)
+        if outer is None:
+            _tls.paraxial_memo = {}
+        try:
+            return orig_generate(self, *args, **kwargs)
+        finally:
+            if outer is None:
+                _tls.paraxial_memo = None
+
+    RayGenerator.generate_rays = generate_rays
+    Paraxial.EPL = lambda self: _memo(("EPL", id(self)), self, lambda: orig_epl(self))
+    Paraxial.EPD = lambda self: _memo(("EPD", id(self)), self, lambda: orig_epd(self))
+    SurfaceGroup.positions = property(lambda self: _memo(("positions", id(self)), self, lambda: orig_positions.fget(self)))
+
     # f-2: spot statistics from the moments epilogue (RayOperand.rms_spot_size, SpotDiagram.rms_spot_radius / centroid)
     from . import spot as _spot
 
@@ -1289,7 +1326,8 @@ def install(engine=None, alias: str | None = None) -> None:
     _state.update(installed=True, orig_group_trace=orig_group_trace, orig_surface_trace=orig_surface_trace,
                   orig_tracer_trace=orig_tracer_trace, orig_tracer_generic=orig_tracer_generic, orig_hf_compute=orig_hf_compute, orig_chief_compute=orig_chief_compute,
                   old_backend=old, alias=alias, fuse_launch=True, fuse_wavefront=True, fuse_spot=True, fuse_fft_psf=True, fuse_aimer=True, orig_trace_subset=orig_trace_subset, orig_aim=orig_aim, saved_spot=saved_spot, saved_fft=saved_fft,
-                  orig_position=orig_position, fast_positions=True)
+                  orig_position=orig_position, fast_positions=True, memo_paraxial=True,
+                  orig_paraxial=(orig_generate, orig_epl, orig_epd, orig_positions))
 
 
 def uninstall() -> None:
@@ -1330,6 +1368,11 @@ def uninstall() -> None:
         from optiland.coordinate_system import CoordinateSystem
 
         CoordinateSystem.position_in_gcs = _state["orig_position"]
+    if _state.get("orig_paraxial") is not None:
+        from optiland.paraxial import Paraxial
+        from optiland.rays.ray_generator import RayGenerator
+
+        RayGenerator.generate_rays, Paraxial.EPL, Paraxial.EPD, SurfaceGroup.positions = _state["orig_paraxial"]
     if _state.get("old_backend") is not None:
         registry["torch"] = _state["old_backend"]
     if _state.get("alias"):
