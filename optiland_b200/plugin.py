@@ -63,6 +63,23 @@ class _FrozenTables:
         return False
 
 
+class _ParaxialMemo:
+    """For the duration of a call in which the optic does not change (``RayGenerator.generate_rays``, the launch scalars of
+    a fused launch) ``Paraxial.EPL / EPD`` and ``SurfaceGroup.positions`` hand out the tensors they computed first
+    (installed by ``install``); re-entrant, the outermost exit drops the memo."""
+
+    def __enter__(self):
+        self.outer = getattr(_tls, "paraxial_memo", None)
+        if self.outer is None:
+            _tls.paraxial_memo = {}
+        return self
+
+    def __exit__(self, *exc):
+        if self.outer is None:
+            _tls.paraxial_memo = None
+        return False
+
+
 def _frozen(key, owner, build):
     """``build()`` memoised on ``key`` while a _FrozenTables context is active (``owner`` is kept alive with the entry so
     that an ``id()`` in the key cannot be recycled)."""
@@ -377,7 +394,8 @@ def _launch_scalars_cached(be, optic, table, hx: float, hy: float) -> dict:
         return launch_scalars(optic, hx, hy)
     sc = _launch_cache.get(key)
     if sc is None:
-        sc = launch_scalars(optic, hx, hy)
+        with _ParaxialMemo():          # EPL / EPD / offset each walk the positions and trace paraxially: once per call
+            sc = launch_scalars(optic, hx, hy)
         _launch_cache[key] = sc
         while len(_launch_cache) > 256:
             _launch_cache.popitem(last=False)
@@ -1293,14 +1311,8 @@ def install(engine=None, alias: str | None = None) -> None:
         return hit[1]
 
     def generate_rays(self, *args, **kwargs):
-        outer = getattr(_tls, "paraxial_memo", None)
-        if outer is None:
-            _tls.paraxial_memo = {}
-        try:
+        with _ParaxialMemo():
             return orig_generate(self, *args, **kwargs)
-        finally:
-            if outer is None:
-                _tls.paraxial_memo = None
 
     RayGenerator.generate_rays = generate_rays
     Paraxial.EPL = lambda self: _memo(("EPL", id(self)), self, lambda: orig_epl(self))
