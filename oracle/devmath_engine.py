@@ -1,0 +1,69 @@
+"""TEST INFRASTRUCTURE ONLY -- a second stand-in for optiland_b200.plugin.CudaEngine on boxes without a GPU: the
+forward trace runs the DEVICE ARITHMETIC itself (csrc/olb_math.cuh + olb_prep.h compiled for the host,
+tests/hostcheck) on the packed table the product would upload (``_lib.HostTable``), where ``OracleEngine`` evaluates
+the NumPy restatement of the reference.  With it a CPU test chains: live reference objects -> ``plugin`` / ``pack`` ->
+prepared table -> the kernel's per-ray code, and compares with the unmodified reference -- everything of the product
+path but the CUDA launch wrapper.  Epilogues (moments, wavefront, PSF) and the adjoint are inherited from
+``OracleEngine`` (their device arithmetic has host instantiations of its own there)."""
+import numpy as np
+
+from oracle.oracle_engine import OracleEngine
+
+_KEYS = ("x", "y", "z", "L", "M", "N", "i", "w", "opd")
+
+
+def _zernike_error(status: int):
+    if status:
+        raise ValueError("Zernike coordinates must be normalized to [-1, 1].")
+
+
+class DeviceMathEngine(OracleEngine):
+    """TEST-ONLY: ``trace`` / ``trace_pupil`` through the host instantiation of the device math."""
+
+    def trace(self, table, rays, first, last):
+        import torch
+
+        from oracle.hostcheck_api import load, run_hostcheck
+
+        self.calls.append((table.num_surfaces, int(rays.x.numel())))
+        n = int(rays.x.numel())
+        inp = {k: np.broadcast_to(getattr(rays, k).detach().double().numpy(), (n,)).copy() for k in _KEYS}
+        polarized = type(rays).__name__ == "PolarizedRays"
+        pmat = rays.p.detach().numpy().astype(np.complex128) if polarized else None
+        out, rec, status = run_hostcheck(load(), table, inp, np.float64, first, last, pmat=pmat)
+        _zernike_error(status)
+        if polarized:
+            rays.p = torch.from_numpy(out["p"])
+        dt = rays.x.dtype
+        for k in ("x", "y", "z", "L", "M", "N", "i", "opd"):
+            setattr(rays, k, torch.from_numpy(out[k]).to(dt))
+        return {k: torch.from_numpy(v).to(dt) for k, v in rec.items()}
+
+    def trace_pupil(self, table, Px, Py, affine, wavelength=None, polarization=False):
+        import torch
+
+        from oracle import trace_oracle as O
+        from oracle.hostcheck_api import load, run_hostcheck
+        from optiland_b200.launch import launch_from_affine
+
+        self.calls.append(("pupil", table.num_surfaces, int(Px.numel())))
+        px, py = Px.detach().double().numpy(), Py.detach().double().numpy()
+        aff = dict(affine)
+        if aff.get("fields") is not None:
+            aff["fields"] = tuple(t.detach().double().numpy() for t in aff["fields"])
+        x, y, z, L, M, N = launch_from_affine(px, py, aff)
+        w = wavelength.detach().double().numpy() if wavelength is not None else np.full_like(px, table.wavelengths[0])
+        i0 = np.full_like(px, affine.get("intensity", 1.0))
+        inp = dict(x=x, y=y, z=z, L=L, M=M, N=N, i=i0, w=w)
+        pmat = None if polarization is False else np.tile(np.eye(3, dtype=np.complex128), (px.size, 1, 1))
+        out, rec, status = run_hostcheck(load(), table, inp, np.float64, pmat=pmat)
+        _zernike_error(status)
+        res = {k: torch.from_numpy(v).to(Px.dtype) for k, v in rec.items()}
+        if polarization is False:
+            return res
+        res["p"] = torch.from_numpy(out["p"]).to(torch.complex128 if Px.dtype == torch.float64 else torch.complex64)
+        if polarization == "matrix":
+            res["i_pol"] = res["intensity"][-1]
+        else:
+            res["i_pol"] = torch.from_numpy(O.polarized_intensity(out["p"], L, M, N, i0, polarization)).to(Px.dtype)
+        return res

@@ -1,0 +1,194 @@
+"""Randomised drop-in test with LIVE reference objects: random sequential systems are built through the reference's own
+API (``Optic.surfaces.add`` with every geometry family of the path: standard / conic, even and odd asphere, polynomial,
+Chebyshev, Zernike in its three orderings, biconic, toroidal, Forbes Q^bfs; catalogue glasses, decenters and tilts,
+radial apertures, finite and infinite conjugates), traced by the UNMODIFIED reference on its NumPy backend, and then by
+the same ``Optic.trace`` call with the plugin installed:
+
+``[oracle]``   CPU, test-only NumPy-oracle engine: pins the host logic (pack, launch scalars, record hand-back);
+``[devmath]``  CPU, the DEVICE ARITHMETIC compiled for the host (``oracle/devmath_engine.py``: olb_math.cuh + olb_prep.h
+               on the packed table the product uploads): everything of the product path but the CUDA launch wrapper;
+``[cuda]``     the product engine on the B200 (written after the round's GPU budget had been spent: last-sorted file).
+
+Every per-surface record (x, y, z, L, M, N, opd, intensity) of both fields must equal the reference's, NaN pattern
+included; the capability must have carried every trace as one fused launch, with no decline."""
+import numpy as np
+import pytest
+
+from oracle.ref_import import reference_available
+
+pytestmark = pytest.mark.skipif(not reference_available(), reason="reference not present on this box")
+
+GLASSES = ["N-BK7", "SF5", "N-SF11", "N-LAK9", "F2"]
+KINDS = ["standard", "conic", "even_asphere", "odd_asphere", "polynomial", "chebyshev", "zernike", "biconic", "toroidal",
+         "forbes_qbfs"]
+
+
+@pytest.fixture(params=["oracle", "devmath", pytest.param("cuda", marks=pytest.mark.gpu)])
+def live(request):
+    from oracle.ref_import import import_reference
+
+    import_reference()
+    import optiland.backend as be
+
+    from optiland_b200 import plugin as P
+
+    if request.param == "cuda":
+        eng = P.CudaEngine()
+    elif request.param == "devmath":
+        from oracle.devmath_engine import DeviceMathEngine
+
+        eng = DeviceMathEngine()
+    else:
+        from oracle.oracle_engine import OracleEngine
+
+        eng = OracleEngine()
+    yield P, eng, be, request.param
+    if P._state.get("installed"):
+        P.uninstall()
+    if request.param == "cuda":
+        be.set_device("cpu")
+    be.set_backend("numpy")
+
+
+def _surface(rng, radius):
+    kind = str(rng.choice(KINDS))
+    if kind == "standard":
+        kw = dict(radius=radius)
+    elif kind == "conic":
+        kw = dict(radius=radius, conic=float(rng.uniform(-0.8, 0.4)))
+    elif kind == "even_asphere":
+        kw = dict(radius=radius, conic=float(rng.uniform(-0.5, 0.2)), surface_type="even_asphere",
+                  coefficients=list(rng.normal(0, 1, 3) * np.array([1e-5, 1e-7, 1e-9])), tol=1e-12)
+    elif kind == "odd_asphere":      # (no r^1 term: a cone tip has no normal)
+        kw = dict(radius=radius, surface_type="odd_asphere", tol=1e-12,
+                  coefficients=[0.0] + list(rng.normal(0, 1, 3) * np.array([1e-4, 1e-5, 1e-6])))
+    elif kind == "polynomial":
+        C = rng.normal(0, 1e-4, (3, 3))
+        C[0, 0] = 0.0
+        kw = dict(radius=radius, surface_type="polynomial", coefficients=C.tolist(), tol=1e-12)
+    elif kind == "chebyshev":
+        C = rng.normal(0, 3e-4, (3, 3))
+        C[0, 0] = 0.0
+        kw = dict(radius=radius, surface_type="chebyshev", coefficients=C.tolist(), norm_x=10.0, norm_y=11.0, tol=1e-12)
+    elif kind == "zernike":
+        kw = dict(radius=radius, surface_type="zernike", zernike_type=str(rng.choice(["fringe", "standard", "noll"])),
+                  coefficients=list(rng.normal(0, 3e-4, 8)), norm_radius=10.0, tol=1e-12)
+    elif kind == "biconic":
+        kw = dict(surface_type="biconic", radius_x=radius, radius_y=radius * float(rng.uniform(0.7, 1.4)),
+                  conic_x=float(rng.uniform(-0.5, 0.3)), conic_y=float(rng.uniform(-0.5, 0.3)), tol=1e-12)
+    elif kind == "toroidal":
+        kw = dict(surface_type="toroidal", radius_x=radius * 2.0, radius_y=radius, conic=float(rng.uniform(-0.4, 0.2)),
+                  toroidal_coeffs_poly_y=[float(rng.normal(0, 1e-6))], tol=1e-12)
+    else:
+        kw = dict(radius=radius, conic=float(rng.uniform(-0.4, 0.2)), surface_type="forbes_qbfs", norm_radius=10.0, tol=1e-12,
+                  radial_terms={0: float(rng.normal(0, 0.01)), 1: float(rng.normal(0, 0.005)), 2: float(rng.normal(0, 0.002))})
+    return kind, kw
+
+
+def _build(be, seed):
+    from optiland import optic as _optic
+    from optiland import physical_apertures as PA
+
+    rng = np.random.default_rng(seed)
+    lens = _optic.Optic()
+    finite = rng.random() < 0.3
+    lens.surfaces.add(index=0, radius=be.inf, thickness=(float(rng.uniform(80, 200)) if finite else be.inf))
+    n = int(rng.integers(3, 7))
+    stop = int(rng.integers(1, n + 1))
+    kinds, in_glass = [], False
+    for i in range(1, n + 1):
+        kind, kw = _surface(rng, float(rng.choice([-1, 1]) * rng.uniform(30, 120)))
+        kinds.append(kind)
+        in_glass = (not in_glass) if rng.random() < 0.8 else in_glass
+        if in_glass:
+            kw["material"] = str(rng.choice(GLASSES))
+        kw["thickness"] = float(rng.uniform(2.0, 6.0)) if i < n else float(rng.uniform(40, 80))
+        if rng.random() < 0.25:
+            kw["dx"], kw["dy"] = float(rng.normal(0, 0.1)), float(rng.normal(0, 0.1))
+        if rng.random() < 0.25:
+            kw["rx"], kw["ry"] = float(rng.normal(0, 0.01)), float(rng.normal(0, 0.01))
+        if rng.random() < 0.2:
+            kw["aperture"] = PA.RadialAperture(r_max=float(rng.uniform(3.0, 6.0)))
+        lens.surfaces.add(index=i, is_stop=(i == stop), **kw)
+    lens.surfaces.add(index=n + 1)
+    lens.set_aperture(aperture_type="EPD", value=float(rng.uniform(4.0, 8.0)))
+    lens.fields.set_type(field_type="object_height" if finite else "angle")
+    lens.fields.add(y=0.0)
+    lens.fields.add(y=3.0)
+    lens.wavelengths.add(value=0.55, is_primary=True)
+    return lens, kinds
+
+
+REC = ("x", "y", "z", "L", "M", "N", "opd", "intensity")
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_live_systems_trace_like_the_numpy_reference(live, seed):
+    P, eng, be, which = live
+    be.set_backend("numpy")
+    try:
+        ref, kinds = _build(be, 500 + seed)
+        want = []
+        for hy in (0.0, 1.0):
+            ref.trace(0.0, hy, 0.55, 12, "ring")
+            want.append({k: np.array(getattr(ref.surfaces, k)) for k in REC})
+    except Exception as e:  # noqa: BLE001  (a random prescription the reference itself cannot trace)
+        pytest.skip(f"the reference does not trace this random system: {type(e).__name__}: {e}")
+    be.set_backend("torch")
+    be.set_precision("float64")
+    be.grad_mode.disable()
+    if which == "cuda":
+        be.set_device("cuda")
+    P.install(engine=eng)
+    P.stats(reset=True)
+    n0 = len(eng.calls)
+    lens, _ = _build(be, 500 + seed)
+    scale = max(1.0, max(float(np.nanmax(np.abs(np.where(np.isfinite(w["z"]), w["z"], 0)))) for w in want))
+    for hy, w in zip((0.0, 1.0), want):
+        lens.trace(0.0, hy, 0.55, 12, "ring")
+        for k, v in w.items():
+            g = be.to_numpy(getattr(lens.surfaces, k))
+            assert g.shape == v.shape, (kinds, k)
+            assert np.array_equal(np.isnan(g), np.isnan(v)), (kinds, k, "NaN pattern")
+            m = np.isfinite(v)
+            # (Newton-family surfaces: per-ray convergence + one polishing step vs. the reference's global stop at tol)
+            assert not m.any() or np.max(np.abs(g[m] - v[m])) <= 1e-11 * scale + 1e-10, (kinds, k, float(np.max(np.abs(g[m] - v[m]))))
+    fused = [c for c in eng.calls[n0:] if c and c[0] == "pupil"]
+    assert len(fused) == 2 and not P.stats(), (kinds, eng.calls[n0:], P.stats())
+
+
+@pytest.fixture
+def plugin_devmath():
+    """The shared ``plugin`` fixture's shape (tests/test_plugin_reference.py) over the device-math engine."""
+    from oracle.devmath_engine import DeviceMathEngine
+    from oracle.ref_import import import_reference
+
+    import_reference()
+    import optiland.backend as be
+
+    from optiland_b200 import plugin as P
+
+    be.set_backend("torch")
+    be.set_precision("float64")
+    be.grad_mode.disable()
+    eng = DeviceMathEngine()
+    P.install(engine=eng)
+    P.stats(reset=True)
+    yield P, eng, be
+    P.uninstall()
+    be.set_backend("numpy")
+
+
+def _samples():
+    import tests.test_zz_samples_sweep as SW
+
+    return SW._sample_classes()
+
+
+@pytest.mark.parametrize("qualname", _samples())
+def test_sample_systems_through_the_device_math(plugin_devmath, qualname):
+    """All sample systems of the reference (tests/test_zz_samples_sweep.py: every field, iterative / robust ray aimers
+    included) with the kernel's arithmetic in place of the NumPy oracle."""
+    import tests.test_zz_samples_sweep as SW
+
+    SW.test_sample_system_traces_like_the_numpy_reference(plugin_devmath, qualname)
