@@ -593,6 +593,13 @@ OLB_HD void newton_slopes(T x, T y, const PrepSurface<T>& S, const T* pool, T& f
 // iterate sits on the noise floor of f, which for fp32 polynomial sags lies above the
 // floor estimate) keeping the better of the last two iterates -- so fp32 cannot spin
 // to max_iter.
+// A step that fails to halve |f| ends the iteration only NEAR the surface (|f| within this factor of the rounding floor
+// 8 eps (|z| + |sag|): the noise-floor stall).  Far from it the ray is not converging at all -- it misses the surface, or
+// Newton is wandering -- and the reference keeps stepping until max_iter or until an iterate leaves the sag's domain
+// (NaN from then on, newton_raphson.py:137-168); so does this loop, which gives such rays the reference's NaN / finite
+// pattern instead of a "best iterate" that is no intersection.
+template <typename T> OLB_HD constexpr T newton_wander_factor() { return (T)1024; }
+
 // Sag and slopes at the same point (one Newton iteration needs both).  Even / odd aspheres share the conic
 // square root and r^2 between the two (returns with fx, fy set); for the other families only the sag is
 // evaluated here and newton_distance calls newton_slopes once the convergence test has passed.
@@ -638,12 +645,13 @@ OLB_HD T newton_distance(T x, T y, T z, T L, T M, T N, const PrepSurface<T>& S, 
     else sag = newton_sag<T, FEAT>(xi, yi, S, pool, status);
     T f = sag - zi;
     T af = o_abs(f);
-    if (!(af == af)) break;  // NaN stays NaN (the reference would spin to max_iter on it)
+    if (!(af == af)) { t = f; break; }  // sag undefined at this iterate (outside the surface's domain): the reference's
+                                        // t -= f / f' turns NaN there and stays NaN to max_iter -- so does the distance
     T tol = S.tol;
     T floor_ = (T)8 * Eps<T>::v * (o_abs(zi) + o_abs(sag));
     if (floor_ > tol) tol = floor_;
     const bool conv = af < tol;
-    if (!conv && !(af < (T)0.5 * f_prev)) {  // stalled on the noise floor (or diverging)
+    if (!conv && !(af < (T)0.5 * f_prev) && !(af > newton_wander_factor<T>() * floor_)) {  // stalled on the noise floor
       if (!(af < f_prev)) t = t_prev;
       break;
     }
@@ -707,13 +715,14 @@ OLB_HD NewtonHit<T> newton_hit_generic(T x, T y, T z, T L, T M, T N, const PrepS
       f = sag - zi;
       af = o_abs(f);
       if (!(af == af)) {
-        final_pass = true;                       // NaN stays NaN (the reference would spin to max_iter on it)
+        final_pass = true;                       // sag undefined at this iterate: the reference's t -= f / f' turns NaN
+        t = f;                                   // there and stays NaN to max_iter -- so does the distance returned here
       } else {
         T tol = S.tol;
         const T floor_ = (T)8 * Eps<T>::v * (o_abs(zi) + o_abs(sag));
         if (floor_ > tol) tol = floor_;
         conv = af < tol;
-        if (!conv && !(af < (T)0.5 * f_prev)) {  // stalled on the noise floor (or diverging)
+        if (!conv && !(af < (T)0.5 * f_prev) && !(af > newton_wander_factor<T>() * floor_)) {  // stalled on the noise floor
           final_pass = true;
           if (!(af < f_prev)) { t = t_prev; continue; }   // keep the better iterate: slopes there
         }

@@ -686,6 +686,10 @@ def _live_coefs(surfaces, table):
                 for row in c])
         if r is not None:
             r = (r if torch.is_tensor(r) else torch.as_tensor(np.asarray(r, dtype=np.float64))).reshape(-1).to(torch.float64)
+            if spec.kind == T.GEOM_CHEBYSHEV and r.requires_grad:
+                # the reference sums over ``argwhere(coefficients != 0)`` (geometries/chebyshev.py:146, 177): a coefficient
+                # that is exactly 0 is not part of its graph and receives gradient 0 -- reproduced, not fixed
+                r = torch.where(r != 0, r, r.detach())
             K = max(K, r.numel())
             dev = r.device
         rows.append(r)

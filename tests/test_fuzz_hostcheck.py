@@ -423,3 +423,30 @@ def test_random_tables_survive_the_abi_layout(seed):
         np.testing.assert_array_equal(a.t, b.t)
         np.testing.assert_array_equal(a.R, b.R)
         np.testing.assert_array_equal(np.ravel(a.coefficients), np.ravel(b.coefficients))
+
+
+def test_rays_that_miss_newton_surfaces_follow_the_reference_nan_pattern(hc):
+    """Wide bundles (|x|, |y| up to 45 mm, direction spread 0.15 on surfaces of 25-150 mm radius): 15-70 % of the rays
+    miss a surface, leave the domain of its sag, or never converge.  The reference keeps stepping such a ray until
+    ``max_iter`` or until an iterate's sag is undefined (NaN from then on, newton_raphson.py:137-168); the device loop
+    does the same (a non-halving step ends the iteration only on the rounding floor, ``newton_wander_factor``; a NaN
+    residual makes the distance NaN), so the NaN / finite pattern of the records agrees up to the chaotic tail of
+    wandering iterates.  Before round 2's last session the loop returned the best iterate instead: 2.9 % of the x / intensity
+    record entries of this very sample differed in the pattern (finite garbage where the reference has NaN); now 0.17 %
+    (fp32: 0.43 %)."""
+    total = differ = 0
+    for seed in range(0, 60, 2):
+        rng = np.random.default_rng(9000 + seed)
+        table = random_system(rng, int(rng.integers(4, 8)))
+        n = 256
+        x, y = rng.uniform(-45, 45, n), rng.uniform(-45, 45, n)
+        L, M = rng.normal(0, 0.15, n), rng.normal(0, 0.15, n)
+        rays = dict(x=x, y=y, z=np.full(n, -5.0), L=L, M=M, N=np.sqrt(1 - L**2 - M**2), i=np.ones(n),
+                    w=np.full(n, table.wavelengths[0]))
+        _, orec, ost = O.trace(table, rays)
+        _, rec, st = run_hostcheck(hc, table, rays, np.float64)[:3]
+        assert st == ost
+        for k in ("x", "intensity"):
+            total += rec[k].size
+            differ += int((np.isnan(rec[k]) != np.isnan(orec[k])).sum())
+    assert total > 60000 and differ <= 0.004 * total, (differ, total)
