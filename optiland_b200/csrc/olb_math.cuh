@@ -1189,7 +1189,7 @@ OLB_HD bool surface_backward(const PrepSurface<T>& S, const T* pool, T xg0, T yg
       g += asph_p;
       gp += asph_pp;
     } else if (S.kind == OLB_GEOM_ODD_ASPHERE) {
-      // sag = conic + sum C_i r^(i+1): slope factor g += sum (i+1) C_i r^(i-1) (0 at r == 0, as the forward pass),
+      // sag = conic + sum C_i r^(i+1): slope factor g += sum (i+1) C_i r^(i-1),
       // d g / d r2 = sum (i+1)(i-1)/2 C_i r^(i-3)
       const T* cf = pool + S.coef_off;
       const T rr = o_sqrt(r2);
@@ -1201,6 +1201,11 @@ OLB_HD bool surface_backward(const PrepSurface<T>& S, const T* pool, T xg0, T yg
           asph_pp = o_fma((T)0.5 * (T)((j + 1) * (j - 1)) * cf[j], pw * ir * ir, asph_pp);
           pw *= rr;
         }
+      } else if (S.n_coef > 1) {
+        // exactly on the vertex (the chief ray of an on-axis field): the slopes x g, y g vanish whatever g is, but the
+        // Hessian g I + 2 g' x x^T of the sag does not -- its limit is the r^2 term's 2 C_1 (an r^1 term, C_0 != 0, is a
+        // cone tip with no Hessian at all; an r^3 term's g' ~ 1/r multiplies x x^T = 0)
+        asph_p = (T)2 * cf[1];
       }
       g += asph_p;
       gp += asph_pp;

@@ -222,6 +222,47 @@ def test_odd_asphere_adjoint_matches_finite_differences(hc):
             assert gpar[s, slot] == pytest.approx(ref, rel=2e-4, abs=1e-6 * gmax), (s, what, gpar[s, slot], ref)
 
 
+def test_odd_asphere_adjoint_on_the_vertex_ray(hc):
+    """The ray through the vertex of an odd asphere (r == 0 exactly: the chief ray of an on-axis field): the slopes x g,
+    y g vanish whatever the slope factor g is, but the sag's Hessian g I does not -- at r = 0 it is the conic
+    curvature plus the r^2 term's 2 C_1.  The adjoint used the forward pass's convention (polynomial part of g := 0 at
+    r == 0) there and lost that term: found by the live gradient fuzz (an on-axis hexapolar bundle through a tilted odd
+    asphere, 3e-4 relative on the decenter gradients against the reference's autograd and central differences)."""
+    rng = np.random.default_rng(5)
+    specs = [
+        T.SurfaceSpec(kind=T.GEOM_NOOP),
+        T.SurfaceSpec(kind=T.GEOM_ODD_ASPHERE, radius=45.0, conic=-0.3, t=[0.0, 0.0, 8.0], n1=[1.0], n2=[1.52],
+                      coefficients=[0.0, 2e-3, -3e-5, 4e-6], tol=1e-14, max_iter=60),
+        T.SurfaceSpec(kind=T.GEOM_PLANE, t=[0.0, 0.0, 30.0], n1=[1.52], n2=[1.52]),
+    ]
+    table = T.SurfaceTable(specs, [0.55])
+    n = 4
+    L, M = np.array([0.0, 0.05, -0.03, 0.02]), np.array([0.0, -0.02, 0.04, 0.0])
+    N = np.sqrt(1 - L**2 - M**2)
+    # every ray aims at the vertex (0, 0, 8) from z = 0: the intersection is at r == 0 exactly for ray 0, to rounding else
+    rays = dict(x=-8.0 * L / N, y=-8.0 * M / N, z=np.zeros(n), L=L, M=M, N=N, i=np.ones(n), w=np.full(n, 0.55))
+    rays["x"][0] = rays["y"][0] = 0.0
+    weights = {k: rng.normal(size=(table.num_surfaces, n)) for k in REC}
+    _, rec, _ = O.trace(table, rays)
+    assert rec["x"][1, 0] == 0.0 and rec["y"][1, 0] == 0.0
+    gin, gpar = run_backward(hc, table, rays, rec, weights)
+    h = 1e-6
+    for k in ("x", "y", "L", "M"):
+        for r in range(n):
+            def shifted(sign):
+                rr = {q: v.copy() for q, v in rays.items()}
+                rr[k][r] += sign * h
+                if k in ("L", "M"):
+                    rr["N"][r] = np.sqrt(1 - rr["L"][r] ** 2 - rr["M"][r] ** 2)
+                return rr
+            ref = (loss_fn(table, shifted(+1), weights) - loss_fn(table, shifted(-1), weights)) / (2 * h)
+            got = gin[k][r] - (gin["N"][r] * rays[k][r] / rays["N"][r] if k in ("L", "M") else 0.0)
+            assert got == pytest.approx(ref, rel=2e-5, abs=1e-7), (k, r, got, ref)
+    for what, slot, hh in (("tx", GP["TX"], 1e-6), ("tz", GP["TZ"], 1e-6), ("coef1", GP["COEF"] + 1, 1e-7)):
+        ref = fd(table, rays, weights, 1, what, hh)
+        assert gpar[1, slot] == pytest.approx(ref, rel=2e-4, abs=1e-6 * np.abs(gpar).max()), (what, gpar[1, slot], ref)
+
+
 @pytest.mark.parametrize("name", ["zernike_fringe", "zernike_noll", "misc_apertures_coatings"])
 def test_polynomial_family_adjoint_matches_finite_differences(hc, name):
     """The adjoint through Zernike / polynomial surfaces (olb_trace_bwd_tables_*: implicit-function theorem with the true
