@@ -7,14 +7,9 @@ path but the CUDA launch wrapper.  Epilogues (moments, wavefront, PSF) and the a
 ``OracleEngine`` (their device arithmetic has host instantiations of its own there)."""
 import numpy as np
 
-from oracle.oracle_engine import OracleEngine
+from oracle.oracle_engine import OracleEngine, raise_status
 
 _KEYS = ("x", "y", "z", "L", "M", "N", "i", "w", "opd")
-
-
-def _zernike_error(status: int):
-    if status:
-        raise ValueError("Zernike coordinates must be normalized to [-1, 1].")
 
 
 class DeviceMathEngine(OracleEngine):
@@ -31,7 +26,7 @@ class DeviceMathEngine(OracleEngine):
         polarized = type(rays).__name__ == "PolarizedRays"
         pmat = rays.p.detach().numpy().astype(np.complex128) if polarized else None
         out, rec, status = run_hostcheck(load(), table, inp, np.float64, first, last, pmat=pmat)
-        _zernike_error(status)
+        raise_status(status)
         if polarized:
             rays.p = torch.from_numpy(out["p"])
         dt = rays.x.dtype
@@ -57,7 +52,7 @@ class DeviceMathEngine(OracleEngine):
         inp = dict(x=x, y=y, z=z, L=L, M=M, N=N, i=i0, w=w)
         pmat = None if polarization is False else np.tile(np.eye(3, dtype=np.complex128), (px.size, 1, 1))
         out, rec, status = run_hostcheck(load(), table, inp, np.float64, pmat=pmat)
-        _zernike_error(status)
+        raise_status(status)
         res = {k: torch.from_numpy(v).to(Px.dtype) for k, v in rec.items()}
         if polarization is False:
             return res

@@ -4,6 +4,19 @@ adjoint (backward).  Used by tests/test_plugin_reference.py and by the reference
 import numpy as np
 
 
+def raise_status(status: int) -> None:
+    """The reference's ValueErrors for out-of-range freeform coordinates -- what optiland_b200.trace._raise_status does with
+    the kernels' status word, from EVERY entry point (plain, pupil launch, moments, wavefront)."""
+    from optiland_b200 import table as T
+
+    if status & T.ST_ZERNIKE_RANGE:
+        raise ValueError("Zernike coordinates must be normalized to [-1, 1]. Consider updating the normalization "
+                         "radius to 1.1x the surface aperture.")
+    if status & T.ST_CHEBYSHEV_RANGE:
+        raise ValueError("Chebyshev input coordinates must be normalized to [-1, 1]. Consider updating the "
+                         "normalization factors.")
+
+
 class OracleEngine:
     """TEST-ONLY stand-in for optiland_b200.plugin.CudaEngine."""
 
@@ -28,8 +41,7 @@ class OracleEngine:
         out, rec, status = O.trace(table, inp, first, last, polarized=polarized)
         if polarized:
             rays.p = torch.from_numpy(out["p"])
-        if status:
-            raise ValueError("Zernike coordinates must be normalized to [-1, 1].")
+        raise_status(status)
         dt = rays.x.dtype
         for k in ("x", "y", "z", "L", "M", "N", "i", "opd"):
             setattr(rays, k, torch.from_numpy(out[k]).to(dt))
@@ -58,9 +70,11 @@ class OracleEngine:
         inp = dict(x=x, y=y, z=z, L=L, M=M, N=N, i=i0, w=w)
         if polarization is False:
             _, rec, status = O.trace(table, inp)
+            raise_status(status)
             return {k: torch.from_numpy(v).to(Px.dtype) for k, v in rec.items()}
         inp["p"] = np.tile(np.eye(3, dtype=np.complex128), (px.size, 1, 1))
         out, rec, status = O.trace(table, inp, polarized=True)
+        raise_status(status)
         res = {k: torch.from_numpy(v).to(Px.dtype) for k, v in rec.items()}
         cdt = torch.complex128 if Px.dtype == torch.float64 else torch.complex64
         res["p"] = torch.from_numpy(out["p"]).to(cdt)
@@ -80,7 +94,8 @@ class OracleEngine:
         inp = dict(x=x, y=y, z=z, L=L, M=M, N=N, i=np.full_like(px, affine.get("intensity", 1.0)),
                    w=np.full_like(px, table.wavelengths[0]))
         last = table.num_surfaces if last is None else last
-        fin, rec, _ = O.trace(table, inp, 0, last)
+        fin, rec, status = O.trace(table, inp, 0, last)
+        raise_status(status)
         gx, gy, ii, oo = rec["x"][-1], rec["y"][-1], rec["intensity"][-1], rec["opd"][-1]
         if not global_xy:
             s = table.surfaces[last - 1]
@@ -108,7 +123,8 @@ class OracleEngine:
                    w=np.full_like(px, table.wavelengths[0]))
         if polarized:
             inp["p"] = np.tile(np.eye(3, dtype=np.complex128), (px.size, 1, 1))
-        fin, _, _ = O.trace(table, inp, polarized=polarized)
+        fin, _, status = O.trace(table, inp, polarized=polarized)
+        raise_status(status)
         out = O.wavefront_reference_sphere(fin, px, py, ref)
         res = {k: torch.from_numpy(np.asarray(v)).to(Px.dtype) for k, v in out.items()}
         if polarized:
