@@ -3,8 +3,9 @@ forward trace runs the DEVICE ARITHMETIC itself (csrc/olb_math.cuh + olb_prep.h 
 tests/hostcheck) on the packed table the product would upload (``_lib.HostTable``), where ``OracleEngine`` evaluates
 the NumPy restatement of the reference.  With it a CPU test chains: live reference objects -> ``plugin`` / ``pack`` ->
 prepared table -> the kernel's per-ray code, and compares with the unmodified reference -- everything of the product
-path but the CUDA launch wrapper.  Epilogues (moments, wavefront, PSF) and the adjoint are inherited from
-``OracleEngine`` (their device arithmetic has host instantiations of its own there)."""
+path but the CUDA launch wrapper.  The wavefront epilogue (``wavefront_point``) and the polarized intensity epilogue
+(``polarized_intensity``) run through their host instantiations as well; moments, PSF and the adjoint are inherited from
+``OracleEngine`` (PSF gridding and the adjoint are host instantiations of device code there too)."""
 import numpy as np
 
 from oracle.oracle_engine import OracleEngine, raise_status
@@ -60,5 +61,32 @@ class DeviceMathEngine(OracleEngine):
         if polarization == "matrix":
             res["i_pol"] = res["intensity"][-1]
         else:
-            res["i_pol"] = torch.from_numpy(O.polarized_intensity(out["p"], L, M, N, i0, polarization)).to(Px.dtype)
+            from oracle.hostcheck_api import run_pol_intensity
+            from optiland_b200 import table as T
+
+            ipol, st = run_pol_intensity(load(), out["p"], (L, M, N), i0, polarization)
+            if st & T.ST_K_PARALLEL_X:
+                raise ValueError("k-vector parallel to x-axis is not currently supported.")
+            res["i_pol"] = torch.from_numpy(ipol).to(Px.dtype)
+        return res
+
+    def trace_wavefront(self, table, Px, Py, affine, ref, polarized=False):
+        import torch
+
+        from oracle.hostcheck_api import load, run_hostcheck, run_wavefront
+        from optiland_b200.launch import launch_from_affine
+
+        self.calls.append(("wavefront", table.num_surfaces, int(Px.numel())))
+        px, py = Px.detach().double().numpy(), Py.detach().double().numpy()
+        x, y, z, L, M, N = launch_from_affine(px, py, affine)
+        inp = dict(x=x, y=y, z=z, L=L, M=M, N=N, i=np.full_like(px, affine.get("intensity", 1.0)),
+                   w=np.full_like(px, table.wavelengths[0]))
+        pmat = np.tile(np.eye(3, dtype=np.complex128), (px.size, 1, 1)) if polarized else None
+        fin, _, status = run_hostcheck(load(), table, inp, np.float64, pmat=pmat)
+        raise_status(status)
+        out = run_wavefront(load(), fin, px, py, ref)
+        out["intensity"] = fin["i"]
+        res = {k: torch.from_numpy(np.asarray(v)).to(Px.dtype) for k, v in out.items()}
+        if polarized:
+            res["p"] = torch.from_numpy(fin["p"]).to(torch.complex128 if Px.dtype == torch.float64 else torch.complex64)
         return res
