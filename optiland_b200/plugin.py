@@ -936,8 +936,8 @@ def install(engine=None, alias: str | None = None) -> None:
 
         def trace_optic_generic(self, tracer, Hx, Hy, Px, Py, wavelength):
             """``RealRayTracer.trace_generic`` (raytrace/real_ray_tracer.py:120-154) for per-ray (Hx, Hy, Px, Py[, lambda])
-            arrays with the launch state generated on the device.  Needs the paraxial aimer (an apodized pupil is
-            served unless vignetting factors are set as well);
+            arrays with the launch state generated on the device.  Needs the paraxial aimer (apodized pupils and
+            vignetting factors are served, also together);
             ``optic.polarization`` set -> ``PolarizedRays`` (config 5's call shape).  Returns the traced rays or None."""
             import numpy as _np
 
@@ -955,10 +955,6 @@ def install(engine=None, alias: str | None = None) -> None:
                                or _np.any(_np.asarray(be.to_numpy(optic.fields.vy)) != 0))
             except Exception:
                 return _fused_decline("vignetting factors are not plain numbers")
-            if optic.apodization and has_vig:
-                # (the factor is evaluated on the pupil point scaled ONCE by the vignetting factor,
-                # real_ray_tracer.py:132-141 -> ray_generator.py:83-85, while the kernel applies the factor itself)
-                return _fused_decline("apodization together with vignetting factors")
             tracer._validate_normalized_coordinates(Hx, Hy, "field")
             tracer._validate_normalized_coordinates(Px, Py, "pupil")
             vig = None
@@ -998,7 +994,16 @@ def install(engine=None, alias: str | None = None) -> None:
                 return _fused_decline("field / pupil arrays not resident on a CUDA device (or of different shapes)")
             if any(t.dtype != Px.dtype for t in (Hx, Hy)):
                 return _fused_decline("field and pupil arrays of different precision")
-            apod = _apodization_factor(be, engine, optic, Px, Py)
+            if optic.apodization and has_vig:
+                # the factor is evaluated on the pupil point scaled ONCE by the vignetting factor (real_ray_tracer.py:132-141
+                # -> ray_generator.py:83-85) while the launch geometry sees it scaled twice, in the kernel: three eager
+                # element-wise ops for the once-scaled point
+                if vig is None:
+                    return _fused_decline("apodization together with vignetting factors of more than 16 fields")
+                vxf, vyf = optic.fields.get_vig_factor(Hx, Hy)
+                apod = _apodization_factor(be, engine, optic, Px * (1 - vxf), Py * (1 - vyf))
+            else:
+                apod = _apodization_factor(be, engine, optic, Px, Py)
             if apod is False:
                 return _fused_decline("apodization factor not resident on the device")
             w = None
