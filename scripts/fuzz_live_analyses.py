@@ -17,7 +17,7 @@ import warnings
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 warnings.filterwarnings("ignore")
 import numpy as np
-import tests.test_zz_live_fuzz as F
+import tests.test_zzz_live_fuzz as F
 from oracle.ref_import import import_reference
 import_reference()
 import optiland.backend as be

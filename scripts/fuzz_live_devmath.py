@@ -1,5 +1,5 @@
 """Fuzz campaign with LIVE reference objects through the plugin over the device-math engine (oracle/devmath_engine.py:
-the kernel's arithmetic compiled for the host) -- wider than tests/test_zz_live_fuzz.py: every geometry family, planes,
+the kernel's arithmetic compiled for the host) -- wider than tests/test_zzz_live_fuzz.py: every geometry family, planes,
 hyperbolas, mirrors, catalogue glasses (never the same glass on both sides of a curved surface: there the REFERENCE's
 polarization basis is rounding noise), decenters / tilts, radial / rectangular / elliptical / boolean
 apertures, four system-aperture types, wide fields with vignetting factors, three wavelengths, polarized and unpolarized
@@ -17,7 +17,7 @@ import warnings
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 warnings.filterwarnings("ignore")
 import numpy as np
-import tests.test_zz_live_fuzz as F
+import tests.test_zzz_live_fuzz as F
 from oracle.ref_import import import_reference
 import_reference()
 import optiland.backend as be

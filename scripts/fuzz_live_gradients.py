@@ -1,4 +1,4 @@
-"""Live fuzz, gradients: the random systems of tests/test_zz_live_fuzz.py with every float surface parameter a leaf that
+"""Live fuzz, gradients: the random systems of tests/test_zzz_live_fuzz.py with every float surface parameter a leaf that
 requires grad; one differentiable step (two fields, spot + OPD loss); the plugin's gradients (forward kernel + hand-derived
 adjoint; test-only engine = oracle forward + the host instantiation of the device adjoint) against the STOCK reference's eager
 autograd.  Systems the stock reference cannot differentiate (Zernike: aten::floor_divide) are reported and skipped; parameters
@@ -9,7 +9,7 @@ import os, sys, traceback, warnings
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); warnings.filterwarnings("ignore")
 import numpy as np
-import tests.test_zz_live_fuzz as F
+import tests.test_zzz_live_fuzz as F
 from oracle.ref_import import import_reference
 import_reference()
 import torch

@@ -344,34 +344,3 @@ def test_catalogue_glass_indices_are_memoised_and_other_materials_are_not():
     finally:
         be.grad_mode.disable()
         be.set_backend("numpy")
-
-
-def test_trace_generic_with_apodization_and_vignetting_factors(plugin):
-    """``trace_generic`` on an apodized optic whose fields carry vignetting factors: the reference evaluates the apodization
-    on the pupil point scaled ONCE by (1 - v) (real_ray_tracer.py:132-141 -> ray_generator.py:83-85) while its aimer scales
-    the launch geometry a second time; the fused launch does the latter in the kernel and the former as three eager ops."""
-    from optiland.apodization import GaussianApodization
-    from optiland.samples.objectives import CookeTriplet
-
-    P, eng, be = plugin
-
-    def make():
-        lens = CookeTriplet()
-        for f, (vx, vy) in zip(lens.fields.fields, ((0.0, 0.0), (0.1, 0.2), (0.15, 0.3))):
-            f.vx, f.vy = vx, vy
-        lens.set_apodization(GaussianApodization(sigma=0.8))
-        return lens
-
-    rng = np.random.default_rng(3)
-    n = 64
-    arrs = [rng.uniform(-0.3, 0.3, n), rng.uniform(-1, 1, n), rng.uniform(-0.7, 0.7, n), rng.uniform(-0.7, 0.7, n)]
-    want, fin = _numpy_reference(make, lambda lens: lens.trace_generic(*[be.array(a) for a in arrs], 0.55))
-    lens = make()
-    P.stats(reset=True)
-    n0 = len(eng.calls)
-    rays = lens.trace_generic(*[be.array(a) for a in arrs], 0.55)
-    assert [c[0] for c in eng.calls[n0:]] == ["pupil"] and not P.stats(), (eng.calls[n0:], P.stats())
-    for k, v in want.items():
-        np.testing.assert_allclose(be.to_numpy(getattr(lens.surfaces, k)), v, rtol=0, atol=1e-10, err_msg=k)
-    np.testing.assert_allclose(be.to_numpy(rays.i), fin["i"], rtol=0, atol=1e-13)
-    assert float(np.ptp(fin["i"])) > 0.05          # the apodization really varies over the sample
