@@ -21,7 +21,7 @@ def test_wide_bundles_kernel_matches_the_host_instantiation(seed):
     instantiation of the same arithmetic -- NaN pattern identical but for the chaotic tail of wandering Newton iterates
     (nvcc and g++ contract FMAs differently; <= 2 % of a record's entries), values to 1e-9 on all but those rays -- and
     against the oracle's NaN pattern (host instantiation vs oracle: 1.6 % on the worst record of this sample, 0.17 % overall;
-    the code before this session: 2.9 % overall, up to 30 % on single systems)."""
+    the code before this session: 2.9 % overall)."""
     from oracle import trace_oracle as O
     from oracle.hostcheck_api import load, run_hostcheck
     from optiland_b200.trace import RealRays, SurfaceGroup
