@@ -593,12 +593,16 @@ OLB_HD void newton_slopes(T x, T y, const PrepSurface<T>& S, const T* pool, T& f
 // iterate sits on the noise floor of f, which for fp32 polynomial sags lies above the
 // floor estimate) keeping the better of the last two iterates -- so fp32 cannot spin
 // to max_iter.
-// A step that fails to halve |f| ends the iteration only NEAR the surface (|f| within this factor of the rounding floor
-// 8 eps (|z| + |sag|): the noise-floor stall).  Far from it the ray is not converging at all -- it misses the surface, or
-// Newton is wandering -- and the reference keeps stepping until max_iter or until an iterate leaves the sag's domain
-// (NaN from then on, newton_raphson.py:137-168); so does this loop, which gives such rays the reference's NaN / finite
-// pattern instead of a "best iterate" that is no intersection.
-template <typename T> OLB_HD constexpr T newton_wander_factor() { return (T)1024; }
+// A step that fails to halve |f| ends the iteration only NEAR the surface: |f| within 1024x the rounding noise of
+// f = sag - (z + t N) itself, 8 eps (|z| + |t| + |sag|) -- the OPERANDS' magnitudes, not the result's: a ray that lands
+// next to the vertex has z + t N ~ 0 with the absolute noise of |z| and |t| (fp32: ~1e-6 mm), and must still count as
+// stalled on the noise floor instead of spinning to max_iter.  Far from the surface the ray is not converging at all -- it
+// misses the surface, or Newton is wandering -- and the reference keeps stepping until max_iter or until an iterate leaves
+// the sag's domain (NaN from then on, newton_raphson.py:137-168); so does this loop, which gives such rays the reference's
+// NaN / finite pattern instead of a "best iterate" that is no intersection.
+template <typename T> OLB_HD T newton_wander_bound(T z, T t, T sag) {
+  return (T)1024 * (T)8 * Eps<T>::v * (o_abs(z) + o_abs(t) + o_abs(sag));
+}
 
 // Sag and slopes at the same point (one Newton iteration needs both).  Even / odd aspheres share the conic
 // square root and r^2 between the two (returns with fx, fy set); for the other families only the sag is
@@ -651,7 +655,7 @@ OLB_HD T newton_distance(T x, T y, T z, T L, T M, T N, const PrepSurface<T>& S, 
     T floor_ = (T)8 * Eps<T>::v * (o_abs(zi) + o_abs(sag));
     if (floor_ > tol) tol = floor_;
     const bool conv = af < tol;
-    if (!conv && !(af < (T)0.5 * f_prev) && !(af > newton_wander_factor<T>() * floor_)) {  // stalled on the noise floor
+    if (!conv && !(af < (T)0.5 * f_prev) && !(af > newton_wander_bound<T>(z, t, sag))) {  // stalled on the noise floor
       if (!(af < f_prev)) t = t_prev;
       break;
     }
@@ -722,7 +726,7 @@ OLB_HD NewtonHit<T> newton_hit_generic(T x, T y, T z, T L, T M, T N, const PrepS
         const T floor_ = (T)8 * Eps<T>::v * (o_abs(zi) + o_abs(sag));
         if (floor_ > tol) tol = floor_;
         conv = af < tol;
-        if (!conv && !(af < (T)0.5 * f_prev) && !(af > newton_wander_factor<T>() * floor_)) {  // stalled on the noise floor
+        if (!conv && !(af < (T)0.5 * f_prev) && !(af > newton_wander_bound<T>(z, t, sag))) {  // stalled on the noise floor
           final_pass = true;
           if (!(af < f_prev)) { t = t_prev; continue; }   // keep the better iterate: slopes there
         }

@@ -429,7 +429,7 @@ def test_rays_that_miss_newton_surfaces_follow_the_reference_nan_pattern(hc):
     """Wide bundles (|x|, |y| up to 45 mm, direction spread 0.15 on surfaces of 25-150 mm radius): 15-70 % of the rays
     miss a surface, leave the domain of its sag, or never converge.  The reference keeps stepping such a ray until
     ``max_iter`` or until an iterate's sag is undefined (NaN from then on, newton_raphson.py:137-168); the device loop
-    does the same (a non-halving step ends the iteration only on the rounding floor, ``newton_wander_factor``; a NaN
+    does the same (a non-halving step ends the iteration only on the rounding floor, ``newton_wander_bound``; a NaN
     residual makes the distance NaN), so the NaN / finite pattern of the records agrees up to the chaotic tail of
     wandering iterates.  Before round 2's last session the loop returned the best iterate instead: 2.9 % of the x / intensity
     record entries of this very sample differed in the pattern (finite garbage where the reference has NaN); now 0.17 %
@@ -450,3 +450,33 @@ def test_rays_that_miss_newton_surfaces_follow_the_reference_nan_pattern(hc):
             total += rec[k].size
             differ += int((np.isnan(rec[k]) != np.isnan(orec[k])).sum())
     assert total > 60000 and differ <= 0.004 * total, (differ, total)
+
+
+def test_near_vertex_rays_do_not_spin_to_max_iter_in_fp32(hc):
+    """fp32 rays that land next to the vertex of an asphere cannot push |f| = |sag - (z + t N)| below ~ulp(t): they stall on
+    the rounding noise of the OPERANDS while |z + t N| + |sag| ~ 0.  The stall must end the Newton loop there
+    (``newton_wander_bound`` scales with |z| + |t| + |sag|); a bound built from the result's magnitude let them iterate to
+    ``max_iter`` = 100 -- 14x the time of this very trace -- for one intermediate state of the last session.  Timing ratio of
+    two traces in the same process (the slow state measured 16)."""
+    import time
+
+    specs = [T.SurfaceSpec(kind=T.GEOM_NOOP),
+             T.SurfaceSpec(kind=T.GEOM_EVEN_ASPHERE, radius=50.0, conic=-0.5, t=[0, 0, 5.0], n1=[1.0], n2=[1.5],
+                           coefficients=[1e-5, 1e-7], tol=1e-10, max_iter=100),
+             T.SurfaceSpec(kind=T.GEOM_PLANE, t=[0, 0, 20.0], n1=[1.5], n2=[1.5])]
+    table = T.SurfaceTable(specs, [0.55])
+    rng = np.random.default_rng(0)
+    n = 200000
+    took = {}
+    for tag, rmax in (("vertex", 0.05), ("wide", 5.0)):
+        x, y = rng.uniform(-rmax, rmax, n), rng.uniform(-rmax, rmax, n)
+        L, M = rng.normal(0, 1e-3, n), rng.normal(0, 1e-3, n)
+        rays = dict(x=x, y=y, z=np.zeros(n), L=L, M=M, N=np.sqrt(1 - L**2 - M**2), i=np.ones(n), w=np.full(n, 0.55))
+        best = np.inf
+        for _ in range(3):
+            t0 = time.perf_counter()
+            _, rec, _ = run_hostcheck(hc, table, rays, np.float32)[:3]
+            best = min(best, time.perf_counter() - t0)
+        took[tag] = best
+        assert np.isfinite(rec["x"]).all()
+    assert took["vertex"] <= 4.0 * took["wide"], took
