@@ -91,3 +91,38 @@ def test_odd_asphere_vertex_ray_adjoint_kernel(dtype_name):
     for k in ("x", "y", "L", "M"):
         g = getattr(rr, k).grad.double().cpu().numpy()
         assert np.max(np.abs(g - gin[k])) <= tol * max(1.0, np.abs(gin[k]).max()), (k, g, gin[k])
+
+
+def test_near_vertex_fp32_bundle_is_not_slower_than_a_wide_one():
+    """The performance trap of the wandering rule (tests/test_fuzz_hostcheck.py::
+    test_near_vertex_rays_do_not_spin_to_max_iter_in_fp32), on the device: fp32 rays that land within 0.05 mm of an even
+    asphere's vertex stall at |f| ~ ulp(t); with a stall bound built from |z + t N| + |sag| they iterated to max_iter = 100
+    (14x on the host instantiation).  CUDA-event time of the same kernel on a near-vertex and on a wide bundle."""
+    from optiland_b200 import table as T
+    from optiland_b200.trace import RealRays, SurfaceGroup
+
+    specs = [T.SurfaceSpec(kind=T.GEOM_NOOP),
+             T.SurfaceSpec(kind=T.GEOM_EVEN_ASPHERE, radius=50.0, conic=-0.5, t=[0, 0, 5.0], n1=[1.0], n2=[1.5],
+                           coefficients=[1e-5, 1e-7], tol=1e-10, max_iter=100),
+             T.SurfaceSpec(kind=T.GEOM_PLANE, t=[0, 0, 20.0], n1=[1.5], n2=[1.5])]
+    table = T.SurfaceTable(specs, [0.55])
+    rng = np.random.default_rng(0)
+    n = 2_000_000
+    ms = {}
+    for tag, rmax in (("vertex", 0.05), ("wide", 5.0)):
+        x, y = rng.uniform(-rmax, rmax, n), rng.uniform(-rmax, rmax, n)
+        L, M = rng.normal(0, 1e-3, n), rng.normal(0, 1e-3, n)
+        sg = SurfaceGroup(table)
+        rays = [RealRays(x, y, np.zeros(n), L, M, np.sqrt(1 - L**2 - M**2), np.ones(n), np.full(n, 0.55), dtype=torch.float32)
+                for _ in range(4)]
+        sg.trace(rays[0])                                  # warm-up (table upload, first launch)
+        torch.cuda.synchronize()
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        for r in rays[1:]:
+            sg.trace(r)
+        stop.record()
+        torch.cuda.synchronize()
+        ms[tag] = start.elapsed_time(stop) / 3
+        assert bool(torch.isfinite(sg.x).all())
+    assert ms["vertex"] <= 3.0 * ms["wide"], ms
