@@ -26,8 +26,12 @@ from . import table as T
 class LazySpotData:
     """Drop-in for ``SpotData`` (core.py:35-47): same three attributes, materialised on first access."""
 
-    def __init__(self, engine, be, table, Px, Py, affine, coordinates: str, optic=None):
+    def __init__(self, engine, be, table, Px, Py, affine, coordinates: str, optic=None, apod=None):
         import weakref
+
+        # per-ray launch intensity of an apodized pupil (strictly positive, checked by _fused_inputs): the mask i > 0 and
+        # with it every moment is the unit-intensity launch's; the materialised records / intensities are scaled by it
+        self._apod = apod
 
         self._engine, self._be = engine, be
         self._optic = weakref.ref(optic) if optic is not None else (lambda: None)
@@ -68,6 +72,8 @@ class LazySpotData:
     def _materialize(self):
         if self._xyz is None:
             rec = self._engine.trace_pupil(self._table, self._Px, self._Py, self._affine)
+            if self._apod is not None:
+                rec = dict(rec, intensity=rec["intensity"] * self._apod)
             optic = self._optic()
             if optic is not None and len(optic.surfaces.surfaces) == self._table.num_surfaces:
                 # the reference's _generate_field_data leaves this trace's records on the optic's surfaces
@@ -102,7 +108,8 @@ def _scalar(be, v) -> float:
 
 
 def _fused_inputs(P, backend, be, optic, Hx, Hy, wavelength, num_rays, distribution):
-    """(table, Px, Py, affine) of a single-field, single-wavelength fused launch, or None (with the reason counted)."""
+    """((table, Px, Py, affine), apodization factor or None) of a single-field, single-wavelength fused launch, or None
+    (with the reason counted)."""
     from .launch import pupil_affine
     from .pack import pack_surface_group
 
@@ -117,8 +124,8 @@ def _fused_inputs(P, backend, be, optic, Hx, Hy, wavelength, num_rays, distribut
         hx, hy = _scalar(be, Hx), _scalar(be, Hy)
     except Exception:
         return P._fused_decline("spot moments: field coordinates are not plain numbers")
-    if optic.apodization or optic.polarization != "ignore":
-        return P._fused_decline("spot moments: apodization / polarization")
+    if optic.polarization != "ignore":
+        return P._fused_decline("spot moments: polarization")
     if getattr(optic.ray_tracer, "ray_aiming_config", {}).get("mode", "paraxial") != "paraxial":
         return P._fused_decline("spot moments: non-paraxial ray aiming")
     if isinstance(distribution, str):
@@ -126,6 +133,11 @@ def _fused_inputs(P, backend, be, optic, Hx, Hy, wavelength, num_rays, distribut
     Px, Py = distribution.x, distribution.y
     if not (engine.accepts_tensor(Px) and engine.accepts_tensor(Py)):
         return P._fused_decline("spot moments: pupil samples not resident on a CUDA device")
+    # An apodized pupil (ray_generator.py:83-87, evaluated on the UNSCALED pupil point as in Optic.trace) only scales the
+    # intensity: the statistics mask i > 0, so with a strictly positive factor they are the unit-intensity launch's.
+    apod = P._apodization_factor(be, engine, optic, Px, Py)
+    if apod is False or (apod is not None and not bool((apod > 0).all())):
+        return P._fused_decline("spot moments: apodization factor not positive everywhere / not on the device")
     try:
         table = pack_surface_group(optic.surfaces, [float(wavelength)])
         sc = P._launch_scalars_cached(be, optic, table, hx, hy)
@@ -134,7 +146,7 @@ def _fused_inputs(P, backend, be, optic, Hx, Hy, wavelength, num_rays, distribut
         return P._fused_decline(f"spot moments unsupported: {e}")
     if any(s.coating == T.COAT_FRESNEL for s in table.surfaces) or table.surfaces[0].kind != T.GEOM_NOOP:
         return None
-    return table, Px, Py, pupil_affine(sc)
+    return (table, Px, Py, pupil_affine(sc)), apod
 
 
 def rms_spot_size(P, backend, be, optic, surface_number, Hx, Hy, num_rays, wavelength, distribution):
@@ -161,7 +173,7 @@ def rms_spot_size(P, backend, be, optic, surface_number, Hx, Hy, num_rays, wavel
         inp = _fused_inputs(P, backend, be, optic, Hx, Hy, wl, num_rays, distribution)
         if inp is None:
             return None
-        jobs.append(inp)
+        jobs.append(inp[0])          # (every ray counts here, no intensity mask: the apodization factor does not enter)
     kw = dict(last=last, global_xy=True, every_ray=True)
     m = engine.spot_moments(*jobs[ref], center=(0.0, 0.0), **kw)
     if not np.isfinite(m[1]) or not np.isfinite(m[2]) or m[0] == 0:
@@ -201,7 +213,7 @@ def install(P, registry, be):
         if hasattr(backend, "trace_optic") and P._state.get("fuse_spot", True):
             inp = _fused_inputs(P, backend, be, self.optic, field[0], field[1], wavelength, num_rays, distribution)
             if inp is not None:
-                return LazySpotData(P._state["engine"], be, *inp, coordinates, optic=self.optic)
+                return LazySpotData(P._state["engine"], be, *inp[0], coordinates, optic=self.optic, apod=inp[1])
         return orig_field_data(self, field, wavelength, num_rays, distribution, coordinates)
 
     def _all_lazy(self):
